@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI declared in include/cryovit_b200.h.
+
+The library is built in-tree by ``cryovit_b200.build`` (nvcc, sm_100a). There is no fallback: if the shared
+object is missing or a call fails, a :class:`CryovitB200Error` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcryovit_b200.so"
+
+
+class CryovitB200Error(RuntimeError):
+    """A call across the C ABI returned a non-zero code, or the CUDA library is unavailable."""
+
+
+P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
+
+# name -> argtypes; every function returns int except the two diagnostics. Mirrors include/cryovit_b200.h.
+SIGNATURES: dict[str, list] = {
+    "cvit_preproc_patchify": [P, I32, P, I64, I64, I64, I64, P],
+    "cvit_patchify_f32_3ch": [P, P, I64, I64, I64, I64, P],
+    "cvit_patch_embed_gemm": [P, I64, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_assemble_special_tokens": [P, P, I64, I64, I64, I64, P],
+    "cvit_layernorm_f32_bf16": [P, I64, P, P, P, I64, I64, I64, F32, P],
+    "cvit_layernorm_f32_f32": [P, I64, P, P, P, I64, I64, I64, F32, P],
+    "cvit_linear_bias_bf16": [P, I64, P, P, P, I64, I64, I64, I64, I32, P],
+    "cvit_linear_swiglu_bf16": [P, I64, P, P, P, I64, I64, I64, I64, P],
+    "cvit_linear_scale_residual_f32": [P, I64, P, P, P, P, I64, I64, I64, I64, P],
+    "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],
+    "cvit_final_norm_writeout_f16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, F32, P],
+    "cvit_features_to_ndhwc_bf16": [P, P, I64, I64, P],
+    "cvit_groupnorm_ndhwc_bf16": [P, P, P, P, P, I64, I64, I64, F32, P],
+    "cvit_conv3d_dilated_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_convT_1x2x2_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, P],
+    "cvit_head_tail_fused": [P, P, P, P, P, P, P, P, I64, I64, I64, P],
+}
+
+_lib: ctypes.CDLL | None = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and bind every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise CryovitB200Error(
+            f"{LIB_PATH} not found: build it with `python -m cryovit_b200.build` (needs nvcc); "
+            "there is no CPU fallback for the CryoVIT hot path"
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    lib.cvit_last_error.restype = c_char_p
+    lib.cvit_last_error.argtypes = []
+    lib.cvit_abi_version.restype = c_int
+    lib.cvit_abi_version.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.cvit_last_error()
+        raise CryovitB200Error(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")

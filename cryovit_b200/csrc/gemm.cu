@@ -1,0 +1,217 @@
+// C-ABI launchers for the tcgen05 GEMM family (ViT linears, patch embed, head 1x1x1 / 3x3x3 /
+// transposed convolutions). See include/cryovit_b200.h for the contracts.
+#include <string.h>
+
+#include "gemm_tcgen05.cuh"
+#include "tmap.h"
+
+namespace cvit {
+
+template <int BN, int EPI, int AMODE, int KSPAN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int num_tiles,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, KSPAN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, KSPAN>;
+  static bool configured = false;  // per instantiation; attribute is per function, setting twice is harmless
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  int grid = num_sms();
+  if (grid > num_tiles) grid = num_tiles;
+  if (grid < 1) return CVIT_OK;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+static int make_tmap_rows(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                          int kspan) {
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t strides[2] = {0, (uint64_t)ld * 2};
+  uint32_t box[2] = {(uint32_t)(kspan / 2), (uint32_t)box_rows};
+  return encode_tmap(tm, TmapDtype::BF16, 2, base, dims, strides, box, kspan);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define CVIT_GEMM_CASE(BN_, EPI_, AMODE_, KSPAN_)                                     \
+  if (bn == BN_ && epi == EPI_ && kspan == KSPAN_)                                    \
+    return launch_gemm<BN_, EPI_, AMODE_, KSPAN_>(tmA, tmB, args, num_tiles, stream);
+
+// Plain [M,K] x [N,K]^T GEMM with a fused epilogue.
+static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, int epi, cudaStream_t stream) {
+  const int64_t M = args.M, N = args.N, K = args.K;
+  if (M <= 0 || N <= 0 || K <= 0) {
+    set_error("gemm: non-positive dimension M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    return CVIT_ERR_INVALID;
+  }
+  if (!A || !B || !args.out || !aligned16(A) || !aligned16(B) || !aligned16(args.out) || (lda % 8) != 0 || (K % 8) != 0) {
+    set_error("gemm: null/unaligned operand (A,B,out need 16B alignment; lda and K multiples of 8)");
+    return CVIT_ERR_INVALID;
+  }
+  int kspan = K >= 64 ? 128 : K >= 32 ? 64 : 32;
+  if (K < 64 && (K != 32 && K != 16)) {
+    set_error("gemm: K=%lld unsupported (need K>=64, or K in {16,32})", (long long)K);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  int bn;
+  if (epi == EPI_BIAS_SWIGLU) bn = (N % 256 == 0) ? 256 : 0;
+  else bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : (N % 32 == 0) ? 32 : 0;
+  if (bn == 0) {
+    set_error("gemm: N=%lld not tileable for epilogue %d", (long long)N, epi);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  if (kspan != 128 && bn > 128) bn = 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_rows(&tmA, A, M, K, lda, GEMM_BM, kspan);
+  if (rc) return rc;
+  rc = make_tmap_rows(&tmB, B, N, K, K, bn, kspan);
+  if (rc) return rc;
+  const int num_tiles = (int)(((M + GEMM_BM - 1) / GEMM_BM) * (N / bn));
+  CVIT_GEMM_CASE(256, EPI_BIAS, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_BIAS, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(256, EPI_BIAS_GELU, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_BIAS_GELU, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(256, EPI_BIAS_SWIGLU, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(256, EPI_SCALE_RESIDUAL, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_SCALE_RESIDUAL, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(256, EPI_PATCH_EMBED, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_PATCH_EMBED, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(256, EPI_CONVT_GELU, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_CONVT_GELU, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(128, EPI_CONVT_GELU, AMODE_ROWS, 64)
+  CVIT_GEMM_CASE(32, EPI_CONVT_GELU, AMODE_ROWS, 32)
+  set_error("gemm: no kernel instantiated for BN=%d epilogue=%d kspan=%d", bn, epi, kspan);
+  return CVIT_ERR_UNSUPPORTED;
+}
+
+// 3x3x3 depth-dilated "same" convolution over a channels-last bf16 volume, + bias + GELU.
+static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t stream) {
+  const int D = args.D, H = args.H, W = args.W, Cin = args.K, Cout = args.N;
+  if (D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || args.dil <= 0) {
+    set_error("conv3: bad geometry D=%d H=%d W=%d Cin=%d Cout=%d dil=%d", D, H, W, Cin, Cout, args.dil);
+    return CVIT_ERR_INVALID;
+  }
+  if (!x || !w || !args.out || !aligned16(x) || !aligned16(w) || !aligned16(args.out)) {
+    set_error("conv3: null/unaligned operand");
+    return CVIT_ERR_INVALID;
+  }
+  int kspan = (Cin % 64 == 0) ? 128 : (Cin == 32) ? 64 : (Cin == 16) ? 32 : 0;
+  if (!kspan) {
+    set_error("conv3: Cin=%d unsupported (need multiple of 64, or 32, or 16)", Cin);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  // tile footprint: BW*BH = 128 output voxels of one depth plane
+  int BW = W >= 128 ? 128 : W, BH = 128 / BW;
+  if ((BW & (BW - 1)) != 0 || W % BW != 0 || H % BH != 0) {
+    set_error("conv3: plane %dx%d not tileable by %dx%d (W must be a power of two <=128 or a multiple of 128; H a multiple of 128/W)", H, W, BH, BW);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  args.BW = BW;
+  args.BH = BH;
+  const int bn = Cout;
+  const int epi = EPI_BIAS_GELU;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+    uint64_t strides[4] = {0, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)(kspan / 2), (uint32_t)BW, (uint32_t)BH, 1u};
+    int rc = encode_tmap(&tmA, TmapDtype::BF16, 4, x, dims, strides, box, kspan);
+    if (rc) return rc;
+  }
+  int rc = make_tmap_rows(&tmB, w, (int64_t)27 * Cout, Cin, Cin, bn, kspan);
+  if (rc) return rc;
+  const int num_tiles = D * (H / BH) * (W / BW);
+  CVIT_GEMM_CASE(192, EPI_BIAS_GELU, AMODE_CONV3, 128)
+  CVIT_GEMM_CASE(64, EPI_BIAS_GELU, AMODE_CONV3, 128)
+  CVIT_GEMM_CASE(32, EPI_BIAS_GELU, AMODE_CONV3, 64)
+  CVIT_GEMM_CASE(32, EPI_BIAS_GELU, AMODE_CONV3, 32)
+  set_error("conv3: no kernel instantiated for Cout=%d kspan=%d", bn, kspan);
+  return CVIT_ERR_UNSUPPORTED;
+}
+
+}  // namespace cvit
+
+using namespace cvit;
+
+static GemmArgs base_args(int64_t M, int64_t N, int64_t K, void* out, int64_t ldo) {
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = (int)N;
+  a.K = (int)K;
+  a.out = out;
+  a.ldo = (int)ldo;
+  a.n_valid = (int)N;
+  return a;
+}
+
+extern "C" {
+
+int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                          int64_t M, int64_t N, int64_t K, int gelu, void* stream) {
+  if (!bias) { set_error("linear_bias: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(M, N, K, out, ldo);
+  a.bias = bias;
+  return gemm_rows(A, lda, W, a, gelu ? EPI_BIAS_GELU : EPI_BIAS, (cudaStream_t)stream);
+}
+
+int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
+                            int64_t ldo, int64_t M, int64_t N2, int64_t K, void* stream) {
+  if (!bias12i) { set_error("linear_swiglu: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(M, N2, K, out, ldo);
+  a.bias = bias12i;
+  return gemm_rows(A, lda, W12i, a, EPI_BIAS_SWIGLU, (cudaStream_t)stream);
+}
+
+int cvit_linear_scale_residual_f32(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
+                                   float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, void* stream) {
+  if (!bias || !gamma) { set_error("linear_scale_residual: bias and gamma are required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(M, N, K, x, ldx);
+  a.bias = bias;
+  a.gamma = gamma;
+  return gemm_rows(A, lda, W, a, EPI_SCALE_RESIDUAL, (cudaStream_t)stream);
+}
+
+int cvit_patch_embed_gemm(const void* patches, int64_t lda, const void* W, const float* pos_bias_table, float* x,
+                          int64_t ldx, int64_t n_slices, int64_t n_patches, int64_t tokens_per_slice,
+                          int64_t first_patch_token, int64_t N, int64_t K, void* stream) {
+  if (!pos_bias_table) { set_error("patch_embed: table is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(n_slices * n_patches, N, K, x, ldx);
+  a.table = pos_bias_table;
+  a.pe_np = (int)n_patches;
+  a.pe_tokens = (int)tokens_per_slice;
+  a.pe_offset = (int)first_patch_token;
+  return gemm_rows(patches, lda, W, a, EPI_PATCH_EMBED, (cudaStream_t)stream);
+}
+
+int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                              int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                              void* stream) {
+  if (!bias) { set_error("conv3d: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(D * H * W, Cout, Cin, out, Cout_valid);
+  a.bias = bias;
+  a.D = (int)D;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.dil = (int)dil;
+  a.n_valid = (int)Cout_valid;
+  return conv3_rows(x, w_taps, a, (cudaStream_t)stream);
+}
+
+int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                           int64_t W, int64_t Cin, int64_t Cout, void* stream) {
+  if (!bias4) { set_error("convT: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(D * H * W, 4 * Cout, Cin, out, Cout);
+  a.bias = bias4;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.c3 = (int)Cout;
+  return gemm_rows(x, Cin, w_sub, a, EPI_CONVT_GELU, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major, i.e. torch Linear weight layout)
+//
+// One CTA per SM, 192 threads:
+//   warp 0      TMA producer  (one lane): cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring
+//   warp 1      MMA issuer    (one lane): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
+//                                          two accumulator buffers so tile i+1 overlaps epilogue i
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 cols) -> warp-private swizzled smem transpose ->
+//               fused math -> row-contiguous vector stores
+//
+// A-operand addressing modes:
+//   AMODE_ROWS  plain 2-D [M,K] matrix (ViT linears, 1x1x1 conv, transposed conv)
+//   AMODE_CONV3 implicit-GEMM 3x3x3 dilated "same" convolution over a channels-last [D,H,W,C] volume:
+//               the K loop walks (tap, channel-chunk); each A tile is one 4-D TMA box shifted by the
+//               tap offset, and TMA's out-of-bounds zero fill IS the zero padding (no im2col, no halo
+//               staging code). Taps whose depth offset falls outside [0,D) are skipped outright.
+//
+// Epilogues (what the reference computes around each GEMM):
+//   EPI_BIAS            out_bf16 = acc + bias                               (qkv)
+//   EPI_BIAS_GELU       out_bf16 = gelu_erf(acc + bias)                     (ViT-S/B/L fc1, head convs)
+//   EPI_BIAS_SWIGLU     out_bf16 = silu(acc1 + b1) * (acc2 + b2)            (ViT-g w12; weights row-interleaved
+//                                                                            per BN tile: [BN/2 of x1 | BN/2 of x2])
+//   EPI_SCALE_RESIDUAL  x_f32   += gamma * (acc + bias)                     (attn.proj + ls1, w3/fc2 + ls2)
+//   EPI_PATCH_EMBED     x_f32[b, off + p] = acc + table[p]                  (patch embed + bias + pos-embed)
+//   EPI_CONVT_GELU      pixel-shuffle store of ConvTranspose3d(1,2,2) + bias + GELU
+#pragma once
+#include "ptx.cuh"
+
+namespace cvit {
+
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_SWIGLU = 2, EPI_SCALE_RESIDUAL = 3, EPI_PATCH_EMBED = 4, EPI_CONVT_GELU = 5 };
+enum { AMODE_ROWS = 0, AMODE_CONV3 = 1 };
+
+struct GemmArgs {
+  int M, N, K;        // rows, output columns, reduction length (per tap for AMODE_CONV3)
+  void* out;          // bf16 or fp32, see epilogues
+  int ldo;            // leading dimension of out, in elements
+  const float* bias;  // [N] (interleaved like the weights for SWIGLU); may be null for PATCH_EMBED
+  const float* gamma; // [N] LayerScale (SCALE_RESIDUAL)
+  const float* table; // [pe_np, N] fp32 pos-embed(+bias) table (PATCH_EMBED)
+  int pe_np, pe_tokens, pe_offset;  // patches per slice, tokens per slice, first patch token index
+  int D, H, W, dil;   // AMODE_CONV3 geometry (M == D*H*W); dilation applies to depth only
+  int BW, BH;         // AMODE_CONV3 tile footprint, BW*BH == 128
+  int c3;             // EPI_CONVT_GELU: output channels per sub-pixel (N == 4*c3); uses H, W too
+  int n_valid;        // columns >= n_valid are computed (zero-padded weights) but never stored
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int KSPAN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * KSPAN;
+  static constexpr int B_BYTES = BN * KSPAN;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STG_BYTES_PER_WARP = 8192;  // two 32x32 fp32 transpose buffers
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256 /*barriers*/ + 1024 /*align slack*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
+  // every stage base must stay 1024-aligned for the swizzle pattern to line up with the descriptor
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must be 1024B multiples");
+};
+
+struct TileCoord {
+  int m0, n0;        // first output row / column of this tile
+  int d, h0, w0;     // AMODE_CONV3: depth plane and spatial origin
+};
+
+template <int BN, int AMODE>
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_n, const GemmArgs& a) {
+  TileCoord t;
+  int mb = tile / num_n;
+  t.n0 = (tile - mb * num_n) * BN;
+  t.m0 = mb * GEMM_BM;
+  t.d = t.h0 = t.w0 = 0;
+  if (AMODE == AMODE_CONV3) {
+    int tiles_w = a.W / a.BW, tiles_h = a.H / a.BH;
+    int per_plane = tiles_w * tiles_h;
+    t.d = mb / per_plane;
+    int r = mb - t.d * per_plane;
+    int th = r / tiles_w;
+    t.h0 = th * a.BH;
+    t.w0 = (r - th * tiles_w) * a.BW;
+  }
+  return t;
+}
+
+// Row r (0..127) of a tile -> linear output row (voxel index for conv), or -1 when out of range.
+template <int AMODE>
+__device__ __forceinline__ int tile_row_to_global(const TileCoord& t, int r, const GemmArgs& a) {
+  if (AMODE == AMODE_CONV3) {
+    int hl = r / a.BW, wl = r - hl * a.BW;
+    return (t.d * a.H + t.h0 + hl) * a.W + t.w0 + wl;
+  }
+  int g = t.m0 + r;
+  return g < a.M ? g : -1;
+}
+
+template <int BN, int EPI, int AMODE, int KSPAN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs args) {
+  using Cfg = GemmCfg<BN, KSPAN>;
+  constexpr int KC = KSPAN / 2;        // bf16 elements of K per stage
+  constexpr int MMAS_PER_STAGE = KC / 16;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t sStg = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t sBar = sStg + 4 * Cfg::STG_BYTES_PER_WARP;
+  const uint32_t bar_full = sBar;                    // STAGES x 8B
+  const uint32_t bar_empty = sBar + 8 * STAGES;      // STAGES x 8B
+  const uint32_t bar_tfull = sBar + 16 * STAGES;     // 2 x 8B
+  const uint32_t bar_tempty = bar_tfull + 16;        // 2 x 8B
+  const uint32_t tmem_slot = bar_tempty + 16;        // 4B
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_n = args.N / BN;
+  const int num_m = AMODE == AMODE_CONV3 ? args.D * (args.H / args.BH) * (args.W / args.BW)
+                                         : (args.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_tiles = num_m * num_n;
+  const int k_chunks = (args.K + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+        const int taps = AMODE == AMODE_CONV3 ? 27 : 1;
+        for (int tap = 0; tap < taps; ++tap) {
+          int dz = 0, dy = 0, dx = 0;
+          if (AMODE == AMODE_CONV3) {
+            int kd = tap / 9, kr = tap - kd * 9, kh = kr / 3, kw = kr - kh * 3;
+            dz = t.d + (kd - 1) * args.dil;
+            dy = t.h0 + kh - 1;
+            dx = t.w0 + kw - 1;
+            if (dz < 0 || dz >= args.D) continue;  // whole tap is zero padding
+          }
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::STAGE_BYTES);
+            if (AMODE == AMODE_CONV3) {
+              tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, dx, dy, dz);
+              tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, tap * args.N + t.n0);
+            } else {
+              tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, t.m0);
+              tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, t.n0);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        uint32_t accumulate = 0;
+        const int taps = AMODE == AMODE_CONV3 ? 27 : 1;
+        for (int tap = 0; tap < taps; ++tap) {
+          if (AMODE == AMODE_CONV3) {
+            int kd = tap / 9;
+            int dz = t.d + (kd - 1) * args.dil;
+            if (dz < 0 || dz >= args.D) continue;
+          }
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(bar_full + 8 * s, ph);
+            tcgen05_fence_after();
+            const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES);
+            const uint64_t bdesc = umma_smem_desc_kmajor<KSPAN>(sB + s * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(bar_empty + 8 * s);  // smem slot reusable once these MMAs retire
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t stg = sStg + (warp - 2) * Cfg::STG_BYTES_PER_WARP;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    constexpr int NCHUNK = (EPI == EPI_BIAS_SWIGLU ? BN / 2 : BN) / 32;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tcgen05_fence_after();
+      const uint32_t t_acc = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int c0 = ch * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(t_acc + c0, v);
+        tmem_ld_wait();
+        // transpose through warp-private smem: thread = row on the way in, 8 lanes per row on the way out
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        if (EPI == EPI_BIAS_SWIGLU) {
+          tmem_ld_32x32(t_acc + BN / 2 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t addr = stg + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                         "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+        }
+        __syncwarp();
+        const int jc = lane & 7;             // 16-byte column group handled by this lane
+        const int ncol = t.n0 + c0 + jc * 4;  // first of its 4 accumulator columns
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4, b4b = b4;
+        if (EPI != EPI_PATCH_EMBED || args.bias != nullptr)
+          if (args.bias) b4 = __ldg(reinterpret_cast<const float4*>(args.bias + ncol));
+        if (EPI == EPI_SCALE_RESIDUAL) g4 = __ldg(reinterpret_cast<const float4*>(args.gamma + ncol));
+        if (EPI == EPI_BIAS_SWIGLU) b4b = __ldg(reinterpret_cast<const float4*>(args.bias + ncol + BN / 2));
+        float4 resid[8];
+        if (EPI == EPI_SCALE_RESIDUAL) {
+          // issue all residual loads up front so their latency overlaps (stores below may alias them)
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = tile_row_to_global<AMODE>(t, q * 32 + it * 4 + (lane >> 3), args);
+            resid[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow >= 0)
+              resid[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(args.out) + (size_t)grow * args.ldo + ncol);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const uint32_t addr = stg + r * 128 + ((jc ^ (r & 7)) << 4);
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+          const int grow = tile_row_to_global<AMODE>(t, q * 32 + r, args);
+          if (grow < 0 || ncol >= args.n_valid) continue;
+          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+            float o0 = x.x + b4.x, o1 = x.y + b4.y, o2 = x.z + b4.z, o3 = x.w + b4.w;
+            if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
+            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)grow * args.ldo + ncol) = pk;
+          } else if (EPI == EPI_BIAS_SWIGLU) {
+            float4 y;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(addr + 4096));
+            float o0 = silu(x.x + b4.x) * (y.x + b4b.x), o1 = silu(x.y + b4.y) * (y.y + b4b.y);
+            float o2 = silu(x.z + b4.z) * (y.z + b4b.z), o3 = silu(x.w + b4.w) * (y.w + b4b.w);
+            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            const int ocol = (t.n0 >> 1) + c0 + jc * 4;
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)grow * args.ldo + ocol) = pk;
+          } else if (EPI == EPI_SCALE_RESIDUAL) {
+            float4* p = reinterpret_cast<float4*>(static_cast<float*>(args.out) + (size_t)grow * args.ldo + ncol);
+            float4 res = resid[it];
+            res.x += g4.x * (x.x + b4.x);
+            res.y += g4.y * (x.y + b4.y);
+            res.z += g4.z * (x.z + b4.z);
+            res.w += g4.w * (x.w + b4.w);
+            *p = res;
+          } else if (EPI == EPI_PATCH_EMBED) {
+            const int b = grow / args.pe_np, p = grow - b * args.pe_np;
+            const float4 tb = __ldg(reinterpret_cast<const float4*>(args.table + (size_t)p * args.N + ncol));
+            float4 o = make_float4(x.x + tb.x + b4.x, x.y + tb.y + b4.y, x.z + tb.z + b4.z, x.w + tb.w + b4.w);
+            const size_t orow = (size_t)b * args.pe_tokens + args.pe_offset + p;
+            *reinterpret_cast<float4*>(static_cast<float*>(args.out) + orow * args.ldo + ncol) = o;
+          } else if (EPI == EPI_CONVT_GELU) {
+            // column n = (i*2 + j) * c3 + co ; voxel grow = (d*H + h)*W + w -> out[d, 2h+i, 2w+j, co]
+            const int ij = ncol / args.c3, co = ncol - ij * args.c3;
+            const int si = ij >> 1, sj = ij & 1;
+            const int w = grow % args.W, dh = grow / args.W;  // dh = d*H + h
+            const size_t orow = ((size_t)(2 * dh + si) * (2 * args.W)) + 2 * w + sj;
+            float o0 = gelu_erf(x.x + b4.x), o1 = gelu_erf(x.y + b4.y), o2 = gelu_erf(x.z + b4.z), o3 = gelu_erf(x.w + b4.w);
+            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + orow * args.c3 + co) = pk;
+          }
+        }
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator buffer are complete (every tcgen05.ld was waited on)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace cvit

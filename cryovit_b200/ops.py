@@ -1,0 +1,138 @@
+"""Torch-tensor front end of the C ABI: validates dtype / layout / device, then passes raw device pointers
+and the current CUDA stream across ``_lib.call``. PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BF16, F16, F32, U8 = torch.bfloat16, torch.float16, torch.float32, torch.uint8
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CryovitB200Error(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.CryovitB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise _lib.CryovitB200Error(f"{name}: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def patch_grid(H: int, W: int) -> tuple[int, int, int, int]:
+    """(OH, OW, ph, pw) after the reference's pad-to-16 + x14/16 resize (vit_dataset.py:100-123)."""
+    H16, W16 = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+    OH, OW = H16 // 16 * 14, W16 // 16 * 14
+    return OH, OW, OH // 14, OW // 14
+
+
+def preproc_patchify(src: torch.Tensor, out: torch.Tensor) -> None:
+    """src u8|f32 [D,H,W] -> out bf16 [D*Np, Kp] (one channel, Kp >= 196)."""
+    D, H, W = src.shape
+    is_u8 = src.dtype == U8
+    _lib.call("cvit_preproc_patchify", _chk(src, U8 if is_u8 else F32, "src"), int(is_u8), _chk(out, BF16, "out"),
+              D, H, W, out.shape[1], _stream())
+
+
+def patchify_f32_3ch(src: torch.Tensor, out: torch.Tensor) -> None:
+    B, C, OH, OW = src.shape
+    if C != 3:
+        raise _lib.CryovitB200Error("patchify_f32_3ch: expected [B,3,H,W]")
+    _lib.call("cvit_patchify_f32_3ch", _chk(src, F32, "src"), _chk(out, BF16, "out"), B, OH, OW, out.shape[1], _stream())
+
+
+def patch_embed_gemm(patches, w, table, x, n_slices, n_patches, tokens, first_patch_token) -> None:
+    N, K = w.shape
+    _lib.call("cvit_patch_embed_gemm", _chk(patches, BF16, "patches"), patches.shape[1], _chk(w, BF16, "w"),
+              _chk(table, F32, "table"), _chk(x, F32, "x"), x.shape[-1], n_slices, n_patches, tokens,
+              first_patch_token, N, K, _stream())
+
+
+def assemble_special_tokens(x: torch.Tensor, special: torch.Tensor, B: int, T: int) -> None:
+    S, C = special.shape
+    _lib.call("cvit_assemble_special_tokens", _chk(x, F32, "x"), _chk(special, F32, "special"), B, T, C, S, _stream())
+
+
+def layernorm(x: torch.Tensor, gamma, beta, out: torch.Tensor, eps: float) -> None:
+    M, C = x.shape
+    if out.dtype == F32:
+        _lib.call("cvit_layernorm_f32_f32", _chk(x, F32, "x"), x.stride(0), _chk(gamma, F32, "gamma"),
+                  _chk(beta, F32, "beta"), _chk(out, F32, "out"), out.stride(0), M, C, float(eps), _stream())
+        return
+    _lib.call("cvit_layernorm_f32_bf16", _chk(x, F32, "x"), x.stride(0), _chk(gamma, F32, "gamma"),
+              _chk(beta, F32, "beta"), _chk(out, BF16, "out"), out.stride(0), M, C, float(eps), _stream())
+
+
+def linear_bias(a, w, bias, out, gelu: bool = False) -> None:
+    M, K = a.shape
+    N = w.shape[0]
+    _lib.call("cvit_linear_bias_bf16", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, N, K, int(gelu), _stream())
+
+
+def linear_swiglu(a, w12i, bias12i, out) -> None:
+    M, K = a.shape
+    N2 = w12i.shape[0]
+    _lib.call("cvit_linear_swiglu_bf16", _chk(a, BF16, "a"), a.stride(0), _chk(w12i, BF16, "w12i"),
+              _chk(bias12i, F32, "bias12i"), _chk(out, BF16, "out"), out.stride(0), M, N2, K, _stream())
+
+
+def linear_scale_residual(a, w, bias, gamma, x) -> None:
+    M, K = a.shape
+    N = w.shape[0]
+    _lib.call("cvit_linear_scale_residual_f32", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"),
+              _chk(bias, F32, "bias"), _chk(gamma, F32, "gamma"), _chk(x, F32, "x"), x.stride(0), M, N, K, _stream())
+
+
+def attention(qkv, out, n_slices: int, tokens: int, heads: int) -> None:
+    _lib.call("cvit_attention_fwd_bf16", _chk(qkv, BF16, "qkv"), _chk(out, BF16, "out"), n_slices, tokens, heads, 64,
+              _stream())
+
+
+def final_norm_writeout(x, gamma, beta, features, n_slices, tokens, first_patch_token, n_patches, d0, eps) -> None:
+    C, D_total = features.shape[0], features.shape[1]
+    _lib.call("cvit_final_norm_writeout_f16", _chk(x, F32, "x"), _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta"),
+              _chk(features, F16, "features"), n_slices, tokens, first_patch_token, n_patches, C, D_total, d0,
+              float(eps), _stream())
+
+
+# ------------------------------------------------------------------------------------------------- head
+def features_to_ndhwc(features: torch.Tensor, out: torch.Tensor) -> None:
+    C = features.shape[0]
+    DHW = features.numel() // C
+    _lib.call("cvit_features_to_ndhwc_bf16", _chk(features, F16, "features"), _chk(out, BF16, "out"), C, DHW, _stream())
+
+
+def groupnorm_ndhwc(x, out, gamma, beta, stats, groups: int, eps: float) -> None:
+    C = x.shape[-1]
+    DHW = x.numel() // C
+    _lib.call("cvit_groupnorm_ndhwc_bf16", _chk(x, BF16, "x"), _chk(out, BF16, "out"), _chk(gamma, F32, "gamma"),
+              _chk(beta, F32, "beta"), _chk(stats, F32, "stats"), DHW, C, groups, float(eps), _stream())
+
+
+def conv3d_dilated(x, w_taps, bias, out, dil: int) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_taps.shape[0] // 27
+    _lib.call("cvit_conv3d_dilated_ndhwc", _chk(x, BF16, "x"), _chk(w_taps, BF16, "w_taps"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, _stream())
+
+
+def convT_1x2x2(x, w_sub, bias4, out) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_sub.shape[0] // 4
+    _lib.call("cvit_convT_1x2x2_ndhwc", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, _stream())
+
+
+def head_tail(x, w1, b1, w2, b2, scratch, logits=None, probs=None) -> None:
+    D, H, W, _ = x.shape
+    _lib.call("cvit_head_tail_fused", _chk(x, BF16, "x"), _chk(w1, F32, "w1"), _chk(b1, F32, "b1"),
+              _chk(w2, F32, "w2"), _chk(b2, F32, "b2"),
+              _chk(logits, F32, "logits") if logits is not None else None,
+              _chk(probs, F32, "probs") if probs is not None else None, _chk(scratch, BF16, "scratch"), D, H, W,
+              _stream())

@@ -1,0 +1,149 @@
+/*
+ * cryovit_b200 C ABI  --  the drop-in boundary of the B200-native CryoVIT hot path.
+ *
+ * The reference (VivianDLi/CryoVIT) is pure Python and has no FFI of its own; its seams for this path are
+ * Python call sites.  This header is seam B7: the operator-level C ABI that the
+ * Python host mirror (cryovit_b200/vit.py, head.py, extract.py) binds with ctypes, and that any other host
+ * (C++, a torch custom op, a napari plugin) can bind the same way.  Each entry point names the reference
+ * computation it replaces (file:line under /root/reference/src/cryovit, or the un-vendored upstream
+ * facebookresearch/dinov2 cross-checked against transformers' Dinov2WithRegisters, "HF:").
+ *
+ * Contract for every function:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns every buffer; nothing is allocated, nothing is freed, no hidden synchronisation;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - returns 0 on success or a negative CVIT_ERR_* code; cvit_last_error() gives the message for the
+ *     calling thread.  No exceptions cross the boundary;
+ *   - re-entrant per (device, stream).  sm_100a only: there is no CPU or other-architecture fallback.
+ *
+ * Layout vocabulary: a "slice" is one z-plane of a tomogram; "tokens" are the ViT tokens of one slice
+ * (1 cls + R registers + Np patches); a "feature volume" is fp16 (C, D, h, w); the head works on
+ * channels-last (D, H, W, C) bf16 volumes ("ndhwc").
+ */
+#ifndef CRYOVIT_B200_H
+#define CRYOVIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVIT_OK 0
+#define CVIT_ERR_INVALID (-1)
+#define CVIT_ERR_CUDA (-2)
+#define CVIT_ERR_DRIVER (-3)
+#define CVIT_ERR_UNSUPPORTED (-4)
+
+/* Library identity / diagnostics. */
+int cvit_abi_version(void);
+const char* cvit_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Slice pre-processing + patchify.
+ * Replaces VITDataset._load_tomogram + _dino_transform (datasets/vit_dataset.py:71-123): uint8 -> /255
+ * (src_is_u8 != 0) or float32 pass-through, edge-pad H,W to multiples of 16, bicubic x14/16 (A=-0.75,
+ * align_corners=False, borders clamped), cut into 14x14 patches.  The reference replicates the single
+ * channel three times; here ONE channel is produced (host pre-sums the patch-embed weight over its 3 input
+ * channels).  Output: bf16 [D * Np, Kp], column i*14+j for pixel (i,j) of the patch, columns 196..Kp-1 zero;
+ * Np = (ceil16(H)*14/16/14) * (ceil16(W)*14/16/14).  Kp is a multiple of 64, >= 196.
+ */
+int cvit_preproc_patchify(const void* src, int src_is_u8, void* patches_bf16, int64_t D, int64_t H, int64_t W,
+                          int64_t Kp, void* stream);
+
+/* Patchify for the reference-facing model call forward_features(x: f32[B,3,H',W']) (run/dino_features.py:58;
+ * upstream PatchEmbed, HF:42-73).  Output bf16 [B * Np, Kp], column c*196 + i*14 + j, zero padded to Kp
+ * (multiple of 64, >= 588). */
+int cvit_patchify_f32_3ch(const float* src, void* patches_bf16, int64_t B, int64_t OH, int64_t OW, int64_t Kp,
+                          void* stream);
+
+/* Patch-embed GEMM: x[b, first_patch_token + p, :] = patches[b*Np + p, :] @ W^T + pos_bias_table[p, :].
+ * Replaces upstream PatchEmbed.proj (conv 14/14 as a GEMM) + the pos-embed add of prepare_tokens_with_masks
+ * (HF:61-71,147-173).  W: bf16 [N, K] row-major; table: fp32 [Np, N] = interpolated pos-embed + conv bias;
+ * x: fp32 [n_slices * tokens_per_slice, ldx]. */
+int cvit_patch_embed_gemm(const void* patches, int64_t lda, const void* W, const float* pos_bias_table, float* x,
+                          int64_t ldx, int64_t n_slices, int64_t n_patches, int64_t tokens_per_slice,
+                          int64_t first_patch_token, int64_t N, int64_t K, void* stream);
+
+/* x[b, s, :] = special[s, :] for s < S (cls + pos[0], then the register tokens; HF:147-173). */
+int cvit_assemble_special_tokens(float* x, const float* special, int64_t B, int64_t T, int64_t C, int64_t S,
+                                 void* stream);
+
+/* LayerNorm over the last dim: out_bf16 = (x - mean) * rsqrt(var + eps) * gamma + beta.  Replaces
+ * Block.norm1 / norm2 (upstream block.py; HF:370,377).  x fp32 [M, ldx]; C in {384, 768, 1024, 1536}. */
+int cvit_layernorm_f32_bf16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
+                            int64_t ldo, int64_t M, int64_t C, float eps, void* stream);
+
+/* Same with fp32 output: the final model.norm when the caller wants x_norm_* tensors (HF:477-503) rather than
+ * the fused fp16 write-out below. */
+int cvit_layernorm_f32_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* out,
+                           int64_t ldo, int64_t M, int64_t C, float eps, void* stream);
+
+/* out_bf16[M, N] = A[M, K] @ W[N, K]^T + bias, optionally followed by exact-erf GELU.  Replaces attn.qkv
+ * (HF:219-221) and, with gelu=1, Mlp.fc1 + GELU of ViT-S/B/L and the head's 1x1x1 Conv3d + GELU
+ * (models/cryovit.py:19-22).  bf16 operands, fp32 accumulation in TMEM. */
+int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                          int64_t M, int64_t N, int64_t K, int gelu, void* stream);
+
+/* SwiGLU FFN input half: out_bf16[M, N2/2] = silu(A @ W1^T + b1) * (A @ W2^T + b2).  Replaces
+ * SwiGLUFFNFused.w12 + silu(x1)*x2 (upstream swiglu_ffn.py; HF:354-360).  W12i / bias12i are the w12
+ * parameters with rows re-ordered per 256-row tile as [128 rows of w1 | the matching 128 rows of w2]
+ * (cryovit_b200.vit.interleave_w12 does this at load time).  N2 = 2 * hidden, multiple of 256. */
+int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
+                            int64_t ldo, int64_t M, int64_t N2, int64_t K, void* stream);
+
+/* x_f32[M, N] += gamma * (A @ W^T + bias).  Replaces attn.proj + ls1 + residual and w3/fc2 + ls2 + residual
+ * (upstream block.py, layer_scale.py; HF:257-300,355-361,386-404). */
+int cvit_linear_scale_residual_f32(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
+                                   float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* Multi-head self-attention of every slice: out[b, t, h*64 + d] = softmax(q k^T / 8) v with
+ * q,k,v = qkv[b, t, {0,1,2}, h, :].  Replaces MemEffAttention / xformers memory_efficient_attention
+ * (upstream attention.py; HF:202-256).  qkv bf16 [n_slices * tokens, 3 * heads * 64]; head_dim must be 64. */
+int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                            int64_t head_dim, void* stream);
+
+/* Final LayerNorm + patch-token slice + (B, Np, C) -> (C, D, Np) transpose + fp16 cast, written into the
+ * tomogram-wide feature volume at depth offset d0.  Replaces model.norm + x_norm_patchtokens (HF:477-503) and
+ * run/dino_features.py:58-64 (reshape, permute([3,0,1,2]).contiguous(), .half(), concatenate(axis=1)). */
+int cvit_final_norm_writeout_f16(const float* x, const float* gamma, const float* beta, void* features_f16,
+                                 int64_t n_slices, int64_t tokens_per_slice, int64_t first_patch_token,
+                                 int64_t n_patches, int64_t C, int64_t D_total, int64_t d0, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CryoVIT 3-D head (models/cryovit.py:10-83), channels-last bf16 volumes.
+ */
+
+/* fp16 feature volume (C, D, h, w) -> bf16 channels-last (D, h, w, C): the head's input permute
+ * (models/cryovit.py:45-46, datamodules/utils.py:105-107) fused with the dtype change. */
+int cvit_features_to_ndhwc_bf16(const void* features_f16, void* out_bf16, int64_t C, int64_t DHW, void* stream);
+
+/* GroupNorm(G groups, eps) over a channels-last bf16 volume [DHW, C], statistics over (C/G) * DHW per group,
+ * in fp32 (models/cryovit.py:69).  stats is a caller-provided fp32 scratch of 2*G floats (zeroed here). */
+int cvit_groupnorm_ndhwc_bf16(const void* x, void* out, const float* gamma, const float* beta, float* stats,
+                              int64_t DHW, int64_t C, int64_t G, float eps, void* stream);
+
+/* Conv3d(Cin -> Cout, kernel 3, padding "same", dilation (dil,1,1)) + bias + GELU as an implicit GEMM
+ * (models/cryovit.py:70-73).  x bf16 [D,H,W,Cin]; w_taps bf16 [27 * Cout, Cin] with tap = (kd*3+kh)*3+kw
+ * (Cout may be zero-padded to a multiple of 32, Cout_valid = real channel count = row pitch of out). */
+int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                              int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                              void* stream);
+
+/* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
+ * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;
+ * bias4 fp32 [4 * Cout] (the bias repeated per sub-pixel); out bf16 [D, 2H, 2W, Cout]. */
+int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                           int64_t W, int64_t Cin, int64_t Cout, void* stream);
+
+/* Head tail: Conv3d(8->8,k3) + GELU + Conv3d(8->1,k3) + clip(-5,5) [+ sigmoid] (models/cryovit.py:30-49).
+ * x bf16 [D,H,W,8]; w1 fp32 [27][8 out][8 in]; w2 fp32 [27][8]; logits/probs fp32 [D,H,W] (either may be
+ * NULL); scratch_bf16 holds the 8-channel intermediate, [D,H,W,8] bf16. */
+int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* logits, float* probs, void* scratch_bf16, int64_t D, int64_t H, int64_t W,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRYOVIT_B200_H */

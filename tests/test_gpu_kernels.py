@@ -1,0 +1,242 @@
+"""Kernel-level parity on a B200: every C-ABI operator against a plain PyTorch fp32 restatement of the same
+operator evaluated on the same (bf16-rounded) operands. Tolerances are stated per test; they bound the bf16
+output rounding (2^-9 relative) plus fp32 accumulation-order differences."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _close(got, ref, atol, rtol, what):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} out of tolerance, max abs err {err.max().item():.4e}, ref max {ref.abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 256), (128, 256, 64), (1029, 384, 384), (257, 1152, 384), (4116, 4608, 1536)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_linear_bias(cuda_lib, M, N, K, gelu):
+    from cryovit_b200 import ops
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+    b = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear_bias(a, w, b, out, gelu=gelu)
+    ref = a.float() @ w.float().t() + b
+    if gelu:
+        ref = F.gelu(ref)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what=f"linear_bias {M}x{N}x{K} gelu={gelu}")
+
+
+@pytest.mark.parametrize("M,H,K", [(300, 256, 128), (1029, 4096, 1536)])
+def test_linear_swiglu(cuda_lib, M, H, K):
+    from cryovit_b200 import ops
+    from cryovit_b200.vit import interleave_w12
+    a = _rand(M, K, seed=1).bfloat16()
+    w12 = _rand(2 * H, K, scale=K ** -0.5, seed=2).bfloat16()
+    b12 = _rand(2 * H, seed=3)
+    w12i, b12i = interleave_w12(w12, b12)
+    out = torch.full((M, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear_swiglu(a, w12i, b12i, out)
+    y = a.float() @ w12.float().t() + b12
+    ref = F.silu(y[:, :H]) * y[:, H:]
+    _close(out, ref, atol=2e-2, rtol=1e-2, what="linear_swiglu")
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1029, 1536, 4096), (789, 384, 1536)])
+def test_linear_scale_residual(cuda_lib, M, N, K):
+    from cryovit_b200 import ops
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+    b, g = _rand(N, seed=3), _rand(N, seed=4)
+    x0 = _rand(M, N, seed=5)
+    x = x0.clone()
+    ops.linear_scale_residual(a, w, b, g, x)
+    ref = x0 + g * (a.float() @ w.float().t() + b)
+    _close(x, ref, atol=1e-3, rtol=1e-4, what="linear_scale_residual")
+
+
+def test_patch_embed_gemm(cuda_lib):
+    from cryovit_b200 import ops
+    B, Np, T, C, K = 3, 64, 69, 384, 256
+    patches = _rand(B * Np, K, seed=1).bfloat16()
+    w = _rand(C, K, scale=K ** -0.5, seed=2).bfloat16()
+    table = _rand(Np, C, seed=3)
+    x = torch.zeros(B * T, C, device=DEV)
+    ops.patch_embed_gemm(patches, w, table, x, B, Np, T, 5)
+    ref = torch.zeros(B, T, C, device=DEV)
+    ref[:, 5:] = (patches.float() @ w.float().t()).view(B, Np, C) + table
+    _close(x.view(B, T, C), ref, atol=1e-3, rtol=1e-4, what="patch_embed")
+
+
+@pytest.mark.parametrize("C", [384, 1536])
+def test_layernorm(cuda_lib, C):
+    from cryovit_b200 import ops
+    M = 1031
+    x = _rand(M, C, scale=3.0, seed=1) + 0.5
+    g, b = _rand(C, seed=2), _rand(C, seed=3)
+    out = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, g, b, out, 1e-6)
+    ref = F.layer_norm(x, (C,), g, b, 1e-6)
+    _close(out, ref, atol=1e-2, rtol=1e-2, what="layernorm")
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2)])
+def test_attention(cuda_lib, B, T, H):
+    from cryovit_b200 import ops
+    C = H * 64
+    qkv = _rand(B * T, 3 * C, seed=1).bfloat16()
+    out = torch.full((B * T, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
+    _close(out, ref, atol=2e-2, rtol=2e-2, what="attention")
+
+
+@pytest.mark.parametrize("D,H,W,u8", [(3, 64, 96, True), (2, 50, 70, True), (2, 64, 64, False)])
+def test_preproc_patchify(cuda_lib, D, H, W, u8):
+    from cryovit_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    if u8:
+        src = torch.randint(0, 256, (D, H, W), generator=g, dtype=torch.uint8).to(DEV)
+        f = src.float() / 255.0
+    else:
+        src = torch.rand(D, H, W, generator=g).to(DEV)
+        f = src
+    OH, OW, ph, pw = ops.patch_grid(H, W)
+    out = torch.full((D * ph * pw, 256), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.preproc_patchify(src, out)
+    H16, W16 = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+    fp = F.pad(f[:, None], (0, W16 - W, 0, H16 - H), mode="replicate")
+    r = F.interpolate(fp, scale_factor=(14 / 16, 14 / 16), mode="bicubic")[:, 0]
+    assert r.shape[-2:] == (OH, OW)
+    ref = r.view(D, ph, 14, pw, 14).permute(0, 1, 3, 2, 4).reshape(D * ph * pw, 196)
+    _close(out[:, :196], ref, atol=6e-3, rtol=8e-3, what="preproc_patchify")
+    assert (out[:, 196:] == 0).all()
+
+
+def test_patchify_3ch(cuda_lib):
+    from cryovit_b200 import ops
+    B, OH, OW = 2, 56, 70
+    x = _rand(B, 3, OH, OW, seed=1)
+    out = torch.empty(B * 4 * 5, 640, device=DEV, dtype=torch.bfloat16)
+    ops.patchify_f32_3ch(x, out)
+    ref = x.view(B, 3, 4, 14, 5, 14).permute(0, 2, 4, 1, 3, 5).reshape(B * 20, 588)
+    _close(out[:, :588], ref, atol=1e-2, rtol=1e-2, what="patchify3")
+    assert (out[:, 588:] == 0).all()
+
+
+@pytest.mark.parametrize("C,Np", [(384, 49), (1536, 1024), (384, 784)])
+def test_final_norm_writeout(cuda_lib, C, Np):
+    from cryovit_b200 import ops
+    B, T, D_total, d0 = 2, Np + 5, 5, 2
+    x = _rand(B * T, C, scale=2.0, seed=1)
+    g, b = _rand(C, seed=2), _rand(C, seed=3)
+    feats = torch.zeros(C, D_total, Np, device=DEV, dtype=torch.float16)
+    ops.final_norm_writeout(x, g, b, feats, B, T, 5, Np, d0, 1e-6)
+    ref = F.layer_norm(x, (C,), g, b, 1e-6).view(B, T, C)[:, 5:]
+    ref = ref.permute(2, 0, 1).half()
+    _close(feats[:, d0:d0 + B], ref, atol=2e-3, rtol=2e-3, what="final_norm_writeout")
+    assert (feats[:, :d0] == 0).all() and (feats[:, d0 + B:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------- head ops
+def test_features_to_ndhwc(cuda_lib):
+    from cryovit_b200 import ops
+    C, D, h, w = 100, 3, 5, 7
+    f = _rand(C, D, h, w, seed=1).half()
+    out = torch.empty(D, h, w, C, device=DEV, dtype=torch.bfloat16)
+    ops.features_to_ndhwc(f, out)
+    assert torch.equal(out, f.permute(1, 2, 3, 0).bfloat16())
+
+
+@pytest.mark.parametrize("C,G", [(1024, 128), (128, 16), (32, 8)])
+def test_groupnorm(cuda_lib, C, G):
+    from cryovit_b200 import ops
+    D, H, W = 3, 8, 16
+    x = (_rand(D, H, W, C, seed=1) * 1.5 + 0.3).bfloat16()
+    g, b = _rand(C, seed=2), _rand(C, seed=3)
+    out = torch.empty_like(x)
+    stats = torch.empty(2 * G, device=DEV)
+    ops.groupnorm_ndhwc(x, out, g, b, stats, G, 1e-3)
+    ref = F.group_norm(x.float().permute(3, 0, 1, 2)[None], G, g, b, 1e-3)[0].permute(1, 2, 3, 0)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what="groupnorm")
+
+
+def _conv_w_taps(w, cout_pad):
+    # torch Conv3d weight [Cout, Cin, 3, 3, 3] -> [27 * cout_pad, Cin], tap = (kd*3+kh)*3+kw
+    Cout, Cin = w.shape[:2]
+    wt = torch.zeros(27, cout_pad, Cin, device=w.device, dtype=w.dtype)
+    wt[:, :Cout] = w.permute(2, 3, 4, 0, 1).reshape(27, Cout, Cin)
+    return wt.reshape(27 * cout_pad, Cin).contiguous()
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [
+    (8, 8, 16, 64, 64, 2),      # generic, Cin one chunk
+    (6, 32, 32, 128, 64, 4),    # SB2a-like, two channel chunks
+    (40, 4, 32, 1024, 192, 32), # SB1a geometry class: D > dil
+    (8, 4, 32, 1024, 192, 32),  # D <= dil: depth taps are pure padding
+    (5, 8, 64, 32, 32, 1),      # SB3-like, 64B swizzle
+    (4, 4, 256, 32, 16, 2),     # SB4a: Cout padded 16 -> 32, W > 128
+    (4, 2, 128, 16, 16, 1),     # SB4b: 32B swizzle
+])
+def test_conv3d_dilated(cuda_lib, D, H, W, Cin, Cout, dil):
+    from cryovit_b200 import ops
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, 3, scale=(27 * Cin) ** -0.5, seed=2).bfloat16()
+    b = _rand(Cout, seed=3)
+    cout_pad = max(32, Cout)
+    bp = torch.zeros(cout_pad, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv3d_dilated(x, _conv_w_taps(w, cout_pad), bp, out, dil)
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding="same", dilation=(dil, 1, 1))
+    ref = F.gelu(ref)[0].permute(1, 2, 3, 0)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what="conv3d_dilated")
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout", [(3, 8, 16, 192, 128), (2, 8, 16, 64, 32), (2, 8, 16, 32, 32), (2, 8, 16, 16, 8)])
+def test_convT(cuda_lib, D, H, W, Cin, Cout):
+    from cryovit_b200 import ops
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = _rand(Cin, Cout, 1, 2, 2, scale=Cin ** -0.5, seed=2).bfloat16()
+    b = _rand(Cout, seed=3)
+    w_sub = w[:, :, 0].permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()  # row (i*2+j)*Cout + co
+    out = torch.full((D, 2 * H, 2 * W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.convT_1x2x2(x, w_sub, b.repeat(4).contiguous(), out)
+    ref = F.conv_transpose3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, stride=(1, 2, 2))
+    ref = F.gelu(ref)[0].permute(1, 2, 3, 0)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what="convT")
+
+
+@pytest.mark.parametrize("D,H,W", [(3, 16, 128), (2, 10, 200)])
+def test_head_tail(cuda_lib, D, H, W):
+    from cryovit_b200 import ops
+    x = _rand(D, H, W, 8, seed=1).bfloat16()
+    w1 = _rand(8, 8, 3, 3, 3, scale=0.1, seed=2)
+    b1 = _rand(8, seed=3)
+    w2 = _rand(1, 8, 3, 3, 3, scale=0.3, seed=4)
+    b2 = _rand(1, seed=5)
+    w1t = w1.permute(2, 3, 4, 0, 1).reshape(27, 8, 8).contiguous()
+    w2t = w2.permute(2, 3, 4, 0, 1).reshape(27, 8).contiguous()
+    scratch = torch.empty(D, H, W, 8, device=DEV, dtype=torch.bfloat16)
+    logits = torch.empty(D, H, W, device=DEV)
+    probs = torch.empty(D, H, W, device=DEV)
+    ops.head_tail(x, w1t, b1, w2t, b2, scratch, logits, probs)
+    y = F.gelu(F.conv3d(x.float().permute(3, 0, 1, 2)[None], w1, b1, padding="same"))
+    y = y.bfloat16().float()  # the 8-channel intermediate is stored in bf16
+    z = F.conv3d(y, w2, b2, padding="same").clamp(-5, 5)[0, 0]
+    _close(logits, z, atol=2e-2, rtol=1e-2, what="tail logits")
+    _close(probs, torch.sigmoid(z), atol=5e-3, rtol=1e-2, what="tail probs")
