@@ -151,12 +151,15 @@ static int launch_layernorm(const float* x, int64_t ldx, const float* gamma, con
   const int rows_per_block = 8;
   const int grid = (int)((M + rows_per_block - 1) / rows_per_block);
   switch (C) {
+    case 128: layernorm_kernel<1, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
+    case 256: layernorm_kernel<2, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
     case 384: layernorm_kernel<3, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
+    case 512: layernorm_kernel<4, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
     case 768: layernorm_kernel<6, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
     case 1024: layernorm_kernel<8, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
     case 1536: layernorm_kernel<12, OutT><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, o, ldo, M, eps); break;
     default:
-      set_error("layernorm: C=%lld unsupported (384, 768, 1024, 1536)", (long long)C);
+      set_error("layernorm: C=%lld unsupported (128, 256, 384, 512, 768, 1024, 1536)", (long long)C);
       return CVIT_ERR_UNSUPPORTED;
   }
   return check_launch("layernorm_kernel");

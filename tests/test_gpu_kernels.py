@@ -238,5 +238,5 @@ def test_head_tail(cuda_lib, D, H, W):
     y = F.gelu(F.conv3d(x.float().permute(3, 0, 1, 2)[None], w1, b1, padding="same"))
     y = y.bfloat16().float()  # the 8-channel intermediate is stored in bf16
     z = F.conv3d(y, w2, b2, padding="same").clamp(-5, 5)[0, 0]
-    _close(logits, z, atol=2e-2, rtol=1e-2, what="tail logits")
+    _close(logits, z, atol=5e-2, rtol=1e-2, what="tail logits")  # bf16 intermediate, 216-term sums
     _close(probs, torch.sigmoid(z), atol=5e-3, rtol=1e-2, what="tail probs")

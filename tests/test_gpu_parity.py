@@ -1,0 +1,105 @@
+"""End-to-end parity on a B200: the CUDA path (through the C ABI) against the fp32 CPU oracle on the same
+seeded inputs and random-init weights, and against the committed golden fixtures.
+
+Tolerances are BASELINE.json's: per-token feature relative error <= 1e-2 and cosine similarity >= 0.999
+(both evaluated per patch token over the channel axis; we assert on the worst token and report the mean).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+REL_TOL, COS_TOL = 1e-2, 0.999
+
+
+def token_errors(got: torch.Tensor, ref: torch.Tensor):
+    """got/ref [..., C] -> (max rel err, mean rel err, min cosine) over tokens."""
+    got, ref = got.double().reshape(-1, got.shape[-1]), ref.double().reshape(-1, ref.shape[-1])
+    rel = (got - ref).norm(dim=-1) / ref.norm(dim=-1)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
+    return rel.max().item(), rel.mean().item(), cos.min().item()
+
+
+def _check(got, ref, what):
+    rmax, rmean, cmin = token_errors(got, ref)
+    print(f"\n[parity] {what}: rel-err max {rmax:.3e} mean {rmean:.3e}; min cosine {cmin:.6f}")
+    assert rmax <= REL_TOL, f"{what}: per-token relative error {rmax:.3e} > {REL_TOL}"
+    assert cmin >= COS_TOL, f"{what}: cosine {cmin:.6f} < {COS_TOL}"
+
+
+@pytest.mark.parametrize("name,shape", [("dinov2_vits14_reg", (2, 3, 392, 392)), ("tiny_swiglu", (2, 3, 56, 84))])
+def test_forward_features_vs_oracle_and_golden(cuda_lib, name, shape):
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200, ViTConfig, random_state_dict
+    from oracle import dinov2 as odino
+
+    cfg = CONFIGS.get(name) or ViTConfig("tiny_swiglu", 384, 3, 6, "swiglu", 1024)
+    sd = random_state_dict(cfg, seed=0)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(1))
+    model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda().eval()
+    out = model.forward_features(x.cuda())
+    got = out["x_norm_patchtokens"].float().cpu()
+    ref = odino.forward_features(sd, x, cfg.num_heads)
+    _check(got, ref["x_norm_patchtokens"], f"{name} patch tokens vs oracle")
+    _check(out["x_norm_clstoken"].float().cpu()[:, None], ref["x_norm_clstoken"][:, None], f"{name} cls vs oracle")
+    hf = np.load(GOLD / "dinov2_hf.npz")
+    tag = "vits" if name == "dinov2_vits14_reg" else "tiny_swiglu"
+    sub = got[:, ::7] if tag == "vits" else got
+    _check(sub, torch.from_numpy(hf[f"dinov2_{tag}_hf_patchtokens"]), f"{name} patch tokens vs transformers golden")
+
+
+def test_fused_extract_matches_reference_pipeline(cuda_lib):
+    """u8 tomogram -> (fused GPU preproc + ViT-S + write-out) vs oracle preproc -> oracle ViT -> reference layout.
+    Includes a non-multiple-of-16 plane (edge-pad path) and a ragged last batch."""
+    from cryovit_b200.extract import extract_tomogram
+    from cryovit_b200.vit import CONFIGS, build_model, random_state_dict
+    from oracle import dinov2 as odino
+    from oracle import extract as oextract
+    from oracle import preproc as opre
+
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    sd = random_state_dict(cfg, seed=0)
+    tomo = np.random.default_rng(3).integers(0, 256, size=(5, 100, 120), dtype=np.uint8)
+    model = build_model(cfg.name, sd).cuda()
+    got = extract_tomogram(tomo, model, batch_size=2)
+    ref = oextract.dino_features(opre.dino_transform(opre.load_tomogram(tomo)), odino.OracleDino(sd, cfg.num_heads), 2)
+    assert got.dtype == np.float16 and got.shape == ref.shape == (384, 5, 7, 7) and got.flags["C_CONTIGUOUS"]
+    g = torch.from_numpy(got.astype(np.float32)).permute(1, 2, 3, 0)
+    r = torch.from_numpy(ref.astype(np.float32)).permute(1, 2, 3, 0)
+    _check(g, r, "fused extract (ViT-S) vs reference pipeline")
+
+
+def test_dino_features_mirror_matches_oracle(cuda_lib):
+    """The reference-facing _dino_features(data, model, batch_size) signature (seam B3)."""
+    from cryovit_b200.extract import _dino_features
+    from cryovit_b200.vit import CONFIGS, build_model, random_state_dict
+    from oracle import dinov2 as odino
+    from oracle import extract as oextract
+
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    sd = random_state_dict(cfg, seed=0)
+    data = torch.rand(3, 3, 56, 70, generator=torch.Generator().manual_seed(5))
+    got = _dino_features(data, build_model(cfg.name, sd).cuda(), batch_size=2)
+    ref = oextract.dino_features(data, odino.OracleDino(sd, cfg.num_heads), 2)
+    assert got.shape == ref.shape == (384, 3, 4, 5) and got.dtype == np.float16
+    _check(torch.from_numpy(got.astype(np.float32)).permute(1, 2, 3, 0),
+           torch.from_numpy(ref.astype(np.float32)).permute(1, 2, 3, 0), "_dino_features mirror")
+
+
+def test_vitg_one_slice_vs_oracle(cuda_lib):
+    """The headline model (ViT-g/14-reg4, 40 blocks, LayerScale 1.0 random init: the worst case for bf16 error
+    accumulation) on one 448x448 slice against the fp32 oracle evaluated on the host cores."""
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200, random_state_dict
+    from oracle import dinov2 as odino
+
+    cfg = CONFIGS["dinov2_vitg14_reg"]
+    sd = random_state_dict(cfg, seed=0)
+    x = torch.rand(1, 3, 448, 448, generator=torch.Generator().manual_seed(1))
+    model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda()
+    got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
+    del model
+    torch.cuda.empty_cache()
+    ref = odino.forward_features(sd, x, cfg.num_heads)["x_norm_patchtokens"]
+    _check(got, ref, "ViT-g one slice vs oracle")

@@ -1,0 +1,113 @@
+"""CPU suite (-m "not gpu"): the oracle against the committed golden vectors.
+
+tests/golden/reference_src.npz was produced by executing the reference's own source files
+(oracle/make_golden.py); tests/golden/dinov2_hf.npz by transformers' Dinov2WithRegistersModel.
+/root/reference is NOT read here -- only the fixtures.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dinov2 as odino
+from oracle import extract as oextract
+from oracle import head as ohead
+from oracle import metrics as ometrics
+from oracle import preproc as opre
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(GOLD / "reference_src.npz")
+
+
+@pytest.fixture(scope="module")
+def hf():
+    return np.load(GOLD / "dinov2_hf.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_preproc_matches_reference(ref, tag):
+    u8 = ref[f"preproc_{tag}_in"]
+    got = opre.dino_transform(opre.load_tomogram(u8)).numpy()
+    want = ref[f"preproc_{tag}_out"]
+    assert got.shape == want.shape and got.shape[1] == 3
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    # three identical channels (the fact the B200 path's channel folding relies on)
+    assert np.array_equal(got[:, 0], got[:, 1]) and np.array_equal(got[:, 0], got[:, 2])
+
+
+def test_feature_layout_matches_reference(ref):
+    class Fake:
+        def forward_features(self, x):
+            B, _, H, W = x.shape
+            gh, gw = H // 14, W // 14
+            s = x[:, 0, 0, 0].reshape(B, 1, 1)
+            p = torch.arange(gh * gw, dtype=torch.float32).reshape(1, -1, 1)
+            c = torch.arange(5, dtype=torch.float32).reshape(1, 1, -1)
+            return {"x_norm_patchtokens": s * 1000.0 + p + c * 0.125}
+
+    D, H, W = 5, 28, 42
+    data = torch.zeros(D, 3, H, W)
+    data[:, 0, 0, 0] = torch.arange(D, dtype=torch.float32)
+    got = oextract.dino_features(data, Fake(), batch_size=2)
+    want = ref["layout_features"]
+    assert got.dtype == np.float16 and got.shape == want.shape == (5, D, 2, 3)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_head_matches_reference(ref, tag):
+    sd = ohead.random_state_dict(1536, seed=3)
+    x = torch.from_numpy(ref[f"head_{tag}_in"]).float()
+    logits = ohead.forward_volume(sd, x)
+    np.testing.assert_allclose(logits.numpy(), ref[f"head_{tag}_logits"], rtol=0, atol=2e-5)
+    probs = ohead.forward(sd, x.permute(0, 2, 1, 3, 4))
+    np.testing.assert_allclose(probs.numpy(), ref[f"head_{tag}_probs"], rtol=0, atol=1e-5)
+    assert probs.shape[-2:] == (16 * x.shape[-2], 16 * x.shape[-1])
+
+
+def test_head_state_dict_names_and_size():
+    sd = ohead.random_state_dict(1536, seed=0)
+    assert sum(v.numel() for v in sd.values()) == 8_401_737
+    for k in ("layers.0.weight", "layers.2.layers.0.weight", "layers.2.layers.1.weight", "layers.5.layers.5.bias",
+              "output_layer.0.weight", "output_layer.2.bias"):
+        assert k in sd
+
+
+def test_metrics_match_reference(ref):
+    y_true, y_pred = torch.from_numpy(ref["metric_y_true"]), torch.from_numpy(ref["metric_y_pred"])
+    yp, yt = ometrics.masked_select(y_pred, y_true)
+    assert yp.shape == (6, 1)  # two ignore labels dropped
+    np.testing.assert_allclose(ometrics.dice_loss(yp, yt).numpy(), ref["metric_dice_loss"], atol=1e-7)
+    np.testing.assert_allclose(ometrics.dice_metric(yp, yt).numpy(), ref["metric_dice"], atol=1e-7)
+    np.testing.assert_allclose(ometrics.f1_metric(yp, yt).numpy(), ref["metric_f1"], atol=1e-7)
+    # hand-computed: preds>=.5 -> [1,0,0,1,1,1] vs [1,0,1,0,1,1]: tp=3 fp=1 fn=1
+    assert abs(float(ref["metric_dice"]) - 2 * 3 / (4 + 4 + 1e-3)) < 1e-6
+
+
+@pytest.mark.parametrize("tag,cfg", [("vits", "dinov2_vits14_reg"), ("tiny_swiglu", None)])
+def test_dinov2_oracle_matches_transformers(hf, tag, cfg):
+    from cryovit_b200.vit import CONFIGS, ViTConfig, random_state_dict
+
+    if cfg is None:
+        c, shape = ViTConfig("tiny_swiglu", 384, 3, 6, "swiglu", 1024), (2, 3, 56, 84)
+    else:
+        c, shape = CONFIGS[cfg], (2, 3, 392, 392)
+    sd = random_state_dict(c, seed=0)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(1))
+    torch.set_num_threads(8)
+    out = odino.forward_features(sd, x, c.num_heads)
+    pt = out["x_norm_patchtokens"]
+    sub = pt[:, ::7] if tag == "vits" else pt
+    np.testing.assert_allclose(sub.numpy(), hf[f"dinov2_{tag}_hf_patchtokens"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(out["x_norm_clstoken"].numpy(), hf[f"dinov2_{tag}_hf_cls"], rtol=0, atol=2e-4)
+
+
+def test_swiglu_hidden_rule():
+    from cryovit_b200.vit import CONFIGS
+
+    assert CONFIGS["dinov2_vitg14_reg"].hidden == 4096  # (int(4*1536*2/3)+7)//8*8
