@@ -32,6 +32,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],
     "cvit_final_norm_writeout_f16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "cvit_features_to_ndhwc_bf16": [P, P, I64, I64, P],
+    "cvit_features_f32_to_ndhwc_bf16": [P, P, I64, I64, P],
     "cvit_groupnorm_ndhwc_bf16": [P, P, P, P, P, I64, I64, I64, F32, P],
     "cvit_conv3d_dilated_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_convT_1x2x2_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, P],

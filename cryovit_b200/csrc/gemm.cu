@@ -105,12 +105,11 @@ static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t 
     set_error("conv3: Cin=%d unsupported (need multiple of 64, or 32, or 16)", Cin);
     return CVIT_ERR_UNSUPPORTED;
   }
-  // tile footprint: BW*BH = 128 output voxels of one depth plane
-  int BW = W >= 128 ? 128 : W, BH = 128 / BW;
-  if ((BW & (BW - 1)) != 0 || W % BW != 0 || H % BH != 0) {
-    set_error("conv3: plane %dx%d not tileable by %dx%d (W must be a power of two <=128 or a multiple of 128; H a multiple of 128/W)", H, W, BH, BW);
-    return CVIT_ERR_UNSUPPORTED;
-  }
+  // tile footprint: BW*BH = 128 output voxels of one depth plane; BW = smallest power of two covering
+  // min(W,128) (>= 8). Planes that are not a multiple of the footprint get partial border tiles.
+  int BW = 8;
+  while (BW < W && BW < 128) BW <<= 1;
+  const int BH = 128 / BW;
   args.BW = BW;
   args.BH = BH;
   const int bn = Cout;
@@ -125,7 +124,7 @@ static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t 
   }
   int rc = make_tmap_rows(&tmB, w, (int64_t)27 * Cout, Cin, Cin, bn, kspan);
   if (rc) return rc;
-  const int num_tiles = D * (H / BH) * (W / BW);
+  const int num_tiles = D * ((H + BH - 1) / BH) * ((W + BW - 1) / BW);
   CVIT_GEMM_CASE(192, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(64, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(32, EPI_BIAS_GELU, AMODE_CONV3, 64)

@@ -79,7 +79,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_n, const GemmA
   t.m0 = mb * GEMM_BM;
   t.d = t.h0 = t.w0 = 0;
   if (AMODE == AMODE_CONV3) {
-    int tiles_w = a.W / a.BW, tiles_h = a.H / a.BH;
+    int tiles_w = (a.W + a.BW - 1) / a.BW, tiles_h = (a.H + a.BH - 1) / a.BH;
     int per_plane = tiles_w * tiles_h;
     t.d = mb / per_plane;
     int r = mb - t.d * per_plane;
@@ -95,7 +95,10 @@ template <int AMODE>
 __device__ __forceinline__ int tile_row_to_global(const TileCoord& t, int r, const GemmArgs& a) {
   if (AMODE == AMODE_CONV3) {
     int hl = r / a.BW, wl = r - hl * a.BW;
-    return (t.d * a.H + t.h0 + hl) * a.W + t.w0 + wl;
+    int h = t.h0 + hl, w = t.w0 + wl;
+    // partial tiles at the plane border: TMA zero-filled the loads, the rows are simply not stored
+    if (h >= a.H || w >= a.W) return -1;
+    return (t.d * a.H + h) * a.W + w;
   }
   int g = t.m0 + r;
   return g < a.M ? g : -1;
@@ -127,8 +130,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   const int num_n = args.N / BN;
-  const int num_m = AMODE == AMODE_CONV3 ? args.D * (args.H / args.BH) * (args.W / args.BW)
-                                         : (args.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_m = AMODE == AMODE_CONV3
+                        ? args.D * ((args.H + args.BH - 1) / args.BH) * ((args.W + args.BW - 1) / args.BW)
+                        : (args.M + GEMM_BM - 1) / GEMM_BM;
   const int num_tiles = num_m * num_n;
   const int k_chunks = (args.K + KC - 1) / KC;
 

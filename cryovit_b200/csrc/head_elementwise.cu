@@ -8,7 +8,11 @@ namespace cvit {
 
 // ------------------------------------------------------------------------------------------------
 // (C, DHW) fp16  ->  (DHW, C) bf16, 64x64 tiles through shared memory.
-__global__ void __launch_bounds__(256) features_to_ndhwc_kernel(const __half* __restrict__ src,
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) features_to_ndhwc_kernel(const T* __restrict__ src,
                                                                  __nv_bfloat16* __restrict__ dst, int C, int64_t DHW) {
   __shared__ float tile[64][65];
   const int64_t v0 = (int64_t)blockIdx.x * 64;
@@ -17,7 +21,7 @@ __global__ void __launch_bounds__(256) features_to_ndhwc_kernel(const __half* __
   for (int i = ty; i < 64; i += 4) {
     const int c = c0 + i;
     const int64_t v = v0 + tx;
-    tile[i][tx] = (c < C && v < DHW) ? __half2float(src[(int64_t)c * DHW + v]) : 0.f;
+    tile[i][tx] = (c < C && v < DHW) ? to_f32(src[(int64_t)c * DHW + v]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 64; i += 4) {
@@ -206,9 +210,20 @@ int cvit_features_to_ndhwc_bf16(const void* features_f16, void* out_bf16, int64_
     return CVIT_ERR_INVALID;
   }
   dim3 grid((unsigned)((DHW + 63) / 64), (unsigned)((C + 63) / 64));
-  features_to_ndhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(features_f16),
-                                                                    static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
+  features_to_ndhwc_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __half*>(features_f16), static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
   return check_launch("features_to_ndhwc_kernel");
+}
+
+int cvit_features_f32_to_ndhwc_bf16(const float* features_f32, void* out_bf16, int64_t C, int64_t DHW, void* stream) {
+  if (!features_f32 || !out_bf16 || C <= 0 || DHW <= 0) {
+    set_error("features_f32_to_ndhwc: bad arguments");
+    return CVIT_ERR_INVALID;
+  }
+  dim3 grid((unsigned)((DHW + 63) / 64), (unsigned)((C + 63) / 64));
+  features_to_ndhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      features_f32, static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
+  return check_launch("features_to_ndhwc_kernel<float>");
 }
 
 int cvit_groupnorm_ndhwc_bf16(const void* x, void* out, const float* gamma, const float* beta, float* stats,

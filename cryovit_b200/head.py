@@ -1,0 +1,163 @@
+"""B200-native CryoVIT 3-D segmentation head (reference src/cryovit/models/cryovit.py:10-83).
+
+``CryoVITHeadB200`` keeps the reference's parameter names (``layers.0.weight``, ``layers.2.layers.1.weight``, ...,
+``output_layer.2.bias``), so a reference ``weights.pt`` loads unchanged (eval_model.py:185-186), and mirrors its
+call surface: ``forward_volume(x[B,C,D,h,w]) -> clipped logits [B,1,D,16h,16w]`` and
+``forward(batch) -> probabilities [B,D,16h,16w]``.
+
+Device layout: every intermediate volume is channels-last bf16 ``[D, H, W, C]``; convolutions are implicit GEMMs on
+tcgen05 (TMA box loads whose out-of-bounds zero fill is the "same" padding), GroupNorm is a two-pass HBM-bound
+kernel, ConvTranspose(1,2,2) is a GEMM with a pixel-shuffle store, and the 8-channel tail runs on CUDA cores.
+``in_channels`` generalises the reference's hard-wired 1536 (BASELINE config 1 feeds ViT-S features, 384).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import CryovitB200Error
+
+BLOCKS = [(1024, 192, 128, 32, 24), (128, 64, 32, 16, 12), (32, 32, 32, 8, 4), (32, 16, 8, 2, 1)]
+
+
+def state_dict_keys() -> list[str]:
+    keys = ["layers.0.weight", "layers.0.bias"]
+    for bi in range(4):
+        for li in (0, 1, 3, 5):
+            keys += [f"layers.{bi + 2}.layers.{li}.weight", f"layers.{bi + 2}.layers.{li}.bias"]
+    return keys + ["output_layer.0.weight", "output_layer.0.bias", "output_layer.2.weight", "output_layer.2.bias"]
+
+
+def _conv_taps(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
+    """Conv3d weight [Cout, Cin, 3, 3, 3] -> [27 * cout_pad, Cin], tap = (kd*3 + kh)*3 + kw."""
+    cout, cin = w.shape[:2]
+    wt = torch.zeros(27, cout_pad, cin, dtype=w.dtype)
+    wt[:, :cout] = w.permute(2, 3, 4, 0, 1).reshape(27, cout, cin)
+    return wt.reshape(27 * cout_pad, cin)
+
+
+class CryoVITHeadB200:
+    def __init__(self, in_channels: int = 1536):
+        self.in_channels = in_channels
+        self.device: torch.device | None = None
+        self._sd_cpu: dict | None = None
+        self._w: dict = {}
+        self._bufs: dict = {}
+        self.launches = 0
+
+    # ----------------------------------------------------------------------------- nn.Module-like surface
+    def load_state_dict(self, sd: dict, strict: bool = True):
+        missing = [k for k in state_dict_keys() if k not in sd]
+        if strict and missing:
+            raise CryovitB200Error(f"head state dict is missing {missing[:3]} ...")
+        if sd["layers.0.weight"].shape[1] != self.in_channels:
+            raise CryovitB200Error(f"layers.0.weight expects {sd['layers.0.weight'].shape[1]} input channels, "
+                                   f"head was built for {self.in_channels}")
+        self._sd_cpu = {k: v.detach().float().cpu() for k, v in sd.items()}
+        if self.device is not None:
+            self._pack()
+        return self
+
+    def state_dict(self) -> dict:
+        return dict(self._sd_cpu or {})
+
+    def cuda(self, device=None):
+        if not torch.cuda.is_available():
+            raise CryovitB200Error("no CUDA device: the B200 hot path has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if self._sd_cpu is not None:
+            self._pack()
+        return self
+
+    def eval(self):
+        return self
+
+    def _pack(self) -> None:
+        sd, dev = self._sd_cpu, self.device
+        bf = lambda t: t.to(dev).to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(dev).float().contiguous()
+        w = {"proj_w": bf(sd["layers.0.weight"].reshape(1024, self.in_channels)), "proj_b": f32(sd["layers.0.bias"])}
+        blocks = []
+        for bi, (c1, c2, c3, d1, d2) in enumerate(BLOCKS):
+            p = f"layers.{bi + 2}.layers."
+            c2p = max(32, c2)  # MMA N tile is a multiple of 32: zero-pad 16 -> 32 output channels
+            ba, bb = torch.zeros(c2p), torch.zeros(c2p)
+            ba[:c2], bb[:c2] = sd[p + "1.bias"], sd[p + "3.bias"]
+            wT = sd[p + "5.weight"]  # [c2, c3, 1, 2, 2]
+            blocks.append({
+                "groups": max(8, c1 // 8), "gn_w": f32(sd[p + "0.weight"]), "gn_b": f32(sd[p + "0.bias"]),
+                "a_w": bf(_conv_taps(sd[p + "1.weight"], c2p)), "a_b": f32(ba), "d1": d1,
+                "b_w": bf(_conv_taps(sd[p + "3.weight"], c2p)), "b_b": f32(bb), "d2": d2,
+                "t_w": bf(wT[:, :, 0].permute(2, 3, 1, 0).reshape(4 * c3, c2)), "t_b": f32(sd[p + "5.bias"].repeat(4)),
+                "c1": c1, "c2": c2, "c3": c3,
+            })
+        w["blocks"] = blocks
+        w["o1_w"] = f32(sd["output_layer.0.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8, 8))
+        w["o1_b"] = f32(sd["output_layer.0.bias"])
+        w["o2_w"] = f32(sd["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8))
+        w["o2_b"] = f32(sd["output_layer.2.bias"])
+        self._w = w
+
+    def _buf(self, name: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
+        b = self._bufs.get(name)
+        if b is None or b.numel() < numel or b.dtype != dtype:
+            b = torch.empty(numel, device=self.device, dtype=dtype)
+            self._bufs[name] = b
+        return b[:numel]
+
+    # ----------------------------------------------------------------------------- forward
+    @torch.inference_mode()
+    def segment_volume(self, features: torch.Tensor, want_probs: bool = True, want_logits: bool = True):
+        """features: CUDA (C, D, h, w) fp16 or fp32 -> (logits, probs), each fp32 [D, 16h, 16w] (or None)."""
+        if self.device is None or not self._w:
+            raise CryovitB200Error("head not ready: call load_state_dict(...) and .cuda() first")
+        if features.dim() != 4 or features.shape[0] != self.in_channels:
+            raise CryovitB200Error(f"expected features (C={self.in_channels}, D, h, w), got {tuple(features.shape)}")
+        C, D, h, w = features.shape
+        w_ = self._w
+        x = self._buf("ping", D * h * w * max(C, 1024)).narrow(0, 0, D * h * w * C).view(D, h, w, C)
+        ops.features_to_ndhwc(features.contiguous(), x)
+        y = self._buf("pong", D * h * w * 1024).view(D * h * w, 1024)
+        ops.linear_bias(x.view(D * h * w, C), w_["proj_w"], w_["proj_b"], y, gelu=True)
+        self.launches += 2
+        cur, H, W = y.view(D, h, w, 1024), h, w
+        stats = self._buf("gn_stats", 256, torch.float32)
+        names = ["ping", "pong"]
+        flip = 0  # cur lives in "pong"
+        for b in w_["blocks"]:
+            c1, c2, c3 = b["c1"], b["c2"], b["c3"]
+            vox = D * H * W
+            ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
+            nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
+            ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
+            cur, flip = nxt, flip ^ 1
+            nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
+            ops.conv3d_dilated(cur, b["b_w"], b["b_b"], nxt, b["d2"])
+            cur, flip = nxt, flip ^ 1
+            nxt = self._buf(names[flip], 4 * vox * c3).view(D, 2 * H, 2 * W, c3)
+            ops.convT_1x2x2(cur, b["t_w"], b["t_b"], nxt)
+            cur, flip = nxt, flip ^ 1
+            H, W = 2 * H, 2 * W
+            self.launches += 6  # memset + 2 GroupNorm kernels are counted as 3
+        scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
+        logits = torch.empty(D, H, W, device=self.device) if want_logits else None
+        probs = torch.empty(D, H, W, device=self.device) if want_probs else None
+        ops.head_tail(cur, w_["o1_w"], w_["o1_b"], w_["o2_w"], w_["o2_b"], scratch, logits, probs)
+        self.launches += 2
+        return logits, probs
+
+    @torch.inference_mode()
+    def forward_volume(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference signature (cryovit.py:36-40): x [B, C, D, h, w] -> clipped logits [B, 1, D, 16h, 16w]."""
+        outs = [self.segment_volume(x[b].to(self.device), want_probs=False)[0] for b in range(x.shape[0])]
+        return torch.stack(outs)[:, None]
+
+    @torch.inference_mode()
+    def forward(self, batch) -> torch.Tensor:
+        """Reference signature (cryovit.py:42-49): batch.tomo_batch [B, D, C, h, w] -> probabilities [B, D, H, W]."""
+        tb = batch.tomo_batch if hasattr(batch, "tomo_batch") else batch
+        outs = [self.segment_volume(tb[b].to(self.device).permute(1, 0, 2, 3).contiguous(), want_logits=False)[1]
+                for b in range(tb.shape[0])]
+        return torch.stack(outs)
+
+    __call__ = forward

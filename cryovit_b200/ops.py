@@ -105,6 +105,10 @@ def final_norm_writeout(x, gamma, beta, features, n_slices, tokens, first_patch_
 def features_to_ndhwc(features: torch.Tensor, out: torch.Tensor) -> None:
     C = features.shape[0]
     DHW = features.numel() // C
+    if features.dtype == F32:
+        _lib.call("cvit_features_f32_to_ndhwc_bf16", _chk(features, F32, "features"), _chk(out, BF16, "out"), C, DHW,
+                  _stream())
+        return
     _lib.call("cvit_features_to_ndhwc_bf16", _chk(features, F16, "features"), _chk(out, BF16, "out"), C, DHW, _stream())
 
 

@@ -117,6 +117,8 @@ int cvit_final_norm_writeout_f16(const float* x, const float* gamma, const float
 /* fp16 feature volume (C, D, h, w) -> bf16 channels-last (D, h, w, C): the head's input permute
  * (models/cryovit.py:45-46, datamodules/utils.py:105-107) fused with the dtype change. */
 int cvit_features_to_ndhwc_bf16(const void* features_f16, void* out_bf16, int64_t C, int64_t DHW, void* stream);
+/* Same from the fp32 (C, D, h, w) volume the reference's collate_fn hands to forward_volume. */
+int cvit_features_f32_to_ndhwc_bf16(const float* features_f32, void* out_bf16, int64_t C, int64_t DHW, void* stream);
 
 /* GroupNorm(G groups, eps) over a channels-last bf16 volume [DHW, C], statistics over (C/G) * DHW per group,
  * in fp32 (models/cryovit.py:69).  stats is a caller-provided fp32 scratch of 2*G floats (zeroed here). */
