@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the CryoVIT feature-extraction hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one synthetic tomogram: 128 slices of 512x512 uint8 -> DINOv2
+ViT-g/14-reg4 features, fp16 (1536, 128, 32, 32) (BASELINE.json configs[1]; slice batch 128 as in the reference's
+DinoFeaturesConfig.batch_size). Under torchrun each rank owns its own tomograms (BASELINE configs[2]: slices /
+tomograms shard across GPUs with no data-path collective), so scaling is weak.
+
+Numbers on the JSON line:
+  value      slices/s with the raw tomogram already resident in HBM (CUDA events, max over ranks)
+  e2e        slices/s through the public API extract_tomogram(np.uint8 host array) -> np.float16 host array,
+             pinned H2D of the tomogram and D2H of the features inside the timed region
+  roofline   the kernel with the largest share of the step, timed live with CUDA events inside the timed steps
+  cpu_baseline  the fp32 oracle (a port: the reference cannot be imported here) on the box's host cores, bounded
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL = "dinov2_vitg14_reg"
+D, H, W, BATCH = 128, 512, 512, 128
+T, NP, C, FH, HEADS, DEPTH = 1029, 1024, 1536, 4096, 24, 40
+# algorithmic work
+FLOP_PER_SLICE = DEPTH * T * (2 * C * 3 * C + 2 * C * C + 2 * C * 2 * FH + 2 * FH * C + 4 * T * C) + 2 * 588 * C * NP
+METRIC = "DINOv2 ViT-g/14 feature slices/sec"
+
+
+def measured_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (recipe: B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_slices_per_s(n_slices: int, sd=None, threads: int | None = None) -> tuple[float, int, float]:
+    """fp32 oracle (pre-processing + ViT-g forward + layout/cast) on the host cores over n_slices slices."""
+    import numpy as np
+    import torch
+
+    from cryovit_b200.vit import CONFIGS, random_state_dict
+    from oracle import dinov2 as odino
+    from oracle import extract as oextract
+    from oracle import preproc as opre
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = CONFIGS[MODEL]
+    if sd is None:
+        sd = random_state_dict(cfg, seed=0)
+    tomo = np.random.default_rng(1234).integers(0, 256, size=(n_slices, H, W), dtype=np.uint8)
+    model = odino.OracleDino(sd, cfg.num_heads)
+    t0 = time.perf_counter()
+    feats = oextract.dino_features(opre.dino_transform(opre.load_tomogram(tomo)), model, BATCH)
+    dt = time.perf_counter() - t0
+    assert feats.shape == (C, n_slices, 32, 32)
+    return n_slices / dt, cores, dt
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sample = 2
+    from cryovit_b200.vit import CONFIGS, random_state_dict
+
+    sd = random_state_dict(CONFIGS[MODEL], seed=0)
+    rates, cores = [], os.cpu_count()
+    for i in range(args.warmup_ref + args.steps_ref):
+        r, cores, _ = cpu_oracle_slices_per_s(sample, sd)
+        if i >= args.warmup_ref:
+            rates.append(r)
+    v = statistics.median(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": round(1e3 * sample / v, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ViT-g/14-reg4 features, {D}x{H}x{W} u8 tomogram, slice batch {BATCH}",
+                   "note": "each step is a bounded sample of the workload (2 slices)"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast"},
+        "e2e": {"value": round(v, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+class KernelTimer:
+    """CUDA-event timing of the ops of ONE transformer block per step, inside the timed region."""
+
+    def __init__(self, torch, ops_mod):
+        self.torch, self.ops, self.records, self.active = torch, ops_mod, {}, False
+        self._orig = {}
+
+    FLOPS = {
+        "linear_bias": lambda M: 2 * M * C * 3 * C,
+        "attention": lambda M: 4 * (M // T) * HEADS * T * T * 64,
+        "linear_swiglu": lambda M: 2 * M * C * 2 * FH,
+    }
+
+    def install(self):
+        for name in ("layernorm", "linear_bias", "attention", "linear_scale_residual", "linear_swiglu"):
+            orig = getattr(self.ops, name)
+            self._orig[name] = orig
+
+            def wrapped(*a, _orig=orig, _name=name, **k):
+                if not self.active:
+                    return _orig(*a, **k)
+                key = _name
+                if _name == "linear_scale_residual":
+                    key = "proj_scale_residual" if a[0].shape[1] == C else "w3_scale_residual"
+                s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = _orig(*a, **k)
+                e.record()
+                self.records.setdefault(key, []).append((s, e))
+                return r
+
+            setattr(self.ops, name, wrapped)
+
+    def summary(self, M: int) -> dict:
+        out = {}
+        flops = {"linear_bias": 2 * M * C * 3 * C, "attention": 4 * (M // T) * HEADS * T * T * 64,
+                 "linear_swiglu": 2 * M * C * 2 * FH, "proj_scale_residual": 2 * M * C * C,
+                 "w3_scale_residual": 2 * M * FH * C}
+        for k, evs in self.records.items():
+            ms = statistics.mean(s.elapsed_time(e) for s, e in evs)
+            out[k] = {"ms": ms, "flops": flops.get(k), "launches_timed": len(evs)}
+        return out
+
+
+def run_b200(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from cryovit_b200 import build, extract, ops
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200, random_state_dict
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    cfg = CONFIGS[MODEL]
+    sd = random_state_dict(cfg, seed=0)
+    model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda(local)
+    if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
+        sd = None  # free 4.5 GB per rank unless the CPU baseline leg needs it
+    g = torch.Generator().manual_seed(1234 + rank)
+    tomo_host = torch.randint(0, 256, (D, H, W), generator=g, dtype=torch.uint8).pin_memory()
+    tomo_dev = tomo_host.cuda(non_blocking=True)
+    feats = torch.empty(C, D, 32, 32, device="cuda", dtype=torch.float16)
+    host_out = torch.empty(C, D, 32, 32, dtype=torch.float16, pin_memory=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        extract.extract_tomogram_device(tomo_dev, model, BATCH, out=feats)
+
+    def step_e2e():
+        dev = tomo_host.cuda(non_blocking=True)
+        extract.extract_tomogram_device(dev, model, BATCH, out=feats)
+        host_out.copy_(feats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup, timer=None):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        launches0 = model.launches
+        if timer:
+            timer.active = True
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        if timer:
+            timer.active = False
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        sync_all()
+        return ms, model.launches - launches0
+
+    # time only one block's kernels per step (block 20) so the event overhead stays negligible
+    timer = KernelTimer(torch, ops)
+    blocks = model._w["blocks"]
+    timer.install()
+    orig_blocks = model._blocks
+
+    def blocks_with_probe(ws, B, T_):
+        x = timer.active
+        model._w["blocks"] = blocks[:20]
+        timer.active = False
+        orig_blocks(ws, B, T_)
+        model._w["blocks"] = blocks[20:21]
+        timer.active = x
+        orig_blocks(ws, B, T_)
+        timer.active = False
+        model._w["blocks"] = blocks[21:]
+        orig_blocks(ws, B, T_)
+        model._w["blocks"] = blocks
+        timer.active = x
+
+    model._blocks = blocks_with_probe
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_device, args.steps, args.warmup, timer)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    slices = world * D * args.steps
+    value = slices / (ms / 1e3)
+    e2e_value = slices / (ms_e2e / 1e3)
+    peaks, peak_src = measured_peaks()
+    ks = timer.summary(BATCH * T)
+    per_step_ms = ms / args.steps
+    shares = {k: v["ms"] * DEPTH / per_step_ms for k, v in ks.items()}
+    # layernorm runs twice per block
+    if "layernorm" in shares:
+        shares["layernorm"] *= 1.0
+    tensor_ks = {k: v for k, v in ks.items() if v["flops"]}
+    top = max(tensor_ks, key=lambda k: tensor_ks[k]["ms"] * (1 if k != "layernorm" else 0)) if tensor_ks else None
+    roof = None
+    if top:
+        tf = tensor_ks[top]["flops"] / tensor_ks[top]["ms"] / 1e9
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        roof = {"kernel": top, "bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(tf / peak, 4), "traffic": None, "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
+                "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
+    kernels = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
+                   "share_of_step": round(shares[k] * (2 if k == "layernorm" else 1), 4)} for k, v in ks.items()}
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"ViT-g/14-reg4 (random init, LayerScale 1.0) features of one {D}x{H}x{W} uint8 tomogram per GPU "
+                               f"per step, slice batch {BATCH}, output fp16 ({C},{D},32,32)",
+                   "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
+                   "parallelism": f"{world} independent replicas, tomograms sharded by rank, no collective"},
+        "model_tflops": round(value * FLOP_PER_SLICE / 1e12, 1),
+        "roofline": roof, "kernels": kernels, "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": "slices/s", "h2d_bytes_per_step": D * H * W,
+                "d2h_bytes_per_step": C * D * 32 * 32 * 2},
+        "gpu_launches": launches,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        del model
+        torch.cuda.empty_cache()
+        v, cores, dt = cpu_oracle_slices_per_s(2, sd)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
+                                "sample": f"2 slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast ({dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.steps_ref, args.warmup_ref = min(args.steps, 3), min(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
