@@ -30,6 +30,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_linear_swiglu_bf16": [P, I64, P, P, P, I64, I64, I64, I64, P],
     "cvit_linear_scale_residual_f32": [P, I64, P, P, P, P, I64, I64, I64, I64, P],
     "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],
+    "cvit_attention_fwd_bf16_mma_sync": [P, P, I64, I64, I64, I64, P],
     "cvit_final_norm_writeout_f16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "cvit_features_to_ndhwc_bf16": [P, P, I64, I64, P],
     "cvit_features_f32_to_ndhwc_bf16": [P, P, I64, I64, P],

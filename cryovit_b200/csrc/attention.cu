@@ -2,7 +2,7 @@
 // fp32 online softmax. Restates upstream MemEffAttention: softmax(q k^T / sqrt(64)) v with
 // q, k, v = qkv.reshape(B, N, 3, H, 64) (HF: modeling_dinov2_with_registers.py:202-256).
 //
-// Round-1 version: warp-level mma.sync (m16n8k16) tiles, cp.async double-buffered K/V, warp-level online
+// Legacy comparison kernel (the first round-1 version; the product path is attention_tcgen05.cu): warp-level mma.sync (m16n8k16) tiles, cp.async double-buffered K/V, warp-level online
 // softmax (quad shuffles). Each CTA owns BQ query rows of one (slice, head); each warp owns 16 rows.
 // The 5-token ragged tail (1029 = 16*64 + 5) is handled by masking keys >= T to -inf and clamping loads.
 #include "ptx.cuh"
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const __nv_bfloa
 
 using namespace cvit;
 
-extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+extern "C" int cvit_attention_fwd_bf16_mma_sync(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                        int64_t head_dim, void* stream) {
   if (!qkv || !out || n_slices <= 0 || tokens <= 0 || heads <= 0) {
     set_error("attention: bad arguments");

@@ -1,0 +1,314 @@
+// Flash-style self-attention of one ViT slice on tcgen05 / TMEM (head_dim 64, bf16 in/out, fp32 softmax).
+// Restates upstream MemEffAttention: softmax(q k^T / 8) v, q,k,v = qkv.reshape(B, N, 3, H, 64).
+//
+// One CTA = one 128-query tile of one (slice, head); two CTAs are co-resident per SM (80 KB smem, 256 TMEM
+// columns each) so one CTA's tensor-core phases overlap the other's softmax. 192 threads:
+//   warp 0    TMA producer: Q tile once, then (K, V) tiles of 128 keys through a 2-stage ring. The tensor map is
+//             3-D (column, token, slice) so tokens past the end of a slice are zero-filled, never the next slice.
+//   warp 1    MMA issuer:  S = Q K^T     (SS: both operands K-major in 128B-swizzled smem, N = 128 keys)
+//                          O += P V      (TS: P read from TMEM as packed bf16, V tile as an MN-major B operand)
+//   warps 2-5 softmax, one thread per query row (TMEM lane): pass A row max (with the lazy-rescale rule: O and l
+//             are only rescaled when the max grows by more than 2^8), pass B p = exp2(s*c - m*c) -> bf16 -> TMEM.
+// TMEM columns: S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256).
+// Ordering: the MMA warp issues PV(j) then S(j+1) and commits ONE barrier, so when the softmax warps see S(j+1)
+// they also know PV(j) has retired: O may be rescaled and P overwritten without further synchronisation.
+// The ragged tail (1029 = 8*128 + 5 keys) runs as an N=16 MMA with the 11 padding keys masked to -inf.
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace cvit {
+
+constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64;
+constexpr int FA_THREADS = 192;
+constexpr int FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr int FA_SMEM = 5 * FA_TILE_BYTES + 128 + 1024;
+constexpr int FA_TMEM_COLS = 256;
+constexpr uint32_t FA_COL_S = 0, FA_COL_P = 128, FA_COL_O = 192;
+
+struct FaArgs {
+  __nv_bfloat16* out;  // [B*T, C]
+  int T, heads, C;
+  float scale_log2e;   // head_dim^-0.5 * log2(e)
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = smem_base + FA_TILE_BYTES;      // 2 stages
+  const uint32_t sV = smem_base + 3 * FA_TILE_BYTES;  // 2 stages
+  const uint32_t sBar = smem_base + 5 * FA_TILE_BYTES;
+  const uint32_t bar_q = sBar, bar_kv_full = sBar + 8, bar_kv_empty = sBar + 24;
+  const uint32_t bar_s = sBar + 40, bar_p = sBar + 48, bar_o = sBar + 56, tmem_slot = sBar + 64;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, slice = blockIdx.z;
+  const int T = args.T;
+  const int n_tiles = (T + FA_BK - 1) / FA_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_kv_full + 8 * s, 1);
+      mbar_init(bar_kv_empty + 8 * s, 1);
+    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
+      mbar_arrive_expect_tx(bar_q, FA_TILE_BYTES);
+      tma_load_3d(sQ, &tmQKV, bar_q, cq, q0, slice);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(bar_kv_empty + 8 * s, ((j >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
+        tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
+        tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t tS = tmem_base + FA_COL_S, tP = tmem_base + FA_COL_P, tO = tmem_base + FA_COL_O;
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(FA_BQ, FA_D) | (1u << 16);  // B is MN-major
+      auto n_mma_of = [&](int j) {  // keys of tile j rounded up to the MMA granularity (16)
+        const int valid = min(FA_BK, T - j * FA_BK);
+        return (valid + 15) & ~15;
+      };
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(bar_kv_full + 8 * s, (j >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
+        const uint64_t qd = umma_smem_desc_kmajor<128>(sQ), kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+      };
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      umma_commit(bar_s);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(bar_p, j & 1);  // P(j) written, S(j) fully read
+        tcgen05_fence_after();
+        const int ksteps = n_mma_of(j) / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2 KB) of the V tile
+          const uint64_t vd = umma_smem_desc_mnmajor_sw128(sV + s * FA_TILE_BYTES + k * 2048, FA_TILE_BYTES);
+          umma_bf16_ts(tO, tP + 8 * k, vd, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
+        if (j + 1 < n_tiles) {
+          issue_s(j + 1);
+          umma_commit(bar_s);  // fires after PV(j) AND S(j+1)
+        } else {
+          umma_commit(bar_o);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps, thread == query row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool warp_active = q0 + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
+    const float c = args.scale_log2e;
+    float m = 0.f, l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tcgen05_fence_after();
+      if (warp_active) {
+        const int valid = min(FA_BK, T - j * FA_BK);
+        if (valid == FA_BK) {
+          // ---- pass A: row max
+          float mt = -INFINITY;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v[i]));
+          }
+          if (j == 0) {
+            m = mt;
+          } else {
+            const bool need = (mt - m) * c > 8.0f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
+#pragma unroll 1
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st_32x32(t_row + FA_COL_O + hh * 32, o);
+              }
+              l *= f;
+              if (need) m = mt;
+            }
+          }
+          // ---- pass B: probabilities
+          const float nmc = -m * c;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
+              l += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x16(t_row + FA_COL_P + ch * 16, pk);
+          }
+        } else {
+          // ---- ragged last tile: `valid` keys inside an N = roundup16(valid) MMA, 16-column chunks
+          const int nch = (valid + 15) >> 4;
+          float mt = -INFINITY;
+          for (int ch = 0; ch < nch; ++ch) {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + FA_COL_S + ch * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ch * 16 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+          }
+          if (j == 0) {
+            m = mt;
+          } else {
+            const bool need = (mt - m) * c > 8.0f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
+#pragma unroll 1
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st_32x32(t_row + FA_COL_O + hh * 32, o);
+              }
+              l *= f;
+              if (need) m = mt;
+            }
+          }
+          const float nmc = -m * c;
+          for (int ch = 0; ch < nch; ++ch) {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + FA_COL_S + ch * 16, v);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k0 = ch * 16 + 2 * i;
+              const float p0 = k0 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc)) : 0.f;
+              const float p1 = k0 + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc)) : 0.f;
+              l += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x8(t_row + FA_COL_P + ch * 8, pk);
+          }
+        }
+        tmem_st_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
+    mbar_wait(bar_o, 0);
+    tcgen05_fence_after();
+    if (warp_active) {
+      const int tok = q0 + row;
+      const float inv = 1.0f / l;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
+        tmem_ld_wait();
+        if (tok < T) {
+          uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)slice * T + tok) * args.C + head * FA_D + hh * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+            dst[i] = w;
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<FA_TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace cvit
+
+using namespace cvit;
+
+extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                                       int64_t head_dim, void* stream) {
+  if (!qkv || !out || n_slices <= 0 || tokens <= 0 || heads <= 0) {
+    set_error("attention: bad arguments");
+    return CVIT_ERR_INVALID;
+  }
+  if (head_dim != FA_D) {
+    set_error("attention: head_dim=%lld unsupported (64 only: every DINOv2 variant)", (long long)head_dim);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  if (n_slices > 65535 || heads > 65535) {
+    set_error("attention: grid dimension overflow (slices=%lld heads=%lld)", (long long)n_slices, (long long)heads);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  const int64_t C = heads * FA_D;
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)tokens, (uint64_t)n_slices};
+  uint64_t strides[3] = {0, (uint64_t)(3 * C) * 2, (uint64_t)tokens * 3 * C * 2};
+  uint32_t box[3] = {FA_D, FA_BK, 1};
+  int rc = encode_tmap(&tm, TmapDtype::BF16, 3, qkv, dims, strides, box, 128);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  FaArgs a;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.T = (int)tokens;
+  a.heads = (int)heads;
+  a.C = (int)C;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  dim3 grid((unsigned)((tokens + FA_BQ - 1) / FA_BQ), (unsigned)heads, (unsigned)n_slices);
+  attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
+  return check_launch("attention_tcgen05_kernel");
+}

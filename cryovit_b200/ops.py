@@ -89,8 +89,8 @@ def linear_scale_residual(a, w, bias, gamma, x) -> None:
               _chk(bias, F32, "bias"), _chk(gamma, F32, "gamma"), _chk(x, F32, "x"), x.stride(0), M, N, K, _stream())
 
 
-def attention(qkv, out, n_slices: int, tokens: int, heads: int) -> None:
-    _lib.call("cvit_attention_fwd_bf16", _chk(qkv, BF16, "qkv"), _chk(out, BF16, "out"), n_slices, tokens, heads, 64,
+def attention(qkv, out, n_slices: int, tokens: int, heads: int, legacy_mma_sync: bool = False) -> None:
+    _lib.call("cvit_attention_fwd_bf16_mma_sync" if legacy_mma_sync else "cvit_attention_fwd_bf16", _chk(qkv, BF16, "qkv"), _chk(out, BF16, "out"), n_slices, tokens, heads, 64,
               _stream())
 
 

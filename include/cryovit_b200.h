@@ -102,6 +102,9 @@ int cvit_linear_scale_residual_f32(const void* A, int64_t lda, const void* W, co
  * (upstream attention.py; HF:202-256).  qkv bf16 [n_slices * tokens, 3 * heads * 64]; head_dim must be 64. */
 int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                             int64_t head_dim, void* stream);
+/* Same contract on the legacy warp-level mma.sync path: kept only as an A/B comparison kernel for profiles. */
+int cvit_attention_fwd_bf16_mma_sync(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                                     int64_t head_dim, void* stream);
 
 /* Final LayerNorm + patch-token slice + (B, Np, C) -> (C, D, Np) transpose + fp16 cast, written into the
  * tomogram-wide feature volume at depth offset d0.  Replaces model.norm + x_norm_patchtokens (HF:477-503) and

@@ -93,16 +93,19 @@ def test_layernorm(cuda_lib, C):
     _close(out, ref, atol=1e-2, rtol=1e-2, what="layernorm")
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2)])
-def test_attention(cuda_lib, B, T, H):
+@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2), (3, 29, 2), (1, 128, 1), (1, 256, 2), (2, 261, 1)])
+@pytest.mark.parametrize("legacy", [False, True])
+@pytest.mark.parametrize("scale", [1.0, 6.0])
+def test_attention(cuda_lib, B, T, H, legacy, scale):
     from cryovit_b200 import ops
     C = H * 64
-    qkv = _rand(B * T, 3 * C, seed=1).bfloat16()
+    # scale 6 makes the logits span +-100: exercises the running-max / lazy-rescale path
+    qkv = (_rand(B * T, 3 * C, seed=1) * scale).bfloat16()
     out = torch.full((B * T, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    ops.attention(qkv, out, B, T, H)
+    ops.attention(qkv, out, B, T, H, legacy_mma_sync=legacy)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
-    _close(out, ref, atol=2e-2, rtol=2e-2, what="attention")
+    _close(out, ref, atol=2e-2 * scale, rtol=2e-2, what=f"attention legacy={legacy}")
 
 
 @pytest.mark.parametrize("D,H,W,u8", [(3, 64, 96, True), (2, 50, 70, True), (2, 64, 64, False)])

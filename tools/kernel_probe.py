@@ -56,7 +56,8 @@ def rec(name, ms, flops=None, bytes_=None):
 
 rec("qkv_gemm", timeit(lambda: ops.linear_bias(ln, qkv_w, qkv_b, qkv)), 2 * M * C * 3 * C)
 rec("cublas_qkv", timeit(lambda: torch.addmm(qkv_b.bfloat16(), ln, qkv_w.t())), 2 * M * C * 3 * C)
-rec("attention", timeit(lambda: ops.attention(qkv, attn, B, T, H)), 4 * B * H * T * T * 64)
+rec("attention_tcgen05", timeit(lambda: ops.attention(qkv, attn, B, T, H)), 4 * B * H * T * T * 64)
+rec("attention_mma_sync", timeit(lambda: ops.attention(qkv, attn, B, T, H, legacy_mma_sync=True)), 4 * B * H * T * T * 64)
 rec("proj_gemm_resid", timeit(lambda: ops.linear_scale_residual(attn, proj_w, proj_b, g, x)), 2 * M * C * C)
 rec("w12_swiglu", timeit(lambda: ops.linear_swiglu(ln, w12i, b12i, hidden)), 2 * M * C * 2 * Fh)
 rec("w3_gemm_resid", timeit(lambda: ops.linear_scale_residual(hidden, w3, b3, g, x)), 2 * M * Fh * C)
