@@ -132,16 +132,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       if (warp_active) {
         const int valid = min(FA_BK, T - j * FA_BK);
         if (valid == FA_BK) {
-          // ---- pass A: row max
-          float mt = -INFINITY;
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, v);
-            tmem_ld_wait();
+          // The whole 128-wide S row lives in registers: one TMEM read per tile, four loads in flight.
+          uint32_t v[128];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v[i]));
+          for (int ch = 0; ch < 4; ++ch)
+            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * ch]));
+          tmem_ld_wait();
+          // ---- row max (4 independent chains)
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            mx[0] = fmaxf(mx[0], __uint_as_float(v[i]));
+            mx[1] = fmaxf(mx[1], __uint_as_float(v[i + 1]));
+            mx[2] = fmaxf(mx[2], __uint_as_float(v[i + 2]));
+            mx[3] = fmaxf(mx[3], __uint_as_float(v[i + 3]));
           }
+          const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           if (j == 0) {
             m = mt;
           } else {
@@ -149,35 +155,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             if (__any_sync(0xffffffffu, need)) {
               const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
 #pragma unroll 1
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t o[32];
-                tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
+              for (int hh = 0; hh < 4; ++hh) {  // 16 columns at a time: the S row keeps 128 registers busy
+                uint32_t o[16];
+                tmem_ld_32x16(t_row + FA_COL_O + hh * 16, o);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                tmem_st_32x32(t_row + FA_COL_O + hh * 32, o);
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st_32x16(t_row + FA_COL_O + hh * 16, o);
               }
               l *= f;
               if (need) m = mt;
             }
           }
-          // ---- pass B: probabilities
+          // ---- probabilities, packed in place (element pair i -> register i), 4 partial row sums
           const float nmc = -m * c;
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
+          float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
-              l += p0 + p1;
-              pk[i] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x16(t_row + FA_COL_P + ch * 16, pk);
+          for (int i = 0; i < 64; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
+            ls[i & 3] += p0 + p1;
+            v[i] = pack_bf16x2(p0, p1);
           }
+          l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            tmem_st_32x16(t_row + FA_COL_P + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
         } else {
           // ---- ragged last tile: `valid` keys inside an N = roundup16(valid) MMA, 16-column chunks
           const int nch = (valid + 15) >> 4;

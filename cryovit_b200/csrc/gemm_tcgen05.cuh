@@ -2,12 +2,13 @@
 //
 //   D[M,N] = A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major, i.e. torch Linear weight layout)
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      TMA producer  (one lane): cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring
 //   warp 1      MMA issuer    (one lane): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
 //                                          two accumulator buffers so tile i+1 overlaps epilogue i
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 cols) -> warp-private swizzled smem transpose ->
-//               fused math -> row-contiguous vector stores
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, alternating 32-column chunks, so every scheduler
+//               has two epilogue warps to hide latency): tcgen05.ld (32 lanes x 32 cols) -> warp-private
+//               swizzled smem transpose -> fused math -> row-contiguous vector stores
 //
 // A-operand addressing modes:
 //   AMODE_ROWS  plain 2-D [M,K] matrix (ViT linears, 1x1x1 conv, transposed conv)
@@ -47,7 +48,8 @@ struct GemmArgs {
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
 
 template <int BN, int KSPAN>
 struct GemmCfg {
@@ -56,10 +58,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int STG_BYTES_PER_WARP = 8192;  // two 32x32 fp32 transpose buffers
+  static constexpr int STG_BYTES_PER_WARP = 4096;  // one 32x32 fp32 transpose buffer per epilogue warp
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * STG_BYTES_PER_WARP + 256 /*barriers*/ + 1024 /*align slack*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
   // every stage base must stay 1024-aligned for the swizzle pattern to line up with the descriptor
@@ -118,7 +120,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t sStg = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t sBar = sStg + 4 * Cfg::STG_BYTES_PER_WARP;
+  const uint32_t sBar = sStg + GEMM_EPI_WARPS * Cfg::STG_BYTES_PER_WARP;
   const uint32_t bar_full = sBar;                    // STAGES x 8B
   const uint32_t bar_empty = sBar + 8 * STAGES;      // STAGES x 8B
   const uint32_t bar_tfull = sBar + 16 * STAGES;     // 2 x 8B
@@ -145,7 +147,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_tempty + 8 * i, GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -230,107 +232,130 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const uint32_t stg = sStg + (warp - 2) * Cfg::STG_BYTES_PER_WARP;
+    const int ew = warp - 2;   // 0..7
+    const int q = warp & 3;    // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int half = ew >> 2;  // the two warps of a quarter take alternate 32-column chunks
+    const uint32_t stg = sStg + ew * Cfg::STG_BYTES_PER_WARP;
     int acc = 0;
     uint32_t acc_ph = 0;
     constexpr int NCHUNK = (EPI == EPI_BIAS_SWIGLU ? BN / 2 : BN) / 32;
+    const int jc = lane & 7;    // 16-byte column group handled by this lane on the way out
+    const int rsub = lane >> 3; // row within each group of 4 rows
+    // smem transpose addresses: thread == row on the way in, (4 rows x 8 column groups) per step on the way out
+    const uint32_t st_addr = stg + lane * 128;
+    const int st_sw = lane & 7;
+    auto stage_in = [&](const uint32_t (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + ((j ^ st_sw) << 4)), "r"(v[4 * j]),
+                     "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                     : "memory");
+      }
+    };
+    auto stage_out = [&](float4 (&x)[8]) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rsub;
+        const uint32_t addr = stg + r * 128 + ((jc ^ (r & 7)) << 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[it].x), "=f"(x[it].y), "=f"(x[it].z), "=f"(x[it].w) : "r"(addr));
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      // global row of this lane's first output row (rows mode: linear, 4 apart per step; conv mode: per row)
+      int grow_it[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) grow_it[it] = tile_row_to_global<AMODE>(t, q * 32 + it * 4 + rsub, args);
 #pragma unroll 1
-      for (int ch = 0; ch < NCHUNK; ++ch) {
+      for (int ch = half; ch < NCHUNK; ch += 2) {
         const int c0 = ch * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(t_acc + c0, v);
-        tmem_ld_wait();
-        // transpose through warp-private smem: thread = row on the way in, 8 lanes per row on the way out
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
-                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                       : "memory");
-        }
-        if (EPI == EPI_BIAS_SWIGLU) {
-          tmem_ld_32x32(t_acc + BN / 2 + c0, v);
+        const int ncol = t.n0 + c0 + jc * 4;  // first of this lane's 4 accumulator columns
+        float4 xs[8], ys[8];
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + c0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t addr = stg + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
-                         "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                         : "memory");
+          stage_in(v);
+          __syncwarp();
+          stage_out(xs);
+          if (EPI == EPI_BIAS_SWIGLU) {
+            __syncwarp();
+            tmem_ld_32x32(t_acc + BN / 2 + c0, v);
+            tmem_ld_wait();
+            stage_in(v);
+            __syncwarp();
+            stage_out(ys);
           }
+          __syncwarp();  // staging buffer free for the next chunk
         }
-        __syncwarp();
-        const int jc = lane & 7;             // 16-byte column group handled by this lane
-        const int ncol = t.n0 + c0 + jc * 4;  // first of its 4 accumulator columns
+        if (ncol >= args.n_valid) continue;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4, b4b = b4;
-        if (EPI != EPI_PATCH_EMBED || args.bias != nullptr)
-          if (args.bias) b4 = __ldg(reinterpret_cast<const float4*>(args.bias + ncol));
+        if (args.bias) b4 = __ldg(reinterpret_cast<const float4*>(args.bias + ncol));
         if (EPI == EPI_SCALE_RESIDUAL) g4 = __ldg(reinterpret_cast<const float4*>(args.gamma + ncol));
         if (EPI == EPI_BIAS_SWIGLU) b4b = __ldg(reinterpret_cast<const float4*>(args.bias + ncol + BN / 2));
-        float4 resid[8];
-        if (EPI == EPI_SCALE_RESIDUAL) {
-          // issue all residual loads up front so their latency overlaps (stores below may alias them)
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_SWIGLU) {
+          const int ocol = EPI == EPI_BIAS_SWIGLU ? (t.n0 >> 1) + c0 + jc * 4 : ncol;
+          __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(args.out) + ocol;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int grow = tile_row_to_global<AMODE>(t, q * 32 + it * 4 + (lane >> 3), args);
-            resid[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow >= 0)
-              resid[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(args.out) + (size_t)grow * args.ldo + ncol);
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3);
-          const uint32_t addr = stg + r * 128 + ((jc ^ (r & 7)) << 4);
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
-          const int grow = tile_row_to_global<AMODE>(t, q * 32 + r, args);
-          if (grow < 0 || ncol >= args.n_valid) continue;
-          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-            float o0 = x.x + b4.x, o1 = x.y + b4.y, o2 = x.z + b4.z, o3 = x.w + b4.w;
+            float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
             if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
-            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)grow * args.ldo + ncol) = pk;
-          } else if (EPI == EPI_BIAS_SWIGLU) {
-            float4 y;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(addr + 4096));
-            float o0 = silu(x.x + b4.x) * (y.x + b4b.x), o1 = silu(x.y + b4.y) * (y.y + b4b.y);
-            float o2 = silu(x.z + b4.z) * (y.z + b4b.z), o3 = silu(x.w + b4.w) * (y.w + b4b.w);
-            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-            const int ocol = (t.n0 >> 1) + c0 + jc * 4;
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)grow * args.ldo + ocol) = pk;
-          } else if (EPI == EPI_SCALE_RESIDUAL) {
-            float4* p = reinterpret_cast<float4*>(static_cast<float*>(args.out) + (size_t)grow * args.ldo + ncol);
-            float4 res = resid[it];
-            res.x += g4.x * (x.x + b4.x);
-            res.y += g4.y * (x.y + b4.y);
-            res.z += g4.z * (x.z + b4.z);
-            res.w += g4.w * (x.w + b4.w);
-            *p = res;
-          } else if (EPI == EPI_PATCH_EMBED) {
+            if (EPI == EPI_BIAS_SWIGLU) {
+              o0 = silu(o0) * (ys[it].x + b4b.x);
+              o1 = silu(o1) * (ys[it].y + b4b.y);
+              o2 = silu(o2) * (ys[it].z + b4b.z);
+              o3 = silu(o3) * (ys[it].w + b4b.w);
+            }
+            if (grow_it[it] >= 0)
+              *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+          }
+        } else if (EPI == EPI_SCALE_RESIDUAL) {
+          float* xbase = static_cast<float*>(args.out) + ncol;
+          float4 resid[8];
+          // issue all residual loads up front so their latency overlaps (the stores below may alias them)
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            resid[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow_it[it] >= 0) resid[it] = *reinterpret_cast<const float4*>(xbase + (size_t)grow_it[it] * args.ldo);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4 r = resid[it];
+            r.x += g4.x * (xs[it].x + b4.x);
+            r.y += g4.y * (xs[it].y + b4.y);
+            r.z += g4.z * (xs[it].z + b4.z);
+            r.w += g4.w * (xs[it].w + b4.w);
+            if (grow_it[it] >= 0) *reinterpret_cast<float4*>(xbase + (size_t)grow_it[it] * args.ldo) = r;
+          }
+        } else if (EPI == EPI_PATCH_EMBED) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = grow_it[it];
+            if (grow < 0) continue;
             const int b = grow / args.pe_np, p = grow - b * args.pe_np;
             const float4 tb = __ldg(reinterpret_cast<const float4*>(args.table + (size_t)p * args.N + ncol));
-            float4 o = make_float4(x.x + tb.x + b4.x, x.y + tb.y + b4.y, x.z + tb.z + b4.z, x.w + tb.w + b4.w);
+            const float4 o = make_float4(xs[it].x + tb.x + b4.x, xs[it].y + tb.y + b4.y, xs[it].z + tb.z + b4.z, xs[it].w + tb.w + b4.w);
             const size_t orow = (size_t)b * args.pe_tokens + args.pe_offset + p;
             *reinterpret_cast<float4*>(static_cast<float*>(args.out) + orow * args.ldo + ncol) = o;
-          } else if (EPI == EPI_CONVT_GELU) {
-            // column n = (i*2 + j) * c3 + co ; voxel grow = (d*H + h)*W + w -> out[d, 2h+i, 2w+j, co]
-            const int ij = ncol / args.c3, co = ncol - ij * args.c3;
-            const int si = ij >> 1, sj = ij & 1;
+          }
+        } else if (EPI == EPI_CONVT_GELU) {
+          // column n = (i*2 + j) * c3 + co ; voxel grow = (d*H + h)*W + w -> out[d, 2h+i, 2w+j, co]
+          const int ij = ncol / args.c3, co = ncol - ij * args.c3;
+          const int si = ij >> 1, sj = ij & 1;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = grow_it[it];
+            if (grow < 0) continue;
             const int w = grow % args.W, dh = grow / args.W;  // dh = d*H + h
             const size_t orow = ((size_t)(2 * dh + si) * (2 * args.W)) + 2 * w + sj;
-            float o0 = gelu_erf(x.x + b4.x), o1 = gelu_erf(x.y + b4.y), o2 = gelu_erf(x.z + b4.z), o3 = gelu_erf(x.w + b4.w);
-            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + orow * args.c3 + co) = pk;
+            const float o0 = gelu_erf(xs[it].x + b4.x), o1 = gelu_erf(xs[it].y + b4.y);
+            const float o2 = gelu_erf(xs[it].z + b4.z), o3 = gelu_erf(xs[it].w + b4.w);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + orow * args.c3 + co) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
           }
         }
-        __syncwarp();
       }
       // all TMEM reads of this accumulator buffer are complete (every tcgen05.ld was waited on)
       tcgen05_fence_before();
