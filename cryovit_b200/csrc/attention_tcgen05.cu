@@ -1,8 +1,10 @@
 // Flash-style self-attention of one ViT slice on tcgen05 / TMEM (head_dim 64, bf16 in/out, fp32 softmax).
 // Restates upstream MemEffAttention: softmax(q k^T / 8) v, q,k,v = qkv.reshape(B, N, 3, H, 64).
 //
-// One CTA = one 128-query tile of one (slice, head); two CTAs are co-resident per SM (80 KB smem, 256 TMEM
-// columns each) so one CTA's tensor-core phases overlap the other's softmax. 192 threads:
+// Persistent kernel: 2 CTAs per SM (80 KB smem, 256 TMEM columns each), each looping over work items
+// (slice, head, 128-query tile), query tile fastest so co-running CTAs share K/V in L2. The two co-resident CTAs
+// overlap one's tensor-core phases with the other's softmax; barrier phases, the K/V ring and the Q buffer run
+// across items, so the next item's Q and first K/V tiles are prefetched during the current item's tail. 192 threads:
 //   warp 0    TMA producer: Q tile once, then (K, V) tiles of 128 keys through a 2-stage ring. The tensor map is
 //             3-D (column, token, slice) so tokens past the end of a slice are zero-filled, never the next slice.
 //   warp 1    MMA issuer:  S = Q K^T     (SS: both operands K-major in 128B-swizzled smem, N = 128 keys)
@@ -27,7 +29,7 @@ constexpr uint32_t FA_COL_S = 0, FA_COL_P = 128, FA_COL_O = 192;
 
 struct FaArgs {
   __nv_bfloat16* out;  // [B*T, C]
-  int T, heads, C;
+  int T, heads, C, slices;
   float scale_log2e;   // head_dim^-0.5 * log2(e)
 };
 
@@ -40,13 +42,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   const uint32_t sV = smem_base + 3 * FA_TILE_BYTES;  // 2 stages
   const uint32_t sBar = smem_base + 5 * FA_TILE_BYTES;
   const uint32_t bar_q = sBar, bar_kv_full = sBar + 8, bar_kv_empty = sBar + 24;
-  const uint32_t bar_s = sBar + 40, bar_p = sBar + 48, bar_o = sBar + 56, tmem_slot = sBar + 64;
+  const uint32_t bar_s = sBar + 40, bar_p = sBar + 48, bar_o = sBar + 56, bar_q_empty = sBar + 64;
+  const uint32_t bar_o_empty = sBar + 72, tmem_slot = sBar + 80;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, slice = blockIdx.z;
   const int T = args.T;
-  const int n_tiles = (T + FA_BK - 1) / FA_BK;
+  const int n_tiles = (T + FA_BK - 1) / FA_BK;   // K/V tiles per item
+  const int n_qt = (T + FA_BQ - 1) / FA_BQ;      // query tiles per (slice, head)
+  const int total_items = n_qt * args.heads * args.slices;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -58,6 +62,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 4);
     mbar_init(bar_o, 1);
+    mbar_init(bar_q_empty, 1);
+    mbar_init(bar_o_empty, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
@@ -68,15 +74,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
 
   if (warp == 0) {
     if (lane == 0) {
-      const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
-      mbar_arrive_expect_tx(bar_q, FA_TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, bar_q, cq, q0, slice);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(bar_kv_empty + 8 * s, ((j >> 1) & 1) ^ 1u);
-        mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
-        tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
-        tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+      uint32_t kv_it = 0, k = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+        const int qt = item % n_qt, bh = item / n_qt;
+        const int head = bh % args.heads, slice = bh / args.heads;
+        const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
+        mbar_wait(bar_q_empty, (k & 1) ^ 1u);  // every S MMA of the previous item has retired
+        mbar_arrive_expect_tx(bar_q, FA_TILE_BYTES);
+        tma_load_3d(sQ, &tmQKV, bar_q, cq, qt * FA_BQ, slice);
+        for (int j = 0; j < n_tiles; ++j, ++kv_it) {
+          const uint32_t s = kv_it & 1;
+          mbar_wait(bar_kv_empty + 8 * s, ((kv_it >> 1) & 1) ^ 1u);
+          mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
+          tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
+          tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+        }
       }
     }
   } else if (warp == 1) {
@@ -87,34 +99,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         const int valid = min(FA_BK, T - j * FA_BK);
         return (valid + 15) & ~15;
       };
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(bar_kv_full + 8 * s, (j >> 1) & 1);
+      uint32_t kv_it = 0, tile_it = 0, k = 0;
+      auto issue_s = [&](int j, uint32_t kv) {
+        const uint32_t s = kv & 1;
+        mbar_wait(bar_kv_full + 8 * s, (kv >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
         const uint64_t qd = umma_smem_desc_kmajor<128>(sQ), kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc_s, k > 0);
+        for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(tS, qd + 2 * kk, kd + 2 * kk, idesc_s, kk > 0);
       };
-      mbar_wait(bar_q, 0);
-      issue_s(0);
-      umma_commit(bar_s);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(bar_p, j & 1);  // P(j) written, S(j) fully read
-        tcgen05_fence_after();
-        const int ksteps = n_mma_of(j) / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2 KB) of the V tile
-          const uint64_t vd = umma_smem_desc_mnmajor_sw128(sV + s * FA_TILE_BYTES + k * 2048, FA_TILE_BYTES);
-          umma_bf16_ts(tO, tP + 8 * k, vd, idesc_pv, (j | k) != 0);
-        }
-        umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
-        if (j + 1 < n_tiles) {
-          issue_s(j + 1);
-          umma_commit(bar_s);  // fires after PV(j) AND S(j+1)
-        } else {
-          umma_commit(bar_o);
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+        mbar_wait(bar_q, k & 1);
+        issue_s(0, kv_it);  // overlaps the previous item's epilogue: S was fully read when its last P was published
+        umma_commit(bar_s);
+        for (int j = 0; j < n_tiles; ++j, ++kv_it, ++tile_it) {
+          const uint32_t s = kv_it & 1;
+          mbar_wait(bar_p, tile_it & 1);  // P(j) written, S(j) fully read
+          if (j == 0) mbar_wait(bar_o_empty, (k & 1) ^ 1u);  // previous item's O has been read out of TMEM
+          tcgen05_fence_after();
+          const int ksteps = n_mma_of(j) / 16;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2 KB) of the V tile
+            const uint64_t vd = umma_smem_desc_mnmajor_sw128(sV + s * FA_TILE_BYTES + kk * 2048, FA_TILE_BYTES);
+            umma_bf16_ts(tO, tP + 8 * kk, vd, idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
+          if (j + 1 < n_tiles) {
+            issue_s(j + 1, kv_it + 1);
+            umma_commit(bar_s);  // fires after PV(j) AND S(j+1)
+          } else {
+            umma_commit(bar_q_empty);
+            umma_commit(bar_o);
+          }
         }
       }
     }
@@ -123,11 +140,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool warp_active = q0 + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
     const float c = args.scale_log2e;
+    uint32_t tile_it = 0, k = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+    const int qt = item % n_qt, bh = item / n_qt;
+    const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
     float m = 0.f, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(bar_s, j & 1);
+    for (int j = 0; j < n_tiles; ++j, ++tile_it) {
+      mbar_wait(bar_s, tile_it & 1);
       tcgen05_fence_after();
       if (warp_active) {
         const int valid = min(FA_BK, T - j * FA_BK);
@@ -236,30 +256,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       if (lane == 0) mbar_arrive(bar_p);
     }
     // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o, k & 1);
     tcgen05_fence_after();
+    uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
     if (warp_active) {
-      const int tok = q0 + row;
       const float inv = 1.0f / l;
-#pragma unroll 1
+#pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t o[32];
         tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
         tmem_ld_wait();
-        if (tok < T) {
-          uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)slice * T + tok) * args.C + head * FA_D + hh * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-            dst[i] = w;
-          }
-        }
+        for (int i = 0; i < 16; ++i)
+          ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
       }
     }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_o_empty);  // O has left TMEM: the next item's first PV may overwrite it
+    if (warp_active) {
+      const int tok = qt * FA_BQ + row;
+      if (tok < T) {
+        uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
+      }
+    }
+    }  // item loop
   }
 
   tcgen05_fence_before();
@@ -285,8 +308,8 @@ extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_sli
     set_error("attention: head_dim=%lld unsupported (64 only: every DINOv2 variant)", (long long)head_dim);
     return CVIT_ERR_UNSUPPORTED;
   }
-  if (n_slices > 65535 || heads > 65535) {
-    set_error("attention: grid dimension overflow (slices=%lld heads=%lld)", (long long)n_slices, (long long)heads);
+  if (((tokens + FA_BQ - 1) / FA_BQ) * heads * n_slices > 0x7fffffffll) {
+    set_error("attention: too many work items");
     return CVIT_ERR_UNSUPPORTED;
   }
   const int64_t C = heads * FA_D;
@@ -310,8 +333,11 @@ extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_sli
   a.T = (int)tokens;
   a.heads = (int)heads;
   a.C = (int)C;
+  a.slices = (int)n_slices;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
-  dim3 grid((unsigned)((tokens + FA_BQ - 1) / FA_BQ), (unsigned)heads, (unsigned)n_slices);
+  const int64_t items = ((tokens + FA_BQ - 1) / FA_BQ) * heads * n_slices;
+  int grid = 2 * num_sms();
+  if (grid > items) grid = (int)items;
   attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
   return check_launch("attention_tcgen05_kernel");
 }
