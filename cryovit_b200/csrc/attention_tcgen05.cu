@@ -1,171 +1,301 @@
 // Flash-style self-attention of one ViT slice on tcgen05 / TMEM (head_dim 64, bf16 in/out, fp32 softmax).
 // Restates upstream MemEffAttention: softmax(q k^T / 8) v, q,k,v = qkv.reshape(B, N, 3, H, 64).
 //
-// Persistent kernel: 2 CTAs per SM (80 KB smem, 256 TMEM columns each), each looping over work items
-// (slice, head, 128-query tile), query tile fastest so co-running CTAs share K/V in L2. The two co-resident CTAs
-// overlap one's tensor-core phases with the other's softmax; barrier phases, the K/V ring and the Q buffer run
-// across items, so the next item's Q and first K/V tiles are prefetched during the current item's tail. 192 threads:
-//   warp 0    TMA producer: Q tile once, then (K, V) tiles of 128 keys through a 2-stage ring. The tensor map is
-//             3-D (column, token, slice) so tokens past the end of a slice are zero-filled, never the next slice.
-//   warp 1    MMA issuer:  S = Q K^T     (SS: both operands K-major in 128B-swizzled smem, N = 128 keys)
-//                          O += P V      (TS: P read from TMEM as packed bf16, V tile as an MN-major B operand)
-//   warps 2-5 softmax, one thread per query row (TMEM lane): pass A row max (with the lazy-rescale rule: O and l
-//             are only rescaled when the max grows by more than 2^8), pass B p = exp2(s*c - m*c) -> bf16 -> TMEM.
-// TMEM columns: S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256).
-// Ordering: the MMA warp issues PV(j) then S(j+1) and commits ONE barrier, so when the softmax warps see S(j+1)
-// they also know PV(j) has retired: O may be rescaled and P overwritten without further synchronisation.
+// Persistent kernel, one CTA per SM, 384 threads = three warpgroups (registers are re-balanced between them with
+// setmaxnreg: the softmax warps hold a whole 128-wide S row and get 224, the control warpgroup keeps 56). A work item is (slice, head, 256 query rows) = two 128-row
+// query tiles A and B that share every K/V tile; items are walked query-pair fastest so co-running CTAs share
+// K/V in L2, and barrier phases / the K/V ring / the Q buffers run across items (the next item's Q and first K/V
+// tiles are prefetched during the current item's tail).
+//   warp 8     TMA producer: Q_A|Q_B once per item, (K, V) tiles of 128 keys through a 4-stage ring. The tensor map
+//              is 3-D (column, token, slice): tokens past the end of a slice are zero-filled, never the next slice.
+//   warp 9     MMA issuer:  S_g = Q_g K^T  (SS: K-major operands in 128B-swizzled smem, N = 128 keys)
+//                           O_g += P_g V   (TS: P read from TMEM as packed bf16, V tile as an MN-major B operand)
+//              It serves the two query tiles STRICTLY alternately (A, B, A, B ...): while group A runs its softmax
+//              the tensor core works for group B and vice versa. (Two independent CTAs per SM fell into lock-step
+//              instead: their MMAs interleaved and both softmax groups then waited together.)
+//   warps 0-3  softmax group A, warps 4-7 softmax group B (warps 10-11 idle); one thread per query row (TMEM lane = row). The whole
+//              128-wide S row is held in registers: row max (3-input FMNMX), lazy rescale (O and l are only
+//              rescaled when the max grows by more than 2^8), p = exp2(s*c - m*c) with packed f32x2 FMA/ADD
+//              -> bf16 pairs -> TMEM.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) | P_A [256,320) P_B [320,384) | O_A [384,448) O_B [448,512).
+// Ordering: for each group the MMA warp issues PV(j) then S(j+1) and commits ONE barrier, so when a softmax group
+// sees S(j+1) it also knows PV(j) retired: O may be rescaled and P overwritten without further synchronisation.
 // The ragged tail (1029 = 8*128 + 5 keys) runs as an N=16 MMA with the 11 padding keys masked to -inf.
+// A slice whose query-tile count is odd ends with an A-only item (group B idles through it).
 #include "ptx.cuh"
 #include "tmap.h"
 
 namespace cvit {
 
 constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64;
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 384;
+constexpr int FA_REGS_SOFTMAX = 200, FA_REGS_CONTROL = 104;  // setmaxnreg: 2 x 224 + 56 <= 512 per scheduler
+constexpr int FA_STAGES = 4;
 constexpr int FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int FA_SMEM = 5 * FA_TILE_BYTES + 128 + 1024;
-constexpr int FA_TMEM_COLS = 256;
-constexpr uint32_t FA_COL_S = 0, FA_COL_P = 128, FA_COL_O = 192;
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 256 + 1024;
+constexpr int FA_TMEM_COLS = 512;
+constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
+#ifndef FA_TURNS
+#define FA_TURNS 0  // 1: softmax groups take turns in their MUFU-bound exp phase (measured: no gain, one warp per scheduler cannot saturate MUFU)
+#endif
+
+// Optional per-phase cycle accounting (tools/fa_trace.py builds with -DCVIT_FA_TRACE): every warp accumulates the
+// cycles it spends in each phase in registers and dumps the totals once at the end (a timeline of global stores
+// proved too intrusive: it moved the phases it was measuring).
+#ifdef CVIT_FA_TRACE
+#define FA_PROF_DECL uint32_t prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t prof_last = clock()
+#define FA_PROF(slot) do { const uint32_t now_ = clock(); prof_acc[slot] += now_ - prof_last; prof_last = now_; } while (0)
+#define FA_PROF_DUMP(tiles) do { if (args.trace && blockIdx.x < 4 && lane == 0) {                      \
+    long long* d_ = args.trace + (blockIdx.x * 12 + warp) * 10;                                        \
+    for (int i_ = 0; i_ < 8; ++i_) d_[i_] = prof_acc[i_];                                              \
+    d_[8] = (tiles); } } while (0)
+#else
+#define FA_PROF_DECL do { } while (0)
+#define FA_PROF(slot) do { } while (0)
+#define FA_PROF_DUMP(tiles) do { } while (0)
+#endif
 
 struct FaArgs {
+  long long* trace;    // debug timeline (tools/fa_trace.py), normally null
   __nv_bfloat16* out;  // [B*T, C]
   int T, heads, C, slices;
   float scale_log2e;   // head_dim^-0.5 * log2(e)
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): halves the FMA-pipe issue slots of the softmax inner loop
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sK = smem_base + FA_TILE_BYTES;      // 2 stages
-  const uint32_t sV = smem_base + 3 * FA_TILE_BYTES;  // 2 stages
-  const uint32_t sBar = smem_base + 5 * FA_TILE_BYTES;
-  const uint32_t bar_q = sBar, bar_kv_full = sBar + 8, bar_kv_empty = sBar + 24;
-  const uint32_t bar_s = sBar + 40, bar_p = sBar + 48, bar_o = sBar + 56, bar_q_empty = sBar + 64;
-  const uint32_t bar_o_empty = sBar + 72, tmem_slot = sBar + 80;
+  const uint32_t sQ = smem_base;                                        // Q_A | Q_B
+  const uint32_t sK = smem_base + 2 * FA_TILE_BYTES;                    // FA_STAGES tiles
+  const uint32_t sV = smem_base + (2 + FA_STAGES) * FA_TILE_BYTES;      // FA_STAGES tiles
+  const uint32_t sBar = smem_base + (2 + 2 * FA_STAGES) * FA_TILE_BYTES;
+  const uint32_t bar_q = sBar, bar_q_empty = sBar + 8;
+  const uint32_t bar_kv_full = sBar + 16;                 // FA_STAGES x 8
+  const uint32_t bar_kv_empty = sBar + 16 + 8 * FA_STAGES;
+  const uint32_t bar_grp = sBar + 16 + 16 * FA_STAGES;    // per group (64 B apart): the five barriers below
+  constexpr uint32_t B_S = 0, B_SFREE = 8, B_P = 16, B_PV = 24, B_OEMPTY = 32;
+  const uint32_t bar_tok = bar_grp + 128;                 // 8 x 8: exp-phase turn of softmax warp w (see below)
+  const uint32_t tmem_slot = bar_tok + 64;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.T;
   const int n_tiles = (T + FA_BK - 1) / FA_BK;   // K/V tiles per item
   const int n_qt = (T + FA_BQ - 1) / FA_BQ;      // query tiles per (slice, head)
-  const int total_items = n_qt * args.heads * args.slices;
+  const int n_pairs = (n_qt + 1) >> 1;
+  const int total_items = n_pairs * args.heads * args.slices;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) {
+    mbar_init(bar_q_empty, 1);
+    for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
       mbar_init(bar_kv_empty + 8 * s, 1);
     }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_q_empty, 1);
-    mbar_init(bar_o_empty, 4);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar_grp + 64 * g + B_S, 1);       // MMA -> softmax: S_g(t) complete
+      mbar_init(bar_grp + 64 * g + B_SFREE, 4);   // softmax -> MMA: S_g(t) is in registers, the TMEM tile may be overwritten
+      mbar_init(bar_grp + 64 * g + B_P, 4);       // softmax -> MMA: P_g(t) stored
+      mbar_init(bar_grp + 64 * g + B_PV, 1);      // MMA -> softmax: PV_g(t) retired (P reusable, O consistent / complete)
+      mbar_init(bar_grp + 64 * g + B_OEMPTY, 4);  // softmax -> MMA: O_g read out, the next item may overwrite it
+    }
+    for (int w = 0; w < 8; ++w) mbar_init(bar_tok + 8 * w, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t kv_it = 0, k = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        const int qt = item % n_qt, bh = item / n_qt;
-        const int head = bh % args.heads, slice = bh / args.heads;
-        const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
-        mbar_wait(bar_q_empty, (k & 1) ^ 1u);  // every S MMA of the previous item has retired
-        mbar_arrive_expect_tx(bar_q, FA_TILE_BYTES);
-        tma_load_3d(sQ, &tmQKV, bar_q, cq, qt * FA_BQ, slice);
-        for (int j = 0; j < n_tiles; ++j, ++kv_it) {
-          const uint32_t s = kv_it & 1;
-          mbar_wait(bar_kv_empty + 8 * s, ((kv_it >> 1) & 1) ^ 1u);
-          mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
-          tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
-          tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA_REGS_CONTROL));
+    if (warp == 8) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        uint32_t kv_it = 0, k = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+          const int pair = item % n_pairs, bh = item / n_pairs;
+          const int head = bh % args.heads, slice = bh / args.heads;
+          const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
+          mbar_wait(bar_q_empty, (k & 1) ^ 1u);  // every S MMA of the previous item has retired
+          mbar_arrive_expect_tx(bar_q, 2 * FA_TILE_BYTES);
+          tma_load_3d(sQ, &tmQKV, bar_q, cq, (2 * pair) * FA_BQ, slice);
+          tma_load_3d(sQ + FA_TILE_BYTES, &tmQKV, bar_q, cq, (2 * pair + 1) * FA_BQ, slice);  // all-OOB box = zeros
+          for (int j = 0; j < n_tiles; ++j, ++kv_it) {
+            const uint32_t s = kv_it % FA_STAGES;
+            mbar_wait(bar_kv_empty + 8 * s, ((kv_it / FA_STAGES) & 1) ^ 1u);
+            mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
+            tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
+            tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t tS = tmem_base + FA_COL_S, tP = tmem_base + FA_COL_P, tO = tmem_base + FA_COL_O;
+    } else if (warp == 9) {
+      // ------------------------------------------------------------------ MMA issuer
+      // The whole warp walks the schedule (control flow stays warp-uniform, so descriptors live in uniform
+      // registers); one elected lane issues the MMAs and their commits. Issue order per K/V tile j:
+      //   S_A(j+1), S_B(j+1)   as soon as the group has pulled S(j) into registers  (runs under its softmax)
+      //   PV_A(j),  PV_B(j)    as soon as the group has stored P(j)
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(FA_BQ, FA_D) | (1u << 16);  // B is MN-major
       auto n_mma_of = [&](int j) {  // keys of tile j rounded up to the MMA granularity (16)
         const int valid = min(FA_BK, T - j * FA_BK);
         return (valid + 15) & ~15;
       };
-      uint32_t kv_it = 0, tile_it = 0, k = 0;
-      auto issue_s = [&](int j, uint32_t kv) {
-        const uint32_t s = kv & 1;
-        mbar_wait(bar_kv_full + 8 * s, (kv >> 1) & 1);
+      uint32_t kv_it = 0, k = 0;
+      uint32_t t_a = 0, t_b = 0, kg_a = 0, kg_b = 0;  // per-group tile / item counters (barrier phases)
+      FA_PROF_DECL;
+      auto issue_s = [&](int g, uint32_t tg, int j, uint32_t kv, bool last_s_of_item) {
+        const uint32_t bg = bar_grp + 64 * g;
+        FA_PROF(7);
+        if (tg > 0) mbar_wait(bg + B_SFREE, (tg - 1) & 1);
+        FA_PROF(0);  // wait: S tile free
+        const uint32_t s = kv % FA_STAGES;
+        mbar_wait(bar_kv_full + 8 * s, (kv / FA_STAGES) & 1);
         tcgen05_fence_after();
-        const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
-        const uint64_t qd = umma_smem_desc_kmajor<128>(sQ), kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
+        FA_PROF(1);  // wait: K/V landed
+        if (elect_one_sync()) {
+          const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
+          const uint64_t qd = umma_smem_desc_kmajor<128>(sQ + g * FA_TILE_BYTES);
+          const uint64_t kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
+          const uint32_t tS = tmem_base + FA_COL_S + g * 128;
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(tS, qd + 2 * kk, kd + 2 * kk, idesc_s, kk > 0);
+          for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(tS, qd + 2 * kk, kd + 2 * kk, idesc_s, kk > 0);
+          if (last_s_of_item) umma_commit(bar_q_empty);
+          umma_commit(bg + B_S);
+        }
+        __syncwarp();
+        FA_PROF(2);  // issue S
+      };
+      auto issue_pv = [&](int g, uint32_t tg, int j, uint32_t kv, uint32_t kg, bool release_kv) {
+        const uint32_t bg = bar_grp + 64 * g;
+        FA_PROF(7);
+        mbar_wait(bg + B_P, tg & 1);
+        FA_PROF(3);  // wait: P stored
+        if (j == 0) mbar_wait(bg + B_OEMPTY, (kg & 1) ^ 1u);  // previous item's O_g has been read out of TMEM
+        tcgen05_fence_after();
+        FA_PROF(4);  // wait: O drained
+        const uint32_t s = kv % FA_STAGES;
+        if (elect_one_sync()) {
+          const uint32_t tP = tmem_base + FA_COL_P + g * 64, tO = tmem_base + FA_COL_O + g * 64;
+          const uint64_t vd = umma_smem_desc_mnmajor_sw128(sV + s * FA_TILE_BYTES, FA_TILE_BYTES);
+          if (n_mma_of(j) == FA_BK) {
+#pragma unroll
+            for (int kk = 0; kk < FA_BK / 16; ++kk)  // 16 keys per step: 8 packed TMEM columns of P, 2 KB of the V tile
+              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, (j | kk) != 0);
+          } else {
+            for (int kk = 0; kk < n_mma_of(j) / 16; ++kk)
+              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, (j | kk) != 0);
+          }
+          if (release_kv) umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
+          umma_commit(bg + B_PV);
+        }
+        __syncwarp();
+        FA_PROF(5);  // issue PV
       };
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
+        const int pair = item % n_pairs;
+        const bool has_b = 2 * pair + 1 < n_qt;  // group B has a real query tile
         mbar_wait(bar_q, k & 1);
-        issue_s(0, kv_it);  // overlaps the previous item's epilogue: S was fully read when its last P was published
-        umma_commit(bar_s);
-        for (int j = 0; j < n_tiles; ++j, ++kv_it, ++tile_it) {
-          const uint32_t s = kv_it & 1;
-          mbar_wait(bar_p, tile_it & 1);  // P(j) written, S(j) fully read
-          if (j == 0) mbar_wait(bar_o_empty, (k & 1) ^ 1u);  // previous item's O has been read out of TMEM
-          tcgen05_fence_after();
-          const int ksteps = n_mma_of(j) / 16;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2 KB) of the V tile
-            const uint64_t vd = umma_smem_desc_mnmajor_sw128(sV + s * FA_TILE_BYTES + kk * 2048, FA_TILE_BYTES);
-            umma_bf16_ts(tO, tP + 8 * kk, vd, idesc_pv, (j | kk) != 0);
-          }
-          umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
+        issue_s(0, t_a, 0, kv_it, n_tiles == 1 && !has_b);
+        if (has_b) issue_s(1, t_b, 0, kv_it, n_tiles == 1);
+        for (int j = 0; j < n_tiles; ++j, ++kv_it) {
           if (j + 1 < n_tiles) {
-            issue_s(j + 1, kv_it + 1);
-            umma_commit(bar_s);  // fires after PV(j) AND S(j+1)
-          } else {
-            umma_commit(bar_q_empty);
-            umma_commit(bar_o);
+            issue_s(0, t_a + 1, j + 1, kv_it + 1, j + 2 == n_tiles && !has_b);
+            if (has_b) issue_s(1, t_b + 1, j + 1, kv_it + 1, j + 2 == n_tiles);
+          }
+          issue_pv(0, t_a, j, kv_it, kg_a, !has_b);
+          ++t_a;
+          if (has_b) {
+            issue_pv(1, t_b, j, kv_it, kg_b, true);
+            ++t_b;
           }
         }
+        ++kg_a;
+        if (has_b) ++kg_b;
       }
-    }
+      FA_PROF(7);
+      FA_PROF_DUMP(t_a + t_b);
+    }  // warps 10-11 idle
   } else {
     // ------------------------------------------------------------------ softmax warps, thread == query row
-    const int q = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA_REGS_SOFTMAX));
+    const int g = warp >> 2;        // 0 = group A, 1 = group B
+    const int q = warp & 3;         // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t tS = t_row + FA_COL_S + g * 128, tP = t_row + FA_COL_P + g * 64, tO = t_row + FA_COL_O + g * 64;
+    const uint32_t bg = bar_grp + 64 * g;
     const float c = args.scale_log2e;
-    uint32_t tile_it = 0, k = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-    const int qt = item % n_qt, bh = item / n_qt;
-    const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
-    float m = 0.f, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j, ++tile_it) {
-      mbar_wait(bar_s, tile_it & 1);
-      tcgen05_fence_after();
-      if (warp_active) {
+    const uint64_t c2 = pack_f32x2(c, c);
+    // exp-phase turn taking: warps q of group A and q of group B sit on the same scheduler and share its MUFU unit.
+    // Left alone the two groups drift into phase and fight for it, then idle together; passing a token back and
+    // forth (A, B, A, B ...) keeps one group's MUFU-bound exp phase under the other's TMEM/max/store phases.
+    const uint32_t my_tok = bar_tok + 8 * warp, peer_tok = bar_tok + 8 * (warp ^ 4);
+    uint32_t tile_it = 0, tok_it = 0;
+    if (g == 1 && lane == 0) mbar_arrive(peer_tok);  // group A goes first
+    FA_PROF_DECL;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int pair = item % n_pairs, bh = item / n_pairs;
+      const int qt = 2 * pair + g;
+      if (qt >= n_qt) continue;  // A-only item: the MMA warp skips this group too
+      const bool paired = FA_TURNS && 2 * pair + 1 < n_qt;  // both groups work on this item: take turns
+      const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
+      float m = 0.f, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++tile_it) {
+        FA_PROF(7);  // loop / epilogue
+        mbar_wait(bg + B_S, tile_it & 1);
+        tcgen05_fence_after();
+        FA_PROF(0);  // wait for S
         const int valid = min(FA_BK, T - j * FA_BK);
-        if (valid == FA_BK) {
+        bool pv_seen = j == 0;  // PV(j-1) known retired: O may be rescaled, P overwritten
+        if (warp_active && valid == FA_BK) {
           // The whole 128-wide S row lives in registers: one TMEM read per tile, four loads in flight.
           uint32_t v[128];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
-            tmem_ld_32x32(t_row + FA_COL_S + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * ch]));
+            tmem_ld_32x32(tS + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * ch]));
           tmem_ld_wait();
-          // ---- row max (4 independent chains)
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bg + B_SFREE);  // the MMA warp may start S(j+1) under this tile's softmax
+          FA_PROF(1);  // TMEM -> registers
+          // ---- row max: 4 independent chains of 3-input max
+          float mx[4];
 #pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            mx[0] = fmaxf(mx[0], __uint_as_float(v[i]));
-            mx[1] = fmaxf(mx[1], __uint_as_float(v[i + 1]));
-            mx[2] = fmaxf(mx[2], __uint_as_float(v[i + 2]));
-            mx[3] = fmaxf(mx[3], __uint_as_float(v[i + 3]));
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1]));
+#pragma unroll
+          for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              mx[u] = fmax3(mx[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
           }
           const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           if (j == 0) {
@@ -173,121 +303,171 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           } else {
             const bool need = (mt - m) * c > 8.0f;
             if (__any_sync(0xffffffffu, need)) {
+              mbar_wait(bg + B_PV, (tile_it - 1) & 1);
+              tcgen05_fence_after();
+              pv_seen = true;
               const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
 #pragma unroll 1
               for (int hh = 0; hh < 4; ++hh) {  // 16 columns at a time: the S row keeps 128 registers busy
                 uint32_t o[16];
-                tmem_ld_32x16(t_row + FA_COL_O + hh * 16, o);
+                tmem_ld_32x16(tO + hh * 16, o);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                tmem_st_32x16(t_row + FA_COL_O + hh * 16, o);
+                tmem_st_32x16(tO + hh * 16, o);
               }
               l *= f;
               if (need) m = mt;
             }
           }
-          // ---- probabilities, packed in place (element pair i -> register i), 4 partial row sums
+          FA_PROF(2);  // row max (+ rescale)
+          if (paired) mbar_wait(my_tok, tok_it & 1);
+          FA_PROF(3);  // wait for the exp turn
+          // ---- probabilities, packed in place (element pair i -> register i); packed FMA + packed row sums
           const float nmc = -m * c;
-          float ls[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+          uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc));
-            ls[i & 3] += p0 + p1;
+            const uint64_t t2 = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, nmc2);
+            float t0, t1;
+            unpack_f32x2(t2, t0, t1);
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+            ls[i & 3] = add_f32x2(ls[i & 3], pack_f32x2(p0, p1));
             v[i] = pack_bf16x2(p0, p1);
           }
-          l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          {
+            float a0, a1;
+            unpack_f32x2(add_f32x2(add_f32x2(ls[0], ls[1]), add_f32x2(ls[2], ls[3])), a0, a1);
+            l += a0 + a1;
+          }
+          if (paired) {
+            ++tok_it;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(peer_tok);
+          }
+          FA_PROF(4);  // exp
+          if (!pv_seen) {
+            mbar_wait(bg + B_PV, (tile_it - 1) & 1);
+            tcgen05_fence_after();
+          }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
-            tmem_st_32x16(t_row + FA_COL_P + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
+            tmem_st_32x16(tP + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
+          tmem_st_wait();
+          FA_PROF(5);  // wait PV(j-1), store P
         } else {
-          // ---- ragged last tile: `valid` keys inside an N = roundup16(valid) MMA, 16-column chunks
-          const int nch = (valid + 15) >> 4;
-          float mt = -INFINITY;
-          for (int ch = 0; ch < nch; ++ch) {
-            uint32_t v[16];
-            tmem_ld_32x16(t_row + FA_COL_S + ch * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (ch * 16 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+          if (paired) {  // keep the turn order moving: this tile has (next to) no exp work
+            mbar_wait(my_tok, tok_it & 1);
+            ++tok_it;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(peer_tok);
           }
-          if (j == 0) {
-            m = mt;
-          } else {
-            const bool need = (mt - m) * c > 8.0f;
-            if (__any_sync(0xffffffffu, need)) {
-              const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
+          if (!pv_seen) {
+            mbar_wait(bg + B_PV, (tile_it - 1) & 1);
+            tcgen05_fence_after();
+          }
+          if (warp_active) {
+            // ---- ragged last tile: `valid` keys inside an N = roundup16(valid) MMA, 16-column chunks
+            const int nch = (valid + 15) >> 4;
+            float mt = -INFINITY;
+            for (int ch = 0; ch < nch; ++ch) {
+              uint32_t v[16];
+              tmem_ld_32x16(tS + ch * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ch * 16 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+            }
+            if (j == 0) {
+              m = mt;
+            } else {
+              const bool need = (mt - m) * c > 8.0f;
+              if (__any_sync(0xffffffffu, need)) {
+                const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
 #pragma unroll 1
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t o[32];
-                tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
-                tmem_ld_wait();
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t o[32];
+                  tmem_ld_32x32(tO + hh * 32, o);
+                  tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                tmem_st_32x32(t_row + FA_COL_O + hh * 32, o);
+                  for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                  tmem_st_32x32(tO + hh * 32, o);
+                }
+                l *= f;
+                if (need) m = mt;
               }
-              l *= f;
-              if (need) m = mt;
             }
-          }
-          const float nmc = -m * c;
-          for (int ch = 0; ch < nch; ++ch) {
-            uint32_t v[16];
-            tmem_ld_32x16(t_row + FA_COL_S + ch * 16, v);
-            tmem_ld_wait();
-            uint32_t pk[8];
+            const float nmc = -m * c;
+            for (int ch = 0; ch < nch; ++ch) {
+              uint32_t v[16];
+              tmem_ld_32x16(tS + ch * 16, v);
+              tmem_ld_wait();
+              uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int k0 = ch * 16 + 2 * i;
-              const float p0 = k0 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc)) : 0.f;
-              const float p1 = k0 + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc)) : 0.f;
-              l += p0 + p1;
-              pk[i] = pack_bf16x2(p0, p1);
+              for (int i = 0; i < 8; ++i) {
+                const int k0 = ch * 16 + 2 * i;
+                const float p0 = k0 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc)) : 0.f;
+                const float p1 = k0 + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc)) : 0.f;
+                l += p0 + p1;
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              tmem_st_32x8(tP + ch * 8, pk);
             }
-            tmem_st_32x8(t_row + FA_COL_P + ch * 8, pk);
+            tmem_st_wait();
           }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bg + B_SFREE);
         }
-        tmem_st_wait();
+        tcgen05_fence_before();
+#ifdef FA_PROF_SPLIT
+        FA_PROF(6);
+        __syncwarp();
+        FA_PROF(3);
+        if (lane == 0) mbar_arrive(bg + B_P);
+        FA_PROF(2);
+#else
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bg + B_P);
+        FA_PROF(6);  // publish P
+#endif
+      }
+      // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
+      mbar_wait(bg + B_PV, (tile_it - 1) & 1);  // the item's last PV retired: O complete
+      tcgen05_fence_after();
+      uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
+      if (warp_active) {
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t o[32];
+          tmem_ld_32x32(tO + hh * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-    }
-    // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
-    mbar_wait(bar_o, k & 1);
-    tcgen05_fence_after();
-    uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
-    if (warp_active) {
-      const float inv = 1.0f / l;
+      if (lane == 0) mbar_arrive(bg + B_OEMPTY);  // O has left TMEM: the next item's first PV may overwrite it
+      if (warp_active) {
+        const int tok = qt * FA_BQ + row;
+        if (tok < T) {
+          uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t o[32];
-        tmem_ld_32x32(t_row + FA_COL_O + hh * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
+        }
       }
-    }
-    tcgen05_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_o_empty);  // O has left TMEM: the next item's first PV may overwrite it
-    if (warp_active) {
-      const int tok = qt * FA_BQ + row;
-      if (tok < T) {
-        uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
-      }
-    }
     }  // item loop
+    FA_PROF(7);
+    FA_PROF_DUMP(tile_it);
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<FA_TMEM_COLS>(tmem_base);
@@ -297,6 +477,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
 }  // namespace cvit
 
 using namespace cvit;
+
+#ifdef CVIT_FA_TRACE
+static long long* g_fa_trace = nullptr;
+extern "C" void cvit_fa_set_trace(long long* p) { g_fa_trace = p; }
+#endif
 
 extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                        int64_t head_dim, void* stream) {
@@ -329,14 +514,20 @@ extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_sli
     configured = true;
   }
   FaArgs a;
+#ifdef CVIT_FA_TRACE
+  a.trace = g_fa_trace;
+#else
+  a.trace = nullptr;
+#endif
   a.out = static_cast<__nv_bfloat16*>(out);
   a.T = (int)tokens;
   a.heads = (int)heads;
   a.C = (int)C;
   a.slices = (int)n_slices;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
-  const int64_t items = ((tokens + FA_BQ - 1) / FA_BQ) * heads * n_slices;
-  int grid = 2 * num_sms();
+  const int n_qt = (int)((tokens + FA_BQ - 1) / FA_BQ);
+  const int64_t items = (int64_t)((n_qt + 1) / 2) * heads * n_slices;
+  int grid = num_sms();
   if (grid > items) grid = (int)items;
   attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
   return check_launch("attention_tcgen05_kernel");

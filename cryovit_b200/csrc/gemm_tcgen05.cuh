@@ -191,7 +191,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the tile / k-chunk schedule so control flow stays warp-uniform and the descriptors live
+    // in uniform registers; one elected lane issues the MMAs and commits. (Issuing from a divergent `lane == 0`
+    // region cost ~90 cycles per tcgen05.mma: every operand went through R2UR and a per-lane ELECT loop.)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -213,19 +216,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int kc = 0; kc < k_chunks; ++kc) {
             mbar_wait(bar_full + 8 * s, ph);
             tcgen05_fence_after();
-            const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES);
-            const uint64_t bdesc = umma_smem_desc_kmajor<KSPAN>(sB + s * Cfg::B_BYTES);
+            if (elect_one_sync()) {
+              const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES);
+              const uint64_t bdesc = umma_smem_desc_kmajor<KSPAN>(sB + s * Cfg::B_BYTES);
 #pragma unroll
-            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+              }
+              umma_commit(bar_empty + 8 * s);  // smem slot reusable once these MMAs retire
             }
-            umma_commit(bar_empty + 8 * s);  // smem slot reusable once these MMAs retire
+            __syncwarp();
+            accumulate = 1;
             if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
         }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        if (elect_one_sync()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1u;
       }

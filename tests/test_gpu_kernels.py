@@ -93,7 +93,8 @@ def test_layernorm(cuda_lib, C):
     _close(out, ref, atol=1e-2, rtol=1e-2, what="layernorm")
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2), (3, 29, 2), (1, 128, 1), (1, 256, 2), (2, 261, 1)])
+@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2), (3, 29, 2), (1, 128, 1), (1, 256, 2), (2, 261, 1),
+                                   (16, 300, 8), (6, 1029, 6), (40, 120, 8)])  # more work items than SMs: persistent path
 @pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("scale", [1.0, 6.0])
 def test_attention(cuda_lib, B, T, H, legacy, scale):
