@@ -1,25 +1,24 @@
 // Flash-style self-attention of one ViT slice on tcgen05 / TMEM (head_dim 64, bf16 in/out, fp32 softmax).
 // Restates upstream MemEffAttention: softmax(q k^T / 8) v, q,k,v = qkv.reshape(B, N, 3, H, 64).
 //
-// Persistent kernel, one CTA per SM, 384 threads = three warpgroups (registers are re-balanced between them with
-// setmaxnreg: the softmax warps hold a whole 128-wide S row and get 224, the control warpgroup keeps 56). A work item is (slice, head, 256 query rows) = two 128-row
-// query tiles A and B that share every K/V tile; items are walked query-pair fastest so co-running CTAs share
-// K/V in L2, and barrier phases / the K/V ring / the Q buffers run across items (the next item's Q and first K/V
-// tiles are prefetched during the current item's tail).
-//   warp 8     TMA producer: Q_A|Q_B once per item, (K, V) tiles of 128 keys through a 4-stage ring. The tensor map
-//              is 3-D (column, token, slice): tokens past the end of a slice are zero-filled, never the next slice.
-//   warp 9     MMA issuer:  S_g = Q_g K^T  (SS: K-major operands in 128B-swizzled smem, N = 128 keys)
-//                           O_g += P_g V   (TS: P read from TMEM as packed bf16, V tile as an MN-major B operand)
-//              It serves the two query tiles STRICTLY alternately (A, B, A, B ...): while group A runs its softmax
-//              the tensor core works for group B and vice versa. (Two independent CTAs per SM fell into lock-step
-//              instead: their MMAs interleaved and both softmax groups then waited together.)
-//   warps 0-3  softmax group A, warps 4-7 softmax group B (warps 10-11 idle); one thread per query row (TMEM lane = row). The whole
-//              128-wide S row is held in registers: row max (3-input FMNMX), lazy rescale (O and l are only
-//              rescaled when the max grows by more than 2^8), p = exp2(s*c - m*c) with packed f32x2 FMA/ADD
-//              -> bf16 pairs -> TMEM.
+// Persistent kernel, one CTA per SM, 512 threads = four warpgroups; registers are re-balanced with setmaxnreg
+// (softmax warps hold a whole 128-wide S row). A work item is (slice, head, 256 query rows) = two 128-row query
+// tiles A and B that share every K/V tile; items are walked query-pair fastest so co-running CTAs share K/V in L2.
+// Barrier phases, the K/V ring and the S/P/O buffers run across items: the tile stream never drains at an item end.
+//   warps 0-3   softmax group A, warps 4-7 softmax group B; one thread per query row (TMEM lane = row). The whole
+//               128-wide S row is held in registers: row max (3-input FMNMX), lazy rescale (O and l are only rescaled
+//               when the max grows by more than 2^8), p = exp2(s*c - m*c) with packed f32x2 FMA/ADD -> bf16 pairs
+//               -> TMEM. P(j) is published to the MMA warp only after the loads of S(j+1) were issued, so the TMEM
+//               store drain (300-600 cycles when the tensor pipe is busy) is off the critical path.
+//   warps 8-11  epilogue: O_g / l -> bf16 -> global, while the softmax warps already run the next item.
+//   warp 12     TMA producer: Q_A|Q_B once per item, (K, V) tiles of 128 keys through a 4-stage ring. The tensor map
+//               is 3-D (column, token, slice): tokens past the end of a slice are zero-filled, never the next slice.
+//   warps 13,14 MMA issuers, one per query tile (whole warp walks the schedule, one elected lane issues):
+//                   S_g = Q_g K^T  (SS: K-major operands in 128B-swizzled smem, N = 128 keys)
+//                   O_g += P_g V   (TS: P read from TMEM as packed bf16, V tile as an MN-major B operand)
+//               Each issues S_g(t+1) as soon as its group has pulled S_g(t) into registers (so the next S is ready
+//               before the softmax of the current one ends), then PV_g(t) when P_g(t) is published.
 // TMEM (512 columns): S_A [0,128) S_B [128,256) | P_A [256,320) P_B [320,384) | O_A [384,448) O_B [448,512).
-// Ordering: for each group the MMA warp issues PV(j) then S(j+1) and commits ONE barrier, so when a softmax group
-// sees S(j+1) it also knows PV(j) retired: O may be rescaled and P overwritten without further synchronisation.
 // The ragged tail (1029 = 8*128 + 5 keys) runs as an N=16 MMA with the 11 padding keys masked to -inf.
 // A slice whose query-tile count is odd ends with an A-only item (group B idles through it).
 #include "ptx.cuh"
@@ -28,16 +27,14 @@
 namespace cvit {
 
 constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64;
-constexpr int FA_THREADS = 384;
-constexpr int FA_REGS_SOFTMAX = 200, FA_REGS_CONTROL = 104;  // setmaxnreg: 2 x 224 + 56 <= 512 per scheduler
+constexpr int FA_THREADS = 512;
+// setmaxnreg budget per scheduler (one warp of each warpgroup): 2 x softmax + epilogue + control <= 512
+constexpr int FA_REGS_SOFTMAX = 184, FA_REGS_EPILOGUE = 72, FA_REGS_CONTROL = 72;
 constexpr int FA_STAGES = 4;
 constexpr int FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 256 + 1024;
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 2048 /* row sums */ + 512 /* barriers */ + 1024;
 constexpr int FA_TMEM_COLS = 512;
 constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
-#ifndef FA_TURNS
-#define FA_TURNS 0  // 1: softmax groups take turns in their MUFU-bound exp phase (measured: no gain, one warp per scheduler cannot saturate MUFU)
-#endif
 
 // Optional per-phase cycle accounting (tools/fa_trace.py builds with -DCVIT_FA_TRACE): every warp accumulates the
 // cycles it spends in each phase in registers and dumps the totals once at the end (a timeline of global stores
@@ -46,7 +43,7 @@ constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
 #define FA_PROF_DECL uint32_t prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t prof_last = clock()
 #define FA_PROF(slot) do { const uint32_t now_ = clock(); prof_acc[slot] += now_ - prof_last; prof_last = now_; } while (0)
 #define FA_PROF_DUMP(tiles) do { if (args.trace && blockIdx.x < 4 && lane == 0) {                      \
-    long long* d_ = args.trace + (blockIdx.x * 12 + warp) * 10;                                        \
+    long long* d_ = args.trace + (blockIdx.x * 16 + warp) * 10;                                        \
     for (int i_ = 0; i_ < 8; ++i_) d_[i_] = prof_acc[i_];                                              \
     d_[8] = (tiles); } } while (0)
 #else
@@ -54,15 +51,14 @@ constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
 #define FA_PROF(slot) do { } while (0)
 #define FA_PROF_DUMP(tiles) do { } while (0)
 #endif
-
 struct FaArgs {
-  long long* trace;    // debug timeline (tools/fa_trace.py), normally null
+  long long* trace;    // debug accounting (tools/fa_trace.py), normally null
   __nv_bfloat16* out;  // [B*T, C]
   int T, heads, C, slices;
   float scale_log2e;   // head_dim^-0.5 * log2(e)
 };
 
-// packed fp32 pairs (Blackwell FFMA2 / FADD2): halves the FMA-pipe issue slots of the softmax inner loop
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): halves the issue slots of the softmax inner loop
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -94,14 +90,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   const uint32_t sQ = smem_base;                                        // Q_A | Q_B
   const uint32_t sK = smem_base + 2 * FA_TILE_BYTES;                    // FA_STAGES tiles
   const uint32_t sV = smem_base + (2 + FA_STAGES) * FA_TILE_BYTES;      // FA_STAGES tiles
-  const uint32_t sBar = smem_base + (2 + 2 * FA_STAGES) * FA_TILE_BYTES;
+  const uint32_t sL = smem_base + (2 + 2 * FA_STAGES) * FA_TILE_BYTES;  // row sums: [item parity][group][128] fp32
+  const uint32_t sBar = sL + 2048;
   const uint32_t bar_q = sBar, bar_q_empty = sBar + 8;
   const uint32_t bar_kv_full = sBar + 16;                 // FA_STAGES x 8
   const uint32_t bar_kv_empty = sBar + 16 + 8 * FA_STAGES;
-  const uint32_t bar_grp = sBar + 16 + 16 * FA_STAGES;    // per group (64 B apart): the five barriers below
-  constexpr uint32_t B_S = 0, B_SFREE = 8, B_P = 16, B_PV = 24, B_OEMPTY = 32;
-  const uint32_t bar_tok = bar_grp + 128;                 // 8 x 8: exp-phase turn of softmax warp w (see below)
-  const uint32_t tmem_slot = bar_tok + 64;
+  const uint32_t bar_grp = sBar + 16 + 16 * FA_STAGES;    // per group (64 B apart): the seven barriers below
+  constexpr uint32_t B_S = 0, B_SFREE = 8, B_P = 16, B_PV = 24, B_OFULL = 32, B_OEMPTY = 40, B_LFULL = 48;
+  const uint32_t tmem_slot = bar_grp + 128;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,34 +106,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   const int n_qt = (T + FA_BQ - 1) / FA_BQ;      // query tiles per (slice, head)
   const int n_pairs = (n_qt + 1) >> 1;
   const int total_items = n_pairs * args.heads * args.slices;
+  // K/V tiles are walked ragged-tile-first: the short tile's P is published at once and its PV retires under the
+  // first full tile (walked last, the single P buffer would stall the softmax behind PV of the tile before it).
+  const bool ragged = (T % FA_BK) != 0;
+  auto kv_tile = [&](int j) { return ragged ? (j == 0 ? n_tiles - 1 : j - 1) : j; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
-    mbar_init(bar_q_empty, 1);
+    mbar_init(bar_q_empty, 2);  // one commit per group (group A commits twice on A-only items)
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
-      mbar_init(bar_kv_empty + 8 * s, 1);
+      mbar_init(bar_kv_empty + 8 * s, 2);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(bar_grp + 64 * g + B_S, 1);       // MMA -> softmax: S_g(t) complete
       mbar_init(bar_grp + 64 * g + B_SFREE, 4);   // softmax -> MMA: S_g(t) is in registers, the TMEM tile may be overwritten
       mbar_init(bar_grp + 64 * g + B_P, 4);       // softmax -> MMA: P_g(t) stored
-      mbar_init(bar_grp + 64 * g + B_PV, 1);      // MMA -> softmax: PV_g(t) retired (P reusable, O consistent / complete)
-      mbar_init(bar_grp + 64 * g + B_OEMPTY, 4);  // softmax -> MMA: O_g read out, the next item may overwrite it
+      mbar_init(bar_grp + 64 * g + B_PV, 1);      // MMA -> softmax: PV_g(t) retired (P reusable, O consistent)
+      mbar_init(bar_grp + 64 * g + B_OFULL, 1);   // MMA -> epilogue: the item's last PV_g retired, O_g complete
+      mbar_init(bar_grp + 64 * g + B_OEMPTY, 4);  // epilogue -> MMA: O_g read out, the next item may overwrite it
+      mbar_init(bar_grp + 64 * g + B_LFULL, 4);   // softmax -> epilogue: row sums of the item are in smem
     }
-    for (int w = 0; w < 8; ++w) mbar_init(bar_tok + 8 * w, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
+  if (warp == 13) tmem_alloc<FA_TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if (warp >= 8) {
+  if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA_REGS_CONTROL));
-    if (warp == 8) {
+    if (warp == 12) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
         uint32_t kv_it = 0, k = 0;
@@ -153,27 +154,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             const uint32_t s = kv_it % FA_STAGES;
             mbar_wait(bar_kv_empty + 8 * s, ((kv_it / FA_STAGES) & 1) ^ 1u);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * FA_TILE_BYTES);
-            tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, j * FA_BK, slice);
-            tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, j * FA_BK, slice);
+            tma_load_3d(sK + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, ck, kv_tile(j) * FA_BK, slice);
+            tma_load_3d(sV + s * FA_TILE_BYTES, &tmQKV, bar_kv_full + 8 * s, cv, kv_tile(j) * FA_BK, slice);
           }
         }
       }
-    } else if (warp == 9) {
-      // ------------------------------------------------------------------ MMA issuer
-      // The whole warp walks the schedule (control flow stays warp-uniform, so descriptors live in uniform
-      // registers); one elected lane issues the MMAs and their commits. Issue order per K/V tile j:
-      //   S_A(j+1), S_B(j+1)   as soon as the group has pulled S(j) into registers  (runs under its softmax)
-      //   PV_A(j),  PV_B(j)    as soon as the group has stored P(j)
+    } else if (warp <= 14) {
+      // ------------------------------------------------------------------ MMA issuers: warp 13 group A, warp 14 group B
+      // One issuer warp per query tile: each walks its own stream  S_g(t+1), PV_g(t), S_g(t+2), PV_g(t+1) ...  and
+      // never waits on the other group's softmax (a single issuer serving both in a fixed order coupled the two
+      // groups through its blocking waits). tcgen05.commit only tracks the issuing thread's own MMAs, which is
+      // exactly the per-group completion the softmax warps need. The whole warp walks the schedule (warp-uniform
+      // control flow keeps the descriptors in uniform registers); one elected lane issues.
+      // Shared barriers take one arrival per group: kv_empty (count 2) and q_empty (count 2); on A-only items
+      // warp 13 commits twice, and warp 14 still waits every q / kv_full phase in order (a waiter that skipped
+      // phases would alias on the parity bit).
+      const int g = warp - 13;
+      const uint32_t bg = bar_grp + 64 * g;
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(FA_BQ, FA_D) | (1u << 16);  // B is MN-major
-      auto n_mma_of = [&](int j) {  // keys of tile j rounded up to the MMA granularity (16)
-        const int valid = min(FA_BK, T - j * FA_BK);
+      auto n_mma_of = [&](int j) {  // keys of the j-th walked tile rounded up to the MMA granularity (16)
+        const int valid = min(FA_BK, T - kv_tile(j) * FA_BK);
         return (valid + 15) & ~15;
       };
-      uint32_t kv_it = 0, k = 0;
-      uint32_t t_a = 0, t_b = 0, kg_a = 0, kg_b = 0;  // per-group tile / item counters (barrier phases)
+      auto paired = [&](int item) { return 2 * (item % n_pairs) + 1 < n_qt; };  // group B has a real query tile
       FA_PROF_DECL;
-      auto issue_s = [&](int g, uint32_t tg, int j, uint32_t kv, bool last_s_of_item) {
-        const uint32_t bg = bar_grp + 64 * g;
+      // S_g for the tile with per-group index tg: walked tile j of the item whose ring position is kv
+      auto issue_s = [&](uint32_t tg, int j, uint32_t kv, bool last_s_of_item, bool solo) {
         FA_PROF(7);
         if (tg > 0) mbar_wait(bg + B_SFREE, (tg - 1) & 1);
         FA_PROF(0);  // wait: S tile free
@@ -188,14 +194,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           const uint32_t tS = tmem_base + FA_COL_S + g * 128;
 #pragma unroll
           for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(tS, qd + 2 * kk, kd + 2 * kk, idesc_s, kk > 0);
-          if (last_s_of_item) umma_commit(bar_q_empty);
+          if (last_s_of_item) {
+            umma_commit(bar_q_empty);
+            if (solo) umma_commit(bar_q_empty);
+          }
           umma_commit(bg + B_S);
         }
         __syncwarp();
         FA_PROF(2);  // issue S
       };
-      auto issue_pv = [&](int g, uint32_t tg, int j, uint32_t kv, uint32_t kg, bool release_kv) {
-        const uint32_t bg = bar_grp + 64 * g;
+      auto issue_pv = [&](uint32_t tg, int j, uint32_t kv, uint32_t kg, bool solo) {
         FA_PROF(7);
         mbar_wait(bg + B_P, tg & 1);
         FA_PROF(3);  // wait: P stored
@@ -214,36 +222,124 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             for (int kk = 0; kk < n_mma_of(j) / 16; ++kk)
               umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, (j | kk) != 0);
           }
-          if (release_kv) umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once these retire
+          umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once both groups' MMAs on them retired
+          if (solo) umma_commit(bar_kv_empty + 8 * s);
           umma_commit(bg + B_PV);
+          if (j + 1 == n_tiles) umma_commit(bg + B_OFULL);
         }
         __syncwarp();
         FA_PROF(5);  // issue PV
       };
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
-        const int pair = item % n_pairs;
-        const bool has_b = 2 * pair + 1 < n_qt;  // group B has a real query tile
+      // skipped (A-only) items: group B's issuer still observes every phase of the shared barriers
+      auto skip_item = [&](uint32_t k) {
         mbar_wait(bar_q, k & 1);
-        issue_s(0, t_a, 0, kv_it, n_tiles == 1 && !has_b);
-        if (has_b) issue_s(1, t_b, 0, kv_it, n_tiles == 1);
-        for (int j = 0; j < n_tiles; ++j, ++kv_it) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const uint32_t kv = k * n_tiles + j;
+          mbar_wait(bar_kv_full + 8 * (kv % FA_STAGES), (kv / FA_STAGES) & 1);
+        }
+      };
+      int item = blockIdx.x;
+      uint32_t k = 0, tg = 0, kg = 0;
+      while (item < total_items && g == 1 && !paired(item)) {
+        skip_item(k);
+        item += gridDim.x;
+        ++k;
+      }
+      if (item < total_items) {
+        mbar_wait(bar_q, k & 1);
+        issue_s(0, 0, k * n_tiles, n_tiles == 1, g == 0 && !paired(item));
+      }
+      while (item < total_items) {
+        const bool solo = g == 0 && !paired(item);
+        const int next = item + gridDim.x;  // group A: always the next item; group B: only if it is a paired one
+        const bool next_direct = next < total_items && (g == 0 || paired(next));
+        for (int j = 0; j < n_tiles; ++j) {
+          const uint32_t kv = k * n_tiles + j;
+          // the next S tile first: it only needs the group's current S to be in registers
+          bool s_after = false;
           if (j + 1 < n_tiles) {
-            issue_s(0, t_a + 1, j + 1, kv_it + 1, j + 2 == n_tiles && !has_b);
-            if (has_b) issue_s(1, t_b + 1, j + 1, kv_it + 1, j + 2 == n_tiles);
+            issue_s(tg + 1, j + 1, kv + 1, j + 2 == n_tiles, solo);
+          } else if (next_direct) {
+            // the next item's Q tiles were requested when this item's last S retired; if the other group is late
+            // and they have not landed yet, do not hold this group's last PV back
+            if (__all_sync(0xffffffffu, mbar_try_wait(bar_q, (k + 1) & 1)))
+              issue_s(tg + 1, 0, kv + 1, n_tiles == 1, g == 0 && !paired(next));
+            else
+              s_after = true;
           }
-          issue_pv(0, t_a, j, kv_it, kg_a, !has_b);
-          ++t_a;
-          if (has_b) {
-            issue_pv(1, t_b, j, kv_it, kg_b, true);
-            ++t_b;
+          issue_pv(tg, j, kv, kg, solo);
+          if (s_after) {
+            mbar_wait(bar_q, (k + 1) & 1);
+            issue_s(tg + 1, 0, kv + 1, n_tiles == 1, g == 0 && !paired(next));
+          }
+          ++tg;
+        }
+        ++kg;
+        item = next;
+        ++k;
+        if (!next_direct && item < total_items) {  // group B steps over A-only items, then starts its next stream
+          while (item < total_items && !paired(item)) {
+            skip_item(k);
+            item += gridDim.x;
+            ++k;
+          }
+          if (item < total_items) {
+            mbar_wait(bar_q, k & 1);
+            issue_s(tg, 0, k * n_tiles, n_tiles == 1, false);
           }
         }
-        ++kg_a;
-        if (has_b) ++kg_b;
       }
       FA_PROF(7);
-      FA_PROF_DUMP(t_a + t_b);
-    }  // warps 10-11 idle
+      FA_PROF_DUMP(tg);
+    }  // warp 15 idle
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA_REGS_EPILOGUE));
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float* sL_gen = reinterpret_cast<const float*>(smem_gen + (sL - smem_base));
+    uint32_t kg[2] = {0, 0};
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int pair = item % n_pairs, bh = item / n_pairs;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int qt = 2 * pair + g;
+        if (qt >= n_qt) continue;
+        const uint32_t bg = bar_grp + 64 * g;
+        const uint32_t par = kg[g] & 1;
+        ++kg[g];
+        mbar_wait(bg + B_LFULL, par);
+        const float l = sL_gen[(par * 2 + g) * 128 + row];
+        mbar_wait(bg + B_OFULL, par);
+        tcgen05_fence_after();
+        const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform
+        uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
+        if (warp_active) {
+          const float inv = 1.0f / l;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_row + FA_COL_O + g * 64 + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bg + B_OEMPTY);  // O has left TMEM: the next item's first PV may overwrite it
+        if (warp_active) {
+          const int tok = qt * FA_BQ + row;
+          if (tok < T) {
+            uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ softmax warps, thread == query row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA_REGS_SOFTMAX));
@@ -255,33 +351,37 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     const uint32_t bg = bar_grp + 64 * g;
     const float c = args.scale_log2e;
     const uint64_t c2 = pack_f32x2(c, c);
-    // exp-phase turn taking: warps q of group A and q of group B sit on the same scheduler and share its MUFU unit.
-    // Left alone the two groups drift into phase and fight for it, then idle together; passing a token back and
-    // forth (A, B, A, B ...) keeps one group's MUFU-bound exp phase under the other's TMEM/max/store phases.
-    const uint32_t my_tok = bar_tok + 8 * warp, peer_tok = bar_tok + 8 * (warp ^ 4);
-    uint32_t tile_it = 0, tok_it = 0;
-    if (g == 1 && lane == 0) mbar_arrive(peer_tok);  // group A goes first
+    float* sL_gen = reinterpret_cast<float*>(smem_gen + (sL - smem_base));
+    uint32_t tile_it = 0, kg = 0;
+    bool pending = false;  // P of the previous tile is stored but not yet published to the MMA warp
     FA_PROF_DECL;
+    auto publish = [&]() {
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bg + B_P);
+      pending = false;
+    };
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int pair = item % n_pairs, bh = item / n_pairs;
+      const int pair = item % n_pairs;
       const int qt = 2 * pair + g;
       if (qt >= n_qt) continue;  // A-only item: the MMA warp skips this group too
-      const bool paired = FA_TURNS && 2 * pair + 1 < n_qt;  // both groups work on this item: take turns
       const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
       float m = 0.f, l = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++tile_it) {
-        FA_PROF(7);  // loop / epilogue
+        FA_PROF(7);  // loop
         mbar_wait(bg + B_S, tile_it & 1);
         tcgen05_fence_after();
         FA_PROF(0);  // wait for S
-        const int valid = min(FA_BK, T - j * FA_BK);
-        bool pv_seen = j == 0;  // PV(j-1) known retired: O may be rescaled, P overwritten
+        const int valid = min(FA_BK, T - kv_tile(j) * FA_BK);
+        bool pv_seen = tile_it == 0;  // PV(t-1) known retired: O may be rescaled, P overwritten
         if (warp_active && valid == FA_BK) {
           // The whole 128-wide S row lives in registers: one TMEM read per tile, four loads in flight.
           uint32_t v[128];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
             tmem_ld_32x32(tS + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * ch]));
+          if (pending) publish();  // P(j-1): its TMEM store drained under the loads above
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
@@ -321,8 +421,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             }
           }
           FA_PROF(2);  // row max (+ rescale)
-          if (paired) mbar_wait(my_tok, tok_it & 1);
-          FA_PROF(3);  // wait for the exp turn
           // ---- probabilities, packed in place (element pair i -> register i); packed FMA + packed row sums
           const float nmc = -m * c;
           const uint64_t nmc2 = pack_f32x2(nmc, nmc);
@@ -341,11 +439,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             unpack_f32x2(add_f32x2(add_f32x2(ls[0], ls[1]), add_f32x2(ls[2], ls[3])), a0, a1);
             l += a0 + a1;
           }
-          if (paired) {
-            ++tok_it;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(peer_tok);
-          }
           FA_PROF(4);  // exp
           if (!pv_seen) {
             mbar_wait(bg + B_PV, (tile_it - 1) & 1);
@@ -354,15 +447,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
             tmem_st_32x16(tP + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
-          tmem_st_wait();
+          pending = true;
+          if (j + 1 == n_tiles) publish();  // the epilogue is waiting for this one
           FA_PROF(5);  // wait PV(j-1), store P
         } else {
-          if (paired) {  // keep the turn order moving: this tile has (next to) no exp work
-            mbar_wait(my_tok, tok_it & 1);
-            ++tok_it;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(peer_tok);
-          }
+          if (pending) publish();
           if (!pv_seen) {
             mbar_wait(bg + B_PV, (tile_it - 1) & 1);
             tcgen05_fence_after();
@@ -414,52 +503,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
               }
               tmem_st_32x8(tP + ch * 8, pk);
             }
-            tmem_st_wait();
           }
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bg + B_SFREE);
-        }
-        tcgen05_fence_before();
-#ifdef FA_PROF_SPLIT
-        FA_PROF(6);
-        __syncwarp();
-        FA_PROF(3);
-        if (lane == 0) mbar_arrive(bg + B_P);
-        FA_PROF(2);
-#else
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bg + B_P);
-        FA_PROF(6);  // publish P
-#endif
-      }
-      // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
-      mbar_wait(bg + B_PV, (tile_it - 1) & 1);  // the item's last PV retired: O complete
-      tcgen05_fence_after();
-      uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
-      if (warp_active) {
-        const float inv = 1.0f / l;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t o[32];
-          tmem_ld_32x32(tO + hh * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          publish();
+          FA_PROF(6);  // ragged / padding tile
         }
       }
-      tcgen05_fence_before();
+      // hand the row sums to the epilogue warps and move on to the next item
+      sL_gen[((kg & 1) * 2 + g) * 128 + row] = l;
+      ++kg;
       __syncwarp();
-      if (lane == 0) mbar_arrive(bg + B_OEMPTY);  // O has left TMEM: the next item's first PV may overwrite it
-      if (warp_active) {
-        const int tok = qt * FA_BQ + row;
-        if (tok < T) {
-          uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
-        }
-      }
+      if (lane == 0) mbar_arrive(bg + B_LFULL);
     }  // item loop
     FA_PROF(7);
     FA_PROF_DUMP(tile_it);
@@ -467,7 +523,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<FA_TMEM_COLS>(tmem_base);

@@ -24,7 +24,7 @@ B, T, H = 128, 1029, 24
 C = H * 64
 qkv = torch.randn(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
 out = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
-trace = torch.zeros(4 * 12 * 10, device="cuda", dtype=torch.int64)
+trace = torch.zeros(4 * 16 * 10, device="cuda", dtype=torch.int64)
 lib.cvit_fa_set_trace(ctypes.c_void_p(trace.data_ptr()))
 lib.cvit_attention_fwd_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p]
 ts = []
@@ -37,14 +37,14 @@ for _ in range(4):
     torch.cuda.synchronize()
     ts.append(s.elapsed_time(e))
 print(f"flags {extra}: kernel ms (with accounting overhead): {min(ts):.3f}")
-tr = trace.cpu().numpy().reshape(4, 12, 10)
+tr = trace.cpu().numpy().reshape(4, 16, 10)
 sm_names = ["wait S", "ld", "max", "wait turn", "exp", "pv+st", "publish", "other"]
 mma_names = ["w sfree", "w kv", "iss S", "w P", "w Oempty", "iss PV", "-", "other"]
 for cta in range(2):
-    for w in list(range(8)) + [9]:
+    for w in list(range(8)) + [13, 14]:
         r = tr[cta, w]
         tiles = max(int(r[8]), 1)
-        names = mma_names if w == 9 else sm_names
-        label = "MMA " if w == 9 else f"{'AB'[w >> 2]}q{w & 3} "
+        names = mma_names if w >= 13 else sm_names
+        label = "MMA " if w >= 13 else f"{'AB'[w >> 2]}q{w & 3} "
         print(f"CTA{cta} {label} tiles {tiles:4d} per-tile:", "  ".join(f"{n} {r[i] / tiles:6.0f}" for i, n in enumerate(names)),
               f" | total {r[:8].sum() / tiles:6.0f}")
