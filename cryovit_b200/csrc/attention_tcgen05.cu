@@ -32,7 +32,7 @@ constexpr int FA_THREADS = 512;
 constexpr int FA_REGS_SOFTMAX = 184, FA_REGS_EPILOGUE = 72, FA_REGS_CONTROL = 72;
 constexpr int FA_STAGES = 4;
 constexpr int FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 2048 /* row sums */ + 512 /* barriers */ + 1024;
+constexpr int FA_SMEM = (4 + 2 * FA_STAGES) * FA_TILE_BYTES + 4096 /* row sums, maxima */ + 512 /* barriers */ + 1024;
 constexpr int FA_TMEM_COLS = 512;
 constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
 
@@ -87,15 +87,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;                                        // Q_A | Q_B
-  const uint32_t sK = smem_base + 2 * FA_TILE_BYTES;                    // FA_STAGES tiles
-  const uint32_t sV = smem_base + (2 + FA_STAGES) * FA_TILE_BYTES;      // FA_STAGES tiles
-  const uint32_t sL = smem_base + (2 + 2 * FA_STAGES) * FA_TILE_BYTES;  // row sums: [item parity][group][128] fp32
-  const uint32_t sBar = sL + 2048;
-  const uint32_t bar_q = sBar, bar_q_empty = sBar + 8;
-  const uint32_t bar_kv_full = sBar + 16;                 // FA_STAGES x 8
-  const uint32_t bar_kv_empty = sBar + 16 + 8 * FA_STAGES;
-  const uint32_t bar_grp = sBar + 16 + 16 * FA_STAGES;    // per group (64 B apart): the seven barriers below
+  const uint32_t sQ = smem_base;                                        // [item parity][Q_A | Q_B]: the next item's
+                                                                        // query tiles land while this one runs
+  const uint32_t sK = smem_base + 4 * FA_TILE_BYTES;                    // FA_STAGES tiles
+  const uint32_t sV = smem_base + (4 + FA_STAGES) * FA_TILE_BYTES;      // FA_STAGES tiles
+  const uint32_t sL = smem_base + (4 + 2 * FA_STAGES) * FA_TILE_BYTES;  // [item parity][group][sums 128 | maxima 128] fp32
+  const uint32_t sBar = sL + 4096;
+  const uint32_t bar_q = sBar, bar_q_empty = sBar + 16;   // 2 x 8 each (one per Q buffer)
+  const uint32_t bar_kv_full = sBar + 32;                 // FA_STAGES x 8
+  const uint32_t bar_kv_empty = sBar + 32 + 8 * FA_STAGES;
+  const uint32_t bar_grp = sBar + 32 + 16 * FA_STAGES;    // per group (64 B apart): the seven barriers below
   constexpr uint32_t B_S = 0, B_SFREE = 8, B_P = 16, B_PV = 24, B_OFULL = 32, B_OEMPTY = 40, B_LFULL = 48;
   const uint32_t tmem_slot = bar_grp + 128;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -110,11 +111,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   // first full tile (walked last, the single P buffer would stall the softmax behind PV of the tile before it).
   const bool ragged = (T % FA_BK) != 0;
   auto kv_tile = [&](int j) { return ragged ? (j == 0 ? n_tiles - 1 : j - 1) : j; };
+  // Item kinds. PAIRED: query tiles 2p (group A) and 2p+1 (group B). When the query-tile count is odd the last
+  // item has a single tile; it is SPLIT between the groups by K/V tile (group g takes the walked tiles j = g mod 2,
+  // each with its own running max / sum / O; the epilogue merges the two partial softmaxes) so that it costs half
+  // an item instead of a whole one. With a single K/V tile there is nothing to split: SOLO (group A alone).
+  enum { PAIRED = 0, SPLIT = 1, SOLO = 2 };
+  auto pair_kind = [&](int pair) { return 2 * pair + 1 < n_qt ? PAIRED : n_tiles > 1 ? SPLIT : SOLO; };
+  auto item_kind = [&](int item) { return pair_kind(item % n_pairs); };
+  // does group g work on walked tile j of an item of this kind?
+  auto mine = [&](int kind, int g, int j) { return kind == PAIRED || (kind == SPLIT ? (j & 1) == g : g == 0); };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_q_empty, 2);  // one commit per group (group A commits twice on A-only items)
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_q + 8 * b, 1);
+      mbar_init(bar_q_empty + 8 * b, 2);  // one commit per group (group A commits twice on SOLO items)
+    }
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
       mbar_init(bar_kv_empty + 8 * s, 2);
@@ -146,10 +158,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           const int pair = item % n_pairs, bh = item / n_pairs;
           const int head = bh % args.heads, slice = bh / args.heads;
           const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
-          mbar_wait(bar_q_empty, (k & 1) ^ 1u);  // every S MMA of the previous item has retired
-          mbar_arrive_expect_tx(bar_q, 2 * FA_TILE_BYTES);
-          tma_load_3d(sQ, &tmQKV, bar_q, cq, (2 * pair) * FA_BQ, slice);
-          tma_load_3d(sQ + FA_TILE_BYTES, &tmQKV, bar_q, cq, (2 * pair + 1) * FA_BQ, slice);  // all-OOB box = zeros
+          const uint32_t qb_ = k & 1, sQk = sQ + qb_ * 2 * FA_TILE_BYTES, bq = bar_q + 8 * qb_;
+          mbar_wait(bar_q_empty + 8 * qb_, ((k >> 1) & 1) ^ 1u);  // every S MMA of item k-2 has retired
+          mbar_arrive_expect_tx(bq, 2 * FA_TILE_BYTES);
+          tma_load_3d(sQk, &tmQKV, bq, cq, (2 * pair) * FA_BQ, slice);
+          const int qb = item_kind(item) == PAIRED ? 2 * pair + 1 : 2 * pair;  // SPLIT: both groups work on tile 2p
+          tma_load_3d(sQk + FA_TILE_BYTES, &tmQKV, bq, cq, qb * FA_BQ, slice);
           for (int j = 0; j < n_tiles; ++j, ++kv_it) {
             const uint32_t s = kv_it % FA_STAGES;
             mbar_wait(bar_kv_empty + 8 * s, ((kv_it / FA_STAGES) & 1) ^ 1u);
@@ -176,10 +190,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         const int valid = min(FA_BK, T - kv_tile(j) * FA_BK);
         return (valid + 15) & ~15;
       };
-      auto paired = [&](int item) { return 2 * (item % n_pairs) + 1 < n_qt; };  // group B has a real query tile
       FA_PROF_DECL;
-      // S_g for the tile with per-group index tg: walked tile j of the item whose ring position is kv
-      auto issue_s = [&](uint32_t tg, int j, uint32_t kv, bool last_s_of_item, bool solo) {
+      // S_g for this group's tile number tg: walked tile j of the item whose first ring position is kv - j
+      auto issue_s = [&](uint32_t tg, int j, uint32_t k, int commits_q) {
+        const uint32_t kv = k * n_tiles + j;
         FA_PROF(7);
         if (tg > 0) mbar_wait(bg + B_SFREE, (tg - 1) & 1);
         FA_PROF(0);  // wait: S tile free
@@ -189,25 +203,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         FA_PROF(1);  // wait: K/V landed
         if (elect_one_sync()) {
           const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
-          const uint64_t qd = umma_smem_desc_kmajor<128>(sQ + g * FA_TILE_BYTES);
+          const uint64_t qd = umma_smem_desc_kmajor<128>(sQ + ((k & 1) * 2 + g) * FA_TILE_BYTES);
           const uint64_t kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
           const uint32_t tS = tmem_base + FA_COL_S + g * 128;
 #pragma unroll
           for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(tS, qd + 2 * kk, kd + 2 * kk, idesc_s, kk > 0);
-          if (last_s_of_item) {
-            umma_commit(bar_q_empty);
-            if (solo) umma_commit(bar_q_empty);
-          }
+          for (int i = 0; i < commits_q; ++i) umma_commit(bar_q_empty + 8 * (k & 1));  // this group's last S of the item
           umma_commit(bg + B_S);
         }
         __syncwarp();
         FA_PROF(2);  // issue S
       };
-      auto issue_pv = [&](uint32_t tg, int j, uint32_t kv, uint32_t kg, bool solo) {
+      auto issue_pv = [&](uint32_t tg, int j, uint32_t kv, bool first, bool last, uint32_t kg, int commits_kv) {
         FA_PROF(7);
         mbar_wait(bg + B_P, tg & 1);
         FA_PROF(3);  // wait: P stored
-        if (j == 0) mbar_wait(bg + B_OEMPTY, (kg & 1) ^ 1u);  // previous item's O_g has been read out of TMEM
+        if (first) mbar_wait(bg + B_OEMPTY, (kg & 1) ^ 1u);  // previous item's O_g has been read out of TMEM
         tcgen05_fence_after();
         FA_PROF(4);  // wait: O drained
         const uint32_t s = kv % FA_STAGES;
@@ -217,80 +228,88 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           if (n_mma_of(j) == FA_BK) {
 #pragma unroll
             for (int kk = 0; kk < FA_BK / 16; ++kk)  // 16 keys per step: 8 packed TMEM columns of P, 2 KB of the V tile
-              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, (j | kk) != 0);
+              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, !first || kk != 0);
           } else {
             for (int kk = 0; kk < n_mma_of(j) / 16; ++kk)
-              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, (j | kk) != 0);
+              umma_bf16_ts(tO, tP + 8 * kk, vd + 128 * kk, idesc_pv, !first || kk != 0);
           }
-          umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once both groups' MMAs on them retired
-          if (solo) umma_commit(bar_kv_empty + 8 * s);
+          for (int i = 0; i < commits_kv; ++i) umma_commit(bar_kv_empty + 8 * s);  // K(j), V(j) free once retired
           umma_commit(bg + B_PV);
-          if (j + 1 == n_tiles) umma_commit(bg + B_OFULL);
+          if (last) umma_commit(bg + B_OFULL);
         }
         __syncwarp();
         FA_PROF(5);  // issue PV
       };
-      // skipped (A-only) items: group B's issuer still observes every phase of the shared barriers
-      auto skip_item = [&](uint32_t k) {
-        mbar_wait(bar_q, k & 1);
-        for (int j = 0; j < n_tiles; ++j) {
-          const uint32_t kv = k * n_tiles + j;
-          mbar_wait(bar_kv_full + 8 * (kv % FA_STAGES), (kv / FA_STAGES) & 1);
+      // Cursors over this group's tiles: (item, k = CTA-local item number, kind, j).
+      struct Cur { int item; uint32_t k; int pair; int kind; int j; };
+      const int pair_step = gridDim.x % n_pairs;  // pair index of item + gridDim.x without a division per tile
+      auto cur_valid = [&](const Cur& c) { return c.item < total_items; };
+      auto first_j = [&](int kind) { return kind == SPLIT ? g : 0; };
+      auto last_j = [&](int kind) { return kind == SPLIT ? n_tiles - 1 - ((n_tiles - 1 - g) & 1) : n_tiles - 1; };
+      auto advance = [&](Cur& c) {  // to the group's next tile
+        for (;;) {
+          ++c.j;
+          if (c.j >= n_tiles) {
+            c.item += gridDim.x;
+            ++c.k;
+            c.j = 0;
+            if (c.item >= total_items) return;
+            c.pair += pair_step;
+            if (c.pair >= n_pairs) c.pair -= n_pairs;
+            c.kind = pair_kind(c.pair);
+          }
+          if (mine(c.kind, g, c.j)) return;
         }
       };
-      int item = blockIdx.x;
-      uint32_t k = 0, tg = 0, kg = 0;
-      while (item < total_items && g == 1 && !paired(item)) {
-        skip_item(k);
-        item += gridDim.x;
-        ++k;
+      Cur cs{(int)blockIdx.x, 0u, (int)(blockIdx.x % n_pairs), 0, -1}, cp = cs;  // next S tile, next PV tile
+      if (cur_valid(cs)) {
+        cs.kind = cp.kind = pair_kind(cs.pair);
+        advance(cs);
+        advance(cp);
       }
-      if (item < total_items) {
-        mbar_wait(bar_q, k & 1);
-        issue_s(0, 0, k * n_tiles, n_tiles == 1, g == 0 && !paired(item));
-      }
-      while (item < total_items) {
-        const bool solo = g == 0 && !paired(item);
-        const int next = item + gridDim.x;  // group A: always the next item; group B: only if it is a paired one
-        const bool next_direct = next < total_items && (g == 0 || paired(next));
-        for (int j = 0; j < n_tiles; ++j) {
-          const uint32_t kv = k * n_tiles + j;
-          // the next S tile first: it only needs the group's current S to be in registers
-          bool s_after = false;
-          if (j + 1 < n_tiles) {
-            issue_s(tg + 1, j + 1, kv + 1, j + 2 == n_tiles, solo);
-          } else if (next_direct) {
-            // the next item's Q tiles were requested when this item's last S retired; if the other group is late
-            // and they have not landed yet, do not hold this group's last PV back
-            if (__all_sync(0xffffffffu, mbar_try_wait(bar_q, (k + 1) & 1)))
-              issue_s(tg + 1, 0, kv + 1, n_tiles == 1, g == 0 && !paired(next));
-            else
-              s_after = true;
-          }
-          issue_pv(tg, j, kv, kg, solo);
-          if (s_after) {
-            mbar_wait(bar_q, (k + 1) & 1);
-            issue_s(tg + 1, 0, kv + 1, n_tiles == 1, g == 0 && !paired(next));
-          }
-          ++tg;
+      // The shared barriers (Q per item, kv_full per ring slot) must be observed phase by phase, also for the tiles
+      // and items this group does not work on: (ok, oj) is the next ring position not yet observed.
+      uint32_t ok = 0, obs_q = ~0u;  // obs_q: last item whose Q phase was observed
+      int oj = 0;
+      auto observe_up_to = [&](const Cur& c) {  // everything before tile (c.k, c.j), plus the Q phase of item c.k
+        while (ok < c.k || (ok == c.k && oj < c.j)) {
+          if (oj == 0) { mbar_wait(bar_q + 8 * (ok & 1), (ok >> 1) & 1); obs_q = ok; }
+          const uint32_t kv = ok * n_tiles + oj;
+          mbar_wait(bar_kv_full + 8 * (kv % FA_STAGES), (kv / FA_STAGES) & 1);
+          if (++oj == n_tiles) { oj = 0; ++ok; }
         }
-        ++kg;
-        item = next;
-        ++k;
-        if (!next_direct && item < total_items) {  // group B steps over A-only items, then starts its next stream
-          while (item < total_items && !paired(item)) {
-            skip_item(k);
-            item += gridDim.x;
-            ++k;
-          }
-          if (item < total_items) {
-            mbar_wait(bar_q, k & 1);
-            issue_s(tg, 0, k * n_tiles, n_tiles == 1, false);
-          }
+        if (oj == 0) { mbar_wait(bar_q + 8 * (ok & 1), (ok >> 1) & 1); obs_q = ok; }
+        if (++oj == n_tiles) { oj = 0; ++ok; }  // the tile itself is waited for by issue_s
+      };
+      uint32_t ts = 0, tp = 0, kg = 0;  // S tiles issued, PV tiles issued, items finished (barrier phases)
+      auto do_s = [&]() {
+        FA_PROF(7);
+        observe_up_to(cs);
+        FA_PROF(6);  // observing shared barrier phases (incl. waiting for the next item's Q)
+        const bool last = cs.j == last_j(cs.kind);
+        issue_s(ts, cs.j, cs.k, last ? (cs.kind == SOLO ? 2 : 1) : 0);
+        ++ts;
+        advance(cs);
+      };
+      if (cur_valid(cs)) do_s();  // S(0)
+      while (cur_valid(cp)) {
+        // The next S tile first (it only needs the group's current S to be in registers) -- unless it belongs to
+        // a later item whose Q has not landed yet (the other group is late): then this group's PV goes first.
+        bool s_first = false;
+        if (cur_valid(cs)) {
+          if (cs.k == obs_q) s_first = true;
+          else if (cs.k == obs_q + 1) s_first = __all_sync(0xffffffffu, mbar_try_wait(bar_q + 8 * (cs.k & 1), (cs.k >> 1) & 1));
         }
+        if (s_first) do_s();
+        const bool first = cp.j == first_j(cp.kind), last = cp.j == last_j(cp.kind);
+        issue_pv(tp, cp.j, cp.k * n_tiles + cp.j, first, last, kg, cp.kind == PAIRED ? 1 : 2);
+        ++tp;
+        if (last) ++kg;
+        advance(cp);
+        if (!s_first && cur_valid(cs)) do_s();
       }
       FA_PROF(7);
-      FA_PROF_DUMP(tg);
+      FA_PROF_DUMP(tp);
     }  // warp 15 idle
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
@@ -299,45 +318,89 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float* sL_gen = reinterpret_cast<const float*>(smem_gen + (sL - smem_base));
+    const float c = args.scale_log2e;
     uint32_t kg[2] = {0, 0};
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int pair = item % n_pairs, bh = item / n_pairs;
+      const int pair = item % n_pairs, bh = item / n_pairs, kind = item_kind(item);
+      __nv_bfloat16* out_bh = args.out + ((size_t)(bh / args.heads) * T) * args.C + (bh % args.heads) * FA_D;
+      if (kind == SPLIT) {
+        // two partial softmaxes of the same query tile (even / odd K/V tiles): merge, then normalise
+        const int qt = 2 * pair;
+        const uint32_t pa = kg[0] & 1, pb = kg[1] & 1;
+        ++kg[0];
+        ++kg[1];
+        mbar_wait(bar_grp + B_LFULL, pa);
+        mbar_wait(bar_grp + 64 + B_LFULL, pb);
+        const float la = sL_gen[(pa * 2 + 0) * 256 + row], ma = sL_gen[(pa * 2 + 0) * 256 + 128 + row];
+        const float lb = sL_gen[(pb * 2 + 1) * 256 + row], mb = sL_gen[(pb * 2 + 1) * 256 + 128 + row];
+        const float mm = fmaxf(ma, mb);
+        float wa = ex2_approx((ma - mm) * c), wb = ex2_approx((mb - mm) * c);
+        const float inv = 1.0f / (wa * la + wb * lb);
+        wa *= inv;
+        wb *= inv;
+        mbar_wait(bar_grp + B_OFULL, pa);
+        mbar_wait(bar_grp + 64 + B_OFULL, pb);
+        tcgen05_fence_after();
+        const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform
+        if (warp_active) {
+          const int tok = qt * FA_BQ + row;
+          uint4* dst = reinterpret_cast<uint4*>(out_bh + (size_t)tok * args.C);
+#pragma unroll 1
+          for (int hh = 0; hh < 4; ++hh) {  // 16 columns of both partial outputs at a time
+            uint32_t oa[16], o2[16], ob[8];
+            tmem_ld_32x16(t_row + FA_COL_O + hh * 16, oa);
+            tmem_ld_32x16(t_row + FA_COL_O + 64 + hh * 16, o2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              ob[i] = pack_bf16x2(__uint_as_float(oa[2 * i]) * wa + __uint_as_float(o2[2 * i]) * wb,
+                                  __uint_as_float(oa[2 * i + 1]) * wa + __uint_as_float(o2[2 * i + 1]) * wb);
+            if (tok < T) {
+              dst[2 * hh] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+              dst[2 * hh + 1] = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_grp + B_OEMPTY);
+          mbar_arrive(bar_grp + 64 + B_OEMPTY);
+        }
+        continue;
+      }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
+        if (kind == SOLO && g == 1) continue;
         const int qt = 2 * pair + g;
-        if (qt >= n_qt) continue;
         const uint32_t bg = bar_grp + 64 * g;
         const uint32_t par = kg[g] & 1;
         ++kg[g];
         mbar_wait(bg + B_LFULL, par);
-        const float l = sL_gen[(par * 2 + g) * 128 + row];
+        const float l = sL_gen[(par * 2 + g) * 256 + row];
         mbar_wait(bg + B_OFULL, par);
         tcgen05_fence_after();
         const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform
-        uint32_t ob[32];  // the 64 outputs of this row, normalised and packed to bf16 pairs
         if (warp_active) {
           const float inv = 1.0f / l;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
+          const int tok = qt * FA_BQ + row;
+          uint4* dst = reinterpret_cast<uint4*>(out_bh + (size_t)tok * args.C);
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {  // 32 of the row's 64 outputs at a time: normalise, pack, store
             uint32_t o[32];
             tmem_ld_32x32(t_row + FA_COL_O + g * 64 + hh * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              ob[hh * 16 + i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            if (tok < T) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[4 * hh + i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
           }
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bg + B_OEMPTY);  // O has left TMEM: the next item's first PV may overwrite it
-        if (warp_active) {
-          const int tok = qt * FA_BQ + row;
-          if (tok < T) {
-            uint4* dst = reinterpret_cast<uint4*>(args.out + ((size_t)(bh / args.heads) * T + tok) * args.C + (bh % args.heads) * FA_D);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
-          }
-        }
       }
     }
   } else {
@@ -363,12 +426,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       pending = false;
     };
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int pair = item % n_pairs;
-      const int qt = 2 * pair + g;
-      if (qt >= n_qt) continue;  // A-only item: the MMA warp skips this group too
+      const int pair = item % n_pairs, kind = item_kind(item);
+      if (kind == SOLO && g == 1) continue;  // nothing for group B here; its issuer skips the item too
+      const int qt = kind == PAIRED ? 2 * pair + g : 2 * pair;
       const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
       float m = 0.f, l = 0.f;
-      for (int j = 0; j < n_tiles; ++j, ++tile_it) {
+      bool first = true;  // first tile this group works on in the item
+      for (int j = 0; j < n_tiles; ++j) {
+        if (!mine(kind, g, j)) continue;
         FA_PROF(7);  // loop
         mbar_wait(bg + B_S, tile_it & 1);
         tcgen05_fence_after();
@@ -398,7 +463,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
               mx[u] = fmax3(mx[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
           }
           const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          if (j == 0) {
+          if (first) {
             m = mt;
           } else {
             const bool need = (mt - m) * c > 8.0f;
@@ -448,7 +513,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           for (int ch = 0; ch < 4; ++ch)
             tmem_st_32x16(tP + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
           pending = true;
-          if (j + 1 == n_tiles) publish();  // the epilogue is waiting for this one
+          if (j + 1 == n_tiles || (kind == SPLIT && j + 2 >= n_tiles)) publish();  // last one: the epilogue is waiting
           FA_PROF(5);  // wait PV(j-1), store P
         } else {
           if (pending) publish();
@@ -468,7 +533,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
               for (int i = 0; i < 16; ++i)
                 if (ch * 16 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
             }
-            if (j == 0) {
+            if (first) {
               m = mt;
             } else {
               const bool need = (mt - m) * c > 8.0f;
@@ -510,9 +575,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           publish();
           FA_PROF(6);  // ragged / padding tile
         }
+        first = false;
+        ++tile_it;
       }
-      // hand the row sums to the epilogue warps and move on to the next item
-      sL_gen[((kg & 1) * 2 + g) * 128 + row] = l;
+      // hand the row sums (and, for the merge of a SPLIT item, the row maxima) to the epilogue warps; next item
+      sL_gen[((kg & 1) * 2 + g) * 256 + row] = l;
+      sL_gen[((kg & 1) * 2 + g) * 256 + 128 + row] = m;
       ++kg;
       __syncwarp();
       if (lane == 0) mbar_arrive(bg + B_LFULL);

@@ -39,7 +39,7 @@ for _ in range(4):
 print(f"flags {extra}: kernel ms (with accounting overhead): {min(ts):.3f}")
 tr = trace.cpu().numpy().reshape(4, 16, 10)
 sm_names = ["wait S", "ld", "max", "wait turn", "exp", "pv+st", "publish", "other"]
-mma_names = ["w sfree", "w kv", "iss S", "w P", "w Oempty", "iss PV", "-", "other"]
+mma_names = ["w sfree", "w kv", "iss S", "w P", "w Oempty", "iss PV", "observe", "other"]
 for cta in range(2):
     for w in list(range(8)) + [13, 14]:
         r = tr[cta, w]
