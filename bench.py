@@ -91,6 +91,63 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+# kernels at the same shapes (profiles/r01_ncu_full_v3_hot_kernels.json); bench.py itself never runs under ncu.
+NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu": "w12_swiglu", "layernorm": "layernorm",
+            "proj_scale_residual": "proj_gemm", "w3_scale_residual": "w3_gemm"}
+
+
+def ncu_traffic(kernel: str) -> float | None:
+    p = ROOT / "profiles" / "r01_ncu_full_v3_hot_kernels.json"
+    if not p.exists() or kernel not in NCU_KEYS:
+        return None
+    for d in json.loads(p.read_text()):
+        if d["kernel"].startswith(NCU_KEYS[kernel]):
+            return round(d["dram_traffic_GB"] * 1e9)
+    return None
+
+
+def head_voxels_per_s(torch, steps: int = 3) -> dict:
+    """CryoVIT 3-D head on one 1536-channel 128x32x32 feature volume (BASELINE config 4) -> 128x512x512 probabilities."""
+    from cryovit_b200.head import CryoVITHeadB200, state_dict_keys
+
+    g = torch.Generator().manual_seed(7)
+    shapes = {"layers.0.weight": (1024, 1536, 1, 1, 1), "layers.0.bias": (1024,)}
+    blocks = [(1024, 192, 128), (128, 64, 32), (32, 32, 32), (32, 16, 8)]
+    for bi, (c1, c2, c3) in enumerate(blocks):
+        p = f"layers.{bi + 2}.layers."
+        shapes.update({p + "0.weight": (c1,), p + "0.bias": (c1,), p + "1.weight": (c2, c1, 3, 3, 3), p + "1.bias": (c2,),
+                       p + "3.weight": (c2, c2, 3, 3, 3), p + "3.bias": (c2,), p + "5.weight": (c2, c3, 1, 2, 2),
+                       p + "5.bias": (c3,)})
+    shapes.update({"output_layer.0.weight": (8, 8, 3, 3, 3), "output_layer.0.bias": (8,),
+                   "output_layer.2.weight": (1, 8, 3, 3, 3), "output_layer.2.bias": (1,)})
+    sd = {}
+    for k in state_dict_keys():
+        shp = shapes[k]
+        fan_in = 1
+        for d in shp[1:]:
+            fan_in *= d
+        sd[k] = (torch.ones(shp) if k.endswith("0.weight") and len(shp) == 1 else
+                 torch.randn(shp, generator=g) * (fan_in ** -0.5 if len(shp) > 1 else 0.02))
+    head = CryoVITHeadB200(1536).load_state_dict(sd).cuda()
+    feats = (torch.randn(1536, D, 32, 32, generator=g) * 0.5).half().cuda()
+    for _ in range(2):
+        head.segment_volume(feats, want_logits=False)
+    torch.cuda.synchronize()
+    l0 = head.launches
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        head.segment_volume(feats, want_logits=False)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    vox = D * H * W
+    return {"value": round(vox / ms * 1e3, 0), "unit": "voxels/s", "ms_per_volume": round(ms, 3),
+            "tflops": round(94864 * vox / ms / 1e9, 1), "launches_per_volume": (head.launches - l0) // steps,
+            "workload": f"CryoVIT head, fp16 (1536,{D},32,32) feature volume -> ({D},{H},{W}) probabilities, weights random"}
+
+
 def cpu_oracle_slices_per_s(n_slices: int, sd=None, threads: int | None = None) -> tuple[float, int, float]:
     """fp32 oracle (pre-processing + ViT-g forward + layout/cast) on the host cores over n_slices slices."""
     import numpy as np
@@ -305,7 +362,9 @@ def run_b200(args) -> None:
         tf = tensor_ks[top]["flops"] / tensor_ks[top]["ms"] / 1e9
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         roof = {"kernel": top, "bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(tf / peak, 4), "traffic": None, "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
+                "frac": round(tf / peak, 4), "traffic": ncu_traffic(top),
+                "traffic_source": "profiles/r01_ncu_full_v3_hot_kernels.json (ncu --set full, one launch, same shapes)",
+                "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
                 "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
     kernels = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
                    "share_of_step": round(shares[k] * (2 if k == "layernorm" else 1), 4)} for k, v in ks.items()}
@@ -323,9 +382,10 @@ def run_b200(args) -> None:
                 "d2h_bytes_per_step": C * D * 32 * 32 * 2},
         "gpu_launches": launches,
     }
+    del model
+    torch.cuda.empty_cache()
+    line["head"] = head_voxels_per_s(torch)
     if world == 1 and not args.no_cpu_baseline:
-        del model
-        torch.cuda.empty_cache()
         v, cores, dt = cpu_oracle_slices_per_s(2, sd)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
                                 "sample": f"2 slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast ({dt:.1f} s)"}

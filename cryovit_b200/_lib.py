@@ -21,6 +21,7 @@ P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 # name -> argtypes; every function returns int except the two diagnostics. Mirrors include/cryovit_b200.h.
 SIGNATURES: dict[str, list] = {
     "cvit_preproc_patchify": [P, I32, P, I64, I64, I64, I64, P],
+    "cvit_preproc_resize_f32_3ch": [P, I32, P, I64, I64, I64, P],
     "cvit_patchify_f32_3ch": [P, P, I64, I64, I64, I64, P],
     "cvit_patch_embed_gemm": [P, I64, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_assemble_special_tokens": [P, P, I64, I64, I64, I64, P],
@@ -38,6 +39,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_conv3d_dilated_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_convT_1x2x2_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, P],
     "cvit_head_tail_fused": [P, P, P, P, P, P, P, P, I64, I64, I64, P],
+    "cvit_seg_stats": [P, P, I64, F32, P, P],
 }
 
 _lib: ctypes.CDLL | None = None

@@ -293,3 +293,59 @@ int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Masked segmentation statistics in one pass over the volume: everything DiceLoss (losses.py:17-32),
+// DiceMetric (metrics.py:30-53) and F1Metric (metrics.py:69-93) reduce over, restricted to voxels whose label is
+// > -1 (BaseModel._masked_predict, base_model.py:91-112). out[8] (fp64, accumulated with atomics, caller zeroes):
+//   0 sum p   1 sum y   2 sum p*y                          (DiceLoss)
+//   3 sum y*[p >= thr]   4 sum [p >= thr]                  (DiceMetric: "pred < thr -> 0 else 1")
+//   5 sum y*[p > .5]   6 sum (1-y)*[p > .5]   7 sum y*(1-[p > .5])     (F1Metric: strict ">")
+namespace cvit {
+__global__ void __launch_bounds__(256) seg_stats_kernel(const float* __restrict__ probs, const float* __restrict__ labels,
+                                                        int64_t n, float thr, double* __restrict__ out) {
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float y = labels[i], p = probs[i];
+    if (y > -1.0f) {
+      const float hge = p >= thr ? 1.f : 0.f, hgt = p > 0.5f ? 1.f : 0.f;
+      v[0] += p;
+      v[1] += y;
+      v[2] += p * y;
+      v[3] += y * hge;
+      v[4] += hge;
+      v[5] += y * hgt;
+      v[6] += (1.f - y) * hgt;
+      v[7] += y * (1.f - hgt);
+    }
+  }
+  __shared__ double red[8][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double t = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(out + threadIdx.x, t);
+  }
+}
+}  // namespace cvit
+
+extern "C" int cvit_seg_stats(const float* probs, const float* labels, int64_t n, float threshold, double* out8,
+                              void* stream) {
+  if (!probs || !labels || !out8 || n <= 0) {
+    cvit::set_error("seg_stats: bad arguments");
+    return cvit::CVIT_ERR_INVALID;
+  }
+  int64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+  const int64_t cap = (int64_t)cvit::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  cvit::seg_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(probs, labels, n, threshold, out8);
+  return cvit::check_launch("seg_stats_kernel");
+}
+

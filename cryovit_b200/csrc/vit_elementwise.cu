@@ -63,6 +63,39 @@ __global__ void preproc_patchify_kernel(const T* __restrict__ src, __nv_bfloat16
   }
 }
 
+// Same resample, written in the reference's own layout f32 [D, 3, OH, OW] (three identical channels): what
+// VITDataset.__getitem__ returns (vit_dataset.py:117-123), for callers that keep the reference's dataset seam.
+template <typename T>
+__global__ void preproc_resize3_kernel(const T* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int OH,
+                                       int OW, float inv_scale) {
+  const int64_t plane_o = (int64_t)OH * OW, total = (int64_t)D * plane_o;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW), oy = (int)((idx / OW) % OH), d = (int)(idx / plane_o);
+    const float A = -0.75f;
+    const float sy = inv_scale * (oy + 0.5f) - 0.5f, sx = inv_scale * (ox + 0.5f) - 0.5f;
+    const float fy = floorf(sy), fx = floorf(sx);
+    const int iy = (int)fy, ix = (int)fx;
+    const float ty = sy - fy, tx = sx - fx;
+    const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+    const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+    const T* plane = src + (int64_t)d * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y = min(max(iy - 1 + i, 0), H - 1);
+      float r = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r += wx[j] * load_px(plane + (int64_t)y * W + min(max(ix - 1 + j, 0), W - 1));
+      acc += wy[i] * r;
+    }
+    float* o = dst + (int64_t)d * 3 * plane_o + (int64_t)oy * OW + ox;
+    o[0] = acc;
+    o[plane_o] = acc;
+    o[2 * plane_o] = acc;
+  }
+}
+
 // General patchify for the reference-facing forward_features(x: f32[B,3,H',W']) entry (seam B2):
 // rows [b*Np + patch], cols c*196 + i*14 + j, zero-padded to Kp.
 __global__ void patchify3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int OH, int OW,
@@ -261,6 +294,24 @@ int cvit_preproc_patchify(const void* src, int src_is_u8, void* patches_bf16, in
         static_cast<const float*>(src), static_cast<__nv_bfloat16*>(patches_bf16), (int)D, (int)H, (int)W, OH, OW,
         (int)Kp, inv_scale);
   return check_launch("preproc_patchify_kernel");
+}
+
+int cvit_preproc_resize_f32_3ch(const void* src, int src_is_u8, float* out, int64_t D, int64_t H, int64_t W,
+                                void* stream) {
+  if (!src || !out || D <= 0 || H <= 0 || W <= 0) {
+    set_error("preproc_resize: bad arguments (D=%lld H=%lld W=%lld)", (long long)D, (long long)H, (long long)W);
+    return CVIT_ERR_INVALID;
+  }
+  const int OH = (int)((H + 15) / 16 * 14), OW = (int)((W + 15) / 16 * 14);
+  const float inv_scale = static_cast<float>(1.0 / 0.875);
+  const int grid = grid_for(D * (int64_t)OH * OW, 256);
+  if (src_is_u8)
+    preproc_resize3_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint8_t*>(src), out, (int)D,
+                                                                          (int)H, (int)W, OH, OW, inv_scale);
+  else
+    preproc_resize3_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(src), out, (int)D,
+                                                                        (int)H, (int)W, OH, OW, inv_scale);
+  return check_launch("preproc_resize3_kernel");
 }
 
 int cvit_patchify_f32_3ch(const float* src, void* patches_bf16, int64_t B, int64_t OH, int64_t OW, int64_t Kp,

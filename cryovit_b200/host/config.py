@@ -1,0 +1,227 @@
+"""Configuration for the hot path, with the reference's keys (config.py:17-156,205-231 and configs/*.yaml).
+
+The reference composes its YAML tree with Hydra. Hydra / OmegaConf are used when importable; this image has
+neither, so :func:`compose` implements the subset the hot path's configs need: ``defaults`` lists (group entries,
+``_self_``, schema nodes and ``override hydra/...`` lines are accepted and skipped), ``${a.b}`` interpolation, ``???``
+mandatory values, and command-line overrides ``a.b=value`` / ``+a.b=value`` / ``group=choice`` -- the forms
+``slurm_scripts/dino_features_job.sh`` passes.
+"""
+from __future__ import annotations
+
+import importlib
+import logging
+import re
+import sys
+from functools import partial
+from pathlib import Path
+from typing import Any
+
+import yaml
+
+DINO_PATCH_SIZE = 14  # config.py:17
+MISSING = "???"
+tomogram_exts: list[str] = [".hdf", ".mrc"]  # config.py:15
+
+# types.py:14-44 (Sample): attribute name -> display name. ``samples`` is the list of directory names.
+SAMPLES: dict[str, str] = {
+    "BACHD": "BACHD", "BACHD_Microtubules": "BACHD Microtubules", "dN17_BACHD": "dN17 BACHD", "Q109": "Q109",
+    "Q109_Microtubules": "Q109 Microtubules", "Q18": "Q18", "Q18_Microtubules": "Q18 Microtubules", "Q20": "Q20",
+    "Q53": "Q53", "Q53_KD": "Q53 PIAS1", "Q66": "Q66", "Q66_GRFS1": "Q66 GRFS1", "Q66_KD": "Q66 PIAS1",
+    "WT": "Wild Type", "WT_Microtubules": "Wild Type Microtubules", "cancer": "Cancer", "AD": "AD",
+    "AD_Abeta": "AD Abeta", "Aged": "Aged", "Young": "Young", "RGC_CM": "RGC CM", "RGC_control": "RGC Control",
+    "RGC_naPP": "RGC naPP", "RGC_PP": "RGC PP", "CZI_Algae": "Algae", "CZI_Campy_C": "Campy C",
+    "CZI_Campy_CDel": "Campy C-Deletion", "CZI_Campy_F": "Campy F", "CZI_Fibroblast": "Mouse Fibroblast",
+}
+samples: list[str] = list(SAMPLES)
+
+# schema defaults of the structured nodes the YAML tree merges with (config.py:113-156)
+SCHEMA_DEFAULTS: dict[str, dict] = {
+    "paths": {"model_dir": MISSING, "data_dir": MISSING, "exp_dir": MISSING, "results_dir": MISSING,
+              "tomo_name": "tomograms", "feature_name": "dino_features", "dino_name": "DINOv2", "sam_name": "SAM2",
+              "csv_name": "csv", "split_name": "splits.csv"},
+    "dino_features": {"batch_size": 128, "model_dir": MISSING, "paths": MISSING, "model": None, "datamodule": MISSING,
+                      "sample": MISSING, "export_features": False, "use_sam": False},
+}
+
+
+class Cfg(dict):
+    """dict with attribute access (what the runner needs of a DictConfig)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _wrap(x):
+    if isinstance(x, dict):
+        return Cfg({k: _wrap(v) for k, v in x.items()})
+    if isinstance(x, list):
+        return [_wrap(v) for v in x]
+    return x
+
+
+def _merge(dst: dict, src: dict) -> dict:
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = v
+    return dst
+
+
+_SCI = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)[eE][+-]?\d+$")
+
+
+def _numbers(node):
+    """PyYAML (YAML 1.1) reads ``1e-4`` as a string; OmegaConf reads it as a float. Follow OmegaConf."""
+    if isinstance(node, dict):
+        return {k: _numbers(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_numbers(v) for v in node]
+    if isinstance(node, str) and _SCI.match(node):
+        return float(node)
+    return node
+
+
+def _load_yaml(path: Path) -> dict:
+    with open(path) as fh:
+        return _numbers(yaml.safe_load(fh) or {})
+
+
+def _compose_file(config_dir: Path, rel: str, choices: dict[str, str]) -> dict:
+    """One YAML file with its ``defaults`` list resolved (group paths are relative to the file's own group)."""
+    path = config_dir / (rel + ".yaml")
+    if not path.exists():
+        raise FileNotFoundError(f"config file {path} not found")
+    body = _load_yaml(path)
+    defaults = body.pop("defaults", ["_self_"])
+    group_dir = str(Path(rel).parent) if "/" in rel else ""
+    out: dict = {}
+    self_done = False
+    for entry in defaults:
+        if entry == "_self_":
+            _merge(out, body)
+            self_done = True
+        elif isinstance(entry, str):
+            cand = (group_dir + "/" if group_dir else "") + entry
+            if (config_dir / (cand + ".yaml")).exists():  # a sibling file of the same group
+                _merge(out, _compose_file(config_dir, cand, choices))
+            # else: a ConfigStore schema node (base_env, dino_features_config ...): defaults come from SCHEMA_DEFAULTS
+        elif isinstance(entry, dict):
+            for group, choice in entry.items():
+                if str(group).startswith("override "):
+                    continue  # hydra logging overrides
+                full_group = (group_dir + "/" if group_dir else "") + group
+                for ch in (choice if isinstance(choice, list) else [choice]):
+                    ch = choices.get(full_group, ch)
+                    sub = _compose_file(config_dir, f"{full_group}/{ch}", choices)
+                    node = out.setdefault(group, {})
+                    if isinstance(choice, list):  # list-valued defaults (losses, metrics): one sub-key per choice
+                        node[ch] = sub.get(ch, sub) if isinstance(sub, dict) else sub
+                    else:
+                        _merge(node, sub)
+    if not self_done:
+        _merge(out, body)
+    return out
+
+
+_INTERP = re.compile(r"\$\{([^}]+)\}")
+
+
+def _lookup(root: dict, dotted: str):
+    cur: Any = root
+    for part in dotted.split("."):
+        cur = cur[part]
+    return cur
+
+
+def _resolve(node, root, depth=0):
+    if depth > 16:
+        raise ValueError("interpolation cycle")
+    if isinstance(node, dict):
+        for k in list(node):
+            node[k] = _resolve(node[k], root, depth)
+        return node
+    if isinstance(node, list):
+        return [_resolve(v, root, depth) for v in node]
+    if isinstance(node, str) and "${" in node:
+        m = _INTERP.fullmatch(node)
+        if m:
+            return _resolve(_lookup(root, m.group(1)), root, depth + 1)
+        return _resolve(_INTERP.sub(lambda mm: str(_resolve(_lookup(root, mm.group(1)), root, depth + 1)), node), root, depth + 1)
+    return node
+
+
+def _parse_value(text: str):
+    if text in ("null", "None", "~"):
+        return None
+    try:
+        return _numbers(yaml.safe_load(text))
+    except yaml.YAMLError:
+        return text
+
+
+def compose(config_name: str, overrides: list[str] | None = None, config_dir: Path | None = None) -> Cfg:
+    """Compose ``<config_dir>/<config_name>.yaml`` with its defaults and apply overrides."""
+    config_dir = Path(config_dir) if config_dir else Path(__file__).resolve().parents[2] / "cryovit" / "configs"
+    overrides = list(overrides or [])
+    choices: dict[str, str] = {}
+    values: list[tuple[str, Any]] = []
+    for ov in overrides:
+        if "=" not in ov:
+            raise ValueError(f"override {ov!r} is not of the form key=value")
+        key, val = ov.split("=", 1)
+        key = key.lstrip("+")
+        if (config_dir / key).is_dir() and (config_dir / key / f"{val}.yaml").exists():
+            choices[key] = val  # config-group choice, e.g. paths=default
+        else:
+            values.append((key, _parse_value(val)))
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in SCHEMA_DEFAULTS.get(config_name, {}).items()}
+    _merge(cfg, _compose_file(config_dir, config_name, choices))
+    if isinstance(cfg.get("paths"), dict):
+        cfg["paths"] = _merge(dict(SCHEMA_DEFAULTS["paths"]), cfg["paths"])
+    for key, val in values:
+        cur = cfg
+        parts = key.split(".")
+        for p in parts[:-1]:
+            if not isinstance(cur.get(p), dict):
+                cur[p] = {}
+            cur = cur[p]
+        cur[parts[-1]] = val
+    return _wrap(_resolve(cfg, cfg))
+
+
+def missing_keys(cfg: dict, prefix: str = "") -> list[str]:
+    out = []
+    for k, v in cfg.items():
+        if isinstance(v, dict):
+            out += missing_keys(v, f"{prefix}{k}.")
+        elif v == MISSING:
+            out.append(prefix + k)
+    return out
+
+
+def validate_dino_config(cfg: dict) -> None:
+    """config.py:205-231: list the mandatory parameters that are still ``???`` and exit(1)."""
+    miss = missing_keys(cfg)
+    if miss:
+        msg = ["The following parameters were missing from dino_features.yaml"]
+        msg += [f"{i}. {k}" for i, k in enumerate(miss, 1)]
+        logging.error("\n".join(msg))
+        sys.exit(1)
+
+
+def instantiate(node: dict, **kwargs):
+    """hydra.utils.instantiate for the two forms the hot path uses: ``_target_`` (+ ``_partial_``)."""
+    node = dict(node)
+    target = node.pop("_target_")
+    is_partial = bool(node.pop("_partial_", False))
+    mod, _, attr = target.rpartition(".")
+    fn = getattr(importlib.import_module(mod), attr)
+    node.update(kwargs)
+    return partial(fn, **node) if is_partial else fn(**node)

@@ -1,0 +1,107 @@
+"""Feature-extraction runner with the reference's functions and file layout (run/dino_features.py:31-64,109-205,
+304-350): ``_dino_features``, ``_save_data``, ``_process_sample``, ``run_trainer``.
+
+Differences that are deliberate, all on the fast side of the same contract:
+  * the model is ``cryovit_b200.vit.build_model("dinov2_vitg14_reg")`` (upstream checkpoint keys) instead of
+    ``torch.hub.load`` (:336) -- there is no network in this image, so without a checkpoint in ``cfg.model_dir``
+    the weights are seeded random (logged loudly);
+  * items may be RAW tomograms (``VITDataset(fused=True)``): pre-processing then runs inside the GPU extractor;
+  * with several ranks (torchrun) the tomograms of a sample are dealt round-robin to the ranks; every rank writes
+    only its own files, no collective is involved.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import extract
+from ..vit import DinoVisionTransformerB200, build_model
+from . import hdf
+from .config import instantiate, samples, tomogram_exts
+from .shard import rank_world, shard_round_robin
+
+dino_model = ("facebookresearch/dinov2", "dinov2_vitg14_reg")  # run/dino_features.py:25-28
+CHECKPOINT_NAMES = ("dinov2_vitg14_reg4_pretrain.pth", "checkpoints/dinov2_vitg14_reg4_pretrain.pth")
+
+
+@torch.inference_mode()
+def _dino_features(data: torch.Tensor, model: DinoVisionTransformerB200, batch_size: int) -> np.ndarray:
+    """Same name, arguments and result as the reference (:31-64): ``np.float16 (C, D, H'/14, W'/14)``.
+    ``data`` is either the reference's pre-processed ``[D, 3, H', W']`` float tensor or a raw ``[D, H, W]`` tomogram."""
+    if data.dim() == 3:
+        return extract.extract_tomogram(data, model, batch_size)
+    return extract._dino_features(data, model, batch_size)
+
+
+def _save_data(data: dict[str, np.ndarray], features: np.ndarray, tomo_name: str, dst_dir: Path) -> None:
+    """:109-153: ``data`` stays ``data`` (gzip), every other source dataset goes under ``labels/`` (gzip), a stale
+    ``dino_features`` is dropped, the new features are stored uncompressed."""
+    out: dict[str, np.ndarray] = {}
+    for key, arr in data.items():
+        if key == "dino_features":
+            continue
+        out["data" if key == "data" else f"labels/{key}"] = arr
+    out["dino_features"] = features
+    hdf.write_tomogram(Path(dst_dir) / tomo_name, out)
+
+
+def _read_source(path: Path) -> dict[str, np.ndarray]:
+    """:193-200: every dataset of the source file, group members flattened to their own name."""
+    return {k.split("/")[-1]: v for k, v in hdf.read_tomogram(path).items()}
+
+
+def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: str, datamodule, batch_size: int,
+                    image_dir: Path | None = None, use_sam: bool = False) -> list[str]:
+    """:156-205. Returns the records this rank processed."""
+    tomo_dir, result_dir, csv_file = Path(src_dir) / sample, Path(dst_dir) / sample, Path(csv_dir) / f"{sample}.csv"
+    if csv_file.exists():
+        import pandas as pd
+
+        records = pd.read_csv(csv_file)["tomo_name"].to_list()
+    else:
+        records = sorted(f.name for f in tomo_dir.glob("*") if f.suffix in tomogram_exts)
+    records = shard_round_robin(records)
+    dataset = instantiate(datamodule["dataset"], data_root=tomo_dir, use_sam=use_sam)(records=records)
+    if image_dir is not None:
+        logging.warning("export_features=True (PCA colour maps) is outside the hot path and is skipped")
+    for i in range(len(dataset)):
+        features = _dino_features(dataset[i], model, batch_size)
+        _save_data(_read_source(tomo_dir / records[i]), features, records[i], result_dir)
+    return records
+
+
+def load_model(model_dir: Path | str | None, name: str = dino_model[1]) -> DinoVisionTransformerB200:
+    """The object the reference gets from torch.hub (:336): a checkpoint under ``model_dir`` if there is one."""
+    if model_dir is not None:
+        for rel in CHECKPOINT_NAMES:
+            p = Path(model_dir) / rel
+            if p.exists():
+                logging.info("loading DINOv2 checkpoint %s", p)
+                return build_model(name, state_dict=torch.load(p, map_location="cpu")).cuda().eval()
+    logging.warning("no DINOv2 checkpoint under %s: using seeded RANDOM weights (no network access to torch.hub)", model_dir)
+    return build_model(name).cuda().eval()
+
+
+def run_trainer(cfg) -> None:
+    """:304-350."""
+    paths = cfg["paths"]
+    data_dir, exp_dir = Path(paths["data_dir"]), Path(paths["exp_dir"])
+    src_dir, dst_dir = data_dir / paths["feature_name"], data_dir / paths["tomo_name"]
+    csv_dir, image_dir = data_dir / paths["csv_name"], exp_dir / "dino_images"
+    sample = cfg.get("sample")
+    if sample is not None and not isinstance(sample, str):
+        sample = getattr(sample, "name", str(sample))
+    sample_names = [sample] if sample is not None else [s for s in samples if (src_dir / s).exists()]
+    if cfg.get("use_sam"):
+        raise NotImplementedError("use_sam=True (SAM2 image encodings) is outside the B200 hot path")
+    rank, world = rank_world()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    model = load_model(cfg.get("model_dir"), cfg.get("dino_variant") or dino_model[1])
+    for name in sample_names:
+        done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
+                               image_dir if cfg.get("export_features") else None, False)
+        logging.info("rank %d/%d: %d tomograms of %s", rank, world, len(done), name)

@@ -39,6 +39,17 @@ def preproc_patchify(src: torch.Tensor, out: torch.Tensor) -> None:
               D, H, W, out.shape[1], _stream())
 
 
+def preproc_resize_3ch(src: torch.Tensor, out: torch.Tensor) -> None:
+    """src u8|f32 [D,H,W] -> out f32 [D,3,OH,OW]: the reference dataset's pre-processed layout (vit_dataset.py:90-123)."""
+    D, H, W = src.shape
+    is_u8 = src.dtype == U8
+    OH, OW, _, _ = patch_grid(H, W)
+    if tuple(out.shape) != (D, 3, OH, OW):
+        raise _lib.CryovitB200Error(f"preproc_resize_3ch: out must be {(D, 3, OH, OW)}, got {tuple(out.shape)}")
+    _lib.call("cvit_preproc_resize_f32_3ch", _chk(src, U8 if is_u8 else F32, "src"), int(is_u8), _chk(out, F32, "out"),
+              D, H, W, _stream())
+
+
 def patchify_f32_3ch(src: torch.Tensor, out: torch.Tensor) -> None:
     B, C, OH, OW = src.shape
     if C != 3:
@@ -140,3 +151,11 @@ def head_tail(x, w1, b1, w2, b2, scratch, logits=None, probs=None) -> None:
               _chk(logits, F32, "logits") if logits is not None else None,
               _chk(probs, F32, "probs") if probs is not None else None, _chk(scratch, BF16, "scratch"), D, H, W,
               _stream())
+
+
+def seg_stats(probs: torch.Tensor, labels: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
+    """Masked (label > -1) reductions behind DiceLoss / DiceMetric / F1Metric, fp64 [8] on the device (see the header)."""
+    out = torch.zeros(8, device=probs.device, dtype=torch.float64)
+    _lib.call("cvit_seg_stats", _chk(probs, F32, "probs"), _chk(labels, F32, "labels"), probs.numel(), float(threshold),
+              out.data_ptr(), _stream())
+    return out

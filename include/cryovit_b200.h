@@ -51,6 +51,11 @@ const char* cvit_last_error(void);
 int cvit_preproc_patchify(const void* src, int src_is_u8, void* patches_bf16, int64_t D, int64_t H, int64_t W,
                           int64_t Kp, void* stream);
 
+/* The same pre-processing written in the reference's own layout: f32 [D, 3, ceil16(H)*14/16, ceil16(W)*14/16]
+ * with three identical channels -- what VITDataset.__getitem__ returns (datasets/vit_dataset.py:90-123). */
+int cvit_preproc_resize_f32_3ch(const void* src, int src_is_u8, float* out, int64_t D, int64_t H, int64_t W,
+                                void* stream);
+
 /* Patchify for the reference-facing model call forward_features(x: f32[B,3,H',W']) (run/dino_features.py:58;
  * upstream PatchEmbed, HF:42-73).  Output bf16 [B * Np, Kp], column c*196 + i*14 + j, zero padded to Kp
  * (multiple of 64, >= 588). */
@@ -147,6 +152,13 @@ int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4,
 int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                          float* logits, float* probs, void* scratch_bf16, int64_t D, int64_t H, int64_t W,
                          void* stream);
+
+/* Masked segmentation statistics, one pass: over voxels with label > -1 (BaseModel._masked_predict,
+ * models/base_model.py:91-112) accumulates out8 (fp64, caller zeroes) = {sum p, sum y, sum p*y | sum y*[p>=thr],
+ * sum [p>=thr] | sum y*[p>.5], sum (1-y)*[p>.5], sum y*(1-[p>.5])}: the reductions behind DiceLoss
+ * (models/losses.py:17-32), DiceMetric (models/metrics.py:30-53, "pred < thr -> 0 else 1") and F1Metric
+ * (models/metrics.py:69-93, strict "> 0.5"). probs, labels: fp32 [n]. */
+int cvit_seg_stats(const float* probs, const float* labels, int64_t n, float threshold, double* out8, void* stream);
 
 #ifdef __cplusplus
 }

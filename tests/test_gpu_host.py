@@ -1,0 +1,129 @@
+"""GPU suite for the host-side mirror: the reference's module entry point end to end (files in -> files out) against
+the oracle, the dataset seam in the reference's own layout against golden vectors produced by the reference's source,
+the fused loss / metric reductions, and the ``cryovit.models.CryoVIT`` surface."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(GOLD / "reference_src.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_vit_dataset_reference_layout_matches_reference(cuda_lib, ref, tag, tmp_path):
+    """VITDataset(fused=False)[i] == the reference's VITDataset.__getitem__ (golden from the reference's source)."""
+    from cryovit.datasets import VITDataset
+    from cryovit_b200.host import hdf
+
+    src = ref[f"preproc_{tag}_in"]
+    hdf.write_tomogram(tmp_path / "t.hdf", {"data": src})
+    item = VITDataset(tmp_path, False, ["t.hdf"], fused=False)[0]
+    want = torch.from_numpy(ref[f"preproc_{tag}_out"])
+    assert item.dtype == torch.float32 and tuple(item.shape) == tuple(want.shape) and not item.is_cuda
+    assert (item - want).abs().max().item() < 2e-6  # same bicubic taps, fp32, different summation order
+    raw = VITDataset(tmp_path, False, ["t.hdf"])[0]
+    assert raw.dtype == torch.uint8 and tuple(raw.shape) == tuple(src.shape)
+
+
+def test_seg_stats_losses_and_metrics_match_oracle(cuda_lib, ref):
+    from cryovit.models import DiceLoss, DiceMetric, F1Metric
+    from oracle import metrics as om
+
+    # the hand-sized golden case computed by the reference's own DiceLoss / DiceMetric / F1Metric
+    yt, yp = torch.from_numpy(ref["metric_y_true"]).cuda(), torch.from_numpy(ref["metric_y_pred"]).cuda()
+    assert abs(float(DiceLoss()(yp, yt)) - float(ref["metric_dice_loss"])) < 1e-6
+    d, f = DiceMetric(0.5), F1Metric()
+    d.update(yp, yt)
+    f.update(yp, yt)
+    assert abs(float(d.compute()) - float(ref["metric_dice"])) < 1e-6
+    assert abs(float(f.compute()) - float(ref["metric_f1"])) < 1e-6
+    # a volume with ignored voxels (-1), probabilities exactly at the thresholds included
+    g = torch.Generator().manual_seed(4)
+    probs = torch.rand(6, 64, 80, generator=g)
+    probs[0, 0, :8] = 0.5
+    labels = torch.randint(-1, 2, (6, 64, 80), generator=g).float()
+    p_sel, y_sel = om.masked_select(probs, labels)
+    assert abs(float(DiceLoss()(probs.cuda(), labels.cuda())) - float(om.dice_loss(p_sel, y_sel))) < 1e-5
+    d.reset(), f.reset()
+    for _ in range(2):  # two batches: the reference averages per-batch scores
+        d.update(probs.cuda(), labels.cuda())
+        f.update(probs.cuda(), labels.cuda())
+    assert abs(float(d.compute()) - float(om.dice_metric(p_sel, y_sel))) < 1e-5 and d.total == 2.0
+    assert abs(float(f.compute()) - float(om.f1_metric(p_sel, y_sel))) < 1e-5
+
+
+def test_cryovit_model_surface_and_parity(cuda_lib):
+    """Hydra target cryovit.models.CryoVIT: reference constructor keywords, state-dict names, forward(batch)."""
+    from cryovit.config import compose, instantiate
+    from cryovit.datamodules.utils import collate_fn
+    from cryovit.types import TomogramData
+    from oracle import head as ohead
+
+    cfg = compose("model/cryovit", [])
+    model = instantiate(cfg, in_channels=384, seed=0)
+    assert model.name == "CryoVIT" and model.input_key == "dino_features" and model.lr == 1e-4 and model.weight_decay == 1e-3
+    assert sorted(model.state_dict()) == sorted(ohead.random_state_dict(384, seed=1))
+    sd = ohead.random_state_dict(384, seed=1)
+    model.load_state_dict(sd).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    feats = (torch.randn(384, 6, 3, 4, generator=g) * 0.5).half()
+    labels = torch.randint(-1, 2, (6, 48, 64), generator=g).to(torch.int8)
+    batch = collate_fn([TomogramData("S", "t", 0, feats, labels, {})])
+    probs = model(batch)
+    assert tuple(probs.shape) == (1, 6, 48, 64)
+    want = ohead.forward(sd, batch.tomo_batch)
+    assert (probs.cpu() - want).abs().max().item() < 5e-3
+    agree = ((probs.cpu() >= 0.5) == (want >= 0.5)).float().mean().item()
+    assert agree >= 0.995, agree
+    res = model.test_step(batch)
+    assert set(res) == {"dice_loss", "dice_metric", "f1_metric"} and all(np.isfinite(v) for v in res.values())
+    vol = model.forward_volume(batch.tomo_batch.permute(0, 2, 1, 3, 4).contiguous())
+    assert tuple(vol.shape) == (1, 1, 6, 48, 64) and float(vol.abs().max()) <= 5.0
+
+
+def test_module_entry_point_end_to_end(cuda_lib, tmp_path):
+    """python -m cryovit.training.dino_features with Hydra-style overrides: source files -> result files with the
+    reference's layout; features agree with the oracle pipeline on the same seeded weights (ViT-S variant)."""
+    from cryovit.training.dino_features import main
+    from cryovit_b200.host import hdf
+    from cryovit_b200.vit import CONFIGS, random_state_dict
+    from oracle import dinov2 as odino
+    from oracle import extract as oextract
+    from oracle import preproc as opre
+
+    rng = np.random.default_rng(9)
+    src = tmp_path / "dino_features" / "Q18"
+    tomos = {"a.hdf": rng.integers(0, 256, (5, 64, 96), dtype=np.uint8), "b.hdf": rng.random((3, 50, 70), dtype=np.float32)}
+    for name, data in tomos.items():
+        hdf.write_tomogram(src / name, {"data": data, "labels/mito": rng.integers(-1, 2, data.shape).astype(np.int8)})
+    main([f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/models", "sample=Q18",
+          "batch_size=2", "+dino_variant=dinov2_vits14_reg"])
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    oracle_model = odino.OracleDino(random_state_dict(cfg, seed=0), cfg.num_heads)
+    for name, data in tomos.items():
+        out = hdf.read_tomogram(tmp_path / "tomograms" / "Q18" / name)
+        assert sorted(out) == ["data", "dino_features", "labels/mito"]
+        assert np.array_equal(out["data"], data) and out["data"].dtype == data.dtype
+        want = oextract.dino_features(opre.dino_transform(opre.load_tomogram(data)), oracle_model, 2)
+        got = out["dino_features"]
+        assert got.dtype == np.float16 and got.shape == want.shape
+        g, w = torch.from_numpy(got.astype(np.float32)), torch.from_numpy(want.astype(np.float32))
+        rel = ((g - w).norm(dim=0) / w.norm(dim=0)).max().item()
+        cos = torch.nn.functional.cosine_similarity(g, w, dim=0).min().item()
+        assert rel <= 1e-2 and cos >= 0.999, (name, rel, cos)
+
+
+def test_entry_point_logs_and_swallows_errors(cuda_lib, tmp_path, caplog):
+    """training/dino_features.py:33-37: a failing run is logged with its traceback, the process does not raise."""
+    from cryovit.training.dino_features import main
+
+    main([f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/m", "sample=Q18",
+          "use_sam=True", "+dino_variant=dinov2_vits14_reg"])
+    assert any("NotImplementedError" in r.getMessage() for r in caplog.records)

@@ -1,0 +1,196 @@
+"""CPU suite for the host-side mirror of the reference interfaces (cryovit_b200/host, re-exported as ``cryovit.*``):
+config composition, the tomogram file layout, crop / collate against golden vectors produced by the reference's own
+source (tests/golden/reference_src.npz), sharding, and a world_size-2 gloo run of the multi-rank paths."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(GOLD / "reference_src.npz")
+
+
+# ------------------------------------------------------------------------------------------------- config (seam B1)
+def test_compose_dino_features_defaults_and_overrides():
+    from cryovit.config import compose, missing_keys
+
+    cfg = compose("dino_features", ["sample=Q18", "paths.data_dir=/data/x", "batch_size=64", "paths=default"])
+    assert cfg.batch_size == 64 and cfg.sample == "Q18" and cfg.export_features is False and cfg.use_sam is False
+    assert cfg.paths.data_dir == "/data/x" and cfg.paths.tomo_name == "tomograms" and cfg.paths.feature_name == "dino_features"
+    assert cfg.paths.results_dir == cfg.paths.exp_dir  # ${paths.exp_dir}
+    assert cfg.model_dir == f"{cfg.paths.model_dir}/DINOv2"  # ${paths.model_dir}/${paths.dino_name}
+    ds, dl = cfg.datamodule.dataset, cfg.datamodule.dataloader
+    assert ds["_target_"] == "cryovit.datasets.VITDataset" and ds["_partial_"] is True
+    assert ds["data_root"] == "/data/x/tomograms"
+    # datamodule/dino.yaml overrides the loader defaults: one whole tomogram per item, no workers
+    assert dl["batch_size"] is None and dl["num_workers"] == 0 and dl["pin_memory"] is True
+    assert missing_keys(cfg) == []
+
+
+def test_missing_mandatory_keys_exit(tmp_path, caplog):
+    from cryovit.config import compose, validate_dino_config
+
+    (tmp_path / "paths").mkdir()
+    (tmp_path / "paths" / "default.yaml").write_text("model_dir: ???\ndata_dir: /d\nexp_dir: /e\nresults_dir: /r\n")
+    (tmp_path / "dino_features.yaml").write_text("defaults:\n  - paths: default\n  - _self_\nmodel_dir: /m\nsample: null\ndatamodule: {}\n")
+    cfg = compose("dino_features", [], config_dir=tmp_path)
+    with pytest.raises(SystemExit) as e:
+        validate_dino_config(cfg)
+    assert e.value.code == 1  # config.py:227-229
+
+
+def test_model_config_targets_resolve():
+    from cryovit.config import compose, instantiate
+
+    cfg = compose("model/cryovit", [])
+    assert cfg["_target_"] == "cryovit.models.CryoVIT" and cfg["input_key"] == "dino_features" and cfg["lr"] == 1e-4
+    assert set(cfg["losses"]) == {"dice_loss"} and set(cfg["metrics"]) == {"dice_metric", "f1_metric"}
+    m = instantiate(cfg["metrics"]["dice_metric"])
+    assert m.threshold == 0.5
+
+
+# ------------------------------------------------------------------------------------------------- file layout (B5)
+def test_save_data_layout_roundtrip(tmp_path):
+    from cryovit.run.dino_features import _save_data
+    from cryovit_b200.host import hdf
+
+    rng = np.random.default_rng(0)
+    src = {"data": rng.integers(0, 256, (4, 32, 48), dtype=np.uint8), "mito": rng.integers(-1, 2, (4, 32, 48)).astype(np.int8),
+           "granule": rng.integers(-1, 2, (4, 32, 48)).astype(np.int8), "dino_features": np.zeros((2, 4, 2, 3), np.float16)}
+    feats = rng.standard_normal((384, 4, 2, 3)).astype(np.float16)
+    _save_data(src, feats, "t0.hdf", tmp_path / "out" / "S")
+    path = tmp_path / "out" / "S" / "t0.hdf"
+    assert sorted(hdf.list_keys(path)) == ["data", "dino_features", "labels/granule", "labels/mito"]
+    back = hdf.read_tomogram(path)
+    assert back["dino_features"].dtype == np.float16 and back["dino_features"].shape == (384, 4, 2, 3)
+    assert np.array_equal(back["dino_features"], feats)  # the stale source features were replaced
+    assert np.array_equal(back["data"], src["data"]) and back["data"].dtype == np.uint8
+    assert np.array_equal(back["labels/mito"], src["mito"]) and back["labels/mito"].dtype == np.int8
+    _save_data({"data": src["data"]}, feats[:1], "t0.hdf", tmp_path / "out" / "S")  # "w": overwrite, no merge
+    assert sorted(hdf.list_keys(path)) == ["data", "dino_features"]
+
+
+# ------------------------------------------------------------------------------------------------- crop / collate (a8)
+def test_random_crop_matches_reference(ref):
+    from cryovit.datasets import TomoDataset
+
+    ds = TomoDataset([], "dino_features", "mito", "split_id", Path("."), train=True)
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((6, 140, 34, 33)).astype(np.float16)
+    label = rng.integers(-1, 2, size=(140, 34 * 16, 33 * 16)).astype(np.int8)
+    rec = {"input": feat, "label": label}
+    np.random.seed(123)
+    ds._random_crop(rec)
+    assert tuple(rec["input"].shape) == tuple(ref["crop_input_shape"]) == (6, 128, 32, 32)
+    assert tuple(rec["label"].shape) == tuple(ref["crop_label_shape"]) == (128, 512, 512)
+    assert rec["input"].astype(np.float64).sum() == float(ref["crop_input_sum"])
+    assert rec["label"].astype(np.int64).sum() == int(ref["crop_label_sum"])
+
+
+def test_collate_matches_reference_and_pads_ragged(ref):
+    from cryovit.datamodules.utils import collate_fn
+    from cryovit.types import TomogramData
+
+    items = [TomogramData("S", f"t{i}", i, torch.from_numpy(ref["collate_in_data"][i]), torch.from_numpy(ref["collate_in_label"][i]), {})
+             for i in range(2)]
+    b = collate_fn(items)
+    assert b.tomo_batch.dtype == torch.float32 and tuple(b.tomo_batch.shape) == (2, 4, 6, 3, 2)
+    assert np.array_equal(b.tomo_batch.numpy(), ref["collate_tomo_batch"])
+    assert np.array_equal(b.labels.numpy(), ref["collate_labels"])
+    assert np.array_equal(b.tomo_sizes.numpy(), ref["collate_tomo_sizes"])
+    assert b.metadata.identifiers() == (["S", "S"], ["t0", "t1"]) and b.metadata.split_id.tolist() == [0, 1]
+    # ragged depths: data padded with 0, labels with -1 (ignored by the masked loss)
+    short = TomogramData("S", "t2", 2, items[0].data[:, :3], items[0].label[:3], {})
+    b2 = collate_fn([items[0], short])
+    assert b2.tomo_sizes.tolist() == [4, 3] and b2.min_slices == 3
+    assert torch.all(b2.labels[1, 3] == -1) and torch.all(b2.tomo_batch[1, 3] == 0)
+
+
+def test_tomo_dataset_reads_layout(tmp_path):
+    from cryovit.datasets import TomoDataset
+    from cryovit_b200.host import hdf
+
+    rng = np.random.default_rng(1)
+    feats = rng.standard_normal((8, 5, 2, 2)).astype(np.float16)
+    lab = rng.integers(-1, 2, (5, 32, 32)).astype(np.int8)
+    hdf.write_tomogram(tmp_path / "S" / "a.hdf", {"data": np.zeros((5, 32, 32), np.uint8), "labels/mito": lab, "dino_features": feats})
+    ds = TomoDataset([{"sample": "S", "tomo_name": "a.hdf", "split_id": 3}], "dino_features", "mito", "split_id", tmp_path)
+    it = ds[0]
+    assert it.split_id == 3 and tuple(it.data.shape) == (8, 5, 2, 2) and it.data.dtype == torch.float16
+    assert np.array_equal(it.label.numpy(), lab)
+    with pytest.raises(IndexError):
+        ds[1]
+
+
+# ------------------------------------------------------------------------------------------------- sharding (8e)
+@pytest.mark.parametrize("n,world", [(128, 8), (128, 3), (5, 8), (0, 2), (1029, 4)])
+def test_shard_range_partitions(n, world):
+    from cryovit_b200.host.shard import shard_range, shard_round_robin
+
+    parts = [shard_range(n, r, world) for r in range(world)]
+    assert [i for p in parts for i in p] == list(range(n))  # contiguous, ordered, complete, disjoint
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    rr = [shard_round_robin(list(range(n)), r, world) for r in range(world)]
+    assert sorted(i for p in rr for i in p) == list(range(n))
+
+
+WORKER = r'''
+import os, sys
+from pathlib import Path
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+from cryovit_b200.host import dino_features as df, hdf
+from cryovit_b200.host.metrics import _MeanOfBatchesMetric
+from cryovit.config import compose
+rank = dist.get_rank()
+# (1) tomograms of a sample are dealt round-robin; every rank writes only its own files (stub extractor: no GPU here)
+df._dino_features = lambda data, model, bs: np.full((4, data.shape[0], 2, 3), float(data.float().mean()), np.float16)
+root = Path(os.environ["WORK"])
+cfg = compose("dino_features", [f"paths.data_dir={root}", f"paths.exp_dir={root}/exp", "sample=Q18"])
+done = df._process_sample(root / "dino_features", root / "tomograms", root / "csv", None, "Q18", cfg["datamodule"], 2)
+(root / f"done_{rank}.txt").write_text("\n".join(done))
+# (2) metric states reduce with "sum" across ranks (metrics.py:24-27 semantics)
+m = _MeanOfBatchesMetric()
+m._add(torch.tensor(0.25 if rank == 0 else 0.75, dtype=torch.float64))
+if rank == 1:
+    m._add(torch.tensor(0.5, dtype=torch.float64))
+m.all_reduce()
+assert abs(float(m.compute()) - 0.5) < 1e-12 and m.total == 3.0, (float(m.compute()), m.total)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharded_extraction_and_metric_reduce(tmp_path):
+    from cryovit_b200.host import hdf
+
+    rng = np.random.default_rng(2)
+    names = [f"tomo_{i}.hdf" for i in range(5)]
+    for i, n in enumerate(names):
+        hdf.write_tomogram(tmp_path / "dino_features" / "Q18" / n, {"data": rng.integers(0, 256, (3 + i, 32, 48), dtype=np.uint8),
+                                                                    "labels/mito": np.zeros((3 + i, 32, 48), np.int8)})
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port, WORK=str(tmp_path), REPO=str(ROOT))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    done = [(tmp_path / f"done_{r}.txt").read_text().split() for r in range(2)]
+    assert done[0] == names[0::2] and done[1] == names[1::2]  # disjoint, complete, no collective needed
+    for i, n in enumerate(names):
+        back = hdf.read_tomogram(tmp_path / "tomograms" / "Q18" / n)
+        assert sorted(back) == ["data", "dino_features", "labels/mito"]
+        assert back["dino_features"].shape == (4, 3 + i, 2, 3) and back["data"].shape == (3 + i, 32, 48)
