@@ -37,8 +37,10 @@ SIGNATURES: dict[str, list] = {
     "cvit_features_f32_to_ndhwc_bf16": [P, P, I64, I64, P],
     "cvit_groupnorm_ndhwc_bf16": [P, P, P, P, P, I64, I64, I64, F32, P],
     "cvit_conv3d_dilated_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_conv3d_halo_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_convT_1x2x2_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, P],
     "cvit_head_tail_fused": [P, P, P, P, P, P, P, P, I64, I64, I64, P],
+    "cvit_head_out_conv": [P, P, P, P, P, I64, I64, I64, P],
     "cvit_seg_stats": [P, P, I64, F32, P, P],
 }
 
@@ -60,6 +62,8 @@ def load() -> ctypes.CDLL:
     lib.cvit_last_error.argtypes = []
     lib.cvit_abi_version.restype = c_int
     lib.cvit_abi_version.argtypes = []
+    lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
+    lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = c_int

@@ -292,6 +292,29 @@ int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const 
   return check_launch("tail_conv_kernel<1>");
 }
 
+// The last convolution alone: Conv3d(8 -> 1, k3) + clip(-5, 5) [+ sigmoid] in fp32 on the CUDA cores (the 8 -> 8
+// convolution before it runs on tensor cores, cvit_conv3d_halo_ndhwc): models/cryovit.py:33,39,49.
+int cvit_head_out_conv(const void* x, const float* w2, const float* b2, float* logits, float* probs, int64_t D, int64_t H,
+                       int64_t W, void* stream) {
+  if (!x || !w2 || !b2 || D <= 0 || H <= 0 || W <= 0 || (!logits && !probs)) {
+    set_error("head_out_conv: bad arguments");
+    return CVIT_ERR_INVALID;
+  }
+  const int smem2 = 3 * (TAIL_TH + 2) * (TAIL_TW + 2) * 16 + 27 * 8 * 4;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tail_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) {
+      set_error("head_out_conv: cudaFuncSetAttribute failed");
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t blocks = D * ((H + TAIL_TH - 1) / TAIL_TH) * ((W + TAIL_TW - 1) / TAIL_TW);
+  tail_conv_kernel<1, true><<<(unsigned)blocks, 256, smem2, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(x), w2, b2, nullptr, logits, probs, (int)D, (int)H, (int)W);
+  return check_launch("tail_conv_kernel<1>");
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------

@@ -36,6 +36,28 @@ def _conv_taps(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
     return wt.reshape(27 * cout_pad, cin)
 
 
+def halo_weight_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
+    """Conv3d weight [Cout, Cin, 3, 3, 3] (Cin in {8, 16, 32}) -> the shared-memory image csrc/conv_halo.cu keeps
+    resident: [kd*3+kh][mma][2 K chunks][cout_pad][8 channels]. For Cin >= 16 MMA i is (tap kw = i // (Cin/16),
+    16-channel step c2 = i % (Cin/16)) and its K chunks are the two halves of those 16 channels; for Cin == 8 an MMA
+    covers two neighbouring taps: (kw0, kw1), then (kw1 with zero weights, kw2)."""
+    cout, cin = w.shape[:2]
+    steps = cin // 16
+    n_mma = 3 * steps if cin >= 16 else 2
+    img = torch.zeros(9, n_mma, 2, cout_pad, 8, dtype=torch.float32)
+    wt = w.float().permute(2, 3, 4, 0, 1).reshape(9, 3, cout, cin)  # [kd*3+kh][kw][co][ci]
+    if cin >= 16:
+        for i in range(n_mma):
+            kw, c2 = divmod(i, steps)
+            for k in range(2):
+                img[:, i, k, :cout] = wt[:, kw, :, c2 * 16 + k * 8: c2 * 16 + k * 8 + 8]
+    else:
+        img[:, 0, 0, :cout] = wt[:, 0]
+        img[:, 0, 1, :cout] = wt[:, 1]
+        img[:, 1, 1, :cout] = wt[:, 2]  # chunk 0 of the second MMA re-reads tap kw1 against zero weights
+    return img.reshape(-1)
+
+
 class CryoVITHeadB200:
     def __init__(self, in_channels: int = 1536):
         self.in_channels = in_channels
@@ -84,7 +106,15 @@ class CryoVITHeadB200:
             ba, bb = torch.zeros(c2p), torch.zeros(c2p)
             ba[:c2], bb[:c2] = sd[p + "1.bias"], sd[p + "3.bias"]
             wT = sd[p + "5.weight"]  # [c2, c3, 1, 2, 2]
+            halo = {}
+            for tag, key, cin in (("a", "1", c1), ("b", "3", c2)):
+                if cin in (8, 16, 32):  # narrow layer: shared-memory halo kernel (csrc/conv_halo.cu)
+                    cp = 32 if c2 > 16 else 16
+                    hb = torch.zeros(cp)
+                    hb[:c2] = sd[p + key + ".bias"]
+                    halo[tag] = (bf(halo_weight_image(sd[p + key + ".weight"], cp)), f32(hb), cp)
             blocks.append({
+                "halo": halo,
                 "groups": max(8, c1 // 8), "gn_w": f32(sd[p + "0.weight"]), "gn_b": f32(sd[p + "0.bias"]),
                 "a_w": bf(_conv_taps(sd[p + "1.weight"], c2p)), "a_b": f32(ba), "d1": d1,
                 "b_w": bf(_conv_taps(sd[p + "3.weight"], c2p)), "b_b": f32(bb), "d2": d2,
@@ -92,8 +122,9 @@ class CryoVITHeadB200:
                 "c1": c1, "c2": c2, "c3": c3,
             })
         w["blocks"] = blocks
-        w["o1_w"] = f32(sd["output_layer.0.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8, 8))
-        w["o1_b"] = f32(sd["output_layer.0.bias"])
+        o1b = torch.zeros(16)
+        o1b[:8] = sd["output_layer.0.bias"]
+        w["o1_img"], w["o1_b16"] = bf(halo_weight_image(sd["output_layer.0.weight"], 16)), f32(o1b)
         w["o2_w"] = f32(sd["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8))
         w["o2_b"] = f32(sd["output_layer.2.bias"])
         self._w = w
@@ -129,10 +160,16 @@ class CryoVITHeadB200:
             vox = D * H * W
             ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
+            if "a" in b["halo"]:
+                ops.conv3d_halo(cur, b["halo"]["a"][0], b["halo"]["a"][1], nxt, b["d1"], b["halo"]["a"][2])
+            else:
+                ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            ops.conv3d_dilated(cur, b["b_w"], b["b_b"], nxt, b["d2"])
+            if "b" in b["halo"]:
+                ops.conv3d_halo(cur, b["halo"]["b"][0], b["halo"]["b"][1], nxt, b["d2"], b["halo"]["b"][2])
+            else:
+                ops.conv3d_dilated(cur, b["b_w"], b["b_b"], nxt, b["d2"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], 4 * vox * c3).view(D, 2 * H, 2 * W, c3)
             ops.convT_1x2x2(cur, b["t_w"], b["t_b"], nxt)
@@ -142,7 +179,8 @@ class CryoVITHeadB200:
         scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
         logits = torch.empty(D, H, W, device=self.device) if want_logits else None
         probs = torch.empty(D, H, W, device=self.device) if want_probs else None
-        ops.head_tail(cur, w_["o1_w"], w_["o1_b"], w_["o2_w"], w_["o2_b"], scratch, logits, probs)
+        ops.conv3d_halo(cur, w_["o1_img"], w_["o1_b16"], scratch, 1, 16)  # output_layer.0 + GELU on tensor cores
+        ops.head_out_conv(scratch, w_["o2_w"], w_["o2_b"], logits, probs)   # output_layer.2 + clip (+ sigmoid), fp32
         self.launches += 2
         return logits, probs
 

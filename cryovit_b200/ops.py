@@ -137,6 +137,16 @@ def conv3d_dilated(x, w_taps, bias, out, dil: int) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, _stream())
 
 
+def conv3d_halo(x, w_img, bias, out, dil: int, cout_pad: int) -> None:
+    """Narrow-layer (Cin 8/16/32) dilated conv + bias + GELU from a shared-memory halo tile; see the header."""
+    D, H, W, Cin = x.shape
+    if w_img.numel() * 2 != _lib.load().cvit_conv3d_halo_weight_bytes(Cin, cout_pad):
+        raise _lib.CryovitB200Error(f"conv3d_halo: weight image has {w_img.numel() * 2} bytes, expected "
+                                    f"{_lib.load().cvit_conv3d_halo_weight_bytes(Cin, cout_pad)}")
+    _lib.call("cvit_conv3d_halo_ndhwc", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, _stream())
+
+
 def convT_1x2x2(x, w_sub, bias4, out) -> None:
     D, H, W, Cin = x.shape
     Cout = w_sub.shape[0] // 4
@@ -151,6 +161,13 @@ def head_tail(x, w1, b1, w2, b2, scratch, logits=None, probs=None) -> None:
               _chk(logits, F32, "logits") if logits is not None else None,
               _chk(probs, F32, "probs") if probs is not None else None, _chk(scratch, BF16, "scratch"), D, H, W,
               _stream())
+
+
+def head_out_conv(x, w2, b2, logits=None, probs=None) -> None:
+    D, H, W, _ = x.shape
+    _lib.call("cvit_head_out_conv", _chk(x, BF16, "x"), _chk(w2, F32, "w2"), _chk(b2, F32, "b2"),
+              _chk(logits, F32, "logits") if logits is not None else None,
+              _chk(probs, F32, "probs") if probs is not None else None, D, H, W, _stream())
 
 
 def seg_stats(probs: torch.Tensor, labels: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:

@@ -140,6 +140,15 @@ int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bi
                               int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
                               void* stream);
 
+/* The same convolution for the NARROW layers (Cin in {8, 16, 32}; SynthesisBlocks 3-4 and output_layer.0,
+ * models/cryovit.py:26-33,68-78) from a shared-memory halo tile: each input voxel is staged once per depth tap
+ * instead of once per tap. w_img is the host-arranged shared-memory image of the weights (bf16,
+ * cvit_conv3d_halo_weight_bytes(Cin, Cout_pad) bytes; cryovit_b200.head.halo_weight_image builds it); Cout_pad in
+ * {16, 32} is the MMA N, Cout_valid (multiple of 8) the stored channel count = row pitch of out. */
+int64_t cvit_conv3d_halo_weight_bytes(int64_t Cin, int64_t Cout_pad);
+int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                           int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, void* stream);
+
 /* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
  * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;
  * bias4 fp32 [4 * Cout] (the bias repeated per sub-pixel); out bf16 [D, 2H, 2W, Cout]. */
@@ -152,6 +161,12 @@ int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4,
 int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                          float* logits, float* probs, void* scratch_bf16, int64_t D, int64_t H, int64_t W,
                          void* stream);
+
+/* The last convolution alone: Conv3d(8->1,k3) + clip(-5,5) [+ sigmoid], fp32 on the CUDA cores
+ * (models/cryovit.py:33,39,49); x bf16 [D,H,W,8] is the GELU output of output_layer.0, which runs on tensor cores
+ * through cvit_conv3d_halo_ndhwc. w2 fp32 [27][8]; logits / probs fp32 [D,H,W] (either may be NULL). */
+int cvit_head_out_conv(const void* x, const float* w2, const float* b2, float* logits, float* probs, int64_t D, int64_t H,
+                       int64_t W, void* stream);
 
 /* Masked segmentation statistics, one pass: over voxels with label > -1 (BaseModel._masked_predict,
  * models/base_model.py:91-112) accumulates out8 (fp64, caller zeroes) = {sum p, sum y, sum p*y | sum y*[p>=thr],

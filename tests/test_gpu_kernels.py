@@ -211,6 +211,32 @@ def test_conv3d_dilated(cuda_lib, D, H, W, Cin, Cout, dil):
     _close(out, ref, atol=2e-2, rtol=1e-2, what="conv3d_dilated")
 
 
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [
+    (5, 32, 16, 32, 32, 1),     # SB3-like, whole tiles
+    (9, 20, 13, 32, 32, 8),     # ragged H and W (partial border tiles), D > dil and D-range taps skipped at the ends
+    (3, 16, 24, 32, 32, 4),     # D <= dil: both outer depth taps are pure padding
+    (4, 17, 260, 32, 16, 2),    # SB4a: Cout 16
+    (4, 33, 40, 16, 16, 1),     # SB4b: Cin 16
+    (4, 16, 8, 8, 8, 1),        # output_layer.0: Cin 8 (two taps per MMA), Cout 8 of N = 16
+    (6, 50, 70, 8, 8, 1),
+    (130, 16, 8, 32, 32, 1),    # more tiles than SMs: persistent loop, ring wrap-around
+])
+def test_conv3d_halo(cuda_lib, D, H, W, Cin, Cout, dil):
+    from cryovit_b200 import ops
+    from cryovit_b200.head import halo_weight_image
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, 3, scale=(27 * Cin) ** -0.5, seed=2).bfloat16()
+    b = _rand(Cout, seed=3)
+    cout_pad = 32 if Cout > 16 else 16
+    bp = torch.zeros(cout_pad, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv3d_halo(x, halo_weight_image(w.cpu(), cout_pad).bfloat16().to(DEV), bp, out, dil, cout_pad)
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding="same", dilation=(dil, 1, 1))
+    ref = F.gelu(ref)[0].permute(1, 2, 3, 0)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what="conv3d_halo")
+
+
 @pytest.mark.parametrize("D,H,W,Cin,Cout", [(3, 8, 16, 192, 128), (2, 8, 16, 64, 32), (2, 8, 16, 32, 32), (2, 8, 16, 16, 8)])
 def test_convT(cuda_lib, D, H, W, Cin, Cout):
     from cryovit_b200 import ops
