@@ -127,3 +127,29 @@ def test_entry_point_logs_and_swallows_errors(cuda_lib, tmp_path, caplog):
     main([f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/m", "sample=Q18",
           "use_sam=True", "+dino_variant=dinov2_vits14_reg"])
     assert any("NotImplementedError" in r.getMessage() for r in caplog.records)
+
+
+def test_fused_pipeline_tomogram_to_mask(cuda_lib):
+    """f3: tomogram -> (ViT features in HBM) -> head -> mask, against the oracle run through the reference's two
+    halves (features rounded to fp16 in between, as on disk). Mask agreement >= 99.5 % (BASELINE north star)."""
+    from cryovit_b200.head import CryoVITHeadB200
+    from cryovit_b200.pipeline import segment_tomogram
+    from cryovit_b200.vit import CONFIGS, build_model, random_state_dict
+    from oracle import dinov2 as odino
+    from oracle import extract as oextract
+    from oracle import head as ohead
+    from oracle import preproc as opre
+
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    sd = random_state_dict(cfg, seed=0)
+    hsd = ohead.random_state_dict(384, seed=2)
+    tomo = np.random.default_rng(5).integers(0, 256, size=(6, 72, 100), dtype=np.uint8)  # not multiples of 16
+    vit = build_model(cfg.name, sd).cuda()
+    head = CryoVITHeadB200(384).load_state_dict(hsd).cuda()
+    mask = segment_tomogram(tomo, vit, head, batch_size=4)
+    assert mask.dtype == np.uint8 and mask.shape == tomo.shape
+    feats = oextract.dino_features(opre.dino_transform(opre.load_tomogram(tomo)), odino.OracleDino(sd, cfg.num_heads), 4)
+    want = ohead.forward(hsd, torch.from_numpy(feats).float().permute(1, 0, 2, 3)[None])[0, :, :72, :100]
+    agree = (torch.from_numpy(mask).bool() == (want >= 0.5)).float().mean().item()
+    print(f"\n[parity] fused pipeline mask agreement {agree:.5f}, positive fraction {float((want >= 0.5).float().mean()):.3f}")
+    assert agree >= 0.995, agree
