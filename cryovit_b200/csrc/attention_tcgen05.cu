@@ -442,26 +442,27 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         bool pv_seen = tile_it == 0;  // PV(t-1) known retired: O may be rescaled, P overwritten
         if (warp_active && valid == FA_BK) {
           // The whole 128-wide S row lives in registers: one TMEM read per tile, four loads in flight.
+          // The row max of each 32-column chunk is taken while the next chunk is still on its way from TMEM
+          // (a TMEM read moves 64 B/clk per scheduler: 16 KB = 256 cycles for the row, more than the 64 FMNMX3).
           uint32_t v[128];
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          tmem_ld_32x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          if (pending) publish();  // P(j-1): its TMEM store drained under the load above
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            tmem_ld_32x32(tS + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * ch]));
-          if (pending) publish();  // P(j-1): its TMEM store drained under the loads above
-          tmem_ld_wait();
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld_wait();
+            if (ch < 3) tmem_ld_32x32(tS + (ch + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * (ch + 1)]));
+#pragma unroll
+            for (int i = 32 * ch; i < 32 * ch + 32; i += 8) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                mx[u] = fmax3(mx[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
+            }
+          }
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bg + B_SFREE);  // the MMA warp may start S(j+1) under this tile's softmax
-          FA_PROF(1);  // TMEM -> registers
-          // ---- row max: 4 independent chains of 3-input max
-          float mx[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1]));
-#pragma unroll
-          for (int i = 8; i < 128; i += 8) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              mx[u] = fmax3(mx[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
-          }
+          FA_PROF(1);  // TMEM -> registers + row max
           const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           if (first) {
             m = mt;

@@ -157,3 +157,27 @@ def test_head_matches_reference_golden(cuda_lib):
         assert err.max() < 6e-3
         probs = head.forward(x.float().permute(0, 2, 1, 3, 4).cuda())
         np.testing.assert_allclose(probs.cpu().numpy(), ref[f"head_{tag}_probs"], atol=2e-3)
+
+
+def test_feature_stream_matches_blocking_extract(cuda_lib):
+    """TomogramFeatureStream (copies on their own streams, recycled slots) returns exactly what the blocking
+    extract_tomogram returns, for tomograms of different shapes and dtypes submitted back to back."""
+    from cryovit_b200.extract import TomogramFeatureStream, extract_tomogram
+    from cryovit_b200.vit import CONFIGS, build_model, random_state_dict
+
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    model = build_model(cfg.name, random_state_dict(cfg, seed=0)).cuda()
+    rng = np.random.default_rng(11)
+    tomos = [rng.integers(0, 256, size=(5, 64, 96), dtype=np.uint8), rng.random((3, 50, 70), dtype=np.float32),
+             rng.integers(0, 256, size=(7, 32, 48), dtype=np.uint8), rng.integers(0, 256, size=(5, 64, 96), dtype=np.uint8)]
+    stream = TomogramFeatureStream(model, batch_size=4, depth=2)
+    got = []
+    tickets = []
+    for t in tomos:
+        tickets.append(stream.submit(t))
+        if len(tickets) > 1:
+            got.append(tickets.pop(0).result().copy())  # valid until `depth` further submits: copy out
+    got.append(tickets.pop(0).result().copy())
+    for t, g in zip(tomos, got):
+        want = extract_tomogram(t, model, batch_size=4)
+        assert g.dtype == np.float16 and g.shape == want.shape and np.array_equal(g, want)
