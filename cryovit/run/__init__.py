@@ -1,1 +1,1 @@
-from . import dino_features  # noqa: F401
+from . import dino_features, infer_model  # noqa: F401

@@ -153,3 +153,30 @@ def test_fused_pipeline_tomogram_to_mask(cuda_lib):
     agree = (torch.from_numpy(mask).bool() == (want >= 0.5)).float().mean().item()
     print(f"\n[parity] fused pipeline mask agreement {agree:.5f}, positive fraction {float((want >= 0.5).float().mean()):.3f}")
     assert agree >= 0.995, agree
+
+
+def test_run_inference_writes_prediction_layout(cuda_lib, tmp_path):
+    """infer_model.run_inference + PredictionWriter layout: <result_dir>/<stem>.hdf with float32 `data` and uint8
+    `<label>_preds`; a file that already carries dino_features skips the ViT and gives the same mask."""
+    from cryovit.run.infer_model import run_inference
+    from cryovit_b200.extract import extract_tomogram
+    from cryovit_b200.head import CryoVITHeadB200
+    from cryovit_b200.host import hdf
+    from cryovit_b200.pipeline import segment_tomogram
+    from cryovit_b200.vit import CONFIGS, build_model, random_state_dict
+    from oracle import head as ohead
+
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    vit = build_model(cfg.name, random_state_dict(cfg, seed=0)).cuda()
+    head = CryoVITHeadB200(384).load_state_dict(ohead.random_state_dict(384, seed=2)).cuda()
+    tomo = np.random.default_rng(6).integers(0, 256, size=(4, 64, 80), dtype=np.uint8)
+    hdf.write_tomogram(tmp_path / "in" / "raw.hdf", {"data": tomo})
+    hdf.write_tomogram(tmp_path / "in" / "feat.hdf", {"data": tomo, "dino_features": extract_tomogram(tomo, vit, 4)})
+    paths = run_inference([tmp_path / "in" / "raw.hdf", tmp_path / "in" / "feat.hdf"], head, tmp_path / "out", 0.5, "mito", vit, 4)
+    assert [p.name for p in paths] == ["raw.hdf", "feat.hdf"]
+    want = segment_tomogram(tomo, vit, head, 4)
+    for p in paths:
+        out = hdf.read_tomogram(p)
+        assert sorted(out) == ["data", "mito_preds"]
+        assert out["data"].dtype == np.float32 and np.allclose(out["data"], tomo.astype(np.float32) / 255.0)
+        assert out["mito_preds"].dtype == np.uint8 and np.array_equal(out["mito_preds"], want)
