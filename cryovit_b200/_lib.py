@@ -42,6 +42,18 @@ SIGNATURES: dict[str, list] = {
     "cvit_head_tail_fused": [P, P, P, P, P, P, P, P, I64, I64, I64, P],
     "cvit_head_out_conv": [P, P, P, P, P, I64, I64, I64, P],
     "cvit_seg_stats": [P, P, I64, F32, P, P],
+    "cvit_conv3d_dilated_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
+    "cvit_conv3d_halo_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
+    "cvit_convT_1x2x2_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I32, P],
+    "cvit_gelu_fwd_bf16": [P, P, I64, P],
+    "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
+    "cvit_dice_bwd": [P, P, P, P, F32, P, I64, P],
+    "cvit_colsum_bf16": [P, P, I64, I64, P],
+    "cvit_groupnorm_bwd_ndhwc_bf16": [P, P, P, P, P, P, P, I64, I64, I64, F32, P],
+    "cvit_pixel_unshuffle_1x2x2_bf16": [P, P, I64, I64, I64, I64, P],
+    "cvit_ndhwc_to_cfirst_padded": [P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_wgrad_splitk": [P, P, P, P, I64, I64, I64, I64, I64, I64, P],
+    "cvit_adamw_f32": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, F32, P],
 }
 
 _lib: ctypes.CDLL | None = None

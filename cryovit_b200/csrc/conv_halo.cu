@@ -56,6 +56,7 @@ struct HaloArgs {
   const float* bias;           // [COUT] (zero padded)
   __nv_bfloat16* out;          // [D, H, W, n_valid]
   int D, H, W, dil, n_valid;
+  int act;  // 1 = GELU (inference), 0 = store the pre-activation (training forward, input gradients)
 };
 
 // K-major, SWIZZLE_NONE shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 @[0,14), LBO>>4 @[16,30)
@@ -226,8 +227,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float a = gelu_erf(__uint_as_float(v[c + 2 * i]) + __ldg(args.bias + c + 2 * i));
-              const float b = gelu_erf(__uint_as_float(v[c + 2 * i + 1]) + __ldg(args.bias + c + 2 * i + 1));
+              float a = __uint_as_float(v[c + 2 * i]) + __ldg(args.bias + c + 2 * i);
+              float b = __uint_as_float(v[c + 2 * i + 1]) + __ldg(args.bias + c + 2 * i + 1);
+              if (args.act) { a = gelu_erf(a); b = gelu_erf(b); }
               pk[i] = pack_bf16x2(a, b);
             }
             *reinterpret_cast<uint4*>(o + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -288,9 +290,19 @@ extern "C" int64_t cvit_conv3d_halo_weight_bytes(int64_t Cin, int64_t Cout_pad) 
   return -1;
 }
 
+extern "C" int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                                          int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                          void* stream);
+
 extern "C" int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
                                       int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil,
                                       void* stream) {
+  return cvit_conv3d_halo_ndhwc_act(x, w_img, bias, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, 1, stream);
+}
+
+extern "C" int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                                          int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                          void* stream) {
   if (!x || !w_img || !bias || !out || D <= 0 || H <= 0 || W <= 0 || dil <= 0 || Cout_valid <= 0 || Cout_valid > Cout_pad ||
       (Cout_valid % 8) != 0) {
     set_error("conv3d_halo: bad arguments (D=%lld H=%lld W=%lld Cin=%lld Cout=%lld/%lld dil=%lld)", (long long)D, (long long)H,
@@ -310,10 +322,12 @@ extern "C" int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const fl
   a.W = (int)W;
   a.dil = (int)dil;
   a.n_valid = (int)Cout_valid;
+  a.act = act;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32 && Cout_pad == 32) return launch_halo<32, 32>(x, a, st);
   if (Cin == 32 && Cout_pad == 16) return launch_halo<32, 16>(x, a, st);
   if (Cin == 16 && Cout_pad == 16) return launch_halo<16, 16>(x, a, st);
+  if (Cin == 16 && Cout_pad == 32) return launch_halo<16, 32>(x, a, st);
   if (Cin == 8 && Cout_pad == 16) return launch_halo<8, 16>(x, a, st);
   set_error("conv3d_halo: no kernel for Cin=%lld Cout_pad=%lld (narrow layers: Cin 8/16/32, Cout 16/32)", (long long)Cin,
             (long long)Cout_pad);

@@ -112,7 +112,12 @@ static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t 
   const int BH = 128 / BW;
   args.BW = BW;
   args.BH = BH;
-  const int bn = Cout;
+  // one N tile for the forward layers' channel counts; wider outputs (input gradients: Cout = the layer's Cin) tile N
+  const int bn = (Cout == 192 || Cout == 64 || Cout == 32) ? Cout : (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 0;
+  if (!bn) {
+    set_error("conv3: Cout=%d unsupported", Cout);
+    return CVIT_ERR_UNSUPPORTED;
+  }
   const int epi = EPI_BIAS_GELU;
   CUtensorMap tmA, tmB;
   {
@@ -124,7 +129,9 @@ static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t 
   }
   int rc = make_tmap_rows(&tmB, w, (int64_t)27 * Cout, Cin, Cin, bn, kspan);
   if (rc) return rc;
-  const int num_tiles = D * ((H + BH - 1) / BH) * ((W + BW - 1) / BW);
+  const int num_tiles = D * ((H + BH - 1) / BH) * ((W + BW - 1) / BW) * (Cout / bn);
+  CVIT_GEMM_CASE(256, EPI_BIAS_GELU, AMODE_CONV3, 128)
+  CVIT_GEMM_CASE(128, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(192, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(64, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(32, EPI_BIAS_GELU, AMODE_CONV3, 64)
@@ -146,6 +153,7 @@ static GemmArgs base_args(int64_t M, int64_t N, int64_t K, void* out, int64_t ld
   a.out = out;
   a.ldo = (int)ldo;
   a.n_valid = (int)N;
+  a.act = 1;
   return a;
 }
 
@@ -188,9 +196,19 @@ int cvit_patch_embed_gemm(const void* patches, int64_t lda, const void* W, const
   return gemm_rows(patches, lda, W, a, EPI_PATCH_EMBED, (cudaStream_t)stream);
 }
 
+int cvit_conv3d_dilated_ndhwc_act(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* stream);
+
 int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
                               int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
                               void* stream) {
+  return cvit_conv3d_dilated_ndhwc_act(x, w_taps, bias, out, D, H, W, Cin, Cout, Cout_valid, dil, 1, stream);
+}
+
+int cvit_conv3d_dilated_ndhwc_act(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* stream) {
   if (!bias) { set_error("conv3d: bias is required"); return CVIT_ERR_INVALID; }
   GemmArgs a = base_args(D * H * W, Cout, Cin, out, Cout_valid);
   a.bias = bias;
@@ -199,17 +217,27 @@ int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bi
   a.W = (int)W;
   a.dil = (int)dil;
   a.n_valid = (int)Cout_valid;
+  a.act = act;
   return conv3_rows(x, w_taps, a, (cudaStream_t)stream);
 }
 
+int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* stream);
+
 int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
                            int64_t W, int64_t Cin, int64_t Cout, void* stream) {
+  return cvit_convT_1x2x2_ndhwc_act(x, w_sub, bias4, out, D, H, W, Cin, Cout, 1, stream);
+}
+
+int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* stream) {
   if (!bias4) { set_error("convT: bias is required"); return CVIT_ERR_INVALID; }
   GemmArgs a = base_args(D * H * W, 4 * Cout, Cin, out, Cout);
   a.bias = bias4;
   a.H = (int)H;
   a.W = (int)W;
   a.c3 = (int)Cout;
+  a.act = act;
   return gemm_rows(x, Cin, w_sub, a, EPI_CONVT_GELU, (cudaStream_t)stream);
 }
 

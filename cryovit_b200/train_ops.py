@@ -1,0 +1,102 @@
+"""Torch-tensor front end of the TRAINING entry points of the C ABI (see include/cryovit_b200.h, "Head TRAINING")."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ops import BF16, F32, _chk, _stream
+
+
+def conv3d_dilated_act(x, w_taps, bias, out, dil: int, act: bool) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_taps.shape[0] // 27
+    _lib.call("cvit_conv3d_dilated_ndhwc_act", _chk(x, BF16, "x"), _chk(w_taps, BF16, "w_taps"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, int(act), _stream())
+
+
+def conv3d_halo_act(x, w_img, bias, out, dil: int, cout_pad: int, act: bool) -> None:
+    D, H, W, Cin = x.shape
+    _lib.call("cvit_conv3d_halo_ndhwc_act", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, int(act), _stream())
+
+
+def convT_act(x, w_sub, bias4, out, act: bool) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_sub.shape[0] // 4
+    _lib.call("cvit_convT_1x2x2_ndhwc_act", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, int(act), _stream())
+
+
+def gelu_fwd(z, a) -> None:
+    _lib.call("cvit_gelu_fwd_bf16", _chk(z, BF16, "z"), _chk(a, BF16, "a"), z.numel(), _stream())
+
+
+def gelu_bwd(da, z, dz) -> None:
+    _lib.call("cvit_gelu_bwd_bf16", _chk(da, BF16, "da"), _chk(z, BF16, "z"), _chk(dz, BF16, "dz"), z.numel(), _stream())
+
+
+def dice_bwd(logits, probs, labels, stats8, dlogit8, scale: float = 1.0) -> None:
+    _lib.call("cvit_dice_bwd", _chk(logits, F32, "logits"), _chk(probs, F32, "probs"), _chk(labels, F32, "labels"),
+              _chk(stats8, torch.float64, "stats8"), float(scale), _chk(dlogit8, BF16, "dlogit8"), logits.numel(), _stream())
+
+
+def colsum(x, out) -> None:
+    R, C = x.numel() // x.shape[-1], x.shape[-1]
+    _lib.call("cvit_colsum_bf16", _chk(x, BF16, "x"), _chk(out, F32, "out"), R, C, _stream())
+
+
+def groupnorm_bwd(x, dy, dx, gamma, stats, dgamma, dbeta, groups: int, eps: float) -> None:
+    C = x.shape[-1]
+    _lib.call("cvit_groupnorm_bwd_ndhwc_bf16", _chk(x, BF16, "x"), _chk(dy, BF16, "dy"), _chk(dx, BF16, "dx"),
+              _chk(gamma, F32, "gamma"), _chk(stats, F32, "stats"), _chk(dgamma, F32, "dgamma"), _chk(dbeta, F32, "dbeta"),
+              x.numel() // C, C, groups, float(eps), _stream())
+
+
+def pixel_unshuffle(src, dst) -> None:
+    D, H2, W2, C = src.shape
+    _lib.call("cvit_pixel_unshuffle_1x2x2_bf16", _chk(src, BF16, "src"), _chk(dst, BF16, "dst"), D, H2 // 2, W2 // 2, C, _stream())
+
+
+def padded_geometry(D: int, H: int, W: int, pd: int, ph: int, pw: int) -> tuple[int, int, int, int]:
+    """(Dp, Hp, Wp, pitch) of the padded channels-first operand: Wp and the row pitch are multiples of 8."""
+    Dp, Hp, Wp = D + 2 * pd, H + 2 * ph, (W + 2 * pw + 7) // 8 * 8
+    return Dp, Hp, Wp, Dp * Hp * Wp
+
+
+def to_cfirst_padded(x, out, pd: int, ph: int, pw: int, wshift: int = 0) -> None:
+    """x bf16 [D,H,W,C] -> out bf16 [C, pitch] (channels first, zero padded, columns shifted by wshift)."""
+    D, H, W, C = x.shape
+    _, _, Wp, _ = padded_geometry(D, H, W, pd, ph, pw)
+    _lib.call("cvit_ndhwc_to_cfirst_padded", _chk(x, BF16, "x"), _chk(out, BF16, "out"), D, H, W, C, pd, ph, pw, Wp, wshift,
+              out.shape[1], _stream())
+
+
+def conv_weight_gradient(x, dz, dil: int, xt_bufs=None, dzt_buf=None) -> torch.Tensor:
+    """dW[27, Cout, Cin] (tap = (kd*3+kh)*3+kw, fp32) of a 3x3x3 depth-dilated "same" convolution from its input x and
+    output gradient dz (both bf16 [D,H,W,C]): three column-shifted channels-first copies of x, one of dz, three
+    9-tap split-K GEMMs."""
+    D, H, W, Cin = x.shape
+    Cout = dz.shape[-1]
+    Dp, Hp, Wp, pitch = padded_geometry(D, H, W, dil, 1, 1)
+    dev = x.device
+    dzt = dzt_buf[:Cout * pitch].view(Cout, pitch) if dzt_buf is not None else torch.empty(Cout, pitch, device=dev, dtype=BF16)
+    to_cfirst_padded(dz, dzt, dil, 1, 1, 0)
+    koffs = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
+    dw = torch.zeros(3, 9, Cout, Cin, device=dev, dtype=F32)
+    for kw in range(3):
+        xt = xt_bufs[kw % len(xt_bufs)][:Cin * pitch].view(Cin, pitch) if xt_bufs is not None else torch.empty(Cin, pitch, device=dev, dtype=BF16)
+        to_cfirst_padded(x, xt, dil, 1, 1, kw - 1)
+        wgrad_splitk(dzt, xt, dw[kw], koffs, pitch)
+    return dw.permute(1, 0, 2, 3).reshape(27, Cout, Cin)
+
+
+def wgrad_splitk(at, bt, out, koffs, k: int) -> None:
+    """out[t, m, n] += sum_k at[m, k] * bt[n, k + koffs[t]]; at [M, pitch], bt [N, pitch] bf16, out fp32 [T, M, N]."""
+    T, M, N = out.shape
+    _lib.call("cvit_wgrad_splitk", _chk(at, BF16, "at"), _chk(bt, BF16, "bt"), _chk(out, F32, "out"),
+              _chk(koffs, torch.int32, "koffs"), M, N, k, at.shape[1], bt.shape[1], T, _stream())
+
+
+def adamw(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    _lib.call("cvit_adamw_f32", _chk(p, F32, "p"), _chk(g, F32, "g"), _chk(m, F32, "m"), _chk(v, F32, "v"), p.numel(),
+              float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())

@@ -168,6 +168,67 @@ int cvit_head_tail_fused(const void* x, const float* w1, const float* b1, const 
 int cvit_head_out_conv(const void* x, const float* w2, const float* b2, float* logits, float* probs, int64_t D, int64_t H,
                        int64_t W, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Head TRAINING (BASELINE config 5; models/base_model.py:58-63,91-164, models/losses.py:17-32,
+ * configs/trainer/fit.yaml). Forward runs the inference kernels with act = 0 (pre-activations are kept) followed by
+ * cvit_gelu_fwd_bf16; input gradients are the same convolution kernels on flipped / transposed weights (act = 0);
+ * weight gradients are split-K GEMMs over channels-first, zero-padded copies of the activations.
+ */
+
+/* The three convolution entry points with an explicit activation switch: act = 1 GELU after the bias (the
+ * inference entry points above), act = 0 none. */
+int cvit_conv3d_dilated_ndhwc_act(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* stream);
+int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                               void* stream);
+int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* stream);
+
+/* a = gelu(z) and dz = da * gelu'(z) (exact erf form, nn.GELU() default), bf16, n a multiple of 8. */
+int cvit_gelu_fwd_bf16(const void* z, void* a, int64_t n, void* stream);
+int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void* stream);
+
+/* Gradient of DiceLoss (models/losses.py:17-32) w.r.t. the raw logits, through sigmoid and clip(-5, 5)
+ * (models/cryovit.py:39,49), masked to label > -1 (models/base_model.py:91-112). stats8 = the device-resident sums
+ * of cvit_seg_stats for the same forward pass; scale multiplies the gradient (1 / world size for data parallel
+ * averaging). Output: bf16 [n][8] with channel 0 = dL/dlogit and channels 1..7 zero (the operand of the narrow
+ * convolution kernel that back-propagates through output_layer.2). */
+int cvit_dice_bwd(const float* logits, const float* probs, const float* labels, const double* stats8, float scale,
+                  void* dlogit8_bf16, int64_t n, void* stream);
+
+/* out[c] += sum over rows of x[r, c] (bias gradients). x bf16 [R, C], out fp32 [C] (caller zeroes), C % 8 == 0. */
+int cvit_colsum_bf16(const void* x, float* out, int64_t R, int64_t C, void* stream);
+
+/* GroupNorm backward over a channels-last bf16 volume (models/cryovit.py:69): x = the forward INPUT, stats = the
+ * forward statistics buffer of cvit_groupnorm_ndhwc_bf16; writes dx (bf16) and dgamma / dbeta (fp32 [C], zeroed
+ * here). */
+int cvit_groupnorm_bwd_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats,
+                                  float* dgamma, float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, void* stream);
+
+/* [D, 2H, 2W, C] -> [D, H, W, 4C], column (i*2+j)*C + c: the transposed convolution's output gradient laid out as the
+ * rows of the GEMM that yields its input gradient. */
+int cvit_pixel_unshuffle_1x2x2_bf16(const void* src, void* dst, int64_t D, int64_t H, int64_t W, int64_t C, void* stream);
+
+/* channels-last bf16 [D,H,W,C] -> channels-first, zero-padded bf16 [C][pitch]: position p over the padded volume
+ * (D + 2 pd, H + 2 ph, Wp) holds voxel (dp - pd, hp - ph, wp - pw + wshift) or zero; Wp >= W + 2 pw is the padded row
+ * pitch, pitch >= the padded size, multiple of 8. Operand layout of cvit_wgrad_splitk (whose shifts must be multiples
+ * of 8 elements: make Wp a multiple of 8 and take the +-1 column taps from copies made with wshift = -1 / +1). */
+int cvit_ndhwc_to_cfirst_padded(const void* src, void* dst, int64_t D, int64_t H, int64_t W, int64_t C, int64_t pd,
+                                int64_t ph, int64_t pw, int64_t Wp, int64_t wshift, int64_t pitch, void* stream);
+
+/* out[t][m][n] += sum_k At[m][k] * Bt[n][k + koffs[t]]  for t < ntaps (fp32 out, caller zeroes; terms whose shifted
+ * index falls outside [0, K) are zero). At bf16 [M][pitch_a], Bt bf16 [N][pitch_b]; koffs int32 [ntaps] on the
+ * device, every shift a multiple of 8 (TMA start alignment). Split over the whole GPU along K; every partial tile is added with red.global.add.f32. */
+int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, const int* koffs, int64_t M, int64_t N, int64_t K,
+                      int64_t pitch_a, int64_t pitch_b, int64_t ntaps, void* stream);
+
+/* AdamW step over a flat fp32 parameter vector, torch.optim.AdamW semantics (models/base_model.py:58-63):
+ * decoupled weight decay, bias-corrected moments; g is multiplied by grad_scale first. step counts from 1. */
+int cvit_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int64_t step, float grad_scale, void* stream);
+
 /* Masked segmentation statistics, one pass: over voxels with label > -1 (BaseModel._masked_predict,
  * models/base_model.py:91-112) accumulates out8 (fp64, caller zeroes) = {sum p, sum y, sum p*y | sum y*[p>=thr],
  * sum [p>=thr] | sum y*[p>.5], sum (1-y)*[p>.5], sum y*(1-[p>.5])}: the reductions behind DiceLoss

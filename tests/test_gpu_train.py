@@ -1,0 +1,144 @@
+"""GPU suite for the head-training kernels: every backward piece against torch autograd (fp32) on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(DEV)
+
+
+def _relerr(got, ref):
+    return ((got.float() - ref.float()).norm() / ref.float().norm().clamp_min(1e-12)).item()
+
+
+def test_gelu_fwd_bwd(cuda_lib):
+    from cryovit_b200 import train_ops as T
+    z = (_rand(4096, 64, scale=2.0, seed=1)).bfloat16()
+    da = _rand(4096, 64, seed=2).bfloat16()
+    a, dz = torch.empty_like(z), torch.empty_like(z)
+    T.gelu_fwd(z, a)
+    T.gelu_bwd(da, z, dz)
+    zr = z.float().requires_grad_(True)
+    ar = F.gelu(zr)
+    ar.backward(da.float())
+    assert _relerr(a, ar.detach()) < 4e-3 and _relerr(dz, zr.grad) < 4e-3
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(6, 12, 20, 64, 192, 2), (5, 16, 8, 32, 32, 1), (4, 9, 11, 16, 16, 1),
+                                                 (3, 16, 16, 8, 8, 1), (9, 8, 8, 192, 64, 4)])
+def test_conv_weight_gradient_splitk(cuda_lib, D, H, W, Cin, Cout, dil):
+    """dW[tap][co][ci] from channels-first padded copies + split-K GEMM == autograd of F.conv3d."""
+    from cryovit_b200 import train_ops as T
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    dz = _rand(D, H, W, Cout, seed=2).bfloat16()
+    dw = T.conv_weight_gradient(x, dz, dil)
+    w = torch.zeros(Cout, Cin, 3, 3, 3, device=DEV, requires_grad=True)
+    y = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w, None, padding="same", dilation=(dil, 1, 1))
+    y.backward(dz.float().permute(3, 0, 1, 2)[None])
+    ref = w.grad.permute(2, 3, 4, 0, 1).reshape(27, Cout, Cin)
+    assert _relerr(dw, ref) < 5e-3, _relerr(dw, ref)
+
+
+def test_linear_weight_gradient_splitk(cuda_lib):
+    """One-tap case (1x1x1 projection, transposed conv): dW[M, N] = dZ^T X over many rows."""
+    from cryovit_b200 import train_ops as T
+    R, M, N = 5000, 200, 328
+    x = _rand(R, 1, 1, N, seed=1).bfloat16()
+    dz = _rand(R, 1, 1, M, seed=2).bfloat16()
+    pitch = T.padded_geometry(R, 1, 1, 0, 0, 0)[3]
+    xt = torch.empty(N, pitch, device=DEV, dtype=torch.bfloat16)
+    dzt = torch.empty(M, pitch, device=DEV, dtype=torch.bfloat16)
+    T.to_cfirst_padded(x, xt, 0, 0, 0)
+    T.to_cfirst_padded(dz, dzt, 0, 0, 0)
+    assert torch.equal(xt.view(N, R, 8)[:, :, 0], x.view(R, N).t()) and torch.all(xt.view(N, R, 8)[:, :, 1:] == 0)
+    dw = torch.zeros(1, M, N, device=DEV)
+    T.wgrad_splitk(dzt, xt, dw, torch.zeros(1, dtype=torch.int32, device=DEV), pitch)
+    ref = dz.view(R, M).float().t() @ x.view(R, N).float()
+    assert _relerr(dw[0], ref) < 5e-3
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil,halo", [(6, 12, 20, 64, 128, 2, False), (5, 8, 16, 192, 1024, 3, False),
+                                                      (5, 16, 8, 32, 32, 1, True), (4, 9, 11, 16, 32, 2, True), (3, 16, 16, 8, 8, 1, True)])
+def test_conv_input_gradient_is_conv_with_flipped_weights(cuda_lib, D, H, W, Cin, Cout, dil, halo):
+    """dX = conv(dZ, W flipped in space, transposed in channels), no bias, no activation: the forward kernels with act=0.
+    Here Cin / Cout are those of the GRADIENT convolution (Cin = channels of dZ)."""
+    from cryovit_b200 import train_ops as T
+    from cryovit_b200.head import _conv_taps, halo_weight_image
+    dz = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = _rand(Cin, Cout, 3, 3, 3, scale=(27 * Cin) ** -0.5, seed=2).bfloat16()  # forward weight [co_fwd = Cin, ci_fwd = Cout]
+    wg = w.float().flip(2, 3, 4).transpose(0, 1).contiguous()                   # gradient conv weight [Cout, Cin, 3,3,3]
+    out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    if halo:
+        cp = 32 if Cout > 16 else 16
+        T.conv3d_halo_act(dz, halo_weight_image(wg.cpu(), cp).bfloat16().to(DEV), torch.zeros(cp, device=DEV), out, dil, cp, False)
+    else:
+        T.conv3d_dilated_act(dz, _conv_taps(wg.cpu(), Cout).bfloat16().to(DEV), torch.zeros(Cout, device=DEV), out, dil, False)
+    xr = torch.zeros(1, Cout, D, H, W, device=DEV, requires_grad=True)
+    y = F.conv3d(xr, w.float(), None, padding="same", dilation=(dil, 1, 1))
+    y.backward(dz.float().permute(3, 0, 1, 2)[None])
+    assert _relerr(out, xr.grad[0].permute(1, 2, 3, 0)) < 6e-3
+
+
+@pytest.mark.parametrize("C,G", [(1024, 128), (128, 16), (32, 8)])
+def test_groupnorm_backward(cuda_lib, C, G):
+    from cryovit_b200 import ops, train_ops as T
+    DHW = 3 * 10 * 12
+    x = (_rand(DHW, C, seed=1) * 1.5 + 0.3).bfloat16()
+    dy = _rand(DHW, C, seed=2).bfloat16()
+    gamma, beta = 1.0 + 0.1 * _rand(C, seed=3), 0.1 * _rand(C, seed=4)
+    y = torch.empty_like(x)
+    stats = torch.zeros(2 * G, device=DEV)
+    ops.groupnorm_ndhwc(x.view(3, 10, 12, C), y.view(3, 10, 12, C), gamma, beta, stats, G, 1e-3)
+    dx = torch.empty_like(x)
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    T.groupnorm_bwd(x, dy, dx, gamma, stats, dg, db, G, 1e-3)
+    xr = x.float().t().reshape(1, C, DHW).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, G, gr, br, 1e-3)
+    yr.backward(dy.float().t().reshape(1, C, DHW))
+    assert _relerr(dx, xr.grad[0].t()) < 6e-3 and _relerr(dg, gr.grad) < 6e-3 and _relerr(db, br.grad) < 6e-3
+
+
+def test_dice_backward_pixel_unshuffle_colsum_adamw(cuda_lib):
+    from cryovit_b200 import ops, train_ops as T
+    g = torch.Generator().manual_seed(5)
+    n = 4 * 32 * 48
+    raw = (torch.randn(n, generator=g) * 3).to(DEV)
+    labels = torch.randint(-1, 2, (n,), generator=g).float().to(DEV)
+    logits = raw.clip(-5, 5)
+    probs = torch.sigmoid(logits)
+    stats = ops.seg_stats(probs, labels)
+    d8 = torch.empty(n, 8, device=DEV, dtype=torch.bfloat16)
+    T.dice_bwd(logits, probs, labels, stats, d8, 0.5)
+    rr = raw.clone().requires_grad_(True)
+    p = torch.sigmoid(rr.clip(-5, 5))
+    m = labels > -1
+    loss = 1 - 2 * (labels[m] * p[m]).sum() / (labels[m].sum() + p[m].sum() + 1e-3)
+    loss.backward()
+    assert torch.all(d8[:, 1:] == 0) and _relerr(d8[:, 0], 0.5 * rr.grad) < 6e-3
+    # pixel un-shuffle
+    src = _rand(2, 6, 8, 16, seed=6).bfloat16()
+    dst = torch.empty(2, 3, 4, 64, device=DEV, dtype=torch.bfloat16)
+    T.pixel_unshuffle(src, dst)
+    ref = src.view(2, 3, 2, 4, 2, 16).permute(0, 1, 3, 2, 4, 5).reshape(2, 3, 4, 64)
+    assert torch.equal(dst, ref)
+    # column sums
+    x = _rand(777, 192, seed=7).bfloat16()
+    cs = torch.zeros(192, device=DEV)
+    T.colsum(x, cs)
+    assert _relerr(cs, x.float().sum(0)) < 1e-5
+    # AdamW against torch.optim.AdamW over three steps
+    pr = torch.nn.Parameter(_rand(1000, seed=8))
+    opt = torch.optim.AdamW([pr], lr=1e-4, weight_decay=1e-3)
+    pm = pr.detach().clone()
+    m1, v1 = torch.zeros_like(pm), torch.zeros_like(pm)
+    for step in range(1, 4):
+        grad = _rand(1000, seed=10 + step)
+        pr.grad = grad.clone()
+        opt.step()
+        T.adamw(pm, grad, m1, v1, 1e-4, 0.9, 0.999, 1e-8, 1e-3, step)
+    assert (pm - pr.detach()).abs().max().item() < 1e-6
