@@ -45,6 +45,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_conv3d_dilated_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
     "cvit_conv3d_halo_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
     "cvit_convT_1x2x2_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I32, P],
+    "cvit_linear_bias_bf16_nvalid": [P, I64, P, P, P, I64, I64, I64, I64, I64, P],
     "cvit_gelu_fwd_bf16": [P, P, I64, P],
     "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
     "cvit_dice_bwd": [P, P, P, P, F32, P, I64, P],

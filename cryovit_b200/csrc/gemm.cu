@@ -74,6 +74,9 @@ static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, i
   const int num_tiles = (int)(((M + GEMM_BM - 1) / GEMM_BM) * (N / bn));
   CVIT_GEMM_CASE(256, EPI_BIAS, AMODE_ROWS, 128)
   CVIT_GEMM_CASE(128, EPI_BIAS, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(64, EPI_BIAS, AMODE_ROWS, 128)   // transposed-convolution input gradients (training)
+  CVIT_GEMM_CASE(32, EPI_BIAS, AMODE_ROWS, 128)
+  CVIT_GEMM_CASE(32, EPI_BIAS, AMODE_ROWS, 64)
   CVIT_GEMM_CASE(256, EPI_BIAS_GELU, AMODE_ROWS, 128)
   CVIT_GEMM_CASE(128, EPI_BIAS_GELU, AMODE_ROWS, 128)
   CVIT_GEMM_CASE(256, EPI_BIAS_SWIGLU, AMODE_ROWS, 128)
@@ -165,6 +168,17 @@ int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float
   GemmArgs a = base_args(M, N, K, out, ldo);
   a.bias = bias;
   return gemm_rows(A, lda, W, a, gelu ? EPI_BIAS_GELU : EPI_BIAS, (cudaStream_t)stream);
+}
+
+// Same as cvit_linear_bias_bf16 for an output narrower than the (zero-row-padded) weight: columns >= n_valid are
+// computed but not stored, ldo is the true row pitch (transposed-convolution input gradient with 16 channels).
+int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                 int64_t M, int64_t N, int64_t K, int64_t n_valid, void* stream) {
+  if (!bias) { set_error("linear_bias: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(M, N, K, out, ldo);
+  a.bias = bias;
+  a.n_valid = (int)n_valid;
+  return gemm_rows(A, lda, W, a, EPI_BIAS, (cudaStream_t)stream);
 }
 
 int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,

@@ -1,0 +1,307 @@
+"""CryoVIT head TRAINING on B200 (BASELINE config 5; reference models/cryovit.py:10-83, models/base_model.py:58-63,
+91-164, models/losses.py:17-32, configs/trainer/fit.yaml: AdamW lr 1e-4 / wd 1e-3, masked DiceLoss, batch of one
+tomogram crop per GPU, 16-mixed precision).
+
+One training step = forward with kept pre-activations -> masked Dice loss -> backward -> (data parallel) all-reduce of
+ONE flat fp32 gradient bucket over NCCL -> fused AdamW on fp32 master weights. All arithmetic of the step runs in the
+sm_100a kernels behind the C ABI:
+
+  forward    the inference convolution kernels with act = 0 (they store the pre-activation z) + cvit_gelu_fwd
+  dX         the SAME convolution kernels run on spatially flipped, channel-transposed weights (a "same" stride-1
+             convolution's input gradient is a "same" convolution), act = 0, zero bias
+  dW         cvit_wgrad_splitk: split-K tcgen05 GEMMs over channels-first zero-padded copies of (dZ, X)
+  the rest   GELU / GroupNorm / Dice backward, pixel un-shuffle, bias column sums, AdamW (csrc/train_elementwise.cu)
+
+torch is used for buffers, for re-packing the bf16 operand copies of the fp32 master weights each step (permutes and
+casts of 8.4 M numbers) and for the NCCL all-reduce (torch.distributed): plumbing, not arithmetic of the model.
+Activation gradients are bf16 (fp32 accumulation inside every kernel), weight gradients and optimizer state fp32.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from . import train_ops as T
+from ._lib import CryovitB200Error
+from .head import BLOCKS, state_dict_keys
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _taps(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
+    """Conv3d weight [Cout, Cin, 3,3,3] -> [27 * cout_pad, Cin] (tap-major), on the tensor's device."""
+    cout, cin = w.shape[:2]
+    out = torch.zeros(27, cout_pad, cin, device=w.device, dtype=w.dtype)
+    out[:, :cout] = w.permute(2, 3, 4, 0, 1).reshape(27, cout, cin)
+    return out.reshape(27 * cout_pad, cin)
+
+
+def _halo_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
+    """cryovit_b200.head.halo_weight_image on the tensor's own device."""
+    cout, cin = w.shape[:2]
+    steps = cin // 16
+    n_mma = 3 * steps if cin >= 16 else 2
+    img = torch.zeros(9, n_mma, 2, cout_pad, 8, device=w.device, dtype=w.dtype)
+    wt = w.permute(2, 3, 4, 0, 1).reshape(9, 3, cout, cin)
+    if cin >= 16:
+        for i in range(n_mma):
+            kw, c2 = divmod(i, steps)
+            for k in range(2):
+                img[:, i, k, :cout] = wt[:, kw, :, c2 * 16 + k * 8: c2 * 16 + k * 8 + 8]
+    else:
+        img[:, 0, 0, :cout] = wt[:, 0]
+        img[:, 0, 1, :cout] = wt[:, 1]
+        img[:, 1, 1, :cout] = wt[:, 2]
+    return img.reshape(-1)
+
+
+class _Conv:
+    """A 3x3x3 depth-dilated convolution in both directions. Narrow inputs (8/16/32 channels) use the halo kernel."""
+
+    def __init__(self, cin: int, cout: int, dil: int):
+        self.cin, self.cout, self.dil = cin, cout, dil
+
+    @staticmethod
+    def _pack(w: torch.Tensor, cin: int, cout: int):
+        """(operand, bias-length, kind) for a convolution cin -> cout with weight w [cout, cin, 3,3,3] (fp32, device)."""
+        if cin in (8, 16, 32):
+            cp = 32 if cout > 16 else 16
+            return _halo_image(w, cp).to(BF16), cp, "halo"
+        cp = max(32, cout)
+        return _taps(w, cp).to(BF16).contiguous(), cp, "taps"
+
+    def run(self, x, w, bias, out, cin, cout, dil):
+        op, cp, kind = self._pack(w, cin, cout)
+        b = torch.zeros(cp, device=x.device, dtype=F32)
+        if bias is not None:
+            b[:cout] = bias
+        if kind == "halo":
+            T.conv3d_halo_act(x, op, b, out, dil, cp, False)
+        else:
+            T.conv3d_dilated_act(x, op, b, out, dil, False)
+
+    def forward(self, x, w, bias, z):
+        self.run(x, w, bias, z, self.cin, self.cout, self.dil)
+
+    def input_gradient(self, dz, w, dx):
+        wg = w.flip(2, 3, 4).transpose(0, 1).contiguous()  # [cin, cout, 3,3,3]: the gradient convolution's weight
+        self.run(dz, wg, None, dx, self.cout, self.cin, self.dil)
+
+
+class CryoVITHeadTrainerB200:
+    """Data-parallel trainer of the CryoVIT head: one process per GPU, one tomogram crop per process and step."""
+
+    def __init__(self, in_channels: int = 1536, lr: float = 1e-4, weight_decay: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, state_dict: dict | None = None, device=None):
+        if not torch.cuda.is_available():
+            raise CryovitB200Error("no CUDA device: the B200 training path has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.in_channels, self.lr, self.weight_decay, self.betas, self.eps = in_channels, lr, weight_decay, betas, eps
+        if state_dict is None:
+            from .host.models import default_state_dict
+
+            state_dict = default_state_dict(in_channels, seed=0)
+        self.keys = state_dict_keys()
+        sizes = [state_dict[k].numel() for k in self.keys]
+        n = sum(sizes)
+        self.flat_p = torch.empty(n, device=self.device, dtype=F32)  # fp32 master weights, ONE bucket
+        self.flat_g = torch.zeros(n, device=self.device, dtype=F32)  # gradients, all-reduced as one flat bucket
+        self.flat_m = torch.zeros(n, device=self.device, dtype=F32)
+        self.flat_v = torch.zeros(n, device=self.device, dtype=F32)
+        self.p, self.g = {}, {}
+        off = 0
+        for k, sz in zip(self.keys, sizes):
+            shape = state_dict[k].shape
+            self.p[k] = self.flat_p[off:off + sz].view(shape)
+            self.g[k] = self.flat_g[off:off + sz].view(shape)
+            self.p[k].copy_(state_dict[k].to(self.device, F32))
+            off += sz
+        self.step_count = 0
+        self.launches = 0
+        self._bufs: dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def state_dict(self) -> dict[str, torch.Tensor]:
+        return {k: v.detach().clone().cpu() for k, v in self.p.items()}
+
+    def _buf(self, name: str, shape, dtype=BF16) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            b = torch.empty(n, device=self.device, dtype=dtype)
+            self._bufs[name] = b
+        return b[:n].view(shape)
+
+    def _wgrad_conv(self, x, dz, dil, key_w, key_b):
+        """Accumulates the weight / bias gradient of a 3x3x3 convolution into the flat bucket."""
+        cin, cout = x.shape[-1], dz.shape[-1]
+        D, H, W, _ = x.shape
+        _, _, _, pitch = T.padded_geometry(D, H, W, dil, 1, 1)
+        for name, need in (("xt_pool", cin * pitch), ("dzt_pool", cout * pitch)):
+            if self._bufs.get(name) is None or self._bufs[name].numel() < need:
+                self._bufs[name] = torch.empty(need, device=self.device, dtype=BF16)
+        dw = T.conv_weight_gradient(x, dz, dil, [self._bufs["xt_pool"]], self._bufs["dzt_pool"])  # [27, cout, cin]
+        self.g[key_w].copy_(dw.view(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
+        if key_b is not None:
+            db = torch.zeros(cout, device=self.device, dtype=F32)
+            T.colsum(dz, db)
+            self.g[key_b].copy_(db)
+        self.launches += 8
+
+    def _wgrad_rows(self, x_rows, dz_rows):
+        """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions)."""
+        R, N = x_rows.shape
+        M = dz_rows.shape[1]
+        pitch = (R + 7) // 8 * 8
+        xt = self._buf("rows_xt", (N, pitch))
+        dzt = self._buf("rows_dzt", (M, pitch))
+        T.to_cfirst_padded(x_rows.view(1, 1, R, N), xt, 0, 0, 0)  # rows along the innermost (W) axis: pitch = roundup8(R)
+        T.to_cfirst_padded(dz_rows.view(1, 1, R, M), dzt, 0, 0, 0)
+        dw = torch.zeros(1, M, N, device=self.device, dtype=F32)
+        T.wgrad_splitk(dzt, xt, dw, torch.zeros(1, dtype=torch.int32, device=self.device), pitch)
+        self.launches += 3
+        return dw[0]
+
+    # ------------------------------------------------------------------ one step
+    def forward_backward(self, features: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0) -> torch.Tensor:
+        """features (C, D, h, w) fp16|fp32, labels (D, 16h, 16w) with -1 = ignore. Fills the gradient bucket and
+        returns the Dice loss (0-dim tensor on the device)."""
+        p, g, dev = self.p, self.g, self.device
+        C, D, h, w = features.shape
+        if C != self.in_channels or tuple(labels.shape) != (D, 16 * h, 16 * w):
+            raise CryovitB200Error(f"features {tuple(features.shape)} / labels {tuple(labels.shape)} do not match")
+        vox = D * h * w
+        # ---------------- forward, keeping what the backward needs
+        x0 = self._buf("x0", (D, h, w, C))
+        ops.features_to_ndhwc(features.to(dev).contiguous(), x0)
+        z_proj, a_proj = self._buf("z_proj", (vox, 1024)), self._buf("a_proj", (D, h, w, 1024))
+        ops.linear_bias(x0.view(vox, C), p["layers.0.weight"].reshape(1024, C).to(BF16), p["layers.0.bias"], z_proj, gelu=False)
+        T.gelu_fwd(z_proj, a_proj.view(vox, 1024))
+        self.launches += 3
+        saved = []
+        cur, H, W = a_proj, h, w
+        for bi, (c1, c2, c3, d1, d2) in enumerate(BLOCKS):
+            pre = f"layers.{bi + 2}.layers."
+            G = max(8, c1 // 8)
+            n_out = self._buf(f"gn{bi}", (D, H, W, c1))
+            stats = self._buf(f"gn{bi}_stats", (2 * G,), F32)
+            ops.groupnorm_ndhwc(cur, n_out, p[pre + "0.weight"], p[pre + "0.bias"], stats, G, 1e-3)
+            ca, cb = _Conv(c1, c2, d1), _Conv(c2, c2, d2)
+            za, aa = self._buf(f"za{bi}", (D, H, W, c2)), self._buf(f"aa{bi}", (D, H, W, c2))
+            ca.forward(n_out, p[pre + "1.weight"], p[pre + "1.bias"], za)
+            T.gelu_fwd(za, aa)
+            zb, ab = self._buf(f"zb{bi}", (D, H, W, c2)), self._buf(f"ab{bi}", (D, H, W, c2))
+            cb.forward(aa, p[pre + "3.weight"], p[pre + "3.bias"], zb)
+            T.gelu_fwd(zb, ab)
+            zt, at = self._buf(f"zt{bi}", (D, 2 * H, 2 * W, c3)), self._buf(f"at{bi}", (D, 2 * H, 2 * W, c3))
+            wT = p[pre + "5.weight"]  # [c2, c3, 1, 2, 2]
+            T.convT_act(ab, wT[:, :, 0].permute(2, 3, 1, 0).reshape(4 * c3, c2).to(BF16).contiguous(),
+                        p[pre + "5.bias"].repeat(4).contiguous(), zt, False)
+            T.gelu_fwd(zt, at)
+            self.launches += 9
+            saved.append((cur, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W))
+            cur, H, W = at, 2 * H, 2 * W
+        co = _Conv(8, 8, 1)
+        z1, a1 = self._buf("z_o0", (D, H, W, 8)), self._buf("a_o0", (D, H, W, 8))
+        co.forward(cur, p["output_layer.0.weight"], p["output_layer.0.bias"], z1)
+        T.gelu_fwd(z1, a1)
+        logits, probs = self._buf("logits", (D, H, W), F32), self._buf("probs", (D, H, W), F32)
+        ops.head_out_conv(a1, p["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8).contiguous(),
+                          p["output_layer.2.bias"], logits, probs)
+        lab = self._buf("labels", (D, H, W), F32)
+        lab.copy_(labels.to(dev))
+        stats8 = ops.seg_stats(probs, lab)
+        loss = 1.0 - 2.0 * stats8[2] / (stats8[1] + stats8[0] + 1e-3)
+        self.launches += 4
+        # ---------------- backward
+        dl8 = self._buf("dlogit8", (D, H, W, 8))
+        T.dice_bwd(logits, probs, lab, stats8, dl8, grad_scale)
+        # output_layer.2 (8 -> 1): operate on the 8-channel padded gradient (channel 0 live)
+        w2 = p["output_layer.2.weight"]                                    # [1, 8, 3,3,3]
+        dw2 = T.conv_weight_gradient(a1, dl8, 1)                           # [27, 8 (co, only 0 live), 8 (ci)]
+        g["output_layer.2.weight"].copy_(dw2[:, 0].view(3, 3, 3, 8).permute(3, 0, 1, 2)[None])
+        db2 = torch.zeros(8, device=dev, dtype=F32)
+        T.colsum(dl8, db2)
+        g["output_layer.2.bias"].copy_(db2[:1])
+        w2_8 = torch.zeros(8, 8, 3, 3, 3, device=dev, dtype=F32)
+        w2_8[0] = w2[0]                                                    # forward weight padded to 8 output channels
+        da1 = self._buf("da_o0", (D, H, W, 8))
+        _Conv(8, 8, 1).input_gradient(dl8, w2_8, da1)
+        dz1 = self._buf("dz_o0", (D, H, W, 8))
+        T.gelu_bwd(da1, z1, dz1)
+        self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight", "output_layer.0.bias")
+        dcur = self._buf("d_top", (D, H, W, 8))
+        co.input_gradient(dz1, p["output_layer.0.weight"], dcur)
+        self.launches += 14
+        for bi in reversed(range(4)):
+            c1, c2, c3, d1, d2 = BLOCKS[bi]
+            pre = f"layers.{bi + 2}.layers."
+            blk_in, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W = saved[bi]
+            # transposed convolution: dcur is d(at) [D, 2H, 2W, c3]
+            dzt = self._buf(f"dzt{bi}", (D, 2 * H, 2 * W, c3))
+            T.gelu_bwd(dcur, zt, dzt)
+            dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
+            T.pixel_unshuffle(dzt, dzun)
+            rows = D * H * W
+            dwt = self._wgrad_rows(ab.view(rows, c2), dzun.view(rows, 4 * c3))          # [(ij, c3), c2]
+            g[pre + "5.weight"].copy_(dwt.view(2, 2, c3, c2).permute(3, 2, 0, 1)[:, :, None])
+            dbt = torch.zeros(4 * c3, device=dev, dtype=F32)
+            T.colsum(dzun, dbt)
+            g[pre + "5.bias"].copy_(dbt.view(4, c3).sum(0))
+            wd = p[pre + "5.weight"][:, :, 0].permute(0, 2, 3, 1).reshape(c2, 4 * c3)      # dX = dZun @ wd^T
+            n_pad = max(32, c2)
+            wd_p = torch.zeros(n_pad, 4 * c3, device=dev, dtype=BF16)
+            wd_p[:c2] = wd.to(BF16)
+            dab = self._buf(f"dab{bi}", (D, H, W, c2))
+            T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, torch.zeros(n_pad, device=dev, dtype=F32), dab.view(rows, c2), c2)
+            # conv b
+            dzb = self._buf(f"dzb{bi}", (D, H, W, c2))
+            T.gelu_bwd(dab, zb, dzb)
+            self._wgrad_conv(aa, dzb, d2, pre + "3.weight", pre + "3.bias")
+            daa = self._buf(f"daa{bi}", (D, H, W, c2))
+            cb.input_gradient(dzb, p[pre + "3.weight"], daa)
+            # conv a
+            dza = self._buf(f"dza{bi}", (D, H, W, c2))
+            T.gelu_bwd(daa, za, dza)
+            self._wgrad_conv(n_out, dza, d1, pre + "1.weight", pre + "1.bias")
+            dn = self._buf(f"dn{bi}", (D, H, W, c1))
+            ca.input_gradient(dza, p[pre + "1.weight"], dn)
+            # GroupNorm
+            dblk = self._buf(f"dblk{bi}", (D, H, W, c1))
+            dgam, dbet = torch.empty(c1, device=dev, dtype=F32), torch.empty(c1, device=dev, dtype=F32)
+            T.groupnorm_bwd(blk_in, dn, dblk, p[pre + "0.weight"], stats, dgam, dbet, G, 1e-3)
+            g[pre + "0.weight"].copy_(dgam)
+            g[pre + "0.bias"].copy_(dbet)
+            dcur = dblk
+            self.launches += 14
+        # projection (1x1x1): only the weight / bias gradient (the features are data)
+        dzp = self._buf("dz_proj", (vox, 1024))
+        T.gelu_bwd(dcur.view(vox, 1024), z_proj, dzp)
+        g["layers.0.weight"].copy_(self._wgrad_rows(x0.view(vox, C), dzp).view(1024, C, 1, 1, 1))
+        dbp = torch.zeros(1024, device=dev, dtype=F32)
+        T.colsum(dzp, dbp)
+        g["layers.0.bias"].copy_(dbp)
+        self.launches += 3
+        return loss
+
+    def optimizer_step(self) -> None:
+        """Data-parallel: sum the flat gradient bucket over the ranks (one NCCL all-reduce; the 1/world factor was
+        applied to the loss gradient), then AdamW on the fp32 master weights."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        self.step_count += 1
+        T.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.step_count)
+        self.launches += 1
+
+    def train_step(self, features: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        loss = self.forward_backward(features, labels, 1.0 / world)
+        self.optimizer_step()
+        return loss

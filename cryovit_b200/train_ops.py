@@ -27,6 +27,13 @@ def convT_act(x, w_sub, bias4, out, act: bool) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, Cout, int(act), _stream())
 
 
+def linear_nvalid(a, w, bias, out, n_valid: int) -> None:
+    """out[M, n_valid] = a[M, K] @ w[N, K]^T + bias (no activation); w may carry zero rows beyond n_valid."""
+    M, K = a.shape
+    _lib.call("cvit_linear_bias_bf16_nvalid", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, w.shape[0], K, n_valid, _stream())
+
+
 def gelu_fwd(z, a) -> None:
     _lib.call("cvit_gelu_fwd_bf16", _chk(z, BF16, "z"), _chk(a, BF16, "a"), z.numel(), _stream())
 

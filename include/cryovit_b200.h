@@ -186,6 +186,11 @@ int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bi
 int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
                                int64_t W, int64_t Cin, int64_t Cout, int act, void* stream);
 
+/* cvit_linear_bias_bf16 (no GELU) for an output narrower than the zero-row-padded weight: columns >= n_valid are not
+ * stored and ldo is the true row pitch (input gradient of the 16-channel transposed convolution). */
+int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                 int64_t M, int64_t N, int64_t K, int64_t n_valid, void* stream);
+
 /* a = gelu(z) and dz = da * gelu'(z) (exact erf form, nn.GELU() default), bf16, n a multiple of 8. */
 int cvit_gelu_fwd_bf16(const void* z, void* a, int64_t n, void* stream);
 int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void* stream);

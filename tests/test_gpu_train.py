@@ -142,3 +142,58 @@ def test_dice_backward_pixel_unshuffle_colsum_adamw(cuda_lib):
         opt.step()
         T.adamw(pm, grad, m1, v1, 1e-4, 0.9, 0.999, 1e-8, 1e-3, step)
     assert (pm - pr.detach()).abs().max().item() < 1e-6
+
+
+def test_training_step_gradients_match_autograd(cuda_lib):
+    """Every parameter gradient of one training step against fp32 autograd of the same head + masked DiceLoss."""
+    import torch.nn.functional as F
+    from cryovit_b200.head import BLOCKS
+    from cryovit_b200.train import CryoVITHeadTrainerB200
+    from oracle import head as ohead
+
+    Cin, D, h, w = 384, 6, 4, 4
+    sd = ohead.random_state_dict(Cin, seed=1)
+    g = torch.Generator().manual_seed(2)
+    feats = (torch.randn(Cin, D, h, w, generator=g) * 0.5).half()
+    labels = torch.randint(-1, 2, (D, 16 * h, 16 * w), generator=g).float()
+    tr = CryoVITHeadTrainerB200(Cin, state_dict=sd)
+    loss = tr.forward_backward(feats.cuda(), labels.cuda())
+    # reference: same graph in fp32 with autograd
+    P = {k: v.clone().float().requires_grad_(True) for k, v in sd.items()}
+    x = F.gelu(F.conv3d(feats.float()[None], P["layers.0.weight"], P["layers.0.bias"]))
+    for bi, (c1, c2, c3, d1, d2) in enumerate(BLOCKS):
+        p = f"layers.{bi + 2}.layers."
+        x = F.group_norm(x, max(8, c1 // 8), P[p + "0.weight"], P[p + "0.bias"], 1e-3)
+        x = F.gelu(F.conv3d(x, P[p + "1.weight"], P[p + "1.bias"], padding="same", dilation=(d1, 1, 1)))
+        x = F.gelu(F.conv3d(x, P[p + "3.weight"], P[p + "3.bias"], padding="same", dilation=(d2, 1, 1)))
+        x = F.gelu(F.conv_transpose3d(x, P[p + "5.weight"], P[p + "5.bias"], stride=(1, 2, 2)))
+    x = F.gelu(F.conv3d(x, P["output_layer.0.weight"], P["output_layer.0.bias"], padding="same"))
+    x = F.conv3d(x, P["output_layer.2.weight"], P["output_layer.2.bias"], padding="same")
+    prob = torch.sigmoid(torch.clip(x, -5, 5))[0, 0]
+    m = labels > -1
+    ref_loss = 1 - 2 * (labels[m] * prob[m]).sum() / (labels[m].sum() + prob[m].sum() + 1e-3)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-3, (float(loss), float(ref_loss))
+    worst = 1.0
+    for k in tr.keys:
+        got, want = tr.g[k].float().cpu().flatten(), P[k].grad.flatten()
+        cos = F.cosine_similarity(got, want, dim=0).item()
+        rel = ((got - want).norm() / want.norm().clamp_min(1e-20)).item()
+        print(f"  {k:32s} cos {cos:.5f} rel {rel:.3e} |g| {want.norm():.3e}")
+        worst = min(worst, cos)
+        assert cos > 0.99 and rel < 0.15, (k, cos, rel)
+    print(f"\n[parity] training step: loss {float(loss):.6f} vs {float(ref_loss):.6f}; worst gradient cosine {worst:.5f}")
+
+
+def test_training_reduces_the_loss(cuda_lib):
+    from cryovit_b200.train import CryoVITHeadTrainerB200
+    from oracle import head as ohead
+
+    Cin, D, h, w = 384, 4, 4, 4
+    g = torch.Generator().manual_seed(3)
+    feats = (torch.randn(Cin, D, h, w, generator=g) * 0.5).half().cuda()
+    labels = (torch.rand(D, 16 * h, 16 * w, generator=g) < 0.3).float().cuda()
+    tr = CryoVITHeadTrainerB200(Cin, lr=1e-3, state_dict=ohead.random_state_dict(Cin, seed=4))
+    losses = [float(tr.train_step(feats, labels)) for _ in range(12)]
+    print("\n[train] losses", [round(l, 4) for l in losses])
+    assert losses[-1] < losses[0] - 0.02 and all(l == l for l in losses)
