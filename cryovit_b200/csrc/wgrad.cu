@@ -11,6 +11,11 @@
 // pitch Wp is a multiple of 8 (depth / row taps are then aligned shifts) and the three column taps use three copies
 // of X made with a built-in column shift of -1, 0, +1. 1x1x1 and transposed convolutions are the one-tap case.
 //
+// Narrow layers (co <= 64) would waste most of the 128 MMA rows, so several taps are PACKED into one A tile: since
+//   sum_p At[co][p] Bt[ci][p + koff] = sum_q At[co][q - koff] Bt[ci][q],
+// tap t's rows are just At loaded with a start coordinate shifted by -koff[t] (one small TMA box per tap, stacked at
+// row t * Mp of the stage), B is loaded once, unshifted, and ONE MMA chain produces 128 / Mp taps at a time.
+//
 // The reduction is split over the grid: a work item is (tap, 128-row tile of co, BN-column tile of ci, K range); every
 // item accumulates in TMEM and adds its partial tile into the fp32 result with red.global.add (the result buffer is
 // zeroed by the caller). One CTA per SM, 192 threads: TMA producer, MMA issuer (warp-uniform, elect.sync), four
@@ -38,6 +43,8 @@ struct WgArgs {
   int M, N, ntaps;      // valid rows of A (co), valid rows of B (ci)
   int k_chunks;         // ceil(K / 64)
   int ksplit;           // K ranges per (tap, tile)
+  int pack;             // taps per A tile (1 = one tap per item, A tile = 128 rows of co; > 1: Mp rows per tap)
+  int Mp;               // rows per packed tap (co rounded up to 8), pack * Mp <= 128
 };
 
 template <int BN>
@@ -54,9 +61,11 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int m_tiles = (args.M + WG_BM - 1) / WG_BM, n_tiles = (args.N + BN - 1) / BN;
+  const int pack = args.pack;
+  const int m_tiles = pack > 1 ? 1 : (args.M + WG_BM - 1) / WG_BM, n_tiles = (args.N + BN - 1) / BN;
   const int per_tap = m_tiles * n_tiles * args.ksplit;
-  const int num_items = args.ntaps * per_tap;
+  const int tap_groups = (args.ntaps + pack - 1) / pack;  // "tap" below is a group of `pack` taps
+  const int num_items = tap_groups * per_tap;
   const int kc_per = (args.k_chunks + args.ksplit - 1) / args.ksplit;
   auto item_of = [&](int item, int& tap, int& m0, int& n0, int& kc0, int& kc1) {
     tap = item / per_tap;
@@ -95,6 +104,19 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int tap, m0, n0, kc0, kc1;
         item_of(item, tap, m0, n0, kc0, kc1);
+        if (pack > 1) {
+          const int t0 = tap * pack, nt = min(pack, args.ntaps - t0);
+          for (int kc = kc0; kc < kc1; ++kc) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, nt * args.Mp * 128 + Cfg::B_BYTES);
+            for (int t = 0; t < nt; ++t)  // tap t's rows: the same co rows, shifted the other way
+              tma_load_2d(sA + s * Cfg::A_BYTES + t * args.Mp * 128, &tmA, bar_full + 8 * s,
+                          kc * WG_KC - __ldg(args.koffs + t0 + t), 0);
+            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * WG_KC, n0);
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+          continue;
+        }
         const int koff = __ldg(args.koffs + tap);
         for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -144,14 +166,20 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + acc * Cfg::ACC + (static_cast<uint32_t>(q * 32) << 16);
-      const int row = m0 + r;
-      float* orow = args.out + ((size_t)tap * args.M + row) * args.N + n0;
+      int row = m0 + r, otap = tap;
+      bool live = row < args.M;
+      if (pack > 1) {  // row r of the tile = tap (tap * pack + r / Mp), output channel r % Mp
+        otap = tap * pack + r / args.Mp;
+        row = r % args.Mp;
+        live = r < pack * args.Mp && otap < args.ntaps && row < args.M;
+      }
+      float* orow = args.out + ((size_t)otap * args.M + row) * args.N + n0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_acc + c0, v);
         tmem_ld_wait();
-        if (row < args.M && kc1 > kc0) {
+        if (live && kc1 > kc0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (n0 + c0 + i < args.N) atomicAdd(orow + c0 + i, __uint_as_float(v[i]));
@@ -186,8 +214,8 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
     }
     configured = true;
   }
-  const int m_tiles = (a.M + WG_BM - 1) / WG_BM, n_tiles = (a.N + BN - 1) / BN;
-  const int items = a.ntaps * m_tiles * n_tiles * a.ksplit;
+  const int m_tiles = a.pack > 1 ? 1 : (a.M + WG_BM - 1) / WG_BM, n_tiles = (a.N + BN - 1) / BN;
+  const int items = ((a.ntaps + a.pack - 1) / a.pack) * m_tiles * n_tiles * a.ksplit;
   int grid = num_sms();
   if (grid > items) grid = items;
   kern<<<grid, WG_THREADS, Cfg::SMEM, st>>>(tmA, tmB, a);
@@ -226,9 +254,75 @@ __global__ void __launch_bounds__(256) ndhwc_to_cfirst_padded_kernel(const __nv_
   }
 }
 
+// Narrow volumes (C <= 32, the layers with tens of millions of voxels): one thread turns 8 consecutive padded positions
+// of one 8-channel chunk into 8 x 16-byte stores (one per channel row, 8 positions each), so a warp writes 512
+// contiguous bytes per row; with NSHIFT = 3 the column-shifted copies -1, 0, +1 come out of the same loads.
+template <int NSHIFT>
+__global__ void __launch_bounds__(256) ndhwc_to_cfirst_padded_narrow_kernel(const __nv_bfloat16* __restrict__ src,
+                                                                             __nv_bfloat16* __restrict__ dst0,
+                                                                             __nv_bfloat16* __restrict__ dst1,
+                                                                             __nv_bfloat16* __restrict__ dst2, int D, int H, int W,
+                                                                             int C, int pd, int ph, int pw, int Wp, int wshift,
+                                                                             int64_t pitch) {
+  const int Hp = H + 2 * ph;
+  const int nchunk = C / 8;
+  const int64_t groups = pitch / 8, total = groups * nchunk;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gp = idx % groups;  // position group fastest: coalesced stores along each channel row
+    const int chunk = (int)(idx / groups);
+    const int64_t p0 = gp * 8;
+    const int wp0 = (int)(p0 % Wp), hp = (int)((p0 / Wp) % Hp);
+    const int d = (int)(p0 / ((int64_t)Wp * Hp)) - pd, h = hp - ph;
+    const bool row_ok = d >= 0 && d < D && h >= 0 && h < H;
+    const __nv_bfloat16* row = src + (((int64_t)(row_ok ? d : 0) * H + (row_ok ? h : 0)) * W) * C + chunk * 8;
+    constexpr int NV = NSHIFT == 3 ? 10 : 8;
+    uint4 v[NV];
+    const int wbase = wp0 - pw + (NSHIFT == 3 ? -1 : wshift);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int w = wbase + i;
+      v[i] = (row_ok && w >= 0 && w < W) ? *reinterpret_cast<const uint4*>(row + (int64_t)w * C) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int sft = 0; sft < NSHIFT; ++sft) {
+      __nv_bfloat16* dst = sft == 0 ? dst0 : sft == 1 ? dst1 : dst2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // channel k of the chunk: gather its value from the 8 voxels
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lo = reinterpret_cast<const uint32_t*>(&v[2 * j + sft])[k >> 1];
+          const uint32_t hi = reinterpret_cast<const uint32_t*>(&v[2 * j + 1 + sft])[k >> 1];
+          o[j] = (k & 1) ? __byte_perm(lo, hi, 0x7632) : __byte_perm(lo, hi, 0x5410);
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)(chunk * 8 + k) * pitch + p0) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 }  // namespace cvit
 
 using namespace cvit;
+
+// Three column-shifted copies (-1, 0, +1) in one pass (narrow volumes; C in {8, 16, 32}).
+extern "C" int cvit_ndhwc_to_cfirst_padded_x3(const void* src, void* dst_m1, void* dst_0, void* dst_p1, int64_t D, int64_t H,
+                                              int64_t W, int64_t C, int64_t pd, int64_t ph, int64_t pw, int64_t Wp, int64_t pitch,
+                                              void* stream) {
+  const int64_t P = (D + 2 * pd) * (H + 2 * ph) * Wp;
+  if (!src || !dst_m1 || !dst_0 || !dst_p1 || D <= 0 || H <= 0 || W <= 0 || (C != 8 && C != 16 && C != 32) || pd < 0 || ph < 0 ||
+      pw < 1 || Wp < W + 2 * pw || (Wp % 8) != 0 || pitch != P) {
+    set_error("ndhwc_to_cfirst_padded_x3: bad arguments");
+    return CVIT_ERR_INVALID;
+  }
+  const int64_t total = pitch / 8 * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+  ndhwc_to_cfirst_padded_narrow_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst_m1), static_cast<__nv_bfloat16*>(dst_0),
+      static_cast<__nv_bfloat16*>(dst_p1), (int)D, (int)H, (int)W, (int)C, (int)pd, (int)ph, (int)pw, (int)Wp, 0, pitch);
+  return check_launch("ndhwc_to_cfirst_padded_narrow_kernel<3>");
+}
 
 extern "C" int cvit_ndhwc_to_cfirst_padded(const void* src, void* dst, int64_t D, int64_t H, int64_t W, int64_t C,
                                            int64_t pd, int64_t ph, int64_t pw, int64_t Wp, int64_t wshift, int64_t pitch,
@@ -238,6 +332,15 @@ extern "C" int cvit_ndhwc_to_cfirst_padded(const void* src, void* dst, int64_t D
       (pitch % 8) != 0) {
     set_error("ndhwc_to_cfirst_padded: bad arguments");
     return CVIT_ERR_INVALID;
+  }
+  if ((C == 8 || C == 16 || C == 32) && (Wp % 8) == 0 && pitch == P) {  // narrow volume: register transpose
+    const int64_t total = pitch / 8 * (C / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+    ndhwc_to_cfirst_padded_narrow_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), nullptr, nullptr, (int)D, (int)H, (int)W, (int)C,
+        (int)pd, (int)ph, (int)pw, (int)Wp, (int)wshift, pitch);
+    return check_launch("ndhwc_to_cfirst_padded_narrow_kernel<1>");
   }
   dim3 grid((unsigned)((pitch + 31) / 32), (unsigned)((C + 31) / 32));
   ndhwc_to_cfirst_padded_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
@@ -259,11 +362,15 @@ extern "C" int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, con
     return CVIT_ERR_INVALID;
   }
   const int bn = N > 128 ? 256 : N > 64 ? 128 : N > 32 ? 64 : 32;
+  // narrow outputs: pack several taps into the 128 MMA rows (see the header comment)
+  const int Mp = (int)((M + 7) / 8 * 8);
+  int pack = (M <= 64 && ntaps > 1) ? WG_BM / Mp : 1;
+  if (pack > ntaps) pack = (int)ntaps;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t strides[2] = {0, (uint64_t)pitch_a * 2};
-    uint32_t box[2] = {WG_KC, WG_BM};
+    uint32_t box[2] = {WG_KC, pack > 1 ? (uint32_t)Mp : (uint32_t)WG_BM};
     int rc = encode_tmap(&tmA, TmapDtype::BF16, 2, At, dims, strides, box, 128);
     if (rc) return rc;
   }
@@ -281,8 +388,10 @@ extern "C" int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, con
   a.N = (int)N;
   a.ntaps = (int)ntaps;
   a.k_chunks = (int)((K + WG_KC - 1) / WG_KC);
-  const int m_tiles = (int)((M + WG_BM - 1) / WG_BM), n_tiles = (int)((N + bn - 1) / bn);
-  const int64_t tiles = ntaps * m_tiles * n_tiles;
+  a.pack = pack;
+  a.Mp = Mp;
+  const int m_tiles = pack > 1 ? 1 : (int)((M + WG_BM - 1) / WG_BM), n_tiles = (int)((N + bn - 1) / bn);
+  const int64_t tiles = ((ntaps + pack - 1) / pack) * m_tiles * n_tiles;
   // enough K ranges for ~4 items per SM, but never K ranges shorter than 32 chunks (2048 reduction steps)
   int ksplit = (int)((4 * (int64_t)num_sms() + tiles - 1) / tiles);
   const int max_split = a.k_chunks / 32 > 0 ? a.k_chunks / 32 : 1;

@@ -138,11 +138,7 @@ class CryoVITHeadTrainerB200:
         """Accumulates the weight / bias gradient of a 3x3x3 convolution into the flat bucket."""
         cin, cout = x.shape[-1], dz.shape[-1]
         D, H, W, _ = x.shape
-        _, _, _, pitch = T.padded_geometry(D, H, W, dil, 1, 1)
-        for name, need in (("xt_pool", cin * pitch), ("dzt_pool", cout * pitch)):
-            if self._bufs.get(name) is None or self._bufs[name].numel() < need:
-                self._bufs[name] = torch.empty(need, device=self.device, dtype=BF16)
-        dw = T.conv_weight_gradient(x, dz, dil, [self._bufs["xt_pool"]], self._bufs["dzt_pool"])  # [27, cout, cin]
+        dw = T.conv_weight_gradient(x, dz, dil, self._bufs.setdefault("wgrad_pool", {}))  # [27, cout, cin]
         self.g[key_w].copy_(dw.view(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
         if key_b is not None:
             db = torch.zeros(cout, device=self.device, dtype=F32)
@@ -220,7 +216,7 @@ class CryoVITHeadTrainerB200:
         T.dice_bwd(logits, probs, lab, stats8, dl8, grad_scale)
         # output_layer.2 (8 -> 1): operate on the 8-channel padded gradient (channel 0 live)
         w2 = p["output_layer.2.weight"]                                    # [1, 8, 3,3,3]
-        dw2 = T.conv_weight_gradient(a1, dl8, 1)                           # [27, 8 (co, only 0 live), 8 (ci)]
+        dw2 = T.conv_weight_gradient(a1, dl8, 1, self._bufs.setdefault("wgrad_pool", {}))  # [27, 8 (co, only 0 live), 8 (ci)]
         g["output_layer.2.weight"].copy_(dw2[:, 0].view(3, 3, 3, 8).permute(3, 0, 1, 2)[None])
         db2 = torch.zeros(8, device=dev, dtype=F32)
         T.colsum(dl8, db2)

@@ -78,22 +78,51 @@ def to_cfirst_padded(x, out, pd: int, ph: int, pw: int, wshift: int = 0) -> None
               out.shape[1], _stream())
 
 
-def conv_weight_gradient(x, dz, dil: int, xt_bufs=None, dzt_buf=None) -> torch.Tensor:
+def to_cfirst_padded_x3(x, outs, pd: int, ph: int, pw: int) -> None:
+    """The three column-shifted copies (-1, 0, +1) of a narrow volume (C in {8, 16, 32}) in one pass."""
+    D, H, W, C = x.shape
+    _, _, Wp, pitch = padded_geometry(D, H, W, pd, ph, pw)
+    _lib.call("cvit_ndhwc_to_cfirst_padded_x3", _chk(x, BF16, "x"), _chk(outs[0], BF16, "out"), _chk(outs[1], BF16, "out"),
+              _chk(outs[2], BF16, "out"), D, H, W, C, pd, ph, pw, Wp, pitch, _stream())
+
+
+_KOFFS: dict = {}
+
+
+def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Tensor:
     """dW[27, Cout, Cin] (tap = (kd*3+kh)*3+kw, fp32) of a 3x3x3 depth-dilated "same" convolution from its input x and
     output gradient dz (both bf16 [D,H,W,C]): three column-shifted channels-first copies of x, one of dz, three
-    9-tap split-K GEMMs."""
+    9-tap split-K GEMMs. ``pool`` (a dict) recycles the operand buffers between calls."""
     D, H, W, Cin = x.shape
     Cout = dz.shape[-1]
     Dp, Hp, Wp, pitch = padded_geometry(D, H, W, dil, 1, 1)
     dev = x.device
-    dzt = dzt_buf[:Cout * pitch].view(Cout, pitch) if dzt_buf is not None else torch.empty(Cout, pitch, device=dev, dtype=BF16)
+    pool = pool if pool is not None else {}
+
+    def buf(name, n):
+        b = pool.get(name)
+        if b is None or b.numel() < n:
+            b = torch.empty(n, device=dev, dtype=BF16)
+            pool[name] = b
+        return b
+
+    dzt = buf("dzt", Cout * pitch)[:Cout * pitch].view(Cout, pitch)
     to_cfirst_padded(dz, dzt, dil, 1, 1, 0)
-    koffs = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
+    key = (dil, Hp, Wp, str(dev))
+    if key not in _KOFFS:
+        _KOFFS[key] = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
+    koffs = _KOFFS[key]
     dw = torch.zeros(3, 9, Cout, Cin, device=dev, dtype=F32)
-    for kw in range(3):
-        xt = xt_bufs[kw % len(xt_bufs)][:Cin * pitch].view(Cin, pitch) if xt_bufs is not None else torch.empty(Cin, pitch, device=dev, dtype=BF16)
-        to_cfirst_padded(x, xt, dil, 1, 1, kw - 1)
-        wgrad_splitk(dzt, xt, dw[kw], koffs, pitch)
+    if Cin in (8, 16, 32):  # all three shifted copies from one pass over x
+        xts = [buf(f"xt{kw}", Cin * pitch)[:Cin * pitch].view(Cin, pitch) for kw in range(3)]
+        to_cfirst_padded_x3(x, xts, dil, 1, 1)
+        for kw in range(3):
+            wgrad_splitk(dzt, xts[kw], dw[kw], koffs, pitch)
+    else:
+        xt = buf("xt0", Cin * pitch)[:Cin * pitch].view(Cin, pitch)
+        for kw in range(3):
+            to_cfirst_padded(x, xt, dil, 1, 1, kw - 1)
+            wgrad_splitk(dzt, xt, dw[kw], koffs, pitch)
     return dw.permute(1, 0, 2, 3).reshape(27, Cout, Cin)
 
 

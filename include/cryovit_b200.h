@@ -223,6 +223,11 @@ int cvit_pixel_unshuffle_1x2x2_bf16(const void* src, void* dst, int64_t D, int64
 int cvit_ndhwc_to_cfirst_padded(const void* src, void* dst, int64_t D, int64_t H, int64_t W, int64_t C, int64_t pd,
                                 int64_t ph, int64_t pw, int64_t Wp, int64_t wshift, int64_t pitch, void* stream);
 
+/* The three column-shifted copies (wshift -1, 0, +1) of a narrow volume (C in {8, 16, 32}) in one pass. */
+int cvit_ndhwc_to_cfirst_padded_x3(const void* src, void* dst_m1, void* dst_0, void* dst_p1, int64_t D, int64_t H,
+                                   int64_t W, int64_t C, int64_t pd, int64_t ph, int64_t pw, int64_t Wp, int64_t pitch,
+                                   void* stream);
+
 /* out[t][m][n] += sum_k At[m][k] * Bt[n][k + koffs[t]]  for t < ntaps (fp32 out, caller zeroes; terms whose shifted
  * index falls outside [0, K) are zero). At bf16 [M][pitch_a], Bt bf16 [N][pitch_b]; koffs int32 [ntaps] on the
  * device, every shift a multiple of 8 (TMA start alignment). Split over the whole GPU along K; every partial tile is added with red.global.add.f32. */

@@ -1,0 +1,66 @@
+"""Timing of one CryoVIT head training step at BASELINE config 5's crop: features (1536, 128, 32, 32), labels (128, 512, 512)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from cryovit_b200 import build, ops, train_ops  # noqa: E402
+from cryovit_b200.train import CryoVITHeadTrainerB200  # noqa: E402
+
+build.build()
+C, D, h, w = 1536, int(sys.argv[1]) if len(sys.argv) > 1 else 128, 32, 32
+g = torch.Generator().manual_seed(0)
+feats = (torch.randn(C, D, h, w, generator=g) * 0.5).half().cuda()
+labels = (torch.rand(D, 16 * h, 16 * w, generator=g) < 0.1).float()
+labels[::5] = -1
+labels = labels.cuda()
+tr = CryoVITHeadTrainerB200(C)
+seq, active = [], False
+for mod, names in ((ops, ["features_to_ndhwc", "linear_bias", "groupnorm_ndhwc", "head_out_conv", "seg_stats"]),
+                   (train_ops, ["conv3d_dilated_act", "conv3d_halo_act", "convT_act", "gelu_fwd", "gelu_bwd", "dice_bwd", "colsum",
+                                "groupnorm_bwd", "pixel_unshuffle", "to_cfirst_padded", "to_cfirst_padded_x3", "wgrad_splitk", "linear_nvalid", "adamw"])):
+    for n in names:
+        orig = getattr(mod, n)
+
+        def wrapped(*a, _o=orig, _n=n, **k):
+            if not active:
+                return _o(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = _o(*a, **k)
+            e.record()
+            tag = _n
+            if _n == "wgrad_splitk":
+                tag = f"wgrad_splitk M={a[2].shape[1]} N={a[2].shape[2]} taps={a[2].shape[0]} K={a[4]}"
+            seq.append((tag, s, e))
+            return r
+        setattr(mod, n, wrapped)
+for _ in range(2):
+    loss = tr.train_step(feats, labels)
+torch.cuda.synchronize()
+print("loss", float(loss), "peak memory GB", torch.cuda.max_memory_allocated() / 1e9)
+active = True
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+tr.train_step(feats, labels)
+e.record()
+torch.cuda.synchronize()
+active = False
+agg = {}
+for n, a, b in seq:
+    t = agg.setdefault(n, [0, 0.0])
+    t[0] += 1
+    t[1] += a.elapsed_time(b)
+for n, (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{n:22s} x{cnt:3d} {ms:9.3f} ms")
+print(f"instrumented step {s.elapsed_time(e):.2f} ms (kernels {sum(v[1] for v in agg.values()):.2f} ms)")
+ts = []
+for _ in range(3):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    tr.train_step(feats, labels)
+    e.record()
+    torch.cuda.synchronize()
+    ts.append(s.elapsed_time(e))
+print(f"train step {sorted(ts)[1]:.2f} ms -> {D * 512 * 512 / sorted(ts)[1] / 1e6:.3f} Gvoxel/s")
