@@ -148,6 +148,42 @@ def head_voxels_per_s(torch, steps: int = 3) -> dict:
             "workload": f"CryoVIT head, fp16 (1536,{D},32,32) feature volume -> ({D},{H},{W}) probabilities, weights random"}
 
 
+def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
+    """BASELINE config 5: data-parallel CryoVIT head training, one (1536,128,32,32) feature crop + (128,512,512) labels
+    per GPU and step: forward, masked DiceLoss, backward, one flat-bucket NCCL all-reduce (world > 1), AdamW."""
+    from cryovit_b200.train import CryoVITHeadTrainerB200
+
+    rank = int(os.environ.get("RANK", "0"))
+    g = torch.Generator().manual_seed(500 + rank)
+    feats = (torch.randn(1536, D, 32, 32, generator=g) * 0.5).half().cuda()
+    labels = (torch.rand(D, H, W, generator=g) < 0.1).float()
+    labels[::5] = -1  # 20 % of the slices unlabelled
+    labels = labels.cuda()
+    tr = CryoVITHeadTrainerB200(1536)
+    for _ in range(2):
+        loss = tr.train_step(feats, labels)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = tr.launches
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        loss = tr.train_step(feats, labels)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    vox = world * D * H * W
+    return {"value": round(vox / ms * 1e3, 0), "unit": "labelled-volume voxels/s (all GPUs)", "ms_per_step": round(ms, 2),
+            "loss": round(float(loss), 5), "launches_per_step": (tr.launches - l0) // steps,
+            "gradient_bucket_bytes": tr.flat_g.numel() * 4, "allreduce": "nccl, one flat fp32 bucket" if world > 1 else "none (1 GPU)",
+            "workload": f"CryoVIT head training step, fp16 (1536,{D},32,32) crop + ({D},{H},{W}) labels per GPU, AdamW lr 1e-4 wd 1e-3, DiceLoss"}
+
+
 def cpu_oracle_slices_per_s(n_slices: int, sd=None, threads: int | None = None) -> tuple[float, int, float]:
     """fp32 oracle (pre-processing + ViT-g forward + layout/cast) on the host cores over n_slices slices."""
     import numpy as np
@@ -369,6 +405,11 @@ def run_b200(args) -> None:
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2), drain=drain_e2e)
 
+    # head inference and data-parallel head training: every rank takes part (training all-reduces its gradients)
+    del stream
+    torch.cuda.empty_cache()
+    head_line = head_voxels_per_s(torch)
+    train_line = head_train_voxels_per_s(torch, dist, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -411,9 +452,10 @@ def run_b200(args) -> None:
                 "d2h_bytes_per_step": C * D * 32 * 32 * 2},
         "gpu_launches": launches,
     }
+    line["head"] = head_line
+    line["head_train"] = train_line
     del model
     torch.cuda.empty_cache()
-    line["head"] = head_voxels_per_s(torch)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, dt = cpu_oracle_slices_per_s(2, sd)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",

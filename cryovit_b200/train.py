@@ -55,6 +55,16 @@ def _halo_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
     return img.reshape(-1)
 
 
+def allreduce_gradient_bucket(flat_g: torch.Tensor) -> None:
+    """Data-parallel gradient exchange: ONE all-reduce (sum) of the flat fp32 bucket holding every parameter gradient
+    (8.4 M numbers, 33.6 MB: latency-bound on NVLink 5, so a single bucket rather than per-layer pieces). The 1/world
+    factor is applied upstream, to the loss gradient. No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_g, op=dist.ReduceOp.SUM)
+
+
 class _Conv:
     """A 3x3x3 depth-dilated convolution in both directions. Narrow inputs (8/16/32 channels) use the halo kernel."""
 
@@ -285,10 +295,7 @@ class CryoVITHeadTrainerB200:
     def optimizer_step(self) -> None:
         """Data-parallel: sum the flat gradient bucket over the ranks (one NCCL all-reduce; the 1/world factor was
         applied to the loss gradient), then AdamW on the fp32 master weights."""
-        import torch.distributed as dist
-
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        allreduce_gradient_bucket(self.flat_g)
         self.step_count += 1
         T.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
                 self.weight_decay, self.step_count)

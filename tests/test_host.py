@@ -166,6 +166,11 @@ if rank == 1:
     m._add(torch.tensor(0.5, dtype=torch.float64))
 m.all_reduce()
 assert abs(float(m.compute()) - 0.5) < 1e-12 and m.total == 3.0, (float(m.compute()), m.total)
+# (3) head training: one flat gradient bucket, summed over ranks (the 1/world factor rides on the loss gradient)
+from cryovit_b200.train import allreduce_gradient_bucket
+bucket = torch.full((1000,), float(rank + 1)) / dist.get_world_size()
+allreduce_gradient_bucket(bucket)
+assert torch.allclose(bucket, torch.full((1000,), 1.5)), bucket[:4]
 dist.barrier()
 dist.destroy_process_group()
 '''
