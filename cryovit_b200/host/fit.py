@@ -1,0 +1,54 @@
+"""Head training loop with the reference's schedule (run/train_model.py:206-312, configs/trainer/fit.yaml,
+configs/callbacks/stochastic_weight_average.yaml): seed, AdamW(lr, weight_decay) on every step, batch of ONE tomogram
+crop per process (dataloader/default.yaml batch_size 1), ``max_epochs`` passes, stochastic weight averaging of the
+weights from ``swa_epoch_start`` on (constant learning rate ``swa_lrs = lr``, so SWA is a running mean of the iterates),
+final ``weights.pt`` = plain state dict with the reference's parameter names (:312). Lightning itself is not used:
+the step is ``CryoVITHeadTrainerB200.train_step`` (native forward / backward / all-reduce / AdamW)."""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from ..train import CryoVITHeadTrainerB200
+from .datasets import TomoDataset
+from .shard import rank_world
+
+
+def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50, lr: float = 1e-4, weight_decay: float = 1e-3,
+             swa_epoch_start: int | None = 40, seed: int = 42, exp_dir: Path | str | None = None, state_dict: dict | None = None,
+             log_every: int = 10) -> dict[str, torch.Tensor]:
+    """Trains on the items of ``dataset`` (``train=True`` gives the reference's random 128 x 32 x 32 feature crops);
+    with several ranks (torchrun) every rank walks its own round-robin share of a common shuffled order and the
+    gradients are averaged over the ranks each step. Returns the final (SWA-averaged if enabled) state dict."""
+    rank, world = rank_world()
+    torch.manual_seed(seed)
+    np.random.seed(seed + rank)  # crops differ per rank, the shuffled ORDER (below) does not
+    trainer = CryoVITHeadTrainerB200(in_channels, lr=lr, weight_decay=weight_decay, state_dict=state_dict)
+    order_rng = np.random.default_rng(seed)
+    swa_avg, swa_n = None, 0
+    step = 0
+    for epoch in range(max_epochs):
+        order = order_rng.permutation(len(dataset))
+        usable = len(order) // world * world  # every rank takes the same number of steps (the all-reduce is collective)
+        losses = []
+        for i in order[:usable][rank::world]:
+            item = dataset[int(i)]
+            loss = trainer.train_step(item.data.cuda(non_blocking=True), item.label.cuda(non_blocking=True))
+            step += 1
+            if step % log_every == 0 or len(losses) == 0:
+                losses.append(float(loss))
+        if swa_epoch_start is not None and epoch >= swa_epoch_start:
+            swa_n += 1
+            swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
+        if rank == 0:
+            logging.info("epoch %d: %d steps/rank, DiceLoss %.4f", epoch, usable // world, float(np.mean(losses)) if losses else float("nan"))
+    if swa_avg is not None:
+        trainer.flat_p.copy_(swa_avg)
+    sd = trainer.state_dict()
+    if exp_dir is not None and rank == 0:
+        Path(exp_dir).mkdir(parents=True, exist_ok=True)
+        torch.save(sd, Path(exp_dir) / "weights.pt")
+    return sd

@@ -180,3 +180,41 @@ def test_run_inference_writes_prediction_layout(cuda_lib, tmp_path):
         assert sorted(out) == ["data", "mito_preds"]
         assert out["data"].dtype == np.float32 and np.allclose(out["data"], tomo.astype(np.float32) / 255.0)
         assert out["mito_preds"].dtype == np.uint8 and np.array_equal(out["mito_preds"], want)
+
+
+def test_fit_head_on_feature_files(cuda_lib, tmp_path):
+    """cfg-5 loop: feature files with the reference layout -> TomoDataset(train=True) crops -> native training steps ->
+    weights.pt with the reference's parameter names; the trained head loads into the inference head and fits the
+    (learnable) toy labels better than the initial weights."""
+    from cryovit.datasets import TomoDataset
+    from cryovit_b200.head import CryoVITHeadB200, state_dict_keys
+    from cryovit_b200.host import hdf
+    from cryovit_b200.host.fit import fit_head
+    from cryovit_b200.host.metrics import DiceMetric
+    from oracle import head as ohead
+
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(2):
+        feats = rng.standard_normal((384, 5, 4, 4)).astype(np.float16)
+        lab = (np.repeat(np.repeat(feats[0].astype(np.float32), 16, axis=1), 16, axis=2) > 0).astype(np.int8)  # learnable from channel 0
+        hdf.write_tomogram(tmp_path / "S" / f"t{i}.hdf", {"data": np.zeros((5, 64, 64), np.uint8), "labels/mito": lab, "dino_features": feats})
+        recs.append({"sample": "S", "tomo_name": f"t{i}.hdf"})
+    ds = TomoDataset(recs, "dino_features", "mito", "split_id", tmp_path, train=True)
+    sd0 = ohead.random_state_dict(384, seed=5)
+    sd = fit_head(ds, in_channels=384, max_epochs=12, lr=2e-3, swa_epoch_start=9, exp_dir=tmp_path / "exp", state_dict=sd0, log_every=1)
+    saved = torch.load(tmp_path / "exp" / "weights.pt")
+    assert sorted(saved) == sorted(state_dict_keys()) and all(torch.equal(saved[k], sd[k]) for k in saved)
+
+    def dice(state):
+        head = CryoVITHeadB200(384).load_state_dict(state).cuda()
+        m = DiceMetric(0.5)
+        for r in recs:
+            f = hdf.read_tomogram(tmp_path / "S" / r["tomo_name"])
+            _, probs = head.segment_volume(torch.from_numpy(f["dino_features"]).cuda(), want_logits=False)
+            m.update(probs, torch.from_numpy(f["labels/mito"]).float().cuda())
+        return float(m.compute())
+
+    before, after = dice(sd0), dice(sd)
+    print(f"\n[train] Dice before {before:.3f} after {after:.3f}")
+    assert after > before + 0.05
