@@ -56,6 +56,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_ndhwc_to_cfirst_padded_x3": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_wgrad_splitk": [P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "cvit_adamw_f32": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, F32, P],
+    "cvit_set_gemm_pair": [I32],  # returns the previous setting, not an error code (use load().cvit_set_gemm_pair)
 }
 
 _lib: ctypes.CDLL | None = None

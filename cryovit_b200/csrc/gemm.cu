@@ -7,11 +7,15 @@
 
 namespace cvit {
 
-template <int BN, int EPI, int AMODE, int KSPAN>
+// 1 = large plain-rows GEMMs with 256-wide N tiles run as CTA pairs (tcgen05 cta_group::2); 0 = single-CTA kernel
+// everywhere. Process-wide switch for A/B measurements (tools/kernel_probe.py); the default is pairs.
+static int g_gemm_pair = 1;
+
+template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int num_tiles,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, KSPAN>;
-  auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, KSPAN>;
+  using Cfg = GemmCfg<BN, KSPAN, PAIR>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, KSPAN, PAIR>;
   static bool configured = false;  // per instantiation; attribute is per function, setting twice is harmless
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -20,6 +24,31 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
       return CVIT_ERR_CUDA;
     }
     configured = true;
+  }
+  if (PAIR) {
+    // num_tiles counts 256-row pair tiles; one cluster of two CTAs per TPC
+    int pairs = num_sms() / 2;
+    if (pairs > num_tiles) pairs = num_tiles;
+    if (pairs < 1) return CVIT_OK;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args);
+    if (e != cudaSuccess) {
+      set_error("gemm_tcgen05_kernel<pair>: %s", cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    return check_launch("gemm_tcgen05_kernel<pair>");
   }
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
@@ -41,6 +70,9 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 #define CVIT_GEMM_CASE(BN_, EPI_, AMODE_, KSPAN_)                                     \
   if (bn == BN_ && epi == EPI_ && kspan == KSPAN_)                                    \
     return launch_gemm<BN_, EPI_, AMODE_, KSPAN_>(tmA, tmB, args, num_tiles, stream);
+#define CVIT_GEMM_PAIR_CASE(EPI_)                                                     \
+  if (pair && epi == EPI_)                                                            \
+    return launch_gemm<256, EPI_, AMODE_ROWS, 128, true>(tmA, tmB, args, num_tiles, stream);
 
 // Plain [M,K] x [N,K]^T GEMM with a fused epilogue.
 static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, int epi, cudaStream_t stream) {
@@ -69,9 +101,17 @@ static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, i
   CUtensorMap tmA, tmB;
   int rc = make_tmap_rows(&tmA, A, M, K, lda, GEMM_BM, kspan);
   if (rc) return rc;
-  rc = make_tmap_rows(&tmB, B, N, K, K, bn, kspan);
+  // CTA pairs (256 x 256 output tile per TPC) whenever there is more than one 128-row tile to share a B tile over
+  const bool pair = g_gemm_pair && bn == 256 && kspan == 128 && M > GEMM_BM &&
+                    (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_SWIGLU || epi == EPI_SCALE_RESIDUAL);
+  rc = make_tmap_rows(&tmB, B, N, K, K, pair ? bn / 2 : bn, kspan);
   if (rc) return rc;
-  const int num_tiles = (int)(((M + GEMM_BM - 1) / GEMM_BM) * (N / bn));
+  const int bm = pair ? 2 * GEMM_BM : GEMM_BM;
+  const int num_tiles = (int)(((M + bm - 1) / bm) * (N / bn));
+  CVIT_GEMM_PAIR_CASE(EPI_BIAS)
+  CVIT_GEMM_PAIR_CASE(EPI_BIAS_GELU)
+  CVIT_GEMM_PAIR_CASE(EPI_BIAS_SWIGLU)
+  CVIT_GEMM_PAIR_CASE(EPI_SCALE_RESIDUAL)
   CVIT_GEMM_CASE(256, EPI_BIAS, AMODE_ROWS, 128)
   CVIT_GEMM_CASE(128, EPI_BIAS, AMODE_ROWS, 128)
   CVIT_GEMM_CASE(64, EPI_BIAS, AMODE_ROWS, 128)   // transposed-convolution input gradients (training)
@@ -161,6 +201,12 @@ static GemmArgs base_args(int64_t M, int64_t N, int64_t K, void* out, int64_t ld
 }
 
 extern "C" {
+
+int cvit_set_gemm_pair(int enable) {
+  const int prev = cvit::g_gemm_pair;
+  cvit::g_gemm_pair = enable ? 1 : 0;
+  return prev;
+}
 
 int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
                           int64_t M, int64_t N, int64_t K, int gelu, void* stream) {

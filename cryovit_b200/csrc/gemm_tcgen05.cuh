@@ -52,10 +52,10 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 
-template <int BN, int KSPAN>
+template <int BN, int KSPAN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * KSPAN;
-  static constexpr int B_BYTES = BN * KSPAN;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KSPAN;  // a CTA pair splits the B tile half/half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -107,11 +107,19 @@ __device__ __forceinline__ int tile_row_to_global(const TileCoord& t, int r, con
   return g < a.M ? g : -1;
 }
 
-template <int BN, int EPI, int AMODE, int KSPAN>
+// PAIR = true (AMODE_ROWS only): the kernel is launched as clusters of two CTAs (the two SMs of a TPC). A pair owns a
+// 256 x BN output tile: CTA rank r loads A rows [m0 + 128 r, +128) and B rows [n0 + BN/2 r, +BN/2), the leader (rank 0)
+// issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory and writes each CTA's 128 accumulator
+// rows into its own TMEM, and each CTA runs its own epilogue. Per SM and per FLOP this halves the B-operand shared
+// memory traffic (TMA writes and MMA reads) against the single-CTA kernel. Barriers: the "full" barriers that count
+// TMA bytes live in the leader (both producers signal them), "empty"/"accumulator full" are multicast commits to both
+// CTAs, "accumulator empty" collects the epilogue warps of both CTAs in the leader.
+template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
-  using Cfg = GemmCfg<BN, KSPAN>;
+  static_assert(!PAIR || AMODE == AMODE_ROWS, "CTA pairs are implemented for the plain-rows GEMM only");
+  using Cfg = GemmCfg<BN, KSPAN, PAIR>;
   constexpr int KC = KSPAN / 2;        // bf16 elements of K per stage
   constexpr int MMAS_PER_STAGE = KC / 16;
   constexpr int STAGES = Cfg::STAGES;
@@ -135,9 +143,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_n = args.N / BN;
   const int num_m = AMODE == AMODE_CONV3
                         ? args.D * ((args.H + args.BH - 1) / args.BH) * ((args.W + args.BW - 1) / args.BW)
-                        : (args.M + GEMM_BM - 1) / GEMM_BM;
+                        : (args.M + (PAIR ? 2 : 1) * GEMM_BM - 1) / ((PAIR ? 2 : 1) * GEMM_BM);
   const int num_tiles = num_m * num_n;
   const int k_chunks = (args.K + KC - 1) / KC;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto coord = [&](int tile) {
+    TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+    if (PAIR) t.m0 = 2 * t.m0 + (int)rank * GEMM_BM;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -148,13 +164,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, GEMM_EPI_WARPS);
+      mbar_init(bar_tempty + 8 * i, (PAIR ? 2 : 1) * GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -163,8 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const TileCoord t = coord(tile);
         const int taps = AMODE == AMODE_CONV3 ? 27 : 1;
         for (int tap = 0; tap < taps; ++tap) {
           int dz = 0, dy = 0, dx = 0;
@@ -177,6 +197,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           for (int kc = 0; kc < k_chunks; ++kc) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            if (PAIR) {
+              // both producers report their bytes to the LEADER's full barrier, which expects the pair's total
+              if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * Cfg::STAGE_BYTES);
+              const uint32_t lead_full = mapa_cluster(bar_full + 8 * s, 0);
+              tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, lead_full, kc * KC, t.m0);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, lead_full, kc * KC, t.n0 + (int)rank * (BN / 2));
+              if (++s == STAGES) { s = 0; ph ^= 1u; }
+              continue;
+            }
             mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::STAGE_BYTES);
             if (AMODE == AMODE_CONV3) {
               tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, dx, dy, dz);
@@ -190,19 +219,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
     // The whole warp walks the tile / k-chunk schedule so control flow stays warp-uniform and the descriptors live
     // in uniform registers; one elected lane issues the MMAs and commits. (Issuing from a divergent `lane == 0`
     // region cost ~90 cycles per tcgen05.mma: every operand went through R2UR and a per-lane ELECT loop.)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * GEMM_BM : GEMM_BM, BN);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const TileCoord t = coord(tile);
         mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
@@ -223,22 +252,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int k = 0; k < MMAS_PER_STAGE; ++k) {
                 // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
               }
-              umma_commit(bar_empty + 8 * s);  // smem slot reusable once these MMAs retire
+              // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+              if (PAIR) umma_commit_pair(bar_empty + 8 * s);
+              else umma_commit(bar_empty + 8 * s);
             }
             __syncwarp();
             accumulate = 1;
             if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
         }
-        if (elect_one_sync()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        if (elect_one_sync()) {  // accumulator complete
+          if (PAIR) umma_commit_pair(bar_tfull + 8 * acc);
+          else umma_commit(bar_tfull + 8 * acc);
+        }
         __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1u;
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;   // 0..7
     const int q = warp & 3;    // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
@@ -268,8 +303,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[it].x), "=f"(x[it].y), "=f"(x[it].z), "=f"(x[it].w) : "r"(addr));
       }
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      const TileCoord t = coord(tile);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
@@ -368,18 +403,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // all TMEM reads of this accumulator buffer are complete (every tcgen05.ld was waited on)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_tempty + 8 * acc, 0));  // the leader's issuer waits for both CTAs
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -210,6 +210,69 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------- CTA pair (cta_group::2)
+// Two CTAs of a cluster on the two SMs of one TPC share every MMA: each supplies its 128 rows of A and HALF of the
+// B tile from its own shared memory, each receives its 128 accumulator rows in its own TMEM. Only the leader (cluster
+// rank 0) issues; shared-memory and TMEM offsets must be identical in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are signalled on a barrier that may live in the
+// peer CTA of the pair (`cluster_bar` is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Executed by the SAME warp index in both CTAs of the pair; both receive the same TMEM address.
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem, both CTAs] (+)= A * B over the pair: M = 256 (128 rows per CTA), B's N split half/half; leader thread only.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives (count 1) on the barrier at this shared-memory offset in BOTH CTAs once the leader's MMAs retired.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are exactly one swizzle span
 // (SWIZZLE_BYTES = 128/64/32 bytes of K per row, rows packed back to back, tile base 1024-aligned).
 // Field layout follows cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 @[0,14),

@@ -38,6 +38,10 @@ extern "C" {
 /* Library identity / diagnostics. */
 int cvit_abi_version(void);
 const char* cvit_last_error(void);
+/* Process-wide switch of the GEMM family: 1 (default) = plain-rows GEMMs with 256-wide N tiles run as CTA pairs
+ * (tcgen05 cta_group::2, 256 x 256 output tile per TPC), 0 = single-CTA kernel everywhere. Returns the previous
+ * value. Exists for A/B measurement only; results are bit-identical in both modes. */
+int cvit_set_gemm_pair(int enable);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Slice pre-processing + patchify.

@@ -68,6 +68,43 @@ def test_linear_scale_residual(cuda_lib, M, N, K):
     _close(x, ref, atol=1e-3, rtol=1e-4, what="linear_scale_residual")
 
 
+@pytest.mark.parametrize("M", [129, 300, 1029, 4116, 20000])
+def test_gemm_cta_pair_matches_single_cta(cuda_lib, M):
+    """The cta_group::2 kernel (256 x 256 tile per CTA pair; the default for the ViT linears) and the single-CTA kernel
+    accumulate every output element over K in the same order, so the two modes must agree BIT FOR BIT, for every
+    fused epilogue, including row counts whose last pair tile is ragged (129: the second CTA's rows are all out of
+    range except one; 1029 = 4*256 + 5: the second CTA of the last pair has no rows at all)."""
+    from cryovit_b200 import ops
+    from cryovit_b200.vit import interleave_w12
+    K, N = 384, 768
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+    b, g, x0 = _rand(N, seed=3), _rand(N, seed=4), _rand(M, N, seed=5)
+    wi, bi = interleave_w12(w, b)
+
+    def run():
+        o1 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        o2 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        o3 = torch.full((M, N // 2), float("nan"), device=DEV, dtype=torch.bfloat16)
+        x = x0.clone()
+        ops.linear_bias(a, w, b, o1)
+        ops.linear_bias(a, w, b, o2, gelu=True)
+        ops.linear_swiglu(a, wi, bi, o3)
+        ops.linear_scale_residual(a, w, b, g, x)
+        torch.cuda.synchronize()
+        return o1, o2, o3, x
+
+    assert cuda_lib.cvit_set_gemm_pair(0) == 1  # pairs are the default
+    try:
+        single = run()
+    finally:
+        cuda_lib.cvit_set_gemm_pair(1)
+    pair = run()
+    for s_, p_, what in zip(single, pair, ("bias", "bias_gelu", "swiglu", "scale_residual")):
+        assert torch.equal(s_, p_), f"{what}: pair and single-CTA kernels differ at M={M}"
+    _close(pair[0], a.float() @ w.float().t() + b, atol=2e-2, rtol=1e-2, what="pair linear_bias vs fp32")
+
+
 def test_patch_embed_gemm(cuda_lib):
     from cryovit_b200 import ops
     B, Np, T, C, K = 3, 64, 69, 384, 256

@@ -54,13 +54,22 @@ def rec(name, ms, flops=None, bytes_=None):
     res[name] = r
     print(name, r, flush=True)
 
-rec("qkv_gemm", timeit(lambda: ops.linear_bias(ln, qkv_w, qkv_b, qkv)), 2 * M * C * 3 * C)
+from cryovit_b200 import _lib  # noqa: E402
+lib = _lib.load()
+gemms = {
+    "qkv_gemm": (lambda: ops.linear_bias(ln, qkv_w, qkv_b, qkv), 2 * M * C * 3 * C),
+    "proj_gemm_resid": (lambda: ops.linear_scale_residual(attn, proj_w, proj_b, g, x), 2 * M * C * C),
+    "w12_swiglu": (lambda: ops.linear_swiglu(ln, w12i, b12i, hidden), 2 * M * C * 2 * Fh),
+    "w3_gemm_resid": (lambda: ops.linear_scale_residual(hidden, w3, b3, g, x), 2 * M * Fh * C),
+}
+for pair in (1, 0):
+    lib.cvit_set_gemm_pair(pair)
+    for name, (fn, fl) in gemms.items():
+        rec(name + ("_pair" if pair else "_single"), timeit(fn), fl)
+lib.cvit_set_gemm_pair(1)
 rec("cublas_qkv", timeit(lambda: torch.addmm(qkv_b.bfloat16(), ln, qkv_w.t())), 2 * M * C * 3 * C)
 rec("attention_tcgen05", timeit(lambda: ops.attention(qkv, attn, B, T, H)), 4 * B * H * T * T * 64)
 rec("attention_mma_sync", timeit(lambda: ops.attention(qkv, attn, B, T, H, legacy_mma_sync=True)), 4 * B * H * T * T * 64)
-rec("proj_gemm_resid", timeit(lambda: ops.linear_scale_residual(attn, proj_w, proj_b, g, x)), 2 * M * C * C)
-rec("w12_swiglu", timeit(lambda: ops.linear_swiglu(ln, w12i, b12i, hidden)), 2 * M * C * 2 * Fh)
-rec("w3_gemm_resid", timeit(lambda: ops.linear_scale_residual(hidden, w3, b3, g, x)), 2 * M * Fh * C)
 rec("layernorm", timeit(lambda: ops.layernorm(x, n1w, n1b, ln, 1e-6)), None, M * C * 6)
 q, k, v = qkv.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
 rec("torch_sdpa", timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v)), 4 * B * H * T * T * 64)
