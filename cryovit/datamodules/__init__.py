@@ -1,1 +1,3 @@
-from cryovit_b200.host.datasets import collate_fn  # noqa: F401
+from cryovit_b200.host.datamodules import (  # noqa: F401
+    BaseDataModule, MultiSampleDataModule, SingleSampleDataModule, TomoLoader,
+)

@@ -1,1 +1,1 @@
-from . import dino_features, infer_model  # noqa: F401
+from . import dino_features, eval_model, infer_model, train_model  # noqa: F401

@@ -119,6 +119,11 @@ def _compose_file(config_dir: Path, rel: str, choices: dict[str, str]) -> dict:
                 full_group = (group_dir + "/" if group_dir else "") + group
                 for ch in (choice if isinstance(choice, list) else [choice]):
                     ch = choices.get(full_group, ch)
+                    if ch == MISSING:  # mandatory group (``model: ???``) not chosen: reported by the validator
+                        out[group] = MISSING
+                        continue
+                    if not isinstance(choice, list):
+                        choices.setdefault("=" + full_group, ch)  # recorded for ${hydra:runtime.choices.<group>}
                     sub = _compose_file(config_dir, f"{full_group}/{ch}", choices)
                     node = out.setdefault(group, {})
                     if isinstance(choice, list):  # list-valued defaults (losses, metrics): one sub-key per choice
@@ -135,7 +140,11 @@ _INTERP = re.compile(r"\$\{([^}]+)\}")
 
 def _lookup(root: dict, dotted: str):
     cur: Any = root
+    if dotted.startswith("hydra:"):  # the one resolver the reference's YAML uses: ${hydra:runtime.choices.<group>}
+        dotted = "hydra." + dotted[len("hydra:"):]
     for part in dotted.split("."):
+        if not isinstance(cur, dict) or part not in cur:
+            return MISSING  # points into a mandatory value that was not given: stays "???" for the validator
         cur = cur[part]
     return cur
 
@@ -177,12 +186,31 @@ def compose(config_name: str, overrides: list[str] | None = None, config_dir: Pa
             raise ValueError(f"override {ov!r} is not of the form key=value")
         key, val = ov.split("=", 1)
         key = key.lstrip("+")
-        if (config_dir / key).is_dir() and (config_dir / key / f"{val}.yaml").exists():
+        if key == "experiments":
+            values.append((key, val))
+        elif (config_dir / key).is_dir() and (config_dir / key / f"{val}.yaml").exists():
             choices[key] = val  # config-group choice, e.g. paths=default
         else:
             values.append((key, _parse_value(val)))
+    # ``+experiments=<name>``: a ``# @package _global_`` file whose body merges at the root and whose defaults may
+    # ``override /<group>: <choice>`` (configs/experiments/*.yaml); command-line group choices still win
+    experiment_bodies: list[dict] = []
+    for key, val in list(values):
+        if key == "experiments":
+            body = _load_yaml(config_dir / "experiments" / f"{val}.yaml")
+            for entry in body.pop("defaults", []):
+                if isinstance(entry, dict):
+                    for g, ch in entry.items():
+                        if str(g).startswith("override /"):
+                            choices.setdefault(str(g)[len("override /"):], ch)
+            body.pop("hydra", None)  # multirun sweeps are a launcher feature, not part of the composed config
+            experiment_bodies.append(body)
+            values.remove((key, val))
     cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in SCHEMA_DEFAULTS.get(config_name, {}).items()}
     _merge(cfg, _compose_file(config_dir, config_name, choices))
+    for body in experiment_bodies:
+        _merge(cfg, body)
+    cfg["hydra"] = {"runtime": {"choices": {k[1:]: v for k, v in choices.items() if k.startswith("=")}}}
     if isinstance(cfg.get("paths"), dict):
         cfg["paths"] = _merge(dict(SCHEMA_DEFAULTS["paths"]), cfg["paths"])
     for key, val in values:
@@ -193,7 +221,9 @@ def compose(config_name: str, overrides: list[str] | None = None, config_dir: Pa
                 cur[p] = {}
             cur = cur[p]
         cur[parts[-1]] = val
-    return _wrap(_resolve(cfg, cfg))
+    cfg = _resolve(cfg, cfg)
+    cfg.pop("hydra", None)
+    return _wrap(cfg)
 
 
 def missing_keys(cfg: dict, prefix: str = "") -> list[str]:
@@ -211,6 +241,16 @@ def validate_dino_config(cfg: dict) -> None:
     miss = missing_keys(cfg)
     if miss:
         msg = ["The following parameters were missing from dino_features.yaml"]
+        msg += [f"{i}. {k}" for i, k in enumerate(miss, 1)]
+        logging.error("\n".join(msg))
+        sys.exit(1)
+
+
+def validate_experiment_config(cfg: dict, config_name: str) -> None:
+    """config.py:205-231 for train_model / eval_model: the same listing of ``???`` keys, then exit(1)."""
+    miss = missing_keys(cfg)
+    if miss:
+        msg = [f"The following parameters were missing from {config_name}.yaml"]
         msg += [f"{i}. {k}" for i, k in enumerate(miss, 1)]
         logging.error("\n".join(msg))
         sys.exit(1)

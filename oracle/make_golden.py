@@ -52,10 +52,15 @@ def install_shims() -> None:
         def __init__(self, *a, **k):
             pass
 
+    class LightningDataModule:
+        pass
+
     pl = mod("pytorch_lightning", LightningModule=LightningModule, Callback=Callback, Trainer=object,
-             LightningDataModule=object, seed_everything=lambda *a, **k: None)
+             LightningDataModule=LightningDataModule, seed_everything=lambda *a, **k: None)
     mod("pytorch_lightning.utilities", grad_norm=lambda *a, **k: {})
     mod("pytorch_lightning.callbacks", Callback=Callback, BasePredictionWriter=BasePredictionWriter)
+    mod("pytorch_lightning.callbacks.prediction_writer", BasePredictionWriter=BasePredictionWriter)
+    mod("pytorch_lightning.utilities.types", STEP_OUTPUT=object)
     pl.utilities = sys.modules["pytorch_lightning.utilities"]
 
     class Metric(torch.nn.Module):
@@ -227,6 +232,48 @@ def golden_crop_collate(out: dict) -> None:
     out["collate_tomo_sizes"] = batch.tomo_sizes.numpy()
 
 
+HOST_SPLITS = [  # (sample, tomo_name, split_id): the synthetic splits.csv of the host-logic fixtures
+    ("A", "a0.hdf", 0), ("A", "a1.hdf", 1), ("A", "a2.hdf", 2), ("A", "a3.hdf", 0), ("B", "b0.hdf", 0), ("B", "b1.hdf", 1),
+    ("B", "b2.hdf", 2), ("C", "c0.hdf", 1), ("C", "c1.hdf", 2),
+]
+HOST_RESULTS = [  # (sample, tomo_name, split_id, dice_metric, f1_metric): rows fed to CsvWriter, incl. a replacement
+    ("A", "a0.hdf", 0, 0.5, 0.25), ("A", "a3.hdf", 0, 0.75, 0.5), ("A", "a0.hdf", 0, 0.625, 0.375), ("B", "b0.hdf", None, 0.1, 0.2),
+]
+
+
+def golden_host(tmp: Path) -> dict:
+    """Selection rules of the reference's Single/MultiSampleDataModule on a small splits.csv, and the csv text its
+    CsvWriter leaves behind (models/callbacks.py:112-206) -- the host logic either side of the head."""
+    import pandas as pd
+
+    single = ref_import("cryovit.datamodules.single_sample_datamodule").SingleSampleDataModule
+    multi = ref_import("cryovit.datamodules.multi_sample_datamodule").MultiSampleDataModule
+    cb = ref_import("cryovit.models.callbacks")
+    types_mod = ref_import("cryovit.types")
+    split_file = tmp / "splits.csv"
+    pd.DataFrame(HOST_SPLITS, columns=["sample", "tomo_name", "split_id"]).to_csv(split_file, index=False)
+    out: dict = {"selection": {}}
+    cases = {
+        "single_A_split0": (single, dict(sample=["A"], split_id=0, split_key="split_id", test_sample=None)),
+        "single_A_nosplit_testB": (single, dict(sample=["A"], split_id=None, split_key="split_id", test_sample=["B"])),
+        "multi_AB_split1": (multi, dict(sample=["A", "B"], split_id=1, split_key="split_id", test_sample=None)),
+        "multi_AB_nosplit_testC": (multi, dict(sample=["A", "B"], split_id=None, split_key="split_id", test_sample=["C"])),
+        "multi_AC_split2_testB": (multi, dict(sample=["A", "C"], split_id=2, split_key="split_id", test_sample=["B"])),
+    }
+    for tag, (cls, kw) in cases.items():
+        dm = cls(split_file=split_file, dataset_fn=None, dataloader_fn=None, **kw)
+        out["selection"][tag] = {k: [list(map(str, r)) for r in getattr(dm, k + "_df")()[["sample", "tomo_name"]].values.tolist()]
+                                 for k in ("train", "val", "test", "predict")}
+    w = cb.CsvWriter(tmp / "results")
+    for s_, t_, sid, dice, f1 in HOST_RESULTS:
+        res = types_mod.BatchedModelResult(num_tomos=1, samples=[s_], tomo_names=[t_], split_id=None if sid is None else [sid],
+                                           data=[], label=[], preds=[], losses={}, metrics={"dice_metric": dice, "f1_metric": f1},
+                                           aux_data=None)
+        w.on_test_batch_end(None, None, res, None, 0)
+    out["csv"] = {f.name: f.read_text() for f in sorted((tmp / "results").glob("*.csv"))}
+    return out
+
+
 def golden_dinov2(out: dict) -> None:
     """Oracle restatement vs transformers' independent Dinov2WithRegisters on identical weights."""
     from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
@@ -305,6 +352,11 @@ def main() -> None:
     golden_crop_collate(ref_out)
     golden_layout(ref_out)
     np.savez_compressed(GOLD / "reference_src.npz", **ref_out)
+    import json
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        (GOLD / "reference_host.json").write_text(json.dumps(golden_host(Path(td)), indent=1))
     hf_out: dict = {}
     golden_dinov2(hf_out)
     np.savez_compressed(GOLD / "dinov2_hf.npz", **hf_out)

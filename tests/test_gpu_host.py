@@ -218,3 +218,43 @@ def test_fit_head_on_feature_files(cuda_lib, tmp_path):
     before, after = dice(sd0), dice(sd)
     print(f"\n[train] Dice before {before:.3f} after {after:.3f}")
     assert after > before + 0.05
+
+
+def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path):
+    """cfg-5 as a user runs it: ``cryovit.training.train_model`` (+experiments=multi_mito, two samples, split 0 held
+    out) writes ``<exp_dir>/<name>/<samples>/split_0/weights.pt``; ``cryovit.training.eval_model`` with the same
+    overrides loads it, scores the held-out tomograms and leaves the reference's csv rows and prediction files."""
+    import pandas as pd
+    from cryovit.config import compose, validate_experiment_config
+    from cryovit.run import eval_model, train_model
+    from cryovit_b200.host import hdf
+
+    rng = np.random.default_rng(4)
+    rows = []
+    for s in ("A", "B"):
+        for i in range(3):
+            feats = rng.standard_normal((384, 4, 3, 3)).astype(np.float16)
+            lab = (np.repeat(np.repeat(feats[0].astype(np.float32), 16, axis=1), 16, axis=2) > 0).astype(np.int8)
+            lab[0, :8] = -1  # some ignored voxels
+            hdf.write_tomogram(tmp_path / "data" / "tomograms" / s / f"{s}{i}.hdf",
+                               {"data": rng.integers(0, 256, (4, 48, 48), dtype=np.uint8), "labels/mito": lab, "dino_features": feats})
+            rows.append((s, f"{s}{i}.hdf", i % 2))
+    (tmp_path / "data" / "csv").mkdir()
+    pd.DataFrame(rows, columns=["sample", "tomo_name", "split_id"]).to_csv(tmp_path / "data" / "csv" / "splits.csv", index=False)
+    common = ["model=cryovit", "+experiments=multi_mito", "datamodule.sample=[A,B]", "datamodule.split_id=0", "+model.in_channels=384",
+              f"paths.data_dir={tmp_path / 'data'}", f"paths.exp_dir={tmp_path / 'exp'}"]
+    cfg = compose("train_model", common + ["trainer.max_epochs=10", "model.lr=2e-3"])
+    validate_experiment_config(cfg, "train_model")
+    weights = train_model.run_trainer(cfg)
+    assert weights == tmp_path / "exp" / "multi_cryovit_mito" / "A_B" / "split_0" / "weights.pt" and weights.exists()
+
+    cfg = compose("eval_model", common)
+    results = eval_model.run_trainer(cfg)
+    assert sorted(r.tomo_names[0] for r in results) == ["A0.hdf", "A2.hdf", "B0.hdf", "B2.hdf"]  # split 0 of both samples
+    for s in ("A", "B"):
+        df = pd.read_csv(tmp_path / "exp" / "results" / "multi_cryovit_mito" / f"{s}_0.csv")
+        assert list(df.columns) == ["sample", "tomo_name", "dice_metric", "f1_metric", "split_id"] and len(df) == 2
+        assert (df["dice_metric"] > 0.5).all(), df  # the toy labels are learnable from feature channel 0
+        pred = hdf.read_tomogram(tmp_path / "exp" / "predictions" / "multi_cryovit_mito" / s / f"{s}0.hdf")
+        assert sorted(pred) == ["data", "mito", "mito_preds"] and pred["mito_preds"].shape == (4, 48, 48)
+        assert pred["mito_preds"].dtype == np.float32 and pred["data"].dtype == np.uint8
