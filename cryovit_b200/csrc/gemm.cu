@@ -11,11 +11,11 @@ namespace cvit {
 // everywhere. Process-wide switch for A/B measurements (tools/kernel_probe.py); the default is pairs.
 static int g_gemm_pair = 1;
 
-template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false>
+template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false, int SUB = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int num_tiles,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, KSPAN, PAIR>;
-  auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, KSPAN, PAIR>;
+  using Cfg = GemmCfg<BN, KSPAN, PAIR, SUB>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, KSPAN, PAIR, SUB>;
   static bool configured = false;  // per instantiation; attribute is per function, setting twice is harmless
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -70,6 +70,10 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 #define CVIT_GEMM_CASE(BN_, EPI_, AMODE_, KSPAN_)                                     \
   if (bn == BN_ && epi == EPI_ && kspan == KSPAN_)                                    \
     return launch_gemm<BN_, EPI_, AMODE_, KSPAN_>(tmA, tmB, args, num_tiles, stream);
+// tall tiles (SUB_ consecutive 128-row blocks per pipeline stage) for single-K-chunk GEMMs with many rows
+#define CVIT_GEMM_TALL_CASE(BN_, EPI_, KSPAN_, SUB_)                                                     \
+  if (bn == BN_ && epi == EPI_ && kspan == KSPAN_ && K <= KSPAN_ / 2 && M >= 8 * SUB_ * GEMM_BM)         \
+    return launch_gemm<BN_, EPI_, AMODE_ROWS, KSPAN_, false, SUB_>(tmA, tmB, args, (int)((M + SUB_ * GEMM_BM - 1) / (SUB_ * GEMM_BM)) * (int)(N / bn), stream);
 #define CVIT_GEMM_PAIR_CASE(EPI_)                                                     \
   if (pair && epi == EPI_)                                                            \
     return launch_gemm<256, EPI_, AMODE_ROWS, 128, true>(tmA, tmB, args, num_tiles, stream);
@@ -108,6 +112,9 @@ static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, i
   if (rc) return rc;
   const int bm = pair ? 2 * GEMM_BM : GEMM_BM;
   const int num_tiles = (int)(((M + bm - 1) / bm) * (N / bn));
+  CVIT_GEMM_TALL_CASE(32, EPI_CONVT_GELU, 32, 8)    // ConvTranspose 16 -> 8 (K = 16, N = 32)
+  CVIT_GEMM_TALL_CASE(128, EPI_CONVT_GELU, 64, 2)   // ConvTranspose 32 -> 32 (K = 32, N = 128)
+  CVIT_GEMM_TALL_CASE(128, EPI_CONVT_GELU, 128, 2)  // ConvTranspose 64 -> 32 (K = 64, N = 128)
   CVIT_GEMM_PAIR_CASE(EPI_BIAS)
   CVIT_GEMM_PAIR_CASE(EPI_BIAS_GELU)
   CVIT_GEMM_PAIR_CASE(EPI_BIAS_SWIGLU)

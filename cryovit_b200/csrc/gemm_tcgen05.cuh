@@ -52,16 +52,23 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 
-template <int BN, int KSPAN, bool PAIR = false>
+// SUB > 1 ("tall" tiles, plain-rows GEMMs with a single short K chunk: the transposed convolutions of the head, K = 16
+// .. 64): one pipeline stage carries SUB consecutive 128-row blocks of A, the issuer runs one MMA chain per block into
+// its own TMEM column range, and the epilogue warps share the SUB x (BN / 32) column chunks. With K this short a
+// 128-row tile is a few hundred cycles of tensor work, so the per-tile barrier round trips (and, for BN = 32, half of
+// the epilogue warps having no chunk at all) dominated; SUB amortises them.
+template <int BN, int KSPAN, bool PAIR = false, int SUB = 1>
 struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * KSPAN;
+  static constexpr int A_BLOCK_BYTES = GEMM_BM * KSPAN;
+  static constexpr int A_BYTES = SUB * A_BLOCK_BYTES;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KSPAN;  // a CTA pair splits the B tile half/half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int STG_BYTES_PER_WARP = 4096;  // one 32x32 fp32 transpose buffer per epilogue warp
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int TMEM_COLS = 2 * SUB * ACC_STRIDE;
+  static_assert(TMEM_COLS <= 512, "SUB x accumulator width exceeds TMEM");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * STG_BYTES_PER_WARP + 256 /*barriers*/ + 1024 /*align slack*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
@@ -114,12 +121,14 @@ __device__ __forceinline__ int tile_row_to_global(const TileCoord& t, int r, con
 // memory traffic (TMA writes and MMA reads) against the single-CTA kernel. Barriers: the "full" barriers that count
 // TMA bytes live in the leader (both producers signal them), "empty"/"accumulator full" are multicast commits to both
 // CTAs, "accumulator empty" collects the epilogue warps of both CTAs in the leader.
-template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false>
+template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false, int SUB = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
   static_assert(!PAIR || AMODE == AMODE_ROWS, "CTA pairs are implemented for the plain-rows GEMM only");
-  using Cfg = GemmCfg<BN, KSPAN, PAIR>;
+  static_assert(SUB == 1 || (AMODE == AMODE_ROWS && !PAIR), "tall tiles are implemented for the single-CTA plain-rows GEMM only");
+  using Cfg = GemmCfg<BN, KSPAN, PAIR, SUB>;
+  constexpr int TILE_M = (PAIR ? 2 : SUB) * GEMM_BM;  // output rows per tile (per CTA pair with PAIR)
   constexpr int KC = KSPAN / 2;        // bf16 elements of K per stage
   constexpr int MMAS_PER_STAGE = KC / 16;
   constexpr int STAGES = Cfg::STAGES;
@@ -143,7 +152,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_n = args.N / BN;
   const int num_m = AMODE == AMODE_CONV3
                         ? args.D * ((args.H + args.BH - 1) / args.BH) * ((args.W + args.BW - 1) / args.BW)
-                        : (args.M + (PAIR ? 2 : 1) * GEMM_BM - 1) / ((PAIR ? 2 : 1) * GEMM_BM);
+                        : (args.M + TILE_M - 1) / TILE_M;
   const int num_tiles = num_m * num_n;
   const int k_chunks = (args.K + KC - 1) / KC;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -152,6 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto coord = [&](int tile) {
     TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
     if (PAIR) t.m0 = 2 * t.m0 + (int)rank * GEMM_BM;
+    if (SUB > 1) t.m0 *= SUB;
     return t;
   };
 
@@ -211,7 +221,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, dx, dy, dz);
               tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, tap * args.N + t.n0);
             } else {
-              tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, t.m0);
+#pragma unroll
+              for (int sub = 0; sub < SUB; ++sub)  // blocks past the last row are zero-filled by TMA and never stored
+                tma_load_2d(sA + s * Cfg::A_BYTES + sub * Cfg::A_BLOCK_BYTES, &tmA, bar_full + 8 * s, kc * KC, t.m0 + sub * GEMM_BM);
               tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, t.n0);
             }
             if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -234,7 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const TileCoord t = coord(tile);
         mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * SUB * Cfg::ACC_STRIDE;
         uint32_t accumulate = 0;
         const int taps = AMODE == AMODE_CONV3 ? 27 : 1;
         for (int tap = 0; tap < taps; ++tap) {
@@ -247,13 +259,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(bar_full + 8 * s, ph);
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES);
               const uint64_t bdesc = umma_smem_desc_kmajor<KSPAN>(sB + s * Cfg::B_BYTES);
 #pragma unroll
-              for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-                // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
-                if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
-                else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+              for (int sub = 0; sub < SUB; ++sub) {
+                const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES + sub * Cfg::A_BLOCK_BYTES);
+#pragma unroll
+                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                  // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
+                  if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                  else umma_bf16(d_tmem + sub * Cfg::ACC_STRIDE, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                }
               }
               // smem slot reusable once these MMAs retire (in both CTAs of a pair)
               if (PAIR) umma_commit_pair(bar_empty + 8 * s);
@@ -307,13 +322,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord t = coord(tile);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tcgen05_fence_after();
-      const uint32_t t_acc = tmem_base + acc * Cfg::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_acc0 = tmem_base + acc * SUB * Cfg::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
       // global row of this lane's first output row (rows mode: linear, 4 apart per step; conv mode: per row)
       int grow_it[8];
+      if (SUB == 1) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) grow_it[it] = tile_row_to_global<AMODE>(t, q * 32 + it * 4 + rsub, args);
+        for (int it = 0; it < 8; ++it) grow_it[it] = tile_row_to_global<AMODE>(t, q * 32 + it * 4 + rsub, args);
+      }
 #pragma unroll 1
-      for (int ch = half; ch < NCHUNK; ch += 2) {
+      for (int idx = half; idx < SUB * NCHUNK; idx += 2) {
+        const int sub = SUB == 1 ? 0 : idx / NCHUNK;
+        const int ch = SUB == 1 ? idx : idx - sub * NCHUNK;
+        const uint32_t t_acc = t_acc0 + sub * Cfg::ACC_STRIDE;
+        if (SUB > 1) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int g = t.m0 + sub * GEMM_BM + q * 32 + it * 4 + rsub;
+            grow_it[it] = g < args.M ? g : -1;
+          }
+        }
         const int c0 = ch * 32;
         const int ncol = t.n0 + c0 + jc * 4;  // first of this lane's 4 accumulator columns
         float4 xs[8], ys[8];

@@ -274,7 +274,9 @@ def test_conv3d_halo(cuda_lib, D, H, W, Cin, Cout, dil):
     _close(out, ref, atol=2e-2, rtol=1e-2, what="conv3d_halo")
 
 
-@pytest.mark.parametrize("D,H,W,Cin,Cout", [(3, 8, 16, 192, 128), (2, 8, 16, 64, 32), (2, 8, 16, 32, 32), (2, 8, 16, 16, 8)])
+@pytest.mark.parametrize("D,H,W,Cin,Cout", [(3, 8, 16, 192, 128), (2, 8, 16, 64, 32), (2, 8, 16, 32, 32), (2, 8, 16, 16, 8),
+                                            # tall-tile path (8 / 2 row blocks per stage), incl. ragged last tiles
+                                            (2, 64, 64, 16, 8), (3, 50, 70, 16, 8), (1, 50, 70, 32, 32), (2, 40, 52, 64, 32)])
 def test_convT(cuda_lib, D, H, W, Cin, Cout):
     from cryovit_b200 import ops
     x = _rand(D, H, W, Cin, seed=1).bfloat16()
