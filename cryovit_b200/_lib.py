@@ -56,6 +56,8 @@ SIGNATURES: dict[str, list] = {
     "cvit_ndhwc_to_cfirst_padded_x3": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_wgrad_splitk": [P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "cvit_adamw_f32": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, F32, P],
+    "cvit_conv3d_wpack8_gelu": [P, P, P, P, I64, I64, I64, I32, P],
+    "cvit_conv3d_wpack8_final": [P, P, P, P, P, I64, I64, I64, P],
     "cvit_set_gemm_pair": [I32],  # returns the previous setting, not an error code (use load().cvit_set_gemm_pair)
 }
 
@@ -79,6 +81,8 @@ def load() -> ctypes.CDLL:
     lib.cvit_abi_version.argtypes = []
     lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
     lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
+    lib.cvit_conv3d_wpack_weight_bytes.restype = c_int64
+    lib.cvit_conv3d_wpack_weight_bytes.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = c_int

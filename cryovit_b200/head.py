@@ -58,6 +58,23 @@ def halo_weight_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
     return img.reshape(-1)
 
 
+def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
+    """Conv3d weight [Cout, 8, 3, 3, 3] -> the banded shared-memory image of csrc/conv_wpack.cu:
+    [kd*3+kh][K step][2 chunks][n = j_out * Cout + co][8 ci], where chunk c of step s is window voxel j_in = 2 s + c
+    (the window of a group of P output voxels starts one voxel to their left) and the entry is w[co, ci, kd, kh, kw] with
+    kw = j_in - j_out when that is a tap (0..2), zero otherwise."""
+    cout, cin = w.shape[:2]
+    assert cin == 8 and (P + 2) % 2 == 0
+    wt = w.float().permute(2, 3, 4, 0, 1).reshape(9, 3, cout, 8)  # [kd*3+kh][kw][co][ci]
+    img = torch.zeros(9, (P + 2) // 2, 2, P, cout, 8, dtype=torch.float32)
+    for j_in in range(P + 2):
+        for kw in range(3):
+            j_out = j_in - kw
+            if 0 <= j_out < P:
+                img[:, j_in // 2, j_in % 2, j_out] = wt[:, kw]
+    return img.reshape(-1)
+
+
 class CryoVITHeadB200:
     def __init__(self, in_channels: int = 1536):
         self.in_channels = in_channels
@@ -127,6 +144,9 @@ class CryoVITHeadB200:
         w["o1_img"], w["o1_b16"] = bf(halo_weight_image(sd["output_layer.0.weight"], 16)), f32(o1b)
         w["o2_w"] = f32(sd["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8))
         w["o2_b"] = f32(sd["output_layer.2.bias"])
+        # W-packed tensor-core versions of both output convolutions (planes whose width is a multiple of 16)
+        w["o1_wp"], w["o1_wp_b"] = bf(wpack_weight_image(sd["output_layer.0.weight"], 8)), f32(sd["output_layer.0.bias"].repeat(8))
+        w["o2_wp"], w["o2_wp_b"] = bf(wpack_weight_image(sd["output_layer.2.weight"], 16)), f32(sd["output_layer.2.bias"].repeat(16))
         self._w = w
 
     def _buf(self, name: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
@@ -179,8 +199,12 @@ class CryoVITHeadB200:
         scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
         logits = torch.empty(D, H, W, device=self.device) if want_logits else None
         probs = torch.empty(D, H, W, device=self.device) if want_probs else None
-        ops.conv3d_halo(cur, w_["o1_img"], w_["o1_b16"], scratch, 1, 16)  # output_layer.0 + GELU on tensor cores
-        ops.head_out_conv(scratch, w_["o2_w"], w_["o2_b"], logits, probs)   # output_layer.2 + clip (+ sigmoid), fp32
+        if W % 16 == 0:  # always true downstream of the ViT (W = 16 w); both on tensor cores, voxels packed into the MMA N
+            ops.conv3d_wpack8_gelu(cur, w_["o1_wp"], w_["o1_wp_b"], scratch)              # output_layer.0 + GELU
+            ops.conv3d_wpack8_final(scratch, w_["o2_wp"], w_["o2_wp_b"], logits, probs)   # output_layer.2 + clip (+ sigmoid)
+        else:
+            ops.conv3d_halo(cur, w_["o1_img"], w_["o1_b16"], scratch, 1, 16)
+            ops.head_out_conv(scratch, w_["o2_w"], w_["o2_b"], logits, probs)
         self.launches += 2
         return logits, probs
 

@@ -147,6 +147,25 @@ def conv3d_halo(x, w_img, bias, out, dil: int, cout_pad: int) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, _stream())
 
 
+def conv3d_wpack8_gelu(x, w_img, bias_n, out, act: bool = True) -> None:
+    """output_layer.0 (8 -> 8, k3) + bias + GELU with 8 output voxels of a row per MMA row (csrc/conv_wpack.cu)."""
+    D, H, W, Cin = x.shape
+    if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_wpack_weight_bytes(8, 8):
+        raise _lib.CryovitB200Error("conv3d_wpack8_gelu: needs 8 input channels and the (P=8, Cout=8) weight image")
+    _lib.call("cvit_conv3d_wpack8_gelu", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias_n, F32, "bias_n"),
+              _chk(out, BF16, "out"), D, H, W, int(act), _stream())
+
+
+def conv3d_wpack8_final(x, w_img, bias_n, logits=None, probs=None) -> None:
+    """output_layer.2 (8 -> 1, k3) + bias + clip(-5, 5) (+ sigmoid) with 16 output voxels of a row per MMA row."""
+    D, H, W, Cin = x.shape
+    if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_wpack_weight_bytes(16, 1):
+        raise _lib.CryovitB200Error("conv3d_wpack8_final: needs 8 input channels and the (P=16, Cout=1) weight image")
+    _lib.call("cvit_conv3d_wpack8_final", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias_n, F32, "bias_n"),
+              _chk(logits, F32, "logits") if logits is not None else None,
+              _chk(probs, F32, "probs") if probs is not None else None, D, H, W, _stream())
+
+
 def convT_1x2x2(x, w_sub, bias4, out) -> None:
     D, H, W, Cin = x.shape
     Cout = w_sub.shape[0] // 4

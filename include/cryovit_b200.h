@@ -153,6 +153,20 @@ int64_t cvit_conv3d_halo_weight_bytes(int64_t Cin, int64_t Cout_pad);
 int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
                            int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, void* stream);
 
+/* The two 8-channel full-resolution convolutions of output_layer (models/cryovit.py:30-34) with P consecutive output
+ * voxels of a row packed into the MMA N dimension (banded weight matrix; csrc/conv_wpack.cu). x is bf16 [D,H,W,8], W a
+ * multiple of P (8 resp. 16), dilation 1. w_img is the host-arranged banded image (bf16,
+ * cvit_conv3d_wpack_weight_bytes(P, Cout) bytes; cryovit_b200.head.wpack_weight_image), bias_n the bias repeated per
+ * packed voxel ([P * Cout] fp32).
+ *   cvit_conv3d_wpack8_gelu : output_layer.0 (8 -> 8) + bias + GELU (act = 1) -> bf16 [D,H,W,8]
+ *   cvit_conv3d_wpack8_final: output_layer.2 (8 -> 1) + bias + clip(-5, 5) -> logits fp32 [D,H,W] and/or
+ *                             sigmoid of them -> probs (cryovit.py:39,49); either pointer may be null. */
+int64_t cvit_conv3d_wpack_weight_bytes(int64_t P, int64_t Cout);
+int cvit_conv3d_wpack8_gelu(const void* x, const void* w_img, const float* bias_n, void* out, int64_t D, int64_t H,
+                            int64_t W, int act, void* stream);
+int cvit_conv3d_wpack8_final(const void* x, const void* w_img, const float* bias_n, float* logits, float* probs,
+                             int64_t D, int64_t H, int64_t W, void* stream);
+
 /* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
  * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;
  * bias4 fp32 [4 * Cout] (the bias repeated per sub-pixel); out bf16 [D, 2H, 2W, Cout]. */

@@ -309,3 +309,40 @@ def test_head_tail(cuda_lib, D, H, W):
     z = F.conv3d(y, w2, b2, padding="same").clamp(-5, 5)[0, 0]
     _close(logits, z, atol=5e-2, rtol=1e-2, what="tail logits")  # bf16 intermediate, 216-term sums
     _close(probs, torch.sigmoid(z), atol=5e-3, rtol=1e-2, what="tail probs")
+
+
+@pytest.mark.parametrize("D,H,W", [(3, 16, 64), (2, 20, 80), (1, 33, 144), (4, 48, 256)])
+def test_conv3d_wpack_output_layers(cuda_lib, D, H, W):
+    """Both 8-channel output convolutions with the output voxels of a row packed into the MMA N dimension (banded
+    weights, csrc/conv_wpack.cu) against fp32 torch on the same bf16 operands: depth taps outside the volume (D = 1, 2),
+    ragged tiles in H (20, 33) and in W (80 and 144 are not multiples of the 64 / 128-voxel tile width)."""
+    from cryovit_b200 import ops
+    from cryovit_b200.head import wpack_weight_image
+    x = _rand(D, H, W, 8, seed=1).bfloat16()
+    w1 = _rand(8, 8, 3, 3, 3, scale=0.1, seed=2).bfloat16()
+    b1 = _rand(8, seed=3)
+    w2 = _rand(1, 8, 3, 3, 3, scale=0.3, seed=4).bfloat16()
+    b2 = _rand(1, seed=5)
+    mid = torch.full((D, H, W, 8), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv3d_wpack8_gelu(x, wpack_weight_image(w1.cpu(), 8).to(DEV).bfloat16(), b1.repeat(8).contiguous(), mid)
+    y = F.gelu(F.conv3d(x.float().permute(3, 0, 1, 2)[None], w1.float(), b1, padding="same"))
+    _close(mid, y[0].permute(1, 2, 3, 0), atol=1e-2, rtol=1e-2, what="wpack 8->8 + GELU")
+    logits = torch.full((D, H, W), float("nan"), device=DEV)
+    probs = torch.full((D, H, W), float("nan"), device=DEV)
+    ops.conv3d_wpack8_final(mid, wpack_weight_image(w2.cpu(), 16).to(DEV).bfloat16(), b2.repeat(16).contiguous(), logits, probs)
+    z = F.conv3d(mid.float().permute(3, 0, 1, 2)[None], w2.float(), b2, padding="same").clamp(-5, 5)[0, 0]
+    _close(logits, z, atol=2e-3, rtol=1e-3, what="wpack 8->1 logits")  # same bf16 operands, fp32 accumulation both sides
+    _close(probs, torch.sigmoid(z), atol=1e-3, rtol=1e-3, what="wpack probs")
+    only = torch.full((D, H, W), float("nan"), device=DEV)
+    ops.conv3d_wpack8_final(mid, wpack_weight_image(w2.cpu(), 16).to(DEV).bfloat16(), b2.repeat(16).contiguous(), None, only)
+    assert torch.equal(only, probs)
+
+
+def test_conv3d_wpack_rejects_unpackable_width(cuda_lib):
+    from cryovit_b200 import ops
+    from cryovit_b200._lib import CryovitB200Error
+    from cryovit_b200.head import wpack_weight_image
+    x = torch.zeros(1, 16, 60, 8, device=DEV, dtype=torch.bfloat16)  # 60 is not a multiple of 8
+    w = wpack_weight_image(torch.zeros(8, 8, 3, 3, 3), 8).to(DEV).bfloat16()
+    with pytest.raises(CryovitB200Error, match="multiple of 8"):
+        ops.conv3d_wpack8_gelu(x, w, torch.zeros(64, device=DEV), torch.empty_like(x))
