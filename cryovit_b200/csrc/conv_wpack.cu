@@ -14,15 +14,22 @@
 // 81 per 2048 voxels for 8 -> 1 (P = 16, N = 16) instead of 144 / 288. The banded matrix multiplies (P + 2) / 3 times
 // more zeros than the convolution needs -- irrelevant, these layers are nowhere near the tensor pipe's rate.
 //
-// Shared-memory image of one staged depth plane (tile = 16 rows x 8 groups, one halo row above and below):
-//     slab j (window voxel j - 1 of every group):  [18 rows h][8 groups g][8 channels = 16 B]      (+16 B pad)
-// A operand of (kh, K step s): rows m = (h, g) are 16 B apart (canonical K-major SWIZZLE_NONE: 8 rows = one 128 B core
-// matrix, SBO = 128 B), the two 8-channel K chunks are slabs 2s and 2s + 1 (LBO = slab pitch), the row tap kh is the
-// start address (+ kh * 8 * 16 B). Nothing is re-laid-out per tap.
-// Staging: four loader warps copy each input voxel (16 B) of the plane from global memory straight to its slab
-// position(s) with cp.async (zero fill = "same" padding), enumerated so that a warp reads consecutive voxels; the two
-// voxels shared by neighbouring groups are copied twice (10 / 8 of the plane). A plane is one pipeline stage; the
-// banded weights of all 27 (kd, kh, kw) taps (92 KB / 41 KB) stay resident.
+// Shared-memory image of one staged depth plane (tile = 16 rows x 8 groups, one halo row above and below; staged row
+// index m' = h * 8 + g, 144 of them): the window's 16-byte chunks j = 0 .. P+1 (window voxel j - 1 of every group) are
+//     chunks 0 .. P-1 : P / 8 atoms of the K-major SWIZZLE_128B layout -- row m' is 128 B, chunk c of the atom sits at
+//                       16-byte slot c ^ (m' & 7) (exactly what TMA's 128B swizzle would produce, and what the ViT
+//                       GEMMs feed the tensor core), so the 8 consecutive voxels a quarter-warp copies fill one 128 B
+//                       row conflict-free AND every core matrix the MMA reads is one aligned 128 B line;
+//     chunks P, P+1   : two SWIZZLE_NONE slabs [144 rows][16 B] (LBO = slab pitch, SBO = 128 B).
+// The row tap kh is the descriptor start address (+ kh * 8 rows = 1024 B resp. 128 B, which keeps the swizzle phase),
+// a K step inside an atom is +32 B. Nothing is re-laid-out per tap. (A first version used P + 2 un-swizzled slabs
+// with a 16 B skew against the loaders' bank conflicts: the skew mis-aligned every core matrix read and doubled the
+// cost of an MMA -- 0.76 ms instead of the per-tap kernel's 1.16 ms, where ~0.4 was expected.)
+// Staging: loader warps copy each input voxel (16 B) of a plane from global memory straight to its position(s) with
+// cp.async (zero fill = "same" padding), enumerated so that a warp reads consecutive voxels; the two voxels shared by
+// neighbouring groups are copied twice (10 / 8 of the plane). A plane is one pipeline stage, and a CTA walks ALONG
+// DEPTH through its tiles with a rolling window of three staged planes, so every plane is staged once per CTA, not
+// once per depth tap. The banded weights of all 27 (kd, kh, kw) taps (92 KB / 41 KB) stay resident.
 //
 // One CTA per SM, persistent over tiles, 288 threads: warps 0-3 loaders, warps 4-7 epilogue (thread = MMA row: P voxels
 // x Cout values -> bias + GELU -> bf16, or + clip / sigmoid -> fp32; 128 / 64 contiguous bytes per thread), warp 8 MMA
@@ -34,17 +41,20 @@ namespace cvit {
 
 constexpr int WP_G = 8, WP_TH = 16;                 // MMA row = (h, g): 16 x 8 = 128
 constexpr int WP_ROWS = WP_TH + 2;                  // staged rows (1-voxel halo)
-constexpr int WP_SLAB = WP_ROWS * WP_G * 16 + 16;   // bytes; +16 so the 8 slabs a quarter-warp writes hit distinct banks
+constexpr int WP_MROWS = WP_ROWS * WP_G;            // staged MMA rows per plane (144)
+constexpr int WP_ATOM = WP_MROWS * 128;             // one SWIZZLE_128B atom: 8 K chunks of every staged row
+constexpr int WP_SLAB = WP_MROWS * 16;              // one un-swizzled slab: one K chunk of every staged row
 constexpr int WP_THREADS = 288;
 constexpr int WP_LOADERS = 128;
-constexpr int WP_LAG = 2;                           // cp.async groups kept in flight per loader thread
 
 template <int P, int COUT>
 struct WpCfg {
   static constexpr int N = P * COUT;                // MMA N
   static constexpr int NS = P + 2;                  // 16-byte K chunks (window voxels) per row
   static constexpr int KSTEPS = NS / 2;             // MMAs (K = 16) per (kd, kh)
-  static constexpr int PLANE = NS * WP_SLAB;
+  static constexpr int ATOMS = P / 8;              // swizzled atoms; the last two chunks are un-swizzled slabs
+  static constexpr int TAIL = ATOMS * WP_ATOM;     // byte offset of the two slabs
+  static constexpr int PLANE = (TAIL + 2 * WP_SLAB + 1023) / 1024 * 1024;  // planes stay 1024-aligned (swizzle phase)
   static constexpr int W_BYTES = 9 * KSTEPS * 2 * N * 16;   // [kd*3+kh][K step][2 chunks][N][16 B]
   static constexpr int STAGES_RAW = (232448 - 1024 - 256 - W_BYTES) / PLANE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -53,8 +63,8 @@ struct WpCfg {
   static constexpr int PER_THREAD = (PIECES + WP_LOADERS - 1) / WP_LOADERS;
   static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 256;
   static constexpr int TW = WP_G * P;               // tile width in voxels
-  static_assert(NS % 2 == 0 && N % 16 == 0 && N <= 128, "P + 2 even; MMA N a multiple of 16");
-  static_assert(STAGES > WP_LAG, "the loaders signal a plane LAG planes late: needs more stages than that");
+  static_assert(P % 8 == 0 && N % 16 == 0 && N <= 128, "whole swizzle atoms; MMA N a multiple of 16");
+  static_assert(STAGES >= 4, "rolling window: three planes held by the MMAs plus at least one being loaded");
   static_assert(PLANE < 65536, "slab offsets are packed into 16 bits");
 };
 
@@ -122,18 +132,27 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  auto tile_of = [&](int tile, int& d, int& h0, int& w0) {
-    d = tile / per_plane;
-    const int r = tile - d * per_plane;
-    const int th = r / tiles_w;
+  // Work = (spatial tile "column", depth) pairs, depth fastest; every CTA owns one contiguous range of them, cut into
+  // SEGMENTS at column changes. Inside a segment the CTA walks along depth with a rolling window of staged planes:
+  // output depth d needs planes d-1, d, d+1, of which only d+1 is new -- one plane load (and a third of the L2
+  // traffic) per output tile instead of three. Planes are numbered in load order (n = 0, 1, ...) by every role;
+  // plane n lives in ring slot n % STAGES with barrier parity (n / STAGES) & 1.
+  const int64_t total = (int64_t)per_plane * args.D;
+  const int i_begin = (int)(total * blockIdx.x / gridDim.x), i_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  auto col_origin = [&](int col, int& h0, int& w0) {
+    const int th = col / tiles_w;
     h0 = th * WP_TH;
-    w0 = (r - th * tiles_w) * Cfg::TW;
+    w0 = (col - th * tiles_w) * Cfg::TW;
   };
+  (void)num_tiles;
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ loaders: global -> slab positions (cp.async)
+    // ------------------------------------------------------------------ loaders: global -> staged positions (cp.async)
+    // All four warps copy every plane; a thread signals plane n-1 (cp.async.wait_group 1, proxy fence, one arrival per
+    // warp) right after issuing plane n, so two plane loads are in flight. Plane n reuses the slot of plane
+    // n - STAGES, which the MMAs released at least one output earlier, so the one-plane lag cannot dead-lock.
     // piece q = (row = h * 8 + g, window chunk j), j fastest: consecutive lanes read consecutive voxels.
-    // Packed per piece, tile-invariant: slab byte offset [0,16) | staged row h [16,21) | tile column + 1 [21,30).
+    // Packed per piece, tile-invariant: staged byte offset [0,16) | staged row h [16,21) | tile column + 1 [21,30).
     uint32_t tab[Cfg::PER_THREAD];
 #pragma unroll
     for (int i = 0; i < Cfg::PER_THREAD; ++i) {
@@ -141,33 +160,28 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
       if (q < Cfg::PIECES) {
         const int row = q / Cfg::NS, j = q - row * Cfg::NS;
         const int h = row / WP_G, g = row - h * WP_G;
-        tab[i] = static_cast<uint32_t>(j * WP_SLAB + row * 16) | (static_cast<uint32_t>(h) << 16) |
-                 (static_cast<uint32_t>(P * g + j) << 21);
+        const int dst = j < P ? (j >> 3) * WP_ATOM + row * 128 + (((j & 7) ^ (row & 7)) << 4)
+                              : Cfg::TAIL + (j - P) * WP_SLAB + row * 16;
+        tab[i] = static_cast<uint32_t>(dst) | (static_cast<uint32_t>(h) << 16) | (static_cast<uint32_t>(P * g + j) << 21);
       } else {
         tab[i] = 0xffffffffu;
       }
     }
-    int s = 0, sig_s = 0, in_flight = 0;
-    uint32_t ph = 0;
-    auto signal_oldest = [&]() {
-      fence_proxy_async_smem();  // this thread's completed cp.async writes -> async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * sig_s);
-      if (++sig_s == STAGES) sig_s = 0;
-      --in_flight;
-    };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int d, h0, w0;
-      tile_of(tile, d, h0, w0);
-      for (int kd = 0; kd < 3; ++kd) {
-        const int dz = d + kd - 1;
-        if (dz < 0 || dz >= args.D) continue;  // the whole depth tap is zero padding
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        const uint32_t dst0 = sIn + s * Cfg::PLANE;
-        const __nv_bfloat16* src_plane = args.x + (int64_t)dz * args.H * args.W * 8;
+    int n = 0;
+    for (int i = i_begin; i < i_end;) {
+      const int col = i / args.D, d_a = i - col * args.D;
+      const int d_b = min(args.D - 1, d_a + (i_end - i) - 1);
+      int h0, w0;
+      col_origin(col, h0, w0);
+      const int p_a = max(d_a - 1, 0), p_b = min(d_b + 1, args.D - 1);
+      for (int pz = p_a; pz <= p_b; ++pz, ++n) {
+        const int slot = n % STAGES;
+        mbar_wait(bar_empty + 8 * slot, (((n / STAGES) & 1) ^ 1) & 1);
+        const uint32_t dst0 = sIn + slot * Cfg::PLANE;
+        const __nv_bfloat16* src_plane = args.x + (int64_t)pz * args.H * args.W * 8;
 #pragma unroll
-        for (int i = 0; i < Cfg::PER_THREAD; ++i) {
-          const uint32_t e = tab[i];
+        for (int k = 0; k < Cfg::PER_THREAD; ++k) {
+          const uint32_t e = tab[k];
           if (e == 0xffffffffu) continue;
           const int hh = h0 - 1 + static_cast<int>((e >> 16) & 31u);
           const int ww = w0 - 1 + static_cast<int>(e >> 21);
@@ -176,53 +190,70 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           cp_async16_zfill(dst0 + (e & 0xffffu), src, ok ? 16u : 0u);
         }
         cp_async_commit();
-        if (++in_flight > WP_LAG) {
-          cp_async_wait<WP_LAG>();
-          signal_oldest();
+        if (n > 0) {
+          cp_async_wait<1>();        // plane n-1 has landed
+          fence_proxy_async_smem();  // this thread's completed cp.async writes -> async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * ((n - 1) % STAGES));
         }
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
+      i += d_b - d_a + 1;
     }
-    cp_async_wait<0>();
-    while (in_flight > 0) signal_oldest();
+    if (n > 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * ((n - 1) % STAGES));
+    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
     constexpr uint32_t B_MMA = 2 * N * 16;
-    int s = 0, acc = 0;
-    uint32_t ph = 0, acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int d = tile / per_plane;
-      mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
-      const uint32_t d_tmem = tmem_base + acc * N;
-      uint32_t accumulate = 0;
-      for (int kd = 0; kd < 3; ++kd) {
-        const int dz = d + kd - 1;
-        if (dz < 0 || dz >= args.D) continue;
-        mbar_wait(bar_full + 8 * s, ph);
+    int acc = 0, n_seg = 0, n_wait = 0;  // n_seg: load index of this segment's first plane; n_wait: planes waited for
+    uint32_t acc_ph = 0;
+    for (int i = i_begin; i < i_end;) {
+      const int col = i / args.D, d_a = i - col * args.D;
+      const int d_b = min(args.D - 1, d_a + (i_end - i) - 1);
+      const int p_a = max(d_a - 1, 0), p_b = min(d_b + 1, args.D - 1);
+      for (int d = d_a; d <= d_b; ++d) {
+        const int newest = n_seg + min(d + 1, args.D - 1) - p_a;
+        for (; n_wait <= newest; ++n_wait) mbar_wait(bar_full + 8 * (n_wait % STAGES), (n_wait / STAGES) & 1);
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
         tcgen05_fence_after();
         if (elect_one_sync()) {
-          const uint32_t plane = sIn + s * Cfg::PLANE;
+          const uint32_t d_tmem = tmem_base + acc * N;
+          uint32_t accumulate = 0;
+          for (int kd = 0; kd < 3; ++kd) {
+            const int pz = d + kd - 1;
+            if (pz < 0 || pz >= args.D) continue;  // the whole depth tap is zero padding
+            const uint32_t plane = sIn + ((n_seg + pz - p_a) % STAGES) * Cfg::PLANE;
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-            for (int st = 0; st < Cfg::KSTEPS; ++st) {
-              const uint32_t a = plane + 2 * st * WP_SLAB + kh * WP_G * 16;
-              const uint32_t b = sW + ((kd * 3 + kh) * Cfg::KSTEPS + st) * B_MMA;
-              umma_bf16(d_tmem, wp_desc_nosw(a, WP_SLAB, 128), wp_desc_nosw(b, N * 16, 128), idesc, accumulate);
-              accumulate = 1;
+              for (int st = 0; st < Cfg::KSTEPS; ++st) {
+                const uint32_t b = sW + ((kd * 3 + kh) * Cfg::KSTEPS + st) * B_MMA;
+                uint64_t adesc;
+                if (st < 4 * Cfg::ATOMS)  // chunks 2 st, 2 st + 1 of atom st / 4: +32 B per K step inside the swizzle span
+                  adesc = umma_smem_desc_kmajor<128>(plane + (st >> 2) * WP_ATOM + kh * WP_G * 128) + 2 * (st & 3);
+                else
+                  adesc = wp_desc_nosw(plane + Cfg::TAIL + kh * WP_G * 16, WP_SLAB, 128);
+                umma_bf16(d_tmem, adesc, wp_desc_nosw(b, N * 16, 128), idesc, accumulate);
+                accumulate = 1;
+              }
             }
           }
-          umma_commit(bar_empty + 8 * s);  // staged plane reusable
+          // plane d-1 has served its last output; at the end of the segment so have the planes still held
+          if (d - 1 >= p_a) umma_commit(bar_empty + 8 * ((n_seg + d - 1 - p_a) % STAGES));
+          if (d == d_b)
+            for (int pz = max(d_b, p_a); pz <= p_b; ++pz) umma_commit(bar_empty + 8 * ((n_seg + pz - p_a) % STAGES));
+          umma_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
         __syncwarp();
-        accumulate = 1;
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1u;
       }
-      if (elect_one_sync()) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1u;
+      n_seg += p_b - p_a + 1;
+      i += d_b - d_a + 1;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: thread == MMA row == P voxels
@@ -231,9 +262,10 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
     const int hl = r / WP_G, g = r - hl * WP_G;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int d, h0, w0;
-      tile_of(tile, d, h0, w0);
+    for (int i = i_begin; i < i_end; ++i) {
+      const int col = i / args.D, d = i - col * args.D;
+      int h0, w0;
+      col_origin(col, h0, w0);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + acc * N + (static_cast<uint32_t>(q * 32) << 16);
@@ -282,11 +314,11 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           for (int j = 0; j < P; ++j) {
             uint32_t pk[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float a = __uint_as_float(v[j * 8 + 2 * i]) + bb[2 * i];
-              float b = __uint_as_float(v[j * 8 + 2 * i + 1]) + bb[2 * i + 1];
+            for (int k = 0; k < 4; ++k) {
+              float a = __uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k];
+              float b = __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1];
               if (args.act) { a = gelu_erf(a); b = gelu_erf(b); }
-              pk[i] = pack_bf16x2(a, b);
+              pk[k] = pack_bf16x2(a, b);
             }
             *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }

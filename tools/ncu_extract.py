@@ -1,5 +1,5 @@
 """`ncu -i X.ncu-rep --page raw --csv` -> small JSON of the metrics the profiles/ summaries quote, one record per
-captured launch.  usage: python tools/ncu_extract.py gpurun_out/X.ncu-rep > profiles/X.json"""
+captured launch.  usage: python tools/ncu_extract.py gpurun_out/X.ncu-rep [extra-metric-regex] > profiles/X.json"""
 import csv
 import io
 import json
@@ -15,6 +15,8 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__cycles_active.avg"]
 
+import re
+EXTRA = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None  # optional: regex of further metric names to keep
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -22,7 +24,7 @@ recs = []
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     rec = {"name": d["Kernel Name"][:120], "grid": d.get("Grid Size"), "block": d.get("Block Size")}
-    for k in KEEP:
+    for k in KEEP + ([h for h in hdr if EXTRA.search(h) and h not in KEEP] if EXTRA else []):
         if k in d and d[k] != "":
             u = units[hdr.index(k)]
             try:
