@@ -432,7 +432,9 @@ def run_b200(args) -> None:
         tf = tensor_ks[top]["flops"] / tensor_ks[top]["ms"] / 1e9
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         roof = {"kernel": top, "bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(tf / peak, 4), "traffic": ncu_traffic(top),
+                "frac": round(tf / peak, 4), "peak_burst": peaks.get("bf16_tflops"),
+                "frac_burst": round(tf / peaks["bf16_tflops"], 4) if peaks.get("bf16_tflops") else None,
+                "traffic": ncu_traffic(top),
                 "traffic_source": "profiles/r01_ncu_full_v8_hot_kernels.json (ncu --set full, one launch, same shapes)",
                 "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
                 "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
