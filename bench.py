@@ -107,7 +107,7 @@ def ncu_traffic(kernel: str) -> float | None:
     return None
 
 
-def head_voxels_per_s(torch, steps: int = 3) -> dict:
+def head_voxels_per_s(torch, dist=None, world: int = 1, steps: int = 3) -> dict:
     """CryoVIT 3-D head on one 1536-channel 128x32x32 feature volume (BASELINE config 4) -> 128x512x512 probabilities."""
     from cryovit_b200.head import CryoVITHeadB200, state_dict_keys
 
@@ -142,10 +142,14 @@ def head_voxels_per_s(torch, steps: int = 3) -> dict:
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / steps
+    if world > 1:  # every rank segments its own volume (tomograms shard by rank, no collective): max over ranks
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     vox = D * H * W
-    return {"value": round(vox / ms * 1e3, 0), "unit": "voxels/s", "ms_per_volume": round(ms, 3),
-            "tflops": round(94864 * vox / ms / 1e9, 1), "launches_per_volume": (head.launches - l0) // steps,
-            "workload": f"CryoVIT head, fp16 (1536,{D},32,32) feature volume -> ({D},{H},{W}) probabilities, weights random"}
+    return {"value": round(world * vox / ms * 1e3, 0), "unit": "voxels/s (all GPUs)", "ms_per_volume": round(ms, 3),
+            "tflops_per_gpu": round(94864 * vox / ms / 1e9, 1), "launches_per_volume": (head.launches - l0) // steps,
+            "workload": f"CryoVIT head, one fp16 (1536,{D},32,32) feature volume per GPU -> ({D},{H},{W}) probabilities, weights random"}
 
 
 def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
@@ -408,7 +412,7 @@ def run_b200(args) -> None:
     # head inference and data-parallel head training: every rank takes part (training all-reduces its gradients)
     del stream
     torch.cuda.empty_cache()
-    head_line = head_voxels_per_s(torch)
+    head_line = head_voxels_per_s(torch, dist, world)
     train_line = head_train_voxels_per_s(torch, dist, world)
     if rank != 0:
         if world > 1:
