@@ -31,6 +31,46 @@ __global__ void __launch_bounds__(256) features_to_ndhwc_kernel(const T* __restr
   }
 }
 
+// The fp16 case with 16-byte accesses on both sides (C % 64 == 0, DHW % 64 == 0, 16-byte aligned pointers): a CTA moves a
+// 64-channel x 64-voxel tile; a thread loads 8 consecutive voxels of one channel (16 B, a warp covers four full 128 B
+// lines), parks them as bf16 in shared memory, then gathers 8 consecutive channels of one voxel (eight 2-byte reads)
+// and writes them as one 16-byte store (8 lanes = the voxel's 128 contiguous bytes of this channel tile).
+constexpr int FT_PITCH = 72;  // halves per shared-memory row: 144 B keeps 16-byte alignment and skews the banks
+__global__ void __launch_bounds__(256) features_f16_to_ndhwc_vec_kernel(const __half* __restrict__ src,
+                                                                         __nv_bfloat16* __restrict__ dst, int C, int64_t DHW) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * FT_PITCH];
+  const int64_t v0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int q = threadIdx.x + k * 256;  // 512 chunks: channel row q / 8, 8-voxel chunk q % 8
+    const int cr = q >> 3, ch = q & 7;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(c0 + cr) * DHW + v0 + ch * 8));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      o[i] = pack_bf16x2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(&tile[cr * FT_PITCH + ch * 8]) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int q = threadIdx.x + k * 256;  // 512 stores: voxel q / 8, 8-channel group q % 8
+    const int vl = q >> 3, cg = q & 7;
+    const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = t16[(cg * 8 + 2 * i) * FT_PITCH + vl], hi = t16[(cg * 8 + 2 * i + 1) * FT_PITCH + vl];
+      o[i] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + (v0 + vl) * C + c0 + cg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm over channels-last bf16 [DHW, C]. Pass 1: per-group sum / sum of squares (fp32, block-reduced,
 // one atomicAdd pair per (block, group)). Pass 2: normalise + affine.
@@ -79,28 +119,46 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ stats, int64_t DHW, int C, int G,
                                                                float eps) {
+  // The grid stride (gridDim * 256 threads) is a multiple of C / 8 (a power-of-two <= 256 here, checked by the
+  // launcher), so a thread meets the SAME 8 channels on every iteration: their scale / shift
+  //   y = x * a + b,  a = gamma * rstd,  b = beta - mean * a
+  // are computed once and live in registers; the loop is one 16-byte load, 8 FMAs and one 16-byte store, unrolled
+  // four deep for memory-level parallelism.
   const int nvec = C / 8;
   const int cpg = C / G;
   const float inv_n = 1.0f / (static_cast<float>(DHW) * cpg);
   const int64_t total = DHW * nvec;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int vec = (int)(idx % nvec);
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + idx * 8);
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const int vec = (int)(first % nvec);
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vec * 8 + i;
+    const int g = c / cpg;
+    const float mean = stats[g] * inv_n;
+    const float var = fmaxf(stats[G + g] * inv_n - mean * mean, 0.f);
+    a[i] = rsqrtf(var + eps) * __ldg(gamma + c);
+    b[i] = __ldg(beta + c) - mean * a[i];
+  }
+  auto apply = [&](const uint4& raw) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = vec * 8 + 2 * i;
-      const int g = c / cpg;
-      const float mean = stats[g] * inv_n;
-      const float var = fmaxf(stats[G + g] * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
       const float2 f = __bfloat1622float2(h[i]);
-      o[i] = pack_bf16x2((f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c),
-                         (f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1));
+      o[i] = pack_bf16x2(fmaf(f.x, a[2 * i], b[2 * i]), fmaf(f.y, a[2 * i + 1], b[2 * i + 1]));
     }
-    *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int64_t idx = first;
+  for (; idx + 3 * stride < total; idx += 4 * stride) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const uint4*>(x + (idx + u * stride) * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(out + (idx + u * stride) * 8) = apply(r[u]);
   }
+  for (; idx < total; idx += stride) *reinterpret_cast<uint4*>(out + idx * 8) = apply(*reinterpret_cast<const uint4*>(x + idx * 8));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -210,8 +268,14 @@ int cvit_features_to_ndhwc_bf16(const void* features_f16, void* out_bf16, int64_
     return CVIT_ERR_INVALID;
   }
   dim3 grid((unsigned)((DHW + 63) / 64), (unsigned)((C + 63) / 64));
-  features_to_ndhwc_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __half*>(features_f16), static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
+  const bool vec = C % 64 == 0 && DHW % 64 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(features_f16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15u) == 0;
+  if (vec)
+    features_f16_to_ndhwc_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(features_f16), static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
+  else
+    features_to_ndhwc_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(features_f16), static_cast<__nv_bfloat16*>(out_bf16), (int)C, DHW);
   return check_launch("features_to_ndhwc_kernel");
 }
 
@@ -234,8 +298,8 @@ int cvit_groupnorm_ndhwc_bf16(const void* x, void* out, const float* gamma, cons
   }
   const int cpg = (int)(C / G);
   const int nvec = (int)(C / 8);
-  if (!(cpg == 4 || (cpg % 8) == 0) || nvec > 256) {
-    set_error("groupnorm: C=%lld G=%lld unsupported (channels per group must be 4 or a multiple of 8; C <= 2048)",
+  if (!(cpg == 4 || (cpg % 8) == 0) || nvec > 256 || (256 % nvec) != 0) {
+    set_error("groupnorm: C=%lld G=%lld unsupported (channels per group must be 4 or a multiple of 8; C / 8 a divisor of 256)",
               (long long)C, (long long)G);
     return CVIT_ERR_UNSUPPORTED;
   }

@@ -194,19 +194,21 @@ def test_final_norm_writeout(cuda_lib, C, Np):
 
 
 # ------------------------------------------------------------------------------------------------- head ops
-def test_features_to_ndhwc(cuda_lib):
+@pytest.mark.parametrize("C,D,h,w", [(100, 3, 5, 7), (384, 4, 8, 8), (1536, 2, 16, 16), (128, 1, 8, 9)])
+def test_features_to_ndhwc(cuda_lib, C, D, h, w):
+    """(C, DHW) fp16 -> (DHW, C) bf16: the scalar tile kernel (ragged shapes) and the 16-byte vectorised one
+    (C and DHW multiples of 64) must both be the exact cast + transpose."""
     from cryovit_b200 import ops
-    C, D, h, w = 100, 3, 5, 7
     f = _rand(C, D, h, w, seed=1).half()
     out = torch.empty(D, h, w, C, device=DEV, dtype=torch.bfloat16)
     ops.features_to_ndhwc(f, out)
     assert torch.equal(out, f.permute(1, 2, 3, 0).bfloat16())
 
 
-@pytest.mark.parametrize("C,G", [(1024, 128), (128, 16), (32, 8)])
-def test_groupnorm(cuda_lib, C, G):
+@pytest.mark.parametrize("C,G,D,H,W", [(1024, 128, 3, 8, 16), (128, 16, 3, 8, 16), (32, 8, 3, 8, 16), (32, 8, 5, 96, 112),
+                                       (1024, 128, 9, 16, 16)])
+def test_groupnorm(cuda_lib, C, G, D, H, W):
     from cryovit_b200 import ops
-    D, H, W = 3, 8, 16
     x = (_rand(D, H, W, C, seed=1) * 1.5 + 0.3).bfloat16()
     g, b = _rand(C, seed=2), _rand(C, seed=3)
     out = torch.empty_like(x)
