@@ -415,11 +415,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // column n = (i*2 + j) * c3 + co ; voxel grow = (d*H + h)*W + w -> out[d, 2h+i, 2w+j, co]
           const int ij = ncol / args.c3, co = ncol - ij * args.c3;
           const int si = ij >> 1, sj = ij & 1;
+          // rows of a chunk are 4 voxels apart (plain-rows GEMM): one division per chunk, then (w, dh) are stepped
+          int w = 0, dh = 0;
+          {
+            const int g0 = t.m0 + (SUB == 1 ? 0 : sub * GEMM_BM) + q * 32 + rsub;
+            dh = g0 / args.W;  // dh = d*H + h
+            w = g0 - dh * args.W;
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int grow = grow_it[it];
+            if (it > 0) {
+              w += 4;
+              while (w >= args.W) { w -= args.W; ++dh; }
+            }
             if (grow < 0) continue;
-            const int w = grow % args.W, dh = grow / args.W;  // dh = d*H + h
             const size_t orow = ((size_t)(2 * dh + si) * (2 * args.W)) + 2 * w + sj;
             float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
             if (args.act) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
