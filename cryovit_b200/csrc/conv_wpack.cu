@@ -28,12 +28,21 @@
 // Staging: loader warps copy each input voxel (16 B) of a plane from global memory straight to its position(s) with
 // cp.async (zero fill = "same" padding), enumerated so that a warp reads consecutive voxels; the two voxels shared by
 // neighbouring groups are copied twice (10 / 8 of the plane). A plane is one pipeline stage, and a CTA walks ALONG
-// DEPTH through its tiles with a rolling window of three staged planes, so every plane is staged once per CTA, not
-// once per depth tap. The banded weights of all 27 (kd, kh, kw) taps (92 KB / 41 KB) stay resident.
+// DEPTH through its tiles, so every plane is staged once per CTA, not once per depth tap. The banded weights of all
+// 27 (kd, kh, kw) taps (92 KB / 41 KB) stay resident.
 //
-// One CTA per SM, persistent over tiles, 288 threads: warps 0-3 loaders, warps 4-7 epilogue (thread = MMA row: P voxels
-// x Cout values -> bias + GELU -> bf16, or + clip / sigmoid -> fp32; 128 / 64 contiguous bytes per thread), warp 8 MMA
-// issuer (warp-uniform, elect.sync) and TMEM owner. Accumulators double-buffered in TMEM.
+// INPUT-STATIONARY along depth. A staged input plane p feeds three outputs: depth p+1 through the kd = 0 weights, p
+// through kd = 1 and p-1 through kd = 2. The banded weights of the three depth taps are stacked along N in that order
+// ([kd=2 | kd=1 | kd=0] blocks of N rows) and the accumulators of consecutive output depths sit in consecutive N-column
+// slots of a ring of 8 in TMEM, so ONE MMA (N_total = 3 N) adds a plane's contribution to all three outputs: every
+// plane is multiplied once instead of three times (15 resp. 27 MMAs per plane-tile plus a few for ring wrap-around and
+// for the first tap, where a fresh accumulator needs its own accumulate = 0 MMA). An output is complete after the
+// plane above it; its slot is handed to the epilogue with tcgen05.commit and comes back on a per-slot barrier.
+//
+// One CTA per SM, persistent over tiles, 416 threads: warps 0-3 loaders, warps 4-11 epilogue (thread = MMA row; the two
+// warps of a TMEM lane quarter split the row's P voxels: bias + GELU -> bf16, 64 contiguous bytes per thread -- the
+// 8 -> 8 layer is bound by exactly this epilogue math; the 8 -> 1 layer's clip / sigmoid -> fp32 needs one warp per
+// quarter only), warp 12 MMA issuer (warp-uniform, elect.sync) and TMEM owner.
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -44,7 +53,7 @@ constexpr int WP_ROWS = WP_TH + 2;                  // staged rows (1-voxel halo
 constexpr int WP_MROWS = WP_ROWS * WP_G;            // staged MMA rows per plane (144)
 constexpr int WP_ATOM = WP_MROWS * 128;             // one SWIZZLE_128B atom: 8 K chunks of every staged row
 constexpr int WP_SLAB = WP_MROWS * 16;              // one un-swizzled slab: one K chunk of every staged row
-constexpr int WP_THREADS = 288;
+constexpr int WP_THREADS = 416;                     // warps 0-3 loaders, 4-11 epilogue, 12 MMA issuer
 constexpr int WP_LOADERS = 128;
 
 template <int P, int COUT>
@@ -55,16 +64,18 @@ struct WpCfg {
   static constexpr int ATOMS = P / 8;              // swizzled atoms; the last two chunks are un-swizzled slabs
   static constexpr int TAIL = ATOMS * WP_ATOM;     // byte offset of the two slabs
   static constexpr int PLANE = (TAIL + 2 * WP_SLAB + 1023) / 1024 * 1024;  // planes stay 1024-aligned (swizzle phase)
-  static constexpr int W_BYTES = 9 * KSTEPS * 2 * N * 16;   // [kd*3+kh][K step][2 chunks][N][16 B]
+  static constexpr int W_BYTES = 9 * KSTEPS * 2 * N * 16;   // [kh][K step][2 chunks][3 blocks: kd = 2, 1, 0][N][16 B]
+  static constexpr int RING = 8;                    // accumulator slots (consecutive output depths) in TMEM
   static constexpr int STAGES_RAW = (232448 - 1024 - 256 - W_BYTES) / PLANE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = STAGES * PLANE + W_BYTES + 256 + 1024;
   static constexpr int PIECES = NS * WP_ROWS * WP_G;  // 16-byte copies per plane
   static constexpr int PER_THREAD = (PIECES + WP_LOADERS - 1) / WP_LOADERS;
-  static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = RING * N <= 32 ? 32 : RING * N <= 64 ? 64 : RING * N <= 128 ? 128 : RING * N <= 256 ? 256 : 512;
+  static_assert(RING * N <= 512, "accumulator ring exceeds TMEM");
   static constexpr int TW = WP_G * P;               // tile width in voxels
   static_assert(P % 8 == 0 && N % 16 == 0 && N <= 128, "whole swizzle atoms; MMA N a multiple of 16");
-  static_assert(STAGES >= 4, "rolling window: three planes held by the MMAs plus at least one being loaded");
+  static_assert(STAGES >= 3, "one plane under the MMAs, one landing, one being issued");
   static_assert(PLANE < 65536, "slab offsets are packed into 16 bits");
 };
 
@@ -101,7 +112,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
   const uint32_t sW = smem_base + STAGES * Cfg::PLANE;
   const uint32_t sBar = (sW + Cfg::W_BYTES + 15u) & ~15u;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES;
-  const uint32_t bar_tfull = sBar + 16 * STAGES, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
+  const uint32_t bar_ofull = sBar + 16 * STAGES, bar_oempty = bar_ofull + 8 * Cfg::RING, tmem_slot = bar_oempty + 8 * Cfg::RING;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,13 +130,13 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
       mbar_init(bar_full + 8 * s, WP_LOADERS / 32);  // one arrival per loader warp
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);
+    for (int i = 0; i < Cfg::RING; ++i) {
+      mbar_init(bar_ofull + 8 * i, 1);    // MMA -> epilogue: the output of this slot is complete
+      mbar_init(bar_oempty + 8 * i, FINAL ? 4 : 8);  // epilogue warps -> MMA: the slot is in registers, may be re-initialised
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 12) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   fence_proxy_async_smem();  // generic-proxy weight stores -> visible to the tensor core (async proxy)
   tcgen05_fence_before();
   __syncthreads();
@@ -133,10 +144,10 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   // Work = (spatial tile "column", depth) pairs, depth fastest; every CTA owns one contiguous range of them, cut into
-  // SEGMENTS at column changes. Inside a segment the CTA walks along depth with a rolling window of staged planes:
-  // output depth d needs planes d-1, d, d+1, of which only d+1 is new -- one plane load (and a third of the L2
-  // traffic) per output tile instead of three. Planes are numbered in load order (n = 0, 1, ...) by every role;
-  // plane n lives in ring slot n % STAGES with barrier parity (n / STAGES) & 1.
+  // SEGMENTS at column changes. Inside a segment the CTA walks along depth: planes d_a-1 .. d_b+1 are staged once each,
+  // in order, and each is consumed once (input-stationary MMAs, see the header). Planes are numbered in load order
+  // (n = 0, 1, ...) by every role; plane n lives in ring slot n % STAGES with barrier parity (n / STAGES) & 1. Outputs
+  // are numbered in processing order too (seq); output seq accumulates in TMEM slot seq % RING.
   const int64_t total = (int64_t)per_plane * args.D;
   const int i_begin = (int)(total * blockIdx.x / gridDim.x), i_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
   auto col_origin = [&](int col, int& h0, int& w0) {
@@ -205,81 +216,97 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * ((n - 1) % STAGES));
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
-    constexpr uint32_t B_MMA = 2 * N * 16;
-    int acc = 0, n_seg = 0, n_wait = 0;  // n_seg: load index of this segment's first plane; n_wait: planes waited for
-    uint32_t acc_ph = 0;
+    constexpr int R = Cfg::RING;
+    constexpr uint32_t idesc1 = umma_idesc_bf16_f32(128, N), idesc2 = umma_idesc_bf16_f32(128, 2 * N),
+                       idesc3 = umma_idesc_bf16_f32(128, 3 * N);
+    constexpr uint32_t B_MMA = 2 * 3 * N * 16, B_LBO = 3 * N * 16;
+    int n = 0, seq_base = 0;  // n: planes consumed (ring slot n % STAGES); seq_base: outputs before this segment
     for (int i = i_begin; i < i_end;) {
       const int col = i / args.D, d_a = i - col * args.D;
       const int d_b = min(args.D - 1, d_a + (i_end - i) - 1);
       const int p_a = max(d_a - 1, 0), p_b = min(d_b + 1, args.D - 1);
-      for (int d = d_a; d <= d_b; ++d) {
-        const int newest = n_seg + min(d + 1, args.D - 1) - p_a;
-        for (; n_wait <= newest; ++n_wait) mbar_wait(bar_full + 8 * (n_wait % STAGES), (n_wait / STAGES) & 1);
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
+      for (int pz = p_a; pz <= p_b; ++pz, ++n) {
+        // wanted outputs of this plane (consecutive depths), their ring slots and whether this is their first plane
+        const int o_lo = max(pz - 1, d_a), o_hi = min(pz + 1, d_b);
+        for (int o = o_lo; o <= o_hi; ++o) {
+          if (pz == max(o - 1, p_a)) {  // fresh accumulator: the epilogue must have drained the slot's previous output
+            const int seq = seq_base + o - d_a;
+            mbar_wait(bar_oempty + 8 * (seq % R), (((seq / R) & 1) ^ 1) & 1);
+          }
+        }
+        mbar_wait(bar_full + 8 * (n % STAGES), (n / STAGES) & 1);
         tcgen05_fence_after();
         if (elect_one_sync()) {
-          const uint32_t d_tmem = tmem_base + acc * N;
-          uint32_t accumulate = 0;
-          for (int kd = 0; kd < 3; ++kd) {
-            const int pz = d + kd - 1;
-            if (pz < 0 || pz >= args.D) continue;  // the whole depth tap is zero padding
-            const uint32_t plane = sIn + ((n_seg + pz - p_a) % STAGES) * Cfg::PLANE;
+          const uint32_t plane = sIn + (n % STAGES) * Cfg::PLANE;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+          for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-              for (int st = 0; st < Cfg::KSTEPS; ++st) {
-                const uint32_t b = sW + ((kd * 3 + kh) * Cfg::KSTEPS + st) * B_MMA;
-                uint64_t adesc;
-                if (st < 4 * Cfg::ATOMS)  // chunks 2 st, 2 st + 1 of atom st / 4: +32 B per K step inside the swizzle span
-                  adesc = umma_smem_desc_kmajor<128>(plane + (st >> 2) * WP_ATOM + kh * WP_G * 128) + 2 * (st & 3);
-                else
-                  adesc = wp_desc_nosw(plane + Cfg::TAIL + kh * WP_G * 16, WP_SLAB, 128);
-                umma_bf16(d_tmem, adesc, wp_desc_nosw(b, N * 16, 128), idesc, accumulate);
-                accumulate = 1;
+            for (int st = 0; st < Cfg::KSTEPS; ++st) {
+              uint64_t adesc;
+              if (st < 4 * Cfg::ATOMS)  // chunks 2 st, 2 st + 1 of atom st / 4: +32 B per K step inside the swizzle span
+                adesc = umma_smem_desc_kmajor<128>(plane + (st >> 2) * WP_ATOM + kh * WP_G * 128) + 2 * (st & 3);
+              else
+                adesc = wp_desc_nosw(plane + Cfg::TAIL + kh * WP_G * 16, WP_SLAB, 128);
+              const uint32_t b0 = sW + (kh * Cfg::KSTEPS + st) * B_MMA;
+              if (kh == 0 && st == 0) {
+                // first tap of the plane: one MMA per output so that fresh accumulators start from zero
+                for (int o = o_lo; o <= o_hi; ++o) {
+                  const int slot = (seq_base + o - d_a) % R, blk = o - (pz - 1);
+                  umma_bf16(tmem_base + slot * N, adesc, wp_desc_nosw(b0 + blk * N * 16, B_LBO, 128), idesc1,
+                            pz == max(o - 1, p_a) ? 0u : 1u);
+                }
+              } else {
+                // one MMA per run of outputs whose slots are consecutive (a second one only where the ring wraps)
+                int o = o_lo;
+                while (o <= o_hi) {
+                  const int slot = (seq_base + o - d_a) % R, blk = o - (pz - 1);
+                  int len = 1;
+                  while (o + len <= o_hi && slot + len < R) ++len;
+                  umma_bf16(tmem_base + slot * N, adesc, wp_desc_nosw(b0 + blk * N * 16, B_LBO, 128),
+                            len == 3 ? idesc3 : len == 2 ? idesc2 : idesc1, 1u);
+                  o += len;
+                }
               }
             }
           }
-          // plane d-1 has served its last output; at the end of the segment so have the planes still held
-          if (d - 1 >= p_a) umma_commit(bar_empty + 8 * ((n_seg + d - 1 - p_a) % STAGES));
-          if (d == d_b)
-            for (int pz = max(d_b, p_a); pz <= p_b; ++pz) umma_commit(bar_empty + 8 * ((n_seg + pz - p_a) % STAGES));
-          umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+          umma_commit(bar_empty + 8 * (n % STAGES));  // the staged plane has served all three of its outputs
+          // the output below this plane is complete; at the end of the segment so is the plane's own depth
+          if (pz - 1 >= d_a) umma_commit(bar_ofull + 8 * ((seq_base + pz - 1 - d_a) % R));
+          if (pz == p_b && pz <= d_b) umma_commit(bar_ofull + 8 * ((seq_base + pz - d_a) % R));
         }
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1u;
       }
-      n_seg += p_b - p_a + 1;
+      seq_base += d_b - d_a + 1;
       i += d_b - d_a + 1;
     }
-  } else {
+  } else if (!(FINAL && warp >= 8)) {
     // ------------------------------------------------------------------ epilogue: thread == MMA row == P voxels
     const int q = warp & 3;  // TMEM lane quarter (hardware rule: warp id % 4)
+    const int half = (warp - 4) >> 2;  // GELU mode: which half of the row's voxels (columns) this warp takes
     const int r = q * 32 + lane;
     const int hl = r / WP_G, g = r - hl * WP_G;
-    int acc = 0;
-    uint32_t acc_ph = 0;
     for (int i = i_begin; i < i_end; ++i) {
       const int col = i / args.D, d = i - col * args.D;
       int h0, w0;
       col_origin(col, h0, w0);
-      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      const int seq = i - i_begin, slot = seq % Cfg::RING;  // outputs take the ring slots in order
+      mbar_wait(bar_ofull + 8 * slot, (seq / Cfg::RING) & 1);
       tcgen05_fence_after();
-      const uint32_t t_acc = tmem_base + acc * N + (static_cast<uint32_t>(q * 32) << 16);
-      uint32_t v[N];
-      if (N == 16) {
+      const uint32_t t_acc = tmem_base + slot * N + (static_cast<uint32_t>(q * 32) << 16);
+      constexpr int NV = FINAL ? N : N / 2;  // columns per epilogue warp
+      uint32_t v[NV];
+      if (FINAL) {
         tmem_ld_32x16(t_acc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
       } else {
 #pragma unroll
-        for (int c = 0; c < N; c += 32) tmem_ld_32x32(t_acc + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+        for (int c = 0; c < NV; c += 32) tmem_ld_32x32(t_acc + half * NV + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
       }
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // the accumulator is in registers
+      if (lane == 0) mbar_arrive(bar_oempty + 8 * slot);  // the accumulator is in registers
       const int h = h0 + hl, w = w0 + P * g;
       if (h < args.H && w < args.W) {  // W is a multiple of P: a group is inside or outside as a whole
         const int64_t vox = ((int64_t)d * args.H + h) * args.W + w;
@@ -305,13 +332,13 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
             }
           }
         } else {
-          // COUT == 8: P voxels x 8 channels, bias + GELU -> bf16, 16 B per voxel, P * 16 contiguous bytes
-          __nv_bfloat16* o = args.out + vox * 8;
+          // COUT == 8: this warp's P / 2 voxels x 8 channels, bias + GELU -> bf16, 16 B per voxel
+          __nv_bfloat16* o = args.out + (vox + half * (P / 2)) * 8;
           float bb[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) bb[c] = __ldg(args.bias + c);
 #pragma unroll
-          for (int j = 0; j < P; ++j) {
+          for (int j = 0; j < P / 2; ++j) {
             uint32_t pk[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -324,14 +351,12 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           }
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1u;
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

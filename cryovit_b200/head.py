@@ -60,18 +60,20 @@ def halo_weight_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
 
 def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
     """Conv3d weight [Cout, 8, 3, 3, 3] -> the banded shared-memory image of csrc/conv_wpack.cu:
-    [kd*3+kh][K step][2 chunks][n = j_out * Cout + co][8 ci], where chunk c of step s is window voxel j_in = 2 s + c
-    (the window of a group of P output voxels starts one voxel to their left) and the entry is w[co, ci, kd, kh, kw] with
-    kw = j_in - j_out when that is a tap (0..2), zero otherwise."""
+    [kh][K step][2 chunks][block: kd = 2, 1, 0][n = j_out * Cout + co][8 ci], where chunk c of step s is window voxel
+    j_in = 2 s + c (the window of a group of P output voxels starts one voxel to their left) and the entry is
+    w[co, ci, kd, kh, kw] with kw = j_in - j_out when that is a tap (0..2), zero otherwise. The three depth taps are
+    stacked along the MMA N dimension in the order of the output depths they feed (p-1, p, p+1 for input plane p)."""
     cout, cin = w.shape[:2]
     assert cin == 8 and (P + 2) % 2 == 0
-    wt = w.float().permute(2, 3, 4, 0, 1).reshape(9, 3, cout, 8)  # [kd*3+kh][kw][co][ci]
-    img = torch.zeros(9, (P + 2) // 2, 2, P, cout, 8, dtype=torch.float32)
+    wt = w.float().permute(2, 3, 4, 0, 1).reshape(3, 3, 3, cout, 8)  # [kd][kh][kw][co][ci]
+    img = torch.zeros(3, (P + 2) // 2, 2, 3, P, cout, 8, dtype=torch.float32)  # [kh][step][chunk][block][j_out][co][ci]
     for j_in in range(P + 2):
         for kw in range(3):
             j_out = j_in - kw
             if 0 <= j_out < P:
-                img[:, j_in // 2, j_in % 2, j_out] = wt[:, kw]
+                for blk in range(3):
+                    img[:, j_in // 2, j_in % 2, blk, j_out] = wt[2 - blk, :, kw]
     return img.reshape(-1)
 
 
