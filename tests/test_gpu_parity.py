@@ -88,21 +88,58 @@ def test_dino_features_mirror_matches_oracle(cuda_lib):
            torch.from_numpy(ref.astype(np.float32)).permute(1, 2, 3, 0), "_dino_features mirror")
 
 
-def test_vitg_one_slice_vs_oracle(cuda_lib):
+@pytest.fixture(scope="module")
+def vitg_sd():
+    from cryovit_b200.vit import CONFIGS, random_state_dict
+
+    return random_state_dict(CONFIGS["dinov2_vitg14_reg"], seed=0)
+
+
+def test_vitg_one_slice_vs_oracle(cuda_lib, vitg_sd):
     """The headline model (ViT-g/14-reg4, 40 blocks, LayerScale 1.0 random init: the worst case for bf16 error
     accumulation) on one 448x448 slice against the fp32 oracle evaluated on the host cores."""
-    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200, random_state_dict
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200
     from oracle import dinov2 as odino
 
     cfg = CONFIGS["dinov2_vitg14_reg"]
-    sd = random_state_dict(cfg, seed=0)
     x = torch.rand(1, 3, 448, 448, generator=torch.Generator().manual_seed(1))
-    model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda()
+    model = DinoVisionTransformerB200(cfg).load_state_dict(vitg_sd).cuda()
     got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
     del model
     torch.cuda.empty_cache()
-    ref = odino.forward_features(sd, x, cfg.num_heads)["x_norm_patchtokens"]
+    ref = odino.forward_features(vitg_sd, x, cfg.num_heads)["x_norm_patchtokens"]
     _check(got, ref, "ViT-g one slice vs oracle")
+
+
+def test_vitg_full_size_tomogram_properties(cuda_lib, vitg_sd):
+    """BASELINE config 2 at its full size (ViT-g/14-reg4, one 128 x 512 x 512 uint8 tomogram, slice batch 128), where the
+    oracle cannot follow, through properties that do not depend on size:
+      * a slice's features do not depend on what else is in its batch: slice batch 128 == slice batch 48 (ragged last
+        batch of 32), bit for bit -- every token's dot products accumulate over K in the same order whatever M is;
+      * slices are independent: permuting the tomogram's slices permutes the features, bit for bit;
+      * one slice of the full-size run, re-computed by the fp32 oracle on the host cores, is within the tolerance."""
+    from cryovit_b200.extract import extract_tomogram
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200
+    from oracle import dinov2 as odino
+    from oracle import preproc as opre
+
+    cfg = CONFIGS["dinov2_vitg14_reg"]
+    model = DinoVisionTransformerB200(cfg).load_state_dict(vitg_sd).cuda()
+    tomo = np.random.default_rng(5).integers(0, 256, size=(128, 512, 512), dtype=np.uint8)
+    full = extract_tomogram(tomo, model, batch_size=128)
+    assert full.shape == (1536, 128, 32, 32) and full.dtype == np.float16 and np.isfinite(full).all()
+    ragged = extract_tomogram(tomo, model, batch_size=48)
+    assert np.array_equal(full, ragged), "features depend on the slice batch size"
+    perm = np.random.default_rng(6).permutation(128)
+    shuffled = extract_tomogram(np.ascontiguousarray(tomo[perm]), model, batch_size=128)
+    assert np.array_equal(shuffled, full[:, perm]), "slices are not independent of their position in the batch"
+    del model
+    torch.cuda.empty_cache()
+    k = 77
+    x = opre.dino_transform(opre.load_tomogram(tomo[k:k + 1]))  # [1, 3, 448, 448] fp32
+    ref = odino.forward_features(vitg_sd, x, cfg.num_heads)["x_norm_patchtokens"][0]  # [1024, 1536]
+    got = torch.from_numpy(full[:, k].astype(np.float32)).reshape(1536, 1024).t()
+    _check(got, ref.half().float(), "full-size run, slice 77 vs oracle")
 
 
 # ------------------------------------------------------------------------------------------------- head
@@ -125,7 +162,7 @@ def _head_case(in_ch, D, h, w, seed, spread_bias=False):
     return logits.cpu(), probs.cpu(), ref_logits
 
 
-@pytest.mark.parametrize("in_ch,D,h,w", [(1536, 40, 4, 8), (384, 8, 7, 7), (1536, 6, 2, 3)])
+@pytest.mark.parametrize("in_ch,D,h,w", [(1536, 40, 4, 8), (384, 8, 7, 7), (1536, 6, 2, 3), (1536, 128, 4, 4)])  # last: full depth
 def test_head_vs_oracle(cuda_lib, in_ch, D, h, w):
     logits, probs, ref = _head_case(in_ch, D, h, w, seed=3, spread_bias=True)
     assert logits.shape == ref.shape == (D, 16 * h, 16 * w)
