@@ -66,15 +66,13 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
     stacked along the MMA N dimension in the order of the output depths they feed (p-1, p, p+1 for input plane p)."""
     cout, cin = w.shape[:2]
     assert cin == 8 and (P + 2) % 2 == 0
-    wt = w.float().permute(2, 3, 4, 0, 1).reshape(3, 3, 3, cout, 8)  # [kd][kh][kw][co][ci]
-    img = torch.zeros(3, (P + 2) // 2, 2, 3, P, cout, 8, dtype=torch.float32)  # [kh][step][chunk][block][j_out][co][ci]
-    for j_in in range(P + 2):
-        for kw in range(3):
-            j_out = j_in - kw
-            if 0 <= j_out < P:
-                for blk in range(3):
-                    img[:, j_in // 2, j_in % 2, blk, j_out] = wt[2 - blk, :, kw]
-    return img.reshape(-1)
+    wt = w.float().permute(2, 3, 4, 0, 1)  # [kd][kh][kw][co][ci], on w's device
+    band = torch.zeros(P + 2, P, 3, device=w.device)  # band[j_in, j_out, kw] = 1 where kw == j_in - j_out
+    for kw in range(3):
+        band[torch.arange(P) + kw, torch.arange(P), kw] = 1.0
+    # [kh][j_in][kd][j_out][co][ci] -> blocks in the order kd = 2, 1, 0 -> j_in split into (K step, chunk)
+    img = torch.einsum("jok,dhkcx->hjdocx", band, wt).flip(2)
+    return img.reshape(3, (P + 2) // 2, 2, 3, P, cout, 8).reshape(-1)
 
 
 class CryoVITHeadB200:

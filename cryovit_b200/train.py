@@ -23,7 +23,7 @@ import torch
 from . import ops
 from . import train_ops as T
 from ._lib import CryovitB200Error
-from .head import BLOCKS, state_dict_keys
+from .head import BLOCKS, state_dict_keys, wpack_weight_image
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -81,6 +81,11 @@ class _Conv:
         return _taps(w, cp).to(BF16).contiguous(), cp, "taps"
 
     def run(self, x, w, bias, out, cin, cout, dil):
+        if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 16 == 0:
+            # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): W-packed kernel
+            b = bias.repeat(8).contiguous() if bias is not None else torch.zeros(64, device=x.device, dtype=F32)
+            ops.conv3d_wpack8_gelu(x, wpack_weight_image(w, 8).to(BF16), b, out, act=False)
+            return
         op, cp, kind = self._pack(w, cin, cout)
         b = torch.zeros(cp, device=x.device, dtype=F32)
         if bias is not None:
@@ -214,8 +219,12 @@ class CryoVITHeadTrainerB200:
         co.forward(cur, p["output_layer.0.weight"], p["output_layer.0.bias"], z1)
         T.gelu_fwd(z1, a1)
         logits, probs = self._buf("logits", (D, H, W), F32), self._buf("probs", (D, H, W), F32)
-        ops.head_out_conv(a1, p["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8).contiguous(),
-                          p["output_layer.2.bias"], logits, probs)
+        if W % 16 == 0:
+            ops.conv3d_wpack8_final(a1, wpack_weight_image(p["output_layer.2.weight"], 16).to(BF16),
+                                    p["output_layer.2.bias"].repeat(16).contiguous(), logits, probs)
+        else:
+            ops.head_out_conv(a1, p["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8).contiguous(),
+                              p["output_layer.2.bias"], logits, probs)
         lab = self._buf("labels", (D, H, W), F32)
         lab.copy_(labels.to(dev))
         stats8 = ops.seg_stats(probs, lab)

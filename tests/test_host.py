@@ -199,3 +199,18 @@ def test_two_rank_gloo_sharded_extraction_and_metric_reduce(tmp_path):
         back = hdf.read_tomogram(tmp_path / "tomograms" / "Q18" / n)
         assert sorted(back) == ["data", "dino_features", "labels/mito"]
         assert back["dino_features"].shape == (4, 3 + i, 2, 3) and back["data"].shape == (3 + i, 32, 48)
+
+
+def test_wpack_weight_image_is_the_banded_matrix():
+    """csrc/conv_wpack.cu's B operand: entry [kh][step][chunk][block][j_out][co][ci] is w[co, ci, kd = 2 - block, kh,
+    kw = j_in - j_out] where j_in = 2 step + chunk, zero outside the three taps."""
+    from cryovit_b200.head import wpack_weight_image
+
+    for cout, P in ((8, 8), (1, 16)):
+        w = torch.randn(cout, 8, 3, 3, 3, generator=torch.Generator().manual_seed(cout))
+        img = wpack_weight_image(w, P).reshape(3, (P + 2) // 2, 2, 3, P, cout, 8)
+        for kh, st, c, blk, jo in ((0, 0, 0, 0, 0), (1, 2, 1, 2, 3), (2, (P + 1) // 2, (P + 1) % 2, 1, P - 1), (1, 0, 1, 1, 5)):
+            kw = 2 * st + c - jo
+            want = w[:, :, 2 - blk, kh, kw] if 0 <= kw <= 2 else torch.zeros(cout, 8)
+            assert torch.equal(img[kh, st, c, blk, jo], want), (cout, P, kh, st, c, blk, jo)
+        assert int((img != 0).sum()) == 27 * cout * 8 * P  # every tap appears once per packed output voxel
