@@ -254,6 +254,55 @@ __global__ void __launch_bounds__(256) ndhwc_to_cfirst_padded_kernel(const __nv_
   }
 }
 
+// The same for C % 64 == 0 with 16-byte accesses on both sides: a CTA moves 64 padded positions x 64 channels; a thread
+// loads 8 consecutive channels of one position (16 B; a warp reads four 128-byte runs), parks them in shared memory,
+// then gathers 8 consecutive positions of one channel (eight conflict-free 2-byte reads: the 32 lanes of a warp take 32
+// consecutive channels) and writes them as one 16-byte store. The scalar kernel above did three 64-bit divisions and
+// two 2-byte memory operations per element: 12.5 ms of a 52 ms training step for 10 GB of traffic.
+constexpr int CF_PITCH = 72;  // halves per shared-memory row (144 B: 16-byte aligned rows, skewed banks)
+__global__ void __launch_bounds__(256) ndhwc_to_cfirst_padded_vec_kernel(const __nv_bfloat16* __restrict__ src,
+                                                                          __nv_bfloat16* __restrict__ dst, int D, int H, int W,
+                                                                          int C, int pd, int ph, int pw, int Wp, int wshift,
+                                                                          int64_t pitch) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * CF_PITCH];
+  const int Hp = H + 2 * ph, Dp = D + 2 * pd;
+  const int64_t P = (int64_t)Dp * Hp * Wp;
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int q = threadIdx.x + k * 256;  // 512 loads: position q / 8, 8-channel chunk q % 8
+    const int pl = q >> 3, ch = q & 7;
+    const int64_t p = p0 + pl;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p < P) {
+      const int64_t row = p / Wp;
+      const int w = (int)(p - row * Wp) - pw + wshift;
+      const int dpl = (int)(row / Hp);
+      const int h = (int)(row - (int64_t)dpl * Hp) - ph, d = dpl - pd;
+      if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D)
+        v = __ldg(reinterpret_cast<const uint4*>(src + (((int64_t)d * H + h) * W + w) * C + c0 + ch * 8));
+    }
+    *reinterpret_cast<uint4*>(&tile[pl * CF_PITCH + ch * 8]) = v;
+  }
+  __syncthreads();
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int q = threadIdx.x + k * 256;  // 512 stores: channel q % 64 (fastest: conflict-free reads), position group q / 64
+    const int c = q & 63, pg = q >> 6;
+    const int64_t p = p0 + pg * 8;
+    if (p >= pitch) continue;  // pitch is a multiple of 8: a group is inside or outside as a whole
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = t16[(pg * 8 + 2 * j) * CF_PITCH + c], hi = t16[(pg * 8 + 2 * j + 1) * CF_PITCH + c];
+      o[j] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + (int64_t)(c0 + c) * pitch + p) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Narrow volumes (C <= 32, the layers with tens of millions of voxels): one thread turns 8 consecutive padded positions
 // of one 8-channel chunk into 8 x 16-byte stores (one per channel row, 8 positions each), so a warp writes 512
 // contiguous bytes per row; with NSHIFT = 3 the column-shifted copies -1, 0, +1 come out of the same loads.
@@ -341,6 +390,13 @@ extern "C" int cvit_ndhwc_to_cfirst_padded(const void* src, void* dst, int64_t D
         static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), nullptr, nullptr, (int)D, (int)H, (int)W, (int)C,
         (int)pd, (int)ph, (int)pw, (int)Wp, (int)wshift, pitch);
     return check_launch("ndhwc_to_cfirst_padded_narrow_kernel<1>");
+  }
+  if (C % 64 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+    dim3 gridv((unsigned)((pitch + 63) / 64), (unsigned)(C / 64));
+    ndhwc_to_cfirst_padded_vec_kernel<<<gridv, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), (int)D, (int)H, (int)W, (int)C, (int)pd,
+        (int)ph, (int)pw, (int)Wp, (int)wshift, pitch);
+    return check_launch("ndhwc_to_cfirst_padded_vec_kernel");
   }
   dim3 grid((unsigned)((pitch + 31) / 32), (unsigned)((C + 31) / 32));
   ndhwc_to_cfirst_padded_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
