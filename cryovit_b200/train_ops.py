@@ -95,11 +95,11 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
     9-tap split-K GEMMs. ``pool`` (a dict) recycles the operand buffers between calls."""
     D, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    if Cin == 8 and Cout == 8:  # full-resolution 8-channel layers: warp-MMA reduction over the channels-last volumes
-        dw8 = torch.zeros(27, 8, 8, device=x.device, dtype=F32)
-        _lib.call("cvit_wgrad_narrow8_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dw8, F32, "dw"), D, H, W, dil,
-                  _stream())
-        return dw8
+    if (Cin, Cout) in ((8, 8), (16, 16), (32, 16), (32, 32)):  # narrow layers: warp-MMA reduction over the channels-last volumes
+        dwn = torch.zeros(27, Cout, Cin, device=x.device, dtype=F32)
+        _lib.call("cvit_wgrad_narrow_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
+                  dil, _stream())
+        return dwn
     Dp, Hp, Wp, pitch = padded_geometry(D, H, W, dil, 1, 1)
     dev = x.device
     pool = pool if pool is not None else {}

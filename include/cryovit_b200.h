@@ -252,11 +252,12 @@ int cvit_ndhwc_to_cfirst_padded_x3(const void* src, void* dst_m1, void* dst_0, v
 int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, const int* koffs, int64_t M, int64_t N, int64_t K,
                       int64_t pitch_a, int64_t pitch_b, int64_t ntaps, void* stream);
 
-/* The same weight gradient for the two 8-channel full-resolution convolutions (output_layer.0 / .2), straight from the
- * channels-last volumes with warp-level MMAs (csrc/wgrad_narrow.cu; no operand copies): dw (fp32 [27][8][8], tap =
- * (kd*3+kh)*3+kw, then [co][ci]) += sum_v dz[v, co] * x[v + off(tap), ci]. x, dz: bf16 [D,H,W,8]. */
-int cvit_wgrad_narrow8_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil,
-                             void* stream);
+/* The same weight gradient for the narrow convolutions (SynthesisBlocks 3-4, output_layer; (Cin, Cout) in {(8,8), (16,16),
+ * (32,16), (32,32)}), straight from the channels-last volumes with warp-level MMAs (csrc/wgrad_narrow.cu; no operand
+ * copies): dw (fp32 [27][Cout][Cin], tap = (kd*3+kh)*3+kw) += sum_v dz[v, co] * x[v + off(tap), ci]; x bf16 [D,H,W,Cin],
+ * dz bf16 [D,H,W,Cout]. */
+int cvit_wgrad_narrow_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                            int64_t Cout, int64_t dil, void* stream);
 
 /* AdamW step over a flat fp32 parameter vector, torch.optim.AdamW semantics (models/base_model.py:58-63):
  * decoupled weight decay, bias-corrected moments; g is multiplied by grad_scale first. step counts from 1. */
