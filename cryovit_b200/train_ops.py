@@ -100,7 +100,11 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
         _lib.call("cvit_wgrad_narrow_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
                   dil, _stream())
         return dwn
-    Dp, Hp, Wp, pitch = padded_geometry(D, H, W, dil, 1, 1)
+    # No depth padding: a depth tap that leaves the volume shifts the K index outside [0, K), where the GEMM's TMA loads
+    # read zeros anyway; only the in-plane wrap-around needs the one-voxel zero border (of dz). With the head's
+    # dilations (up to 32 planes of 128) padded planes would be a third of K.
+    pd = 0
+    Dp, Hp, Wp, pitch = padded_geometry(D, H, W, pd, 1, 1)
     dev = x.device
     pool = pool if pool is not None else {}
 
@@ -112,7 +116,7 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
         return b
 
     dzt = buf("dzt", Cout * pitch)[:Cout * pitch].view(Cout, pitch)
-    to_cfirst_padded(dz, dzt, dil, 1, 1, 0)
+    to_cfirst_padded(dz, dzt, pd, 1, 1, 0)
     key = (dil, Hp, Wp, str(dev))
     if key not in _KOFFS:
         _KOFFS[key] = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
@@ -120,13 +124,13 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
     dw = torch.zeros(3, 9, Cout, Cin, device=dev, dtype=F32)
     if Cin in (8, 16, 32):  # all three shifted copies from one pass over x
         xts = [buf(f"xt{kw}", Cin * pitch)[:Cin * pitch].view(Cin, pitch) for kw in range(3)]
-        to_cfirst_padded_x3(x, xts, dil, 1, 1)
+        to_cfirst_padded_x3(x, xts, pd, 1, 1)
         for kw in range(3):
             wgrad_splitk(dzt, xts[kw], dw[kw], koffs, pitch)
     else:
         xt = buf("xt0", Cin * pitch)[:Cin * pitch].view(Cin, pitch)
         for kw in range(3):
-            to_cfirst_padded(x, xt, dil, 1, 1, kw - 1)
+            to_cfirst_padded(x, xt, pd, 1, 1, kw - 1)
             wgrad_splitk(dzt, xt, dw[kw], koffs, pitch)
     return dw.permute(1, 0, 2, 3).reshape(27, Cout, Cin)
 
