@@ -58,6 +58,9 @@ def halo_weight_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
     return img.reshape(-1)
 
 
+_BANDS: dict = {}
+
+
 def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
     """Conv3d weight [Cout, 8, 3, 3, 3] -> the banded shared-memory image of csrc/conv_wpack.cu:
     [kh][K step][2 chunks][block: kd = 2, 1, 0][n = j_out * Cout + co][8 ci], where chunk c of step s is window voxel
@@ -67,9 +70,13 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
     cout, cin = w.shape[:2]
     assert cin == 8 and (P + 2) % 2 == 0
     wt = w.float().permute(2, 3, 4, 0, 1)  # [kd][kh][kw][co][ci], on w's device
-    band = torch.zeros(P + 2, P, 3, device=w.device)  # band[j_in, j_out, kw] = 1 where kw == j_in - j_out
-    for kw in range(3):
-        band[torch.arange(P) + kw, torch.arange(P), kw] = 1.0
+    key = (P, str(w.device))
+    band = _BANDS.get(key)
+    if band is None:  # band[j_in, j_out, kw] = 1 where kw == j_in - j_out (built once per device: no host copies later)
+        band = torch.zeros(P + 2, P, 3)
+        for kw in range(3):
+            band[torch.arange(P) + kw, torch.arange(P), kw] = 1.0
+        band = _BANDS[key] = band.to(w.device)
     # [kh][j_in][kd][j_out][co][ci] -> blocks in the order kd = 2, 1, 0 -> j_in split into (K step, chunk)
     img = torch.einsum("jok,dhkcx->hjdocx", band, wt).flip(2)
     return img.reshape(3, (P + 2) // 2, 2, 3, P, cout, 8).reshape(-1)

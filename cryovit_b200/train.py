@@ -134,6 +134,8 @@ class CryoVITHeadTrainerB200:
         self.step_count = 0
         self.launches = 0
         self._bufs: dict[str, torch.Tensor] = {}
+        self._graphs: dict = {}
+        self._graph_broken = False
 
     # ------------------------------------------------------------------ helpers
     def state_dict(self) -> dict[str, torch.Tensor]:
@@ -314,6 +316,53 @@ class CryoVITHeadTrainerB200:
         import torch.distributed as dist
 
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        loss = self.forward_backward(features, labels, 1.0 / world)
+        loss = self._forward_backward_graphed(features, labels, 1.0 / world)
         self.optimizer_step()
         return loss
+
+    # ----------------------------------------------------------------------------- CUDA graph of forward + backward
+    def _forward_backward_graphed(self, features: torch.Tensor, labels: torch.Tensor, grad_scale: float) -> torch.Tensor:
+        """forward_backward is ~200 kernels of ours plus the small torch kernels that re-pack the updated weights:
+        launch-bound for a fifth of the step. The first two steps of a given crop shape run eagerly (first-use
+        allocations, attribute settings, lookup tables); the third is captured into a CUDA graph over static input
+        buffers and every later step replays it. The all-reduce and AdamW (whose bias correction takes the step number
+        by value) stay outside the graph. CVIT_TRAIN_GRAPH=0 or a failed capture falls back to eager launches."""
+        import os
+
+        if os.environ.get("CVIT_TRAIN_GRAPH", "1") == "0" or self._graph_broken:
+            return self.forward_backward(features, labels, grad_scale)
+        key = (tuple(features.shape), features.dtype, tuple(labels.shape), labels.dtype, float(grad_scale))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 2:  # every graph keeps its own pool of temporaries: only the two commonest crop shapes
+                return self.forward_backward(features, labels, grad_scale)
+            ent = self._graphs[key] = {"seen": 0}
+        if "graph" not in ent:
+            ent["seen"] += 1
+            if ent["seen"] <= 2:
+                return self.forward_backward(features, labels, grad_scale)
+            try:
+                ent["f"] = torch.empty(features.shape, device=self.device, dtype=features.dtype)
+                ent["l"] = torch.empty(labels.shape, device=self.device, dtype=labels.dtype)
+                ent["f"].copy_(features, non_blocking=True)
+                ent["l"].copy_(labels, non_blocking=True)
+                torch.cuda.synchronize()
+                l0 = self.launches
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ent["loss"] = self.forward_backward(ent["f"], ent["l"], grad_scale)
+                ent["launches"] = self.launches - l0
+                self.launches = l0
+                ent["graph"] = graph
+            except Exception as e:  # noqa: BLE001  (capture is an optimisation: never fatal)
+                import logging
+
+                logging.warning("CUDA-graph capture of the training step failed (%s: %s); running eagerly", type(e).__name__, e)
+                self._graph_broken = True
+                torch.cuda.synchronize()
+                return self.forward_backward(features, labels, grad_scale)
+        ent["f"].copy_(features, non_blocking=True)
+        ent["l"].copy_(labels, non_blocking=True)
+        ent["graph"].replay()
+        self.launches += ent["launches"]
+        return ent["loss"]

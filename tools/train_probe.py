@@ -1,4 +1,5 @@
 """Timing of one CryoVIT head training step at BASELINE config 5's crop: features (1536, 128, 32, 32), labels (128, 512, 512)."""
+import os
 import sys
 from pathlib import Path
 
@@ -36,6 +37,7 @@ for mod, names in ((ops, ["features_to_ndhwc", "linear_bias", "groupnorm_ndhwc",
             seq.append((tag, s, e))
             return r
         setattr(mod, n, wrapped)
+os.environ["CVIT_TRAIN_GRAPH"] = "0"  # per-kernel events need eager launches
 for _ in range(2):
     loss = tr.train_step(feats, labels)
 torch.cuda.synchronize()
@@ -63,4 +65,15 @@ for _ in range(3):
     e.record()
     torch.cuda.synchronize()
     ts.append(s.elapsed_time(e))
-print(f"train step {sorted(ts)[1]:.2f} ms -> {D * 512 * 512 / sorted(ts)[1] / 1e6:.3f} Gvoxel/s")
+print(f"train step, eager launches {sorted(ts)[1]:.2f} ms -> {D * 512 * 512 / sorted(ts)[1] / 1e6:.3f} Gvoxel/s")
+os.environ["CVIT_TRAIN_GRAPH"] = "1"  # forward + backward captured into a CUDA graph on the third step of a shape
+ts = []
+for _ in range(7):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    loss = tr.train_step(feats, labels)
+    e.record()
+    torch.cuda.synchronize()
+    ts.append(s.elapsed_time(e))
+print(f"train step, CUDA graph {sorted(ts[3:])[2]:.2f} ms -> {D * 512 * 512 / sorted(ts[3:])[2] / 1e6:.3f} Gvoxel/s (loss {float(loss):.4f}, "
+      f"graph active: {any('graph' in v for v in tr._graphs.values())})")
