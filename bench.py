@@ -164,7 +164,7 @@ def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
     labels[::5] = -1  # 20 % of the slices unlabelled
     labels = labels.cuda()
     tr = CryoVITHeadTrainerB200(1536)
-    for _ in range(2):
+    for _ in range(4):  # two eager steps, the step that captures forward + backward into a CUDA graph, one replay
         loss = tr.train_step(feats, labels)
     torch.cuda.synchronize()
     if world > 1:
