@@ -66,41 +66,42 @@ def allreduce_gradient_bucket(flat_g: torch.Tensor) -> None:
 
 
 class _Conv:
-    """A 3x3x3 depth-dilated convolution in both directions. Narrow inputs (8/16/32 channels) use the halo kernel."""
+    """A 3x3x3 depth-dilated convolution in both directions. Narrow inputs (8/16/32 channels) use the halo kernel, the
+    8 -> 8 full-resolution case the W-packed kernel. The bf16 operand images come from the trainer's per-step gather
+    (``CryoVITHeadTrainerB200._pk``): ``key`` names the parameter, ``pre`` an optional re-arrangement applied first."""
 
-    def __init__(self, cin: int, cout: int, dil: int):
-        self.cin, self.cout, self.dil = cin, cout, dil
+    def __init__(self, trainer, key: str, cin: int, cout: int, dil: int, pre=None):
+        self.tr, self.key, self.cin, self.cout, self.dil, self.pre = trainer, key, cin, cout, dil, pre
 
-    @staticmethod
-    def _pack(w: torch.Tensor, cin: int, cout: int):
-        """(operand, bias-length, kind) for a convolution cin -> cout with weight w [cout, cin, 3,3,3] (fp32, device)."""
-        if cin in (8, 16, 32):
-            cp = 32 if cout > 16 else 16
-            return _halo_image(w, cp).to(BF16), cp, "halo"
-        cp = max(32, cout)
-        return _taps(w, cp).to(BF16).contiguous(), cp, "taps"
-
-    def run(self, x, w, bias, out, cin, cout, dil):
+    def run(self, tag, x, wfn, bias, out, cin, cout, dil):
+        """wfn: fp32 parameter -> the [cout, cin, 3,3,3] weight of THIS convolution (identity, or flip + transpose)."""
         if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 16 == 0:
             # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): W-packed kernel
             b = bias.repeat(8).contiguous() if bias is not None else torch.zeros(64, device=x.device, dtype=F32)
-            ops.conv3d_wpack8_gelu(x, wpack_weight_image(w, 8).to(BF16), b, out, act=False)
+            op = self.tr._pk(f"{self.key}/{tag}/wpack", self.key, lambda w: wpack_weight_image(wfn(w), 8))
+            ops.conv3d_wpack8_gelu(x, op, b, out, act=False)
             return
-        op, cp, kind = self._pack(w, cin, cout)
+        halo = cin in (8, 16, 32)
+        cp = (32 if cout > 16 else 16) if halo else max(32, cout)
         b = torch.zeros(cp, device=x.device, dtype=F32)
         if bias is not None:
             b[:cout] = bias
-        if kind == "halo":
+        if halo:
+            op = self.tr._pk(f"{self.key}/{tag}/halo", self.key, lambda w: _halo_image(wfn(w), cp))
             T.conv3d_halo_act(x, op, b, out, dil, cp, False)
         else:
+            op = self.tr._pk(f"{self.key}/{tag}/taps", self.key, lambda w: _taps(wfn(w), cp))
             T.conv3d_dilated_act(x, op, b, out, dil, False)
 
-    def forward(self, x, w, bias, z):
-        self.run(x, w, bias, z, self.cin, self.cout, self.dil)
+    def _w(self, w):
+        return self.pre(w) if self.pre is not None else w
 
-    def input_gradient(self, dz, w, dx):
-        wg = w.flip(2, 3, 4).transpose(0, 1).contiguous()  # [cin, cout, 3,3,3]: the gradient convolution's weight
-        self.run(dz, wg, None, dx, self.cout, self.cin, self.dil)
+    def forward(self, x, bias, z):
+        self.run("f", x, self._w, bias, z, self.cin, self.cout, self.dil)
+
+    def input_gradient(self, dz, dx):
+        # [cin, cout, 3,3,3]: the gradient convolution's weight
+        self.run("g", dz, lambda w: self._w(w).flip(2, 3, 4).transpose(0, 1).contiguous(), None, dx, self.cout, self.cin, self.dil)
 
 
 class CryoVITHeadTrainerB200:
@@ -119,23 +120,63 @@ class CryoVITHeadTrainerB200:
         self.keys = state_dict_keys()
         sizes = [state_dict[k].numel() for k in self.keys]
         n = sum(sizes)
-        self.flat_p = torch.empty(n, device=self.device, dtype=F32)  # fp32 master weights, ONE bucket
+        self._flat_store = torch.zeros(n + 1, device=self.device, dtype=F32)  # [n] is the zero every padded operand entry reads
+        self.flat_p = self._flat_store[:n]  # fp32 master weights, ONE bucket
         self.flat_g = torch.zeros(n, device=self.device, dtype=F32)  # gradients, all-reduced as one flat bucket
         self.flat_m = torch.zeros(n, device=self.device, dtype=F32)
         self.flat_v = torch.zeros(n, device=self.device, dtype=F32)
-        self.p, self.g = {}, {}
+        self.p, self.g, self._offsets, self._nparams = {}, {}, {}, n
+        self._pk_tables: dict = {}  # operand name -> (gather table into _flat_store, shape)
+        self._pk_views: dict = {}   # operand name -> this step's bf16 operand
+        self._pk_cat = None
         off = 0
         for k, sz in zip(self.keys, sizes):
             shape = state_dict[k].shape
             self.p[k] = self.flat_p[off:off + sz].view(shape)
             self.g[k] = self.flat_g[off:off + sz].view(shape)
             self.p[k].copy_(state_dict[k].to(self.device, F32))
+            self._offsets[k] = off
             off += sz
         self.step_count = 0
         self.launches = 0
         self._bufs: dict[str, torch.Tensor] = {}
         self._graphs: dict = {}
         self._graph_broken = False
+
+    # ------------------------------------------------------------------ bf16 operand images of the updated weights
+    def _pk(self, name: str, key: str, fn) -> torch.Tensor:
+        """The bf16 operand ``fn(p[key])`` where fn is a pure re-arrangement with zero padding (tap-major layout,
+        shared-memory images, flips / transposes for input gradients ...). The weights change every step and the
+        re-arrangements are dozens of small torch kernels per layer, so on first use fn runs on the parameter's GLOBAL
+        INDICES (exact in fp32 up to 2^24) and the result is kept as a gather table; from the next step on ONE
+        ``index_select`` over the flat bucket plus one cast produce every operand of the step (``_pk_refresh``)."""
+        v = self._pk_views.get(name)
+        if v is not None:
+            return v
+        w = self.p[key]
+        if name not in self._pk_tables:
+            idx = (torch.arange(w.numel(), device=self.device, dtype=F32) + float(self._offsets[key] + 1)).view(w.shape)
+            t = fn(idx)
+            table = t.round().long().flatten() - 1
+            table[table < 0] = self._nparams  # padding -> the zero slot
+            self._pk_tables[name] = (table, tuple(t.shape))
+            self._pk_cat = None
+        return fn(w).to(BF16).contiguous()
+
+    def _pk_refresh(self) -> None:
+        """One gather + one cast for all operand images whose tables exist (called at the start of a step)."""
+        self._pk_views = {}
+        if not self._pk_tables:
+            return
+        if self._pk_cat is None:
+            self._pk_names = list(self._pk_tables)
+            self._pk_cat = torch.cat([self._pk_tables[k][0] for k in self._pk_names])
+        packed = self._flat_store.index_select(0, self._pk_cat).to(BF16)
+        off = 0
+        for k in self._pk_names:
+            table, shape = self._pk_tables[k]
+            self._pk_views[k] = packed[off:off + table.numel()].view(shape)
+            off += table.numel()
 
     # ------------------------------------------------------------------ helpers
     def state_dict(self) -> dict[str, torch.Tensor]:
@@ -186,11 +227,13 @@ class CryoVITHeadTrainerB200:
         if C != self.in_channels or tuple(labels.shape) != (D, 16 * h, 16 * w):
             raise CryovitB200Error(f"features {tuple(features.shape)} / labels {tuple(labels.shape)} do not match")
         vox = D * h * w
+        self._pk_refresh()
         # ---------------- forward, keeping what the backward needs
         x0 = self._buf("x0", (D, h, w, C))
         ops.features_to_ndhwc(features.to(dev).contiguous(), x0)
         z_proj, a_proj = self._buf("z_proj", (vox, 1024)), self._buf("a_proj", (D, h, w, 1024))
-        ops.linear_bias(x0.view(vox, C), p["layers.0.weight"].reshape(1024, C).to(BF16), p["layers.0.bias"], z_proj, gelu=False)
+        ops.linear_bias(x0.view(vox, C), self._pk("proj/f", "layers.0.weight", lambda w_: w_.reshape(1024, C)), p["layers.0.bias"],
+                        z_proj, gelu=False)
         T.gelu_fwd(z_proj, a_proj.view(vox, 1024))
         self.launches += 3
         saved = []
@@ -201,28 +244,29 @@ class CryoVITHeadTrainerB200:
             n_out = self._buf(f"gn{bi}", (D, H, W, c1))
             stats = self._buf(f"gn{bi}_stats", (2 * G,), F32)
             ops.groupnorm_ndhwc(cur, n_out, p[pre + "0.weight"], p[pre + "0.bias"], stats, G, 1e-3)
-            ca, cb = _Conv(c1, c2, d1), _Conv(c2, c2, d2)
+            ca, cb = _Conv(self, pre + "1.weight", c1, c2, d1), _Conv(self, pre + "3.weight", c2, c2, d2)
             za, aa = self._buf(f"za{bi}", (D, H, W, c2)), self._buf(f"aa{bi}", (D, H, W, c2))
-            ca.forward(n_out, p[pre + "1.weight"], p[pre + "1.bias"], za)
+            ca.forward(n_out, p[pre + "1.bias"], za)
             T.gelu_fwd(za, aa)
             zb, ab = self._buf(f"zb{bi}", (D, H, W, c2)), self._buf(f"ab{bi}", (D, H, W, c2))
-            cb.forward(aa, p[pre + "3.weight"], p[pre + "3.bias"], zb)
+            cb.forward(aa, p[pre + "3.bias"], zb)
             T.gelu_fwd(zb, ab)
             zt, at = self._buf(f"zt{bi}", (D, 2 * H, 2 * W, c3)), self._buf(f"at{bi}", (D, 2 * H, 2 * W, c3))
-            wT = p[pre + "5.weight"]  # [c2, c3, 1, 2, 2]
-            T.convT_act(ab, wT[:, :, 0].permute(2, 3, 1, 0).reshape(4 * c3, c2).to(BF16).contiguous(),
+            # ConvTranspose weight [c2, c3, 1, 2, 2] -> rows (i*2+j)*c3 + co of the sub-pixel GEMM
+            T.convT_act(ab, self._pk(pre + "5/f", pre + "5.weight",
+                                     lambda wT, c2_=c2, c3_=c3: wT[:, :, 0].permute(2, 3, 1, 0).reshape(4 * c3_, c2_)),
                         p[pre + "5.bias"].repeat(4).contiguous(), zt, False)
             T.gelu_fwd(zt, at)
             self.launches += 9
             saved.append((cur, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W))
             cur, H, W = at, 2 * H, 2 * W
-        co = _Conv(8, 8, 1)
+        co = _Conv(self, "output_layer.0.weight", 8, 8, 1)
         z1, a1 = self._buf("z_o0", (D, H, W, 8)), self._buf("a_o0", (D, H, W, 8))
-        co.forward(cur, p["output_layer.0.weight"], p["output_layer.0.bias"], z1)
+        co.forward(cur, p["output_layer.0.bias"], z1)
         T.gelu_fwd(z1, a1)
         logits, probs = self._buf("logits", (D, H, W), F32), self._buf("probs", (D, H, W), F32)
         if W % 16 == 0:
-            ops.conv3d_wpack8_final(a1, wpack_weight_image(p["output_layer.2.weight"], 16).to(BF16),
+            ops.conv3d_wpack8_final(a1, self._pk("out2/f/wpack", "output_layer.2.weight", lambda w_: wpack_weight_image(w_, 16)),
                                     p["output_layer.2.bias"].repeat(16).contiguous(), logits, probs)
         else:
             ops.head_out_conv(a1, p["output_layer.2.weight"].permute(2, 3, 4, 0, 1).reshape(27, 8).contiguous(),
@@ -236,21 +280,20 @@ class CryoVITHeadTrainerB200:
         dl8 = self._buf("dlogit8", (D, H, W, 8))
         T.dice_bwd(logits, probs, lab, stats8, dl8, grad_scale)
         # output_layer.2 (8 -> 1): operate on the 8-channel padded gradient (channel 0 live)
-        w2 = p["output_layer.2.weight"]                                    # [1, 8, 3,3,3]
         dw2 = T.conv_weight_gradient(a1, dl8, 1, self._bufs.setdefault("wgrad_pool", {}))  # [27, 8 (co, only 0 live), 8 (ci)]
         g["output_layer.2.weight"].copy_(dw2[:, 0].view(3, 3, 3, 8).permute(3, 0, 1, 2)[None])
         db2 = torch.zeros(8, device=dev, dtype=F32)
         T.colsum(dl8, db2)
         g["output_layer.2.bias"].copy_(db2[:1])
-        w2_8 = torch.zeros(8, 8, 3, 3, 3, device=dev, dtype=F32)
-        w2_8[0] = w2[0]                                                    # forward weight padded to 8 output channels
         da1 = self._buf("da_o0", (D, H, W, 8))
-        _Conv(8, 8, 1).input_gradient(dl8, w2_8, da1)
+        # forward weight zero-padded to 8 output channels (the gradient volume carries 8 channels, channel 0 live)
+        _Conv(self, "output_layer.2.weight", 8, 8, 1,
+              pre=lambda w_: torch.cat([w_, torch.zeros(7, 8, 3, 3, 3, device=w_.device, dtype=w_.dtype)])).input_gradient(dl8, da1)
         dz1 = self._buf("dz_o0", (D, H, W, 8))
         T.gelu_bwd(da1, z1, dz1)
         self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight", "output_layer.0.bias")
         dcur = self._buf("d_top", (D, H, W, 8))
-        co.input_gradient(dz1, p["output_layer.0.weight"], dcur)
+        co.input_gradient(dz1, dcur)
         self.launches += 14
         for bi in reversed(range(4)):
             c1, c2, c3, d1, d2 = BLOCKS[bi]
@@ -267,10 +310,13 @@ class CryoVITHeadTrainerB200:
             dbt = torch.zeros(4 * c3, device=dev, dtype=F32)
             T.colsum(dzun, dbt)
             g[pre + "5.bias"].copy_(dbt.view(4, c3).sum(0))
-            wd = p[pre + "5.weight"][:, :, 0].permute(0, 2, 3, 1).reshape(c2, 4 * c3)      # dX = dZun @ wd^T
-            n_pad = max(32, c2)
-            wd_p = torch.zeros(n_pad, 4 * c3, device=dev, dtype=BF16)
-            wd_p[:c2] = wd.to(BF16)
+            n_pad = max(32, c2)  # dX = dZun @ wd^T, wd = the weight as [c2, (i, j, co)], zero rows up to the MMA N tile
+
+            def wd_fn(wT, c2_=c2, c3_=c3, n_=n_pad):
+                wd = wT[:, :, 0].permute(0, 2, 3, 1).reshape(c2_, 4 * c3_)
+                return torch.cat([wd, torch.zeros(n_ - c2_, 4 * c3_, device=wT.device, dtype=wT.dtype)]) if n_ > c2_ else wd
+
+            wd_p = self._pk(pre + "5/g", pre + "5.weight", wd_fn)
             dab = self._buf(f"dab{bi}", (D, H, W, c2))
             T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, torch.zeros(n_pad, device=dev, dtype=F32), dab.view(rows, c2), c2)
             # conv b
@@ -278,13 +324,13 @@ class CryoVITHeadTrainerB200:
             T.gelu_bwd(dab, zb, dzb)
             self._wgrad_conv(aa, dzb, d2, pre + "3.weight", pre + "3.bias")
             daa = self._buf(f"daa{bi}", (D, H, W, c2))
-            cb.input_gradient(dzb, p[pre + "3.weight"], daa)
+            cb.input_gradient(dzb, daa)
             # conv a
             dza = self._buf(f"dza{bi}", (D, H, W, c2))
             T.gelu_bwd(daa, za, dza)
             self._wgrad_conv(n_out, dza, d1, pre + "1.weight", pre + "1.bias")
             dn = self._buf(f"dn{bi}", (D, H, W, c1))
-            ca.input_gradient(dza, p[pre + "1.weight"], dn)
+            ca.input_gradient(dza, dn)
             # GroupNorm
             dblk = self._buf(f"dblk{bi}", (D, H, W, c1))
             dgam, dbet = torch.empty(c1, device=dev, dtype=F32), torch.empty(c1, device=dev, dtype=F32)
