@@ -62,7 +62,16 @@ def run_trainer(cfg) -> Path:
         s = swa.get("swa_epoch_start", 0.8)
         swa_start = int(s * max_epochs) if isinstance(s, float) else int(s)
     ckpt = cfg.get("ckpt_path")
-    state = torch.load(ckpt) if ckpt else None
+    state = None
+    if ckpt:  # fine-tune from a .pt state dict or a .model file (run/train_model.py:118-137)
+        if str(ckpt).endswith(".model"):
+            from .model_io import load_model
+
+            state = load_model(ckpt)[0].state_dict()
+        elif str(ckpt).endswith(".pt"):
+            state = torch.load(ckpt)
+        else:
+            raise ValueError(f"Unsupported checkpoint format: {Path(ckpt).suffix}. Use .pt or .model files.")
     logging.info("Starting training.")
     fit_head(dataset, in_channels=int(cfg.model.get("in_channels", 1536)), max_epochs=max_epochs, lr=float(cfg.model.lr),
              weight_decay=float(cfg.model.get("weight_decay", 1e-3)), swa_epoch_start=swa_start, seed=int(cfg.random_seed),
