@@ -19,7 +19,7 @@ SOURCES = ["host_common.cu", "gemm.cu", "vit_elementwise.cu", "attention.cu", "a
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("CVIT_NVCC_EXTRA", "").split()  # e.g. -DFA_POLY_EVERY=4 for A/B builds of one kernel
 
 
 def _nvcc() -> str:
