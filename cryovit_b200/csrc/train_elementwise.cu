@@ -15,11 +15,19 @@ static int ew_grid(int64_t n, int per_thread = 8) {
   return (int)(b < 1 ? 1 : b);
 }
 
-// d/dz [ 0.5 z (1 + erf(z / sqrt 2)) ] = Phi(z) + z phi(z)
+// d/dz [ 0.5 z (1 + erf(z / sqrt 2)) ] = Phi(z) + z phi(z). erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, see
+// gelu_erf in ptx.cuh); its exp(-z^2 / 2) is the one phi(z) needs, so the whole derivative costs one ex2 and one rcp.
 __device__ __forceinline__ float gelu_grad(float z) {
-  const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-  return cdf + z * pdf;
+  const float u = fabsf(z) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(u * u * -1.4426950408889634f);  // exp(-z^2 / 2)
+  const float cdf = fmaf(0.5f, copysignf(fmaf(-p, e, 1.0f), z), 0.5f);
+  return fmaf(z * 0.3989422804014327f, e, cdf);
 }
 
 // a = gelu(z), 8 bf16 per thread-iteration
@@ -52,6 +60,45 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const uint4* __restrict__
     }
     dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
+}
+
+// The same with the bias gradient db[c] += sum over rows of dz[r, c] accumulated on the way (the column sums of dz that
+// every convolution's bias gradient is): thread t owns the 8-channel vector t % (C/8) and strides over the rows of its
+// block's range, so the partial sums stay in registers; one shared-memory and one global atomic pass per block.
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
+                                                               uint4* __restrict__ dz, float* __restrict__ db, int64_t R, int C,
+                                                               int64_t rows_per_block) {
+  extern __shared__ float s_db[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
+  __syncthreads();
+  const int nvec = C / 8;
+  const int vec = threadIdx.x % nvec, rsub = threadIdx.x / nvec, rstep = blockDim.x / nvec;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rsub < rstep) {
+    for (int64_t r = r0 + rsub; r < r1; r += rstep) {
+      const int64_t i = r * nvec + vec;
+      const uint4 rg = da[i], rz = z[i];
+      const __nv_bfloat162* g = reinterpret_cast<const __nv_bfloat162*>(&rg);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rz);
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fg = __bfloat1622float2(g[k]), fz = __bfloat1622float2(h[k]);
+        const __nv_bfloat162 d2 = __floats2bfloat162_rn(fg.x * gelu_grad(fz.x), fg.y * gelu_grad(fz.y));
+        o[k] = *reinterpret_cast<const uint32_t*>(&d2);
+        const float2 dr = __bfloat1622float2(d2);  // the sums are over the STORED (bf16) gradient, as a separate pass would see it
+        acc[2 * k] += dr.x;
+        acc[2 * k + 1] += dr.y;
+      }
+      dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_db[vec * 8 + k], acc[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(db + i, s_db[i]);
 }
 
 // Dice loss L = 1 - 2 I / (Sy + Sp + eps) over the voxels with label > -1, p = sigmoid(clip(x, -5, 5)):
@@ -245,6 +292,18 @@ int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void*
   gelu_bwd_kernel<<<ew_grid(n / 8, 4), 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(da), static_cast<const uint4*>(z),
                                                                        static_cast<uint4*>(dz), n / 8);
   return check_launch("gelu_bwd_kernel");
+}
+
+// dz = da * gelu'(z) over a bf16 [R, C] matrix and db[c] += sum_r dz[r, c] (fp32 [C], caller zeroes); C % 8 == 0, C <= 2048.
+int cvit_gelu_bwd_colsum_bf16(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, void* stream) {
+  if (!da || !z || !dz || !db || R <= 0 || C <= 0 || (C % 8) || C > 2048) { set_error("gelu_bwd_colsum: bad arguments"); return CVIT_ERR_INVALID; }
+  int64_t blocks = (int64_t)num_sms() * 8;
+  int64_t rpb = (R + blocks - 1) / blocks;
+  if (rpb < 1) rpb = 1;
+  blocks = (R + rpb - 1) / rpb;
+  gelu_bwd_colsum_kernel<<<(unsigned)blocks, 256, C * sizeof(float), (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(da), static_cast<const uint4*>(z), static_cast<uint4*>(dz), db, R, (int)C, rpb);
+  return check_launch("gelu_bwd_colsum_kernel");
 }
 
 int cvit_dice_bwd(const float* logits, const float* probs, const float* labels, const double* stats8, float scale,

@@ -192,17 +192,19 @@ class CryoVITHeadTrainerB200:
             self._bufs[name] = b
         return b[:n].view(shape)
 
-    def _wgrad_conv(self, x, dz, dil, key_w, key_b):
-        """Accumulates the weight / bias gradient of a 3x3x3 convolution into the flat bucket."""
+    def _gelu_bwd_bias(self, da, z, dz, key_b):
+        """dz = da * gelu'(z) and the layer's bias gradient (the column sums of dz) in the same pass."""
+        db = torch.zeros(z.shape[-1], device=self.device, dtype=F32)
+        T.gelu_bwd(da, z, dz, db)
+        self.g[key_b].copy_(db)
+
+    def _wgrad_conv(self, x, dz, dil, key_w):
+        """Accumulates the weight gradient of a 3x3x3 convolution into the flat bucket (the bias gradient comes out of
+        ``_gelu_bwd_bias``, which produced dz)."""
         cin, cout = x.shape[-1], dz.shape[-1]
-        D, H, W, _ = x.shape
         dw = T.conv_weight_gradient(x, dz, dil, self._bufs.setdefault("wgrad_pool", {}))  # [27, cout, cin]
         self.g[key_w].copy_(dw.view(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
-        if key_b is not None:
-            db = torch.zeros(cout, device=self.device, dtype=F32)
-            T.colsum(dz, db)
-            self.g[key_b].copy_(db)
-        self.launches += 8
+        self.launches += 7
 
     def _wgrad_rows(self, x_rows, dz_rows):
         """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions)."""
@@ -290,8 +292,8 @@ class CryoVITHeadTrainerB200:
         _Conv(self, "output_layer.2.weight", 8, 8, 1,
               pre=lambda w_: torch.cat([w_, torch.zeros(7, 8, 3, 3, 3, device=w_.device, dtype=w_.dtype)])).input_gradient(dl8, da1)
         dz1 = self._buf("dz_o0", (D, H, W, 8))
-        T.gelu_bwd(da1, z1, dz1)
-        self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight", "output_layer.0.bias")
+        self._gelu_bwd_bias(da1, z1, dz1, "output_layer.0.bias")
+        self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight")
         dcur = self._buf("d_top", (D, H, W, 8))
         co.input_gradient(dz1, dcur)
         self.launches += 14
@@ -301,15 +303,12 @@ class CryoVITHeadTrainerB200:
             blk_in, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W = saved[bi]
             # transposed convolution: dcur is d(at) [D, 2H, 2W, c3]
             dzt = self._buf(f"dzt{bi}", (D, 2 * H, 2 * W, c3))
-            T.gelu_bwd(dcur, zt, dzt)
+            self._gelu_bwd_bias(dcur, zt, dzt, pre + "5.bias")  # summed over voxels AND sub-pixels: dzt is [.., c3]
             dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
             T.pixel_unshuffle(dzt, dzun)
             rows = D * H * W
             dwt = self._wgrad_rows(ab.view(rows, c2), dzun.view(rows, 4 * c3))          # [(ij, c3), c2]
             g[pre + "5.weight"].copy_(dwt.view(2, 2, c3, c2).permute(3, 2, 0, 1)[:, :, None])
-            dbt = torch.zeros(4 * c3, device=dev, dtype=F32)
-            T.colsum(dzun, dbt)
-            g[pre + "5.bias"].copy_(dbt.view(4, c3).sum(0))
             n_pad = max(32, c2)  # dX = dZun @ wd^T, wd = the weight as [c2, (i, j, co)], zero rows up to the MMA N tile
 
             def wd_fn(wT, c2_=c2, c3_=c3, n_=n_pad):
@@ -321,14 +320,14 @@ class CryoVITHeadTrainerB200:
             T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, torch.zeros(n_pad, device=dev, dtype=F32), dab.view(rows, c2), c2)
             # conv b
             dzb = self._buf(f"dzb{bi}", (D, H, W, c2))
-            T.gelu_bwd(dab, zb, dzb)
-            self._wgrad_conv(aa, dzb, d2, pre + "3.weight", pre + "3.bias")
+            self._gelu_bwd_bias(dab, zb, dzb, pre + "3.bias")
+            self._wgrad_conv(aa, dzb, d2, pre + "3.weight")
             daa = self._buf(f"daa{bi}", (D, H, W, c2))
             cb.input_gradient(dzb, daa)
             # conv a
             dza = self._buf(f"dza{bi}", (D, H, W, c2))
-            T.gelu_bwd(daa, za, dza)
-            self._wgrad_conv(n_out, dza, d1, pre + "1.weight", pre + "1.bias")
+            self._gelu_bwd_bias(daa, za, dza, pre + "1.bias")
+            self._wgrad_conv(n_out, dza, d1, pre + "1.weight")
             dn = self._buf(f"dn{bi}", (D, H, W, c1))
             ca.input_gradient(dza, dn)
             # GroupNorm
@@ -341,12 +340,9 @@ class CryoVITHeadTrainerB200:
             self.launches += 14
         # projection (1x1x1): only the weight / bias gradient (the features are data)
         dzp = self._buf("dz_proj", (vox, 1024))
-        T.gelu_bwd(dcur.view(vox, 1024), z_proj, dzp)
+        self._gelu_bwd_bias(dcur.view(vox, 1024), z_proj, dzp, "layers.0.bias")
         g["layers.0.weight"].copy_(self._wgrad_rows(x0.view(vox, C), dzp).view(1024, C, 1, 1, 1))
-        dbp = torch.zeros(1024, device=dev, dtype=F32)
-        T.colsum(dzp, dbp)
-        g["layers.0.bias"].copy_(dbp)
-        self.launches += 3
+        self.launches += 2
         return loss
 
     def optimizer_step(self) -> None:

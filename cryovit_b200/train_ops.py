@@ -38,8 +38,14 @@ def gelu_fwd(z, a) -> None:
     _lib.call("cvit_gelu_fwd_bf16", _chk(z, BF16, "z"), _chk(a, BF16, "a"), z.numel(), _stream())
 
 
-def gelu_bwd(da, z, dz) -> None:
-    _lib.call("cvit_gelu_bwd_bf16", _chk(da, BF16, "da"), _chk(z, BF16, "z"), _chk(dz, BF16, "dz"), z.numel(), _stream())
+def gelu_bwd(da, z, dz, db=None) -> None:
+    """dz = da * gelu'(z); with ``db`` (fp32 [C], zeroed by the caller) also db += column sums of dz over the last axis."""
+    if db is None:
+        _lib.call("cvit_gelu_bwd_bf16", _chk(da, BF16, "da"), _chk(z, BF16, "z"), _chk(dz, BF16, "dz"), z.numel(), _stream())
+        return
+    C = z.shape[-1]
+    _lib.call("cvit_gelu_bwd_colsum_bf16", _chk(da, BF16, "da"), _chk(z, BF16, "z"), _chk(dz, BF16, "dz"), _chk(db, F32, "db"),
+              z.numel() // C, C, _stream())
 
 
 def dice_bwd(logits, probs, labels, stats8, dlogit8, scale: float = 1.0) -> None:

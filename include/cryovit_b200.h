@@ -212,6 +212,9 @@ int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, cons
 /* a = gelu(z) and dz = da * gelu'(z) (exact erf form, nn.GELU() default), bf16, n a multiple of 8. */
 int cvit_gelu_fwd_bf16(const void* z, void* a, int64_t n, void* stream);
 int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void* stream);
+/* The same over a bf16 [R, C] matrix with the bias gradient on the way: db[c] += sum_r dz[r, c] (fp32 [C], caller zeroes;
+ * C % 8 == 0, C <= 2048) -- what autograd's conv bias gradient reduces, without a second pass over dz. */
+int cvit_gelu_bwd_colsum_bf16(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, void* stream);
 
 /* Gradient of DiceLoss (models/losses.py:17-32) w.r.t. the raw logits, through sigmoid and clip(-5, 5)
  * (models/cryovit.py:39,49), masked to label > -1 (models/base_model.py:91-112). stats8 = the device-resident sums

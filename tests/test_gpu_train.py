@@ -26,6 +26,15 @@ def test_gelu_fwd_bwd(cuda_lib):
     ar = F.gelu(zr)
     ar.backward(da.float())
     assert _relerr(a, ar.detach()) < 4e-3 and _relerr(dz, zr.grad) < 4e-3
+    # fused variant: the same dz, bit for bit, plus the column sums of the stored gradient (the bias gradient)
+    for C in (64, 192, 8, 1024):
+        n = z.numel() // C * C  # 192 does not divide the element count: use the leading part
+        zc, dac = z.reshape(-1)[:n].reshape(-1, C), da.reshape(-1)[:n].reshape(-1, C)
+        dz2, db = torch.empty_like(zc), torch.zeros(C, device=DEV)
+        T.gelu_bwd(dac, zc, dz2, db)
+        assert torch.equal(dz2.reshape(-1), dz.reshape(-1)[:n])
+        ref = dz2.float().sum(0)
+        assert (db - ref).abs().max() <= 1e-3 * ref.abs().max() + 1e-3, C
 
 
 @pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(6, 12, 20, 64, 192, 2), (5, 16, 8, 32, 32, 1), (4, 9, 11, 16, 16, 1),
