@@ -1,7 +1,8 @@
 """Head training loop with the reference's schedule (run/train_model.py:206-312, configs/trainer/fit.yaml,
 configs/callbacks/stochastic_weight_average.yaml): seed, AdamW(lr, weight_decay) on every step, batch of ONE tomogram
 crop per process (dataloader/default.yaml batch_size 1), ``max_epochs`` passes, stochastic weight averaging of the
-weights from ``swa_epoch_start`` on (constant learning rate ``swa_lrs = lr``, so SWA is a running mean of the iterates),
+weights from ``swa_epoch_start`` on (constant learning rate ``swa_lrs = lr``, so SWA is a running mean of the weights
+at the epoch starts, as Lightning's callback samples them),
 final ``weights.pt`` = plain state dict with the reference's parameter names (:312). Lightning itself is not used:
 the step is ``CryoVITHeadTrainerB200.train_step`` (native forward / backward / all-reduce / AdamW)."""
 from __future__ import annotations
@@ -31,6 +32,12 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
     swa_avg, swa_n = None, 0
     step = 0
     for epoch in range(max_epochs):
+        # Lightning's StochasticWeightAveraging.on_train_epoch_START: epochs swa_start .. max_epochs - 1 each add the
+        # weights they START from to the running mean (so the last epoch's own updates are not in it), and the mean
+        # replaces the weights when training ends.
+        if swa_epoch_start is not None and epoch >= swa_epoch_start:
+            swa_n += 1
+            swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
         order = order_rng.permutation(len(dataset))
         usable = len(order) // world * world  # every rank takes the same number of steps (the all-reduce is collective)
         losses = []
@@ -40,9 +47,6 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
             step += 1
             if step % log_every == 0 or len(losses) == 0:
                 losses.append(float(loss))
-        if swa_epoch_start is not None and epoch >= swa_epoch_start:
-            swa_n += 1
-            swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
         if rank == 0:
             logging.info("epoch %d: %d steps/rank, DiceLoss %.4f", epoch, usable // world, float(np.mean(losses)) if losses else float("nan"))
     if swa_avg is not None:
