@@ -384,7 +384,7 @@ def run_b200(args) -> None:
 
     cfg = CONFIGS[MODEL]
     sd = random_state_dict(cfg, seed=0)
-    model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda(local)
+    model = DinoVisionTransformerB200(cfg, torch.float16 if args.operands == "fp16" else torch.bfloat16).load_state_dict(sd).cuda(local)
     if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
         sd = None  # free 4.5 GB per rank unless the CPU baseline leg needs it
     g = torch.Generator().manual_seed(1234 + rank)
@@ -515,7 +515,7 @@ def run_b200(args) -> None:
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16+bf16 operands, fp32 accumulate" if args.operands == "fp16" else "bf16", "data": "synthetic",
         "config": {"workload": f"ViT-g/14-reg4 (random init, LayerScale 1.0) features of one {D}x{H}x{W} uint8 tomogram per GPU "
                                f"per step, slice batch {BATCH}, output fp16 ({C},{D},32,32)",
                    "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
@@ -548,6 +548,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--operands", default="bf16", choices=["fp16", "bf16"],
+                    help="16-bit type of the bounded ViT operands (LayerNorm output, q/k/v, attention output and their weights)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.steps_ref, args.warmup_ref = min(args.steps, 3), min(args.warmup, 1)

@@ -26,11 +26,16 @@ SIGNATURES: dict[str, list] = {
     "cvit_patch_embed_gemm": [P, I64, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_assemble_special_tokens": [P, P, I64, I64, I64, I64, P],
     "cvit_layernorm_f32_bf16": [P, I64, P, P, P, I64, I64, I64, F32, P],
+    "cvit_layernorm_f32_f16": [P, I64, P, P, P, I64, I64, I64, F32, P],
     "cvit_layernorm_f32_f32": [P, I64, P, P, P, I64, I64, I64, F32, P],
     "cvit_linear_bias_bf16": [P, I64, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_linear_swiglu_bf16": [P, I64, P, P, P, I64, I64, I64, I64, P],
     "cvit_linear_scale_residual_f32": [P, I64, P, P, P, P, I64, I64, I64, I64, P],
+    "cvit_linear_bias_fmt": [P, I64, P, P, P, I64, I64, I64, I64, I32, I32, P],
+    "cvit_linear_swiglu_fmt": [P, I64, P, P, P, I64, I64, I64, I64, I32, P],
+    "cvit_linear_scale_residual_fmt": [P, I64, P, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],
+    "cvit_attention_fwd_f16": [P, P, I64, I64, I64, I64, P],
     "cvit_attention_fwd_bf16_mma_sync": [P, P, I64, I64, I64, I64, P],
     "cvit_final_norm_writeout_f16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "cvit_features_to_ndhwc_bf16": [P, P, I64, I64, P],

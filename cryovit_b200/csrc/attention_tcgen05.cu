@@ -83,6 +83,9 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+// F16: q/k/v, P and the output are IEEE fp16 instead of bf16 (three more mantissa bits for these bounded operands;
+// P <= 2^8 under the lazy rescale, far inside the fp16 range). Everything else is identical.
+template <bool F16>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -185,7 +188,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       // phases would alias on the parity bit).
       const int g = warp - 13;
       const uint32_t bg = bar_grp + 64 * g;
-      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(FA_BQ, FA_D) | (1u << 16);  // B is MN-major
+      constexpr uint32_t idesc_pv = (F16 ? umma_idesc_f16_f32(FA_BQ, FA_D) : umma_idesc_bf16_f32(FA_BQ, FA_D)) | (1u << 16);  // B is MN-major
       auto n_mma_of = [&](int j) {  // keys of the j-th walked tile rounded up to the MMA granularity (16)
         const int valid = min(FA_BK, T - kv_tile(j) * FA_BK);
         return (valid + 15) & ~15;
@@ -202,7 +205,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         tcgen05_fence_after();
         FA_PROF(1);  // wait: K/V landed
         if (elect_one_sync()) {
-          const uint32_t idesc_s = umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
+          const uint32_t idesc_s = F16 ? umma_idesc_f16_f32(FA_BQ, n_mma_of(j)) : umma_idesc_bf16_f32(FA_BQ, n_mma_of(j));
           const uint64_t qd = umma_smem_desc_kmajor<128>(sQ + ((k & 1) * 2 + g) * FA_TILE_BYTES);
           const uint64_t kd = umma_smem_desc_kmajor<128>(sK + s * FA_TILE_BYTES);
           const uint32_t tS = tmem_base + FA_COL_S + g * 128;
@@ -353,7 +356,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              ob[i] = pack_bf16x2(__uint_as_float(oa[2 * i]) * wa + __uint_as_float(o2[2 * i]) * wb,
+              ob[i] = pack_16x2<F16>(__uint_as_float(oa[2 * i]) * wa + __uint_as_float(o2[2 * i]) * wb,
                                   __uint_as_float(oa[2 * i + 1]) * wa + __uint_as_float(o2[2 * i + 1]) * wb);
             if (tok < T) {
               dst[2 * hh] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
@@ -391,7 +394,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             tmem_ld_32x32(t_row + FA_COL_O + g * 64 + hh * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            for (int i = 0; i < 16; ++i) o[i] = pack_16x2<F16>(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
             if (tok < T) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[4 * hh + i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -498,7 +501,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             unpack_f32x2(t2, t0, t1);
             const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
             ls[i & 3] = add_f32x2(ls[i & 3], pack_f32x2(p0, p1));
-            v[i] = pack_bf16x2(p0, p1);
+            v[i] = pack_16x2<F16>(p0, p1);
           }
           {
             float a0, a1;
@@ -565,7 +568,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
                 const float p0 = k0 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc)) : 0.f;
                 const float p1 = k0 + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc)) : 0.f;
                 l += p0 + p1;
-                pk[i] = pack_bf16x2(p0, p1);
+                pk[i] = pack_16x2<F16>(p0, p1);
               }
               tmem_st_32x8(tP + ch * 8, pk);
             }
@@ -608,8 +611,9 @@ static long long* g_fa_trace = nullptr;
 extern "C" void cvit_fa_set_trace(long long* p) { g_fa_trace = p; }
 #endif
 
-extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
-                                       int64_t head_dim, void* stream) {
+template <bool F16>
+static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads, int64_t head_dim,
+                         void* stream) {
   if (!qkv || !out || n_slices <= 0 || tokens <= 0 || heads <= 0) {
     set_error("attention: bad arguments");
     return CVIT_ERR_INVALID;
@@ -627,11 +631,11 @@ extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_sli
   uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)tokens, (uint64_t)n_slices};
   uint64_t strides[3] = {0, (uint64_t)(3 * C) * 2, (uint64_t)tokens * 3 * C * 2};
   uint32_t box[3] = {FA_D, FA_BK, 1};
-  int rc = encode_tmap(&tm, TmapDtype::BF16, 3, qkv, dims, strides, box, 128);
+  int rc = encode_tmap(&tm, F16 ? TmapDtype::F16 : TmapDtype::BF16, 3, qkv, dims, strides, box, 128);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CVIT_ERR_CUDA;
@@ -654,6 +658,17 @@ extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_sli
   const int64_t items = (int64_t)((n_qt + 1) / 2) * heads * n_slices;
   int grid = num_sms();
   if (grid > items) grid = (int)items;
-  attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
+  attention_tcgen05_kernel<F16><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
   return check_launch("attention_tcgen05_kernel");
+}
+
+extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                                       int64_t head_dim, void* stream) {
+  return attention_fwd<false>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+}
+
+// Same kernel with IEEE fp16 q/k/v, probabilities and output (the fp16-operand ViT path).
+extern "C" int cvit_attention_fwd_f16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                                      int64_t head_dim, void* stream) {
+  return attention_fwd<true>(qkv, out, n_slices, tokens, heads, head_dim, stream);
 }

@@ -58,11 +58,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 }
 
 static int make_tmap_rows(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
-                          int kspan) {
+                          int kspan, bool f16 = false) {
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
   uint64_t strides[2] = {0, (uint64_t)ld * 2};
   uint32_t box[2] = {(uint32_t)(kspan / 2), (uint32_t)box_rows};
-  return encode_tmap(tm, TmapDtype::BF16, 2, base, dims, strides, box, kspan);
+  return encode_tmap(tm, f16 ? TmapDtype::F16 : TmapDtype::BF16, 2, base, dims, strides, box, kspan);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -103,12 +103,13 @@ static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, i
   }
   if (kspan != 128 && bn > 128) bn = 128;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_rows(&tmA, A, M, K, lda, GEMM_BM, kspan);
+  const bool f16 = (args.fmt & GEMM_FMT_OPERANDS_F16) != 0;
+  int rc = make_tmap_rows(&tmA, A, M, K, lda, GEMM_BM, kspan, f16);
   if (rc) return rc;
   // CTA pairs (256 x 256 output tile per TPC) whenever there is more than one 128-row tile to share a B tile over
   const bool pair = g_gemm_pair && bn == 256 && kspan == 128 && M > GEMM_BM &&
                     (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_SWIGLU || epi == EPI_SCALE_RESIDUAL);
-  rc = make_tmap_rows(&tmB, B, N, K, K, pair ? bn / 2 : bn, kspan);
+  rc = make_tmap_rows(&tmB, B, N, K, K, pair ? bn / 2 : bn, kspan, f16);
   if (rc) return rc;
   const int bm = pair ? 2 * GEMM_BM : GEMM_BM;
   const int num_tiles = (int)(((M + bm - 1) / bm) * (N / bn));
@@ -215,12 +216,27 @@ int cvit_set_gemm_pair(int enable) {
   return prev;
 }
 
-int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
-                          int64_t M, int64_t N, int64_t K, int gelu, void* stream) {
+static int check_fmt(int fmt) {
+  if (fmt & ~(GEMM_FMT_OPERANDS_F16 | GEMM_FMT_OUT_F16)) {
+    set_error("linear: unknown format flags 0x%x", fmt);
+    return CVIT_ERR_INVALID;
+  }
+  return CVIT_OK;
+}
+
+int cvit_linear_bias_fmt(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                         int64_t M, int64_t N, int64_t K, int gelu, int fmt, void* stream) {
   if (!bias) { set_error("linear_bias: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_fmt(fmt)) return rc;
   GemmArgs a = base_args(M, N, K, out, ldo);
   a.bias = bias;
+  a.fmt = fmt;
   return gemm_rows(A, lda, W, a, gelu ? EPI_BIAS_GELU : EPI_BIAS, (cudaStream_t)stream);
+}
+
+int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                          int64_t M, int64_t N, int64_t K, int gelu, void* stream) {
+  return cvit_linear_bias_fmt(A, lda, W, bias, out, ldo, M, N, K, gelu, 0, stream);
 }
 
 // Same as cvit_linear_bias_bf16 for an output narrower than the (zero-row-padded) weight: columns >= n_valid are
@@ -234,21 +250,35 @@ int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, cons
   return gemm_rows(A, lda, W, a, EPI_BIAS, (cudaStream_t)stream);
 }
 
-int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
-                            int64_t ldo, int64_t M, int64_t N2, int64_t K, void* stream) {
+int cvit_linear_swiglu_fmt(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
+                           int64_t ldo, int64_t M, int64_t N2, int64_t K, int fmt, void* stream) {
   if (!bias12i) { set_error("linear_swiglu: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_fmt(fmt)) return rc;
   GemmArgs a = base_args(M, N2, K, out, ldo);
   a.bias = bias12i;
+  a.fmt = fmt;
   return gemm_rows(A, lda, W12i, a, EPI_BIAS_SWIGLU, (cudaStream_t)stream);
+}
+
+int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
+                            int64_t ldo, int64_t M, int64_t N2, int64_t K, void* stream) {
+  return cvit_linear_swiglu_fmt(A, lda, W12i, bias12i, out, ldo, M, N2, K, 0, stream);
+}
+
+int cvit_linear_scale_residual_fmt(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
+                                   float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, int fmt, void* stream) {
+  if (!bias || !gamma) { set_error("linear_scale_residual: bias and gamma are required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_fmt(fmt)) return rc;
+  GemmArgs a = base_args(M, N, K, x, ldx);
+  a.bias = bias;
+  a.gamma = gamma;
+  a.fmt = fmt & GEMM_FMT_OPERANDS_F16;
+  return gemm_rows(A, lda, W, a, EPI_SCALE_RESIDUAL, (cudaStream_t)stream);
 }
 
 int cvit_linear_scale_residual_f32(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
                                    float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, void* stream) {
-  if (!bias || !gamma) { set_error("linear_scale_residual: bias and gamma are required"); return CVIT_ERR_INVALID; }
-  GemmArgs a = base_args(M, N, K, x, ldx);
-  a.bias = bias;
-  a.gamma = gamma;
-  return gemm_rows(A, lda, W, a, EPI_SCALE_RESIDUAL, (cudaStream_t)stream);
+  return cvit_linear_scale_residual_fmt(A, lda, W, bias, gamma, x, ldx, M, N, K, 0, stream);
 }
 
 int cvit_patch_embed_gemm(const void* patches, int64_t lda, const void* W, const float* pos_bias_table, float* x,

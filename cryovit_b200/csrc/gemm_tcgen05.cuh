@@ -1,6 +1,7 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
 //
 //   D[M,N] = A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major, i.e. torch Linear weight layout)
+//   (GemmArgs::fmt: both operands IEEE fp16 instead, and/or the 16-bit output stored as fp16)
 //
 // One CTA per SM, 320 threads:
 //   warp 0      TMA producer  (one lane): cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring
@@ -46,7 +47,12 @@ struct GemmArgs {
   int c3;             // EPI_CONVT_GELU: output channels per sub-pixel (N == 4*c3); uses H, W too
   int n_valid;        // columns >= n_valid are computed (zero-padded weights) but never stored
   int act;            // EPI_BIAS_GELU / EPI_CONVT_GELU: 1 = GELU (inference), 0 = store the pre-activation (training, dgrad)
+  int fmt;            // GEMM_FMT_* bits: 16-bit type of the operands / of the stored output (0 = bf16 everywhere)
 };
+// A and B hold IEEE fp16 instead of bf16 (same type on both sides: tcgen05 kind::f16 rule); EPI_BIAS / _GELU / _SWIGLU
+// store fp16 instead of bf16. fp16 keeps three more mantissa bits than bf16 for operands whose range is bounded
+// (LayerNorm output, q/k/v, attention output and the weights they meet).
+enum { GEMM_FMT_OPERANDS_F16 = 1, GEMM_FMT_OUT_F16 = 2 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;
@@ -237,7 +243,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // in uniform registers; one elected lane issues the MMAs and commits. (Issuing from a divergent `lane == 0`
     // region cost ~90 cycles per tcgen05.mma: every operand went through R2UR and a per-lane ELECT loop.)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * GEMM_BM : GEMM_BM, BN);
+      const uint32_t idesc = umma_idesc_f16_f32(PAIR ? 2 * GEMM_BM : GEMM_BM, BN) |
+                             ((args.fmt & GEMM_FMT_OPERANDS_F16) ? 0u : UMMA_IDESC_BF16_BITS);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -297,6 +304,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_ph = 0;
     constexpr int NCHUNK = (EPI == EPI_BIAS_SWIGLU ? BN / 2 : BN) / 32;
+    const bool out_f16 = (args.fmt & GEMM_FMT_OUT_F16) != 0;
     const int jc = lane & 7;    // 16-byte column group handled by this lane on the way out
     const int rsub = lane >> 3; // row within each group of 4 rows
     // smem transpose addresses: thread == row on the way in, (4 rows x 8 column groups) per step on the way out
@@ -379,8 +387,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o2 = silu(o2) * (ys[it].z + b4b.z);
               o3 = silu(o3) * (ys[it].w + b4b.w);
             }
-            if (grow_it[it] >= 0)
-              *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            if (grow_it[it] >= 0) {
+              const uint2 pk = out_f16 ? make_uint2(pack_f16x2(o0, o1), pack_f16x2(o2, o3))
+                                       : make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+              *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) = pk;
+            }
           }
         } else if (EPI == EPI_SCALE_RESIDUAL) {
           float* xbase = static_cast<float*>(args.out) + ncol;

@@ -297,6 +297,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// Same with IEEE fp16 operands (a/b_format = 0). Both operands of a kind::f16 MMA must have the SAME 16-bit type on
+// sm_100a: a bf16 x fp16 descriptor raises cudaErrorIllegalInstruction (profiles/r01_attention_notes.md).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// format bits that turn umma_idesc_f16_f32 into umma_idesc_bf16_f32
+constexpr uint32_t UMMA_IDESC_BF16_BITS = (1u << 7) | (1u << 10);
 
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -333,6 +340,15 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + ex2
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 -> one packed pair of the 16-bit operand type (F16: IEEE fp16, else bf16)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

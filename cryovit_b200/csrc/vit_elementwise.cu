@@ -139,6 +139,9 @@ __global__ void assemble_special_kernel(float* __restrict__ x, const float* __re
 __device__ __forceinline__ void ln_store4(__nv_bfloat16* row, int i4, float o0, float o1, float o2, float o3) {
   reinterpret_cast<uint2*>(row)[i4] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
 }
+__device__ __forceinline__ void ln_store4(__half* row, int i4, float o0, float o1, float o2, float o3) {
+  reinterpret_cast<uint2*>(row)[i4] = make_uint2(pack_f16x2(o0, o1), pack_f16x2(o2, o3));
+}
 __device__ __forceinline__ void ln_store4(float* row, int i4, float o0, float o1, float o2, float o3) {
   reinterpret_cast<float4*>(row)[i4] = make_float4(o0, o1, o2, o3);
 }
@@ -345,6 +348,16 @@ int cvit_layernorm_f32_bf16(const float* x, int64_t ldx, const float* gamma, con
     return CVIT_ERR_INVALID;
   }
   return launch_layernorm(x, ldx, gamma, beta, static_cast<__nv_bfloat16*>(out), ldo, M, C, eps, (cudaStream_t)stream);
+}
+
+// Same with an IEEE fp16 result: the A operand of the fp16-operand linears (cvit_linear_*_fmt).
+int cvit_layernorm_f32_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
+                           int64_t ldo, int64_t M, int64_t C, float eps, void* stream) {
+  if (!x || !gamma || !beta || !out || M <= 0 || (ldx % 4) || (ldo % 4)) {
+    set_error("layernorm: bad arguments");
+    return CVIT_ERR_INVALID;
+  }
+  return launch_layernorm(x, ldx, gamma, beta, static_cast<__half*>(out), ldo, M, C, eps, (cudaStream_t)stream);
 }
 
 int cvit_layernorm_f32_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* out,

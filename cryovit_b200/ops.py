@@ -75,32 +75,52 @@ def layernorm(x: torch.Tensor, gamma, beta, out: torch.Tensor, eps: float) -> No
         _lib.call("cvit_layernorm_f32_f32", _chk(x, F32, "x"), x.stride(0), _chk(gamma, F32, "gamma"),
                   _chk(beta, F32, "beta"), _chk(out, F32, "out"), out.stride(0), M, C, float(eps), _stream())
         return
-    _lib.call("cvit_layernorm_f32_bf16", _chk(x, F32, "x"), x.stride(0), _chk(gamma, F32, "gamma"),
-              _chk(beta, F32, "beta"), _chk(out, BF16, "out"), out.stride(0), M, C, float(eps), _stream())
+    name = "cvit_layernorm_f32_f16" if out.dtype == F16 else "cvit_layernorm_f32_bf16"
+    _lib.call(name, _chk(x, F32, "x"), x.stride(0), _chk(gamma, F32, "gamma"),
+              _chk(beta, F32, "beta"), _chk(out, out.dtype if out.dtype == F16 else BF16, "out"), out.stride(0), M, C, float(eps), _stream())
+
+
+FMT_OPERANDS_F16, FMT_OUT_F16 = 1, 2  # include/cryovit_b200.h CVIT_FMT_*
+
+
+def _fmt16(a, w, out=None) -> int:
+    """Format flags of a linear from the tensors' own dtypes: A and W must share one 16-bit type (bf16 or fp16: a
+    tcgen05 kind::f16 MMA takes one type for both operands); a 16-bit output may be either."""
+    if a.dtype not in (BF16, F16) or w.dtype != a.dtype:
+        raise _lib.CryovitB200Error(f"linear: operands must both be bf16 or both fp16, got {a.dtype} x {w.dtype}")
+    if out is not None and out.dtype not in (BF16, F16):
+        raise _lib.CryovitB200Error(f"linear: output must be bf16 or fp16, got {out.dtype}")
+    return (FMT_OPERANDS_F16 if a.dtype == F16 else 0) | (FMT_OUT_F16 if out is not None and out.dtype == F16 else 0)
 
 
 def linear_bias(a, w, bias, out, gelu: bool = False) -> None:
     M, K = a.shape
     N = w.shape[0]
-    _lib.call("cvit_linear_bias_bf16", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
-              _chk(out, BF16, "out"), out.stride(0), M, N, K, int(gelu), _stream())
+    fmt = _fmt16(a, w, out)
+    _lib.call("cvit_linear_bias_fmt", _chk(a, a.dtype, "a"), a.stride(0), _chk(w, w.dtype, "w"), _chk(bias, F32, "bias"),
+              _chk(out, out.dtype, "out"), out.stride(0), M, N, K, int(gelu), fmt, _stream())
 
 
 def linear_swiglu(a, w12i, bias12i, out) -> None:
     M, K = a.shape
     N2 = w12i.shape[0]
-    _lib.call("cvit_linear_swiglu_bf16", _chk(a, BF16, "a"), a.stride(0), _chk(w12i, BF16, "w12i"),
-              _chk(bias12i, F32, "bias12i"), _chk(out, BF16, "out"), out.stride(0), M, N2, K, _stream())
+    fmt = _fmt16(a, w12i, out)
+    _lib.call("cvit_linear_swiglu_fmt", _chk(a, a.dtype, "a"), a.stride(0), _chk(w12i, w12i.dtype, "w12i"),
+              _chk(bias12i, F32, "bias12i"), _chk(out, out.dtype, "out"), out.stride(0), M, N2, K, fmt, _stream())
 
 
 def linear_scale_residual(a, w, bias, gamma, x) -> None:
     M, K = a.shape
     N = w.shape[0]
-    _lib.call("cvit_linear_scale_residual_f32", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"),
-              _chk(bias, F32, "bias"), _chk(gamma, F32, "gamma"), _chk(x, F32, "x"), x.stride(0), M, N, K, _stream())
+    fmt = _fmt16(a, w)
+    _lib.call("cvit_linear_scale_residual_fmt", _chk(a, a.dtype, "a"), a.stride(0), _chk(w, w.dtype, "w"),
+              _chk(bias, F32, "bias"), _chk(gamma, F32, "gamma"), _chk(x, F32, "x"), x.stride(0), M, N, K, fmt, _stream())
 
 
 def attention(qkv, out, n_slices: int, tokens: int, heads: int, legacy_mma_sync: bool = False) -> None:
+    if qkv.dtype == F16 and not legacy_mma_sync:
+        _lib.call("cvit_attention_fwd_f16", _chk(qkv, F16, "qkv"), _chk(out, F16, "out"), n_slices, tokens, heads, 64, _stream())
+        return
     _lib.call("cvit_attention_fwd_bf16_mma_sync" if legacy_mma_sync else "cvit_attention_fwd_bf16", _chk(qkv, BF16, "qkv"), _chk(out, BF16, "out"), n_slices, tokens, heads, 64,
               _stream())
 

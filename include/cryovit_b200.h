@@ -83,6 +83,10 @@ int cvit_assemble_special_tokens(float* x, const float* special, int64_t B, int6
 int cvit_layernorm_f32_bf16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
                             int64_t ldo, int64_t M, int64_t C, float eps, void* stream);
 
+/* Same with an IEEE fp16 result: the A operand of the fp16-operand linears below (CVIT_FMT_OPERANDS_F16). */
+int cvit_layernorm_f32_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
+                           int64_t ldo, int64_t M, int64_t C, float eps, void* stream);
+
 /* Same with fp32 output: the final model.norm when the caller wants x_norm_* tensors (HF:477-503) rather than
  * the fused fp16 write-out below. */
 int cvit_layernorm_f32_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* out,
@@ -106,11 +110,31 @@ int cvit_linear_swiglu_bf16(const void* A, int64_t lda, const void* W12i, const 
 int cvit_linear_scale_residual_f32(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
                                    float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* 16-bit operand formats of the three linears above.  The reference runs these GEMMs in TF32 (10 mantissa bits,
+ * run/dino_features.py:24 set_float32_matmul_precision("high")); IEEE fp16 keeps the same 10 bits for operands whose
+ * range is bounded (LayerNorm output, q/k/v, attention output, and the weights they meet), bf16 (7 bits) stays the
+ * choice where range matters (the FFN hidden activations).  `fmt` is a combination of:
+ *   CVIT_FMT_OPERANDS_F16  A and W hold IEEE fp16 instead of bf16 (always both: a tcgen05 kind::f16 MMA takes one
+ *                          16-bit type for both operands);
+ *   CVIT_FMT_OUT_F16       the 16-bit output of linear_bias / linear_swiglu is stored as fp16 instead of bf16.
+ * fmt = 0 is exactly the *_bf16 / *_f32 entry point of the same name. */
+#define CVIT_FMT_OPERANDS_F16 1
+#define CVIT_FMT_OUT_F16 2
+int cvit_linear_bias_fmt(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                         int64_t M, int64_t N, int64_t K, int gelu, int fmt, void* stream);
+int cvit_linear_swiglu_fmt(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
+                           int64_t ldo, int64_t M, int64_t N2, int64_t K, int fmt, void* stream);
+int cvit_linear_scale_residual_fmt(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
+                                   float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, int fmt, void* stream);
+
 /* Multi-head self-attention of every slice: out[b, t, h*64 + d] = softmax(q k^T / 8) v with
  * q,k,v = qkv[b, t, {0,1,2}, h, :].  Replaces MemEffAttention / xformers memory_efficient_attention
  * (upstream attention.py; HF:202-256).  qkv bf16 [n_slices * tokens, 3 * heads * 64]; head_dim must be 64. */
 int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                             int64_t head_dim, void* stream);
+/* Same kernel with IEEE fp16 q/k/v, probabilities and output (fp32 scores, softmax and accumulation as above). */
+int cvit_attention_fwd_f16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                           int64_t head_dim, void* stream);
 /* Same contract on the legacy warp-level mma.sync path: kept only as an A/B comparison kernel for profiles. */
 int cvit_attention_fwd_bf16_mma_sync(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                      int64_t head_dim, void* stream);

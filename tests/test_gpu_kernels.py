@@ -105,6 +105,37 @@ def test_gemm_cta_pair_matches_single_cta(cuda_lib, M):
     _close(pair[0], a.float() @ w.float().t() + b, atol=2e-2, rtol=1e-2, what="pair linear_bias vs fp32")
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 256), (1029, 384, 384), (4116, 4608, 1536)])
+def test_linears_fp16_operands(cuda_lib, M, N, K):
+    """The fp16-operand format of the three ViT linears (CVIT_FMT_OPERANDS_F16 / CVIT_FMT_OUT_F16): same kernels, IEEE
+    fp16 A and W, output fp16 (qkv), bf16 (FFN hidden keeps the fp32 range) or the fp32 residual. The tolerance on the
+    fp16 output is 8x tighter than the bf16 one above (2^-11 relative rounding); mixing the two operand types is refused
+    on the host (a bf16 x fp16 MMA is an illegal instruction on sm_100a)."""
+    from cryovit_b200 import ops
+    from cryovit_b200._lib import CryovitB200Error
+    from cryovit_b200.vit import interleave_w12
+    a = _rand(M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b, g, x0 = _rand(N, seed=3), _rand(N, seed=4), _rand(M, N, seed=5)
+    y = a.float() @ w.float().t() + b
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    ops.linear_bias(a, w, b, out)
+    _close(out, y, atol=3e-3, rtol=1.5e-3, what="linear_bias fp16 -> fp16")
+    out_g = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear_bias(a, w, b, out_g, gelu=True)
+    _close(out_g, F.gelu(y), atol=2e-2, rtol=1e-2, what="linear_bias+gelu fp16 -> bf16")
+    if N % 256 == 0:  # SwiGLU tiles interleave 128 rows of w1 with 128 of w2
+        wi, bi = interleave_w12(w, b)
+        out_s = torch.full((M, N // 2), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.linear_swiglu(a, wi, bi, out_s)
+        _close(out_s, F.silu(y[:, :N // 2]) * y[:, N // 2:], atol=2e-2, rtol=1e-2, what="linear_swiglu fp16 -> bf16")
+    x = x0.clone()
+    ops.linear_scale_residual(a, w, b, g, x)
+    _close(x, x0 + g * y, atol=1e-3, rtol=1e-4, what="linear_scale_residual fp16")
+    with pytest.raises(CryovitB200Error):
+        ops.linear_bias(a, w.bfloat16(), b, out)
+
+
 def test_patch_embed_gemm(cuda_lib):
     from cryovit_b200 import ops
     B, Np, T, C, K = 3, 64, 69, 384, 256
@@ -128,6 +159,9 @@ def test_layernorm(cuda_lib, C):
     ops.layernorm(x, g, b, out, 1e-6)
     ref = F.layer_norm(x, (C,), g, b, 1e-6)
     _close(out, ref, atol=1e-2, rtol=1e-2, what="layernorm")
+    out16 = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    ops.layernorm(x, g, b, out16, 1e-6)
+    _close(out16, ref, atol=1e-3, rtol=1e-3, what="layernorm fp16")
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2), (3, 29, 2), (1, 128, 1), (1, 256, 2), (2, 261, 1),
@@ -144,6 +178,20 @@ def test_attention(cuda_lib, B, T, H, legacy, scale):
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
     _close(out, ref, atol=2e-2 * scale, rtol=2e-2, what=f"attention legacy={legacy}")
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (3, 29, 2), (2, 261, 1), (16, 300, 8)])
+@pytest.mark.parametrize("scale", [1.0, 6.0])
+def test_attention_fp16(cuda_lib, B, T, H, scale):
+    """Same kernel with fp16 q/k/v, probabilities and output; the tolerance is 4x tighter than the bf16 one."""
+    from cryovit_b200 import ops
+    C = H * 64
+    qkv = (_rand(B * T, 3 * C, seed=1) * scale).half()
+    out = torch.full((B * T, C), float("nan"), device=DEV, dtype=torch.float16)
+    ops.attention(qkv, out, B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
+    _close(out, ref, atol=5e-3 * scale, rtol=5e-3, what="attention fp16")
 
 
 @pytest.mark.parametrize("D,H,W,u8", [(3, 64, 96, True), (2, 50, 70, True), (2, 64, 64, False)])

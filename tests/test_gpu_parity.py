@@ -95,20 +95,29 @@ def vitg_sd():
     return random_state_dict(CONFIGS["dinov2_vitg14_reg"], seed=0)
 
 
-def test_vitg_one_slice_vs_oracle(cuda_lib, vitg_sd):
-    """The headline model (ViT-g/14-reg4, 40 blocks, LayerScale 1.0 random init: the worst case for bf16 error
-    accumulation) on one 448x448 slice against the fp32 oracle evaluated on the host cores."""
-    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200
+@pytest.fixture(scope="module")
+def vitg_oracle_slice(vitg_sd):
+    from cryovit_b200.vit import CONFIGS
     from oracle import dinov2 as odino
 
-    cfg = CONFIGS["dinov2_vitg14_reg"]
     x = torch.rand(1, 3, 448, 448, generator=torch.Generator().manual_seed(1))
-    model = DinoVisionTransformerB200(cfg).load_state_dict(vitg_sd).cuda()
+    return x, odino.forward_features(vitg_sd, x, CONFIGS["dinov2_vitg14_reg"].num_heads)["x_norm_patchtokens"]
+
+
+@pytest.mark.parametrize("operands", ["fp16", "bf16"])
+def test_vitg_one_slice_vs_oracle(cuda_lib, vitg_sd, vitg_oracle_slice, operands):
+    """The headline model (ViT-g/14-reg4, 40 blocks, LayerScale 1.0 random init: the worst case for 16-bit error
+    accumulation) on one 448x448 slice against the fp32 oracle evaluated on the host cores: the default operand format
+    (fp16 for the bounded operands, bf16 for the FFN hidden) and the all-bf16 alternative, both within the tolerance."""
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200
+
+    cfg = CONFIGS["dinov2_vitg14_reg"]
+    x, ref = vitg_oracle_slice
+    model = DinoVisionTransformerB200(cfg, torch.float16 if operands == "fp16" else torch.bfloat16).load_state_dict(vitg_sd).cuda()
     got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
     del model
     torch.cuda.empty_cache()
-    ref = odino.forward_features(vitg_sd, x, cfg.num_heads)["x_norm_patchtokens"]
-    _check(got, ref, "ViT-g one slice vs oracle")
+    _check(got, ref, f"ViT-g one slice vs oracle ({operands} operands)")
 
 
 def test_vitg_full_size_tomogram_properties(cuda_lib, vitg_sd):
