@@ -258,3 +258,23 @@ def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path)
         pred = hdf.read_tomogram(tmp_path / "exp" / "predictions" / "multi_cryovit_mito" / s / f"{s}0.hdf")
         assert sorted(pred) == ["data", "mito", "mito_preds"] and pred["mito_preds"].shape == (4, 48, 48)
         assert pred["mito_preds"].dtype == np.float32 and pred["data"].dtype == np.uint8
+
+
+def test_baseline_config1_end_to_end_with_a_fitted_head(cuda_lib):
+    """BASELINE config 1 in full (the block bench.py prints as ``config1``): ViT-S/14-reg4 features of a 32x448x448 uint8
+    phantom + the CryoVIT head, GPU path vs the CPU oracle end to end. The head is first fitted with the B200 training
+    path to the phantom's block mask (a random-init head predicts one class everywhere, which would make a mask
+    comparison vacuous); both sides load the same fitted weights. North-star tolerances: per-token feature relative
+    error <= 1e-2, cosine >= 0.999, mask voxel agreement >= 99.5 %."""
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+
+    r = bench.config1_line(torch)
+    print(f"\n[parity] config 1: feature rel-err {r['feature_rel_err_max']}, cosine {r['feature_cosine_min']}, mask agreement "
+          f"{r['mask_agreement']} (positive fraction {r['mask_positive_fraction']}), fit {r['head_fit']}")
+    assert r["feature_rel_err_max"] <= 1e-2 and r["feature_cosine_min"] >= 0.999
+    assert r["head_fit"]["dice_loss_last"] < 0.1 and r["head_fit"]["mask_vs_labels_agreement"] > 0.95, r["head_fit"]
+    assert 0.1 < r["mask_positive_fraction"] < 0.9, "the fitted mask is trivial"
+    assert r["mask_agreement"] >= 0.995, r
