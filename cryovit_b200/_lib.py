@@ -32,6 +32,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_linear_swiglu_bf16": [P, I64, P, P, P, I64, I64, I64, I64, P],
     "cvit_linear_scale_residual_f32": [P, I64, P, P, P, P, I64, I64, I64, I64, P],
     "cvit_linear_bias_fmt": [P, I64, P, P, P, I64, I64, I64, I64, I32, I32, P],
+    "cvit_linear_bias_cfirst_f16": [P, I64, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_linear_swiglu_fmt": [P, I64, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_linear_scale_residual_fmt": [P, I64, P, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],

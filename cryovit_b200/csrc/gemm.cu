@@ -140,6 +140,44 @@ static int gemm_rows(const void* A, int64_t lda, const void* B, GemmArgs args, i
   return CVIT_ERR_UNSUPPORTED;
 }
 
+// out[M,N] = At[K,M]^T x B[N,K]^T + bias (+ GELU): A is read from its TRANSPOSED storage (M contiguous) as an MN-major
+// operand. fp16 operands (the feature volume on disk is fp16), bf16 output.
+static int gemm_rows_mn(const void* At, int64_t ldat, const void* B, GemmArgs args, cudaStream_t stream) {
+  const int64_t M = args.M, N = args.N, K = args.K;
+  if (M <= 0 || N <= 0 || K <= 0) {
+    set_error("gemm_mn: non-positive dimension M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    return CVIT_ERR_INVALID;
+  }
+  if (!At || !B || !args.out || !aligned16(At) || !aligned16(B) || !aligned16(args.out) || (ldat % 8) != 0 || (K % 8) != 0 || K < 64) {
+    set_error("gemm_mn: null/unaligned operand (At,B,out need 16B alignment; ldat and K multiples of 8, K >= 64)");
+    return CVIT_ERR_INVALID;
+  }
+  const int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 0;
+  if (!bn) {
+    set_error("gemm_mn: N=%lld must be a multiple of 128", (long long)N);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  const int epi = EPI_BIAS_GELU, kspan = 128;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};
+    uint64_t strides[2] = {0, (uint64_t)ldat * 2};
+    uint32_t box[2] = {64u, 64u};  // 64 rows (128 bytes, contiguous) x 64 channels
+    int rc = encode_tmap(&tmA, TmapDtype::F16, 2, At, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  const bool pair = g_gemm_pair && bn == 256 && M > GEMM_BM;
+  int rc = make_tmap_rows(&tmB, B, N, K, K, pair ? bn / 2 : bn, kspan, true);
+  if (rc) return rc;
+  const int bm = pair ? 2 * GEMM_BM : GEMM_BM;
+  const int num_tiles = (int)(((M + bm - 1) / bm) * (N / bn));
+  if (pair) return launch_gemm<256, EPI_BIAS_GELU, AMODE_ROWS_MN, 128, true>(tmA, tmB, args, num_tiles, stream);
+  CVIT_GEMM_CASE(256, EPI_BIAS_GELU, AMODE_ROWS_MN, 128)
+  CVIT_GEMM_CASE(128, EPI_BIAS_GELU, AMODE_ROWS_MN, 128)
+  set_error("gemm_mn: no kernel instantiated for BN=%d", bn);
+  return CVIT_ERR_UNSUPPORTED;
+}
+
 // 3x3x3 depth-dilated "same" convolution over a channels-last bf16 volume, + bias + GELU.
 static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t stream) {
   const int D = args.D, H = args.H, W = args.W, Cin = args.K, Cout = args.N;
@@ -248,6 +286,16 @@ int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, cons
   a.bias = bias;
   a.n_valid = (int)n_valid;
   return gemm_rows(A, lda, W, a, EPI_BIAS, (cudaStream_t)stream);
+}
+
+int cvit_linear_bias_cfirst_f16(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                int64_t M, int64_t N, int64_t K, int gelu, void* stream) {
+  if (!bias) { set_error("linear_bias_cfirst: bias is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(M, N, K, out, ldo);
+  a.bias = bias;
+  a.act = gelu ? 1 : 0;
+  a.fmt = GEMM_FMT_OPERANDS_F16;
+  return gemm_rows_mn(At, ldat, W, a, (cudaStream_t)stream);
 }
 
 int cvit_linear_swiglu_fmt(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,

@@ -17,6 +17,9 @@
 //               the K loop walks (tap, channel-chunk); each A tile is one 4-D TMA box shifted by the
 //               tap offset, and TMA's out-of-bounds zero fill IS the zero padding (no im2col, no halo
 //               staging code). Taps whose depth offset falls outside [0,D) are skipped outright.
+//   AMODE_ROWS_MN  the same [M,K] matrix stored TRANSPOSED in memory ([K,M], M contiguous): the head's projection reads
+//               the on-disk feature layout (C, D*h*w) directly as an MN-major A operand (two 64-row x 64-channel
+//               128B-swizzled boxes per stage), so no channels-last copy of the features is ever written.
 //
 // Epilogues (what the reference computes around each GEMM):
 //   EPI_BIAS            out_bf16 = acc + bias                               (qkv)
@@ -32,7 +35,7 @@
 namespace cvit {
 
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_SWIGLU = 2, EPI_SCALE_RESIDUAL = 3, EPI_PATCH_EMBED = 4, EPI_CONVT_GELU = 5 };
-enum { AMODE_ROWS = 0, AMODE_CONV3 = 1 };
+enum { AMODE_ROWS = 0, AMODE_CONV3 = 1, AMODE_ROWS_MN = 2 };
 
 struct GemmArgs {
   int M, N, K;        // rows, output columns, reduction length (per tap for AMODE_CONV3)
@@ -131,8 +134,9 @@ template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false, int SUB = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
-  static_assert(!PAIR || AMODE == AMODE_ROWS, "CTA pairs are implemented for the plain-rows GEMM only");
+  static_assert(!PAIR || AMODE != AMODE_CONV3, "CTA pairs are implemented for the plain-rows GEMMs only");
   static_assert(SUB == 1 || (AMODE == AMODE_ROWS && !PAIR), "tall tiles are implemented for the single-CTA plain-rows GEMM only");
+  static_assert(AMODE != AMODE_ROWS_MN || KSPAN == 128, "the MN-major A operand is staged in 128-byte swizzled rows");
   using Cfg = GemmCfg<BN, KSPAN, PAIR, SUB>;
   constexpr int TILE_M = (PAIR ? 2 : SUB) * GEMM_BM;  // output rows per tile (per CTA pair with PAIR)
   constexpr int KC = KSPAN / 2;        // bf16 elements of K per stage
@@ -217,6 +221,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // both producers report their bytes to the LEADER's full barrier, which expects the pair's total
               if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * Cfg::STAGE_BYTES);
               const uint32_t lead_full = mapa_cluster(bar_full + 8 * s, 0);
+              if (AMODE == AMODE_ROWS_MN) {  // two boxes of 64 rows (inner, contiguous) x KC channels
+                tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, lead_full, t.m0, kc * KC);
+                tma_load_2d_pair(sA + s * Cfg::A_BYTES + Cfg::A_BYTES / 2, &tmA, lead_full, t.m0 + 64, kc * KC);
+              } else
               tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, lead_full, kc * KC, t.m0);
               tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, lead_full, kc * KC, t.n0 + (int)rank * (BN / 2));
               if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -226,6 +234,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (AMODE == AMODE_CONV3) {
               tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kc * KC, dx, dy, dz);
               tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, tap * args.N + t.n0);
+            } else if (AMODE == AMODE_ROWS_MN) {
+              tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, t.m0, kc * KC);
+              tma_load_2d(sA + s * Cfg::A_BYTES + Cfg::A_BYTES / 2, &tmA, bar_full + 8 * s, t.m0 + 64, kc * KC);
+              tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kc * KC, t.n0);
             } else {
 #pragma unroll
               for (int sub = 0; sub < SUB; ++sub)  // blocks past the last row are zero-filled by TMA and never stored
@@ -244,7 +256,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // region cost ~90 cycles per tcgen05.mma: every operand went through R2UR and a per-lane ELECT loop.)
     {
       const uint32_t idesc = umma_idesc_f16_f32(PAIR ? 2 * GEMM_BM : GEMM_BM, BN) |
-                             ((args.fmt & GEMM_FMT_OPERANDS_F16) ? 0u : UMMA_IDESC_BF16_BITS);
+                             ((args.fmt & GEMM_FMT_OPERANDS_F16) ? 0u : UMMA_IDESC_BF16_BITS) |
+                             (AMODE == AMODE_ROWS_MN ? (1u << 15) : 0u);  // bit 15: A is MN-major
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -269,12 +282,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint64_t bdesc = umma_smem_desc_kmajor<KSPAN>(sB + s * Cfg::B_BYTES);
 #pragma unroll
               for (int sub = 0; sub < SUB; ++sub) {
-                const uint64_t adesc = umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES + sub * Cfg::A_BLOCK_BYTES);
+                // K-major A: 16 elements of K = 32 bytes inside the swizzle span (+2 in 16-byte units). MN-major A: 16 K
+                // rows of 128 bytes (+128); the two 64-row blocks of the tile are LBO = A_BYTES / 2 apart.
+                const uint64_t adesc = AMODE == AMODE_ROWS_MN
+                                           ? umma_smem_desc_mnmajor_sw128(sA + s * Cfg::A_BYTES, Cfg::A_BYTES / 2)
+                                           : umma_smem_desc_kmajor<KSPAN>(sA + s * Cfg::A_BYTES + sub * Cfg::A_BLOCK_BYTES);
+                constexpr int ASTEP = AMODE == AMODE_ROWS_MN ? 128 : 2;
 #pragma unroll
                 for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-                  // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
-                  if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
-                  else umma_bf16(d_tmem + sub * Cfg::ACC_STRIDE, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                  // B: advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in 16-byte units
+                  if (PAIR) umma_bf16_pair(d_tmem, adesc + ASTEP * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
+                  else umma_bf16(d_tmem + sub * Cfg::ACC_STRIDE, adesc + ASTEP * k, bdesc + 2 * k, idesc, accumulate | (k > 0));
                 }
               }
               // smem slot reusable once these MMAs retire (in both CTAs of a pair)

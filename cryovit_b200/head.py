@@ -123,6 +123,9 @@ class CryoVITHeadB200:
         bf = lambda t: t.to(dev).to(torch.bfloat16).contiguous()
         f32 = lambda t: t.to(dev).float().contiguous()
         w = {"proj_w": bf(sd["layers.0.weight"].reshape(1024, self.in_channels)), "proj_b": f32(sd["layers.0.bias"])}
+        pw = sd["layers.0.weight"].reshape(1024, self.in_channels).float()
+        if float(pw.abs().max()) < 6.0e4:  # fp16 image of the projection for the transposed-A kernel (fp16 features)
+            w["proj_w16"] = pw.to(self.device).to(torch.float16).contiguous()
         blocks = []
         for bi, (c1, c2, c3, d1, d2) in enumerate(BLOCKS):
             p = f"layers.{bi + 2}.layers."
@@ -173,11 +176,17 @@ class CryoVITHeadB200:
             raise CryovitB200Error(f"expected features (C={self.in_channels}, D, h, w), got {tuple(features.shape)}")
         C, D, h, w = features.shape
         w_ = self._w
-        x = self._buf("ping", D * h * w * max(C, 1024)).narrow(0, 0, D * h * w * C).view(D, h, w, C)
-        ops.features_to_ndhwc(features.contiguous(), x)
         y = self._buf("pong", D * h * w * 1024).view(D * h * w, 1024)
-        ops.linear_bias(x.view(D * h * w, C), w_["proj_w"], w_["proj_b"], y, gelu=True)
-        self.launches += 2
+        vox0 = D * h * w
+        if features.dtype == torch.float16 and "proj_w16" in w_ and vox0 % 8 == 0 and C % 8 == 0 and C >= 64:
+            # the on-disk layout (C, D*h*w) IS the A operand (MN-major): no channels-last copy of the features
+            ops.linear_bias_cfirst(features.contiguous().view(C, vox0), w_["proj_w16"], w_["proj_b"], y, gelu=True)
+            self.launches += 1
+        else:
+            x = self._buf("ping", vox0 * max(C, 1024)).narrow(0, 0, vox0 * C).view(D, h, w, C)
+            ops.features_to_ndhwc(features.contiguous(), x)
+            ops.linear_bias(x.view(vox0, C), w_["proj_w"], w_["proj_b"], y, gelu=True)
+            self.launches += 2
         cur, H, W = y.view(D, h, w, 1024), h, w
         stats = self._buf("gn_stats", 256, torch.float32)
         names = ["ping", "pong"]

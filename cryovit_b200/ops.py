@@ -101,6 +101,14 @@ def linear_bias(a, w, bias, out, gelu: bool = False) -> None:
               _chk(out, out.dtype, "out"), out.stride(0), M, N, K, int(gelu), fmt, _stream())
 
 
+def linear_bias_cfirst(at, w, bias, out, gelu: bool = False) -> None:
+    """out bf16 [M, N] = at[K, M]^T @ w[N, K]^T + bias (+ GELU); at and w fp16, at read as an MN-major operand."""
+    K, M = at.shape
+    N = w.shape[0]
+    _lib.call("cvit_linear_bias_cfirst_f16", _chk(at, F16, "at"), at.stride(0), _chk(w, F16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, N, K, int(gelu), _stream())
+
+
 def linear_swiglu(a, w12i, bias12i, out) -> None:
     M, K = a.shape
     N2 = w12i.shape[0]

@@ -127,6 +127,15 @@ int cvit_linear_swiglu_fmt(const void* A, int64_t lda, const void* W12i, const f
 int cvit_linear_scale_residual_fmt(const void* A, int64_t lda, const void* W, const float* bias, const float* gamma,
                                    float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, int fmt, void* stream);
 
+/* out_bf16[M, N] = At[K, M]^T @ W[N, K]^T + bias (+ exact-erf GELU): the same linear with A read from its TRANSPOSED
+ * storage (row k of At holds the M values of input channel k, M contiguous, ldat elements apart) as an MN-major
+ * tensor-core operand.  At and W are IEEE fp16.  Replaces, in one kernel, the head's input permute
+ * (models/cryovit.py:38-41, datamodules/utils.py collate: (C, D, h, w) features -> channels-last) AND layers[0]
+ * Conv3d 1x1x1 + GELU (models/cryovit.py:19-22): the on-disk fp16 feature volume is the A operand as it lies, no
+ * channels-last copy is written.  M, ldat multiples of 8; K >= 64; N multiple of 128. */
+int cvit_linear_bias_cfirst_f16(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                int64_t M, int64_t N, int64_t K, int gelu, void* stream);
+
 /* Multi-head self-attention of every slice: out[b, t, h*64 + d] = softmax(q k^T / 8) v with
  * q,k,v = qkv[b, t, {0,1,2}, h, :].  Replaces MemEffAttention / xformers memory_efficient_attention
  * (upstream attention.py; HF:202-256).  qkv bf16 [n_slices * tokens, 3 * heads * 64]; head_dim must be 64. */

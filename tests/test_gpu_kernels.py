@@ -136,6 +136,24 @@ def test_linears_fp16_operands(cuda_lib, M, N, K):
         ops.linear_bias(a, w.bfloat16(), b, out)
 
 
+@pytest.mark.parametrize("K,M,N", [(384, 4104, 1024), (1536, 200, 1024), (1536, 136, 1024), (128, 64, 256), (1536, 16384, 1024), (192, 520, 128)])
+@pytest.mark.parametrize("gelu", [True, False])
+def test_linear_bias_cfirst(cuda_lib, K, M, N, gelu):
+    """The head's projection with A read from its transposed storage (the (C, D*h*w) feature layout) as an MN-major
+    tensor-core operand: row counts that are not multiples of the 64-row TMA box or of the 256-row pair tile, K not a
+    multiple of the 64-channel stage (192: the last stage is half zero fill)."""
+    from cryovit_b200 import ops
+    at = _rand(K, M, scale=0.7, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear_bias_cfirst(at, w, b, out, gelu=gelu)
+    ref = at.float().t() @ w.float().t() + b
+    if gelu:
+        ref = F.gelu(ref)
+    _close(out, ref, atol=2e-2, rtol=1e-2, what=f"linear_bias_cfirst K={K} M={M} N={N}")
+
+
 def test_patch_embed_gemm(cuda_lib):
     from cryovit_b200 import ops
     B, Np, T, C, K = 3, 64, 69, 384, 256

@@ -51,6 +51,25 @@ def test_forward_features_vs_oracle_and_golden(cuda_lib, name, shape):
     _check(sub, torch.from_numpy(hf[f"dinov2_{tag}_hf_patchtokens"]), f"{name} patch tokens vs transformers golden")
 
 
+@pytest.mark.parametrize("dim,heads,ffn,hidden", [(768, 12, "mlp", 3072), (1024, 16, "mlp", 4096), (1536, 24, "swiglu", 4096)])
+@pytest.mark.parametrize("operands", ["bf16", "fp16"])
+def test_every_dinov2_width_vs_oracle(cuda_lib, dim, heads, ffn, hidden, operands):
+    """The widths of the other hub entries the reference's ``dino_model`` config can name (ViT-B/14: 768 x 12 heads,
+    ViT-L/14: 1024 x 16 heads, ViT-g/14: 1536 x 24 heads with SwiGLU), three blocks each, ragged batch of 3 slices on a
+    non-square 4 x 6 patch grid, both operand formats."""
+    from cryovit_b200.vit import DinoVisionTransformerB200, ViTConfig, random_state_dict
+    from oracle import dinov2 as odino
+
+    cfg = ViTConfig(f"w{dim}", dim, 3, heads, ffn, hidden)
+    sd = random_state_dict(cfg, seed=2)
+    x = torch.rand(3, 3, 56, 84, generator=torch.Generator().manual_seed(3))
+    model = DinoVisionTransformerB200(cfg, torch.float16 if operands == "fp16" else torch.bfloat16).load_state_dict(sd).cuda()
+    got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
+    ref = odino.forward_features(sd, x, cfg.num_heads)["x_norm_patchtokens"]
+    assert got.shape == ref.shape == (3, 24, dim)
+    _check(got, ref, f"width {dim} ({ffn}, {operands} operands) vs oracle")
+
+
 def test_fused_extract_matches_reference_pipeline(cuda_lib):
     """u8 tomogram -> (fused GPU preproc + ViT-S + write-out) vs oracle preproc -> oracle ViT -> reference layout.
     Includes a non-multiple-of-16 plane (edge-pad path) and a ragged last batch."""

@@ -16,7 +16,7 @@ head = CryoVITHeadB200(C).load_state_dict(ohead.random_state_dict(C, seed=0)).cu
 feats = (torch.randn(C, D, h, w, device="cuda") * 0.5).half()
 
 records = {}
-names = ["features_to_ndhwc", "linear_bias", "groupnorm_ndhwc", "conv3d_dilated", "conv3d_halo", "convT_1x2x2", "head_out_conv", "conv3d_wpack8_gelu", "conv3d_wpack8_final"]
+names = ["features_to_ndhwc", "linear_bias", "linear_bias_cfirst", "groupnorm_ndhwc", "conv3d_dilated", "conv3d_halo", "convT_1x2x2", "head_out_conv", "conv3d_wpack8_gelu", "conv3d_wpack8_final"]
 orig = {n: getattr(ops, n) for n in names}
 active = False
 seq = []
