@@ -206,14 +206,18 @@ class CryoVITHeadTrainerB200:
         self.g[key_w].copy_(dw.view(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
         self.launches += 7
 
-    def _wgrad_rows(self, x_rows, dz_rows):
-        """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions)."""
-        R, N = x_rows.shape
-        M = dz_rows.shape[1]
+    def _wgrad_rows(self, x_rows, dz_rows, xt=None):
+        """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions). ``xt``:
+        x already channels-first, bf16 [N, R] with R a multiple of 8 (then x_rows is not read)."""
+        R, M = dz_rows.shape
         pitch = (R + 7) // 8 * 8
-        xt = self._buf("rows_xt", (N, pitch))
         dzt = self._buf("rows_dzt", (M, pitch))
-        T.to_cfirst_padded(x_rows.view(1, 1, R, N), xt, 0, 0, 0)  # rows along the innermost (W) axis: pitch = roundup8(R)
+        if xt is None:
+            N = x_rows.shape[1]
+            xt = self._buf("rows_xt", (N, pitch))
+            T.to_cfirst_padded(x_rows.view(1, 1, R, N), xt, 0, 0, 0)  # rows along the innermost (W) axis: pitch = roundup8(R)
+        else:
+            N = xt.shape[0]
         T.to_cfirst_padded(dz_rows.view(1, 1, R, M), dzt, 0, 0, 0)
         dw = torch.zeros(1, M, N, device=self.device, dtype=F32)
         T.wgrad_splitk(dzt, xt, dw, torch.zeros(1, dtype=torch.int32, device=self.device), pitch)
@@ -231,11 +235,20 @@ class CryoVITHeadTrainerB200:
         vox = D * h * w
         self._pk_refresh()
         # ---------------- forward, keeping what the backward needs
-        x0 = self._buf("x0", (D, h, w, C))
-        ops.features_to_ndhwc(features.to(dev).contiguous(), x0)
         z_proj, a_proj = self._buf("z_proj", (vox, 1024)), self._buf("a_proj", (D, h, w, 1024))
-        ops.linear_bias(x0.view(vox, C), self._pk("proj/f", "layers.0.weight", lambda w_: w_.reshape(1024, C)), p["layers.0.bias"],
-                        z_proj, gelu=False)
+        feats = features.to(dev).contiguous()
+        # fp16 feature volumes whose row pitch TMA accepts: the (C, vox) layout is the projection's A operand as it lies
+        # (MN-major) and, cast to bf16, already the channels-first operand of its weight gradient -- no transposes
+        cfirst = feats.dtype == torch.float16 and vox % 8 == 0 and C % 8 == 0 and C >= 64
+        x0 = None
+        if cfirst:
+            w16 = p["layers.0.weight"].reshape(1024, C).clamp(-6.0e4, 6.0e4).to(torch.float16)
+            ops.linear_bias_cfirst(feats.view(C, vox), w16, p["layers.0.bias"], z_proj, gelu=False)
+        else:
+            x0 = self._buf("x0", (D, h, w, C))
+            ops.features_to_ndhwc(feats, x0)
+            ops.linear_bias(x0.view(vox, C), self._pk("proj/f", "layers.0.weight", lambda w_: w_.reshape(1024, C)), p["layers.0.bias"],
+                            z_proj, gelu=False)
         T.gelu_fwd(z_proj, a_proj.view(vox, 1024))
         self.launches += 3
         saved = []
@@ -341,7 +354,11 @@ class CryoVITHeadTrainerB200:
         # projection (1x1x1): only the weight / bias gradient (the features are data)
         dzp = self._buf("dz_proj", (vox, 1024))
         self._gelu_bwd_bias(dcur.view(vox, 1024), z_proj, dzp, "layers.0.bias")
-        g["layers.0.weight"].copy_(self._wgrad_rows(x0.view(vox, C), dzp).view(1024, C, 1, 1, 1))
+        if cfirst:
+            dw0 = self._wgrad_rows(None, dzp, xt=feats.view(C, vox).to(BF16))
+        else:
+            dw0 = self._wgrad_rows(x0.view(vox, C), dzp)
+        g["layers.0.weight"].copy_(dw0.view(1024, C, 1, 1, 1))
         self.launches += 2
         return loss
 
