@@ -37,6 +37,10 @@ def _dino_features(data: torch.Tensor, model: DinoVisionTransformerB200, batch_s
     if data.dim() != 4 or data.shape[1] != 3:
         raise CryovitB200Error(f"expected [D, 3, H, W], got {tuple(data.shape)}")
     D = data.shape[0]
+    if D == 0:  # the reference concatenates an empty list of batches here (run/dino_features.py:64)
+        raise ValueError("need at least one array to concatenate")
+    if data.shape[-2] % 14 or data.shape[-1] % 14:
+        raise CryovitB200Error(f"slice size {tuple(data.shape[-2:])} is not a multiple of the 14-pixel patch")
     w, h = np.array(data.shape[-2:]) // 14  # the reference's (confusingly named) rows, cols
     feats = _features_buffer(model, D, int(w), int(h))
     src = data if data.is_cuda else data.pin_memory()

@@ -214,3 +214,24 @@ def test_wpack_weight_image_is_the_banded_matrix():
             want = w[:, :, 2 - blk, kh, kw] if 0 <= kw <= 2 else torch.zeros(cout, 8)
             assert torch.equal(img[kh, st, c, blk, jo], want), (cout, P, kh, st, c, blk, jo)
         assert int((img != 0).sum()) == 27 * cout * 8 * P  # every tap appears once per packed output voxel
+
+
+def test_dino_features_argument_errors_match_the_reference():
+    """Host-side argument handling of the extractor seam (run/dino_features.py:31-64), checked before any GPU work: an
+    empty tomogram fails like the reference's ``np.concatenate([])``, a zero batch size like its ``range(0, D, 0)``,
+    and shapes the 14-pixel patch grid cannot tile are refused."""
+    import torch
+
+    from cryovit_b200._lib import CryovitB200Error
+    from cryovit_b200.extract import _dino_features
+    from cryovit_b200.vit import build_model
+
+    m = build_model("dinov2_vits14_reg")
+    with pytest.raises(ValueError, match="at least one array"):
+        _dino_features(torch.zeros(0, 3, 28, 28), m, 4)
+    with pytest.raises(CryovitB200Error):
+        _dino_features(torch.zeros(2, 3, 30, 28), m, 4)
+    with pytest.raises(CryovitB200Error):
+        _dino_features(torch.zeros(2, 1, 28, 28), m, 4)
+    with pytest.raises(CryovitB200Error):
+        _dino_features(torch.zeros(2, 3, 28, 28), object(), 4)
