@@ -147,9 +147,33 @@ def head_voxels_per_s(torch, dist=None, world: int = 1, steps: int = 3) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     vox = D * H * W
+    head_voxels_per_s.head = head  # reused by pipeline_line
     return {"value": round(world * vox / ms * 1e3, 0), "unit": "voxels/s (all GPUs)", "ms_per_volume": round(ms, 3),
             "tflops_per_gpu": round(94864 * vox / ms / 1e9, 1), "launches_per_volume": (head.launches - l0) // steps,
             "workload": f"CryoVIT head, one fp16 (1536,{D},32,32) feature volume per GPU -> ({D},{H},{W}) probabilities, weights random"}
+
+
+def pipeline_line(torch, dist, world: int, vit, head, tomo_np, runs: int = 2) -> dict:
+    """Tomogram in, mask out (the reference's dino_features + infer_model pair without the feature
+    file in between): host uint8 (128,512,512) tomogram -> ViT-g features (stay in HBM) -> head -> uint8 mask on the
+    host, through the public ``cryovit_b200.pipeline.segment_tomogram``; wall clock around the blocking call."""
+    from cryovit_b200.pipeline import segment_tomogram
+
+    segment_tomogram(tomo_np, vit, head, BATCH)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(runs):
+        mask = segment_tomogram(tomo_np, vit, head, BATCH)
+    sec = (time.perf_counter() - t0) / runs
+    assert mask.shape == tomo_np.shape and mask.dtype.name == "uint8"
+    if world > 1:
+        t = torch.tensor([sec], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return {"value": round(world * tomo_np.shape[0] / sec, 2), "unit": "slices/s (all GPUs), tomogram -> mask, host to host",
+            "ms_per_tomogram": round(1e3 * sec, 2), "h2d_bytes_per_tomogram": int(tomo_np.size),
+            "d2h_bytes_per_tomogram": int(mask.size),
+            "workload": f"uint8 ({D},{H},{W}) tomogram -> ViT-g/14 features in HBM -> CryoVIT head -> uint8 mask, one tomogram per GPU"}
 
 
 def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
@@ -492,6 +516,9 @@ def run_b200(args) -> None:
     del stream
     torch.cuda.empty_cache()
     head_line = head_voxels_per_s(torch, dist, world)
+    pipe_line = pipeline_line(torch, dist, world, model, head_voxels_per_s.head, tomo_np)
+    del head_voxels_per_s.head
+    torch.cuda.empty_cache()
     train_line = head_train_voxels_per_s(torch, dist, world)
     if rank != 0:
         if world > 1:
@@ -538,6 +565,7 @@ def run_b200(args) -> None:
         "gpu_launches": launches,
     }
     line["head"] = head_line
+    line["pipeline"] = pipe_line
     line["head_train"] = train_line
     del model
     torch.cuda.empty_cache()
