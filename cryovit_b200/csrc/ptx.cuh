@@ -317,12 +317,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 11 FMA-pipe instructions
-// and two MUFU (rcp, ex2) instead of erff's two-branch polynomial. |gelu error| <= 5e-7 absolute over the whole
-// range (checked against float64 in tests/test_oracle.py::test_fast_gelu_formula); every consumer rounds the result
-// to bf16 (relative 4e-3) or feeds a fp32 epilogue of a bf16 GEMM, so the two are indistinguishable downstream. The
-// head's narrow layers are bound by exactly this epilogue math (268 M activations per layer at 512 x 512).
-__device__ __forceinline__ float gelu_erf(float x) {
+// GELU(erf) = x Phi(x). Two evaluations:
+//
+// gelu_erf_as (the first one used here; kept as the accuracy reference of tests/test_oracle.py): erf from
+// Abramowitz-Stegun 7.1.26, 11 FMA-pipe instructions and two MUFU (rcp, ex2), |error| <= 5e-7 absolute.
+//
+// gelu_erf (what every epilogue calls): Phi(x) = sigmoid(x q(x^2)) with q an even cubic fitted to logit(Phi(x)) / x --
+// the "tanh approximation" 0.5 (1 + tanh(u)) = sigmoid(2u) with one more term and re-fitted coefficients. 7 FMA-pipe
+// instructions and the same two MUFU: the head's narrow layers and transposed convolutions are bound by exactly this
+// epilogue math (268 M activations per layer at 512 x 512, ~29 instructions per output before). |error| <= 2.6e-5
+// absolute over the whole real line and <= 2.1e-4 relative wherever |gelu| >= 0.1 (tests/test_oracle.py::
+// test_fast_gelu_formula): a ninth of the 2^-9 rounding step of the bf16 value every consumer stores.
+// x^2 is clamped at 36 (the cubic turns over near x^2 = 52); beyond |x| = 6, sigmoid(3.35 |x|) is 0 or 1 to 2e-9.
+__device__ __forceinline__ float gelu_erf_as(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
@@ -334,6 +341,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float h = 0.5f * x;
   return fmaf(h, copysignf(erf_abs, x), h);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float x2 = fminf(x * x, 36.0f);
+  float q = fmaf(7.030335764e-4f * L2E, x2, -7.401129204e-2f * L2E);   // -log2(e) q(x^2)
+  q = fmaf(q, x2, -1.5950157686f * L2E);
+  const float e = ex2_approx(q * x);        // exp(-x q): inf for very negative x, then rcp(inf) = 0
+  return x * rcp_approx(1.0f + e);
 }
 // x * sigmoid(x) with ex2.approx + rcp.approx (both ~2^-22 relative error): 4 instructions instead of an IEEE division
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
