@@ -92,13 +92,13 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
-# kernels at the same shapes (profiles/r01_ncu_full_v8_hot_kernels.json); bench.py itself never runs under ncu.
+# kernels at the same shapes (profiles/r01_ncu_full_v14_hot_kernels.json); bench.py itself never runs under ncu.
 NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu": "w12_swiglu", "layernorm": "layernorm",
             "proj_scale_residual": "proj_gemm", "w3_scale_residual": "w3_gemm"}
 
 
 def ncu_traffic(kernel: str) -> float | None:
-    p = ROOT / "profiles" / "r01_ncu_full_v8_hot_kernels.json"
+    p = ROOT / "profiles" / "r01_ncu_full_v14_hot_kernels.json"
     if not p.exists() or kernel not in NCU_KEYS:
         return None
     for d in json.loads(p.read_text()):
@@ -545,7 +545,7 @@ def run_b200(args) -> None:
                 "frac": round(tf / peak, 4), "peak_burst": peaks.get("bf16_tflops"),
                 "frac_burst": round(tf / peaks["bf16_tflops"], 4) if peaks.get("bf16_tflops") else None,
                 "traffic": ncu_traffic(top),
-                "traffic_source": "profiles/r01_ncu_full_v8_hot_kernels.json (ncu --set full, one launch, same shapes)",
+                "traffic_source": "profiles/r01_ncu_full_v14_hot_kernels.json (ncu --set full, one launch, same shapes)",
                 "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
                 "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
     kernels = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
