@@ -229,7 +229,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
             for (int i = 0; i < 4; ++i) {
               float a = __uint_as_float(v[c + 2 * i]) + __ldg(args.bias + c + 2 * i);
               float b = __uint_as_float(v[c + 2 * i + 1]) + __ldg(args.bias + c + 2 * i + 1);
-              if (args.act) { a = gelu_erf(a); b = gelu_erf(b); }
+              if (args.act) gelu_erf2(a, b);
               pk[i] = pack_bf16x2(a, b);
             }
             *reinterpret_cast<uint4*>(o + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

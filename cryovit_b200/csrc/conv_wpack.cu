@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
             for (int k = 0; k < 4; ++k) {
               float a = __uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k];
               float b = __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1];
-              if (args.act) { a = gelu_erf(a); b = gelu_erf(b); }
+              if (args.act) gelu_erf2(a, b);
               pk[k] = pack_bf16x2(a, b);
             }
             *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -398,7 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
-            if (EPI == EPI_BIAS_GELU && args.act) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
+            if (EPI == EPI_BIAS_GELU && args.act) { gelu_erf2(o0, o1); gelu_erf2(o2, o3); }
             if (EPI == EPI_BIAS_SWIGLU) {
               o0 = silu(o0) * (ys[it].x + b4b.x);
               o1 = silu(o1) * (ys[it].y + b4b.y);
@@ -461,7 +461,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (grow < 0) continue;
             const size_t orow = ((size_t)(2 * dh + si) * (2 * args.W)) + 2 * w + sj;
             float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
-            if (args.act) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
+            if (args.act) { gelu_erf2(o0, o1); gelu_erf2(o2, o3); }
             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + orow * args.c3 + co) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
           }
         }

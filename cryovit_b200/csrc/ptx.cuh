@@ -350,6 +350,38 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = ex2_approx(q * x);        // exp(-x q): inf for very negative x, then rcp(inf) = 0
   return x * rcp_approx(1.0f + e);
 }
+// The same for two values at once on the packed fp32 pipe (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot per PAIR);
+// the clamp and the two MUFU stay scalar. Bit-identical to two gelu_erf calls (same roundings in the same order).
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+  constexpr float L2E = 1.4426950408889634f;
+  uint64_t x, x2, q, t;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(x2) : "l"(x));
+  float x2a, x2b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x2a), "=f"(x2b) : "l"(x2));
+  x2a = fminf(x2a, 36.0f);
+  x2b = fminf(x2b, 36.0f);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(x2a), "f"(x2b));
+  uint64_t c2, c1, c0, one;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(7.030335764e-4f * L2E));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(-7.401129204e-2f * L2E));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(-1.5950157686f * L2E));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(one) : "f"(1.0f));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(c2), "l"(x2), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(q), "l"(x2), "l"(c0));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(q), "l"(x));
+  float ta, tb;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ta), "=f"(tb) : "l"(t));
+  uint64_t e;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(e) : "f"(ex2_approx(ta)), "f"(ex2_approx(tb)));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(e) : "l"(e), "l"(one));
+  float da, db;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(da), "=f"(db) : "l"(e));
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(rcp_approx(da)), "f"(rcp_approx(db)));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(r));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
 // x * sigmoid(x) with ex2.approx + rcp.approx (both ~2^-22 relative error): 4 instructions instead of an IEEE division
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
