@@ -444,26 +444,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // column n = (i*2 + j) * c3 + co ; voxel grow = (d*H + h)*W + w -> out[d, 2h+i, 2w+j, co]
           const int ij = ncol / args.c3, co = ncol - ij * args.c3;
           const int si = ij >> 1, sj = ij & 1;
-          // rows of a chunk are 4 voxels apart (plain-rows GEMM): one division per chunk, then (w, dh) are stepped
-          int w = 0, dh = 0;
+          // rows of a chunk are 4 voxels apart (plain-rows GEMM): one division per chunk, then (w, dh) are stepped.
+          // The loops below are kept free of branches (predicated selects, activation switch hoisted, stores predicated)
+          // so that the eight rows' GELU chains interleave: with two epilogue warps per scheduler the kernel waited on
+          // fixed-latency dependencies (ncu: 38 % stall_wait, 8 % branch resolving with a branchy row loop).
+          size_t off_it[8];
           {
             const int g0 = t.m0 + (SUB == 1 ? 0 : sub * GEMM_BM) + q * 32 + rsub;
-            dh = g0 / args.W;  // dh = d*H + h
-            w = g0 - dh * args.W;
+            int dh = g0 / args.W;  // dh = d*H + h
+            int w = g0 - dh * args.W;
+            const int W2 = 2 * args.W;
+            if (args.W >= 4) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                if (it > 0) {
+                  w += 4;
+                  const int wrap = w >= args.W ? 1 : 0;
+                  w -= wrap * args.W;
+                  dh += wrap;
+                }
+                off_it[it] = ((size_t)(2 * dh + si) * W2 + 2 * w + sj) * args.c3 + co;
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                if (it > 0) {
+                  w += 4;
+                  while (w >= args.W) { w -= args.W; ++dh; }
+                }
+                off_it[it] = ((size_t)(2 * dh + si) * W2 + 2 * w + sj) * args.c3 + co;
+              }
+            }
+          }
+          uint2 pk[8];
+          if (args.act) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
+              gelu_erf2(o0, o1);
+              gelu_erf2(o2, o3);
+              pk[it] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              pk[it] = make_uint2(pack_bf16x2(xs[it].x + b4.x, xs[it].y + b4.y), pack_bf16x2(xs[it].z + b4.z, xs[it].w + b4.w));
           }
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = grow_it[it];
-            if (it > 0) {
-              w += 4;
-              while (w >= args.W) { w -= args.W; ++dh; }
-            }
-            if (grow < 0) continue;
-            const size_t orow = ((size_t)(2 * dh + si) * (2 * args.W)) + 2 * w + sj;
-            float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
-            if (args.act) { gelu_erf2(o0, o1); gelu_erf2(o2, o3); }
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + orow * args.c3 + co) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-          }
+          for (int it = 0; it < 8; ++it)
+            if (grow_it[it] >= 0) *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + off_it[it]) = pk[it];
         }
       }
       // all TMEM reads of this accumulator buffer are complete (every tcgen05.ld was waited on)
