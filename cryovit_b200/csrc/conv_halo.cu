@@ -221,20 +221,25 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
       const int h = h0 + hl, w = w0 + wl;
       if (h < args.H && w < args.W) {
         __nv_bfloat16* o = args.out + (((int64_t)d * args.H + h) * args.W + w) * args.n_valid;
+        // math for all COUT channels without branches (activation switch hoisted), then predicated 16-byte stores
+        uint32_t pk[COUT / 2];
+        if (args.act) {
 #pragma unroll
-        for (int c = 0; c < COUT; c += 8) {
-          if (c < args.n_valid) {  // n_valid is a multiple of 8
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float a = __uint_as_float(v[c + 2 * i]) + __ldg(args.bias + c + 2 * i);
-              float b = __uint_as_float(v[c + 2 * i + 1]) + __ldg(args.bias + c + 2 * i + 1);
-              if (args.act) gelu_erf2(a, b);
-              pk[i] = pack_bf16x2(a, b);
-            }
-            *reinterpret_cast<uint4*>(o + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int i = 0; i < COUT / 2; ++i) {
+            float a = __uint_as_float(v[2 * i]) + __ldg(args.bias + 2 * i);
+            float b = __uint_as_float(v[2 * i + 1]) + __ldg(args.bias + 2 * i + 1);
+            gelu_erf2(a, b);
+            pk[i] = pack_bf16x2(a, b);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < COUT / 2; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + __ldg(args.bias + 2 * i), __uint_as_float(v[2 * i + 1]) + __ldg(args.bias + 2 * i + 1));
         }
+#pragma unroll
+        for (int c = 0; c < COUT; c += 8)
+          if (c < args.n_valid)  // n_valid is a multiple of 8
+            *reinterpret_cast<uint4*>(o + c) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
       }
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;

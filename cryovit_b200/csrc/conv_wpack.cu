@@ -337,17 +337,30 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           float bb[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) bb[c] = __ldg(args.bias + c);
+          // the activation switch is hoisted: a branch inside the unrolled loops keeps the voxels' GELU chains from
+          // interleaving (see the transposed-convolution epilogue in gemm_tcgen05.cuh)
+          if (args.act) {
 #pragma unroll
-          for (int j = 0; j < P / 2; ++j) {
-            uint32_t pk[4];
+            for (int j = 0; j < P / 2; ++j) {
+              uint32_t pk[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float a = __uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k];
-              float b = __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1];
-              if (args.act) gelu_erf2(a, b);
-              pk[k] = pack_bf16x2(a, b);
+              for (int k = 0; k < 4; ++k) {
+                float a = __uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k];
+                float b = __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1];
+                gelu_erf2(a, b);
+                pk[k] = pack_bf16x2(a, b);
+              }
+              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                pk[k] = pack_bf16x2(__uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k], __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1]);
+              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
         }
       }

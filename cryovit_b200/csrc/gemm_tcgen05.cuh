@@ -395,22 +395,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_SWIGLU) {
           const int ocol = EPI == EPI_BIAS_SWIGLU ? (t.n0 >> 1) + c0 + jc * 4 : ncol;
           __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(args.out) + ocol;
+          // branch-free row loops (uniform switches hoisted, stores predicated) so the rows' chains interleave
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            float o0 = xs[it].x + b4.x, o1 = xs[it].y + b4.y, o2 = xs[it].z + b4.z, o3 = xs[it].w + b4.w;
-            if (EPI == EPI_BIAS_GELU && args.act) { gelu_erf2(o0, o1); gelu_erf2(o2, o3); }
+            xs[it].x += b4.x; xs[it].y += b4.y; xs[it].z += b4.z; xs[it].w += b4.w;
             if (EPI == EPI_BIAS_SWIGLU) {
-              o0 = silu(o0) * (ys[it].x + b4b.x);
-              o1 = silu(o1) * (ys[it].y + b4b.y);
-              o2 = silu(o2) * (ys[it].z + b4b.z);
-              o3 = silu(o3) * (ys[it].w + b4b.w);
-            }
-            if (grow_it[it] >= 0) {
-              const uint2 pk = out_f16 ? make_uint2(pack_f16x2(o0, o1), pack_f16x2(o2, o3))
-                                       : make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-              *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) = pk;
+              xs[it].x = silu(xs[it].x) * (ys[it].x + b4b.x);
+              xs[it].y = silu(xs[it].y) * (ys[it].y + b4b.y);
+              xs[it].z = silu(xs[it].z) * (ys[it].z + b4b.z);
+              xs[it].w = silu(xs[it].w) * (ys[it].w + b4b.w);
             }
           }
+          if (EPI == EPI_BIAS_GELU && args.act) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              gelu_erf2(xs[it].x, xs[it].y);
+              gelu_erf2(xs[it].z, xs[it].w);
+            }
+          }
+          uint2 pk[8];
+          if (out_f16) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) pk[it] = make_uint2(pack_f16x2(xs[it].x, xs[it].y), pack_f16x2(xs[it].z, xs[it].w));
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) pk[it] = make_uint2(pack_bf16x2(xs[it].x, xs[it].y), pack_bf16x2(xs[it].z, xs[it].w));
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (grow_it[it] >= 0) *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) = pk[it];
         } else if (EPI == EPI_SCALE_RESIDUAL) {
           float* xbase = static_cast<float*>(args.out) + ncol;
           float4 resid[8];
