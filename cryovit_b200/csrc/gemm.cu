@@ -216,9 +216,15 @@ static int conv3_rows(const void* x, const void* w, GemmArgs args, cudaStream_t 
     int rc = encode_tmap(&tmA, TmapDtype::BF16, 4, x, dims, strides, box, kspan);
     if (rc) return rc;
   }
-  int rc = make_tmap_rows(&tmB, w, (int64_t)27 * Cout, Cin, Cin, bn, kspan);
+  // CTA pairs (two consecutive row tiles of one depth plane share every B tile, half each) for the wide layers: the
+  // single-CTA kernel re-fetches the tap's whole weight tile for every 128 voxels and is bound by L2 -> SM traffic
+  const int per_plane = ((H + BH - 1) / BH) * ((W + BW - 1) / BW);
+  const bool pair = g_gemm_pair && kspan == 128 && (bn == 192 || bn == 256) && (per_plane % 2) == 0;
+  int rc = make_tmap_rows(&tmB, w, (int64_t)27 * Cout, Cin, Cin, pair ? bn / 2 : bn, kspan);
   if (rc) return rc;
-  const int num_tiles = D * ((H + BH - 1) / BH) * ((W + BW - 1) / BW) * (Cout / bn);
+  const int num_tiles = D * per_plane * (Cout / bn);
+  if (pair && bn == 192) return launch_gemm<192, EPI_BIAS_GELU, AMODE_CONV3, 128, true>(tmA, tmB, args, num_tiles / 2, stream);
+  if (pair && bn == 256) return launch_gemm<256, EPI_BIAS_GELU, AMODE_CONV3, 128, true>(tmA, tmB, args, num_tiles / 2, stream);
   CVIT_GEMM_CASE(256, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(128, EPI_BIAS_GELU, AMODE_CONV3, 128)
   CVIT_GEMM_CASE(192, EPI_BIAS_GELU, AMODE_CONV3, 128)

@@ -90,11 +90,13 @@ struct TileCoord {
   int d, h0, w0;     // AMODE_CONV3: depth plane and spatial origin
 };
 
+// MB_MUL / mb_add: a CTA pair in AMODE_CONV3 walks PAIRS of row tiles (row tile = 2 * pair tile + cluster rank)
 template <int BN, int AMODE>
-__device__ __forceinline__ TileCoord tile_coord(int tile, int num_n, const GemmArgs& a) {
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_n, const GemmArgs& a, int mb_mul = 1, int mb_add = 0) {
   TileCoord t;
   int mb = tile / num_n;
   t.n0 = (tile - mb * num_n) * BN;
+  mb = mb * mb_mul + mb_add;
   t.m0 = mb * GEMM_BM;
   t.d = t.h0 = t.w0 = 0;
   if (AMODE == AMODE_CONV3) {
@@ -115,8 +117,9 @@ __device__ __forceinline__ int tile_row_to_global(const TileCoord& t, int r, con
   if (AMODE == AMODE_CONV3) {
     int hl = r / a.BW, wl = r - hl * a.BW;
     int h = t.h0 + hl, w = t.w0 + wl;
-    // partial tiles at the plane border: TMA zero-filled the loads, the rows are simply not stored
-    if (h >= a.H || w >= a.W) return -1;
+    // partial tiles at the plane border (or the odd last tile of a CTA pair, d == D): TMA zero-filled the loads, the
+    // rows are simply not stored
+    if (h >= a.H || w >= a.W || t.d >= a.D) return -1;
     return (t.d * a.H + h) * a.W + w;
   }
   int g = t.m0 + r;
@@ -134,7 +137,9 @@ template <int BN, int EPI, int AMODE, int KSPAN, bool PAIR = false, int SUB = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
-  static_assert(!PAIR || AMODE != AMODE_CONV3, "CTA pairs are implemented for the plain-rows GEMMs only");
+  // PAIR with AMODE_CONV3: the two CTAs take two consecutive row tiles of the SAME depth plane (the host only selects
+  // the pair kernel when the number of tiles per plane is even), so both skip the same out-of-range depth taps and the
+  // leader's MMA schedule matches both producers'.
   static_assert(SUB == 1 || (AMODE == AMODE_ROWS && !PAIR), "tall tiles are implemented for the single-CTA plain-rows GEMM only");
   static_assert(AMODE != AMODE_ROWS_MN || KSPAN == 128, "the MN-major A operand is staged in 128-byte swizzled rows");
   using Cfg = GemmCfg<BN, KSPAN, PAIR, SUB>;
@@ -161,7 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int num_n = args.N / BN;
   const int num_m = AMODE == AMODE_CONV3
-                        ? args.D * ((args.H + args.BH - 1) / args.BH) * ((args.W + args.BW - 1) / args.BW)
+                        ? (args.D * ((args.H + args.BH - 1) / args.BH) * ((args.W + args.BW - 1) / args.BW) + (PAIR ? 1 : 0)) / (PAIR ? 2 : 1)
                         : (args.M + TILE_M - 1) / TILE_M;
   const int num_tiles = num_m * num_n;
   const int k_chunks = (args.K + KC - 1) / KC;
@@ -169,6 +174,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto coord = [&](int tile) {
+    if (PAIR && AMODE == AMODE_CONV3) return tile_coord<BN, AMODE>(tile, num_n, args, 2, (int)rank);
     TileCoord t = tile_coord<BN, AMODE>(tile, num_n, args);
     if (PAIR) t.m0 = 2 * t.m0 + (int)rank * GEMM_BM;
     if (SUB > 1) t.m0 *= SUB;
@@ -221,6 +227,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // both producers report their bytes to the LEADER's full barrier, which expects the pair's total
               if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * Cfg::STAGE_BYTES);
               const uint32_t lead_full = mapa_cluster(bar_full + 8 * s, 0);
+              if (AMODE == AMODE_CONV3) {
+                tma_load_4d_pair(sA + s * Cfg::A_BYTES, &tmA, lead_full, kc * KC, dx, dy, dz);
+                tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, lead_full, kc * KC, tap * args.N + t.n0 + (int)rank * (BN / 2));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                continue;
+              }
               if (AMODE == AMODE_ROWS_MN) {  // two boxes of 64 rows (inner, contiguous) x KC channels
                 tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, lead_full, t.m0, kc * KC);
                 tma_load_2d_pair(sA + s * Cfg::A_BYTES + Cfg::A_BYTES / 2, &tmA, lead_full, t.m0 + 64, kc * KC);

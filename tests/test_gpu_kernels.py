@@ -300,6 +300,11 @@ def _conv_w_taps(w, cout_pad):
     (5, 8, 64, 32, 32, 1),      # SB3-like, 64B swizzle
     (4, 4, 256, 32, 16, 2),     # SB4a: Cout padded 16 -> 32, W > 128
     (4, 2, 128, 16, 16, 1),     # SB4b: 32B swizzle
+    (10, 8, 32, 128, 192, 3),   # CTA-pair path (even tile count per plane): two row tiles of a plane share each B tile
+    (6, 12, 16, 64, 192, 2),    # CTA pair, the second tile of every plane is partial (rows 8..11 of 16)
+    (6, 16, 16, 64, 256, 2),    # CTA pair, 256-wide tile (input-gradient shapes of the training path)
+    (4, 16, 16, 64, 512, 1),    # CTA pair, two N tiles
+    (3, 32, 32, 1024, 192, 32), # CTA pair at the head's own plane size, D <= dil
 ])
 def test_conv3d_dilated(cuda_lib, D, H, W, Cin, Cout, dil):
     from cryovit_b200 import ops
