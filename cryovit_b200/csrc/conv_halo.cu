@@ -202,6 +202,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
     const int hl = r / CH_TW, wl = r % CH_TW;
     int acc = 0;
     uint32_t acc_ph = 0;
+    float bias_r[COUT];  // in registers for the whole kernel, not one __ldg round trip per tile
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias_r[c] = __ldg(args.bias + c);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int d, h0, w0;
       tile_of(tile, d, h0, w0);
@@ -226,15 +229,15 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
         if (args.act) {
 #pragma unroll
           for (int i = 0; i < COUT / 2; ++i) {
-            float a = __uint_as_float(v[2 * i]) + __ldg(args.bias + 2 * i);
-            float b = __uint_as_float(v[2 * i + 1]) + __ldg(args.bias + 2 * i + 1);
+            float a = __uint_as_float(v[2 * i]) + bias_r[2 * i];
+            float b = __uint_as_float(v[2 * i + 1]) + bias_r[2 * i + 1];
             gelu_erf2(a, b);
             pk[i] = pack_bf16x2(a, b);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < COUT / 2; ++i)
-            pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + __ldg(args.bias + 2 * i), __uint_as_float(v[2 * i + 1]) + __ldg(args.bias + 2 * i + 1));
+            pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + bias_r[2 * i], __uint_as_float(v[2 * i + 1]) + bias_r[2 * i + 1]);
         }
 #pragma unroll
         for (int c = 0; c < COUT; c += 8)

@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
     const int half = (warp - 4) >> 2;  // GELU mode: which half of the row's voxels (columns) this warp takes
     const int r = q * 32 + lane;
     const int hl = r / WP_G, g = r - hl * WP_G;
+    // the bias lives in registers for the whole kernel (a per-tile __ldg put a global-load round trip in front of
+    // every tile's first FADD: ncu source page, stall_long_sb)
+    float bb[FINAL ? P : 8];
+#pragma unroll
+    for (int c = 0; c < (FINAL ? P : 8); ++c) bb[c] = __ldg(args.bias + c);
     for (int i = i_begin; i < i_end; ++i) {
       const int col = i / args.D, d = i - col * args.D;
       int h0, w0;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           // COUT == 1: P clipped logits (and their sigmoid), fp32, contiguous along W
           float lg[P];
 #pragma unroll
-          for (int j = 0; j < P; ++j) lg[j] = fminf(fmaxf(__uint_as_float(v[j]) + __ldg(args.bias + j), -5.0f), 5.0f);
+          for (int j = 0; j < P; ++j) lg[j] = fminf(fmaxf(__uint_as_float(v[j]) + bb[j], -5.0f), 5.0f);
           if (args.logits) {
 #pragma unroll
             for (int j = 0; j < P; j += 4)
@@ -334,9 +339,6 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
         } else {
           // COUT == 8: this warp's P / 2 voxels x 8 channels, bias + GELU -> bf16, 16 B per voxel
           __nv_bfloat16* o = args.out + (vox + half * (P / 2)) * 8;
-          float bb[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) bb[c] = __ldg(args.bias + c);
           // the activation switch is hoisted: a branch inside the unrolled loops keeps the voxels' GELU chains from
           // interleaving (see the transposed-convolution epilogue in gemm_tcgen05.cuh)
           if (args.act) {
