@@ -235,3 +235,24 @@ def test_dino_features_argument_errors_match_the_reference():
         _dino_features(torch.zeros(2, 1, 28, 28), m, 4)
     with pytest.raises(CryovitB200Error):
         _dino_features(torch.zeros(2, 3, 28, 28), object(), 4)
+
+
+def test_operand_format_switch(monkeypatch):
+    """The 16-bit format of the bounded ViT operands: constructor argument, CRYOVIT_B200_OPERANDS for the Hydra entry
+    points, bf16 by default; anything else is refused before any GPU work."""
+    import torch
+
+    from cryovit_b200._lib import CryovitB200Error
+    from cryovit_b200.vit import DinoVisionTransformerB200, build_model
+
+    monkeypatch.delenv("CRYOVIT_B200_OPERANDS", raising=False)
+    assert build_model("dinov2_vits14_reg").operand_dtype == torch.bfloat16
+    assert build_model("dinov2_vits14_reg", operand_dtype=torch.float16).operand_dtype == torch.float16
+    monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "fp16")
+    assert build_model("dinov2_vits14_reg").operand_dtype == torch.float16
+    assert build_model("dinov2_vits14_reg", operand_dtype=torch.bfloat16).operand_dtype == torch.bfloat16  # argument wins
+    monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "fp8")
+    with pytest.raises(CryovitB200Error):
+        build_model("dinov2_vits14_reg")
+    with pytest.raises(CryovitB200Error):
+        DinoVisionTransformerB200("dinov2_vits14_reg", torch.float32)
