@@ -91,6 +91,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# the workload both arms are quoted on (BASELINE config 2)
+WORKLOAD = (f"ViT-g/14-reg4 (random init, LayerScale 1.0) features of one {D}x{H}x{W} uint8 tomogram per GPU per step, "
+            f"slice batch {BATCH}, output fp16 ({C},{D},32,32)")
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
 # kernels at the same shapes (profiles/r01_ncu_full_v14_hot_kernels.json); bench.py itself never runs under ncu.
 NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu": "w12_swiglu", "layernorm": "layernorm",
@@ -333,7 +337,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "slices/s", "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": round(1e3 * sample / v, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-g/14-reg4 features, {D}x{H}x{W} u8 tomogram, slice batch {BATCH}",
+        "config": {"workload": WORKLOAD,
                    "note": "each step is a bounded sample of the workload (2 slices)"},
         "cpu_baseline": {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast"},
@@ -554,8 +558,7 @@ def run_b200(args) -> None:
         "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16+bf16 operands, fp32 accumulate" if args.operands == "fp16" else "bf16", "data": "synthetic",
-        "config": {"workload": f"ViT-g/14-reg4 (random init, LayerScale 1.0) features of one {D}x{H}x{W} uint8 tomogram per GPU "
-                               f"per step, slice batch {BATCH}, output fp16 ({C},{D},32,32)",
+        "config": {"workload": WORKLOAD,
                    "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
                    "parallelism": f"{world} independent replicas, tomograms sharded by rank, no collective"},
         "model_tflops": round(value * FLOP_PER_SLICE / 1e12, 1),
