@@ -8,6 +8,7 @@ mandatory values, and command-line overrides ``a.b=value`` / ``+a.b=value`` / ``
 """
 from __future__ import annotations
 
+import copy
 import importlib
 import logging
 import re
@@ -93,12 +94,42 @@ def _load_yaml(path: Path) -> dict:
         return _numbers(yaml.safe_load(fh) or {})
 
 
-def _compose_file(config_dir: Path, rel: str, choices: dict[str, str]) -> dict:
-    """One YAML file with its ``defaults`` list resolved (group paths are relative to the file's own group)."""
-    path = config_dir / (rel + ".yaml")
-    if not path.exists():
-        raise FileNotFoundError(f"config file {path} not found")
-    body = _load_yaml(path)
+class _DirSource:
+    """A directory of Hydra YAML files (``config_dir=``): node ``<group>/<choice>`` is ``<dir>/<group>/<choice>.yaml``."""
+
+    def __init__(self, root: Path):
+        self.root = Path(root)
+
+    def exists(self, rel: str) -> bool:
+        return (self.root / (rel + ".yaml")).exists()
+
+    def load(self, rel: str) -> dict:
+        path = self.root / (rel + ".yaml")
+        if not path.exists():
+            raise FileNotFoundError(f"config file {path} not found")
+        return _load_yaml(path)
+
+
+class _TreeSource:
+    """The built-in tree (``config_tree.TREE``): the same nodes as data."""
+
+    def __init__(self):
+        from .config_tree import TREE
+
+        self.tree = TREE
+
+    def exists(self, rel: str) -> bool:
+        return rel in self.tree
+
+    def load(self, rel: str) -> dict:
+        if rel not in self.tree:
+            raise FileNotFoundError(f"config node {rel!r} not found in the built-in tree")
+        return _numbers(copy.deepcopy(self.tree[rel]))
+
+
+def _compose_file(config_dir, rel: str, choices: dict[str, str]) -> dict:
+    """One config node with its ``defaults`` list resolved (group paths are relative to the node's own group)."""
+    body = config_dir.load(rel)
     defaults = body.pop("defaults", ["_self_"])
     group_dir = str(Path(rel).parent) if "/" in rel else ""
     out: dict = {}
@@ -109,7 +140,7 @@ def _compose_file(config_dir: Path, rel: str, choices: dict[str, str]) -> dict:
             self_done = True
         elif isinstance(entry, str):
             cand = (group_dir + "/" if group_dir else "") + entry
-            if (config_dir / (cand + ".yaml")).exists():  # a sibling file of the same group
+            if config_dir.exists(cand):  # a sibling node of the same group
                 _merge(out, _compose_file(config_dir, cand, choices))
             # else: a ConfigStore schema node (base_env, dino_features_config ...): defaults come from SCHEMA_DEFAULTS
         elif isinstance(entry, dict):
@@ -176,8 +207,9 @@ def _parse_value(text: str):
 
 
 def compose(config_name: str, overrides: list[str] | None = None, config_dir: Path | None = None) -> Cfg:
-    """Compose ``<config_dir>/<config_name>.yaml`` with its defaults and apply overrides."""
-    config_dir = Path(config_dir) if config_dir else Path(__file__).resolve().parents[2] / "cryovit" / "configs"
+    """Compose node ``config_name`` of the built-in tree (or ``<config_dir>/<config_name>.yaml`` of a directory of Hydra
+    YAML files) with its defaults and apply overrides."""
+    config_dir = _DirSource(config_dir) if config_dir else _TreeSource()
     overrides = list(overrides or [])
     choices: dict[str, str] = {}
     values: list[tuple[str, Any]] = []
@@ -188,7 +220,7 @@ def compose(config_name: str, overrides: list[str] | None = None, config_dir: Pa
         key = key.lstrip("+")
         if key == "experiments":
             values.append((key, val))
-        elif (config_dir / key).is_dir() and (config_dir / key / f"{val}.yaml").exists():
+        elif config_dir.exists(f"{key}/{val}"):
             choices[key] = val  # config-group choice, e.g. paths=default
         else:
             values.append((key, _parse_value(val)))
@@ -197,7 +229,7 @@ def compose(config_name: str, overrides: list[str] | None = None, config_dir: Pa
     experiment_bodies: list[dict] = []
     for key, val in list(values):
         if key == "experiments":
-            body = _load_yaml(config_dir / "experiments" / f"{val}.yaml")
+            body = config_dir.load(f"experiments/{val}")
             for entry in body.pop("defaults", []):
                 if isinstance(entry, dict):
                     for g, ch in entry.items():
