@@ -147,9 +147,16 @@ def _compose_file(config_dir, rel: str, choices: dict[str, str]) -> dict:
             for group, choice in entry.items():
                 if str(group).startswith("override "):
                     continue  # hydra logging overrides
+                optional = str(group).startswith("optional ")  # Hydra: skip silently when the choice does not exist
+                if optional:
+                    group = str(group)[len("optional "):].strip()
                 full_group = (group_dir + "/" if group_dir else "") + group
                 for ch in (choice if isinstance(choice, list) else [choice]):
                     ch = choices.get(full_group, ch)
+                    if isinstance(ch, str) and ch.startswith("${") and ch.endswith("}"):  # e.g. ``${model}``: another group's choice
+                        ch = choices.get(ch[2:-1], choices.get("=" + ch[2:-1], ch))
+                    if optional and not (isinstance(ch, str) and config_dir.exists(f"{full_group}/{ch}")):
+                        continue
                     if ch == MISSING:  # mandatory group (``model: ???``) not chosen: reported by the validator
                         out[group] = MISSING
                         continue

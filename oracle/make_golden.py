@@ -274,6 +274,30 @@ def golden_host(tmp: Path) -> dict:
     return out
 
 
+CONFIG_CASES = {
+    "dino_features": ("dino_features", ["sample=Q18", "batch_size=64"]),
+    "train_multi": ("train_model", ["model=cryovit", "+experiments=multi_mito", "datamodule.sample=[Q18,Q53]",
+                                    "datamodule.split_id=3", "label_key=mito"]),
+    "train_single": ("train_model", ["model=cryovit", "datamodule=single", "datamodule.sample=Q18", "label_key=mito"]),
+    "eval_multi": ("eval_model", ["model=cryovit", "datamodule=multi", "datamodule.sample=[Q18]",
+                                  "datamodule.test_sample=[Q53]", "label_key=mito"]),
+}
+CONFIG_PATHS = ["paths.model_dir=/m", "paths.data_dir=/d", "paths.exp_dir=/e"]
+
+
+def golden_configs() -> dict:
+    """The reference's OWN YAML tree (src/cryovit/configs/**), composed for the command lines of the three entry points:
+    what the built-in tree of cryovit_b200/host/config_tree.py has to reproduce key for key. Composed with this repo's
+    Hydra-subset composer pointed at the reference's directory (Hydra is not installed here); the schema defaults the
+    reference supplies from ConfigStore dataclasses (config.py:30-156) are therefore absent on this side and show up
+    as ``???`` or missing keys, which the test skips."""
+    from cryovit_b200.host.config import compose
+
+    ref_dir = REF_SRC / "cryovit" / "configs"
+    return {k: {"config_name": name, "overrides": ov + CONFIG_PATHS, "composed": compose(name, ov + CONFIG_PATHS, config_dir=ref_dir)}
+            for k, (name, ov) in CONFIG_CASES.items()}
+
+
 def golden_dinov2(out: dict) -> None:
     """Oracle restatement vs transformers' independent Dinov2WithRegisters on identical weights."""
     from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
@@ -356,7 +380,9 @@ def main() -> None:
     import tempfile
 
     with tempfile.TemporaryDirectory() as td:
-        (GOLD / "reference_host.json").write_text(json.dumps(golden_host(Path(td)), indent=1))
+        host = golden_host(Path(td))
+    host["composed_configs"] = golden_configs()
+    (GOLD / "reference_host.json").write_text(json.dumps(host, indent=1))
     hf_out: dict = {}
     golden_dinov2(hf_out)
     np.savez_compressed(GOLD / "dinov2_hf.npz", **hf_out)
