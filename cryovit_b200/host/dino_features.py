@@ -7,7 +7,9 @@ Differences that are deliberate, all on the fast side of the same contract:
     the weights are seeded random (logged loudly);
   * items may be RAW tomograms (``VITDataset(fused=True)``): pre-processing then runs inside the GPU extractor;
   * with several ranks (torchrun) the tomograms of a sample are dealt round-robin to the ranks; every rank writes
-    only its own files, no collective is involved.
+    only its own files, no collective is involved;
+  * file reads and writes overlap the GPU work (one reader, one writer thread, ``_process_sample``), and
+    ``+skip_existing=true`` resumes an interrupted run (both absent from the reference, whose loop is serial).
 """
 from __future__ import annotations
 
@@ -54,8 +56,18 @@ def _read_source(path: Path) -> dict[str, np.ndarray]:
 
 
 def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: str, datamodule, batch_size: int,
-                    image_dir: Path | None = None, use_sam: bool = False) -> list[str]:
-    """:156-205. Returns the records this rank processed."""
+                    image_dir: Path | None = None, use_sam: bool = False, skip_existing: bool = False) -> list[str]:
+    """:156-205. Returns the records this rank processed.
+
+    The reference reads, extracts and writes one tomogram after the other (:186-204). At a third of a second of GPU time
+    per tomogram the gzip of ``data`` and the 403 MB feature write would dominate, so the three stages overlap here
+    (SURVEY.md 8f row f2): a reader thread loads tomogram i+1 and its pass-through datasets while the GPU extracts
+    tomogram i, a writer thread stores tomogram i-1. At most one read and one write are in flight (bounded host memory);
+    files are written in record order; an error in either thread surfaces at the next hand-over, i.e. inside the same
+    call, where the entry point logs it. ``skip_existing`` (not in the reference) leaves alone result files that already
+    hold ``dino_features``, so an interrupted run can be resumed."""
+    from concurrent.futures import ThreadPoolExecutor
+
     tomo_dir, result_dir, csv_file = Path(src_dir) / sample, Path(dst_dir) / sample, Path(csv_dir) / f"{sample}.csv"
     if csv_file.exists():
         import pandas as pd
@@ -64,12 +76,38 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
     else:
         records = sorted(f.name for f in tomo_dir.glob("*") if f.suffix in tomogram_exts)
     records = shard_round_robin(records)
+    if skip_existing:
+        def done(name: str) -> bool:
+            try:
+                return "dino_features" in hdf.list_keys(result_dir / name)
+            except (OSError, KeyError, ValueError):
+                return False
+
+        kept = [r for r in records if not done(r)]
+        if len(kept) < len(records):
+            logging.info("%s: %d of %d tomograms already have features, skipped", sample, len(records) - len(kept), len(records))
+        records = kept
     dataset = instantiate(datamodule["dataset"], data_root=tomo_dir, use_sam=use_sam)(records=records)
     if image_dir is not None:
         logging.warning("export_features=True (PCA colour maps) is outside the hot path and is skipped")
-    for i in range(len(dataset)):
-        features = _dino_features(dataset[i], model, batch_size)
-        _save_data(_read_source(tomo_dir / records[i]), features, records[i], result_dir)
+
+    def load(i: int):
+        return dataset[i], _read_source(tomo_dir / records[i])
+
+    n = len(dataset)
+    with ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-read") as reader, \
+            ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-write") as writer:
+        nxt = reader.submit(load, 0) if n else None
+        pending = None
+        for i in range(n):
+            item, source = nxt.result()
+            nxt = reader.submit(load, i + 1) if i + 1 < n else None
+            features = _dino_features(item, model, batch_size)
+            if pending is not None:
+                pending.result()
+            pending = writer.submit(_save_data, source, features, records[i], result_dir)
+        if pending is not None:
+            pending.result()
     return records
 
 
@@ -103,5 +141,5 @@ def run_trainer(cfg) -> None:
     model = load_model(cfg.get("model_dir"), cfg.get("dino_variant") or dino_model[1])
     for name in sample_names:
         done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
-                               image_dir if cfg.get("export_features") else None, False)
+                               image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)))
         logging.info("rank %d/%d: %d tomograms of %s", rank, world, len(done), name)

@@ -256,3 +256,55 @@ def test_operand_format_switch(monkeypatch):
         build_model("dinov2_vits14_reg")
     with pytest.raises(CryovitB200Error):
         DinoVisionTransformerB200("dinov2_vits14_reg", torch.float32)
+
+
+def test_process_sample_overlaps_io_and_can_resume(tmp_path, monkeypatch):
+    """``_process_sample`` (run/dino_features.py:156-205) with the read of tomogram i+1 and the write of tomogram i-1
+    overlapped with the extraction of tomogram i (stub extractor: no GPU here): same files, same keys and record order as
+    the serial loop; the reader really runs ahead; an error in the writer thread surfaces in the call; ``skip_existing``
+    resumes an interrupted run without touching finished files."""
+    import threading
+
+    from cryovit.config import compose
+    from cryovit_b200.host import dino_features as df, hdf
+
+    rng = np.random.default_rng(4)
+    names = [f"tomo_{i}.hdf" for i in range(4)]
+    for i, n in enumerate(names):
+        hdf.write_tomogram(tmp_path / "dino_features" / "Q18" / n, {"data": rng.integers(0, 256, (2 + i, 32, 48), dtype=np.uint8),
+                                                                    "labels/mito": np.full((2 + i, 32, 48), i, np.int8)})
+    cfg = compose("dino_features", [f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", "sample=Q18"])
+    events, main_thread = [], threading.get_ident()
+    real_read = df._read_source
+
+    def spy_read(path):
+        events.append(("read", Path(path).name, threading.get_ident() != main_thread))
+        return real_read(path)
+
+    def fake_features(data, model, bs):
+        events.append(("extract", int(data.shape[0]), False))
+        return np.full((4, data.shape[0], 2, 3), float(data.float().mean()), np.float16)
+
+    monkeypatch.setattr(df, "_read_source", spy_read)
+    monkeypatch.setattr(df, "_dino_features", fake_features)
+    args = (tmp_path / "dino_features", tmp_path / "tomograms", tmp_path / "csv", None, "Q18", cfg["datamodule"], 2)
+    assert df._process_sample(*args) == names
+    assert all(off_main for kind, _, off_main in events if kind == "read"), "reads must run on the reader thread"
+    # the read of tomogram 1 was submitted before tomogram 0 was extracted: it appears before the SECOND extract
+    order = [(k, v) for k, v, _ in events]
+    assert order.index(("read", names[1])) < order.index(("extract", 3))
+    for i, n in enumerate(names):
+        back = hdf.read_tomogram(tmp_path / "tomograms" / "Q18" / n)
+        assert sorted(back) == ["data", "dino_features", "labels/mito"]
+        assert back["dino_features"].shape == (4, 2 + i, 2, 3) and (back["labels/mito"] == i).all()
+    # resume: nothing left to do, nothing read, nothing rewritten
+    stamp = {n: (tmp_path / "tomograms" / "Q18" / n).stat().st_mtime_ns for n in names}
+    events.clear()
+    assert df._process_sample(*args, skip_existing=True) == []
+    assert not events and stamp == {n: (tmp_path / "tomograms" / "Q18" / n).stat().st_mtime_ns for n in names}
+    (tmp_path / "tomograms" / "Q18" / names[2]).unlink()
+    assert df._process_sample(*args, skip_existing=True) == [names[2]]
+    # a failing writer surfaces inside the call
+    monkeypatch.setattr(df, "_save_data", lambda *a, **k: (_ for _ in ()).throw(OSError("disk full")))
+    with pytest.raises(OSError, match="disk full"):
+        df._process_sample(*args)
