@@ -36,6 +36,10 @@ T, NP, C, FH, HEADS, DEPTH = 1029, 1024, 1536, 4096, 24, 40
 # algorithmic work
 FLOP_PER_SLICE = DEPTH * T * (2 * C * 3 * C + 2 * C * C + 2 * C * 2 * FH + 2 * FH * C + 4 * T * C) + 2 * 588 * C * NP
 METRIC = "DINOv2 ViT-g/14 feature slices/sec"
+# arithmetic type of the path per --operands mode (all accumulate in fp32 on the tensor cores, fp32 residual stream)
+DTYPES = {"mixed": "fp16 (LayerNorm out, attention out, qkv/proj/w12 weights) + bf16 (q/k/v, probabilities, FFN hidden, w3) operands, fp32 accumulate",
+          "fp16": "fp16 (LayerNorm out, q/k/v, probabilities, attention out, qkv/proj/w12 weights) + bf16 (FFN hidden, w3) operands, fp32 accumulate",
+          "bf16": "bf16 operands, fp32 accumulate"}
 
 
 def measured_peaks() -> tuple[dict, str]:
@@ -423,7 +427,7 @@ def run_b200(args) -> None:
 
     cfg = CONFIGS[MODEL]
     sd = random_state_dict(cfg, seed=0)
-    model = DinoVisionTransformerB200(cfg, torch.float16 if args.operands == "fp16" else torch.bfloat16).load_state_dict(sd).cuda(local)
+    model = DinoVisionTransformerB200(cfg, args.operands).load_state_dict(sd).cuda(local)
     if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
         sd = None  # free 4.5 GB per rank unless the CPU baseline leg needs it
     g = torch.Generator().manual_seed(1234 + rank)
@@ -557,7 +561,7 @@ def run_b200(args) -> None:
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp16+bf16 operands, fp32 accumulate" if args.operands == "fp16" else "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPES[args.operands], "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
                    "parallelism": f"{world} independent replicas, tomograms sharded by rank, no collective"},
@@ -590,8 +594,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--operands", default="bf16", choices=["fp16", "bf16"],
-                    help="16-bit type of the bounded ViT operands (LayerNorm output, q/k/v, attention output and their weights)")
+    ap.add_argument("--operands", default="mixed", choices=["mixed", "fp16", "bf16"],
+                    help="16-bit formats of the ViT operands (cryovit_b200/vit.py): mixed = fp16 LayerNorm / attention output and "
+                         "their weights, bf16 q/k/v/P and FFN hidden (default, the product path)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.steps_ref, args.warmup_ref = min(args.steps, 3), min(args.warmup, 1)

@@ -37,6 +37,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_linear_scale_residual_fmt": [P, I64, P, P, P, P, I64, I64, I64, I64, I32, P],
     "cvit_attention_fwd_bf16": [P, P, I64, I64, I64, I64, P],
     "cvit_attention_fwd_f16": [P, P, I64, I64, I64, I64, P],
+    "cvit_attention_fwd_fmt": [P, P, I64, I64, I64, I64, I32, P],
     "cvit_attention_fwd_bf16_mma_sync": [P, P, I64, I64, I64, I64, P],
     "cvit_final_norm_writeout_f16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, F32, P],
     "cvit_features_to_ndhwc_bf16": [P, P, I64, I64, P],

@@ -83,9 +83,10 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
-// F16: q/k/v, P and the output are IEEE fp16 instead of bf16 (three more mantissa bits for these bounded operands;
-// P <= 2^8 under the lazy rescale, far inside the fp16 range). Everything else is identical.
-template <bool F16>
+// F16: q/k/v and P are IEEE fp16 instead of bf16 (P <= 2^8 under the lazy rescale, far inside the fp16 range);
+// OUT16: the output is stored as IEEE fp16 instead of bf16 (independent of F16: the output only has to match the
+// operand type of the projection GEMM that reads it). Everything else is identical.
+template <bool F16, bool OUT16>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -356,7 +357,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              ob[i] = pack_16x2<F16>(__uint_as_float(oa[2 * i]) * wa + __uint_as_float(o2[2 * i]) * wb,
+              ob[i] = pack_16x2<OUT16>(__uint_as_float(oa[2 * i]) * wa + __uint_as_float(o2[2 * i]) * wb,
                                   __uint_as_float(oa[2 * i + 1]) * wa + __uint_as_float(o2[2 * i + 1]) * wb);
             if (tok < T) {
               dst[2 * hh] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
@@ -394,7 +395,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             tmem_ld_32x32(t_row + FA_COL_O + g * 64 + hh * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = pack_16x2<F16>(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            for (int i = 0; i < 16; ++i) o[i] = pack_16x2<OUT16>(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
             if (tok < T) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[4 * hh + i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -611,7 +612,7 @@ static long long* g_fa_trace = nullptr;
 extern "C" void cvit_fa_set_trace(long long* p) { g_fa_trace = p; }
 #endif
 
-template <bool F16>
+template <bool F16, bool OUT16>
 static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads, int64_t head_dim,
                          void* stream) {
   if (!qkv || !out || n_slices <= 0 || tokens <= 0 || heads <= 0) {
@@ -635,7 +636,7 @@ static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t t
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<F16, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CVIT_ERR_CUDA;
@@ -658,17 +659,30 @@ static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t t
   const int64_t items = (int64_t)((n_qt + 1) / 2) * heads * n_slices;
   int grid = num_sms();
   if (grid > items) grid = (int)items;
-  attention_tcgen05_kernel<F16><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
+  attention_tcgen05_kernel<F16, OUT16><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
   return check_launch("attention_tcgen05_kernel");
 }
 
 extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                        int64_t head_dim, void* stream) {
-  return attention_fwd<false>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+  return attention_fwd<false, false>(qkv, out, n_slices, tokens, heads, head_dim, stream);
 }
 
 // Same kernel with IEEE fp16 q/k/v, probabilities and output (the fp16-operand ViT path).
 extern "C" int cvit_attention_fwd_f16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                       int64_t head_dim, void* stream) {
-  return attention_fwd<true>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+  return attention_fwd<true, true>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+}
+
+// fmt: CVIT_FMT_OPERANDS_F16 (q/k/v and the probabilities are fp16) | CVIT_FMT_OUT_F16 (the output is stored as fp16).
+extern "C" int cvit_attention_fwd_fmt(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                                      int64_t head_dim, int fmt, void* stream) {
+  switch (fmt) {
+    case 0: return attention_fwd<false, false>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+    case 2: return attention_fwd<false, true>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+    case 3: return attention_fwd<true, true>(qkv, out, n_slices, tokens, heads, head_dim, stream);
+    default:
+      set_error("attention: unsupported format flags 0x%x (0, OUT_F16, OPERANDS_F16|OUT_F16)", fmt);
+      return CVIT_ERR_UNSUPPORTED;
+  }
 }

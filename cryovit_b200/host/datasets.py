@@ -52,7 +52,13 @@ class VITDataset:
     def __getitem__(self, idx: int) -> torch.Tensor:
         if idx >= len(self):
             raise IndexError
-        data = self._load_tomogram(self.records[idx])
+        return self.item_from_array(self._load_tomogram(self.records[idx]))
+
+    def item_from_array(self, data: np.ndarray) -> torch.Tensor:
+        """The item for a ``data`` array that is already in memory (the feature runner reads each source file once
+        and passes its ``data`` both here and through to the result file)."""
+        if data.dtype not in (np.uint8, np.float32):
+            data = data.astype(np.float32)
         _, h, w = data.shape
         if (h % 16 or w % 16) and not self._warned:
             logging.warning("Resizing tomogram from %s to %s", (h, w), ((h + 15) // 16 * 16, (w + 15) // 16 * 16))

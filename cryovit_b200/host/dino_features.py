@@ -3,8 +3,9 @@
 
 Differences that are deliberate, all on the fast side of the same contract:
   * the model is ``cryovit_b200.vit.build_model("dinov2_vitg14_reg")`` (upstream checkpoint keys) instead of
-    ``torch.hub.load`` (:336) -- there is no network in this image, so without a checkpoint in ``cfg.model_dir``
-    the weights are seeded random (logged loudly);
+    ``torch.hub.load`` (:336). Like the reference, which fails when torch.hub cannot produce the model (:335-337),
+    the run FAILS when no checkpoint is found under ``cfg.model_dir``; seeded random weights (tests, benchmarks on
+    a box without network) have to be asked for explicitly with ``+allow_random_weights=true``;
   * items may be RAW tomograms (``VITDataset(fused=True)``): pre-processing then runs inside the GPU extractor;
   * with several ranks (torchrun) the tomograms of a sample are dealt round-robin to the ranks; every rank writes
     only its own files, no collective is involved;
@@ -23,7 +24,7 @@ from .. import extract
 from ..vit import DinoVisionTransformerB200, build_model
 from . import hdf
 from .config import instantiate, samples, tomogram_exts
-from .shard import rank_world, shard_round_robin
+from .shard import process_group, rank_world, shard_round_robin
 
 dino_model = ("facebookresearch/dinov2", "dinov2_vitg14_reg")  # run/dino_features.py:25-28
 CHECKPOINT_NAMES = ("dinov2_vitg14_reg4_pretrain.pth", "checkpoints/dinov2_vitg14_reg4_pretrain.pth")
@@ -80,7 +81,7 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
         def done(name: str) -> bool:
             try:
                 return "dino_features" in hdf.list_keys(result_dir / name)
-            except (OSError, KeyError, ValueError):
+            except Exception:  # noqa: BLE001 - unreadable / truncated (zipfile.BadZipFile, h5py OSError ...): redo it
                 return False
 
         kept = [r for r in records if not done(r)]
@@ -92,7 +93,12 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
         logging.warning("export_features=True (PCA colour maps) is outside the hot path and is skipped")
 
     def load(i: int):
-        return dataset[i], _read_source(tomo_dir / records[i])
+        # one read (and one gunzip) of the source file per tomogram: the extractor input is built from the same
+        # ``data`` array that is passed through to the result file
+        source = _read_source(tomo_dir / records[i])
+        from_array = getattr(dataset, "item_from_array", None)
+        item = from_array(source["data"]) if from_array is not None and "data" in source else dataset[i]
+        return item, source
 
     n = len(dataset)
     with ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-read") as reader, \
@@ -111,15 +117,32 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
     return records
 
 
-def load_model(model_dir: Path | str | None, name: str = dino_model[1]) -> DinoVisionTransformerB200:
-    """The object the reference gets from torch.hub (:336): a checkpoint under ``model_dir`` if there is one."""
+def checkpoint_names(name: str) -> tuple[str, ...]:
+    """File names torch.hub gives the *_reg checkpoints: dinov2_vitg14_reg -> dinov2_vitg14_reg4_pretrain.pth."""
+    stem = name.replace("_reg", "_reg4") if name.endswith("_reg") else name
+    return (f"{stem}_pretrain.pth", f"checkpoints/{stem}_pretrain.pth", f"{name}.pth")
+
+
+def load_model(model_dir: Path | str | None, name: str = dino_model[1], allow_random_weights: bool = False) -> DinoVisionTransformerB200:
+    """The object the reference gets from torch.hub (:336): the checkpoint under ``model_dir``.
+
+    The reference raises when ``torch.hub.load`` cannot deliver the model (:335-337); so does this: features from
+    random weights are 403 MB of noise per tomogram, never a silent default. ``allow_random_weights`` (entry point:
+    ``+allow_random_weights=true``) is the explicit override for tests and synthetic benchmarks."""
+    tried = []
     if model_dir is not None:
-        for rel in CHECKPOINT_NAMES:
+        for rel in dict.fromkeys(checkpoint_names(name) + CHECKPOINT_NAMES):
             p = Path(model_dir) / rel
+            tried.append(str(p))
             if p.exists():
                 logging.info("loading DINOv2 checkpoint %s", p)
                 return build_model(name, state_dict=torch.load(p, map_location="cpu")).cuda().eval()
-    logging.warning("no DINOv2 checkpoint under %s: using seeded RANDOM weights (no network access to torch.hub)", model_dir)
+    if not allow_random_weights:
+        raise FileNotFoundError(
+            f"no DINOv2 checkpoint for {name}: looked for {tried or 'nothing (model_dir is not set)'}. Download it where "
+            "there is network access (torch.hub: facebookresearch/dinov2) and put it under model_dir; "
+            "+allow_random_weights=true runs with seeded RANDOM weights instead (tests / synthetic benchmarks only)")
+    logging.warning("no DINOv2 checkpoint under %s: +allow_random_weights=true, using seeded RANDOM weights", model_dir)
     return build_model(name).cuda().eval()
 
 
@@ -136,9 +159,13 @@ def run_trainer(cfg) -> None:
     if cfg.get("use_sam"):
         raise NotImplementedError("use_sam=True (SAM2 image encodings) is outside the B200 hot path")
     rank, world = rank_world()
-    if torch.cuda.is_available():
-        torch.cuda.set_device(rank % torch.cuda.device_count())
-    model = load_model(cfg.get("model_dir"), cfg.get("dino_variant") or dino_model[1])
+    with process_group(need_collectives=False):  # binds LOCAL_RANK's GPU; tomograms shard by rank, nothing is exchanged
+        _run_samples(cfg, paths, src_dir, dst_dir, csv_dir, image_dir, sample_names, rank, world)
+
+
+def _run_samples(cfg, paths, src_dir, dst_dir, csv_dir, image_dir, sample_names, rank, world) -> None:
+    model_dir = cfg.get("model_dir") or paths.get("model_dir")
+    model = load_model(model_dir, cfg.get("dino_variant") or dino_model[1], bool(cfg.get("allow_random_weights", False)))
     for name in sample_names:
         done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
                                image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)))

@@ -14,7 +14,7 @@ import torch
 from .._lib import CryovitB200Error
 from .callbacks import BatchedModelResult, CsvWriter, TestPredictionWriter
 from .config import instantiate
-from .shard import rank_world
+from .shard import process_group, rank_world
 from .train_model import build_datamodule, setup_exp_dir
 
 
@@ -47,6 +47,11 @@ def run_trainer(cfg) -> list[BatchedModelResult]:
     """eval_model.py:143-197. Returns this rank's results (metrics only are kept; volumes are dropped after writing)."""
     if cfg.model["_target_"] != "cryovit.models.CryoVIT":
         raise CryovitB200Error(f"model {cfg.model['_target_']} is outside the B200 hot path (CryoVIT head only)")
+    with process_group():  # every rank on its own GPU; the group carries the gather of the metric rows
+        return _run_trainer(cfg)
+
+
+def _run_trainer(cfg) -> list[BatchedModelResult]:
     torch.manual_seed(cfg.random_seed)
     cfg = setup_exp_dir(cfg, create=False)
     cfg.paths.results_dir.mkdir(parents=True, exist_ok=True)

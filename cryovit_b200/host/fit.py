@@ -15,7 +15,7 @@ import torch
 
 from ..train import CryoVITHeadTrainerB200
 from .datasets import TomoDataset
-from .shard import rank_world
+from .shard import rank_world, require_process_group
 
 
 def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50, lr: float = 1e-4, weight_decay: float = 1e-3,
@@ -25,9 +25,12 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
     with several ranks (torchrun) every rank walks its own round-robin share of a common shuffled order and the
     gradients are averaged over the ranks each step. Returns the final (SWA-averaged if enabled) state dict."""
     rank, world = rank_world()
+    require_process_group("fit_head")  # the data is sharded by rank below: the gradients must really be exchanged
     torch.manual_seed(seed)
     np.random.seed(seed + rank)  # crops differ per rank, the shuffled ORDER (below) does not
-    trainer = CryoVITHeadTrainerB200(in_channels, lr=lr, weight_decay=weight_decay, state_dict=state_dict)
+    # the initial weights follow the seed (the reference's seed_everything(cfg.random_seed)) and are identical on
+    # every rank
+    trainer = CryoVITHeadTrainerB200(in_channels, lr=lr, weight_decay=weight_decay, state_dict=state_dict, seed=seed)
     order_rng = np.random.default_rng(seed)
     swa_avg, swa_n = None, 0
     step = 0

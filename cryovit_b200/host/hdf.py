@@ -13,6 +13,7 @@ reported by :func:`backend`.
 from __future__ import annotations
 
 import io
+import os
 import zipfile
 from pathlib import Path
 
@@ -66,15 +67,23 @@ def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompress
     gzip-compressed except those named in ``uncompressed`` (the reference stores dino_features raw, :148-153)."""
     path = Path(path)
     path.parent.mkdir(parents=True, exist_ok=True)
-    if _H5:
-        with h5py.File(path, "w") as fh:
-            for key, arr in datasets.items():
-                kw = {} if key in uncompressed else {"compression": "gzip"}
-                fh.create_dataset(key, data=arr, shape=arr.shape, dtype=arr.dtype, **kw)
-        return
-    with zipfile.ZipFile(path, "w") as zf:
-        for key, arr in datasets.items():
-            buf = io.BytesIO()
-            np.save(buf, np.ascontiguousarray(arr), allow_pickle=False)
-            comp = zipfile.ZIP_STORED if key in uncompressed else zipfile.ZIP_DEFLATED
-            zf.writestr(zipfile.ZipInfo(key + ".npy"), buf.getvalue(), compress_type=comp)
+    # written next to the target and renamed over it: an interrupted run never leaves a truncated result file
+    # behind (``skip_existing`` would have to trust it), and a reader never sees a half-written one
+    tmp = path.with_name(path.name + f".tmp{os.getpid()}")
+    try:
+        if _H5:
+            with h5py.File(tmp, "w") as fh:
+                for key, arr in datasets.items():
+                    kw = {} if key in uncompressed else {"compression": "gzip"}
+                    fh.create_dataset(key, data=arr, shape=arr.shape, dtype=arr.dtype, **kw)
+        else:
+            with zipfile.ZipFile(tmp, "w") as zf:
+                for key, arr in datasets.items():
+                    info = zipfile.ZipInfo(key + ".npy")
+                    info.compress_type = zipfile.ZIP_STORED if key in uncompressed else zipfile.ZIP_DEFLATED
+                    with zf.open(info, "w", force_zip64=True) as member:  # streamed: no second copy of 403 MB
+                        np.save(member, np.ascontiguousarray(arr), allow_pickle=False)
+        os.replace(tmp, path)
+    finally:
+        if tmp.exists():
+            tmp.unlink()

@@ -13,6 +13,7 @@ import torch
 from .._lib import CryovitB200Error
 from .config import instantiate
 from .fit import fit_head
+from .shard import process_group
 
 
 def _joined(x):
@@ -44,9 +45,15 @@ def build_datamodule(cfg):
 
 
 def run_trainer(cfg) -> Path:
-    """train_model.py:206-312. Returns the path of the saved ``weights.pt``."""
+    """train_model.py:206-312. Returns the path of the saved ``weights.pt``. Under torchrun every rank binds its own
+    GPU and joins one NCCL group for the gradient all-reduce (Lightning's DDP strategy in the reference)."""
     if cfg.model["_target_"] != "cryovit.models.CryoVIT":
         raise CryovitB200Error(f"model {cfg.model['_target_']} is outside the B200 hot path (CryoVIT head only)")
+    with process_group():
+        return _run_trainer(cfg)
+
+
+def _run_trainer(cfg) -> Path:
     torch.manual_seed(cfg.random_seed)
     cfg = setup_exp_dir(cfg)
     datamodule = build_datamodule(cfg)

@@ -126,8 +126,12 @@ def linear_scale_residual(a, w, bias, gamma, x) -> None:
 
 
 def attention(qkv, out, n_slices: int, tokens: int, heads: int, legacy_mma_sync: bool = False) -> None:
-    if qkv.dtype == F16 and not legacy_mma_sync:
-        _lib.call("cvit_attention_fwd_f16", _chk(qkv, F16, "qkv"), _chk(out, F16, "out"), n_slices, tokens, heads, 64, _stream())
+    if not legacy_mma_sync:
+        if qkv.dtype not in (BF16, F16) or out.dtype not in (BF16, F16) or (qkv.dtype == F16 and out.dtype != F16):
+            raise _lib.CryovitB200Error(f"attention: unsupported formats qkv {qkv.dtype} -> out {out.dtype}")
+        fmt = (FMT_OPERANDS_F16 if qkv.dtype == F16 else 0) | (FMT_OUT_F16 if out.dtype == F16 else 0)
+        _lib.call("cvit_attention_fwd_fmt", _chk(qkv, qkv.dtype, "qkv"), _chk(out, out.dtype, "out"), n_slices, tokens, heads, 64,
+                  fmt, _stream())
         return
     _lib.call("cvit_attention_fwd_bf16_mma_sync" if legacy_mma_sync else "cvit_attention_fwd_bf16", _chk(qkv, BF16, "qkv"), _chk(out, BF16, "out"), n_slices, tokens, heads, 64,
               _stream())

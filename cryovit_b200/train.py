@@ -104,11 +104,28 @@ class _Conv:
         self.run("g", dz, lambda w: self._w(w).flip(2, 3, 4).transpose(0, 1).contiguous(), None, dx, self.cout, self.cin, self.dil)
 
 
+class _KeepAlivePool(dict):
+    """Scratch-buffer table whose superseded entries are never freed: a captured CUDA graph has the raw pointers of
+    the buffers it was captured with baked in, so a buffer that is re-allocated for a larger crop shape must stay
+    alive for as long as the trainer does (otherwise a later replay of the older graph writes into memory the caching
+    allocator has handed to somebody else)."""
+
+    def __init__(self, retired: list):
+        super().__init__()
+        self._retired = retired
+
+    def __setitem__(self, key, value):
+        old = self.get(key)
+        if old is not None and old is not value:
+            self._retired.append(old)
+        super().__setitem__(key, value)
+
+
 class CryoVITHeadTrainerB200:
     """Data-parallel trainer of the CryoVIT head: one process per GPU, one tomogram crop per process and step."""
 
     def __init__(self, in_channels: int = 1536, lr: float = 1e-4, weight_decay: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, state_dict: dict | None = None, device=None):
+                 eps: float = 1e-8, state_dict: dict | None = None, device=None, seed: int = 0):
         if not torch.cuda.is_available():
             raise CryovitB200Error("no CUDA device: the B200 training path has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -116,7 +133,7 @@ class CryoVITHeadTrainerB200:
         if state_dict is None:
             from .host.models import default_state_dict
 
-            state_dict = default_state_dict(in_channels, seed=0)
+            state_dict = default_state_dict(in_channels, seed=seed)  # same on every rank (fit_head passes cfg.random_seed)
         self.keys = state_dict_keys()
         sizes = [state_dict[k].numel() for k in self.keys]
         n = sum(sizes)
@@ -139,7 +156,9 @@ class CryoVITHeadTrainerB200:
             off += sz
         self.step_count = 0
         self.launches = 0
-        self._bufs: dict[str, torch.Tensor] = {}
+        self._retired: list = []  # superseded scratch buffers, kept alive for the graphs captured over them
+        self._bufs: dict = _KeepAlivePool(self._retired)
+        self._bufs["wgrad_pool"] = _KeepAlivePool(self._retired)
         self._graphs: dict = {}
         self._graph_broken = False
 
@@ -160,6 +179,8 @@ class CryoVITHeadTrainerB200:
             table = t.round().long().flatten() - 1
             table[table < 0] = self._nparams  # padding -> the zero slot
             self._pk_tables[name] = (table, tuple(t.shape))
+            if self._pk_cat is not None:
+                self._retired.append(self._pk_cat)  # an already captured graph gathers through the old table
             self._pk_cat = None
         return fn(w).to(BF16).contiguous()
 

@@ -16,15 +16,18 @@ Layout in HBM for a batch of B slices (T tokens per slice, C channels, F hidden)
     hidden   bf16 [B*T, F]        post-activation FFN hidden
     features fp16 [C, D, Np]      the reference's on-disk layout (C, D, h, w)
 
-op16 = ``operand_dtype``: bf16 by default, IEEE fp16 on request. The reference runs these GEMMs in TF32 (10 mantissa
-bits); ln, q/k/v, the softmax probabilities and the attention output are bounded (LayerNorm output times gamma; convex
-combinations of v), so ``operand_dtype=torch.float16`` gives them and the weights they meet (qkv, proj, w12 / fc1) the
-same 10 bits at the same bytes (bf16 has 7); the FFN hidden activations, where DINOv2's large-magnitude channels are
-born, and the w3 / fc2 weights they meet stay bf16 (fp32 range) either way. Measured on B200, ViT-g random init with
-LayerScale 1.0 (the worst case): per-token relative error 8.8e-3 (bf16) -> 4.1e-3 (fp16) against the 1e-2 tolerance,
-and 405 -> 390 slices/s: the kernels are identical, but the tensor cores draw more power multiplying 11-bit
-significands, and under the 1000 W cap the SM clock settles ~3 % lower (1400 -> 1357 MHz). bf16 is the default because
-it is inside the tolerance and faster; fp16 is the switch for users who want the margin.
+op16 = the operand format, chosen by ``operands`` (``"mixed"`` default | ``"fp16"`` | ``"bf16"``). The reference runs
+these GEMMs in TF32 (10 mantissa bits). ln and the attention output are bounded (LayerNorm output times gamma; convex
+combinations of v), so ``mixed`` / ``fp16`` give them and the weights they meet (qkv, proj, w12 / fc1) the same 10 bits
+as IEEE fp16 at the same bytes (bf16 has 7); the FFN hidden activations, where DINOv2's large-magnitude channels are
+born, and the w3 / fc2 weights they meet stay bf16 (fp32 range) in every mode. ``mixed`` keeps q/k/v and the softmax
+probabilities bf16: emulating each rounding inside the fp32 oracle (tests/quant_emulation.py, ViT-g, 40 blocks,
+LayerScale 1.0) shows that their format does not move the end-to-end error at all (fp16 everywhere 4.10e-3; fp16 with
+bf16 q/k/v/P 4.10e-3; bf16 everywhere 8.83e-3; only LayerNorm-side fp16 6.39e-3), while bf16 probabilities cannot
+overflow whatever running maximum the flash softmax uses. Measured on B200, ViT-g random init with LayerScale 1.0 (the
+worst case): per-token relative error 8.8e-3 (bf16) -> 4.1e-3 (fp16 / mixed) against the 1e-2 tolerance. bf16 operands
+are ~4 % faster under the 1000 W power cap (the tensor cores draw more multiplying 11-bit significands) but leave a 12 %
+margin only, so ``mixed`` is the default and the format the benchmark reports.
 """
 from __future__ import annotations
 
@@ -57,6 +60,8 @@ def _swiglu_hidden(dim: int) -> int:
     # upstream SwiGLUFFNFused: hidden = (int(4*dim * 2/3) + 7) // 8 * 8
     return (int(4 * dim * 2 / 3) + 7) // 8 * 8
 
+
+OPERAND_MODES = ("mixed", "fp16", "bf16")
 
 CONFIGS = {
     "dinov2_vits14_reg": ViTConfig("dinov2_vits14_reg", 384, 12, 6, "mlp", 1536),
@@ -142,11 +147,15 @@ class DinoVisionTransformerB200:
     KP1 = 256  # one-channel patch row, 196 -> 256
     KP3 = 640  # three-channel patch row, 588 -> 640
 
-    def __init__(self, cfg: ViTConfig | str = "dinov2_vitg14_reg", operand_dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, cfg: ViTConfig | str = "dinov2_vitg14_reg", operands: str | torch.dtype = "mixed"):
         self.cfg = CONFIGS[cfg] if isinstance(cfg, str) else cfg
-        if operand_dtype not in (torch.float16, torch.bfloat16):
-            raise CryovitB200Error(f"operand_dtype must be torch.float16 or torch.bfloat16, got {operand_dtype}")
-        self.operand_dtype = operand_dtype
+        operands = {torch.float16: "fp16", torch.bfloat16: "bf16"}.get(operands, operands)
+        if operands not in OPERAND_MODES:
+            raise CryovitB200Error(f"operands must be one of {OPERAND_MODES} (or torch.float16 / torch.bfloat16), got {operands!r}")
+        self.operands = operands
+        # ln / attention output / qkv, proj, w12 weights  |  q, k, v and the softmax probabilities
+        self.operand_dtype = torch.bfloat16 if operands == "bf16" else torch.float16
+        self.qkv_dtype = torch.float16 if operands == "fp16" else torch.bfloat16
         self.device: torch.device | None = None
         self._sd_cpu: dict[str, torch.Tensor] | None = None
         self._w: dict = {}
@@ -266,7 +275,7 @@ class DinoVisionTransformerB200:
                     "patches": torch.empty(B * Np, kp, **bf16),
                     "x": torch.empty(M, C, device=dev, dtype=torch.float32),
                     "ln": torch.empty(M, C, **op16),
-                    "qkv": torch.empty(M, 3 * C, **op16),
+                    "qkv": torch.empty(M, 3 * C, device=dev, dtype=self.qkv_dtype),
                     "attn": torch.empty(M, C, **op16),
                     "hidden": torch.empty(M, Fh, **bf16),
                 }
@@ -377,17 +386,16 @@ def random_state_dict_keys(cfg: ViTConfig) -> list[str]:
 
 
 def build_model(name: str = "dinov2_vitg14_reg", state_dict: dict | None = None, seed: int = 0,
-                operand_dtype: torch.dtype | None = None) -> DinoVisionTransformerB200:
-    """Stand-in for torch.hub.load(*dino_model): random-init (seeded) unless a state dict is given. ``operand_dtype``
-    None reads CRYOVIT_B200_OPERANDS (``bf16`` | ``fp16``, default bf16), so the Hydra entry points can switch it
-    without a config key the reference does not have."""
-    if operand_dtype is None:
+                operands: str | torch.dtype | None = None) -> DinoVisionTransformerB200:
+    """Stand-in for torch.hub.load(*dino_model): random-init (seeded) unless a state dict is given. ``operands``
+    None reads CRYOVIT_B200_OPERANDS (``mixed`` | ``fp16`` | ``bf16``, default mixed), so the Hydra entry points can
+    switch it without a config key the reference does not have."""
+    if operands is None:
         import os
 
-        choice = os.environ.get("CRYOVIT_B200_OPERANDS", "bf16").lower()
-        if choice not in ("bf16", "fp16"):
-            raise CryovitB200Error(f"CRYOVIT_B200_OPERANDS must be bf16 or fp16, got {choice!r}")
-        operand_dtype = torch.float16 if choice == "fp16" else torch.bfloat16
-    m = DinoVisionTransformerB200(name, operand_dtype)
+        operands = os.environ.get("CRYOVIT_B200_OPERANDS", "mixed").lower()
+        if operands not in OPERAND_MODES:
+            raise CryovitB200Error(f"CRYOVIT_B200_OPERANDS must be one of {OPERAND_MODES}, got {operands!r}")
+    m = DinoVisionTransformerB200(name, operands)
     m.load_state_dict(state_dict if state_dict is not None else random_state_dict(m.cfg, seed))
     return m

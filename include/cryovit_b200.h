@@ -144,6 +144,11 @@ int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_
 /* Same kernel with IEEE fp16 q/k/v, probabilities and output (fp32 scores, softmax and accumulation as above). */
 int cvit_attention_fwd_f16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                            int64_t head_dim, void* stream);
+/* The same kernel by format flags: fmt = 0 (all bf16), CVIT_FMT_OUT_F16 (bf16 q/k/v and probabilities, fp16 output:
+ * the default ViT path -- the format of q/k/v/P does not move the end-to-end error, the format of the output that
+ * meets the projection weights does), or CVIT_FMT_OPERANDS_F16 | CVIT_FMT_OUT_F16 (= cvit_attention_fwd_f16). */
+int cvit_attention_fwd_fmt(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
+                           int64_t head_dim, int fmt, void* stream);
 /* Same contract on the legacy warp-level mma.sync path: kept only as an A/B comparison kernel for profiles. */
 int cvit_attention_fwd_bf16_mma_sync(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                      int64_t head_dim, void* stream);

@@ -103,10 +103,16 @@ def test_module_entry_point_end_to_end(cuda_lib, tmp_path):
     tomos = {"a.hdf": rng.integers(0, 256, (5, 64, 96), dtype=np.uint8), "b.hdf": rng.random((3, 50, 70), dtype=np.float32)}
     for name, data in tomos.items():
         hdf.write_tomogram(src / name, {"data": data, "labels/mito": rng.integers(-1, 2, data.shape).astype(np.int8)})
+    # the checkpoint where torch.hub.set_dir(cfg.model_dir) + torch.hub.load leave it (run/dino_features.py:335-336),
+    # under the upstream parameter names; seed 4 so that a silent fall-back to the seeded default (seed 0) would fail
+    cfg = CONFIGS["dinov2_vits14_reg"]
+    sd = random_state_dict(cfg, seed=4)
+    ckpt = tmp_path / "models" / "DINOv2" / "checkpoints" / "dinov2_vits14_reg4_pretrain.pth"
+    ckpt.parent.mkdir(parents=True)
+    torch.save(sd, ckpt)
     main([f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/models", "sample=Q18",
           "batch_size=2", "+dino_variant=dinov2_vits14_reg"])
-    cfg = CONFIGS["dinov2_vits14_reg"]
-    oracle_model = odino.OracleDino(random_state_dict(cfg, seed=0), cfg.num_heads)
+    oracle_model = odino.OracleDino(sd, cfg.num_heads)
     for name, data in tomos.items():
         out = hdf.read_tomogram(tmp_path / "tomograms" / "Q18" / name)
         assert sorted(out) == ["data", "dino_features", "labels/mito"]
@@ -127,6 +133,23 @@ def test_entry_point_logs_and_swallows_errors(cuda_lib, tmp_path, caplog):
     main([f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/m", "sample=Q18",
           "use_sam=True", "+dino_variant=dinov2_vits14_reg"])
     assert any("NotImplementedError" in r.getMessage() for r in caplog.records)
+
+
+def test_entry_point_fails_without_a_checkpoint_unless_overridden(cuda_lib, tmp_path, caplog):
+    """run/dino_features.py:335-337: no model, no run -- the error is logged by the entry point and nothing is written;
+    ``+allow_random_weights=true`` is the explicit override."""
+    from cryovit.training.dino_features import main
+    from cryovit_b200.host import hdf
+
+    rng = np.random.default_rng(2)
+    hdf.write_tomogram(tmp_path / "dino_features" / "Q18" / "a.hdf", {"data": rng.integers(0, 256, (2, 32, 32), dtype=np.uint8)})
+    args = [f"paths.data_dir={tmp_path}", f"paths.exp_dir={tmp_path}/exp", f"paths.model_dir={tmp_path}/models", "sample=Q18",
+            "batch_size=2", "+dino_variant=dinov2_vits14_reg"]
+    main(args)
+    assert any("FileNotFoundError" in r.getMessage() and "allow_random_weights" in r.getMessage() for r in caplog.records)
+    assert not (tmp_path / "tomograms" / "Q18" / "a.hdf").exists()
+    main(args + ["+allow_random_weights=true"])
+    assert "dino_features" in hdf.list_keys(tmp_path / "tomograms" / "Q18" / "a.hdf")
 
 
 def test_fused_pipeline_tomogram_to_mask(cuda_lib):

@@ -52,7 +52,7 @@ def test_forward_features_vs_oracle_and_golden(cuda_lib, name, shape):
 
 
 @pytest.mark.parametrize("dim,heads,ffn,hidden", [(768, 12, "mlp", 3072), (1024, 16, "mlp", 4096), (1536, 24, "swiglu", 4096)])
-@pytest.mark.parametrize("operands", ["bf16", "fp16"])
+@pytest.mark.parametrize("operands", ["bf16", "fp16", "mixed"])
 def test_every_dinov2_width_vs_oracle(cuda_lib, dim, heads, ffn, hidden, operands):
     """The widths of the other hub entries the reference's ``dino_model`` config can name (ViT-B/14: 768 x 12 heads,
     ViT-L/14: 1024 x 16 heads, ViT-g/14: 1536 x 24 heads with SwiGLU), three blocks each, ragged batch of 3 slices on a
@@ -63,7 +63,7 @@ def test_every_dinov2_width_vs_oracle(cuda_lib, dim, heads, ffn, hidden, operand
     cfg = ViTConfig(f"w{dim}", dim, 3, heads, ffn, hidden)
     sd = random_state_dict(cfg, seed=2)
     x = torch.rand(3, 3, 56, 84, generator=torch.Generator().manual_seed(3))
-    model = DinoVisionTransformerB200(cfg, torch.float16 if operands == "fp16" else torch.bfloat16).load_state_dict(sd).cuda()
+    model = DinoVisionTransformerB200(cfg, operands).load_state_dict(sd).cuda()
     got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
     ref = odino.forward_features(sd, x, cfg.num_heads)["x_norm_patchtokens"]
     assert got.shape == ref.shape == (3, 24, dim)
@@ -124,20 +124,23 @@ def vitg_oracle_slice(vitg_sd):
     return x, odino.forward_features(vitg_sd, x, CONFIGS["dinov2_vitg14_reg"].num_heads)["x_norm_patchtokens"]
 
 
-@pytest.mark.parametrize("operands", ["fp16", "bf16"])
+@pytest.mark.parametrize("operands", ["mixed", "fp16", "bf16"])
 def test_vitg_one_slice_vs_oracle(cuda_lib, vitg_sd, vitg_oracle_slice, operands):
     """The headline model (ViT-g/14-reg4, 40 blocks, LayerScale 1.0 random init: the worst case for 16-bit error
     accumulation) on one 448x448 slice against the fp32 oracle evaluated on the host cores: the default operand format
-    (fp16 for the bounded operands, bf16 for the FFN hidden) and the all-bf16 alternative, both within the tolerance."""
+    ("mixed": fp16 LayerNorm / attention output and their weights, bf16 q/k/v/P and FFN hidden), fp16 everywhere it is
+    bounded, and the all-bf16 alternative -- all within the 1e-2 tolerance; the default must keep half of it as margin."""
     from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200
 
     cfg = CONFIGS["dinov2_vitg14_reg"]
     x, ref = vitg_oracle_slice
-    model = DinoVisionTransformerB200(cfg, torch.float16 if operands == "fp16" else torch.bfloat16).load_state_dict(vitg_sd).cuda()
+    model = DinoVisionTransformerB200(cfg, operands).load_state_dict(vitg_sd).cuda()
     got = model.forward_features(x.cuda())["x_norm_patchtokens"].float().cpu()
     del model
     torch.cuda.empty_cache()
     _check(got, ref, f"ViT-g one slice vs oracle ({operands} operands)")
+    if operands != "bf16":
+        assert token_errors(got, ref)[0] <= 5e-3
 
 
 def test_vitg_full_size_tomogram_properties(cuda_lib, vitg_sd):
@@ -169,6 +172,115 @@ def test_vitg_full_size_tomogram_properties(cuda_lib, vitg_sd):
     ref = odino.forward_features(vitg_sd, x, cfg.num_heads)["x_norm_patchtokens"][0]  # [1024, 1536]
     got = torch.from_numpy(full[:, k].astype(np.float32)).reshape(1536, 1024).t()
     _check(got, ref.half().float(), "full-size run, slice 77 vs oracle")
+
+
+def _oracle_fp32_on_gpu(sd_gpu, x, heads):
+    """The fp32 oracle evaluated on the GPU in strict fp32 (TF32 off everywhere): same restatement, same arithmetic
+    type as on the host cores, fast enough to follow whole batches of ViT-g slices. Checked against the host-core
+    evaluation in test_vitg_parity_sweep before it is trusted."""
+    from oracle import dinov2 as odino
+
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.get_float32_matmul_precision())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    try:
+        outs = [odino.forward_features(sd_gpu, x[i:i + 4].cuda(), heads)["x_norm_patchtokens"].cpu() for i in range(0, x.shape[0], 4)]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags[:2]
+        torch.set_float32_matmul_precision(flags[2])
+    return torch.cat(outs)
+
+
+def heavy_tailed_state_dict(cfg, seed):
+    """Random init pushed towards what a TRAINED DINOv2 looks like, where random init is benign: LayerScale gammas
+    log-uniform in [1e-2, 1] instead of 1.0, a handful of residual-stream channels with 50x outliers (patch-embed bias
+    and the LayerNorm gains that meet them), and a few FFN hidden units / output channels scaled 50x (the large-magnitude
+    channels of the *_reg models are born in the FFN)."""
+    from cryovit_b200.vit import random_state_dict
+
+    sd = random_state_dict(cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    C, Fh = cfg.embed_dim, cfg.hidden
+    hot = torch.randperm(C, generator=g)[:6]
+    sd["patch_embed.proj.bias"][hot] *= 50.0
+    for i in range(cfg.depth):
+        p = f"blocks.{i}."
+        for ls in ("ls1.gamma", "ls2.gamma"):
+            sd[p + ls] = 10.0 ** (-2.0 * torch.rand(C, generator=g))
+        units = torch.randperm(Fh, generator=g)[:4]
+        outs = torch.randperm(C, generator=g)[:3]
+        if cfg.ffn == "swiglu":
+            sd[p + "mlp.w12.weight"][units] *= 50.0          # silu input of a few hidden units
+            sd[p + "mlp.w3.weight"][outs] *= 50.0            # a few output channels of the FFN
+        else:
+            sd[p + "mlp.fc1.weight"][units] *= 50.0
+            sd[p + "mlp.fc2.weight"][outs] *= 50.0
+        sd[p + "norm1.weight"][hot] *= 0.1                   # trained models damp their outlier channels in the norms
+        sd[p + "norm2.weight"][hot] *= 0.1
+    return sd
+
+
+def _percentiles(got, ref):
+    got, ref = got.double().reshape(-1, got.shape[-1]), ref.double().reshape(-1, ref.shape[-1])
+    rel = (got - ref).norm(dim=-1) / ref.norm(dim=-1)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
+    return rel.max().item(), rel.mean().item(), rel.quantile(0.999).item(), cos.min().item()
+
+
+def test_vitg_parity_sweep(cuda_lib, vitg_sd, vitg_oracle_slice):
+    """The ViT-g margin over more than one slice and one set of weights, for the DEFAULT operand
+    format (the one bench.py reports): 16 slices of a full-size 128 x 512 x 512 run, three weight seeds on one slice,
+    and one heavy-tailed set of weights, each against the fp32 oracle. The oracle is evaluated on the GPU in strict
+    fp32 (first checked against its host-core evaluation on the fixture slice). Bar: worst token of the whole set
+    <= 8e-3 relative error (the 1e-2 tolerance with 20 % to spare) and cosine >= 0.999."""
+    from cryovit_b200.extract import extract_tomogram
+    from cryovit_b200.vit import CONFIGS, DinoVisionTransformerB200, random_state_dict
+    from oracle import preproc as opre
+
+    cfg = CONFIGS["dinov2_vitg14_reg"]
+    x1, ref_cpu = vitg_oracle_slice
+    sd_gpu = {k: v.cuda() for k, v in vitg_sd.items()}
+    ref_gpu = _oracle_fp32_on_gpu(sd_gpu, x1, cfg.num_heads)
+    rmax, _, _, cmin = _percentiles(ref_gpu, ref_cpu)
+    print(f"\n[parity] fp32 oracle on the GPU vs on the host cores: rel-err max {rmax:.2e}, min cosine {cmin:.8f}")
+    assert rmax < 2e-4, "the GPU evaluation of the oracle is not fp32-faithful"
+
+    worst = {}
+    # (a) 16 slices of the full-size run, default format
+    model = DinoVisionTransformerB200(cfg).load_state_dict(vitg_sd).cuda()
+    assert model.operands == "mixed"
+    tomo = np.random.default_rng(5).integers(0, 256, size=(128, 512, 512), dtype=np.uint8)
+    full = extract_tomogram(tomo, model, batch_size=128)
+    ks = list(range(3, 128, 8))
+    x = opre.dino_transform(opre.load_tomogram(tomo[ks]))
+    ref = _oracle_fp32_on_gpu(sd_gpu, x, cfg.num_heads).half().float()                       # [16, 1024, 1536]
+    got = torch.from_numpy(full[:, ks].astype(np.float32)).reshape(1536, len(ks), 1024).permute(1, 2, 0)
+    worst["16 slices of the full-size run"] = _percentiles(got, ref)
+    # the all-bf16 alternative on the same slices, for the record (not the default, not asserted at 8e-3)
+    del model
+    model = DinoVisionTransformerB200(cfg, "bf16").load_state_dict(vitg_sd).cuda()
+    got_bf = model.forward_features(x[:4].cuda())["x_norm_patchtokens"].float().cpu()
+    bf16_stats = _percentiles(got_bf, ref[:4])
+    del model, sd_gpu
+    torch.cuda.empty_cache()
+    # (b) three more weight seeds, (c) heavy-tailed weights: one slice each
+    cases = [(f"weights seed {s}", random_state_dict(cfg, seed=s)) for s in (11, 12, 13)]
+    cases.append(("heavy-tailed weights (outlier channels x50, LayerScale 1e-2..1)", heavy_tailed_state_dict(cfg, 21)))
+    for name, sd in cases:
+        model = DinoVisionTransformerB200(cfg).load_state_dict(sd).cuda()
+        got = model.forward_features(x1.cuda())["x_norm_patchtokens"].float().cpu()
+        del model
+        ref = _oracle_fp32_on_gpu({k: v.cuda() for k, v in sd.items()}, x1, cfg.num_heads)
+        torch.cuda.empty_cache()
+        worst[name] = _percentiles(got, ref)
+    print("[parity] ViT-g/14-reg4, default operand format (mixed), per-token relative error vs the fp32 oracle:")
+    for name, (rmax, rmean, r999, cmin) in worst.items():
+        print(f"[parity]   {name}: max {rmax:.3e}  mean {rmean:.3e}  99.9th pct {r999:.3e}  min cosine {cmin:.6f}")
+    print(f"[parity]   (all-bf16 operands, 4 of the 16 slices: max {bf16_stats[0]:.3e} mean {bf16_stats[1]:.3e})")
+    assert max(v[0] for v in worst.values()) <= 8e-3
+    assert min(v[3] for v in worst.values()) >= COS_TOL
+    assert bf16_stats[0] <= REL_TOL
 
 
 # ------------------------------------------------------------------------------------------------- head

@@ -209,3 +209,42 @@ def test_training_reduces_the_loss(cuda_lib):
     losses = [float(tr.train_step(feats, labels)) for _ in range(12)]
     print("\n[train] losses", [round(l, 4) for l in losses])
     assert losses[-1] < losses[0] - 0.02 and all(l == l for l in losses)
+
+
+def test_graph_replay_survives_buffer_growth(cuda_lib, monkeypatch):
+    """Crop shapes that alternate (datasets mixing tomograms with D < 128 and D >= 128): the CUDA graph captured for the
+    SMALL shape has the scratch buffers of that moment baked in; when the LARGE shape arrives afterwards the scratch
+    buffers are re-allocated. Replaying the first graph must neither read stale operands nor write into memory that now
+    belongs to other tensors: the graphed run must follow the eager run step for step, and a canary tensor
+    allocated right after the growth must stay intact."""
+    from cryovit_b200.train import CryoVITHeadTrainerB200
+    from oracle import head as ohead
+
+    Cin = 384
+    g = torch.Generator().manual_seed(5)
+    shapes = [(4, 4, 4), (9, 4, 6)]
+    data = []
+    for D, h, w in shapes:
+        feats = (torch.randn(Cin, D, h, w, generator=g) * 0.5).half().cuda()
+        labels = (torch.rand(D, 16 * h, 16 * w, generator=g) < 0.3).float().cuda()
+        data.append((feats, labels))
+    order = [0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0, 0, 1]  # small x4 (captured at step 3), large x4 (buffers grow, captured), mixed
+
+    def run(graph: bool):
+        monkeypatch.setenv("CVIT_TRAIN_GRAPH", "1" if graph else "0")
+        tr = CryoVITHeadTrainerB200(Cin, lr=1e-3, state_dict=ohead.random_state_dict(Cin, seed=4))
+        losses, canaries = [], []
+        for step, i in enumerate(order):
+            losses.append(float(tr.train_step(*data[i])))
+            if step == 4:  # right after the first large step: blocks the allocator may hand out from freed scratch
+                canaries = [torch.full((1 << 18,), 7.0, device="cuda") for _ in range(16)]
+        assert all(bool((c == 7.0).all()) for c in canaries), "a graph replay wrote into memory it does not own"
+        return losses, tr.state_dict(), len(tr._graphs), sum("graph" in e for e in tr._graphs.values())
+
+    eager, sd_e, _, n_cap_e = run(False)
+    graphed, sd_g, n_shapes, n_cap = run(True)
+    assert n_cap_e == 0 and n_shapes == 2 and n_cap == 2, "both crop shapes must have been captured"
+    print("\n[train] eager  ", [round(x, 5) for x in eager], "\n[train] graphed", [round(x, 5) for x in graphed])
+    assert all(abs(a - b) < 2e-3 for a, b in zip(eager, graphed)), (eager, graphed)
+    worst = max(((sd_e[k] - sd_g[k]).norm() / sd_e[k].norm().clamp_min(1e-12)).item() for k in sd_e)
+    assert worst < 2e-2, worst

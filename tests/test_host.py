@@ -239,23 +239,40 @@ def test_dino_features_argument_errors_match_the_reference():
 
 def test_operand_format_switch(monkeypatch):
     """The 16-bit format of the bounded ViT operands: constructor argument, CRYOVIT_B200_OPERANDS for the Hydra entry
-    points, bf16 by default; anything else is refused before any GPU work."""
+    points, "mixed" by default (fp16 LayerNorm / attention output and their weights, bf16 q/k/v and probabilities);
+    anything else is refused before any GPU work."""
     import torch
 
     from cryovit_b200._lib import CryovitB200Error
     from cryovit_b200.vit import DinoVisionTransformerB200, build_model
 
     monkeypatch.delenv("CRYOVIT_B200_OPERANDS", raising=False)
-    assert build_model("dinov2_vits14_reg").operand_dtype == torch.bfloat16
-    assert build_model("dinov2_vits14_reg", operand_dtype=torch.float16).operand_dtype == torch.float16
-    monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "fp16")
-    assert build_model("dinov2_vits14_reg").operand_dtype == torch.float16
-    assert build_model("dinov2_vits14_reg", operand_dtype=torch.bfloat16).operand_dtype == torch.bfloat16  # argument wins
+    m = build_model("dinov2_vits14_reg")
+    assert (m.operands, m.operand_dtype, m.qkv_dtype) == ("mixed", torch.float16, torch.bfloat16)
+    m = build_model("dinov2_vits14_reg", operands=torch.float16)
+    assert (m.operands, m.operand_dtype, m.qkv_dtype) == ("fp16", torch.float16, torch.float16)
+    monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "bf16")
+    m = build_model("dinov2_vits14_reg")
+    assert (m.operands, m.operand_dtype, m.qkv_dtype) == ("bf16", torch.bfloat16, torch.bfloat16)
+    assert build_model("dinov2_vits14_reg", operands="fp16").operands == "fp16"  # argument wins
     monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "fp8")
     with pytest.raises(CryovitB200Error):
         build_model("dinov2_vits14_reg")
     with pytest.raises(CryovitB200Error):
         DinoVisionTransformerB200("dinov2_vits14_reg", torch.float32)
+
+
+def test_load_model_refuses_to_run_without_a_checkpoint(tmp_path):
+    """run/dino_features.py:335-337: the reference fails when torch.hub cannot deliver the model; so does the mirror.
+    Random weights need the explicit ``allow_random_weights`` override (checked before any GPU work)."""
+    from cryovit_b200.host import dino_features as df
+
+    with pytest.raises(FileNotFoundError, match="allow_random_weights"):
+        df.load_model(tmp_path, "dinov2_vits14_reg")
+    with pytest.raises(FileNotFoundError):
+        df.load_model(None)
+    assert "dinov2_vitg14_reg4_pretrain.pth" in df.checkpoint_names("dinov2_vitg14_reg")
+    assert "dinov2_vits14_reg4_pretrain.pth" in df.checkpoint_names("dinov2_vits14_reg")
 
 
 def test_process_sample_overlaps_io_and_can_resume(tmp_path, monkeypatch):
