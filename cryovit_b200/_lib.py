@@ -90,6 +90,10 @@ def load() -> ctypes.CDLL:
     lib.cvit_abi_version.argtypes = []
     lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
     lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
+    lib.cvit_attention_redo_items.restype = c_int64
+    lib.cvit_attention_redo_items.argtypes = []
+    lib.cvit_attention_launches_per_call.restype = c_int
+    lib.cvit_attention_launches_per_call.argtypes = [c_int, c_int64]
     lib.cvit_conv3d_wpack_weight_bytes.restype = c_int64
     lib.cvit_conv3d_wpack_weight_bytes.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():

@@ -6,8 +6,12 @@ point (accumulation stays fp32, as on the tensor cores), and compared with the u
 
     python tests/quant_emulation.py [--depth 40] [--seed 0] [--size 448]
 
-Formats per operand group (b = bf16, h = IEEE fp16):  ln (LayerNorm output + qkv / w12 weights), qkv (q, k, v and
-the softmax probabilities), attn (attention output + proj weights); the FFN hidden activations and w3 are always bf16.
+Formats per operand group (b = bf16, h = IEEE fp16, t = TF32 rounding of that group only):  ln (LayerNorm output +
+qkv / w12 weights), qkv (q, k, v and the softmax probabilities), attn (attention output + proj weights); the FFN
+hidden activations, w3 and the patch embedding are bf16 -- except with ln = "T", which rounds EVERY matmul operand of
+the network to TF32 (10 mantissa bits): the arithmetic of the reference's own GPU path
+(run/dino_features.py:24 ``torch.set_float32_matmul_precision("high")``), i.e. the yardstick for "as accurate as the
+reference is against exact fp32".
 """
 from __future__ import annotations
 
@@ -27,7 +31,15 @@ from oracle import dinov2 as odino  # noqa: E402
 DT = {"b": torch.bfloat16, "h": torch.float16, "f": None}
 
 
+def tf32(t: torch.Tensor) -> torch.Tensor:
+    """Round to TF32 (8 exponent bits, 10 mantissa bits), nearest, ties away from zero (cvt.rna.tf32.f32)."""
+    i = t.float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def rnd(t: torch.Tensor, fmt: str) -> torch.Tensor:
+    if fmt in ("t", "T"):
+        return tf32(t)
     return t if DT[fmt] is None else t.to(DT[fmt]).float()
 
 
@@ -37,7 +49,7 @@ def forward_emulated(sd: dict, x: torch.Tensor, heads: int, ln_fmt: str, qkv_fmt
     B = x.shape[0]
     C = sd["cls_token"].shape[-1]
     # patch embed: bf16 patches x bf16 folded one-channel weight (three identical channels)
-    pe = "f" if ln_fmt == "f" else "b"
+    pe = ln_fmt if ln_fmt in ("f", "T") else "b"
     t = F.conv2d(rnd(x.float(), pe), rnd(sd["patch_embed.proj.weight"], pe), sd["patch_embed.proj.bias"], stride=14)
     gh, gw = t.shape[-2:]
     t = t.flatten(2).transpose(1, 2)
@@ -83,7 +95,7 @@ def main():
     ap.add_argument("--depth", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--size", type=int, default=448)
-    ap.add_argument("--variants", default="bbb,hhh,hbh,hbb,bhb")
+    ap.add_argument("--variants", default="bbb,hhh,hbh,hbb,bhb,TTT")
     a = ap.parse_args()
     base = CONFIGS["dinov2_vitg14_reg"]
     cfg = ViTConfig("g", base.embed_dim, a.depth, base.num_heads, base.ffn, base.hidden)

@@ -1,6 +1,7 @@
 """GPU suite for the host-side mirror: the reference's module entry point end to end (files in -> files out) against
 the oracle, the dataset seam in the reference's own layout against golden vectors produced by the reference's source,
 the fused loss / metric reductions, and the ``cryovit.models.CryoVIT`` surface."""
+import os
 from pathlib import Path
 
 import numpy as np
@@ -281,6 +282,51 @@ def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path)
         pred = hdf.read_tomogram(tmp_path / "exp" / "predictions" / "multi_cryovit_mito" / s / f"{s}0.hdf")
         assert sorted(pred) == ["data", "mito", "mito_preds"] and pred["mito_preds"].shape == (4, 48, 48)
         assert pred["mito_preds"].dtype == np.float32 and pred["data"].dtype == np.uint8
+
+
+def test_two_gpu_torchrun_train_then_eval_entry_points(cuda_lib, tmp_path):
+    """``torchrun --nproc-per-node 2 -m cryovit.training.train_model`` must train ONE model over both
+    ranks' data (NCCL gradient all-reduce, each rank on its own GPU) and ``... eval_model`` must gather every rank's rows
+    into the csv. Needs two GPUs (skipped on a one-GPU box; run with ``gpurun --gpus 2``)."""
+    import subprocess
+    import sys
+
+    import pandas as pd
+    from cryovit_b200.host import hdf
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(4)
+    rows = []
+    for s in ("A", "B"):
+        for i in range(4):
+            feats = rng.standard_normal((384, 4, 3, 3)).astype(np.float16)
+            lab = (np.repeat(np.repeat(feats[0].astype(np.float32), 16, axis=1), 16, axis=2) > 0).astype(np.int8)
+            hdf.write_tomogram(tmp_path / "data" / "tomograms" / s / f"{s}{i}.hdf",
+                               {"data": rng.integers(0, 256, (4, 48, 48), dtype=np.uint8), "labels/mito": lab, "dino_features": feats})
+            rows.append((s, f"{s}{i}.hdf", i % 2))
+    (tmp_path / "data" / "csv").mkdir()
+    pd.DataFrame(rows, columns=["sample", "tomo_name", "split_id"]).to_csv(tmp_path / "data" / "csv" / "splits.csv", index=False)
+    common = ["model=cryovit", "+experiments=multi_mito", "datamodule.sample=[A,B]", "datamodule.split_id=0", "+model.in_channels=384",
+              f"paths.data_dir={tmp_path / 'data'}", f"paths.exp_dir={tmp_path / 'exp'}"]
+    root = str(Path(__file__).resolve().parent.parent)
+    launch = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+              "--master-port", str(29600 + os.getpid() % 300)]
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run(launch + ["-m", "cryovit.training.train_model", *common, "trainer.max_epochs=12", "model.lr=2e-3"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Error" not in r.stderr or "Traceback" not in r.stderr, r.stderr
+    weights = tmp_path / "exp" / "multi_cryovit_mito" / "A_B" / "split_0" / "weights.pt"
+    assert weights.exists(), r.stdout + r.stderr
+    assert "2 steps/rank" in r.stderr + r.stdout  # 4 training tomograms (split 1 of A and B) over 2 ranks
+    r = subprocess.run(launch + ["-m", "cryovit.training.eval_model", *common], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for s in ("A", "B"):
+        df = pd.read_csv(tmp_path / "exp" / "results" / "multi_cryovit_mito" / f"{s}_0.csv")
+        assert sorted(df["tomo_name"]) == [f"{s}0.hdf", f"{s}2.hdf"], (df, r.stderr)  # both ranks' rows, merged by rank 0
+        assert (df["dice_metric"] > 0.5).all(), df
 
 
 def test_baseline_config1_end_to_end_with_a_fitted_head(cuda_lib):

@@ -201,6 +201,55 @@ def test_two_rank_gloo_sharded_extraction_and_metric_reduce(tmp_path):
         assert back["dino_features"].shape == (4, 3 + i, 2, 3) and back["data"].shape == (3 + i, 32, 48)
 
 
+PG_WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from cryovit_b200.host import shard
+from cryovit_b200.host.eval_model import _merge_rows
+rank, world = shard.rank_world()
+assert world == 2 and not dist.is_initialized()
+try:
+    shard.require_process_group("fit_head")
+    raise SystemExit("require_process_group accepted WORLD_SIZE=2 without a process group")
+except RuntimeError as e:
+    assert "WORLD_SIZE=2" in str(e)
+from cryovit_b200.host import fit
+try:  # the training loop refuses BEFORE it touches a device: no rank trains alone on a share of the data
+    fit.fit_head([], in_channels=384)
+    raise SystemExit("fit_head ran without a process group")
+except RuntimeError as e:
+    assert "not initialised" in str(e)
+with shard.process_group(need_collectives=False):
+    assert not dist.is_initialized()          # feature extraction: ranks only split an index range
+with shard.process_group():                    # train / eval entry points: launcher env -> gloo here, NCCL on a GPU box
+    assert dist.is_initialized() and dist.get_world_size() == 2 and dist.get_rank() == rank
+    shard.require_process_group("fit_head")
+    class W:
+        rows = []
+        def on_test_batch_end(self, res): self.rows.append(res)
+    w = W()
+    _merge_rows([f"row-of-rank-{rank}"], [w], rank, world)
+    assert (w.rows == ["row-of-rank-0", "row-of-rank-1"]) if rank == 0 else (w.rows == [])
+assert not dist.is_initialized()               # torn down again: it was created here
+'''
+
+
+def test_entry_point_process_group_plumbing_two_ranks(tmp_path):
+    """ADVICE r1 (high): under torchrun the train / eval entry points must join ONE process group (gradient all-reduce,
+    csv row gather) and bind their own GPU; a loop that shards by RANK without a group must refuse to run. Launched
+    the way torchrun launches (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT), gloo on this CPU box."""
+    script = tmp_path / "pg_worker.py"
+    script.write_text(PG_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port, REPO=str(ROOT))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
 def test_wpack_weight_image_is_the_banded_matrix():
     """csrc/conv_wpack.cu's B operand: entry [kh][step][chunk][block][j_out][co][ci] is w[co, ci, kd = 2 - block, kh,
     kw = j_in - j_out] where j_in = 2 step + chunk, zero outside the three taps."""

@@ -25,4 +25,17 @@ for _ in range(9):
 q, k, v = qkv[: 4 * T].view(4, T, 3, H, 64).permute(2, 0, 3, 1, 4).float()
 ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(4 * T, H * 64)
 err = (out[: 4 * T].float() - ref).abs().max().item()
-print(f"attention {sorted(ts)[4]:.4f} ms (min {min(ts):.4f}), max abs err vs fp32 SDPA {err:.3e}")
+import os
+from cryovit_b200 import _lib
+print(f"attention ({'exact' if os.environ.get('CVIT_FA_EXACT') == '1' else 'fast'} pass) {sorted(ts)[4]:.4f} ms (min {min(ts):.4f}), "
+      f"max abs err vs fp32 SDPA {err:.3e}, exact-pass items {_lib.load().cvit_attention_redo_items()}")
+qq, kk, vv = qkv.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+ts = []
+for _ in range(6):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    torch.nn.functional.scaled_dot_product_attention(qq, kk, vv)
+    e.record()
+    torch.cuda.synchronize()
+    ts.append(s.elapsed_time(e))
+print(f"torch SDPA {sorted(ts)[3]:.4f} ms")
