@@ -9,7 +9,10 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcryovit_b200.so"
+import os
+
+# CRYOVIT_B200_LIB: load another build of the same library (A/B runs of a kernel variant, tools/build_variant.py)
+LIB_PATH = Path(os.environ.get("CRYOVIT_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libcryovit_b200.so")
 
 
 class CryovitB200Error(RuntimeError):
@@ -90,10 +93,6 @@ def load() -> ctypes.CDLL:
     lib.cvit_abi_version.argtypes = []
     lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
     lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
-    lib.cvit_attention_redo_items.restype = c_int64
-    lib.cvit_attention_redo_items.argtypes = []
-    lib.cvit_attention_launches_per_call.restype = c_int
-    lib.cvit_attention_launches_per_call.argtypes = [c_int, c_int64]
     lib.cvit_conv3d_wpack_weight_bytes.restype = c_int64
     lib.cvit_conv3d_wpack_weight_bytes.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():

@@ -21,8 +21,6 @@
 // TMEM (512 columns): S_A [0,128) S_B [128,256) | P_A [256,320) P_B [320,384) | O_A [384,448) O_B [448,512).
 // The ragged tail (1029 = 8*128 + 5 keys) runs as an N=16 MMA with the 11 padding keys masked to -inf.
 // A slice whose query-tile count is odd ends with an A-only item (group B idles through it).
-#include <stdlib.h>
-
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -58,26 +56,7 @@ struct FaArgs {
   __nv_bfloat16* out;  // [B*T, C]
   int T, heads, C, slices;
   float scale_log2e;   // head_dim^-0.5 * log2(e)
-  // FAST / REDO hand-over (one slot of the static tables below per call)
-  unsigned int* redo_cnt;     // number of work items the fast pass could not finish
-  unsigned int* redo_done;    // CTAs of the exact pass that have finished (the last one resets the slot)
-  int* redo_list;             // their item numbers
-  unsigned int* redo_flag;    // item -> already listed
 };
-
-// The fast pass (below) takes each tile's exponentials against the running maximum of the tiles BEFORE it; a tile
-// whose scores exceed that maximum by more than 2^FA_POISON_LOG2 could overflow fp32. Such a work item is listed
-// here and recomputed by a second, exact launch of the same kernel (REDO) that walks only the listed items -- in
-// practice an empty launch. Static device tables (nothing is allocated per call); calls rotate through the slots so
-// that attention launches in flight on different streams do not share a list.
-constexpr int FA_REDO_SLOTS = 8, FA_REDO_CAP = 1 << 16;
-__device__ unsigned int g_fa_redo_cnt[FA_REDO_SLOTS], g_fa_redo_done[FA_REDO_SLOTS];
-__device__ int g_fa_redo_list[FA_REDO_SLOTS][FA_REDO_CAP];
-__device__ unsigned int g_fa_redo_flag[FA_REDO_SLOTS][FA_REDO_CAP];
-__device__ unsigned long long g_fa_redo_total;  // work items ever recomputed by the exact pass (diagnostic)
-constexpr float FA_RESCALE_LOG2_EXACT = 8.0f;   // exact pass: P <= 2^8 (fp16-safe)
-constexpr float FA_RESCALE_LOG2_FAST = 16.0f;   // fast pass (bf16 P): rescale O / l when the maximum grew by > 2^16
-constexpr float FA_POISON_LOG2 = 100.0f;        // fast pass: beyond this a tile's exponentials are not trusted
 
 // packed fp32 pairs (Blackwell FFMA2 / FADD2): halves the issue slots of the softmax inner loop
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -107,19 +86,9 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // F16: q/k/v and P are IEEE fp16 instead of bf16 (P <= 2^8 under the lazy rescale, far inside the fp16 range);
 // OUT16: the output is stored as IEEE fp16 instead of bf16 (independent of F16: the output only has to match the
 // operand type of the projection GEMM that reads it). Everything else is identical.
-// FAST (bf16 P only): the softmax of every tile but a group's first of an item runs against the running maximum of
-//   the PREVIOUS tiles (bf16 probabilities and fp32 sums / accumulators are scale-free, so any reference maximum
-//   gives the same softmax as long as nothing overflows): the exponentials no longer wait for the tile's own row
-//   maximum, which is taken in the shadow of the MUFU-bound loop (FMNMX3 on the otherwise idle ALU pipe) and only
-//   feeds the NEXT tile; the TMEM -> register load of the S row is overlapped with the loop chunk by chunk, and the
-//   loop itself is software-pipelined (exponentials of 8 elements in flight before the first is consumed) so one
-//   warp keeps the exponential unit busy on its own. O / l are rescaled lazily when the maximum grew by > 2^16; a
-//   tile that outgrows the reference by > 2^100 marks its work item for the exact pass.
-// REDO: the exact kernel over the listed work items only (see the tables above).
-template <bool F16, bool OUT16, bool FAST, bool REDO>
+template <bool F16, bool OUT16>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs args) {
-  static_assert(!(FAST && F16) && !(FAST && REDO), "FAST needs bf16 probabilities; the REDO pass is exact");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;                                        // [item parity][Q_A | Q_B]: the next item's
@@ -141,13 +110,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   const int n_tiles = (T + FA_BK - 1) / FA_BK;   // K/V tiles per item
   const int n_qt = (T + FA_BQ - 1) / FA_BQ;      // query tiles per (slice, head)
   const int n_pairs = (n_qt + 1) >> 1;
-  // Work units: every (slice, head, query pair) -- or, in the REDO pass, the listed ones. idx -> item number.
-  const int total_items = REDO ? (int)*reinterpret_cast<volatile unsigned int*>(args.redo_cnt) : n_pairs * args.heads * args.slices;
-  auto item_of = [&](int idx) { return REDO ? args.redo_list[idx] : idx; };
-  if (REDO && total_items == 0) {  // the common case: nothing to redo (uniform over the CTA: nothing was set up yet)
-    if (threadIdx.x == 0 && atomicAdd(args.redo_done, 1u) == gridDim.x - 1) *args.redo_done = 0;
-    return;
-  }
+  const int total_items = n_pairs * args.heads * args.slices;
   // K/V tiles are walked ragged-tile-first: the short tile's P is published at once and its PV retires under the
   // first full tile (walked last, the single P buffer would stall the softmax behind PV of the tile before it).
   const bool ragged = (T % FA_BK) != 0;
@@ -162,6 +125,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
   // does group g work on walked tile j of an item of this kind?
   auto mine = [&](int kind, int g, int j) { return kind == PAIRED || (kind == SPLIT ? (j & 1) == g : g == 0); };
 
+  // Lazy rescale: O and l follow the running maximum only when it grew by more than 2^FA_RESCALE_LOG2, i.e. stored
+  // probabilities reach at most that. fp16 probabilities (max 65504) keep 2^8; bf16 ones have fp32's range, and 2^16
+  // makes the kernel's time independent of the score distribution (1.77 -> 1.54 ms on scores with std 2.25, where the
+  // 2^8 threshold rescaled on most early tiles; profiles/r02_attention_notes.md).
+  constexpr float FA_RESCALE_LOG2 = F16 ? 8.0f : 16.0f;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int b = 0; b < 2; ++b) {
@@ -195,8 +163,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
         uint32_t kv_it = 0, k = 0;
-        for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x, ++k) {
-          const int item = item_of(idx);
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++k) {
           const int pair = item % n_pairs, bh = item / n_pairs;
           const int head = bh % args.heads, slice = bh / args.heads;
           const int cq = head * FA_D, ck = args.C + head * FA_D, cv = 2 * args.C + head * FA_D;
@@ -283,7 +250,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         FA_PROF(5);  // issue PV
       };
       // Cursors over this group's tiles: (item, k = CTA-local item number, kind, j).
-      struct Cur { int item; uint32_t k; int pair; int kind; int j; };  // item: the work-unit index (idx)
+      struct Cur { int item; uint32_t k; int pair; int kind; int j; };
       const int pair_step = gridDim.x % n_pairs;  // pair index of item + gridDim.x without a division per tile
       auto cur_valid = [&](const Cur& c) { return c.item < total_items; };
       auto first_j = [&](int kind) { return kind == SPLIT ? g : 0; };
@@ -296,12 +263,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             ++c.k;
             c.j = 0;
             if (c.item >= total_items) return;
-            if (REDO) {
-              c.pair = item_of(c.item) % n_pairs;
-            } else {
-              c.pair += pair_step;
-              if (c.pair >= n_pairs) c.pair -= n_pairs;
-            }
+            c.pair += pair_step;
+            if (c.pair >= n_pairs) c.pair -= n_pairs;
             c.kind = pair_kind(c.pair);
           }
           if (mine(c.kind, g, c.j)) return;
@@ -309,7 +272,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       };
       Cur cs{(int)blockIdx.x, 0u, (int)(blockIdx.x % n_pairs), 0, -1}, cp = cs;  // next S tile, next PV tile
       if (cur_valid(cs)) {
-        if (REDO) cs.pair = cp.pair = item_of(cs.item) % n_pairs;
         cs.kind = cp.kind = pair_kind(cs.pair);
         advance(cs);
         advance(cp);
@@ -367,8 +329,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     const float* sL_gen = reinterpret_cast<const float*>(smem_gen + (sL - smem_base));
     const float c = args.scale_log2e;
     uint32_t kg[2] = {0, 0};
-    for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
-      const int item = item_of(idx);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int pair = item % n_pairs, bh = item / n_pairs, kind = item_kind(item);
       __nv_bfloat16* out_bh = args.out + ((size_t)(bh / args.heads) * T) * args.C + (bh % args.heads) * FA_D;
       if (kind == SPLIT) {
@@ -473,17 +434,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
       if (lane == 0) mbar_arrive(bg + B_P);
       pending = false;
     };
-    for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
-      const int item = item_of(idx);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int pair = item % n_pairs, kind = item_kind(item);
       if (kind == SOLO && g == 1) continue;  // nothing for group B here; its issuer skips the item too
       const int qt = kind == PAIRED ? 2 * pair + g : 2 * pair;
       const bool warp_active = qt * FA_BQ + q * 32 < T;  // warp-uniform: all-padding warps only keep the barriers moving
       float m = 0.f, l = 0.f;
       bool first = true;  // first tile this group works on in the item
-      // FAST: the reference maximum of the NEXT tile, decided at the end of this one (m_next > m only if resc)
-      float m_next = 0.f;
-      bool resc = false;
       for (int j = 0; j < n_tiles; ++j) {
         if (!mine(kind, g, j)) continue;
         FA_PROF(7);  // loop
@@ -492,103 +449,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
         FA_PROF(0);  // wait for S
         const int valid = min(FA_BK, T - kv_tile(j) * FA_BK);
         bool pv_seen = tile_it == 0;  // PV(t-1) known retired: O may be rescaled, P overwritten
-        if (FAST && warp_active && valid == FA_BK && !first) {
-          // ---- fast path: exponentials against the maximum of the tiles before this one (see the kernel header)
-          uint32_t v[128];
-          tmem_ld_32x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          if (pending) publish();  // P(j-1): its TMEM store drained under the load above
-          if (__any_sync(0xffffffffu, resc)) {
-            // deferred lazy rescale: the previous tile's maximum outgrew the reference by > 2^16
-            mbar_wait(bg + B_PV, (tile_it - 1) & 1);
-            tcgen05_fence_after();
-            pv_seen = true;
-            const float f = resc ? ex2_approx((m - m_next) * c) : 1.0f;
-#pragma unroll 1
-            for (int hh = 0; hh < 4; ++hh) {
-              uint32_t o[16];
-              tmem_ld_32x16(tO + hh * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st_32x16(tO + hh * 16, o);
-            }
-            l *= f;
-            if (resc) m = m_next;
-            resc = false;
-          }
-          tmem_ld_wait();
-          // the other three quarters of the row land under the exponentials of the first
-          tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_32x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
-          tmem_ld_32x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
-          FA_PROF(1);  // TMEM -> registers (first quarter)
-          const float nmc = -m * c;
-          const uint64_t nmc2 = pack_f32x2(nmc, nmc);
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};
-          float pp[8];
-          // 16 batches of 4 element pairs; batch b's exponentials are issued before batch b-1's are consumed
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            if (b == 4) {  // elements 32.. are needed from here on; the loads were issued ~250 cycles ago
-              tmem_ld_wait();
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bg + B_SFREE);  // the MMA warp may start S(j+1) under the rest of this tile
-            }
-            float p[8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = 4 * b + u;
-              const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-              mx[u] = fmax3(mx[u], s0, s1);
-              float t0, t1;
-              unpack_f32x2(fma_f32x2(pack_f32x2(s0, s1), c2, nmc2), t0, t1);
-              p[2 * u] = ex2_approx(t0);
-              p[2 * u + 1] = ex2_approx(t1);
-            }
-            if (b > 0) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                ls[u] = add_f32x2(ls[u], pack_f32x2(pp[2 * u], pp[2 * u + 1]));
-                v[4 * (b - 1) + u] = pack_16x2<F16>(pp[2 * u], pp[2 * u + 1]);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pp[u] = p[u];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            ls[u] = add_f32x2(ls[u], pack_f32x2(pp[2 * u], pp[2 * u + 1]));
-            v[60 + u] = pack_16x2<F16>(pp[2 * u], pp[2 * u + 1]);
-          }
-          {
-            float a0, a1;
-            unpack_f32x2(add_f32x2(add_f32x2(ls[0], ls[1]), add_f32x2(ls[2], ls[3])), a0, a1);
-            l += a0 + a1;
-          }
-          // this tile's own maximum: only the NEXT tile's reference, and the overflow guard
-          const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          const float grow = (mt - m) * c;
-          resc = grow > FA_RESCALE_LOG2_FAST;
-          m_next = mt;
-          if (__any_sync(0xffffffffu, grow > FA_POISON_LOG2)) {
-            // exponentials beyond 2^100: not trusted. List the work item for the exact pass (once).
-            if (lane == 0 && atomicExch(args.redo_flag + item, 1u) == 0u)
-              args.redo_list[atomicAdd(args.redo_cnt, 1u)] = item;
-          }
-          FA_PROF(4);  // exp (+ row max in its shadow)
-          if (!pv_seen) {
-            mbar_wait(bg + B_PV, (tile_it - 1) & 1);
-            tcgen05_fence_after();
-          }
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            tmem_st_32x16(tP + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * ch]));
-          pending = true;
-          if (j + 1 == n_tiles || (kind == SPLIT && j + 2 >= n_tiles)) publish();  // last one: the epilogue is waiting
-          FA_PROF(5);  // wait PV(j-1), store P
-        } else if (warp_active && valid == FA_BK) {
+        if (warp_active && valid == FA_BK) {
           // The whole 128-wide S row lives in registers: one TMEM read per tile, four loads in flight.
           // The row max of each 32-column chunk is taken while the next chunk is still on its way from TMEM
           // (a TMEM read moves 64 B/clk per scheduler: 16 KB = 256 cycles for the row, more than the 64 FMNMX3).
@@ -615,7 +476,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           if (first) {
             m = mt;
           } else {
-            const bool need = (mt - m) * c > FA_RESCALE_LOG2_EXACT;
+            const bool need = (mt - m) * c > FA_RESCALE_LOG2;
             if (__any_sync(0xffffffffu, need)) {
               mbar_wait(bg + B_PV, (tile_it - 1) & 1);
               tcgen05_fence_after();
@@ -685,7 +546,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
             if (first) {
               m = mt;
             } else {
-              const bool need = (mt - m) * c > FA_RESCALE_LOG2_EXACT;
+              const bool need = (mt - m) * c > FA_RESCALE_LOG2;
               if (__any_sync(0xffffffffu, need)) {
                 const float f = need ? ex2_approx((m - mt) * c) : 1.0f;
 #pragma unroll 1
@@ -745,18 +606,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
     tcgen05_fence_after();
     tmem_dealloc<FA_TMEM_COLS>(tmem_base);
   }
-  if (REDO && threadIdx.x == 0) {
-    // every CTA has read the list by the time it gets here: the last one to finish empties the slot for its next call
-    __threadfence();
-    if (atomicAdd(args.redo_done, 1u) == gridDim.x - 1) {
-      const unsigned int n = *reinterpret_cast<volatile unsigned int*>(args.redo_cnt);
-      for (unsigned int i = 0; i < n; ++i) args.redo_flag[args.redo_list[i]] = 0u;
-      g_fa_redo_total += n;
-      *args.redo_cnt = 0u;
-      *args.redo_done = 0u;
-      __threadfence();
-    }
-  }
 }
 
 }  // namespace cvit
@@ -767,30 +616,6 @@ using namespace cvit;
 static long long* g_fa_trace = nullptr;
 extern "C" void cvit_fa_set_trace(long long* p) { g_fa_trace = p; }
 #endif
-
-template <bool F16, bool OUT16, bool FAST, bool REDO>
-static int fa_configure() {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<F16, OUT16, FAST, REDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
-    if (e != cudaSuccess) {
-      set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return CVIT_ERR_CUDA;
-    }
-    configured = true;
-  }
-  return 0;
-}
-
-// CVIT_FA_EXACT=1 in the environment disables the fast pass (A/B runs, debugging).
-static bool fa_fast_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVIT_FA_EXACT");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
 
 template <bool F16, bool OUT16>
 static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads, int64_t head_dim,
@@ -814,6 +639,15 @@ static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t t
   uint32_t box[3] = {FA_D, FA_BK, 1};
   int rc = encode_tmap(&tm, F16 ? TmapDtype::F16 : TmapDtype::BF16, 3, qkv, dims, strides, box, 128);
   if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<F16, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
   FaArgs a;
 #ifdef CVIT_FA_TRACE
   a.trace = g_fa_trace;
@@ -826,59 +660,12 @@ static int attention_fwd(const void* qkv, void* out, int64_t n_slices, int64_t t
   a.C = (int)C;
   a.slices = (int)n_slices;
   a.scale_log2e = 0.125f * 1.4426950408889634f;
-  a.redo_cnt = a.redo_done = a.redo_flag = nullptr;
-  a.redo_list = nullptr;
   const int n_qt = (int)((tokens + FA_BQ - 1) / FA_BQ);
   const int64_t items = (int64_t)((n_qt + 1) / 2) * heads * n_slices;
   int grid = num_sms();
   if (grid > items) grid = (int)items;
-  // The fast pass needs bf16 probabilities and more than one K/V tile per item (a single tile is always exact).
-  constexpr bool CAN_FAST = !F16;
-  if constexpr (CAN_FAST) if (fa_fast_enabled() && items <= FA_REDO_CAP && tokens > FA_BK) {
-    static unsigned int *d_cnt = nullptr, *d_done = nullptr, *d_flag = nullptr;
-    static int* d_list = nullptr;
-    static unsigned int call_no = 0;
-    if (!d_cnt) {
-      cudaError_t e = cudaGetSymbolAddress((void**)&d_cnt, g_fa_redo_cnt);
-      if (e == cudaSuccess) e = cudaGetSymbolAddress((void**)&d_done, g_fa_redo_done);
-      if (e == cudaSuccess) e = cudaGetSymbolAddress((void**)&d_flag, g_fa_redo_flag);
-      if (e == cudaSuccess) e = cudaGetSymbolAddress((void**)&d_list, g_fa_redo_list);
-      if (e != cudaSuccess) {
-        d_cnt = nullptr;
-        set_error("attention: cudaGetSymbolAddress: %s", cudaGetErrorString(e));
-        return CVIT_ERR_CUDA;
-      }
-    }
-    const unsigned int slot = call_no++ % FA_REDO_SLOTS;
-    a.redo_cnt = d_cnt + slot;
-    a.redo_done = d_done + slot;
-    a.redo_flag = d_flag + (size_t)slot * FA_REDO_CAP;
-    a.redo_list = d_list + (size_t)slot * FA_REDO_CAP;
-    if ((rc = fa_configure<F16, OUT16, CAN_FAST, false>())) return rc;
-    if ((rc = fa_configure<F16, OUT16, false, true>())) return rc;
-    attention_tcgen05_kernel<F16, OUT16, CAN_FAST, false><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
-    if ((rc = check_launch("attention_tcgen05_kernel<fast>"))) return rc;
-    // the exact pass over whatever the fast pass listed (normally nothing: every CTA returns at once)
-    attention_tcgen05_kernel<F16, OUT16, false, true><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
-    return check_launch("attention_tcgen05_kernel<redo>");
-  }
-  if ((rc = fa_configure<F16, OUT16, false, false>())) return rc;
-  attention_tcgen05_kernel<F16, OUT16, false, false><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
+  attention_tcgen05_kernel<F16, OUT16><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(tm, a);
   return check_launch("attention_tcgen05_kernel");
-}
-
-// Diagnostic (synchronises the device): how many work items the exact pass has recomputed since the library loaded.
-extern "C" long long cvit_attention_redo_items(void) {
-  unsigned long long n = 0;
-  if (cudaMemcpyFromSymbol(&n, g_fa_redo_total, sizeof(n)) != cudaSuccess) return -1;
-  return (long long)n;
-}
-
-// Number of kernels the last-configured path launches per call (2 with the fast pass + exact re-do pass, else 1):
-// lets the host count its launches honestly.
-extern "C" int cvit_attention_launches_per_call(int fmt, int64_t tokens) {
-  const bool f16 = (fmt & 1) != 0;
-  return (!f16 && fa_fast_enabled() && tokens > FA_BK) ? 2 : 1;
 }
 
 extern "C" int cvit_attention_fwd_bf16(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,

@@ -137,10 +137,6 @@ def attention(qkv, out, n_slices: int, tokens: int, heads: int, legacy_mma_sync:
               _stream())
 
 
-def attention_launches_per_call(fmt: int, tokens: int) -> int:
-    return int(_lib.load().cvit_attention_launches_per_call(fmt, tokens))
-
-
 def final_norm_writeout(x, gamma, beta, features, n_slices, tokens, first_patch_token, n_patches, d0, eps) -> None:
     C, D_total = features.shape[0], features.shape[1]
     _lib.call("cvit_final_norm_writeout_f16", _chk(x, F32, "x"), _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta"),

@@ -301,9 +301,7 @@ class DinoVisionTransformerB200:
             else:
                 ops.linear_bias(ln, b["fc1_w"], b["fc1_b"], hidden, gelu=True)
             ops.linear_scale_residual(hidden, b["out_w"], b["out_b"], b["ls2"], x)
-        # 6 kernels per block + the attention call (fast pass + the normally empty exact re-do pass with bf16 probabilities)
-        fmt = (ops.FMT_OPERANDS_F16 if self.qkv_dtype == torch.float16 else 0) | (ops.FMT_OUT_F16 if self.operand_dtype == torch.float16 else 0)
-        self.launches += (6 + ops.attention_launches_per_call(fmt, T)) * len(self._w["blocks"])
+        self.launches += 7 * len(self._w["blocks"])
 
     def _embed(self, ws: dict, B: int, T: int, gh: int, gw: int, pe_w: torch.Tensor) -> None:
         table, special = self._pos_tables(gh, gw)

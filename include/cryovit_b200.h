@@ -149,15 +149,6 @@ int cvit_attention_fwd_f16(const void* qkv, void* out, int64_t n_slices, int64_t
  * meets the projection weights does), or CVIT_FMT_OPERANDS_F16 | CVIT_FMT_OUT_F16 (= cvit_attention_fwd_f16). */
 int cvit_attention_fwd_fmt(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                            int64_t head_dim, int fmt, void* stream);
-/* With bf16 probabilities (fmt without CVIT_FMT_OPERANDS_F16) and more than 128 tokens the call is TWO launches: a
- * fast pass whose tile softmax runs against the running maximum of the tiles before it, and an exact pass over the
- * work items the fast pass could not finish (scores outgrowing that maximum by > 2^100; normally none, the launch
- * returns at once).  Same results contract either way; CVIT_FA_EXACT=1 in the environment forces the single exact
- * launch.  Returns the number of launches per call (not an error code). */
-int cvit_attention_launches_per_call(int fmt, int64_t tokens);
-/* Diagnostic: work items the exact pass has recomputed since the library was loaded (synchronises the device;
- * -1 on a CUDA error). */
-long long cvit_attention_redo_items(void);
 /* Same contract on the legacy warp-level mma.sync path: kept only as an A/B comparison kernel for profiles. */
 int cvit_attention_fwd_bf16_mma_sync(const void* qkv, void* out, int64_t n_slices, int64_t tokens, int64_t heads,
                                      int64_t head_dim, void* stream);

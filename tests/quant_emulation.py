@@ -44,12 +44,14 @@ def rnd(t: torch.Tensor, fmt: str) -> torch.Tensor:
 
 
 @torch.no_grad()
-def forward_emulated(sd: dict, x: torch.Tensor, heads: int, ln_fmt: str, qkv_fmt: str, attn_fmt: str, eps: float = 1e-6):
+def forward_emulated(sd: dict, x: torch.Tensor, heads: int, ln_fmt: str, qkv_fmt: str, attn_fmt: str, eps: float = 1e-6,
+                     hid_fmt: str | None = None):
     sd = {k: v.float() for k, v in sd.items()}
     B = x.shape[0]
     C = sd["cls_token"].shape[-1]
     # patch embed: bf16 patches x bf16 folded one-channel weight (three identical channels)
     pe = ln_fmt if ln_fmt in ("f", "T") else "b"
+    hf = pe if hid_fmt is None else hid_fmt  # FFN hidden activations and w3 / fc2
     t = F.conv2d(rnd(x.float(), pe), rnd(sd["patch_embed.proj.weight"], pe), sd["patch_embed.proj.bias"], stride=14)
     gh, gw = t.shape[-2:]
     t = t.flatten(2).transpose(1, 2)
@@ -73,11 +75,11 @@ def forward_emulated(sd: dict, x: torch.Tensor, heads: int, ln_fmt: str, qkv_fmt
         if p + "mlp.w12.weight" in sd:
             x12 = F.linear(ln, rnd(sd[p + "mlp.w12.weight"], ln_fmt), sd[p + "mlp.w12.bias"])
             x1, x2 = x12.chunk(2, dim=-1)
-            h = rnd(F.silu(x1) * x2, pe)
-            f = F.linear(h, rnd(sd[p + "mlp.w3.weight"], pe), sd[p + "mlp.w3.bias"])
+            h = rnd(F.silu(x1) * x2, hf)
+            f = F.linear(h, rnd(sd[p + "mlp.w3.weight"], hf), sd[p + "mlp.w3.bias"])
         else:
-            h = rnd(F.gelu(F.linear(ln, rnd(sd[p + "mlp.fc1.weight"], ln_fmt), sd[p + "mlp.fc1.bias"])), pe)
-            f = F.linear(h, rnd(sd[p + "mlp.fc2.weight"], pe), sd[p + "mlp.fc2.bias"])
+            h = rnd(F.gelu(F.linear(ln, rnd(sd[p + "mlp.fc1.weight"], ln_fmt), sd[p + "mlp.fc1.bias"])), hf)
+            f = F.linear(h, rnd(sd[p + "mlp.fc2.weight"], hf), sd[p + "mlp.fc2.bias"])
         t = t + sd[p + "ls2.gamma"] * f
     xn = F.layer_norm(t, (C,), sd["norm.weight"], sd["norm.bias"], eps)
     return xn[:, 1 + sd["register_tokens"].shape[1]:]

@@ -201,9 +201,9 @@ def test_attention(cuda_lib, B, T, H, legacy, scale):
 @pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (3, 261, 2), (1, 1024, 2), (16, 300, 8)])
 @pytest.mark.parametrize("scale", [1.0, 6.0, 20.0])
 def test_attention_bf16_in_fp16_out(cuda_lib, B, T, H, scale):
-    """The default ViT format: bf16 q/k/v and probabilities (the fast pass: every tile's softmax runs against the
-    running maximum of the tiles before it), output stored as fp16 for the projection GEMM. scale 20 makes the scores
-    span +-1000 between tiles: lazy rescales on nearly every tile, still exact softmax semantics."""
+    """The default ViT format: bf16 q/k/v and probabilities, output stored as fp16 for the projection GEMM. scale 20
+    makes the scores span +-1000 between tiles: lazy rescales (threshold 2^16 with bf16 probabilities) on nearly every
+    tile."""
     from cryovit_b200 import ops
     C = H * 64
     qkv = (_rand(B * T, 3 * C, seed=1) * scale).bfloat16()
@@ -214,40 +214,24 @@ def test_attention_bf16_in_fp16_out(cuda_lib, B, T, H, scale):
     _close(out, ref, atol=2e-2 * scale, rtol=2e-2, what="attention bf16 -> fp16")
 
 
-def test_attention_fast_pass_overflow_goes_to_the_exact_pass(cuda_lib):
-    """Scores that outgrow the running maximum by more than 2^100 inside ONE tile cannot be exponentiated against the
-    previous tiles' maximum (fp32 overflow): the fast pass lists such work items and the exact pass recomputes them.
-    Adversarial q/k: in a few (slice, head)s one late key lines up with every query (score +12800 against ~0 elsewhere).
-    The result must be the exact softmax (that key's v), the rest of the batch untouched, the exact pass must really
-    have run (diagnostic counter), and the hand-over slots must be clean for the following calls."""
-    from cryovit_b200 import _lib, ops
+def test_attention_extreme_scores(cuda_lib):
+    """One key per (slice, head) whose score exceeds every other by ~12800 (q = k = 40 on all 64 dimensions), sitting in
+    a middle tile, the ragged tile or the first tile: the running maximum jumps by 2^18000 inside one tile; the lazy
+    rescale must follow (exp2 of the old maximum underflows to exactly 0) and the result is that key's v."""
+    from cryovit_b200 import ops
     B, T, H = 4, 700, 3
     C = H * 64
     qkv = (_rand(B * T, 3 * C, seed=3) * 0.5).bfloat16().view(B, T, 3, H, 64)
-    hot = [(1, 0, 300), (3, 2, 699), (2, 1, 5)]  # (slice, head, key): keys in a middle tile, the ragged tile, the first tile
-    for b, h, key in hot:
+    for b, h, key in [(1, 0, 300), (3, 2, 699), (2, 1, 5)]:
         qkv[b, :, 0, h, :] = 40.0
         qkv[b, key, 1, h, :] = 40.0
     qkv = qkv.view(B * T, 3 * C).contiguous()
-    lib = _lib.load()
-    before = lib.cvit_attention_redo_items()
-    assert before >= 0
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
-    for rep in range(10):  # more calls than hand-over slots: every slot is used, emptied and used again
-        out = torch.full((B * T, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    for odt in (torch.bfloat16, torch.float16):
+        out = torch.full((B * T, C), float("nan"), device=DEV, dtype=odt)
         ops.attention(qkv, out, B, T, H)
-        _close(out, ref, atol=2e-2, rtol=2e-2, what=f"attention with overflowing tiles (call {rep})")
-    redone = lib.cvit_attention_redo_items() - before
-    # keys 300 and 5 sit in tiles that follow other tiles in the walk (ragged tile first): their (slice, head)s overflow
-    # in every query pair = 3 items each, 10 calls; key 699 sits in the ragged tile, which is always taken exactly
-    assert redone == 10 * 2 * 3, redone
-    plain = (_rand(B * T, 3 * C, seed=4)).bfloat16()
-    out = torch.empty(B * T, C, device=DEV, dtype=torch.bfloat16)
-    ops.attention(plain, out, B, T, H)
-    assert lib.cvit_attention_redo_items() - before == redone  # ordinary inputs never reach the exact pass
-    q, k, v = plain.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
-    _close(out, F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C), atol=2e-2, rtol=2e-2, what="after")
+        _close(out, ref, atol=2e-2, rtol=2e-2, what=f"attention with one dominant key, out {odt}")
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (3, 29, 2), (2, 261, 1), (16, 300, 8)])
