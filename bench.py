@@ -99,6 +99,15 @@ class ClockSampler:
 WORKLOAD = (f"ViT-g/14-reg4 (random init, LayerScale 1.0) features of one {D}x{H}x{W} uint8 tomogram per GPU per step, "
             f"slice batch {BATCH}, output fp16 ({C},{D},32,32)")
 
+
+
+def config_dict(world: int) -> dict:
+    """The SAME config object on both arms (the driver compares them key for key)."""
+    return {"workload": WORKLOAD,
+            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
+            "parallelism": f"{world} independent replicas, tomograms sharded by rank, no collective"}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
 # kernels at the same shapes (profiles/r01_ncu_full_v14_hot_kernels.json); bench.py itself never runs under ncu.
 NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu": "w12_swiglu", "layernorm": "layernorm",
@@ -113,6 +122,116 @@ def ncu_traffic(kernel: str) -> float | None:
         if d["kernel"].startswith(NCU_KEYS[kernel]):
             return round(d["dram_traffic_GB"] * 1e9)
     return None
+
+
+class CallProfiler:
+    """CUDA-event timing of EVERY call across the C ABI (``_lib.call``) while active: one record per launch with the
+    symbol, its integer arguments (the shapes) and the events. Used for the per-layer tables of the head and of the
+    training step (the ViT blocks have their own, lighter KernelTimer inside the timed region)."""
+
+    # symbol -> (label, flops(int args)) ; int args are the call's integer arguments in order (pointers are skipped)
+    @staticmethod
+    def _conv(i):  # D, H, W, Cin, Cout(_pad), Cout_valid, dil
+        return 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[5]
+
+    FLOPS = {
+        "cvit_linear_bias_cfirst_f16": lambda i: 2 * i[2] * i[3] * i[4],        # ldat, ldo, M, N, K, gelu
+        "cvit_linear_bias_fmt": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_linear_bias_bf16_nvalid": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_conv3d_dilated_ndhwc": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_dilated_ndhwc_act": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_halo_ndhwc": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_halo_ndhwc_act": lambda i: CallProfiler._conv(i),
+        "cvit_convT_1x2x2_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * 4 * i[4],
+        "cvit_convT_1x2x2_ndhwc_act": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * 4 * i[4],
+        "cvit_conv3d_wpack8_gelu": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 64,
+        "cvit_conv3d_wpack8_final": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 8,
+        "cvit_wgrad_splitk": lambda i: 2 * i[5] * i[0] * i[1] * i[2],           # M, N, k, lda, ldb, T
+        "cvit_wgrad_narrow_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[4],
+    }
+
+    def __init__(self, torch):
+        from cryovit_b200 import _lib
+
+        self.torch, self._lib, self.records, self.active = torch, _lib, [], False
+        self._orig = _lib.call
+
+        def wrapped(name, *a):
+            if not self.active:
+                return self._orig(name, *a)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = self._orig(name, *a)
+            e.record()
+            ints = tuple(int(x) for x in a[:-1] if isinstance(x, int) and not isinstance(x, bool) and abs(x) < (1 << 40))
+            self.records.append((name, ints, s, e))
+            return r
+
+        _lib.call = wrapped
+
+    def close(self):
+        self._lib.call = self._orig
+
+    def table(self, passes: int) -> list[dict]:
+        """Launches of the profiled passes merged by (symbol, shape) in first-seen order; ms = per pass."""
+        rows: dict = {}
+        for name, ints, s, e in self.records:
+            # device pointers are huge ints and were dropped above (< 2^40 keeps sizes, strides, flags)
+            key = (name, ints)
+            r = rows.setdefault(key, {"kernel": name.replace("cvit_", ""), "dims": list(ints), "ms": 0.0, "launches": 0})
+            r["ms"] += s.elapsed_time(e)
+            r["launches"] += 1
+        out = []
+        for (name, ints), r in rows.items():
+            r["ms"] = round(r["ms"] / passes, 4)
+            r["launches"] = r["launches"] // passes
+            f = self.FLOPS.get(name)
+            if f is not None:
+                try:
+                    r["tflops"] = round(f(ints) * r["launches"] / r["ms"] / 1e9, 1) if r["ms"] > 0 else None
+                    r["flop"] = f(ints) * r["launches"]
+                except IndexError:
+                    pass
+            out.append(r)
+        return out
+
+
+def _roofline_of(rows: list[dict], peaks: dict, peak_src: str, traffic_file: str, what: str) -> dict | None:
+    """Roofline block of the slowest tensor-core kernel of a per-layer table."""
+    cand = [r for r in rows if r.get("tflops")]
+    if not cand:
+        return None
+    top = max(cand, key=lambda r: r["ms"])
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    traffic, src = None, None
+    p = ROOT / "profiles" / traffic_file
+    if p.exists():
+        for d in json.loads(p.read_text()):
+            if d.get("kernel") == top["kernel"] and d.get("dims") == top["dims"]:
+                traffic, src = d.get("dram_bytes"), f"profiles/{traffic_file} ({d.get('build', '?')})"
+    return {"kernel": f"{top['kernel']} {top['dims']}", "what": what, "bound": "tensor", "achieved": top["tflops"], "peak": peak,
+            "unit": "TFLOP/s", "frac": round(top["tflops"] / peak, 4), "frac_burst": round(top["tflops"] / peaks["bf16_tflops"], 4),
+            "avg_launch_ms": round(top["ms"] / max(top["launches"], 1), 4), "flop_per_launch": top["flop"] // max(top["launches"], 1),
+            "share_of_pass": round(top["ms"] / sum(r["ms"] for r in rows), 4), "traffic": traffic, "traffic_source": src,
+            "peak_source": f"{peak_src} (sustained bf16)"}
+
+
+def head_cpu_baseline(torch) -> dict:
+    """The oracle head (fp32, all host threads) on a (1536, 32, 28, 28) feature volume -> (32, 448, 448) logits,
+    scaled to voxels/s (head-1536 on a bounded volume, extrapolated linearly and labelled)."""
+    from oracle import head as ohead
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = ohead.random_state_dict(1536, seed=0)
+    x = torch.randn(1, 1536, 32, 28, 28, generator=torch.Generator().manual_seed(3)) * 0.5
+    t0 = time.perf_counter()
+    out = ohead.forward_volume(sd, x)
+    dt = time.perf_counter() - t0
+    vox = out.numel()
+    return {"value": round(vox / dt, 0), "unit": "voxels/s", "cores": cores, "kind": "port",
+            "sample": f"oracle head on one (1536,32,28,28) volume -> (32,448,448) logits in {dt:.1f} s; the full (1536,128,32,32) "
+                      "volume scales linearly in voxels"}
 
 
 def head_voxels_per_s(torch, dist=None, world: int = 1, steps: int = 3) -> dict:
@@ -156,9 +275,24 @@ def head_voxels_per_s(torch, dist=None, world: int = 1, steps: int = 3) -> dict:
         ms = float(t.item())
     vox = D * H * W
     head_voxels_per_s.head = head  # reused by pipeline_line
-    return {"value": round(world * vox / ms * 1e3, 0), "unit": "voxels/s (all GPUs)", "ms_per_volume": round(ms, 3),
+    line = {"value": round(world * vox / ms * 1e3, 0), "unit": "voxels/s (all GPUs)", "ms_per_volume": round(ms, 3),
             "tflops_per_gpu": round(94864 * vox / ms / 1e9, 1), "launches_per_volume": (head.launches - l0) // steps,
             "workload": f"CryoVIT head, one fp16 (1536,{D},32,32) feature volume per GPU -> ({D},{H},{W}) probabilities, weights random"}
+    if int(os.environ.get("RANK", "0")) == 0:
+        # per-layer table: two more passes with an event pair around every launch (outside the timed region above)
+        prof = CallProfiler(torch)
+        prof.active = True
+        for _ in range(2):
+            head.segment_volume(feats, want_logits=False)
+        torch.cuda.synchronize()
+        prof.active = False
+        prof.close()
+        rows = prof.table(2)
+        peaks, peak_src = measured_peaks()
+        line["frac_of_tensor_peak"] = round(line["tflops_per_gpu"] / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), 4)
+        line["layers"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops") if k in r} for r in rows]
+        line["roofline"] = _roofline_of(rows, peaks, peak_src, "r02_ncu_traffic.json", "dominant kernel of the head forward")
+    return line
 
 
 def pipeline_line(torch, dist, world: int, vit, head, tomo_np, runs: int = 2) -> dict:
@@ -214,10 +348,30 @@ def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     vox = world * D * H * W
-    return {"value": round(vox / ms * 1e3, 0), "unit": "labelled-volume voxels/s (all GPUs)", "ms_per_step": round(ms, 2),
+    line = {"value": round(vox / ms * 1e3, 0), "unit": "labelled-volume voxels/s (all GPUs)", "ms_per_step": round(ms, 2),
             "loss": round(float(loss), 5), "launches_per_step": (tr.launches - l0) // steps,
             "gradient_bucket_bytes": tr.flat_g.numel() * 4, "allreduce": "nccl, one flat fp32 bucket" if world > 1 else "none (1 GPU)",
             "workload": f"CryoVIT head training step, fp16 (1536,{D},32,32) crop + ({D},{H},{W}) labels per GPU, AdamW lr 1e-4 wd 1e-3, DiceLoss"}
+    if rank == 0:
+        # per-kernel table from one EAGER forward + backward (the timed steps above replay a CUDA graph, which events
+        # cannot look into); gradients only, no optimizer step, so the trained state is not touched
+        prof = CallProfiler(torch)
+        tr.forward_backward(feats, labels, 1.0 / world)  # eager warm-up outside the profile
+        torch.cuda.synchronize()
+        prof.active = True
+        tr.forward_backward(feats, labels, 1.0 / world)
+        torch.cuda.synchronize()
+        prof.active = False
+        prof.close()
+        rows = prof.table(1)
+        peaks, peak_src = measured_peaks()
+        top = sorted(rows, key=lambda r: -r["ms"])[:10]
+        line["eager_forward_backward_ms"] = round(sum(r["ms"] for r in rows), 2)
+        line["kernels_top10"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops") if k in r} for r in top]
+        line["model_tflops_per_step"] = round(3 * 94864 * D * H * W / 1e12, 2)
+        line["frac_of_tensor_peak"] = round(3 * 94864 * D * H * W / ms / 1e9 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), 4)
+        line["roofline"] = _roofline_of(rows, peaks, peak_src, "r02_ncu_traffic.json", "dominant tensor-core kernel of one training step")
+    return line
 
 
 def cpu_oracle_slices_per_s(n_slices: int, sd=None, threads: int | None = None) -> tuple[float, int, float]:
@@ -242,6 +396,189 @@ def cpu_oracle_slices_per_s(n_slices: int, sd=None, threads: int | None = None) 
     dt = time.perf_counter() - t0
     assert feats.shape == (C, n_slices, 32, 32)
     return n_slices / dt, cores, dt
+
+
+def gpu_eager_baseline(torch, sd_cpu) -> dict:
+    """The reference's own PyTorch path on THIS B200 ("the number our kernels must
+    beat"): the oracle modules moved to the GPU and run through stock torch / cuBLAS / cuDNN --
+      * ViT-g: fp32 weights with TF32 matmuls (run/dino_features.py:24 set_float32_matmul_precision("high")), and again
+        under bf16 autocast; attention through torch SDPA in both (the reference calls xformers
+        memory_efficient_attention, which is not installed: SDPA is the same fused-attention class of kernel);
+      * head: fp16 autocast (Lightning "16-mixed", config.py:70) over channels_last_3d tensors, cuDNN convolutions.
+    Inputs are device resident (pre-processed slices / feature volume), i.e. these are kernel-only numbers to hold against
+    ``value`` / ``head.value``, not against ``e2e``. None of our kernels run here."""
+    import torch.nn.functional as F
+
+    from cryovit_b200.vit import CONFIGS
+    from oracle import dinov2 as odino
+    from oracle import head as ohead
+
+    cfg = CONFIGS[MODEL]
+    out: dict = {"note": "oracle modules on the same GPU through stock torch (cuBLAS / cuDNN / SDPA); device-resident inputs"}
+    orig_attn = odino._attention
+
+    def sdpa_attention(x, sd, p, heads):  # upstream MemEffAttention: the fused kernel instead of the materialised softmax
+        B, N, C = x.shape
+        qkv = F.linear(x, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]).reshape(B, N, 3, heads, C // heads)
+        q, k, v = qkv.permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+        return F.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    prec = torch.get_float32_matmul_precision()
+    try:
+        odino._attention = sdpa_attention
+        sd = {k: v.cuda() for k, v in sd_cpu.items()}
+        nb = 32
+        x = torch.rand(nb, 3, 448, 448, device="cuda")
+        torch.set_float32_matmul_precision("high")
+        torch.backends.cudnn.allow_tf32 = True
+        ms = timed(lambda: odino.forward_features(sd, x, cfg.num_heads), 2)
+        out["vit_tf32"] = {"value": round(nb / ms * 1e3, 2), "unit": "slices/s", "ms_per_128_slices": round(ms * 128 / nb, 1),
+                           "tflops": round(nb * FLOP_PER_SLICE / ms / 1e9, 1), "batch": nb,
+                           "how": "fp32 weights, torch.set_float32_matmul_precision('high') as the reference, SDPA attention"}
+        sd16 = {k: v.bfloat16() for k, v in sd.items()}
+        del sd
+
+        ms = timed(lambda: _bf16_vit(sd16, x, cfg.num_heads), 2)
+        out["vit_bf16_autocast"] = {"value": round(nb / ms * 1e3, 2), "unit": "slices/s", "ms_per_128_slices": round(ms * 128 / nb, 1),
+                                    "tflops": round(nb * FLOP_PER_SLICE / ms / 1e9, 1), "batch": nb,
+                                    "how": "bf16 weights and activations (what torch.autocast(bfloat16) computes in), fp32 LayerNorm, SDPA"}
+        del sd16, x
+        torch.cuda.empty_cache()
+    except Exception as err:  # noqa: BLE001 - a baseline that cannot run is reported, not fatal
+        out["vit_error"] = f"{type(err).__name__}: {err}"[:300]
+    finally:
+        odino._attention = orig_attn
+        torch.set_float32_matmul_precision(prec)
+    try:
+        hsd = {k: v.cuda() for k, v in ohead.random_state_dict(1536, seed=0).items()}
+        feats = (torch.randn(1, 1536, D, 32, 32, device="cuda") * 0.5).to(memory_format=torch.channels_last_3d)
+
+        def head_forward():
+            with torch.autocast("cuda", dtype=torch.float16):
+                return torch.sigmoid(_autocast_head(hsd, feats))
+
+        ms = timed(head_forward, 2)
+        out["head_fp16_autocast"] = {"value": round(D * H * W / ms * 1e3, 0), "unit": "voxels/s", "ms_per_volume": round(ms, 2),
+                                     "tflops": round(94864 * D * H * W / ms / 1e9, 1),
+                                     "how": "fp16 autocast (Lightning 16-mixed), channels_last_3d, cuDNN convolutions, fp32 GroupNorm"}
+    except Exception as err:  # noqa: BLE001
+        out["head_error"] = f"{type(err).__name__}: {err}"[:300]
+    torch.cuda.empty_cache()
+    return out
+
+
+def _bf16_vit(sd16, x, heads):
+    """oracle.dinov2.forward_features without its ``.float()`` of the weights: the same graph on bf16 tensors."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import dinov2 as odino
+
+    with torch.no_grad():
+        B = x.shape[0]
+        C = sd16["cls_token"].shape[-1]
+        t = F.conv2d(x.bfloat16(), sd16["patch_embed.proj.weight"], sd16["patch_embed.proj.bias"], stride=14)
+        gh, gw = t.shape[-2:]
+        t = t.flatten(2).transpose(1, 2)
+        t = torch.cat([sd16["cls_token"].expand(B, -1, -1), t], dim=1)
+        t = t + odino.interpolate_pos_encoding(sd16["pos_embed"], gh, gw).to(t.dtype)
+        t = torch.cat([t[:, :1], sd16["register_tokens"].expand(B, -1, -1), t[:, 1:]], dim=1)
+        depth = 1 + max(int(k.split(".")[1]) for k in sd16 if k.startswith("blocks."))
+        for i in range(depth):
+            p = f"blocks.{i}."
+            t = t + sd16[p + "ls1.gamma"] * odino._attention(F.layer_norm(t, (C,), sd16[p + "norm1.weight"], sd16[p + "norm1.bias"], 1e-6), sd16, p, heads)
+            t = t + sd16[p + "ls2.gamma"] * odino._ffn(F.layer_norm(t, (C,), sd16[p + "norm2.weight"], sd16[p + "norm2.bias"], 1e-6), sd16, p)
+        return F.layer_norm(t, (C,), sd16["norm.weight"], sd16["norm.bias"], 1e-6)[:, 5:]
+
+
+def _autocast_head(sd, x):
+    """oracle.head.forward_volume without its ``.float()`` casts, so that autocast chooses the arithmetic."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle.head import BLOCKS
+
+    with torch.no_grad():
+        x = F.gelu(F.conv3d(x, sd["layers.0.weight"], sd["layers.0.bias"]))
+        for bi, (c1, c2, c3, d1, d2) in enumerate(BLOCKS):
+            p = f"layers.{bi + 2}.layers."
+            x = F.group_norm(x, max(8, c1 // 8), sd[p + "0.weight"], sd[p + "0.bias"], eps=1e-3)
+            x = F.gelu(F.conv3d(x, sd[p + "1.weight"], sd[p + "1.bias"], padding="same", dilation=(d1, 1, 1)))
+            x = F.gelu(F.conv3d(x, sd[p + "3.weight"], sd[p + "3.bias"], padding="same", dilation=(d2, 1, 1)))
+            x = F.gelu(F.conv_transpose3d(x, sd[p + "5.weight"], sd[p + "5.bias"], stride=(1, 2, 2)))
+        x = F.gelu(F.conv3d(x, sd["output_layer.0.weight"], sd["output_layer.0.bias"], padding="same"))
+        x = F.conv3d(x, sd["output_layer.2.weight"], sd["output_layer.2.bias"], padding="same")
+        return torch.clip(x, -5.0, 5.0)
+
+
+def dataset_line(torch, dist, world: int, model, n_per_rank: int = 6) -> dict:
+    """BASELINE config 3 through the FILES: every rank owns ``n_per_rank`` synthetic 128x512x512 uint8 tomogram files of
+    one sample directory on the box's local disk and runs them through ``host.dino_features._process_sample`` -- the
+    loop behind ``python -m cryovit.training.dino_features`` (reader / writer threads around the extractor, gzip of
+    ``data``, 403 MB feature write per tomogram). Wall clock around the whole sample, max over ranks."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+
+    from cryovit_b200.host import dino_features as df
+    from cryovit_b200.host import hdf
+    from cryovit_b200.host.config import compose
+
+    rank = int(os.environ.get("RANK", "0"))
+    root = Path(tempfile.mkdtemp(prefix=f"cryovit_ds_r{rank}_"))
+    try:
+        rng = np.random.default_rng(77 + rank)
+        sample = "Q18"
+        t0 = time.perf_counter()
+        for i in range(n_per_rank):
+            hdf.write_tomogram(root / "dino_features" / sample / f"tomo_{rank}_{i}.hdf",
+                               {"data": rng.integers(0, 256, (D, H, W), dtype=np.uint8)})
+        t_gen = time.perf_counter() - t0
+        cfg = compose("dino_features", [f"paths.data_dir={root}", f"paths.exp_dir={root}/exp", f"sample={sample}", f"batch_size={BATCH}"])
+        env_rank, env_world = os.environ.get("RANK"), os.environ.get("WORLD_SIZE")
+        os.environ["RANK"], os.environ["WORLD_SIZE"] = "0", "1"  # this rank's private directory: no further sharding inside
+        try:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            done = df._process_sample(root / "dino_features", root / "tomograms", root / "csv", model, sample, cfg["datamodule"], BATCH)
+            sec = time.perf_counter() - t0
+        finally:
+            for k, v in (("RANK", env_rank), ("WORLD_SIZE", env_world)):
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        assert len(done) == n_per_rank
+        out_bytes = sum(f.stat().st_size for f in (root / "tomograms" / sample).iterdir())
+        back = hdf.list_keys(root / "tomograms" / sample / done[0])
+        assert sorted(back) == ["data", "dino_features"], back
+        if world > 1:
+            t = torch.tensor([sec], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return {"value": round(world * n_per_rank * D / sec, 2), "unit": "slices/s (all GPUs), tomogram FILES in -> feature FILES out, wall clock",
+                "tomograms_per_gpu": n_per_rank, "seconds": round(sec, 2), "hdf_backend": hdf.backend(),
+                "bytes_written_per_gpu": int(out_bytes), "write_GBps_per_gpu": round(out_bytes / sec / 1e9, 2),
+                "source_generation_s": round(t_gen, 1), "disk": str(root.parent),
+                "workload": f"BASELINE config 3 per GPU: {n_per_rank} x ({D},{H},{W}) uint8 files -> gzip data + fp16 ({C},{D},32,32) "
+                            "dino_features per result file, read / write threads around the GPU extractor"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 def config1_phantom(np):
@@ -341,10 +678,10 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "slices/s", "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": round(1e3 * sample / v, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "note": "each step is a bounded sample of the workload (2 slices)"},
+        "config": config_dict(args.gpus),
         "cpu_baseline": {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast"},
+                         "sample": f"each step is a bounded sample of the workload: {sample} slices of {H}x{W} through preproc + "
+                                   "ViT-g fp32 oracle + layout/cast, all host threads"},
         "e2e": {"value": round(v, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -528,6 +865,7 @@ def run_b200(args) -> None:
     del head_voxels_per_s.head
     torch.cuda.empty_cache()
     train_line = head_train_voxels_per_s(torch, dist, world)
+    data_line = None if args.no_dataset else dataset_line(torch, dist, world, model)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -562,9 +900,7 @@ def run_b200(args) -> None:
         "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPES[args.operands], "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
-                   "parallelism": f"{world} independent replicas, tomograms sharded by rank, no collective"},
+        "config": config_dict(world),
         "model_tflops": round(value * FLOP_PER_SLICE / 1e12, 1),
         "roofline": roof, "kernels": kernels, "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "slices/s", "h2d_bytes_per_step": D * H * W,
@@ -574,13 +910,17 @@ def run_b200(args) -> None:
     line["head"] = head_line
     line["pipeline"] = pipe_line
     line["head_train"] = train_line
+    if data_line is not None:
+        line["dataset"] = data_line
     del model
     torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(torch, sd)
         v, cores, dt = cpu_oracle_slices_per_s(2, sd)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port",
                                 "sample": f"2 slices of {H}x{W} through preproc + ViT-g fp32 oracle + layout/cast ({dt:.1f} s)"}
         del sd
+        line["head"]["cpu_baseline"] = head_cpu_baseline(torch)
         line["config1"] = config1_line(torch)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -593,7 +933,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-oracle and GPU-eager baseline legs")
+    ap.add_argument("--no-dataset", action="store_true", help="skip the file-based BASELINE config 3 leg")
     ap.add_argument("--operands", default="mixed", choices=["mixed", "fp16", "bf16"],
                     help="16-bit formats of the ViT operands (cryovit_b200/vit.py): mixed = fp16 LayerNorm / attention output and "
                          "their weights, bf16 q/k/v/P and FFN hidden (default, the product path)")

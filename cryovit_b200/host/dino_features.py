@@ -57,15 +57,16 @@ def _read_source(path: Path) -> dict[str, np.ndarray]:
 
 
 def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: str, datamodule, batch_size: int,
-                    image_dir: Path | None = None, use_sam: bool = False, skip_existing: bool = False) -> list[str]:
+                    image_dir: Path | None = None, use_sam: bool = False, skip_existing: bool = False, writers: int = 3) -> list[str]:
     """:156-205. Returns the records this rank processed.
 
     The reference reads, extracts and writes one tomogram after the other (:186-204). At a third of a second of GPU time
     per tomogram the gzip of ``data`` and the 403 MB feature write would dominate, so the three stages overlap here
     (SURVEY.md 8f row f2): a reader thread loads tomogram i+1 and its pass-through datasets while the GPU extracts
-    tomogram i, a writer thread stores tomogram i-1. At most one read and one write are in flight (bounded host memory);
-    files are written in record order; an error in either thread surfaces at the next hand-over, i.e. inside the same
-    call, where the entry point logs it. ``skip_existing`` (not in the reference) leaves alone result files that already
+    tomogram i, ``writers`` writer threads store the tomograms before it (zlib releases the GIL: the gzip of ``data``, about
+    a second per 33 MB of incompressible voxels, is what a single writer cannot keep up with). At most one read and
+    ``writers`` writes are in flight (bounded host memory: 0.44 GB each); an error in any thread surfaces at a later
+    hand-over or at the end, i.e. inside the same call, where the entry point logs it. ``skip_existing`` (not in the reference) leaves alone result files that already
     hold ``dino_features``, so an interrupted run can be resumed."""
     from concurrent.futures import ThreadPoolExecutor
 
@@ -102,18 +103,18 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
 
     n = len(dataset)
     with ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-read") as reader, \
-            ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-write") as writer:
+            ThreadPoolExecutor(max_workers=max(1, writers), thread_name_prefix="cryovit-write") as writer:
         nxt = reader.submit(load, 0) if n else None
-        pending = None
+        pending: list = []  # writes in flight, oldest first; at most ``writers`` (bounded host memory)
         for i in range(n):
             item, source = nxt.result()
             nxt = reader.submit(load, i + 1) if i + 1 < n else None
             features = _dino_features(item, model, batch_size)
-            if pending is not None:
-                pending.result()
-            pending = writer.submit(_save_data, source, features, records[i], result_dir)
-        if pending is not None:
-            pending.result()
+            while len(pending) >= max(1, writers):
+                pending.pop(0).result()
+            pending.append(writer.submit(_save_data, source, features, records[i], result_dir))
+        for f in pending:
+            f.result()
     return records
 
 
@@ -168,5 +169,6 @@ def _run_samples(cfg, paths, src_dir, dst_dir, csv_dir, image_dir, sample_names,
     model = load_model(model_dir, cfg.get("dino_variant") or dino_model[1], bool(cfg.get("allow_random_weights", False)))
     for name in sample_names:
         done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
-                               image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)))
+                               image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)),
+                               int(cfg.get("writers", 3)))
         logging.info("rank %d/%d: %d tomograms of %s", rank, world, len(done), name)

@@ -74,10 +74,10 @@ def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompress
         if _H5:
             with h5py.File(tmp, "w") as fh:
                 for key, arr in datasets.items():
-                    kw = {} if key in uncompressed else {"compression": "gzip"}
+                    kw = {} if key in uncompressed else {"compression": "gzip"}  # h5py default: level 4
                     fh.create_dataset(key, data=arr, shape=arr.shape, dtype=arr.dtype, **kw)
         else:
-            with zipfile.ZipFile(tmp, "w") as zf:
+            with zipfile.ZipFile(tmp, "w", compresslevel=4) as zf:  # h5py's gzip default is level 4 too
                 for key, arr in datasets.items():
                     info = zipfile.ZipInfo(key + ".npy")
                     info.compress_type = zipfile.ZIP_STORED if key in uncompressed else zipfile.ZIP_DEFLATED
