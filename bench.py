@@ -131,8 +131,18 @@ class CallProfiler:
 
     # symbol -> (label, flops(int args)) ; int args are the call's integer arguments in order (pointers are skipped)
     @staticmethod
-    def _conv(i):  # D, H, W, Cin, Cout(_pad), Cout_valid, dil
+    def _conv(i):  # D, H, W, Cin, Cout(_pad), Cout_valid, dil -- ALGORITHMIC: all 27 taps, zero-padded ones included
         return 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[5]
+
+    @staticmethod
+    def executed_fraction(name: str, i) -> float:
+        """Share of a dilated convolution's algorithmic FLOPs that the kernels execute: depth taps that fall outside
+        [0, D) are skipped outright (with dilation 32 of 128 planes that is one tap in six)."""
+        if "conv3d_dilated" not in name and "conv3d_halo" not in name:
+            return 1.0
+        D, dil = i[0], i[6]
+        valid = sum((d - dil >= 0) + 1 + (d + dil < D) for d in range(D))
+        return valid / (3.0 * D)
 
     FLOPS = {
         "cvit_linear_bias_cfirst_f16": lambda i: 2 * i[2] * i[3] * i[4],        # ldat, ldo, M, N, K, gelu
@@ -190,6 +200,9 @@ class CallProfiler:
                 try:
                     r["tflops"] = round(f(ints) * r["launches"] / r["ms"] / 1e9, 1) if r["ms"] > 0 else None
                     r["flop"] = f(ints) * r["launches"]
+                    ex = self.executed_fraction(name, ints)
+                    if ex < 1.0:  # the algorithmic figure counts zero-padded depth taps the kernel skips
+                        r["tflops_executed"] = round(r["tflops"] * ex, 1)
                 except IndexError:
                     pass
             out.append(r)
@@ -209,8 +222,12 @@ def _roofline_of(rows: list[dict], peaks: dict, peak_src: str, traffic_file: str
         for d in json.loads(p.read_text()):
             if d.get("kernel") == top["kernel"] and d.get("dims") == top["dims"]:
                 traffic, src = d.get("dram_bytes"), f"profiles/{traffic_file} ({d.get('build', '?')})"
+    executed = top.get("tflops_executed", top["tflops"])
     return {"kernel": f"{top['kernel']} {top['dims']}", "what": what, "bound": "tensor", "achieved": top["tflops"], "peak": peak,
             "unit": "TFLOP/s", "frac": round(top["tflops"] / peak, 4), "frac_burst": round(top["tflops"] / peaks["bf16_tflops"], 4),
+            "achieved_executed": executed, "frac_executed": round(executed / peak, 4),
+            "note": "achieved counts the algorithmic FLOPs (all 27 taps, SURVEY.md a13); *_executed discounts the zero-padded depth "
+                    "taps the kernel skips",
             "avg_launch_ms": round(top["ms"] / max(top["launches"], 1), 4), "flop_per_launch": top["flop"] // max(top["launches"], 1),
             "share_of_pass": round(top["ms"] / sum(r["ms"] for r in rows), 4), "traffic": traffic, "traffic_source": src,
             "peak_source": f"{peak_src} (sustained bf16)"}
@@ -290,7 +307,7 @@ def head_voxels_per_s(torch, dist=None, world: int = 1, steps: int = 3) -> dict:
         rows = prof.table(2)
         peaks, peak_src = measured_peaks()
         line["frac_of_tensor_peak"] = round(line["tflops_per_gpu"] / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), 4)
-        line["layers"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops") if k in r} for r in rows]
+        line["layers"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops", "tflops_executed") if k in r} for r in rows]
         line["roofline"] = _roofline_of(rows, peaks, peak_src, "r02_ncu_traffic.json", "dominant kernel of the head forward")
     return line
 

@@ -6,7 +6,7 @@ object is missing or a call fails, a :class:`CryovitB200Error` is raised.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
 import os
@@ -19,7 +19,7 @@ class CryovitB200Error(RuntimeError):
     """A call across the C ABI returned a non-zero code, or the CUDA library is unavailable."""
 
 
-P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
+P, I64, I32, F32, F64 = c_void_p, c_int64, c_int, c_float, c_double
 
 # name -> argtypes; every function returns int except the two diagnostics. Mirrors include/cryovit_b200.h.
 SIGNATURES: dict[str, list] = {
@@ -70,6 +70,12 @@ SIGNATURES: dict[str, list] = {
     "cvit_adamw_f32": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, F32, P],
     "cvit_conv3d_wpack8_gelu": [P, P, P, P, I64, I64, I64, I32, P],
     "cvit_conv3d_wpack8_final": [P, P, P, P, P, I64, I64, I64, P],
+    "cvit_linear_bias_cfirst_f16_gn": [P, I64, P, P, P, I64, I64, I64, I64, I32, P, I64, P],
+    "cvit_linear_bias_gelu_bf16_gn": [P, I64, P, P, P, I64, I64, I64, I64, P, I64, P],
+    "cvit_convT_1x2x2_ndhwc_gn": [P, P, P, P, I64, I64, I64, I64, I64, P, I64, P],
+    "cvit_groupnorm_fold": [P, I64, I64, I64, I64, F64, P, P, F32, P, P, P, I64, I64, I64, I32, P, P, P],
+    "cvit_conv3d_dilated_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_conv3d_halo_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_set_gemm_pair": [I32],  # returns the previous setting, not an error code (use load().cvit_set_gemm_pair)
 }
 
@@ -93,6 +99,8 @@ def load() -> ctypes.CDLL:
     lib.cvit_abi_version.argtypes = []
     lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
     lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
+    lib.cvit_groupnorm_fold_ab_elems.restype = c_int64
+    lib.cvit_groupnorm_fold_ab_elems.argtypes = [c_int64, c_int64]
     lib.cvit_conv3d_wpack_weight_bytes.restype = c_int64
     lib.cvit_conv3d_wpack_weight_bytes.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():

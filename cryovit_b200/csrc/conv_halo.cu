@@ -42,9 +42,10 @@ struct HaloCfg {
   // MMAs (K = 16) per in-plane row of taps: Cin >= 16 -> 3 taps x Cin/16; Cin == 8 -> 2 (tap pairs)
   static constexpr int MMA_PER_KH = CIN >= 16 ? 3 * (CIN / 16) : 2;
   static constexpr int W_BYTES = 9 * MMA_PER_KH * 2 * COUT * 16;  // [kd*3+kh][mma][2 K chunks][Cout][16 B]
-  static constexpr int STAGES_RAW = (200 * 1024 - W_BYTES) / STAGE;
+  static constexpr int TAB_BYTES = 64 * COUT * 4;           // bias table of a folded GroupNorm (HaloArgs::bias_table)
+  static constexpr int STAGES_RAW = (200 * 1024 - W_BYTES - TAB_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE + W_BYTES + 256 + 1024;
+  static constexpr int SMEM = STAGES * STAGE + W_BYTES + TAB_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = COUT <= 16 ? 32 : 2 * COUT;   // two accumulators
   static_assert(CIN == 8 || CIN == 16 || CIN == 32, "narrow layers only");
   static_assert(COUT == 16 || COUT == 32, "MMA N (zero-padded output channels)");
@@ -54,6 +55,8 @@ struct HaloCfg {
 struct HaloArgs {
   const __nv_bfloat16* w_img;  // host-arranged smem image of the weights, HaloCfg::W_BYTES
   const float* bias;           // [COUT] (zero padded)
+  const float* bias_table;     // optional fp32 [64][COUT]: per-voxel bias row by in-bounds tap masks (folded GroupNorm,
+                               // see gn_fold.cu / GemmArgs::bias_table); replaces `bias` when non-null
   __nv_bfloat16* out;          // [D, H, W, n_valid]
   int D, H, W, dil, n_valid;
   int act;  // 1 = GELU (inference), 0 = store the pre-activation (training forward, input gradients)
@@ -84,7 +87,8 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sIn = smem_base;
   const uint32_t sW = smem_base + STAGES * Cfg::STAGE;
-  const uint32_t sBar = sW + Cfg::W_BYTES;
+  const uint32_t sTab = sW + Cfg::W_BYTES;
+  const uint32_t sBar = sTab + Cfg::TAB_BYTES;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES;
   const uint32_t bar_tfull = sBar + 16 * STAGES, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -99,6 +103,11 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
     const uint4* src = reinterpret_cast<const uint4*>(args.w_img);
     uint4* dst = reinterpret_cast<uint4*>(smem_gen + (sW - smem_base));
     for (int i = threadIdx.x; i < Cfg::W_BYTES / 16; i += CH_THREADS) dst[i] = __ldg(src + i);
+    if (args.bias_table) {
+      const uint4* tsrc = reinterpret_cast<const uint4*>(args.bias_table);
+      uint4* tdst = reinterpret_cast<uint4*>(smem_gen + (sTab - smem_base));
+      for (int i = threadIdx.x; i < Cfg::TAB_BYTES / 16; i += CH_THREADS) tdst[i] = __ldg(tsrc + i);
+    }
   }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -224,6 +233,17 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
       const int h = h0 + hl, w = w0 + wl;
       if (h < args.H && w < args.W) {
         __nv_bfloat16* o = args.out + (((int64_t)d * args.H + h) * args.W + w) * args.n_valid;
+        if (args.bias_table) {
+          // folded GroupNorm: this voxel's bias row by which taps are inside the volume (mostly row 63: a broadcast read)
+          const int dm = (d >= args.dil ? 1 : 0) | (d + args.dil < args.D ? 2 : 0);
+          const int hm = (h >= 1 ? 1 : 0) | (h + 1 < args.H ? 2 : 0), wm = (w >= 1 ? 1 : 0) | (w + 1 < args.W ? 2 : 0);
+          const float4* row = reinterpret_cast<const float4*>(smem_gen + (sTab - smem_base)) + ((dm * 4 + hm) * 4 + wm) * (COUT / 4);
+#pragma unroll
+          for (int c = 0; c < COUT / 4; ++c) {
+            const float4 tb = row[c];
+            bias_r[4 * c] = tb.x; bias_r[4 * c + 1] = tb.y; bias_r[4 * c + 2] = tb.z; bias_r[4 * c + 3] = tb.w;
+          }
+        }
         // math for all COUT channels without branches (activation switch hoisted), then predicated 16-byte stores
         uint32_t pk[COUT / 2];
         if (args.act) {
@@ -308,9 +328,29 @@ extern "C" int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const fl
   return cvit_conv3d_halo_ndhwc_act(x, w_img, bias, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, 1, stream);
 }
 
+static int conv3d_halo_impl(const void* x, const void* w_img, const float* bias, const float* bias_table, void* out, int64_t D,
+                           int64_t H, int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                           void* stream);
+
 extern "C" int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
                                           int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
                                           void* stream) {
+  return conv3d_halo_impl(x, w_img, bias, nullptr, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, act, stream);
+}
+
+// The convolution after a folded GroupNorm: per-voxel bias rows from the 64-row table (see gn_fold.cu), + GELU.
+extern "C" int cvit_conv3d_halo_ndhwc_tab(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                                          int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, void* stream) {
+  if (!bias_table || (reinterpret_cast<uintptr_t>(bias_table) & 15u)) {
+    set_error("conv3d_halo_tab: a 16-byte aligned bias table is required");
+    return CVIT_ERR_INVALID;
+  }
+  return conv3d_halo_impl(x, w_img, bias_table + 63 * Cout_pad, bias_table, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, 1, stream);
+}
+
+static int conv3d_halo_impl(const void* x, const void* w_img, const float* bias, const float* bias_table, void* out, int64_t D,
+                           int64_t H, int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                           void* stream) {
   if (!x || !w_img || !bias || !out || D <= 0 || H <= 0 || W <= 0 || dil <= 0 || Cout_valid <= 0 || Cout_valid > Cout_pad ||
       (Cout_valid % 8) != 0) {
     set_error("conv3d_halo: bad arguments (D=%lld H=%lld W=%lld Cin=%lld Cout=%lld/%lld dil=%lld)", (long long)D, (long long)H,
@@ -331,6 +371,7 @@ extern "C" int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, cons
   a.dil = (int)dil;
   a.n_valid = (int)Cout_valid;
   a.act = act;
+  a.bias_table = bias_table;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32 && Cout_pad == 32) return launch_halo<32, 32>(x, a, st);
   if (Cin == 32 && Cout_pad == 16) return launch_halo<32, 16>(x, a, st);

@@ -304,6 +304,39 @@ int cvit_linear_bias_cfirst_f16(const void* At, int64_t ldat, const void* W, con
   return gemm_rows_mn(At, ldat, W, a, (cudaStream_t)stream);
 }
 
+// GroupNorm-producer variants (see GemmArgs::gn_partials): same GEMM, plus per-(32-row block, group) statistics.
+static int check_gn(const float* partials, int64_t cpg, int64_t N) {
+  if (!partials || (cpg != 4 && cpg != 8) || (N % 32) != 0 || (reinterpret_cast<uintptr_t>(partials) & 7u)) {
+    set_error("gn producer: partials must be a non-null 8-byte aligned buffer, channels per group 4 or 8 (got %lld)", (long long)cpg);
+    return CVIT_ERR_INVALID;
+  }
+  return CVIT_OK;
+}
+
+int cvit_linear_bias_cfirst_f16_gn(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                   int64_t M, int64_t N, int64_t K, int gelu, float* gn_partials, int64_t gn_cpg, void* stream) {
+  if (!bias) { set_error("linear_bias_cfirst: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_gn(gn_partials, gn_cpg, N)) return rc;
+  GemmArgs a = base_args(M, N, K, out, ldo);
+  a.bias = bias;
+  a.act = gelu ? 1 : 0;
+  a.fmt = GEMM_FMT_OPERANDS_F16;
+  a.gn_partials = gn_partials;
+  a.gn_cpg = (int)gn_cpg;
+  return gemm_rows_mn(At, ldat, W, a, (cudaStream_t)stream);
+}
+
+int cvit_linear_bias_gelu_bf16_gn(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                  int64_t M, int64_t N, int64_t K, float* gn_partials, int64_t gn_cpg, void* stream) {
+  if (!bias) { set_error("linear_bias: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_gn(gn_partials, gn_cpg, N)) return rc;
+  GemmArgs a = base_args(M, N, K, out, ldo);
+  a.bias = bias;
+  a.gn_partials = gn_partials;
+  a.gn_cpg = (int)gn_cpg;
+  return gemm_rows(A, lda, W, a, EPI_BIAS_GELU, (cudaStream_t)stream);
+}
+
 int cvit_linear_swiglu_fmt(const void* A, int64_t lda, const void* W12i, const float* bias12i, void* out,
                            int64_t ldo, int64_t M, int64_t N2, int64_t K, int fmt, void* stream) {
   if (!bias12i) { set_error("linear_swiglu: bias is required"); return CVIT_ERR_INVALID; }
@@ -390,6 +423,39 @@ int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bi
   a.c3 = (int)Cout;
   a.act = act;
   return gemm_rows(x, Cin, w_sub, a, EPI_CONVT_GELU, (cudaStream_t)stream);
+}
+
+int cvit_convT_1x2x2_ndhwc_gn(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                              int64_t W, int64_t Cin, int64_t Cout, float* gn_partials, int64_t gn_cpg, void* stream) {
+  if (!bias4) { set_error("convT: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_gn(gn_partials, gn_cpg, 4 * Cout)) return rc;
+  if (Cout % gn_cpg) { set_error("convT_gn: %lld channels do not split into groups of %lld", (long long)Cout, (long long)gn_cpg); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(D * H * W, 4 * Cout, Cin, out, Cout);
+  a.bias = bias4;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.c3 = (int)Cout;
+  a.act = 1;
+  a.gn_partials = gn_partials;
+  a.gn_cpg = (int)gn_cpg;
+  return gemm_rows(x, Cin, w_sub, a, EPI_CONVT_GELU, (cudaStream_t)stream);
+}
+
+// Consumer variant (see GemmArgs::bias_table): the convolution after a folded GroupNorm.
+int cvit_conv3d_dilated_ndhwc_tab(const void* x, const void* w_taps, const float* bias_table, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  void* stream) {
+  if (!bias_table || (reinterpret_cast<uintptr_t>(bias_table) & 15u)) { set_error("conv3d_tab: a 16-byte aligned bias table is required"); return CVIT_ERR_INVALID; }
+  GemmArgs a = base_args(D * H * W, Cout, Cin, out, Cout_valid);
+  a.bias = bias_table + 63 * Cout;  // the all-taps-inside row; the kernel swaps in the voxel's own row
+  a.bias_table = bias_table;
+  a.D = (int)D;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.dil = (int)dil;
+  a.n_valid = (int)Cout_valid;
+  a.act = 1;
+  return conv3_rows(x, w_taps, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -51,6 +51,18 @@ struct GemmArgs {
   int n_valid;        // columns >= n_valid are computed (zero-padded weights) but never stored
   int act;            // EPI_BIAS_GELU / EPI_CONVT_GELU: 1 = GELU (inference), 0 = store the pre-activation (training, dgrad)
   int fmt;            // GEMM_FMT_* bits: 16-bit type of the operands / of the stored output (0 = bf16 everywhere)
+  // GroupNorm fused into its neighbours (head inference, models/cryovit.py:56 SynthesisBlock.layers[0]):
+  //  * PRODUCER side (EPI_BIAS_GELU on plain rows, EPI_CONVT_GELU): gn_partials != null -> every epilogue warp also
+  //    writes, per 32-row block and per group of gn_cpg consecutive output columns, the (sum, sum of squares) of the
+  //    values it stores: fp32 [ceil(M/32)][N / gn_cpg][2], one plain store per entry (each entry has exactly one
+  //    owner, so the later fixed-order reduction is deterministic). N == n_valid is required.
+  //  * CONSUMER side (EPI_BIAS_GELU with AMODE_CONV3): bias_table != null -> the bias of an output voxel is row
+  //    ((dm*4 + hm)*4 + wm) of fp32 [64][N], where the 2-bit masks say which of the taps -1 / +1 along depth (dilated),
+  //    height and width fall inside the volume. With the GroupNorm affine folded into the weights (w' = w * a_c) the
+  //    shift b_c contributes  sum over the IN-BOUNDS taps of sum_c w[tap][c] * b_c, which depends on exactly that.
+  float* gn_partials;
+  int gn_cpg;
+  const float* bias_table;
 };
 // A and B hold IEEE fp16 instead of bf16 (same type on both sides: tcgen05 kind::f16 rule); EPI_BIAS / _GELU / _SWIGLU
 // store fp16 instead of bf16. fp16 keeps three more mantissa bits than bf16 for operands whose range is bounded
@@ -356,6 +368,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[it].x), "=f"(x[it].y), "=f"(x[it].z), "=f"(x[it].w) : "r"(addr));
       }
     };
+    // GroupNorm statistics of what this warp stores for one 32-column chunk: this lane's 4 columns x 8 rows, summed
+    // over the rows of the lanes that share the columns (and over the lane pair that shares an 8-column group), one
+    // (sum, sum of squares) store per group by its first lane. row0 = first of the warp's 32 rows (a multiple of 32).
+    auto gn_stats = [&](const float4 (&v)[8], const int (&grow)[8], int row0, int ncol) {
+      float sm = 0.f, sq = 0.f;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (grow[it] >= 0) {
+          sm += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+          sq += (v[it].x * v[it].x + v[it].y * v[it].y) + (v[it].z * v[it].z + v[it].w * v[it].w);
+        }
+      }
+      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+      if (args.gn_cpg == 8) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      }
+      if (rsub == 0 && (args.gn_cpg == 4 || (jc & 1) == 0)) {
+        float2* dst = reinterpret_cast<float2*>(args.gn_partials) + (size_t)(row0 >> 5) * (args.N / args.gn_cpg) + ncol / args.gn_cpg;
+        *dst = make_float2(sm, sq);
+      }
+    };
     for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const TileCoord t = coord(tile);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
@@ -408,6 +445,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int ocol = EPI == EPI_BIAS_SWIGLU ? (t.n0 >> 1) + c0 + jc * 4 : ncol;
           __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(args.out) + ocol;
           // branch-free row loops (uniform switches hoisted, stores predicated) so the rows' chains interleave
+          if (EPI == EPI_BIAS_GELU && AMODE == AMODE_CONV3 && args.bias_table) {
+            // folded GroupNorm: the bias row depends on which taps of this voxel are inside the volume
+            const int dm = (t.d >= args.dil ? 1 : 0) | (t.d + args.dil < args.D ? 2 : 0);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = q * 32 + it * 4 + rsub;
+              const int hl = r / args.BW, h = t.h0 + hl, w = t.w0 + (r - hl * args.BW);
+              const int hm = (h >= 1 ? 1 : 0) | (h + 1 < args.H ? 2 : 0), wm = (w >= 1 ? 1 : 0) | (w + 1 < args.W ? 2 : 0);
+              const float4 tb = __ldg(reinterpret_cast<const float4*>(args.bias_table + ((dm * 4 + hm) * 4 + wm) * args.N + ncol));
+              xs[it].x += tb.x - b4.x; xs[it].y += tb.y - b4.y; xs[it].z += tb.z - b4.z; xs[it].w += tb.w - b4.w;
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             xs[it].x += b4.x; xs[it].y += b4.y; xs[it].z += b4.z; xs[it].w += b4.w;
@@ -425,6 +474,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               gelu_erf2(xs[it].z, xs[it].w);
             }
           }
+          if (EPI == EPI_BIAS_GELU && AMODE != AMODE_CONV3 && args.gn_partials)
+            gn_stats(xs, grow_it, t.m0 + (SUB == 1 ? 0 : sub * GEMM_BM) + q * 32, ncol);
           uint2 pk[8];
           if (out_f16) {
 #pragma unroll
@@ -509,7 +560,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               gelu_erf2(o0, o1);
               gelu_erf2(o2, o3);
               pk[it] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+              xs[it] = make_float4(o0, o1, o2, o3);
             }
+            // statistics for the GroupNorm that follows: columns (i, j, co) -> groups of gn_cpg channels per sub-pixel
+            if (args.gn_partials) gn_stats(xs, grow_it, t.m0 + (SUB == 1 ? 0 : sub * GEMM_BM) + q * 32, ncol);
           } else {
 #pragma unroll
             for (int it = 0; it < 8; ++it)

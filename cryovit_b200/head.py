@@ -6,8 +6,10 @@ call surface: ``forward_volume(x[B,C,D,h,w]) -> clipped logits [B,1,D,16h,16w]``
 ``forward(batch) -> probabilities [B,D,16h,16w]``.
 
 Device layout: every intermediate volume is channels-last bf16 ``[D, H, W, C]``; convolutions are implicit GEMMs on
-tcgen05 (TMA box loads whose out-of-bounds zero fill is the "same" padding), GroupNorm is a two-pass HBM-bound
-kernel, ConvTranspose(1,2,2) is a GEMM with a pixel-shuffle store, and the 8-channel tail runs on CUDA cores.
+tcgen05 (TMA box loads whose out-of-bounds zero fill is the "same" padding), ConvTranspose(1,2,2) is a GEMM with a
+pixel-shuffle store. GroupNorm never touches the volume on its own: its statistics come out of the epilogue of the
+layer that produces its input, its scale is folded into the weights of the convolution that follows and its shift into
+a 64-row border-aware bias table (csrc/gn_fold.cu); ``fuse_groupnorm=False`` keeps the two-pass kernel (A/B, tests).
 ``in_channels`` generalises the reference's hard-wired 1536 (BASELINE config 1 feeds ViT-S features, 384).
 """
 from __future__ import annotations
@@ -83,8 +85,9 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
 
 
 class CryoVITHeadB200:
-    def __init__(self, in_channels: int = 1536):
+    def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool = True):
         self.in_channels = in_channels
+        self.fuse_groupnorm = fuse_groupnorm
         self.device: torch.device | None = None
         self._sd_cpu: dict | None = None
         self._w: dict = {}
@@ -140,8 +143,17 @@ class CryoVITHeadB200:
                     hb = torch.zeros(cp)
                     hb[:c2] = sd[p + key + ".bias"]
                     halo[tag] = (bf(halo_weight_image(sd[p + key + ".weight"], cp)), f32(hb), cp)
+            # fp32 originals in the operand layout of the convolution that follows the GroupNorm (folded per volume)
+            if "a" in halo:
+                a32, a_layout, a_cp = f32(halo_weight_image(sd[p + "1.weight"], halo["a"][2])), ops.LAYOUT_HALO, halo["a"][2]
+                a_bias = halo["a"][1]
+            else:
+                a32, a_layout, a_cp, a_bias = f32(_conv_taps(sd[p + "1.weight"], c2p)).reshape(-1), ops.LAYOUT_TAPS, c2p, f32(ba)
             blocks.append({
-                "halo": halo,
+                "halo": halo, "a_w32": a32, "a_layout": a_layout, "a_cp": a_cp, "a_bias": a_bias,
+                "a_fold": torch.empty(a32.numel(), device=dev, dtype=torch.bfloat16),
+                "a_table": torch.empty(64 * a_cp, device=dev, dtype=torch.float32),
+                "gn_ab": ops.groupnorm_fold_ab(c1, max(8, c1 // 8), dev),
                 "groups": max(8, c1 // 8), "gn_w": f32(sd[p + "0.weight"]), "gn_b": f32(sd[p + "0.bias"]),
                 "a_w": bf(_conv_taps(sd[p + "1.weight"], c2p)), "a_b": f32(ba), "d1": d1,
                 "b_w": bf(_conv_taps(sd[p + "3.weight"], c2p)), "b_b": f32(bb), "d2": d2,
@@ -178,28 +190,56 @@ class CryoVITHeadB200:
         w_ = self._w
         y = self._buf("pong", D * h * w * 1024).view(D * h * w, 1024)
         vox0 = D * h * w
+        fuse = self.fuse_groupnorm
+        blocks = w_["blocks"]
+        # GroupNorm statistics ride on the producer of each normalised tensor: [32-row block][group (x sub-pixel)][2]
+        cpg = [b["c1"] // b["groups"] for b in blocks]
+        partials = None
+        if fuse:
+            need = ops.gn_partials_numel(vox0, 1024, cpg[0])
+            Hc, Wc = h, w
+            for bi in range(len(blocks) - 1):
+                need = max(need, ops.gn_partials_numel(D * Hc * Wc, 4 * blocks[bi]["c3"], cpg[bi + 1]))
+                Hc, Wc = 2 * Hc, 2 * Wc
+            partials = self._buf("gn_partials", need, torch.float32)
         if features.dtype == torch.float16 and "proj_w16" in w_ and vox0 % 8 == 0 and C % 8 == 0 and C >= 64:
             # the on-disk layout (C, D*h*w) IS the A operand (MN-major): no channels-last copy of the features
-            ops.linear_bias_cfirst(features.contiguous().view(C, vox0), w_["proj_w16"], w_["proj_b"], y, gelu=True)
+            if fuse:
+                ops.linear_bias_cfirst_gn(features.contiguous().view(C, vox0), w_["proj_w16"], w_["proj_b"], y, partials, cpg[0])
+            else:
+                ops.linear_bias_cfirst(features.contiguous().view(C, vox0), w_["proj_w16"], w_["proj_b"], y, gelu=True)
             self.launches += 1
         else:
             x = self._buf("ping", vox0 * max(C, 1024)).narrow(0, 0, vox0 * C).view(D, h, w, C)
             ops.features_to_ndhwc(features.contiguous(), x)
-            ops.linear_bias(x.view(vox0, C), w_["proj_w"], w_["proj_b"], y, gelu=True)
+            if fuse:
+                ops.linear_bias_gelu_gn(x.view(vox0, C), w_["proj_w"], w_["proj_b"], y, partials, cpg[0])
+            else:
+                ops.linear_bias(x.view(vox0, C), w_["proj_w"], w_["proj_b"], y, gelu=True)
             self.launches += 2
         cur, H, W = y.view(D, h, w, 1024), h, w
         stats = self._buf("gn_stats", 256, torch.float32)
         names = ["ping", "pong"]
         flip = 0  # cur lives in "pong"
-        for b in w_["blocks"]:
+        prod_rows, prod_cols = vox0, 1024  # GEMM rows / columns of the layer that produced `cur`
+        for bi, b in enumerate(blocks):
             c1, c2, c3 = b["c1"], b["c2"], b["c3"]
             vox = D * H * W
-            ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            if "a" in b["halo"]:
-                ops.conv3d_halo(cur, b["halo"]["a"][0], b["halo"]["a"][1], nxt, b["d1"], b["halo"]["a"][2])
+            if fuse:
+                # statistics -> scale / shift -> folded weights + border-aware bias table -> convolution of the RAW tensor
+                ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3, b["gn_ab"],
+                                   b["a_w32"], b["a_fold"], c1, b["a_cp"], b["a_layout"], b["a_bias"], b["a_table"])
+                if "a" in b["halo"]:
+                    ops.conv3d_halo_tab(cur, b["a_fold"], b["a_table"], nxt, b["d1"], b["a_cp"])
+                else:
+                    ops.conv3d_dilated_tab(cur, b["a_fold"].view(27 * b["a_cp"], c1), b["a_table"], nxt, b["d1"])
             else:
-                ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
+                ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
+                if "a" in b["halo"]:
+                    ops.conv3d_halo(cur, b["halo"]["a"][0], b["halo"]["a"][1], nxt, b["d1"], b["halo"]["a"][2])
+                else:
+                    ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
             if "b" in b["halo"]:
@@ -208,10 +248,14 @@ class CryoVITHeadB200:
                 ops.conv3d_dilated(cur, b["b_w"], b["b_b"], nxt, b["d2"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], 4 * vox * c3).view(D, 2 * H, 2 * W, c3)
-            ops.convT_1x2x2(cur, b["t_w"], b["t_b"], nxt)
+            if fuse and bi + 1 < len(blocks):
+                ops.convT_1x2x2_gn(cur, b["t_w"], b["t_b"], nxt, partials, cpg[bi + 1])
+                prod_rows, prod_cols = vox, 4 * c3
+            else:
+                ops.convT_1x2x2(cur, b["t_w"], b["t_b"], nxt)
             cur, flip = nxt, flip ^ 1
             H, W = 2 * H, 2 * W
-            self.launches += 6  # memset + 2 GroupNorm kernels are counted as 3
+            self.launches += 5 if fuse else 6  # fused: finalize + fold + 3 layers; else memset + 2 GroupNorm kernels + 3 layers
         scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
         logits = torch.empty(D, H, W, device=self.device) if want_logits else None
         probs = torch.empty(D, H, W, device=self.device) if want_probs else None

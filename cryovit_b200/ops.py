@@ -109,6 +109,74 @@ def linear_bias_cfirst(at, w, bias, out, gelu: bool = False) -> None:
               _chk(out, BF16, "out"), out.stride(0), M, N, K, int(gelu), _stream())
 
 
+def gn_partials_numel(rows: int, n_cols: int, cpg: int) -> int:
+    """fp32 elements of the statistics buffer a GroupNorm-producer call needs for ``rows`` GEMM rows and ``n_cols`` output
+    columns in groups of ``cpg``: tiles may overhang the rows by up to a 1024-row tile."""
+    return (rows + 1023) // 1024 * 32 * (n_cols // cpg) * 2
+
+
+def linear_bias_cfirst_gn(at, w, bias, out, partials, cpg: int) -> None:
+    """linear_bias_cfirst + GELU that also writes the GroupNorm statistics of its output (see the header)."""
+    K, M = at.shape
+    N = w.shape[0]
+    if partials.numel() < gn_partials_numel(M, N, cpg):
+        raise _lib.CryovitB200Error("linear_bias_cfirst_gn: statistics buffer too small")
+    _lib.call("cvit_linear_bias_cfirst_f16_gn", _chk(at, F16, "at"), at.stride(0), _chk(w, F16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, N, K, 1, _chk(partials, F32, "partials"), cpg, _stream())
+
+
+def linear_bias_gelu_gn(a, w, bias, out, partials, cpg: int) -> None:
+    M, K = a.shape
+    N = w.shape[0]
+    if partials.numel() < gn_partials_numel(M, N, cpg):
+        raise _lib.CryovitB200Error("linear_bias_gelu_gn: statistics buffer too small")
+    _lib.call("cvit_linear_bias_gelu_bf16_gn", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, N, K, _chk(partials, F32, "partials"), cpg, _stream())
+
+
+def convT_1x2x2_gn(x, w_sub, bias4, out, partials, cpg: int) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_sub.shape[0] // 4
+    if partials.numel() < gn_partials_numel(D * H * W, 4 * Cout, cpg):
+        raise _lib.CryovitB200Error("convT_1x2x2_gn: statistics buffer too small")
+    _lib.call("cvit_convT_1x2x2_ndhwc_gn", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, _chk(partials, F32, "partials"), cpg, _stream())
+
+
+LAYOUT_TAPS, LAYOUT_HALO = 0, 1
+
+
+def groupnorm_fold_ab(channels: int, groups: int, device) -> torch.Tensor:
+    """The zero-filled scale / shift + scratch buffer groupnorm_fold works in (allocate once per layer)."""
+    return torch.zeros(int(_lib.load().cvit_groupnorm_fold_ab_elems(channels, groups)), device=device, dtype=F32)
+
+
+def groupnorm_fold(partials, rows: int, partial_cols: int, groups: int, n_per_group: int, gamma, beta, eps: float, ab,
+                   w32, w_out, cin: int, cout_pad: int, layout: int, bias, table) -> None:
+    """Statistics partials of ``rows`` producer rows -> scale / shift (ab) -> folded bf16 weights + 64-row bias table."""
+    C = gamma.numel()
+    if w32.numel() != 27 * cin * cout_pad or w_out.numel() != w32.numel() or table.numel() != 64 * cout_pad or \
+            ab.numel() < _lib.load().cvit_groupnorm_fold_ab_elems(C, groups):
+        raise _lib.CryovitB200Error("groupnorm_fold: buffer sizes do not match the layer")
+    _lib.call("cvit_groupnorm_fold", _chk(partials, F32, "partials"), (rows + 31) // 32, partial_cols, groups, C, float(n_per_group),
+              _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta"), float(eps), _chk(ab, F32, "ab"), _chk(w32, F32, "w32"),
+              _chk(w_out, BF16, "w_out"), w32.numel(), cin, cout_pad, layout, _chk(bias, F32, "bias"), _chk(table, F32, "table"),
+              _stream())
+
+
+def conv3d_dilated_tab(x, w_taps, table, out, dil: int) -> None:
+    D, H, W, Cin = x.shape
+    Cout = w_taps.shape[0] // 27
+    _lib.call("cvit_conv3d_dilated_ndhwc_tab", _chk(x, BF16, "x"), _chk(w_taps, BF16, "w_taps"), _chk(table, F32, "table"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, _stream())
+
+
+def conv3d_halo_tab(x, w_img, table, out, dil: int, cout_pad: int) -> None:
+    D, H, W, Cin = x.shape
+    _lib.call("cvit_conv3d_halo_ndhwc_tab", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, _stream())
+
+
 def linear_swiglu(a, w12i, bias12i, out) -> None:
     M, K = a.shape
     N2 = w12i.shape[0]

@@ -175,6 +175,43 @@ int cvit_features_f32_to_ndhwc_bf16(const float* features_f32, void* out_bf16, i
 int cvit_groupnorm_ndhwc_bf16(const void* x, void* out, const float* gamma, const float* beta, float* stats,
                               int64_t DHW, int64_t C, int64_t G, float eps, void* stream);
 
+/* GroupNorm FOLDED into its neighbours (head inference; models/cryovit.py:56-62 GroupNorm -> Conv3d of a SynthesisBlock).
+ * Instead of a statistics pass and a normalise pass over the volume:
+ *   producer  cvit_linear_bias_cfirst_f16_gn / cvit_linear_bias_gelu_bf16_gn (layers[0] + GELU) and
+ *             cvit_convT_1x2x2_ndhwc_gn (the previous block's ConvTranspose3d + GELU) are the plain kernels of the same name
+ *             that ALSO write gn_partials: fp32 [rows32][N / gn_cpg][2] = (sum, sum of squares) of the stored values per
+ *             32-row block and per group of gn_cpg (4 or 8) consecutive output columns. rows32 must cover
+ *             ceil(M / 1024) * 32 row blocks (tiles may overhang M); entries past ceil(M / 32) are not defined.
+ *   fold      cvit_groupnorm_fold reduces the first rows32 = ceil(M / 32) row blocks in a fixed order to the per-channel
+ *             scale a_c = gamma_c * rstd_g and shift b_c = beta_c - mean_g * a_c (ab: fp32 [2][channels]; partial_cols =
+ *             N / gn_cpg = reps * groups; n_per_group = values per group), then writes w_out = bf16(w32 * a_ci) in the
+ *             consumer's operand layout (layout 0: cvit_conv3d_dilated_ndhwc's [27 * cout_pad][cin]; layout 1:
+ *             cvit_conv3d_halo_ndhwc's image, cin a multiple of 16; n_elems = 27 * cin * cout_pad; w32 is the fp32 original in
+ *             the same layout) and table: fp32 [64][cout_pad], row (dm*4 + hm)*4 + wm = bias + sum over the taps that the
+ *             2-bit masks (bit 0: the -1 tap, bit 1: the +1 tap along depth / height / width is inside the volume) admit
+ *             of sum_ci w32[tap][co][ci] * b_ci -- zero padding pads the NORMALISED tensor, so a border voxel must not
+ *             receive the shift through taps that fall outside.
+ *   consumer  cvit_conv3d_dilated_ndhwc_tab / cvit_conv3d_halo_ndhwc_tab convolve the un-normalised volume with the folded
+ *             weights and add each voxel's table row (+ GELU). */
+int cvit_linear_bias_cfirst_f16_gn(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                   int64_t M, int64_t N, int64_t K, int gelu, float* gn_partials, int64_t gn_cpg, void* stream);
+int cvit_linear_bias_gelu_bf16_gn(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                  int64_t M, int64_t N, int64_t K, float* gn_partials, int64_t gn_cpg, void* stream);
+int cvit_convT_1x2x2_ndhwc_gn(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                              int64_t W, int64_t Cin, int64_t Cout, float* gn_partials, int64_t gn_cpg, void* stream);
+ /* ab must hold cvit_groupnorm_fold_ab_elems(channels, groups) floats (scale / shift first, then the reduction's
+  * scratch), 16-byte aligned, ZERO-FILLED once before its first use (the kernels leave the scratch as they found it). */
+int64_t cvit_groupnorm_fold_ab_elems(int64_t channels, int64_t groups);
+int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_t partial_cols, int64_t groups, int64_t channels,
+                        double n_per_group, const float* gamma, const float* beta, float eps, float* ab,
+                        const float* w32, void* w_out, int64_t n_elems, int64_t cin, int64_t cout_pad, int layout,
+                        const float* bias, float* table, void* stream);
+int cvit_conv3d_dilated_ndhwc_tab(const void* x, const void* w_taps, const float* bias_table, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  void* stream);
+int cvit_conv3d_halo_ndhwc_tab(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, void* stream);
+
 /* Conv3d(Cin -> Cout, kernel 3, padding "same", dilation (dil,1,1)) + bias + GELU as an implicit GEMM
  * (models/cryovit.py:70-73).  x bf16 [D,H,W,Cin]; w_taps bf16 [27 * Cout, Cin] with tap = (kd*3+kh)*3+kw
  * (Cout may be zero-padded to a multiple of 32, Cout_valid = real channel count = row pitch of out). */

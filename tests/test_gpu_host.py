@@ -267,7 +267,7 @@ def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path)
     pd.DataFrame(rows, columns=["sample", "tomo_name", "split_id"]).to_csv(tmp_path / "data" / "csv" / "splits.csv", index=False)
     common = ["model=cryovit", "+experiments=multi_mito", "datamodule.sample=[A,B]", "datamodule.split_id=0", "+model.in_channels=384",
               f"paths.data_dir={tmp_path / 'data'}", f"paths.exp_dir={tmp_path / 'exp'}"]
-    cfg = compose("train_model", common + ["trainer.max_epochs=10", "model.lr=2e-3"])
+    cfg = compose("train_model", common + ["trainer.max_epochs=30", "model.lr=2e-3"])
     validate_experiment_config(cfg, "train_model")
     weights = train_model.run_trainer(cfg)
     assert weights == tmp_path / "exp" / "multi_cryovit_mito" / "A_B" / "split_0" / "weights.pt" and weights.exists()
@@ -313,7 +313,7 @@ def test_two_gpu_torchrun_train_then_eval_entry_points(cuda_lib, tmp_path):
     launch = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
               "--master-port", str(29600 + os.getpid() % 300)]
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run(launch + ["-m", "cryovit.training.train_model", *common, "trainer.max_epochs=12", "model.lr=2e-3"],
+    r = subprocess.run(launch + ["-m", "cryovit.training.train_model", *common, "trainer.max_epochs=30", "model.lr=2e-3"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Error" not in r.stderr or "Traceback" not in r.stderr, r.stderr

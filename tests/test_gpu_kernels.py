@@ -399,6 +399,91 @@ def test_convT(cuda_lib, D, H, W, Cin, Cout):
     _close(out, ref, atol=2e-2, rtol=1e-2, what="convT")
 
 
+def _gn_partial_sums(partials, rows, n_cols, cpg):
+    """[32-row block][n_cols / cpg][2] statistics buffer -> (sum, sum of squares) per column group over the valid rows."""
+    pc = n_cols // cpg
+    p = partials[: (rows + 31) // 32 * pc * 2].view(-1, pc, 2).double().sum(0)
+    return p[:, 0], p[:, 1]
+
+
+@pytest.mark.parametrize("M,N,K,cpg", [(300, 1024, 384, 8), (4104, 1024, 1536, 8), (136, 1024, 1536, 8), (70, 256, 64, 4)])
+def test_groupnorm_statistics_from_the_projection_epilogue(cuda_lib, M, N, K, cpg):
+    """layers[0] + GELU that also emits the GroupNorm statistics of what it stores (both A layouts): per group of cpg
+    columns, the sums over all rows -- tiles overhanging M, CTA pairs and single CTAs -- against torch."""
+    from cryovit_b200 import ops
+    at = _rand(K, M, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2)
+    b = _rand(N, seed=3)
+    ref = F.gelu(at.float().t() @ w.half().float().t() + b).double()
+    rs, rq = ref.view(M, N // cpg, cpg).sum((0, 2)), (ref * ref).view(M, N // cpg, cpg).sum((0, 2))
+    for cfirst in (True, False):
+        if cfirst and (M % 8 or N % 128):
+            continue
+        out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        partials = torch.full((ops.gn_partials_numel(M, N, cpg),), float("nan"), device=DEV)
+        if cfirst:
+            ops.linear_bias_cfirst_gn(at, w.half(), b, out, partials, cpg)
+        else:
+            ops.linear_bias_gelu_gn(at.t().contiguous().bfloat16(), w.bfloat16(), b, out, partials, cpg)
+        _close(out, ref, atol=3e-2, rtol=2e-2, what="projection")
+        s, q = _gn_partial_sums(partials, M, N, cpg)
+        tol = 3e-2 if not cfirst else 1e-2  # the bf16 variant rounds A and W to bf16: compare loosely
+        assert torch.allclose(s, rs, rtol=tol, atol=tol * M ** 0.5 * cpg), (s - rs).abs().max()
+        assert torch.allclose(q, rq, rtol=tol, atol=tol * M ** 0.5), (q - rq).abs().max()
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout,cpg,Cn,dil,halo", [(3, 8, 16, 192, 128, 8, 64, 2, False), (5, 16, 24, 64, 32, 4, 32, 3, True),
+                                                        (4, 16, 16, 32, 32, 4, 16, 1, True), (9, 8, 8, 192, 128, 8, 64, 4, False)])
+def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, cpg, Cn, dil, halo):
+    """The fused GroupNorm chain of a SynthesisBlock boundary against torch: ConvTranspose3d + GELU (statistics from its
+    epilogue) -> GroupNorm(Cout / cpg groups, eps 1e-3, random affine) -> dilated Conv3d(Cout -> Cn) + GELU, where the
+    normalisation is folded into the convolution's weights and its 64-row border-aware bias table. Every border voxel
+    (all three axes, dilated depth taps) must match: the shift may only arrive through taps inside the volume."""
+    from cryovit_b200 import ops
+    from cryovit_b200.head import _conv_taps, halo_weight_image
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    wt = _rand(Cin, Cout, 1, 2, 2, scale=Cin ** -0.5, seed=2)
+    bt = _rand(Cout, seed=3)
+    gamma, beta = 1.0 + 0.3 * _rand(Cout, seed=4), 0.5 * _rand(Cout, seed=5)
+    wc = _rand(Cn, Cout, 3, 3, 3, scale=(27 * Cout) ** -0.5, seed=6)
+    bc = _rand(Cn, seed=7)
+    G = Cout // cpg
+    # producer: transposed convolution + GELU with statistics
+    y = torch.empty(D, 2 * H, 2 * W, Cout, device=DEV, dtype=torch.bfloat16)
+    partials = torch.full((ops.gn_partials_numel(D * H * W, 4 * Cout, cpg),), float("nan"), device=DEV)
+    w_sub = wt[:, :, 0].permute(2, 3, 1, 0).reshape(4 * Cout, Cin).bfloat16().contiguous()
+    ops.convT_1x2x2_gn(x, w_sub, bt.repeat(4).contiguous(), y, partials, cpg)
+    yr = F.gelu(F.conv_transpose3d(x.float().permute(3, 0, 1, 2)[None], wt.bfloat16().float(), bt, stride=(1, 2, 2)))  # [1,Cout,D,2H,2W]
+    _close(y, yr[0].permute(1, 2, 3, 0), atol=3e-2, rtol=2e-2, what="convT")
+    # fold + consumer
+    cp = (32 if Cn > 16 else 16) if halo else max(32, Cn)
+    bias = torch.zeros(cp, device=DEV)
+    bias[:Cn] = bc
+    if halo:
+        w32, layout = halo_weight_image(wc.cpu(), cp).to(DEV), ops.LAYOUT_HALO
+    else:
+        w32, layout = _conv_taps(wc.cpu(), cp).reshape(-1).to(DEV), ops.LAYOUT_TAPS
+    ab = ops.groupnorm_fold_ab(Cout, G, DEV)
+    w_fold = torch.empty(w32.numel(), device=DEV, dtype=torch.bfloat16)
+    table = torch.empty(64 * cp, device=DEV)
+    vox = D * 2 * H * 2 * W
+    ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32, w_fold, Cout, cp, layout, bias, table)
+    # scale / shift against torch's statistics of the STORED tensor
+    ys = y.float().permute(3, 0, 1, 2).reshape(G, -1)
+    mean, var = ys.mean(1), ys.var(1, unbiased=False)
+    a_ref = gamma * (var + 1e-3).rsqrt().repeat_interleave(cpg)
+    b_ref = beta - mean.repeat_interleave(cpg) * a_ref
+    assert torch.allclose(ab[:Cout], a_ref, rtol=2e-3, atol=1e-4) and torch.allclose(ab[Cout:2 * Cout], b_ref, rtol=2e-3, atol=2e-3)
+    out = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
+    if halo:
+        ops.conv3d_halo_tab(y, w_fold, table, out, dil, cp)
+    else:
+        ops.conv3d_dilated_tab(y, w_fold.view(27 * cp, Cout), table, out, dil)
+    ref = F.gelu(F.conv3d(F.group_norm(y.float().permute(3, 0, 1, 2)[None], G, gamma, beta, eps=1e-3), wc, bc, padding="same",
+                          dilation=(dil, 1, 1)))[0].permute(1, 2, 3, 0)
+    _close(out, ref, atol=4e-2, rtol=3e-2, what=f"GroupNorm folded into conv (halo={halo})")
+
+
 @pytest.mark.parametrize("D,H,W", [(3, 16, 128), (2, 10, 200)])
 def test_head_tail(cuda_lib, D, H, W):
     from cryovit_b200 import ops
