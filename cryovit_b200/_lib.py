@@ -76,6 +76,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_groupnorm_fold": [P, I64, I64, I64, I64, F64, P, P, F32, P, P, P, I64, I64, I64, I32, P, P, P],
     "cvit_conv3d_dilated_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_conv3d_halo_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "cvit_conv3d_wpackn_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
     "cvit_set_gemm_pair": [I32],  # returns the previous setting, not an error code (use load().cvit_set_gemm_pair)
 }
 
@@ -99,6 +100,9 @@ def load() -> ctypes.CDLL:
     lib.cvit_abi_version.argtypes = []
     lib.cvit_conv3d_halo_weight_bytes.restype = c_int64
     lib.cvit_conv3d_halo_weight_bytes.argtypes = [c_int64, c_int64]
+    for fn in (lib.cvit_conv3d_wpackn_group, lib.cvit_conv3d_wpackn_weight_bytes):
+        fn.restype = c_int64
+        fn.argtypes = [c_int64, c_int64]
     lib.cvit_groupnorm_fold_ab_elems.restype = c_int64
     lib.cvit_groupnorm_fold_ab_elems.argtypes = [c_int64, c_int64]
     lib.cvit_conv3d_wpack_weight_bytes.restype = c_int64

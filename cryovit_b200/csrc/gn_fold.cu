@@ -95,11 +95,22 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restri
 //   LAYOUT_TAPS: conv3d_dilated (gemm.cu conv3_rows): [tap = (kd*3+kh)*3+kw][coutp][cin]
 //   LAYOUT_HALO: conv3d_halo (conv_halo.cu, cin >= 16): [kd*3+kh][mma i = kw * (cin/16) + c2][k chunk][coutp][8],
 //                channel = c2*16 + k*8 + e
-enum { LAYOUT_TAPS = 0, LAYOUT_HALO = 1 };
+//   LAYOUT_WPACKN: conv3d_wpackn (conv_wpackn.cu): [kd*3+kh][K step][2 chunks][n = j_out * coutp + co][8], chunk k = 2 step + c
+//                = (window voxel j_in, c_hi) = divmod(k, cin / 8), channel = c_hi*8 + e, tap kw = j_in - j_out; `p` voxels per row
+enum { LAYOUT_TAPS = 0, LAYOUT_HALO = 1, LAYOUT_WPACKN = 2 };
 
 template <int LAYOUT>
-__device__ __forceinline__ void decode(int64_t idx, int cin, int coutp, int& tap, int& co, int& ci) {
-  if (LAYOUT == LAYOUT_TAPS) {
+__device__ __forceinline__ void decode(int64_t idx, int cin, int coutp, int& tap, int& co, int& ci, int p = 0) {
+  if (LAYOUT == LAYOUT_WPACKN) {
+    const int ch = cin / 8, ksteps = (p + 2) * ch / 2, n_cols = p * coutp;
+    const int e = (int)(idx & 7);
+    int64_t r = idx >> 3;
+    r /= n_cols;  // the column (j_out, co) does not matter for the channel
+    const int c = (int)(r & 1);
+    const int st = (int)((r >> 1) % ksteps);
+    ci = ((2 * st + c) % ch) * 8 + e;
+    tap = co = 0;
+  } else if (LAYOUT == LAYOUT_TAPS) {
     ci = (int)(idx % cin);
     const int64_t r = idx / cin;
     co = (int)(r % coutp);
@@ -120,61 +131,53 @@ __device__ __forceinline__ void decode(int64_t idx, int cin, int coutp, int& tap
   }
 }
 
-// blocks [0, gridDim.x - coutp): w_out = bf16(w32 * a[ci]) over the whole image (grid stride)
-// blocks [gridDim.x - coutp, gridDim.x): one output channel each: B[tap] = sum_ci w32 * b[ci], then the 64 table rows
+// blocks [0, coutp): one output channel each: B[tap] = sum_ci w32 * b[ci], then the 64 table rows (first in the grid:
+//                    they are the longer-running blocks)
+// blocks [coutp, gridDim.x): w_out = bf16(w32 * a[ci]) over the whole image (grid stride)
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ w_out, int64_t n_elems,
                                                       int cin, int coutp, const float* __restrict__ ab, int C,
-                                                      const float* __restrict__ bias, float* __restrict__ table) {
-  const int n_scale_blocks = (int)gridDim.x - coutp;
-  if ((int)blockIdx.x < n_scale_blocks) {
+                                                      const float* __restrict__ bias, float* __restrict__ table, int p) {
+  if ((int)blockIdx.x >= coutp) {
+    const unsigned n_scale_blocks = gridDim.x - (unsigned)coutp, b0 = blockIdx.x - (unsigned)coutp;
     // n_elems < 2^31 (checked by the launcher): 32-bit index arithmetic, one divide per element
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)n_elems; idx += (unsigned)n_scale_blocks * blockDim.x) {
+    for (unsigned idx = b0 * blockDim.x + threadIdx.x; idx < (unsigned)n_elems; idx += n_scale_blocks * blockDim.x) {
       int ci;
       if (LAYOUT == LAYOUT_TAPS) {
         ci = (int)(idx % (unsigned)cin);
       } else {
         int tap, co;
-        decode<LAYOUT>((int64_t)idx, cin, coutp, tap, co, ci);
+        decode<LAYOUT>((int64_t)idx, cin, coutp, tap, co, ci, p);
       }
       w_out[idx] = __float2bfloat16(w32[idx] * ab[ci]);
     }
     return;
   }
-  const int co = (int)blockIdx.x - n_scale_blocks;
-  __shared__ float part[27][8];  // per tap, per warp
+  const int co = (int)blockIdx.x;
   __shared__ float B[27];
-  float acc[27];
-#pragma unroll
-  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-  // this channel's weights: 27 taps x cin, walked in a fixed order per thread
-  for (int j = threadIdx.x; j < 27 * cin; j += blockDim.x) {
-    const int tap = j / cin, ci = j - tap * cin;
-    int64_t idx;
-    if (LAYOUT == LAYOUT_TAPS) {
-      idx = ((int64_t)tap * coutp + co) * cin + ci;
-    } else {
-      const int steps = cin / 16, t9 = tap / 3, kw = tap - t9 * 3;
-      const int c2 = ci >> 4, k = (ci >> 3) & 1, e = ci & 7;
-      idx = ((((int64_t)t9 * (3 * steps) + kw * steps + c2) * 2 + k) * coutp + co) * 8 + e;
-    }
-    const float v = w32[idx] * ab[C + ci];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] += (t == tap) ? v : 0.f;
-  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp w takes taps w, w + 8, ...; its lanes stride over the input channels (coalesced), fixed-order shuffle tree
+  for (int tap = warp; tap < 27; tap += 8) {
+    float acc = 0.f;
+    for (int ci = lane; ci < cin; ci += 32) {
+      int64_t idx;
+      if (LAYOUT == LAYOUT_TAPS) {
+        idx = ((int64_t)tap * coutp + co) * cin + ci;
+      } else if (LAYOUT == LAYOUT_WPACKN) {
+        // the tap's weights as they sit in the column of output voxel j_out = 0: window voxel j_in = kw
+        const int ch = cin / 8, ksteps = (p + 2) * ch / 2, n_cols = p * coutp, t9 = tap / 3, kw = tap - t9 * 3;
+        const int k = kw * ch + (ci >> 3);
+        idx = ((((int64_t)t9 * ksteps + (k >> 1)) * 2 + (k & 1)) * n_cols + co) * 8 + (ci & 7);
+      } else {
+        const int steps = cin / 16, t9 = tap / 3, kw = tap - t9 * 3;
+        const int c2 = ci >> 4, k = (ci >> 3) & 1, e = ci & 7;
+        idx = ((((int64_t)t9 * (3 * steps) + kw * steps + c2) * 2 + k) * coutp + co) * 8 + e;
+      }
+      acc += w32[idx] * ab[C + ci];
+    }
 #pragma unroll
-  for (int t = 0; t < 27; ++t) {
-    float v = acc[t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) part[t][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 27) {
-    float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += part[threadIdx.x][w];
-    B[threadIdx.x] = v;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) B[tap] = acc;
   }
   __syncthreads();
   if (threadIdx.x < 64) {
@@ -198,6 +201,8 @@ __global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ 
 
 using namespace cvit;
 
+extern "C" int64_t cvit_conv3d_wpackn_group(int64_t Cin, int64_t Cout_pad);
+
 // See include/cryovit_b200.h.
 // fp32 elements the `ab` argument of cvit_groupnorm_fold must hold: scale / shift, the ticket, the slice sums.
 extern "C" int64_t cvit_groupnorm_fold_ab_elems(int64_t channels, int64_t groups) {
@@ -210,10 +215,22 @@ extern "C" int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_
                                    const float* bias, float* table, void* stream) {
   if (!partials || !gamma || !beta || !ab || !w32 || !w_out || !bias || !table || rows32 <= 0 || groups <= 0 ||
       channels % groups != 0 || partial_cols % groups != 0 || cin != channels || cout_pad <= 0 || n_per_group <= 0.0 ||
-      n_elems != 27 * cin * cout_pad || n_elems >= (1ll << 31) || (layout != LAYOUT_TAPS && layout != LAYOUT_HALO) || (layout == LAYOUT_HALO && (cin % 16) != 0)) {
+      n_elems >= (1ll << 31) || layout < LAYOUT_TAPS || layout > LAYOUT_WPACKN || (layout == LAYOUT_HALO && (cin % 16) != 0)) {
     set_error("groupnorm_fold: bad arguments (rows32=%lld cols=%lld G=%lld C=%lld cin=%lld coutp=%lld n=%lld layout=%d)", (long long)rows32,
               (long long)partial_cols, (long long)groups, (long long)channels, (long long)cin, (long long)cout_pad, (long long)n_elems,
               layout);
+    return CVIT_ERR_INVALID;
+  }
+  int p = 0;
+  if (layout == LAYOUT_WPACKN) {
+    p = (int)cvit_conv3d_wpackn_group(cin, cout_pad);
+    if (p == 0 || n_elems != 9 * (p + 2) * cin * p * cout_pad) {
+      set_error("groupnorm_fold: no W-packed layout for cin=%lld cout_pad=%lld (or n_elems=%lld does not match it)", (long long)cin,
+                (long long)cout_pad, (long long)n_elems);
+      return CVIT_ERR_INVALID;
+    }
+  } else if (n_elems != 27 * cin * cout_pad) {
+    set_error("groupnorm_fold: n_elems=%lld does not match 27 x %lld x %lld", (long long)n_elems, (long long)cin, (long long)cout_pad);
     return CVIT_ERR_INVALID;
   }
   const int cpg = (int)(channels / groups);
@@ -239,9 +256,12 @@ extern "C" int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_
   const unsigned grid = (unsigned)(scale_blocks + cout_pad);
   if (layout == LAYOUT_TAPS)
     gn_fold_kernel<LAYOUT_TAPS><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,
-                                                     (int)channels, bias, table);
-  else
+                                                     (int)channels, bias, table, 0);
+  else if (layout == LAYOUT_HALO)
     gn_fold_kernel<LAYOUT_HALO><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,
-                                                     (int)channels, bias, table);
+                                                     (int)channels, bias, table, 0);
+  else
+    gn_fold_kernel<LAYOUT_WPACKN><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,
+                                                       (int)channels, bias, table, p);
   return check_launch("gn_fold_kernel");
 }

@@ -60,6 +60,22 @@ def halo_weight_image(w: torch.Tensor, cout_pad: int) -> torch.Tensor:
     return img.reshape(-1)
 
 
+def wpackn_weight_image(w: torch.Tensor, cout_pad: int, P: int) -> torch.Tensor:
+    """Conv3d weight [Cout, Cin, 3, 3, 3] (Cin 16 or 32) -> the banded shared-memory image of csrc/conv_wpackn.cu (fp32, flat):
+    [kd*3+kh][K step][2 chunks][n = j_out * cout_pad + co][8], where chunk k = 2 step + c is (window voxel j_in, channel
+    chunk c_hi) = divmod(k, Cin / 8) -- the window of a group of P output voxels starts one voxel to their left -- and the
+    entry is w[co, c_hi*8 + e, kd, kh, kw] with kw = j_in - j_out when that is a tap (0..2), zero otherwise."""
+    cout, cin = w.shape[:2]
+    ch = cin // 8
+    wt = torch.zeros(9, 3, cout_pad, ch, 8, device=w.device)
+    wt[:, :, :cout] = w.float().permute(2, 3, 4, 0, 1).reshape(9, 3, cout, ch, 8)
+    img = torch.zeros(9, P + 2, ch, P, cout_pad, 8, device=w.device)
+    for j_out in range(P):
+        for kw in range(3):
+            img[:, j_out + kw, :, j_out] = wt[:, kw].permute(0, 2, 1, 3)  # [9, ch, cout_pad, 8]
+    return img.reshape(-1)
+
+
 _BANDS: dict = {}
 
 
@@ -85,9 +101,10 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
 
 
 class CryoVITHeadB200:
-    def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool = True):
+    def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool = True, wpack_narrow: bool = True):
         self.in_channels = in_channels
         self.fuse_groupnorm = fuse_groupnorm
+        self.wpack_narrow = wpack_narrow  # False: the 16- / 32-channel layers run on the per-tap halo kernel (A/B, tests)
         self.device: torch.device | None = None
         self._sd_cpu: dict | None = None
         self._w: dict = {}
@@ -136,13 +153,18 @@ class CryoVITHeadB200:
             ba, bb = torch.zeros(c2p), torch.zeros(c2p)
             ba[:c2], bb[:c2] = sd[p + "1.bias"], sd[p + "3.bias"]
             wT = sd[p + "5.weight"]  # [c2, c3, 1, 2, 2]
-            halo = {}
+            halo, wpn = {}, {}
             for tag, key, cin in (("a", "1", c1), ("b", "3", c2)):
                 if cin in (8, 16, 32):  # narrow layer: shared-memory halo kernel (csrc/conv_halo.cu)
                     cp = 32 if c2 > 16 else 16
                     hb = torch.zeros(cp)
                     hb[:c2] = sd[p + key + ".bias"]
                     halo[tag] = (bf(halo_weight_image(sd[p + key + ".weight"], cp)), f32(hb), cp)
+                    P = ops.wpackn_group(cin, cp)
+                    if P:  # ... or, on planes whose width is a multiple of P, P voxels per tensor-core row (csrc/conv_wpackn.cu)
+                        img32 = f32(wpackn_weight_image(sd[p + key + ".weight"], cp, P))
+                        wpn[tag] = {"P": P, "cp": cp, "w32": img32, "w": img32.to(torch.bfloat16),
+                                    "table": f32(hb.repeat(64)), "fold": torch.empty_like(img32, dtype=torch.bfloat16)}
             # fp32 originals in the operand layout of the convolution that follows the GroupNorm (folded per volume)
             if "a" in halo:
                 a32, a_layout, a_cp = f32(halo_weight_image(sd[p + "1.weight"], halo["a"][2])), ops.LAYOUT_HALO, halo["a"][2]
@@ -150,6 +172,7 @@ class CryoVITHeadB200:
             else:
                 a32, a_layout, a_cp, a_bias = f32(_conv_taps(sd[p + "1.weight"], c2p)).reshape(-1), ops.LAYOUT_TAPS, c2p, f32(ba)
             blocks.append({
+                "wpn": wpn,
                 "halo": halo, "a_w32": a32, "a_layout": a_layout, "a_cp": a_cp, "a_bias": a_bias,
                 "a_fold": torch.empty(a32.numel(), device=dev, dtype=torch.bfloat16),
                 "a_table": torch.empty(64 * a_cp, device=dev, dtype=torch.float32),
@@ -226,23 +249,36 @@ class CryoVITHeadB200:
             c1, c2, c3 = b["c1"], b["c2"], b["c3"]
             vox = D * H * W
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
+            wa = b["wpn"].get("a") if self.wpack_narrow and "a" in b["wpn"] and W % b["wpn"]["a"]["P"] == 0 else None
+            wb = b["wpn"].get("b") if self.wpack_narrow and "b" in b["wpn"] and W % b["wpn"]["b"]["P"] == 0 else None
             if fuse:
                 # statistics -> scale / shift -> folded weights + border-aware bias table -> convolution of the RAW tensor
-                ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3, b["gn_ab"],
-                                   b["a_w32"], b["a_fold"], c1, b["a_cp"], b["a_layout"], b["a_bias"], b["a_table"])
-                if "a" in b["halo"]:
+                if wa is not None:
+                    ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3,
+                                       b["gn_ab"], wa["w32"], wa["fold"], c1, wa["cp"], ops.LAYOUT_WPACKN, b["a_bias"], b["a_table"])
+                    ops.conv3d_wpackn(cur, wa["fold"], b["a_table"], nxt, b["d1"], wa["cp"])
+                else:
+                    ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3,
+                                       b["gn_ab"], b["a_w32"], b["a_fold"], c1, b["a_cp"], b["a_layout"], b["a_bias"], b["a_table"])
+                if wa is not None:
+                    pass
+                elif "a" in b["halo"]:
                     ops.conv3d_halo_tab(cur, b["a_fold"], b["a_table"], nxt, b["d1"], b["a_cp"])
                 else:
                     ops.conv3d_dilated_tab(cur, b["a_fold"].view(27 * b["a_cp"], c1), b["a_table"], nxt, b["d1"])
             else:
                 ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
-                if "a" in b["halo"]:
+                if wa is not None:
+                    ops.conv3d_wpackn(cur, wa["w"], wa["table"], nxt, b["d1"], wa["cp"])
+                elif "a" in b["halo"]:
                     ops.conv3d_halo(cur, b["halo"]["a"][0], b["halo"]["a"][1], nxt, b["d1"], b["halo"]["a"][2])
                 else:
                     ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            if "b" in b["halo"]:
+            if wb is not None:
+                ops.conv3d_wpackn(cur, wb["w"], wb["table"], nxt, b["d2"], wb["cp"])
+            elif "b" in b["halo"]:
                 ops.conv3d_halo(cur, b["halo"]["b"][0], b["halo"]["b"][1], nxt, b["d2"], b["halo"]["b"][2])
             else:
                 ops.conv3d_dilated(cur, b["b_w"], b["b_b"], nxt, b["d2"])

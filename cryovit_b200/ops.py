@@ -143,7 +143,7 @@ def convT_1x2x2_gn(x, w_sub, bias4, out, partials, cpg: int) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, Cout, _chk(partials, F32, "partials"), cpg, _stream())
 
 
-LAYOUT_TAPS, LAYOUT_HALO = 0, 1
+LAYOUT_TAPS, LAYOUT_HALO, LAYOUT_WPACKN = 0, 1, 2
 
 
 def groupnorm_fold_ab(channels: int, groups: int, device) -> torch.Tensor:
@@ -155,7 +155,7 @@ def groupnorm_fold(partials, rows: int, partial_cols: int, groups: int, n_per_gr
                    w32, w_out, cin: int, cout_pad: int, layout: int, bias, table) -> None:
     """Statistics partials of ``rows`` producer rows -> scale / shift (ab) -> folded bf16 weights + 64-row bias table."""
     C = gamma.numel()
-    if w32.numel() != 27 * cin * cout_pad or w_out.numel() != w32.numel() or table.numel() != 64 * cout_pad or \
+    if w_out.numel() != w32.numel() or table.numel() != 64 * cout_pad or \
             ab.numel() < _lib.load().cvit_groupnorm_fold_ab_elems(C, groups):
         raise _lib.CryovitB200Error("groupnorm_fold: buffer sizes do not match the layer")
     _lib.call("cvit_groupnorm_fold", _chk(partials, F32, "partials"), (rows + 31) // 32, partial_cols, groups, C, float(n_per_group),
@@ -175,6 +175,20 @@ def conv3d_halo_tab(x, w_img, table, out, dil: int, cout_pad: int) -> None:
     D, H, W, Cin = x.shape
     _lib.call("cvit_conv3d_halo_ndhwc_tab", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
               _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, _stream())
+
+
+def wpackn_group(cin: int, cout_pad: int) -> int:
+    """Voxels per tensor-core row of the W-packed narrow-layer kernel for this layer; 0 = no such kernel."""
+    return int(_lib.load().cvit_conv3d_wpackn_group(cin, cout_pad))
+
+
+def conv3d_wpackn(x, w_img, table, out, dil: int, cout_pad: int, act: bool = True) -> None:
+    """Narrow-layer (Cin 16 / 32) dilated conv + bias-table row + GELU, P output voxels of a row per MMA row (csrc/conv_wpackn.cu)."""
+    D, H, W, Cin = x.shape
+    if w_img.numel() * 2 != _lib.load().cvit_conv3d_wpackn_weight_bytes(Cin, cout_pad):
+        raise _lib.CryovitB200Error("conv3d_wpackn: weight image does not match the layer")
+    _lib.call("cvit_conv3d_wpackn_ndhwc", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, int(act), _stream())
 
 
 def linear_swiglu(a, w12i, bias12i, out) -> None:

@@ -212,6 +212,17 @@ int cvit_conv3d_dilated_ndhwc_tab(const void* x, const void* w_taps, const float
 int cvit_conv3d_halo_ndhwc_tab(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
                                int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, void* stream);
 
+/* The same narrow-layer convolution (Conv3d 3x3x3, dilation (dil,1,1), "same", + bias + GELU; models/cryovit.py:68-78) with
+ * P consecutive output voxels along W packed into one tensor-core row (csrc/conv_wpackn.cu): (Cin, Cout_pad) = (32,16) and
+ * (32,32) with P = 2, (16,16) with P = 4; W must be a multiple of P.  cvit_conv3d_wpackn_group returns P (0: no such kernel),
+ * cvit_conv3d_wpackn_weight_bytes the size of the banded weight image [kd*3+kh][K step][2][j_out * Cout_pad + co][8] that
+ * cryovit_b200.head.wpackn_weight_image builds (layout 2 of cvit_groupnorm_fold).  bias_table: fp32 [64][Cout_pad] as for the
+ * *_tab kernels (64 equal rows for a plain bias).  act: 1 = GELU, 0 = store the pre-activation. */
+int64_t cvit_conv3d_wpackn_group(int64_t Cin, int64_t Cout_pad);
+int64_t cvit_conv3d_wpackn_weight_bytes(int64_t Cin, int64_t Cout_pad);
+int cvit_conv3d_wpackn_ndhwc(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                             int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act, void* stream);
+
 /* Conv3d(Cin -> Cout, kernel 3, padding "same", dilation (dil,1,1)) + bias + GELU as an implicit GEMM
  * (models/cryovit.py:70-73).  x bf16 [D,H,W,Cin]; w_taps bf16 [27 * Cout, Cin] with tap = (kd*3+kh)*3+kw
  * (Cout may be zero-padded to a multiple of 32, Cout_valid = real channel count = row pitch of out). */

@@ -399,6 +399,30 @@ def test_convT(cuda_lib, D, H, W, Cin, Cout):
     _close(out, ref, atol=2e-2, rtol=1e-2, what="convT")
 
 
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(3, 16, 16, 32, 16, 1), (5, 20, 40, 32, 16, 2), (4, 33, 64, 16, 16, 1), (9, 16, 32, 32, 32, 4),
+                                                 (2, 50, 36, 16, 16, 1), (7, 8, 6, 32, 16, 8), (3, 48, 256, 32, 16, 2)])
+def test_conv3d_wpackn(cuda_lib, D, H, W, Cin, Cout, dil):
+    """Narrow-layer convolution with P output voxels of a row per tensor-core row (banded weights, csrc/conv_wpackn.cu)
+    against torch on the same bf16 operands: ragged tiles in H and W, dilated depth taps leaving the volume (D <= dil),
+    plain bias (64 equal table rows), with and without the GELU."""
+    from cryovit_b200 import ops
+    from cryovit_b200.head import wpackn_weight_image
+    cp = 32 if Cout > 16 else 16
+    P = ops.wpackn_group(Cin, cp)
+    assert P in (2, 4) and W % P == 0
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, 3, scale=(27 * Cin) ** -0.5, seed=2).bfloat16()
+    b = _rand(Cout, seed=3)
+    bias = torch.zeros(cp, device=DEV)
+    bias[:Cout] = b
+    img = wpackn_weight_image(w.float().cpu(), cp, P).to(DEV).bfloat16()
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding="same", dilation=(dil, 1, 1))[0].permute(1, 2, 3, 0)
+    for act in (True, False):
+        out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.conv3d_wpackn(x, img, bias.repeat(64).contiguous(), out, dil, cp, act=act)
+        _close(out, F.gelu(ref) if act else ref, atol=2e-2, rtol=1e-2, what=f"conv3d_wpackn act={act}")
+
+
 def _gn_partial_sums(partials, rows, n_cols, cpg):
     """[32-row block][n_cols / cpg][2] statistics buffer -> (sum, sum of squares) per column group over the valid rows."""
     pc = n_cols // cpg
@@ -482,6 +506,17 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
     ref = F.gelu(F.conv3d(F.group_norm(y.float().permute(3, 0, 1, 2)[None], G, gamma, beta, eps=1e-3), wc, bc, padding="same",
                           dilation=(dil, 1, 1)))[0].permute(1, 2, 3, 0)
     _close(out, ref, atol=4e-2, rtol=3e-2, what=f"GroupNorm folded into conv (halo={halo})")
+    if halo and ops.wpackn_group(Cout, cp):  # the same fold into the W-packed kernel's banded weight image
+        from cryovit_b200.head import wpackn_weight_image
+        w32p = wpackn_weight_image(wc.cpu(), cp, ops.wpackn_group(Cout, cp)).to(DEV)
+        w_foldp = torch.empty(w32p.numel(), device=DEV, dtype=torch.bfloat16)
+        table2 = torch.empty(64 * cp, device=DEV)
+        ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32p, w_foldp, Cout, cp,
+                           ops.LAYOUT_WPACKN, bias, table2)
+        assert torch.allclose(table2, table, rtol=1e-4, atol=1e-5)
+        out2 = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.conv3d_wpackn(y, w_foldp, table2, out2, dil, cp)
+        _close(out2, ref, atol=4e-2, rtol=3e-2, what="GroupNorm folded into the W-packed conv")
 
 
 @pytest.mark.parametrize("D,H,W", [(3, 16, 128), (2, 10, 200)])
