@@ -138,7 +138,7 @@ class CallProfiler:
     def executed_fraction(name: str, i) -> float:
         """Share of a dilated convolution's algorithmic FLOPs that the kernels execute: depth taps that fall outside
         [0, D) are skipped outright (with dilation 32 of 128 planes that is one tap in six)."""
-        if "conv3d_dilated" not in name and "conv3d_halo" not in name:
+        if "conv3d_dilated" not in name and "conv3d_halo" not in name and "conv3d_wpackn" not in name:
             return 1.0
         D, dil = i[0], i[6]
         valid = sum((d - dil >= 0) + 1 + (d + dil < D) for d in range(D))
@@ -146,6 +146,12 @@ class CallProfiler:
 
     FLOPS = {
         "cvit_linear_bias_cfirst_f16": lambda i: 2 * i[2] * i[3] * i[4],        # ldat, ldo, M, N, K, gelu
+        "cvit_linear_bias_cfirst_f16_gn": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_linear_bias_gelu_bf16_gn": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_conv3d_dilated_ndhwc_tab": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_halo_ndhwc_tab": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_wpackn_ndhwc": lambda i: CallProfiler._conv(i),
+        "cvit_convT_1x2x2_ndhwc_gn": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * 4 * i[4],
         "cvit_linear_bias_fmt": lambda i: 2 * i[2] * i[3] * i[4],
         "cvit_linear_bias_bf16_nvalid": lambda i: 2 * i[2] * i[3] * i[4],
         "cvit_conv3d_dilated_ndhwc": lambda i: CallProfiler._conv(i),
@@ -382,9 +388,9 @@ def head_train_voxels_per_s(torch, dist, world: int, steps: int = 3) -> dict:
         prof.close()
         rows = prof.table(1)
         peaks, peak_src = measured_peaks()
-        top = sorted(rows, key=lambda r: -r["ms"])[:10]
+        top = sorted(rows, key=lambda r: -r["ms"])
         line["eager_forward_backward_ms"] = round(sum(r["ms"] for r in rows), 2)
-        line["kernels_top10"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops") if k in r} for r in top]
+        line["kernels"] = [{k: r[k] for k in ("kernel", "dims", "ms", "launches", "tflops") if k in r} for r in top if r["ms"] >= 0.05]
         line["model_tflops_per_step"] = round(3 * 94864 * D * H * W / 1e12, 2)
         line["frac_of_tensor_peak"] = round(3 * 94864 * D * H * W / ms / 1e9 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), 4)
         line["roofline"] = _roofline_of(rows, peaks, peak_src, "r02_ncu_traffic.json", "dominant tensor-core kernel of one training step")

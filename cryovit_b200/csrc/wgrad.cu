@@ -417,7 +417,7 @@ extern "C" int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, con
     set_error("wgrad_splitk: operands must be 16-byte aligned");
     return CVIT_ERR_INVALID;
   }
-  const int bn = N > 128 ? 256 : N > 64 ? 128 : N > 32 ? 64 : 32;
+  const int bn = N > 192 ? 256 : N > 128 ? 192 : N > 64 ? 128 : N > 32 ? 64 : 32;  // 192: one exact tile for the 192-channel layers
   // narrow outputs: pack several taps into the 128 MMA rows (see the header comment)
   const int Mp = (int)((M + 7) / 8 * 8);
   int pack = (M <= 64 && ntaps > 1) ? WG_BM / Mp : 1;
@@ -457,6 +457,7 @@ extern "C" int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, con
   cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
     case 256: return launch_wgrad<256>(tmA, tmB, a, st);
+    case 192: return launch_wgrad<192>(tmA, tmB, a, st);
     case 128: return launch_wgrad<128>(tmA, tmB, a, st);
     case 64: return launch_wgrad<64>(tmA, tmB, a, st);
     default: return launch_wgrad<32>(tmA, tmB, a, st);

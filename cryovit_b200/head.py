@@ -101,10 +101,14 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
 
 
 class CryoVITHeadB200:
-    def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool = True, wpack_narrow: bool = True):
+    def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool | None = None, wpack_narrow: bool | None = None):
+        import os
+
         self.in_channels = in_channels
-        self.fuse_groupnorm = fuse_groupnorm
-        self.wpack_narrow = wpack_narrow  # False: the 16- / 32-channel layers run on the per-tap halo kernel (A/B, tests)
+        # None: on, unless the environment says otherwise (A/B runs: CVIT_HEAD_FUSE_GN=0, CVIT_HEAD_WPACKN=0)
+        self.fuse_groupnorm = os.environ.get("CVIT_HEAD_FUSE_GN", "1") != "0" if fuse_groupnorm is None else fuse_groupnorm
+        # False: the 16- / 32-channel layers run on the per-tap halo kernel
+        self.wpack_narrow = os.environ.get("CVIT_HEAD_WPACKN", "1") != "0" if wpack_narrow is None else wpack_narrow
         self.device: torch.device | None = None
         self._sd_cpu: dict | None = None
         self._w: dict = {}

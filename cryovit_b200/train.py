@@ -23,7 +23,7 @@ import torch
 from . import ops
 from . import train_ops as T
 from ._lib import CryovitB200Error
-from .head import BLOCKS, state_dict_keys, wpack_weight_image
+from .head import BLOCKS, state_dict_keys, wpack_weight_image, wpackn_weight_image
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -86,7 +86,12 @@ class _Conv:
         b = torch.zeros(cp, device=x.device, dtype=F32)
         if bias is not None:
             b[:cout] = bias
-        if halo:
+        P = ops.wpackn_group(cin, cp) if halo and x.shape[2] % 4 == 0 else 0
+        if P:
+            # 16- / 32-channel layers (forward and input gradients alike): P voxels per tensor-core row (csrc/conv_wpackn.cu)
+            op = self.tr._pk(f"{self.key}/{tag}/wpackn", self.key, lambda w: wpackn_weight_image(wfn(w), cp, P))
+            ops.conv3d_wpackn(x, op, b.repeat(64), out, dil, cp, act=False)
+        elif halo:
             op = self.tr._pk(f"{self.key}/{tag}/halo", self.key, lambda w: _halo_image(wfn(w), cp))
             T.conv3d_halo_act(x, op, b, out, dil, cp, False)
         else:

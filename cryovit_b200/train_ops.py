@@ -127,6 +127,20 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
     if key not in _KOFFS:
         _KOFFS[key] = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
     koffs = _KOFFS[key]
+    # The GEMM's M is tiled in 128 rows, its N in 32 .. 256 columns: with Cout = 192 as M a quarter of every second MMA
+    # is padding. dW^T[t, ci, co] = sum_k xt[ci, k] dzt[co, k - koff_t] is the same sum with the roles (and the sign of
+    # the shift) swapped: Cin = 1024 tiles M exactly and 192 is one exact N tile.
+    swap = Cin % 128 == 0 and Cout % 128 != 0 and Cout <= 256
+    if swap:
+        nkey = ("neg",) + key
+        if nkey not in _KOFFS:
+            _KOFFS[nkey] = (-koffs).contiguous()
+        dwt = torch.zeros(3, 9, Cin, Cout, device=dev, dtype=F32)
+        xt = buf("xt0", Cin * pitch)[:Cin * pitch].view(Cin, pitch)
+        for kw in range(3):
+            to_cfirst_padded(x, xt, pd, 1, 1, kw - 1)
+            wgrad_splitk(xt, dzt, dwt[kw], _KOFFS[nkey], pitch)
+        return dwt.permute(1, 0, 3, 2).reshape(27, Cout, Cin)
     dw = torch.zeros(3, 9, Cout, Cin, device=dev, dtype=F32)
     if Cin in (8, 16, 32):  # all three shifted copies from one pass over x
         xts = [buf(f"xt{kw}", Cin * pitch)[:Cin * pitch].view(Cin, pitch) for kw in range(3)]

@@ -256,8 +256,10 @@ def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path)
     rng = np.random.default_rng(4)
     rows = []
     for s in ("A", "B"):
-        for i in range(3):
-            feats = rng.standard_normal((384, 4, 3, 3)).astype(np.float16)
+        for i in range(6):  # split 1 (three tomograms per sample) trains, split 0 is held out
+            # learnable AND generalising: channel 0 carries the label at amplitude 2, the other 383 channels are weak noise
+            feats = (0.1 * rng.standard_normal((384, 4, 3, 3))).astype(np.float16)
+            feats[0] = 2.0 * np.sign(rng.standard_normal((4, 3, 3)))
             lab = (np.repeat(np.repeat(feats[0].astype(np.float32), 16, axis=1), 16, axis=2) > 0).astype(np.int8)
             lab[0, :8] = -1  # some ignored voxels
             hdf.write_tomogram(tmp_path / "data" / "tomograms" / s / f"{s}{i}.hdf",
@@ -267,18 +269,19 @@ def test_train_then_eval_through_the_experiment_entry_points(cuda_lib, tmp_path)
     pd.DataFrame(rows, columns=["sample", "tomo_name", "split_id"]).to_csv(tmp_path / "data" / "csv" / "splits.csv", index=False)
     common = ["model=cryovit", "+experiments=multi_mito", "datamodule.sample=[A,B]", "datamodule.split_id=0", "+model.in_channels=384",
               f"paths.data_dir={tmp_path / 'data'}", f"paths.exp_dir={tmp_path / 'exp'}"]
-    cfg = compose("train_model", common + ["trainer.max_epochs=30", "model.lr=2e-3"])
+    cfg = compose("train_model", common + ["trainer.max_epochs=60", "model.lr=4e-4"])
     validate_experiment_config(cfg, "train_model")
     weights = train_model.run_trainer(cfg)
     assert weights == tmp_path / "exp" / "multi_cryovit_mito" / "A_B" / "split_0" / "weights.pt" and weights.exists()
 
     cfg = compose("eval_model", common)
     results = eval_model.run_trainer(cfg)
-    assert sorted(r.tomo_names[0] for r in results) == ["A0.hdf", "A2.hdf", "B0.hdf", "B2.hdf"]  # split 0 of both samples
+    assert sorted(r.tomo_names[0] for r in results) == ["A0.hdf", "A2.hdf", "A4.hdf", "B0.hdf", "B2.hdf", "B4.hdf"]  # split 0 of both samples
     for s in ("A", "B"):
         df = pd.read_csv(tmp_path / "exp" / "results" / "multi_cryovit_mito" / f"{s}_0.csv")
-        assert list(df.columns) == ["sample", "tomo_name", "dice_metric", "f1_metric", "split_id"] and len(df) == 2
-        assert (df["dice_metric"] > 0.5).all(), df  # the toy labels are learnable from feature channel 0
+        assert list(df.columns) == ["sample", "tomo_name", "dice_metric", "f1_metric", "split_id"] and len(df) == 3
+        # really learnt (predicting one class everywhere scores ~0.65 here), on HELD-OUT tomograms
+        assert (df["dice_metric"] > 0.85).all(), df
         pred = hdf.read_tomogram(tmp_path / "exp" / "predictions" / "multi_cryovit_mito" / s / f"{s}0.hdf")
         assert sorted(pred) == ["data", "mito", "mito_preds"] and pred["mito_preds"].shape == (4, 48, 48)
         assert pred["mito_preds"].dtype == np.float32 and pred["data"].dtype == np.uint8
@@ -299,8 +302,9 @@ def test_two_gpu_torchrun_train_then_eval_entry_points(cuda_lib, tmp_path):
     rng = np.random.default_rng(4)
     rows = []
     for s in ("A", "B"):
-        for i in range(4):
-            feats = rng.standard_normal((384, 4, 3, 3)).astype(np.float16)
+        for i in range(8):
+            feats = (0.1 * rng.standard_normal((384, 4, 3, 3))).astype(np.float16)
+            feats[0] = 2.0 * np.sign(rng.standard_normal((4, 3, 3)))
             lab = (np.repeat(np.repeat(feats[0].astype(np.float32), 16, axis=1), 16, axis=2) > 0).astype(np.int8)
             hdf.write_tomogram(tmp_path / "data" / "tomograms" / s / f"{s}{i}.hdf",
                                {"data": rng.integers(0, 256, (4, 48, 48), dtype=np.uint8), "labels/mito": lab, "dino_features": feats})
@@ -313,20 +317,20 @@ def test_two_gpu_torchrun_train_then_eval_entry_points(cuda_lib, tmp_path):
     launch = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
               "--master-port", str(29600 + os.getpid() % 300)]
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run(launch + ["-m", "cryovit.training.train_model", *common, "trainer.max_epochs=30", "model.lr=2e-3"],
+    r = subprocess.run(launch + ["-m", "cryovit.training.train_model", *common, "trainer.max_epochs=60", "model.lr=4e-4"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Error" not in r.stderr or "Traceback" not in r.stderr, r.stderr
     weights = tmp_path / "exp" / "multi_cryovit_mito" / "A_B" / "split_0" / "weights.pt"
     assert weights.exists(), r.stdout + r.stderr
-    assert "2 steps/rank" in r.stderr + r.stdout  # 4 training tomograms (split 1 of A and B) over 2 ranks
+    assert "4 steps/rank" in r.stderr + r.stdout  # 8 training tomograms (split 1 of A and B) over 2 ranks
     r = subprocess.run(launch + ["-m", "cryovit.training.eval_model", *common], cwd=root, env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     for s in ("A", "B"):
         df = pd.read_csv(tmp_path / "exp" / "results" / "multi_cryovit_mito" / f"{s}_0.csv")
-        assert sorted(df["tomo_name"]) == [f"{s}0.hdf", f"{s}2.hdf"], (df, r.stderr)  # both ranks' rows, merged by rank 0
-        assert (df["dice_metric"] > 0.5).all(), df
+        assert sorted(df["tomo_name"]) == [f"{s}{i}.hdf" for i in (0, 2, 4, 6)], (df, r.stderr)  # both ranks' rows, merged by rank 0
+        assert (df["dice_metric"] > 0.85).all(), df
 
 
 def test_baseline_config1_end_to_end_with_a_fitted_head(cuda_lib):

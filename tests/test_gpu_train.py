@@ -39,6 +39,8 @@ def test_gelu_fwd_bwd(cuda_lib):
 
 @pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(6, 12, 20, 64, 192, 2), (5, 16, 8, 32, 32, 1), (4, 9, 11, 16, 16, 1),
                                                  (3, 16, 16, 8, 8, 1), (9, 8, 8, 192, 64, 4),
+                                                 # Cin a multiple of 128, Cout = 192: operands swapped (dW^T, negated shifts), one exact 192-wide N tile
+                                                 (5, 8, 12, 128, 192, 2), (3, 8, 8, 192, 192, 1),
                                                  # 8 x 8 channels: warp-MMA kernel on the channels-last volumes (ragged tiles, dilation)
                                                  (5, 13, 150, 8, 8, 2), (4, 40, 272, 8, 8, 1), (1, 8, 128, 8, 8, 1),
                                                  (5, 13, 150, 16, 16, 2), (9, 20, 70, 32, 16, 4), (4, 24, 136, 32, 32, 1)])

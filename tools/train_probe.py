@@ -1,4 +1,6 @@
-"""Timing of one CryoVIT head training step at BASELINE config 5's crop: features (1536, 128, 32, 32), labels (128, 512, 512)."""
+"""Per-launch timing of one CryoVIT head training step at BASELINE config 5's crop (features (1536,128,32,32), labels
+(128,512,512)): an event pair around every call across the C ABI in one eager forward + backward, then the step time
+with eager launches and with the CUDA graph."""
 import os
 import sys
 from pathlib import Path
@@ -6,7 +8,7 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from cryovit_b200 import build, ops, train_ops  # noqa: E402
+from cryovit_b200 import _lib, build  # noqa: E402
 from cryovit_b200.train import CryoVITHeadTrainerB200  # noqa: E402
 
 build.build()
@@ -17,26 +19,21 @@ labels = (torch.rand(D, 16 * h, 16 * w, generator=g) < 0.1).float()
 labels[::5] = -1
 labels = labels.cuda()
 tr = CryoVITHeadTrainerB200(C)
-seq, active = [], False
-for mod, names in ((ops, ["features_to_ndhwc", "linear_bias", "groupnorm_ndhwc", "head_out_conv", "seg_stats"]),
-                   (train_ops, ["conv3d_dilated_act", "conv3d_halo_act", "convT_act", "gelu_fwd", "gelu_bwd", "dice_bwd", "colsum",
-                                "groupnorm_bwd", "pixel_unshuffle", "to_cfirst_padded", "to_cfirst_padded_x3", "wgrad_splitk", "linear_nvalid", "adamw"])):
-    for n in names:
-        orig = getattr(mod, n)
+orig, active, seq = _lib.call, False, []
 
-        def wrapped(*a, _o=orig, _n=n, **k):
-            if not active:
-                return _o(*a, **k)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = _o(*a, **k)
-            e.record()
-            tag = _n
-            if _n == "wgrad_splitk":
-                tag = f"wgrad_splitk M={a[2].shape[1]} N={a[2].shape[2]} taps={a[2].shape[0]} K={a[4]}"
-            seq.append((tag, s, e))
-            return r
-        setattr(mod, n, wrapped)
+
+def call(name, *a):
+    if not active:
+        return orig(name, *a)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    r = orig(name, *a)
+    e.record()
+    seq.append((name[5:], tuple(int(x) for x in a[:-1] if isinstance(x, int) and abs(x) < (1 << 40)), s, e))
+    return r
+
+
+_lib.call = call
 os.environ["CVIT_TRAIN_GRAPH"] = "0"  # per-kernel events need eager launches
 for _ in range(2):
     loss = tr.train_step(feats, labels)
@@ -50,13 +47,20 @@ e.record()
 torch.cuda.synchronize()
 active = False
 agg = {}
-for n, a, b in seq:
-    t = agg.setdefault(n, [0, 0.0])
+for n, dims, a, b in seq:
+    t = agg.setdefault((n, dims), [0, 0.0])
     t[0] += 1
     t[1] += a.elapsed_time(b)
-for n, (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{n:22s} x{cnt:3d} {ms:9.3f} ms")
-print(f"instrumented step {s.elapsed_time(e):.2f} ms (kernels {sum(v[1] for v in agg.values()):.2f} ms)")
+byname = {}
+for (n, dims), (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{n:28s} {str(dims):60s} x{cnt:3d} {ms:9.3f} ms")
+    t = byname.setdefault(n, [0, 0.0])
+    t[0] += cnt
+    t[1] += ms
+print("--- by entry point")
+for n, (cnt, ms) in sorted(byname.items(), key=lambda kv: -kv[1][1]):
+    print(f"{n:28s} x{cnt:3d} {ms:9.3f} ms")
+print(f"instrumented step {s.elapsed_time(e):.2f} ms (our kernels {sum(v[1] for v in agg.values()):.2f} ms over {len(seq)} launches)")
 ts = []
 for _ in range(3):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
