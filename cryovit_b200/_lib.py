@@ -77,6 +77,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_conv3d_dilated_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_conv3d_halo_ndhwc_tab": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_conv3d_wpackn_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
+    "cvit_wgrad_mn_ndhwc": [P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
     "cvit_set_gemm_pair": [I32],  # returns the previous setting, not an error code (use load().cvit_set_gemm_pair)
 }
 

@@ -167,8 +167,12 @@ def run_trainer(cfg) -> None:
 def _run_samples(cfg, paths, src_dir, dst_dir, csv_dir, image_dir, sample_names, rank, world) -> None:
     model_dir = cfg.get("model_dir") or paths.get("model_dir")
     model = load_model(model_dir, cfg.get("dino_variant") or dino_model[1], bool(cfg.get("allow_random_weights", False)))
+    import time
+
     for name in sample_names:
+        t0 = time.perf_counter()
         done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
                                image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)),
                                int(cfg.get("writers", 3)))
-        logging.info("rank %d/%d: %d tomograms of %s", rank, world, len(done), name)
+        logging.info("rank %d/%d: %d tomograms of %s in %.2f s (files in -> files out, %s container)", rank, world, len(done), name,
+                     time.perf_counter() - t0, hdf.backend())

@@ -229,12 +229,17 @@ class CryoVITHeadTrainerB200:
         ``_gelu_bwd_bias``, which produced dz)."""
         cin, cout = x.shape[-1], dz.shape[-1]
         dw = T.conv_weight_gradient(x, dz, dil, self._bufs.setdefault("wgrad_pool", {}))  # [27, cout, cin]
-        self.g[key_w].copy_(dw.view(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
+        self.g[key_w].copy_(dw.reshape(3, 3, 3, cout, cin).permute(3, 4, 0, 1, 2))
         self.launches += 7
 
     def _wgrad_rows(self, x_rows, dz_rows, xt=None):
         """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions). ``xt``:
         x already channels-first, bf16 [N, R] with R a multiple of 8 (then x_rows is not read)."""
+        if xt is None:  # straight from the row-major operands when the MN-major kernel takes the shapes (no transposed copies)
+            direct = T.rows_weight_gradient(x_rows, dz_rows)
+            if direct is not None:
+                self.launches += 1
+                return direct
         R, M = dz_rows.shape
         pitch = (R + 7) // 8 * 8
         dzt = self._buf("rows_dzt", (M, pitch))

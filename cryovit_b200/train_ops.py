@@ -92,6 +92,39 @@ def to_cfirst_padded_x3(x, outs, pd: int, ph: int, pw: int) -> None:
               _chk(outs[2], BF16, "out"), D, H, W, C, pd, ph, pw, Wp, pitch, _stream())
 
 
+def wgrad_mn(a, b, out, dil: int = 1, shift_a: bool = False) -> None:
+    """out[t, m, n] += sum_v a[v + off_a(t), m] * b[v + off_b(t), n] from channels-last bf16 volumes [D,H,W,C] (27 taps) or
+    [rows, C] matrices (one tap); see cvit_wgrad_mn_ndhwc."""
+    ntaps = out.shape[0]
+    if a.dim() == 2:
+        D, H, W = 1, 1, a.shape[0]
+    else:
+        D, H, W = a.shape[:3]
+    _lib.call("cvit_wgrad_mn_ndhwc", _chk(a, BF16, "a"), _chk(b, BF16, "b"), _chk(out, F32, "out"), D, H, W, a.shape[-1], b.shape[-1],
+              dil, ntaps, int(shift_a), _stream())
+
+
+def rows_weight_gradient(x_rows, dz_rows):
+    """dW[M, N] = dz_rows^T @ x_rows for row-major bf16 [R, N] / [R, M] (1x1x1 and transposed convolutions) without any
+    transposed copy, or None when the shapes do not fit the MN-major kernel (then the caller uses the split-K path).
+    Operands narrower than 64 channels are widened by viewing f consecutive rows as one row of f x C channels (both
+    operands alike): the product then holds f x f blocks of which the f diagonal ones sum to dW."""
+    R, N = x_rows.shape
+    M = dz_rows.shape[1]
+    f = 1
+    while min(M, N) * f < 64:
+        f *= 2
+    if R % f or (M * f) % 8 or (N * f) % 8 or not x_rows.is_contiguous() or not dz_rows.is_contiguous():
+        return None
+    a, b = dz_rows.view(R // f, f * M), x_rows.view(R // f, f * N)
+    out = torch.zeros(1, f * M, f * N, device=x_rows.device, dtype=F32)
+    wgrad_mn(a, b, out)
+    if f == 1:
+        return out[0]
+    blocks = out[0].view(f, M, f, N)
+    return sum(blocks[i, :, i, :] for i in range(f))
+
+
 _KOFFS: dict = {}
 
 
@@ -106,6 +139,19 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
         _lib.call("cvit_wgrad_narrow_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
                   dil, _stream())
         return dwn
+    # Wide layers: both operands straight from the channels-last volumes (MN-major tensor-core operands, the tap is the TMA
+    # box origin of the shifted one; csrc/wgrad_mn.cu). The GEMM's M is tiled in 128 channels, its N in 64 .. 256: the
+    # operand whose channel count fills 128-row tiles best becomes A (1024 -> 192: x; 192 as M would waste a quarter).
+    if Cin >= 64 and Cout >= 64 and Cin % 8 == 0 and Cout % 8 == 0:
+        waste = lambda c: (c + 127) // 128 * 128 / c
+        if waste(Cin) <= waste(Cout):
+            out = torch.zeros(27, Cin, Cout, device=x.device, dtype=F32)
+            wgrad_mn(x, dz, out, dil, shift_a=True)   # out[t, ci, co] = sum_v x[v + off_t, ci] dz[v, co]
+            return out.transpose(1, 2)
+        out = torch.zeros(27, Cout, Cin, device=x.device, dtype=F32)
+        wgrad_mn(dz, x, out, dil, shift_a=False)
+        return out
+    # Remaining shapes: channels-first zero-padded operand copies + the K-major split-K GEMM (csrc/wgrad.cu).
     # No depth padding: a depth tap that leaves the volume shifts the K index outside [0, K), where the GEMM's TMA loads
     # read zeros anyway; only the in-plane wrap-around needs the one-voxel zero border (of dz). With the head's
     # dilations (up to 32 planes of 128) padded planes would be a third of K.
@@ -127,20 +173,6 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
     if key not in _KOFFS:
         _KOFFS[key] = torch.tensor([((kd - 1) * dil * Hp + (kh - 1)) * Wp for kd in range(3) for kh in range(3)], dtype=torch.int32, device=dev)
     koffs = _KOFFS[key]
-    # The GEMM's M is tiled in 128 rows, its N in 32 .. 256 columns: with Cout = 192 as M a quarter of every second MMA
-    # is padding. dW^T[t, ci, co] = sum_k xt[ci, k] dzt[co, k - koff_t] is the same sum with the roles (and the sign of
-    # the shift) swapped: Cin = 1024 tiles M exactly and 192 is one exact N tile.
-    swap = Cin % 128 == 0 and Cout % 128 != 0 and Cout <= 256
-    if swap:
-        nkey = ("neg",) + key
-        if nkey not in _KOFFS:
-            _KOFFS[nkey] = (-koffs).contiguous()
-        dwt = torch.zeros(3, 9, Cin, Cout, device=dev, dtype=F32)
-        xt = buf("xt0", Cin * pitch)[:Cin * pitch].view(Cin, pitch)
-        for kw in range(3):
-            to_cfirst_padded(x, xt, pd, 1, 1, kw - 1)
-            wgrad_splitk(xt, dzt, dwt[kw], _KOFFS[nkey], pitch)
-        return dwt.permute(1, 0, 3, 2).reshape(27, Cout, Cin)
     dw = torch.zeros(3, 9, Cout, Cin, device=dev, dtype=F32)
     if Cin in (8, 16, 32):  # all three shifted copies from one pass over x
         xts = [buf(f"xt{kw}", Cin * pitch)[:Cin * pitch].view(Cin, pitch) for kw in range(3)]

@@ -341,6 +341,16 @@ int cvit_ndhwc_to_cfirst_padded_x3(const void* src, void* dst_m1, void* dst_0, v
 int cvit_wgrad_splitk(const void* At, const void* Bt, float* out, const int* koffs, int64_t M, int64_t N, int64_t K,
                       int64_t pitch_a, int64_t pitch_b, int64_t ntaps, void* stream);
 
+/* out[t][m][n] += sum over voxels v of  A[v + off_a(t)][m] * B[v + off_b(t)][n]   (fp32 out [ntaps][Ca][Cb], caller zeroes)
+ * straight from two channels-last bf16 volumes a [D,H,W,Ca], b [D,H,W,Cb] (Ca, Cb >= 64, multiples of 8): the weight
+ * gradient of a wide 3x3x3 depth-dilated "same" convolution (ntaps = 27, tap t = (kd*3+kh)*3+kw shifts the operand chosen
+ * by shift_a by ((kd-1) dil, kh-1, kw-1), zero outside the volume; models/cryovit.py:58-66) or of a 1x1x1 / transposed
+ * convolution over [rows][channels] matrices (ntaps = 1, W = rows, H = D = 1).  Both operands are read as MN-major
+ * tensor-core operands through TMA boxes of the tensors as they lie: no channels-first, padded or column-shifted copies
+ * (cvit_wgrad_splitk needs all three).  Split over the GPU along the voxels; partial tiles are added with red.global.add. */
+int cvit_wgrad_mn_ndhwc(const void* a, const void* b, float* out, int64_t D, int64_t H, int64_t W, int64_t Ca, int64_t Cb,
+                        int64_t dil, int64_t ntaps, int shift_a, void* stream);
+
 /* The same weight gradient for the narrow convolutions (SynthesisBlocks 3-4, output_layer; (Cin, Cout) in {(8,8), (16,16),
  * (32,16), (32,32)}), straight from the channels-last volumes with warp-level MMAs (csrc/wgrad_narrow.cu; no operand
  * copies): dw (fp32 [27][Cout][Cin], tap = (kd*3+kh)*3+kw) += sum_v dz[v, co] * x[v + off(tap), ci]; x bf16 [D,H,W,Cin],

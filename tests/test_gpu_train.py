@@ -57,6 +57,19 @@ def test_conv_weight_gradient_splitk(cuda_lib, D, H, W, Cin, Cout, dil):
     assert _relerr(dw, ref) < 5e-3, _relerr(dw, ref)
 
 
+@pytest.mark.parametrize("R,N,M", [(4104, 192, 512), (2048, 64, 128), (8192, 32, 128), (4096, 16, 32), (1000, 1024, 64)])
+def test_rows_weight_gradient_mn_major(cuda_lib, R, N, M):
+    """dW = dZ^T X straight from the row-major operands (MN-major tensor-core operands, csrc/wgrad_mn.cu), including the
+    narrow cases widened by viewing f rows as one (diagonal blocks summed)."""
+    from cryovit_b200 import train_ops as T
+    x = _rand(R, N, seed=1).bfloat16()
+    dz = _rand(R, M, seed=2).bfloat16()
+    dw = T.rows_weight_gradient(x, dz)
+    assert dw is not None and tuple(dw.shape) == (M, N)
+    ref = dz.float().t() @ x.float()
+    assert _relerr(dw, ref) < 2e-3, _relerr(dw, ref)
+
+
 def test_linear_weight_gradient_splitk(cuda_lib):
     """One-tap case (1x1x1 projection, transposed conv): dW[M, N] = dZ^T X over many rows."""
     from cryovit_b200 import train_ops as T
