@@ -56,6 +56,13 @@ SIGNATURES: dict[str, list] = {
     "cvit_conv3d_halo_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P],
     "cvit_convT_1x2x2_ndhwc_act": [P, P, P, P, I64, I64, I64, I64, I64, I32, P],
     "cvit_linear_bias_bf16_nvalid": [P, I64, P, P, P, I64, I64, I64, I64, I64, P],
+    "cvit_linear_bias_bf16_nvalid_aux": [P, I64, P, P, P, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_linear_bias_cfirst_f16_aux": [P, I64, P, P, P, I64, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_dilated_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_halo_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_convT_1x2x2_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_wpackn_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_wpack8_aux": [P, P, P, P, I64, I64, I64, I32, P, P],
     "cvit_gelu_fwd_bf16": [P, P, I64, P],
     "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
     "cvit_gelu_bwd_colsum_bf16": [P, P, P, P, I64, I64, P],
@@ -67,6 +74,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_ndhwc_to_cfirst_padded_x3": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_wgrad_splitk": [P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "cvit_wgrad_narrow_ndhwc": [P, P, P, I64, I64, I64, I64, I64, I64, P],
+    "cvit_wgrad_tc8_ndhwc": [P, P, P, I64, I64, I64, I64, P],
     "cvit_adamw_f32": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, F32, P],
     "cvit_conv3d_wpack8_gelu": [P, P, P, P, I64, I64, I64, I32, P],
     "cvit_conv3d_wpack8_final": [P, P, P, P, P, I64, I64, I64, P],

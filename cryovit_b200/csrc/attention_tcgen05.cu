@@ -525,6 +525,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaArgs
           pending = true;
           if (j + 1 == n_tiles || (kind == SPLIT && j + 2 >= n_tiles)) publish();  // last one: the epilogue is waiting
           FA_PROF(5);  // wait PV(j-1), store P
+        } else if (warp_active && valid <= 16 && first) {
+          // ---- short ragged tile walked first (1029 = 8 * 128 + 5): its 16 columns stay in registers, S is released at
+          // once, and the wait for the previous item's last PV (P is about to be overwritten) comes after the
+          // exponentials instead of in front of the load; the publish is deferred like that of a full tile.
+          uint32_t v[16];
+          tmem_ld_32x16(tS, v);
+          if (pending) publish();
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bg + B_SFREE);
+          float mt = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+          m = mt;
+          const float nmc = -m * c;
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float p0 = 2 * i < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nmc)) : 0.f;
+            const float p1 = 2 * i + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nmc)) : 0.f;
+            l += p0 + p1;
+            pk[i] = pack_16x2<F16>(p0, p1);
+          }
+          if (!pv_seen) {
+            mbar_wait(bg + B_PV, (tile_it - 1) & 1);
+            tcgen05_fence_after();
+          }
+          tmem_st_32x8(tP, pk);
+          pending = true;
+          if (j + 1 == n_tiles || (kind == SPLIT && j + 2 >= n_tiles)) publish();
+          FA_PROF(6);  // ragged tile
         } else {
           if (pending) publish();
           if (!pv_seen) {

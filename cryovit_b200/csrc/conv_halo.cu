@@ -59,7 +59,8 @@ struct HaloArgs {
                                // see gn_fold.cu / GemmArgs::bias_table); replaces `bias` when non-null
   __nv_bfloat16* out;          // [D, H, W, n_valid]
   int D, H, W, dil, n_valid;
-  int act;  // 1 = GELU (inference), 0 = store the pre-activation (training forward, input gradients)
+  int act;  // ptx.cuh ACT_*: 1 = GELU (inference), 0 = none, 2 = out = z and aux = gelu(z), 3 = out = y * gelu'(aux)
+  __nv_bfloat16* aux;  // [D, H, W, n_valid], act 2 / 3 only
 };
 
 // K-major, SWIZZLE_NONE shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 @[0,14), LBO>>4 @[16,30)
@@ -246,7 +247,34 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args)
         }
         // math for all COUT channels without branches (activation switch hoisted), then predicated 16-byte stores
         uint32_t pk[COUT / 2];
-        if (args.act) {
+        if (args.act == ACT_GELU_GRAD) {  // input gradient times gelu'(z) of the layer below (training)
+          const __nv_bfloat16* zp = args.aux + (o - args.out);
+          uint32_t z[COUT / 2];
+#pragma unroll
+          for (int c = 0; c < COUT; c += 8) {
+            uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            if (c < args.n_valid) z4 = __ldg(reinterpret_cast<const uint4*>(zp + c));
+            z[c / 2] = z4.x; z[c / 2 + 1] = z4.y; z[c / 2 + 2] = z4.z; z[c / 2 + 3] = z4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < COUT / 2; ++i)
+            pk[i] = act_gelu_grad_pair(__uint_as_float(v[2 * i]) + bias_r[2 * i], __uint_as_float(v[2 * i + 1]) + bias_r[2 * i + 1], z[i]);
+        } else if (args.act == ACT_DUAL) {  // pre-activation -> out here, activation -> aux below
+          uint32_t pz[COUT / 2];
+#pragma unroll
+          for (int i = 0; i < COUT / 2; ++i) {
+            float a = __uint_as_float(v[2 * i]) + bias_r[2 * i];
+            float b = __uint_as_float(v[2 * i + 1]) + bias_r[2 * i + 1];
+            pz[i] = pack_bf16x2(a, b);
+            gelu_erf2(a, b);
+            pk[i] = pack_bf16x2(a, b);
+          }
+#pragma unroll
+          for (int c = 0; c < COUT; c += 8)
+            if (c < args.n_valid)
+              *reinterpret_cast<uint4*>(o + c) = make_uint4(pz[c / 2], pz[c / 2 + 1], pz[c / 2 + 2], pz[c / 2 + 3]);
+          o = args.aux + (o - args.out);
+        } else if (args.act) {
 #pragma unroll
           for (int i = 0; i < COUT / 2; ++i) {
             float a = __uint_as_float(v[2 * i]) + bias_r[2 * i];
@@ -330,12 +358,23 @@ extern "C" int cvit_conv3d_halo_ndhwc(const void* x, const void* w_img, const fl
 
 static int conv3d_halo_impl(const void* x, const void* w_img, const float* bias, const float* bias_table, void* out, int64_t D,
                            int64_t H, int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
-                           void* stream);
+                           void* aux, void* stream);
 
 extern "C" int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
                                           int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
                                           void* stream) {
-  return conv3d_halo_impl(x, w_img, bias, nullptr, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, act, stream);
+  return conv3d_halo_impl(x, w_img, bias, nullptr, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, act ? 1 : 0, nullptr, stream);
+}
+
+// act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it, 3 out = result * gelu'(aux) (ptx.cuh ACT_*).
+extern "C" int cvit_conv3d_halo_ndhwc_aux(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                                          int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                          void* aux, void* stream) {
+  if (act < 0 || act > 3 || (act >= 2 && (!aux || (reinterpret_cast<uintptr_t>(aux) & 15u)))) {
+    set_error("conv3d_halo: act=%d needs a 16-byte aligned aux (0 none, 1 GELU, 2 out=z aux=gelu(z), 3 out=y*gelu'(aux))", act);
+    return CVIT_ERR_INVALID;
+  }
+  return conv3d_halo_impl(x, w_img, bias, nullptr, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, act, aux, stream);
 }
 
 // The convolution after a folded GroupNorm: per-voxel bias rows from the 64-row table (see gn_fold.cu), + GELU.
@@ -345,12 +384,12 @@ extern "C" int cvit_conv3d_halo_ndhwc_tab(const void* x, const void* w_img, cons
     set_error("conv3d_halo_tab: a 16-byte aligned bias table is required");
     return CVIT_ERR_INVALID;
   }
-  return conv3d_halo_impl(x, w_img, bias_table + 63 * Cout_pad, bias_table, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, 1, stream);
+  return conv3d_halo_impl(x, w_img, bias_table + 63 * Cout_pad, bias_table, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, 1, nullptr, stream);
 }
 
 static int conv3d_halo_impl(const void* x, const void* w_img, const float* bias, const float* bias_table, void* out, int64_t D,
                            int64_t H, int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
-                           void* stream) {
+                           void* aux, void* stream) {
   if (!x || !w_img || !bias || !out || D <= 0 || H <= 0 || W <= 0 || dil <= 0 || Cout_valid <= 0 || Cout_valid > Cout_pad ||
       (Cout_valid % 8) != 0) {
     set_error("conv3d_halo: bad arguments (D=%lld H=%lld W=%lld Cin=%lld Cout=%lld/%lld dil=%lld)", (long long)D, (long long)H,
@@ -371,6 +410,7 @@ static int conv3d_halo_impl(const void* x, const void* w_img, const float* bias,
   a.dil = (int)dil;
   a.n_valid = (int)Cout_valid;
   a.act = act;
+  a.aux = static_cast<__nv_bfloat16*>(aux);
   a.bias_table = bias_table;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32 && Cout_pad == 32) return launch_halo<32, 32>(x, a, st);

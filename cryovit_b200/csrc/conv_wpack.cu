@@ -84,6 +84,7 @@ struct WpArgs {
   const __nv_bfloat16* w_img;  // WpCfg::W_BYTES, host-arranged (cryovit_b200.head.wpack_weight_image)
   const float* bias;           // [N]: bias[j_out * COUT + co] = b[co]
   __nv_bfloat16* out;          // GELU mode: [D, H, W, 8]
+  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out); ACT_GELU_GRAD: the pre-activation whose gelu' scales the result
   float* logits;               // final mode: [D, H, W] clipped logits (may be null)
   float* probs;                // final mode: [D, H, W] sigmoid of the clipped logits (may be null)
   int D, H, W, act;
@@ -341,7 +342,37 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3d_wpack_kernel(const WpArg
           __nv_bfloat16* o = args.out + (vox + half * (P / 2)) * 8;
           // the activation switch is hoisted: a branch inside the unrolled loops keeps the voxels' GELU chains from
           // interleaving (see the transposed-convolution epilogue in gemm_tcgen05.cuh)
-          if (args.act) {
+          if (args.act == ACT_GELU_GRAD) {  // input gradient times gelu'(z) of the layer below (training)
+            const __nv_bfloat16* zp = args.aux + (vox + half * (P / 2)) * 8;
+            uint4 z4[P / 2];
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) z4[j] = __ldg(reinterpret_cast<const uint4*>(zp + j * 8));
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) {
+              const uint32_t zz[4] = {z4[j].x, z4[j].y, z4[j].z, z4[j].w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                pk[k] = act_gelu_grad_pair(__uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k], __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1], zz[k]);
+              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else if (args.act == ACT_DUAL) {  // pre-activation -> out, activation -> aux (training forward)
+            __nv_bfloat16* o2 = args.aux + (vox + half * (P / 2)) * 8;
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) {
+              uint32_t pz[4], pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float a = __uint_as_float(v[j * 8 + 2 * k]) + bb[2 * k];
+                float b = __uint_as_float(v[j * 8 + 2 * k + 1]) + bb[2 * k + 1];
+                pz[k] = pack_bf16x2(a, b);
+                gelu_erf2(a, b);
+                pk[k] = pack_bf16x2(a, b);
+              }
+              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
+              *reinterpret_cast<uint4*>(o2 + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else if (args.act) {
 #pragma unroll
             for (int j = 0; j < P / 2; ++j) {
               uint32_t pk[4];
@@ -426,10 +457,23 @@ static int wpack_check(const void* x, const void* w_img, const float* bias, int6
   return CVIT_OK;
 }
 
+extern "C" int cvit_conv3d_wpack8_aux(const void* x, const void* w_img, const float* bias_n, void* out, int64_t D, int64_t H,
+                                      int64_t W, int act, void* aux, void* stream);
+
 extern "C" int cvit_conv3d_wpack8_gelu(const void* x, const void* w_img, const float* bias_n, void* out, int64_t D, int64_t H,
                                        int64_t W, int act, void* stream) {
+  return cvit_conv3d_wpack8_aux(x, w_img, bias_n, out, D, H, W, act ? 1 : 0, nullptr, stream);
+}
+
+// act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it, 3 out = result * gelu'(aux) (ptx.cuh ACT_*).
+extern "C" int cvit_conv3d_wpack8_aux(const void* x, const void* w_img, const float* bias_n, void* out, int64_t D, int64_t H,
+                                      int64_t W, int act, void* aux, void* stream) {
   int rc = wpack_check(x, w_img, bias_n, D, H, W, 8);
   if (rc) return rc;
+  if (act < 0 || act > 3 || (act >= 2 && (!aux || (reinterpret_cast<uintptr_t>(aux) & 15u)))) {
+    set_error("conv3d_wpack8: act=%d needs a 16-byte aligned aux (0 none, 1 GELU, 2 out=z aux=gelu(z), 3 out=y*gelu'(aux))", act);
+    return CVIT_ERR_INVALID;
+  }
   if (!out || (reinterpret_cast<uintptr_t>(out) & 15u)) {
     set_error("conv3d_wpack8_gelu: out must be a 16-byte aligned bf16 [D,H,W,8] buffer");
     return CVIT_ERR_INVALID;
@@ -445,6 +489,7 @@ extern "C" int cvit_conv3d_wpack8_gelu(const void* x, const void* w_img, const f
   a.H = (int)H;
   a.W = (int)W;
   a.act = act;
+  a.aux = static_cast<__nv_bfloat16*>(aux);
   return launch_wpack<8, 8, false>(a, (cudaStream_t)stream);
 }
 
@@ -467,5 +512,6 @@ extern "C" int cvit_conv3d_wpack8_final(const void* x, const void* w_img, const 
   a.H = (int)H;
   a.W = (int)W;
   a.act = 0;
+  a.aux = nullptr;
   return launch_wpack<16, 1, true>(a, (cudaStream_t)stream);
 }

@@ -43,6 +43,7 @@ struct WnArgs {
   const __nv_bfloat16* w_img;  // WnCfg::W_BYTES, host-arranged (cryovit_b200.head.wpackn_weight_image)
   const float* table;          // fp32 [64][COUT]: bias row by in-bounds tap masks (a plain bias = 64 equal rows)
   __nv_bfloat16* out;          // [D, H, W, n_valid]
+  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out); ACT_GELU_GRAD: the pre-activation whose gelu' scales the result
   int D, H, W, dil, n_valid, act;
 };
 
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(192, 1) conv3d_wpackt_kernel(const __grid_cons
       if (h < args.H) {
         const int dm = (d >= args.dil ? 1 : 0) | (d + args.dil < args.D ? 2 : 0);
         const int hm = (h >= 1 ? 1 : 0) | (h + 1 < args.H ? 2 : 0);
-        __nv_bfloat16* o = args.out + (((int64_t)d * args.H + h) * args.W + wv0) * args.n_valid;
+        const int64_t off0 = (((int64_t)d * args.H + h) * args.W + wv0) * args.n_valid;
+        __nv_bfloat16* o = args.out + off0;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
           const int w = wv0 + j;
@@ -219,22 +221,50 @@ __global__ void __launch_bounds__(192, 1) conv3d_wpackt_kernel(const __grid_cons
           const int wm = (w >= 1 ? 1 : 0) | (w + 1 < args.W ? 2 : 0);
           const float4* row = tab4 + ((dm * 4 + hm) * 4 + wm) * (COUT / 4);
           uint32_t pk[COUT / 2];
+          if (args.act == ACT_GELU_GRAD) {  // input gradient times gelu'(z) of the layer below
+            uint32_t z[COUT / 2];
 #pragma unroll
-          for (int c = 0; c < COUT / 4; ++c) {
-            const float4 tb = row[c];
-            float a0 = __uint_as_float(v[j * COUT + 4 * c]) + tb.x, a1 = __uint_as_float(v[j * COUT + 4 * c + 1]) + tb.y;
-            float a2 = __uint_as_float(v[j * COUT + 4 * c + 2]) + tb.z, a3 = __uint_as_float(v[j * COUT + 4 * c + 3]) + tb.w;
-            if (args.act) {
-              gelu_erf2(a0, a1);
-              gelu_erf2(a2, a3);
+            for (int c = 0; c < COUT; c += 8) {
+              uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+              if (c < args.n_valid) z4 = __ldg(reinterpret_cast<const uint4*>(args.aux + off0 + (int64_t)j * args.n_valid + c));
+              z[c / 2] = z4.x; z[c / 2 + 1] = z4.y; z[c / 2 + 2] = z4.z; z[c / 2 + 3] = z4.w;
             }
-            pk[2 * c] = pack_bf16x2(a0, a1);
-            pk[2 * c + 1] = pack_bf16x2(a2, a3);
+#pragma unroll
+            for (int c = 0; c < COUT / 4; ++c) {
+              const float4 tb = row[c];
+              pk[2 * c] = act_gelu_grad_pair(__uint_as_float(v[j * COUT + 4 * c]) + tb.x, __uint_as_float(v[j * COUT + 4 * c + 1]) + tb.y, z[2 * c]);
+              pk[2 * c + 1] = act_gelu_grad_pair(__uint_as_float(v[j * COUT + 4 * c + 2]) + tb.z, __uint_as_float(v[j * COUT + 4 * c + 3]) + tb.w, z[2 * c + 1]);
+            }
+          } else {
+            uint32_t pz[COUT / 2];
+#pragma unroll
+            for (int c = 0; c < COUT / 4; ++c) {
+              const float4 tb = row[c];
+              float a0 = __uint_as_float(v[j * COUT + 4 * c]) + tb.x, a1 = __uint_as_float(v[j * COUT + 4 * c + 1]) + tb.y;
+              float a2 = __uint_as_float(v[j * COUT + 4 * c + 2]) + tb.z, a3 = __uint_as_float(v[j * COUT + 4 * c + 3]) + tb.w;
+              if (args.act == ACT_DUAL) {
+                pz[2 * c] = pack_bf16x2(a0, a1);
+                pz[2 * c + 1] = pack_bf16x2(a2, a3);
+              }
+              if (args.act) {
+                gelu_erf2(a0, a1);
+                gelu_erf2(a2, a3);
+              }
+              pk[2 * c] = pack_bf16x2(a0, a1);
+              pk[2 * c + 1] = pack_bf16x2(a2, a3);
+            }
+            if (args.act == ACT_DUAL) {  // pre-activation -> out, activation -> aux (stored below through `o`)
+#pragma unroll
+              for (int c = 0; c < COUT; c += 8)
+                if (c < args.n_valid)
+                  *reinterpret_cast<uint4*>(o + (int64_t)j * args.n_valid + c) = make_uint4(pz[c / 2], pz[c / 2 + 1], pz[c / 2 + 2], pz[c / 2 + 3]);
+            }
           }
+          __nv_bfloat16* o2 = args.act == ACT_DUAL ? args.aux + off0 : o;
 #pragma unroll
           for (int c = 0; c < COUT; c += 8)
             if (c < args.n_valid)
-              *reinterpret_cast<uint4*>(o + (int64_t)j * args.n_valid + c) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
+              *reinterpret_cast<uint4*>(o2 + (int64_t)j * args.n_valid + c) = make_uint4(pk[c / 2], pk[c / 2 + 1], pk[c / 2 + 2], pk[c / 2 + 3]);
         }
       }
       acc ^= 1;
@@ -297,9 +327,24 @@ extern "C" int64_t cvit_conv3d_wpackn_weight_bytes(int64_t Cin, int64_t Cout_pad
   return -1;
 }
 
+extern "C" int cvit_conv3d_wpackn_ndhwc_aux(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                                            int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                            void* aux, void* stream);
+
 extern "C" int cvit_conv3d_wpackn_ndhwc(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
                                         int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
                                         void* stream) {
+  return cvit_conv3d_wpackn_ndhwc_aux(x, w_img, bias_table, out, D, H, W, Cin, Cout_pad, Cout_valid, dil, act ? 1 : 0, nullptr, stream);
+}
+
+// act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it, 3 out = result * gelu'(aux) (ptx.cuh ACT_*).
+extern "C" int cvit_conv3d_wpackn_ndhwc_aux(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                                            int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                            void* aux, void* stream) {
+  if (act < 0 || act > 3 || (act >= 2 && (!aux || (reinterpret_cast<uintptr_t>(aux) & 15u)))) {
+    set_error("conv3d_wpackn: act=%d needs a 16-byte aligned aux (0 none, 1 GELU, 2 out=z aux=gelu(z), 3 out=y*gelu'(aux))", act);
+    return CVIT_ERR_INVALID;
+  }
   const int64_t P = cvit_conv3d_wpackn_group(Cin, Cout_pad);
   if (!x || !w_img || !bias_table || !out || D <= 0 || H <= 0 || W <= 0 || dil <= 0 || Cout_valid <= 0 || Cout_valid > Cout_pad ||
       (Cout_valid % 8) != 0) {
@@ -328,6 +373,7 @@ extern "C" int cvit_conv3d_wpackn_ndhwc(const void* x, const void* w_img, const 
   a.dil = (int)dil;
   a.n_valid = (int)Cout_valid;
   a.act = act;
+  a.aux = static_cast<__nv_bfloat16*>(aux);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32 && Cout_pad == 16) return launch_wpackt<32, 16, 2>(a, st);
   if (Cin == 16 && Cout_pad == 16) return launch_wpackt<16, 16, 4>(a, st);

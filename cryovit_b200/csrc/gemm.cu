@@ -254,6 +254,16 @@ static GemmArgs base_args(int64_t M, int64_t N, int64_t K, void* out, int64_t ld
 
 extern "C" {
 
+int cvit_linear_bias_bf16_nvalid_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                     int64_t M, int64_t N, int64_t K, int64_t n_valid, int act, const void* aux, void* stream);
+int cvit_linear_bias_cfirst_f16_aux(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                    int64_t M, int64_t N, int64_t K, int act, void* aux, void* stream);
+int cvit_conv3d_dilated_ndhwc_aux(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* aux, void* stream);
+int cvit_convT_1x2x2_ndhwc_aux(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* aux, void* stream);
+
 int cvit_set_gemm_pair(int enable) {
   const int prev = cvit::g_gemm_pair;
   cvit::g_gemm_pair = enable ? 1 : 0;
@@ -287,19 +297,49 @@ int cvit_linear_bias_bf16(const void* A, int64_t lda, const void* W, const float
 // computed but not stored, ldo is the true row pitch (transposed-convolution input gradient with 16 channels).
 int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
                                  int64_t M, int64_t N, int64_t K, int64_t n_valid, void* stream) {
+  return cvit_linear_bias_bf16_nvalid_aux(A, lda, W, bias, out, ldo, M, N, K, n_valid, 0, nullptr, stream);
+}
+
+// act = 0: the plain entry point; act = 3 (ACT_GELU_GRAD): out = (A W^T + bias) * gelu'(aux), aux bf16 [M, n_valid] with
+// row pitch ldo -- the transposed convolution's input gradient handed on as the gradient of the pre-activation below it.
+int cvit_linear_bias_bf16_nvalid_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                     int64_t M, int64_t N, int64_t K, int64_t n_valid, int act, const void* aux, void* stream) {
   if (!bias) { set_error("linear_bias: bias is required"); return CVIT_ERR_INVALID; }
+  if ((act != ACT_NONE && act != ACT_GELU_GRAD) || (act == ACT_GELU_GRAD && (!aux || (reinterpret_cast<uintptr_t>(aux) & 7u)))) {
+    set_error("linear_bias_nvalid_aux: act must be 0 or 3 (with an 8-byte aligned aux)");
+    return CVIT_ERR_INVALID;
+  }
   GemmArgs a = base_args(M, N, K, out, ldo);
   a.bias = bias;
   a.n_valid = (int)n_valid;
+  a.act = act;
+  a.aux = const_cast<void*>(aux);
   return gemm_rows(A, lda, W, a, EPI_BIAS, (cudaStream_t)stream);
+}
+
+static int check_act_aux(const char* who, int act, const void* aux, bool grad_ok) {
+  const bool known = act == ACT_NONE || act == ACT_GELU || act == ACT_DUAL || (grad_ok && act == ACT_GELU_GRAD);
+  if (!known || ((act == ACT_DUAL || act == ACT_GELU_GRAD) && (!aux || (reinterpret_cast<uintptr_t>(aux) & 15u)))) {
+    set_error("%s: act=%d unsupported here, or aux missing / not 16-byte aligned (0 none, 1 GELU, 2 out=z aux=gelu(z)%s)", who, act,
+              grad_ok ? ", 3 out=y*gelu'(aux)" : "");
+    return CVIT_ERR_INVALID;
+  }
+  return CVIT_OK;
 }
 
 int cvit_linear_bias_cfirst_f16(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
                                 int64_t M, int64_t N, int64_t K, int gelu, void* stream) {
+  return cvit_linear_bias_cfirst_f16_aux(At, ldat, W, bias, out, ldo, M, N, K, gelu ? 1 : 0, nullptr, stream);
+}
+
+int cvit_linear_bias_cfirst_f16_aux(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                    int64_t M, int64_t N, int64_t K, int act, void* aux, void* stream) {
   if (!bias) { set_error("linear_bias_cfirst: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_act_aux("linear_bias_cfirst", act, aux, false)) return rc;
   GemmArgs a = base_args(M, N, K, out, ldo);
   a.bias = bias;
-  a.act = gelu ? 1 : 0;
+  a.act = act;
+  a.aux = aux;
   a.fmt = GEMM_FMT_OPERANDS_F16;
   return gemm_rows_mn(At, ldat, W, a, (cudaStream_t)stream);
 }
@@ -393,8 +433,16 @@ int cvit_conv3d_dilated_ndhwc(const void* x, const void* w_taps, const float* bi
 int cvit_conv3d_dilated_ndhwc_act(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
                                   int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
                                   int act, void* stream) {
+  return cvit_conv3d_dilated_ndhwc_aux(x, w_taps, bias, out, D, H, W, Cin, Cout, Cout_valid, dil, act ? 1 : 0, nullptr, stream);
+}
+
+int cvit_conv3d_dilated_ndhwc_aux(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* aux, void* stream) {
   if (!bias) { set_error("conv3d: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_act_aux("conv3d_dilated", act, aux, true)) return rc;
   GemmArgs a = base_args(D * H * W, Cout, Cin, out, Cout_valid);
+  a.aux = aux;
   a.bias = bias;
   a.D = (int)D;
   a.H = (int)H;
@@ -415,8 +463,15 @@ int cvit_convT_1x2x2_ndhwc(const void* x, const void* w_sub, const float* bias4,
 
 int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
                                int64_t W, int64_t Cin, int64_t Cout, int act, void* stream) {
+  return cvit_convT_1x2x2_ndhwc_aux(x, w_sub, bias4, out, D, H, W, Cin, Cout, act ? 1 : 0, nullptr, stream);
+}
+
+int cvit_convT_1x2x2_ndhwc_aux(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* aux, void* stream) {
   if (!bias4) { set_error("convT: bias is required"); return CVIT_ERR_INVALID; }
+  if (int rc = check_act_aux("convT", act, aux, false)) return rc;
   GemmArgs a = base_args(D * H * W, 4 * Cout, Cin, out, Cout);
+  a.aux = aux;
   a.bias = bias4;
   a.H = (int)H;
   a.W = (int)W;

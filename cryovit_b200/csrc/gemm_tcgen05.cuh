@@ -49,7 +49,9 @@ struct GemmArgs {
   int BW, BH;         // AMODE_CONV3 tile footprint, BW*BH == 128
   int c3;             // EPI_CONVT_GELU: output channels per sub-pixel (N == 4*c3); uses H, W too
   int n_valid;        // columns >= n_valid are computed (zero-padded weights) but never stored
-  int act;            // EPI_BIAS_GELU / EPI_CONVT_GELU: 1 = GELU (inference), 0 = store the pre-activation (training, dgrad)
+  int act;            // EPI_BIAS_GELU / EPI_CONVT_GELU: ACT_* of ptx.cuh (1 = GELU: inference; 0 / 2 / 3: training); EPI_BIAS reads
+                      // only ACT_GELU_GRAD
+  void* aux;          // ACT_DUAL: bf16 activation output; ACT_GELU_GRAD: bf16 saved pre-activation (indexed like out)
   int fmt;            // GEMM_FMT_* bits: 16-bit type of the operands / of the stored output (0 = bf16 everywhere)
   // GroupNorm fused into its neighbours (head inference, models/cryovit.py:56 SynthesisBlock.layers[0]):
   //  * PRODUCER side (EPI_BIAS_GELU on plain rows, EPI_CONVT_GELU): gn_partials != null -> every epilogue warp also
@@ -467,7 +469,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               xs[it].w = silu(xs[it].w) * (ys[it].w + b4b.w);
             }
           }
-          if (EPI == EPI_BIAS_GELU && args.act) {
+          if ((EPI == EPI_BIAS_GELU || EPI == EPI_BIAS) && args.act == ACT_GELU_GRAD) {
+            // input-gradient GEMM / convolution: times gelu'(z) of the layer below, z read where the result is stored
+            const __nv_bfloat16* zbase = static_cast<const __nv_bfloat16*>(args.aux) + ocol;
+            uint2 z2[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              z2[it] = make_uint2(0u, 0u);
+              if (grow_it[it] >= 0) z2[it] = __ldg(reinterpret_cast<const uint2*>(zbase + (size_t)grow_it[it] * args.ldo));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              xs[it].x *= gelu_grad(__uint_as_float(z2[it].x << 16));
+              xs[it].y *= gelu_grad(__uint_as_float(z2[it].x & 0xffff0000u));
+              xs[it].z *= gelu_grad(__uint_as_float(z2[it].y << 16));
+              xs[it].w *= gelu_grad(__uint_as_float(z2[it].y & 0xffff0000u));
+            }
+          }
+          if (EPI == EPI_BIAS_GELU && args.act == ACT_DUAL) {
+            // training forward: the pre-activation stays in `out` for the backward pass, the activation goes to `aux`
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (grow_it[it] >= 0)
+                *reinterpret_cast<uint2*>(obase + (size_t)grow_it[it] * args.ldo) =
+                    make_uint2(pack_bf16x2(xs[it].x, xs[it].y), pack_bf16x2(xs[it].z, xs[it].w));
+            obase = static_cast<__nv_bfloat16*>(args.aux) + ocol;
+          }
+          if (EPI == EPI_BIAS_GELU && (args.act == ACT_GELU || args.act == ACT_DUAL)) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               gelu_erf2(xs[it].x, xs[it].y);
@@ -553,6 +581,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           uint2 pk[8];
+          __nv_bfloat16* obaseT = static_cast<__nv_bfloat16*>(args.out);
+          if (args.act == ACT_DUAL) {  // training forward: pre-activation -> out, activation -> aux
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (grow_it[it] >= 0)
+                *reinterpret_cast<uint2*>(obaseT + off_it[it]) =
+                    make_uint2(pack_bf16x2(xs[it].x + b4.x, xs[it].y + b4.y), pack_bf16x2(xs[it].z + b4.z, xs[it].w + b4.w));
+            obaseT = static_cast<__nv_bfloat16*>(args.aux);
+          }
           if (args.act) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -571,7 +608,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            if (grow_it[it] >= 0) *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(args.out) + off_it[it]) = pk[it];
+            if (grow_it[it] >= 0) *reinterpret_cast<uint2*>(obaseT + off_it[it]) = pk[it];
         }
       }
       // all TMEM reads of this accumulator buffer are complete (every tcgen05.ld was waited on)

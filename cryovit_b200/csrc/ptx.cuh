@@ -390,6 +390,36 @@ __device__ __forceinline__ void gelu_erf2(float& a, float& b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(r));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
 }
+// d/dz [ 0.5 z (1 + erf(z / sqrt 2)) ] = Phi(z) + z phi(z). erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, see
+// gelu_erf in ptx.cuh); its exp(-z^2 / 2) is the one phi(z) needs, so the whole derivative costs one ex2 and one rcp.
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float u = fabsf(z) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(u * u * -1.4426950408889634f);  // exp(-z^2 / 2)
+  const float cdf = fmaf(0.5f, copysignf(fmaf(-p, e, 1.0f), z), 0.5f);
+  return fmaf(z * 0.3989422804014327f, e, cdf);
+}
+
+// Activation modes of the head kernels' epilogues (`act` in the C ABI). Training fuses the element-wise passes into the
+// convolutions: ACT_DUAL keeps the pre-activation for the backward pass and hands the activation to the next layer in
+// one epilogue; ACT_GELU_GRAD turns an input-gradient convolution into "gradient of the previous pre-activation".
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_DUAL = 2, ACT_GELU_GRAD = 3 };
+//   ACT_NONE       out = y
+//   ACT_GELU       out = gelu(y)
+//   ACT_DUAL       out = y, aux = gelu(y)           (aux: bf16, same shape / indexing as out)
+//   ACT_GELU_GRAD  out = y * gelu'(aux)             (aux: the saved pre-activation z of the layer below)
+// Pair form used by every epilogue: (a, b) are two neighbouring channels, z2 / a2 point at their packed bf16 pair.
+__device__ __forceinline__ uint32_t act_gelu_grad_pair(float a, float b, uint32_t z2) {
+  const float z0 = __uint_as_float(z2 << 16), z1 = __uint_as_float(z2 & 0xffff0000u);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b * gelu_grad(z1)), "f"(a * gelu_grad(z0)));
+  return r;
+}
 // x * sigmoid(x) with ex2.approx + rcp.approx (both ~2^-22 relative error): 4 instructions instead of an IEEE division
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

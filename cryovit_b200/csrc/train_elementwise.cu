@@ -15,21 +15,6 @@ static int ew_grid(int64_t n, int per_thread = 8) {
   return (int)(b < 1 ? 1 : b);
 }
 
-// d/dz [ 0.5 z (1 + erf(z / sqrt 2)) ] = Phi(z) + z phi(z). erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, see
-// gelu_erf in ptx.cuh); its exp(-z^2 / 2) is the one phi(z) needs, so the whole derivative costs one ex2 and one rcp.
-__device__ __forceinline__ float gelu_grad(float z) {
-  const float u = fabsf(z) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(u * u * -1.4426950408889634f);  // exp(-z^2 / 2)
-  const float cdf = fmaf(0.5f, copysignf(fmaf(-p, e, 1.0f), z), 0.5f);
-  return fmaf(z * 0.3989422804014327f, e, cdf);
-}
-
 // a = gelu(z), 8 bf16 per thread-iteration
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ a, int64_t nvec) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {

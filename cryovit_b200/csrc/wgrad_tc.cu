@@ -1,0 +1,215 @@
+// Weight gradient of the 8 -> 8 channel 3x3x3 convolutions of the CryoVIT head (output_layer.0 / output_layer.2 at full
+// resolution, models/cryovit.py:30-34; head training, BASELINE config 5) on tcgen05, straight from the channels-last
+// volumes:
+//
+//   dW[kd][kh][kw][co][ci] = sum over output voxels (z, y, x) of  dZ[z, y, x][co] * X[z + (kd-1) dil, y + kh - 1, x + kw - 1][ci]
+//
+// 116 GFLOP whose result is 1728 numbers: a reduction over 33.5 M voxels. The warp-level kernel (csrc/wgrad_narrow.cu) is
+// bound by the mma.sync rate of this chip (1.07 ms per launch, two launches per step). Here the VOXELS ARE THE K DIMENSION
+// OF ONE tcgen05 MMA and nothing is re-laid-out:
+//
+//   * 8 channels of a channels-last voxel are 16 bytes, so a row segment [voxels][8] in shared memory is, as it lies, an
+//     MN-major SWIZZLE_NONE operand: a core matrix is 8 consecutive voxels (K) x 8 channels (M or N) = 128 contiguous
+//     bytes, the next 8 voxels follow 128 bytes on (LBO).
+//   * A = X. The three column taps kw are the SAME row read one voxel further on, and one voxel is 16 bytes = the stride
+//     between core matrices along M (SBO = 16): accumulator row m = kw * 8 + ci reads X[.., x0 + k - 1 + kw][ci]. No
+//     shifted copies. (M = 128 reads 13 more "taps"; those accumulator rows are never looked at.)
+//   * B = dZ. For the X row (z0, y0) the nine (kd, kh) taps pair it with the dZ rows (z0 - (kd-1) dil, y0 - (kh-1)). A stage
+//     holds the dZ rows y0 - 1 .. y0 + R of the three planes as equal-sized arrays ordered [row][plane], so the nine arrays
+//     of one X row are consecutive: accumulator column n = ((yr * 3 + kd) * 8 + co), SBO = array size. R consecutive X
+//     rows share the stage's dZ rows: (R + 2) * 3 row loads per R rows instead of 9 R.
+//   * Every TMA box is whole 128-byte lines ([8 voxels][8 channels]); out-of-bounds zero fill is the convolution's
+//     padding (x = -1, x = W, rows and planes outside the volume) and the ragged ends of the tiling.
+//
+// One MMA (M 128, N 80, K 16 voxels) per 16 voxels of a row for all 27 taps: 2.1 M MMAs per launch over 148 SMs. The
+// accumulator (80 TMEM columns) lives for the whole kernel; one red.global.add pass per CTA at the end.
+// One CTA per SM, 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warp 4 the final read-out.
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace cvit {
+
+constexpr int WT_THREADS = 192;
+constexpr int WT_R = 8;        // X rows per stage
+constexpr int WT_KSEG = 128;   // voxels of a row per stage
+constexpr int WT_XARR = (WT_KSEG + 16) * 16;  // X row array: voxels x0 - 8 .. x0 + KSEG + 7 (whole 128-byte lines)
+constexpr int WT_ZARR = WT_KSEG * 16;         // dZ row array: voxels x0 .. x0 + KSEG - 1
+constexpr int WT_X_BYTES = WT_R * WT_XARR;
+constexpr int WT_Z_BYTES = ((WT_R + 2) * 3 + 1) * WT_ZARR;  // + one array: N = 80 reads a tenth (ignored) column block
+constexpr int WT_STAGE = (WT_X_BYTES + WT_Z_BYTES + 1023) / 1024 * 1024;
+constexpr int WT_STAGES = 2;
+constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 256 + 1024;
+constexpr int WT_N = 80, WT_TMEM_COLS = 128;
+constexpr uint32_t WT_TX_BYTES = WT_R * WT_XARR + (WT_R + 2) * 3 * WT_ZARR;
+
+struct WtArgs {
+  float* dw;  // [27][8][8] fp32, accumulated into (tap = (kd*3+kh)*3+kw, then co, then ci)
+  int D, H, W, dil;
+};
+
+// MN-major SWIZZLE_NONE operand: core matrix = 8 K-rows of 16 bytes; LBO = next 8 K, SBO = next 8 M/N elements
+// (cute::UMMA canonical layout ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units)
+__device__ __forceinline__ uint64_t wt_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+#ifdef WT_SWAP_LBO_SBO
+  const uint32_t t = lbo; lbo = sbo; sbo = t;
+#endif
+  return static_cast<uint64_t>((addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad_tc8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, const WtArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = smem_base + WT_STAGES * WT_STAGE;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * WT_STAGES, bar_done = sBar + 16 * WT_STAGES, tmem_slot = bar_done + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int segs = (args.W + WT_KSEG - 1) / WT_KSEG, hblocks = (args.H + WT_R - 1) / WT_R;
+  const int num_blocks = args.D * hblocks * segs;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmZ);
+    for (int s = 0; s < WT_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<WT_TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+        const int seg = blk % segs, hb = (blk / segs) % hblocks, z0 = blk / (segs * hblocks);
+        const int x0 = seg * WT_KSEG, yb = hb * WT_R;
+        const uint32_t s = it % WT_STAGES;
+        mbar_wait(bar_empty + 8 * s, ((it / WT_STAGES) & 1) ^ 1u);
+        const uint32_t sX = smem_base + s * WT_STAGE, sZ = sX + WT_X_BYTES, bar = bar_full + 8 * s;
+        mbar_arrive_expect_tx(bar, WT_TX_BYTES);
+        for (int r = 0; r < WT_R; ++r)  // voxels x0 - 8 .. x0 + KSEG + 7 of row yb + r
+          tma_load_4d(sX + r * WT_XARR, &tmX, bar, 0, x0 / 8 - 1, yb + r, z0);
+        for (int rr = 0; rr < WT_R + 2; ++rr)
+          for (int kd = 0; kd < 3; ++kd)
+            tma_load_4d(sZ + (rr * 3 + kd) * WT_ZARR, &tmZ, bar, 0, x0 / 8, yb - 1 + rr, z0 - (kd - 1) * args.dil);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, WT_N) | (1u << 15) | (1u << 16);  // A and B MN-major
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      const uint32_t s = it % WT_STAGES;
+      mbar_wait(bar_full + 8 * s, (it / WT_STAGES) & 1);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sX = smem_base + s * WT_STAGE, sZ = sX + WT_X_BYTES;
+#pragma unroll 1
+        for (int r = 0; r < WT_R; ++r) {
+          // A: row r from voxel x0 - 1 (array voxel 7); B: the nine dZ arrays (rows r .. r + 2 of the stage, three planes)
+          const uint64_t ad = wt_desc(sX + r * WT_XARR + 7 * 16, 128, 16);
+          const uint64_t bd = wt_desc(sZ + r * 3 * WT_ZARR, 128, WT_ZARR);
+#pragma unroll
+          for (int ks = 0; ks < WT_KSEG / 16; ++ks)  // 16 voxels = 256 bytes further on in both operands
+            umma_bf16(tmem_base, ad + 16 * ks, bd + 16 * ks, idesc, (it | r | ks) != 0);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(bar_done);
+    __syncwarp();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ read-out: lanes 0..23 = (kw, ci)
+    mbar_wait(bar_done, 0);
+    tcgen05_fence_after();
+    if (blockIdx.x < num_blocks) {
+      const int kw = lane >> 3, ci = lane & 7;
+#pragma unroll 1
+      for (int c = 0; c < 5; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + c * 16, v);
+        tmem_ld_wait();
+        if (lane < 24) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = c * 16 + i;
+            if (n < 72) {
+              const int co = n & 7, blkn = n >> 3, yr = blkn / 3, kd = blkn - 3 * yr, kh = 2 - yr;
+              atomicAdd(args.dw + ((((kd * 3 + kh) * 3 + kw) * 8 + co) * 8 + ci), __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<WT_TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace cvit
+
+using namespace cvit;
+
+// dw (fp32 [27][8][8], tap = (kd*3+kh)*3+kw, then co, then ci) += weight gradient of an 8 -> 8 channel 3x3x3 depth-dilated
+// "same" convolution: x the forward input, dz the output gradient, both bf16 [D,H,W,8], W a multiple of 8.
+extern "C" int cvit_wgrad_tc8_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil,
+                                    void* stream) {
+  if (!x || !dz || !dw || D <= 0 || H <= 0 || W <= 0 || dil <= 0) {
+    set_error("wgrad_tc8: bad arguments (D=%lld H=%lld W=%lld dil=%lld)", (long long)D, (long long)H, (long long)W, (long long)dil);
+    return CVIT_ERR_INVALID;
+  }
+  if (W % 8) {
+    set_error("wgrad_tc8: W=%lld must be a multiple of 8 (use cvit_wgrad_narrow_ndhwc otherwise)", (long long)W);
+    return CVIT_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz)) & 15u) {
+    set_error("wgrad_tc8: x and dz must be 16-byte aligned");
+    return CVIT_ERR_INVALID;
+  }
+  // both volumes as (128-byte line = 8 voxels x 8 channels, lines per row, rows, planes)
+  CUtensorMap tmX, tmZ;
+  uint64_t dims[4] = {64, (uint64_t)(W / 8), (uint64_t)H, (uint64_t)D};
+  uint64_t strides[4] = {0, 128, (uint64_t)W * 16, (uint64_t)H * W * 16};
+  uint32_t boxX[4] = {64, WT_KSEG / 8 + 2, 1, 1}, boxZ[4] = {64, WT_KSEG / 8, 1, 1};
+  int rc = encode_tmap(&tmX, TmapDtype::BF16, 4, x, dims, strides, boxX, 0);
+  if (rc) return rc;
+  rc = encode_tmap(&tmZ, TmapDtype::BF16, 4, dz, dims, strides, boxZ, 0);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc8: cudaFuncSetAttribute(smem=%d): %s", WT_SMEM, cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t blocks = D * ((H + WT_R - 1) / WT_R) * ((W + WT_KSEG - 1) / WT_KSEG);
+  int grid = num_sms();
+  if (grid > blocks) grid = (int)blocks;
+  WtArgs a;
+  a.dw = dw;
+  a.D = (int)D;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.dil = (int)dil;
+  wgrad_tc8_kernel<<<grid, WT_THREADS, WT_SMEM, (cudaStream_t)stream>>>(tmX, tmZ, a);
+  return check_launch("wgrad_tc8_kernel");
+}

@@ -101,12 +101,16 @@ def linear_bias(a, w, bias, out, gelu: bool = False) -> None:
               _chk(out, out.dtype, "out"), out.stride(0), M, N, K, int(gelu), fmt, _stream())
 
 
-def linear_bias_cfirst(at, w, bias, out, gelu: bool = False) -> None:
-    """out bf16 [M, N] = at[K, M]^T @ w[N, K]^T + bias (+ GELU); at and w fp16, at read as an MN-major operand."""
+def linear_bias_cfirst(at, w, bias, out, gelu=False, aux=None) -> None:
+    """out bf16 [M, N] = at[K, M]^T @ w[N, K]^T + bias (+ GELU); at and w fp16, at read as an MN-major operand.
+    gelu = 2 with ``aux``: out keeps the pre-activation, aux (contiguous, out's shape) receives its GELU."""
     K, M = at.shape
     N = w.shape[0]
-    _lib.call("cvit_linear_bias_cfirst_f16", _chk(at, F16, "at"), at.stride(0), _chk(w, F16, "w"), _chk(bias, F32, "bias"),
-              _chk(out, BF16, "out"), out.stride(0), M, N, K, int(gelu), _stream())
+    act, auxp = _aux(gelu, aux, out)
+    if act == 2 and (aux.stride(0) != out.stride(0)):
+        raise _lib.CryovitB200Error("linear_bias_cfirst: aux must have the output's row pitch")
+    _lib.call("cvit_linear_bias_cfirst_f16_aux", _chk(at, F16, "at"), at.stride(0), _chk(w, F16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, N, K, act, auxp, _stream())
 
 
 def gn_partials_numel(rows: int, n_cols: int, cpg: int) -> int:
@@ -182,13 +186,24 @@ def wpackn_group(cin: int, cout_pad: int) -> int:
     return int(_lib.load().cvit_conv3d_wpackn_group(cin, cout_pad))
 
 
-def conv3d_wpackn(x, w_img, table, out, dil: int, cout_pad: int, act: bool = True) -> None:
+def _aux(act, aux, out):
+    """(act, aux pointer) of the *_aux entry points: act 0 none, 1 GELU, 2 out = z and aux = gelu(z), 3 out = y * gelu'(aux)."""
+    act = int(act)
+    if act >= 2:
+        if aux is None or tuple(aux.shape) != tuple(out.shape):
+            raise _lib.CryovitB200Error(f"act={act} needs an aux tensor of the output's shape {tuple(out.shape)}")
+        return act, _chk(aux, BF16, "aux")
+    return act, None
+
+
+def conv3d_wpackn(x, w_img, table, out, dil: int, cout_pad: int, act=True, aux=None) -> None:
     """Narrow-layer (Cin 16 / 32) dilated conv + bias-table row + GELU, P output voxels of a row per MMA row (csrc/conv_wpackn.cu)."""
     D, H, W, Cin = x.shape
     if w_img.numel() * 2 != _lib.load().cvit_conv3d_wpackn_weight_bytes(Cin, cout_pad):
         raise _lib.CryovitB200Error("conv3d_wpackn: weight image does not match the layer")
-    _lib.call("cvit_conv3d_wpackn_ndhwc", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
-              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, int(act), _stream())
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_wpackn_ndhwc_aux", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, act, auxp, _stream())
 
 
 def linear_swiglu(a, w12i, bias12i, out) -> None:
@@ -261,13 +276,14 @@ def conv3d_halo(x, w_img, bias, out, dil: int, cout_pad: int) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, _stream())
 
 
-def conv3d_wpack8_gelu(x, w_img, bias_n, out, act: bool = True) -> None:
+def conv3d_wpack8_gelu(x, w_img, bias_n, out, act=True, aux=None) -> None:
     """output_layer.0 (8 -> 8, k3) + bias + GELU with 8 output voxels of a row per MMA row (csrc/conv_wpack.cu)."""
     D, H, W, Cin = x.shape
     if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_wpack_weight_bytes(8, 8):
         raise _lib.CryovitB200Error("conv3d_wpack8_gelu: needs 8 input channels and the (P=8, Cout=8) weight image")
-    _lib.call("cvit_conv3d_wpack8_gelu", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias_n, F32, "bias_n"),
-              _chk(out, BF16, "out"), D, H, W, int(act), _stream())
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_wpack8_aux", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias_n, F32, "bias_n"),
+              _chk(out, BF16, "out"), D, H, W, act, auxp, _stream())
 
 
 def conv3d_wpack8_final(x, w_img, bias_n, logits=None, probs=None) -> None:

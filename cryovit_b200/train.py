@@ -73,13 +73,20 @@ class _Conv:
     def __init__(self, trainer, key: str, cin: int, cout: int, dil: int, pre=None):
         self.tr, self.key, self.cin, self.cout, self.dil, self.pre = trainer, key, cin, cout, dil, pre
 
-    def run(self, tag, x, wfn, bias, out, cin, cout, dil):
-        """wfn: fp32 parameter -> the [cout, cin, 3,3,3] weight of THIS convolution (identity, or flip + transpose)."""
+    def run(self, tag, x, wfn, bias, out, cin, cout, dil, act=0, aux=None):
+        """wfn: fp32 parameter -> the [cout, cin, 3,3,3] weight of THIS convolution (identity, or flip + transpose).
+        act / aux: the fused element-wise pass of the epilogue (2: out = z, aux = gelu(z); 3: out = y * gelu'(aux))."""
         if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 16 == 0:
             # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): W-packed kernel
             b = bias.repeat(8).contiguous() if bias is not None else torch.zeros(64, device=x.device, dtype=F32)
             op = self.tr._pk(f"{self.key}/{tag}/wpack", self.key, lambda w: wpack_weight_image(wfn(w), 8))
-            ops.conv3d_wpack8_gelu(x, op, b, out, act=False)
+            if act == 2 and not self.tr.fuse_store_bound:
+                # measured (profiles/r02_train_notes.md): this kernel is bound by its stores; the second store costs what
+                # the separate pass does
+                ops.conv3d_wpack8_gelu(x, op, b, out, act=0)
+                T.gelu_fwd(out, aux)
+            else:
+                ops.conv3d_wpack8_gelu(x, op, b, out, act=act, aux=aux)
             return
         halo = cin in (8, 16, 32)
         cp = (32 if cout > 16 else 16) if halo else max(32, cout)
@@ -90,23 +97,27 @@ class _Conv:
         if P:
             # 16- / 32-channel layers (forward and input gradients alike): P voxels per tensor-core row (csrc/conv_wpackn.cu)
             op = self.tr._pk(f"{self.key}/{tag}/wpackn", self.key, lambda w: wpackn_weight_image(wfn(w), cp, P))
-            ops.conv3d_wpackn(x, op, b.repeat(64), out, dil, cp, act=False)
+            ops.conv3d_wpackn(x, op, b.repeat(64), out, dil, cp, act=act, aux=aux)
         elif halo:
             op = self.tr._pk(f"{self.key}/{tag}/halo", self.key, lambda w: _halo_image(wfn(w), cp))
-            T.conv3d_halo_act(x, op, b, out, dil, cp, False)
+            T.conv3d_halo_act(x, op, b, out, dil, cp, act, aux)
         else:
             op = self.tr._pk(f"{self.key}/{tag}/taps", self.key, lambda w: _taps(wfn(w), cp))
-            T.conv3d_dilated_act(x, op, b, out, dil, False)
+            T.conv3d_dilated_act(x, op, b, out, dil, act, aux)
 
     def _w(self, w):
         return self.pre(w) if self.pre is not None else w
 
-    def forward(self, x, bias, z):
-        self.run("f", x, self._w, bias, z, self.cin, self.cout, self.dil)
+    def forward(self, x, bias, z, a=None):
+        """z = conv(x) + bias; with ``a`` also a = gelu(z) from the same epilogue."""
+        self.run("f", x, self._w, bias, z, self.cin, self.cout, self.dil, 2 if a is not None else 0, a)
 
-    def input_gradient(self, dz, dx):
+    def input_gradient(self, dz, dx, z_below=None):
+        """dx = conv^T(dz); with ``z_below`` (the pre-activation whose GELU produced this convolution's input) the
+        epilogue multiplies by gelu'(z_below): dx is then the gradient of that pre-activation."""
         # [cin, cout, 3,3,3]: the gradient convolution's weight
-        self.run("g", dz, lambda w: self._w(w).flip(2, 3, 4).transpose(0, 1).contiguous(), None, dx, self.cout, self.cin, self.dil)
+        self.run("g", dz, lambda w: self._w(w).flip(2, 3, 4).transpose(0, 1).contiguous(), None, dx, self.cout, self.cin, self.dil,
+                 3 if z_below is not None else 0, z_below)
 
 
 class _KeepAlivePool(dict):
@@ -135,6 +146,15 @@ class CryoVITHeadTrainerB200:
             raise CryovitB200Error("no CUDA device: the B200 training path has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.in_channels, self.lr, self.weight_decay, self.betas, self.eps = in_channels, lr, weight_decay, betas, eps
+        import os
+
+        # GELU forward (z and gelu(z) from one epilogue) and backward (gelu'(z) applied by the input-gradient epilogue)
+        # fused into the convolutions; CVIT_TRAIN_FUSE_ACT=0 keeps the separate element-wise kernels (A/B, tests)
+        self.fuse_activations = os.environ.get("CVIT_TRAIN_FUSE_ACT", "1") != "0"
+        # ... also in the two kernels that are bound by their stores (transposed convolution, 8 -> 8 at full resolution),
+        # and gelu' in the input-gradient epilogues: both measured slower than the separate passes, off by default
+        self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "0") != "0"
+        self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
         if state_dict is None:
             from .host.models import default_state_dict
 
@@ -224,6 +244,12 @@ class CryoVITHeadTrainerB200:
         T.gelu_bwd(da, z, dz, db)
         self.g[key_b].copy_(db)
 
+    def _bias_grad(self, dz, key_b):
+        """The bias gradient alone (column sums of dz), for layers whose gelu' was applied by the producing epilogue."""
+        db = torch.zeros(dz.shape[-1], device=self.device, dtype=F32)
+        T.colsum(dz, db)
+        self.g[key_b].copy_(db)
+
     def _wgrad_conv(self, x, dz, dil, key_w):
         """Accumulates the weight gradient of a 3x3x3 convolution into the flat bucket (the bias gradient comes out of
         ``_gelu_bwd_bias``, which produced dz)."""
@@ -264,6 +290,10 @@ class CryoVITHeadTrainerB200:
         if C != self.in_channels or tuple(labels.shape) != (D, 16 * h, 16 * w):
             raise CryovitB200Error(f"features {tuple(features.shape)} / labels {tuple(labels.shape)} do not match")
         vox = D * h * w
+        # CVIT_TRAIN_FUSE_ACT=0: GELU forward / backward as separate element-wise kernels (the A/B arm; default: fused
+        # into the epilogues of the convolutions that produce z / the input gradients)
+        fuse = self.fuse_activations
+        fuse_sb, fuse_bwd = fuse and self.fuse_store_bound, fuse and self.fuse_backward
         self._pk_refresh()
         # ---------------- forward, keeping what the backward needs
         z_proj, a_proj = self._buf("z_proj", (vox, 1024)), self._buf("a_proj", (D, h, w, 1024))
@@ -274,13 +304,15 @@ class CryoVITHeadTrainerB200:
         x0 = None
         if cfirst:
             w16 = p["layers.0.weight"].reshape(1024, C).clamp(-6.0e4, 6.0e4).to(torch.float16)
-            ops.linear_bias_cfirst(feats.view(C, vox), w16, p["layers.0.bias"], z_proj, gelu=False)
+            ops.linear_bias_cfirst(feats.view(C, vox), w16, p["layers.0.bias"], z_proj, gelu=2 if fuse else 0,
+                                   aux=a_proj.view(vox, 1024) if fuse else None)
         else:
             x0 = self._buf("x0", (D, h, w, C))
             ops.features_to_ndhwc(feats, x0)
             ops.linear_bias(x0.view(vox, C), self._pk("proj/f", "layers.0.weight", lambda w_: w_.reshape(1024, C)), p["layers.0.bias"],
                             z_proj, gelu=False)
-        T.gelu_fwd(z_proj, a_proj.view(vox, 1024))
+        if not (fuse and cfirst):
+            T.gelu_fwd(z_proj, a_proj.view(vox, 1024))
         self.launches += 3
         saved = []
         cur, H, W = a_proj, h, w
@@ -292,24 +324,34 @@ class CryoVITHeadTrainerB200:
             ops.groupnorm_ndhwc(cur, n_out, p[pre + "0.weight"], p[pre + "0.bias"], stats, G, 1e-3)
             ca, cb = _Conv(self, pre + "1.weight", c1, c2, d1), _Conv(self, pre + "3.weight", c2, c2, d2)
             za, aa = self._buf(f"za{bi}", (D, H, W, c2)), self._buf(f"aa{bi}", (D, H, W, c2))
-            ca.forward(n_out, p[pre + "1.bias"], za)
-            T.gelu_fwd(za, aa)
+            if fuse:
+                ca.forward(n_out, p[pre + "1.bias"], za, aa)
+            else:
+                ca.forward(n_out, p[pre + "1.bias"], za)
+                T.gelu_fwd(za, aa)
             zb, ab = self._buf(f"zb{bi}", (D, H, W, c2)), self._buf(f"ab{bi}", (D, H, W, c2))
-            cb.forward(aa, p[pre + "3.bias"], zb)
-            T.gelu_fwd(zb, ab)
+            if fuse:
+                cb.forward(aa, p[pre + "3.bias"], zb, ab)
+            else:
+                cb.forward(aa, p[pre + "3.bias"], zb)
+                T.gelu_fwd(zb, ab)
             zt, at = self._buf(f"zt{bi}", (D, 2 * H, 2 * W, c3)), self._buf(f"at{bi}", (D, 2 * H, 2 * W, c3))
             # ConvTranspose weight [c2, c3, 1, 2, 2] -> rows (i*2+j)*c3 + co of the sub-pixel GEMM
             T.convT_act(ab, self._pk(pre + "5/f", pre + "5.weight",
                                      lambda wT, c2_=c2, c3_=c3: wT[:, :, 0].permute(2, 3, 1, 0).reshape(4 * c3_, c2_)),
-                        p[pre + "5.bias"].repeat(4).contiguous(), zt, False)
-            T.gelu_fwd(zt, at)
+                        p[pre + "5.bias"].repeat(4).contiguous(), zt, 2 if fuse_sb else 0, at if fuse_sb else None)
+            if not fuse_sb:
+                T.gelu_fwd(zt, at)
             self.launches += 9
             saved.append((cur, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W))
             cur, H, W = at, 2 * H, 2 * W
         co = _Conv(self, "output_layer.0.weight", 8, 8, 1)
         z1, a1 = self._buf("z_o0", (D, H, W, 8)), self._buf("a_o0", (D, H, W, 8))
-        co.forward(cur, p["output_layer.0.bias"], z1)
-        T.gelu_fwd(z1, a1)
+        if fuse:
+            co.forward(cur, p["output_layer.0.bias"], z1, a1)
+        else:
+            co.forward(cur, p["output_layer.0.bias"], z1)
+            T.gelu_fwd(z1, a1)
         logits, probs = self._buf("logits", (D, H, W), F32), self._buf("probs", (D, H, W), F32)
         if W % 16 == 0:
             ops.conv3d_wpack8_final(a1, self._pk("out2/f/wpack", "output_layer.2.weight", lambda w_: wpack_weight_image(w_, 16)),
@@ -331,23 +373,34 @@ class CryoVITHeadTrainerB200:
         db2 = torch.zeros(8, device=dev, dtype=F32)
         T.colsum(dl8, db2)
         g["output_layer.2.bias"].copy_(db2[:1])
-        da1 = self._buf("da_o0", (D, H, W, 8))
         # forward weight zero-padded to 8 output channels (the gradient volume carries 8 channels, channel 0 live)
-        _Conv(self, "output_layer.2.weight", 8, 8, 1,
-              pre=lambda w_: torch.cat([w_, torch.zeros(7, 8, 3, 3, 3, device=w_.device, dtype=w_.dtype)])).input_gradient(dl8, da1)
+        c_out2 = _Conv(self, "output_layer.2.weight", 8, 8, 1,
+                       pre=lambda w_: torch.cat([w_, torch.zeros(7, 8, 3, 3, 3, device=w_.device, dtype=w_.dtype)]))
         dz1 = self._buf("dz_o0", (D, H, W, 8))
-        self._gelu_bwd_bias(da1, z1, dz1, "output_layer.0.bias")
+        if fuse_bwd:
+            c_out2.input_gradient(dl8, dz1, z_below=z1)
+            self._bias_grad(dz1, "output_layer.0.bias")
+        else:
+            da1 = self._buf("da_o0", (D, H, W, 8))
+            c_out2.input_gradient(dl8, da1)
+            self._gelu_bwd_bias(da1, z1, dz1, "output_layer.0.bias")
         self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight")
-        dcur = self._buf("d_top", (D, H, W, 8))
-        co.input_gradient(dz1, dcur)
+        dcur = self._buf("d_top", (D, H, W, 8))  # d(at) of the last block, or (fused) already d(zt)
+        co.input_gradient(dz1, dcur, z_below=saved[3][10] if fuse_bwd else None)
+        dcur_is_dz = fuse_bwd
         self.launches += 14
         for bi in reversed(range(4)):
             c1, c2, c3, d1, d2 = BLOCKS[bi]
             pre = f"layers.{bi + 2}.layers."
             blk_in, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W = saved[bi]
             # transposed convolution: dcur is d(at) [D, 2H, 2W, c3]
-            dzt = self._buf(f"dzt{bi}", (D, 2 * H, 2 * W, c3))
-            self._gelu_bwd_bias(dcur, zt, dzt, pre + "5.bias")  # summed over voxels AND sub-pixels: dzt is [.., c3]
+            if dcur_is_dz:  # the producer's epilogue already applied gelu'(zt)
+                dzt = dcur
+                self._bias_grad(dzt, pre + "5.bias")
+                dcur_is_dz = False
+            else:
+                dzt = self._buf(f"dzt{bi}", (D, 2 * H, 2 * W, c3))
+                self._gelu_bwd_bias(dcur, zt, dzt, pre + "5.bias")  # summed over voxels AND sub-pixels: dzt is [.., c3]
             dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
             T.pixel_unshuffle(dzt, dzun)
             rows = D * H * W
@@ -360,17 +413,26 @@ class CryoVITHeadTrainerB200:
                 return torch.cat([wd, torch.zeros(n_ - c2_, 4 * c3_, device=wT.device, dtype=wT.dtype)]) if n_ > c2_ else wd
 
             wd_p = self._pk(pre + "5/g", pre + "5.weight", wd_fn)
-            dab = self._buf(f"dab{bi}", (D, H, W, c2))
-            T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, torch.zeros(n_pad, device=dev, dtype=F32), dab.view(rows, c2), c2)
-            # conv b
             dzb = self._buf(f"dzb{bi}", (D, H, W, c2))
-            self._gelu_bwd_bias(dab, zb, dzb, pre + "3.bias")
-            self._wgrad_conv(aa, dzb, d2, pre + "3.weight")
-            daa = self._buf(f"daa{bi}", (D, H, W, c2))
-            cb.input_gradient(dzb, daa)
-            # conv a
             dza = self._buf(f"dza{bi}", (D, H, W, c2))
-            self._gelu_bwd_bias(daa, za, dza, pre + "1.bias")
+            zero_b = torch.zeros(n_pad, device=dev, dtype=F32)
+            if fuse_bwd:
+                # conv b, conv a: each input gradient leaves its epilogue as the gradient of the pre-activation below
+                T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, zero_b, dzb.view(rows, c2), c2, z=zb.view(rows, c2))
+                self._bias_grad(dzb, pre + "3.bias")
+                self._wgrad_conv(aa, dzb, d2, pre + "3.weight")
+                cb.input_gradient(dzb, dza, z_below=za)
+                self._bias_grad(dza, pre + "1.bias")
+            else:
+                dab = self._buf(f"dab{bi}", (D, H, W, c2))
+                T.linear_nvalid(dzun.view(rows, 4 * c3), wd_p, zero_b, dab.view(rows, c2), c2)
+                # conv b
+                self._gelu_bwd_bias(dab, zb, dzb, pre + "3.bias")
+                self._wgrad_conv(aa, dzb, d2, pre + "3.weight")
+                daa = self._buf(f"daa{bi}", (D, H, W, c2))
+                cb.input_gradient(dzb, daa)
+                # conv a
+                self._gelu_bwd_bias(daa, za, dza, pre + "1.bias")
             self._wgrad_conv(n_out, dza, d1, pre + "1.weight")
             dn = self._buf(f"dn{bi}", (D, H, W, c1))
             ca.input_gradient(dza, dn)

@@ -1,37 +1,47 @@
 """Torch-tensor front end of the TRAINING entry points of the C ABI (see include/cryovit_b200.h, "Head TRAINING")."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
-from .ops import BF16, F32, _chk, _stream
+from .ops import BF16, F32, _aux, _chk, _stream
 
 
-def conv3d_dilated_act(x, w_taps, bias, out, dil: int, act: bool) -> None:
+def conv3d_dilated_act(x, w_taps, bias, out, dil: int, act, aux=None) -> None:
+    """act: 0 none, 1 GELU, 2 out = z and aux = gelu(z), 3 out = y * gelu'(aux) (include/cryovit_b200.h, *_aux)."""
     D, H, W, Cin = x.shape
     Cout = w_taps.shape[0] // 27
-    _lib.call("cvit_conv3d_dilated_ndhwc_act", _chk(x, BF16, "x"), _chk(w_taps, BF16, "w_taps"), _chk(bias, F32, "bias"),
-              _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, int(act), _stream())
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_dilated_ndhwc_aux", _chk(x, BF16, "x"), _chk(w_taps, BF16, "w_taps"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, out.shape[-1], dil, act, auxp, _stream())
 
 
-def conv3d_halo_act(x, w_img, bias, out, dil: int, cout_pad: int, act: bool) -> None:
+def conv3d_halo_act(x, w_img, bias, out, dil: int, cout_pad: int, act, aux=None) -> None:
     D, H, W, Cin = x.shape
-    _lib.call("cvit_conv3d_halo_ndhwc_act", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias, F32, "bias"),
-              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, int(act), _stream())
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_halo_ndhwc_aux", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), D, H, W, Cin, cout_pad, out.shape[-1], dil, act, auxp, _stream())
 
 
-def convT_act(x, w_sub, bias4, out, act: bool) -> None:
+def convT_act(x, w_sub, bias4, out, act, aux=None) -> None:
     D, H, W, Cin = x.shape
     Cout = w_sub.shape[0] // 4
-    _lib.call("cvit_convT_1x2x2_ndhwc_act", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
-              _chk(out, BF16, "out"), D, H, W, Cin, Cout, int(act), _stream())
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_convT_1x2x2_ndhwc_aux", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, act, auxp, _stream())
 
 
-def linear_nvalid(a, w, bias, out, n_valid: int) -> None:
-    """out[M, n_valid] = a[M, K] @ w[N, K]^T + bias (no activation); w may carry zero rows beyond n_valid."""
+def linear_nvalid(a, w, bias, out, n_valid: int, z=None) -> None:
+    """out[M, n_valid] = a[M, K] @ w[N, K]^T + bias (no activation); w may carry zero rows beyond n_valid. With ``z``
+    (bf16, out's shape and pitch) the result is multiplied by gelu'(z): the gradient of the pre-activation z."""
     M, K = a.shape
-    _lib.call("cvit_linear_bias_bf16_nvalid", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
-              _chk(out, BF16, "out"), out.stride(0), M, w.shape[0], K, n_valid, _stream())
+    act, auxp = _aux(3 if z is not None else 0, z, out)
+    if z is not None and z.stride(0) != out.stride(0):
+        raise _lib.CryovitB200Error("linear_nvalid: z must have the output's row pitch")
+    _lib.call("cvit_linear_bias_bf16_nvalid_aux", _chk(a, BF16, "a"), a.stride(0), _chk(w, BF16, "w"), _chk(bias, F32, "bias"),
+              _chk(out, BF16, "out"), out.stride(0), M, w.shape[0], K, n_valid, act, auxp, _stream())
 
 
 def gelu_fwd(z, a) -> None:
@@ -134,8 +144,11 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
     9-tap split-K GEMMs. ``pool`` (a dict) recycles the operand buffers between calls."""
     D, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    if (Cin, Cout) in ((8, 8), (16, 16), (32, 16), (32, 32)):  # narrow layers: warp-MMA reduction over the channels-last volumes
+    if (Cin, Cout) in ((8, 8), (16, 16), (32, 16), (32, 32)):  # narrow layers: reduction over the channels-last volumes
         dwn = torch.zeros(27, Cout, Cin, device=x.device, dtype=F32)
+        if Cin == 8 and W % 8 == 0 and os.environ.get("CVIT_WGRAD_TC8", "1") != "0":  # tcgen05, voxels as K (csrc/wgrad_tc.cu)
+            _lib.call("cvit_wgrad_tc8_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, dil, _stream())
+            return dwn
         _lib.call("cvit_wgrad_narrow_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
                   dil, _stream())
         return dwn

@@ -290,6 +290,33 @@ int cvit_conv3d_halo_ndhwc_act(const void* x, const void* w_img, const float* bi
 int cvit_convT_1x2x2_ndhwc_act(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
                                int64_t W, int64_t Cin, int64_t Cout, int act, void* stream);
 
+/* Fused element-wise passes of the training step (reference: nn.GELU() between the layers of models/cryovit.py:19-37,
+ * 68-78 and its autograd backward). The *_aux entry points are the kernels above with a second bf16 tensor `aux` of
+ * the output's shape and indexing, and act one of
+ *     0  out = y                          1  out = gelu(y)
+ *     2  out = y, aux = gelu(y)           (training forward: the pre-activation is kept for the backward pass)
+ *     3  out = y * gelu'(aux)             (input-gradient convolution; aux = saved pre-activation of the layer below)
+ * y = the convolution / GEMM result plus bias. act 0 / 1 ignore aux (may be null); act 3 is not offered by the
+ * transposed convolution and the channels-first linear. aux must be 16-byte aligned. */
+int cvit_conv3d_dilated_ndhwc_aux(const void* x, const void* w_taps, const float* bias, void* out, int64_t D,
+                                  int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t Cout_valid, int64_t dil,
+                                  int act, void* aux, void* stream);
+int cvit_conv3d_halo_ndhwc_aux(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                               void* aux, void* stream);
+int cvit_conv3d_wpackn_ndhwc_aux(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                                 int64_t W, int64_t Cin, int64_t Cout_pad, int64_t Cout_valid, int64_t dil, int act,
+                                 void* aux, void* stream);
+int cvit_conv3d_wpack8_aux(const void* x, const void* w_img, const float* bias_n, void* out, int64_t D, int64_t H,
+                           int64_t W, int act, void* aux, void* stream);
+int cvit_convT_1x2x2_ndhwc_aux(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
+                               int64_t W, int64_t Cin, int64_t Cout, int act, void* aux, void* stream);
+int cvit_linear_bias_cfirst_f16_aux(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
+                                    int64_t M, int64_t N, int64_t K, int act, void* aux, void* stream);
+/* act 0 or 3 only; aux bf16 [M, n_valid] with row pitch ldo. */
+int cvit_linear_bias_bf16_nvalid_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
+                                     int64_t M, int64_t N, int64_t K, int64_t n_valid, int act, const void* aux, void* stream);
+
 /* cvit_linear_bias_bf16 (no GELU) for an output narrower than the zero-row-padded weight: columns >= n_valid are not
  * stored and ldo is the true row pitch (input gradient of the 16-channel transposed convolution). */
 int cvit_linear_bias_bf16_nvalid(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
@@ -357,6 +384,13 @@ int cvit_wgrad_mn_ndhwc(const void* a, const void* b, float* out, int64_t D, int
  * dz bf16 [D,H,W,Cout]. */
 int cvit_wgrad_narrow_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t Cin,
                             int64_t Cout, int64_t dil, void* stream);
+
+/* The 8 -> 8 channel case (output_layer.0 / output_layer.2 at full resolution) on tcgen05 (csrc/wgrad_tc.cu): the voxels
+ * of a row are the K dimension of one MMA per 16 voxels for all 27 taps, both operands are the channels-last volumes as
+ * they lie (MN-major, the column taps are 16-byte shifts of the same row). Same contract as cvit_wgrad_narrow_ndhwc with
+ * Cin = Cout = 8; W must be a multiple of 8. */
+int cvit_wgrad_tc8_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil,
+                         void* stream);
 
 /* AdamW step over a flat fp32 parameter vector, torch.optim.AdamW semantics (models/base_model.py:58-63):
  * decoupled weight decay, bias-corrected moments; g is multiplied by grad_scale first. step counts from 1. */

@@ -183,7 +183,8 @@ def test_layernorm(cuda_lib, C):
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (2, 70, 2), (3, 29, 2), (1, 128, 1), (1, 256, 2), (2, 261, 1),
-                                   (16, 300, 8), (6, 1029, 6), (40, 120, 8)])  # more work items than SMs: persistent path
+                                   (16, 300, 8), (6, 1029, 6), (40, 120, 8),  # more work items than SMs: persistent path
+                                   (2, 133, 2), (2, 264, 2), (3, 385, 1), (1, 517, 2)])  # 1..8 trailing keys: epilogue path
 @pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("scale", [1.0, 6.0])
 def test_attention(cuda_lib, B, T, H, legacy, scale):
@@ -222,19 +223,21 @@ def test_attention_extreme_scores(cuda_lib):
     B, T, H = 4, 700, 3
     C = H * 64
     qkv = (_rand(B * T, 3 * C, seed=3) * 0.5).bfloat16().view(B, T, 3, H, 64)
-    for b, h, key in [(1, 0, 300), (3, 2, 699), (2, 1, 5)]:
-        qkv[b, :, 0, h, :] = 40.0
-        qkv[b, key, 1, h, :] = 40.0
-    qkv = qkv.view(B * T, 3 * C).contiguous()
-    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
-    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
-    for odt in (torch.bfloat16, torch.float16):
-        out = torch.full((B * T, C), float("nan"), device=DEV, dtype=odt)
-        ops.attention(qkv, out, B, T, H)
-        _close(out, ref, atol=2e-2, rtol=2e-2, what=f"attention with one dominant key, out {odt}")
+    for T in (700, 645):  # 645 = 5 * 128 + 5: the trailing five keys are merged by the epilogue warps (fp32, CUDA cores)
+        qkv = (_rand(B * T, 3 * C, seed=3) * 0.5).bfloat16().view(B, T, 3, H, 64)
+        for b, h, key in [(1, 0, 300), (3, 2, T - 1), (2, 1, 5), (0, 1, T - 4)]:
+            qkv[b, :, 0, h, :] = 40.0
+            qkv[b, key, 1, h, :] = 40.0
+        qkv = qkv.view(B * T, 3 * C).contiguous()
+        q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+        ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, C)
+        for odt in (torch.bfloat16, torch.float16):
+            out = torch.full((B * T, C), float("nan"), device=DEV, dtype=odt)
+            ops.attention(qkv, out, B, T, H)
+            _close(out, ref, atol=2e-2, rtol=2e-2, what=f"attention with one dominant key, T {T}, out {odt}")
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (3, 29, 2), (2, 261, 1), (16, 300, 8)])
+@pytest.mark.parametrize("B,T,H", [(2, 1029, 3), (1, 789, 6), (3, 29, 2), (2, 261, 1), (16, 300, 8), (2, 136, 2)])
 @pytest.mark.parametrize("scale", [1.0, 6.0])
 def test_attention_fp16(cuda_lib, B, T, H, scale):
     """Same kernel with fp16 q/k/v, probabilities and output; the tolerance is 4x tighter than the bf16 one."""

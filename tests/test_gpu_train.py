@@ -43,6 +43,8 @@ def test_gelu_fwd_bwd(cuda_lib):
                                                  (5, 8, 12, 128, 192, 2), (3, 8, 8, 192, 192, 1),
                                                  # 8 x 8 channels: warp-MMA kernel on the channels-last volumes (ragged tiles, dilation)
                                                  (5, 13, 150, 8, 8, 2), (4, 40, 272, 8, 8, 1), (1, 8, 128, 8, 8, 1),
+                                                 # W % 8 == 0: tcgen05 kernel with the voxels as K (ragged row blocks / segments, dilation)
+                                                 (7, 21, 264, 8, 8, 3), (2, 3, 8, 8, 8, 1), (40, 64, 512, 8, 8, 1),
                                                  (5, 13, 150, 16, 16, 2), (9, 20, 70, 32, 16, 4), (4, 24, 136, 32, 32, 1)])
 def test_conv_weight_gradient_splitk(cuda_lib, D, H, W, Cin, Cout, dil):
     """dW[tap][co][ci] from channels-first padded copies + split-K GEMM == autograd of F.conv3d."""
@@ -108,6 +110,82 @@ def test_conv_input_gradient_is_conv_with_flipped_weights(cuda_lib, D, H, W, Cin
     y = F.conv3d(xr, w.float(), None, padding="same", dilation=(dil, 1, 1))
     y.backward(dz.float().permute(3, 0, 1, 2)[None])
     assert _relerr(out, xr.grad[0].permute(1, 2, 3, 0)) < 6e-3
+
+
+@pytest.mark.parametrize("kind,D,H,W,Cin,Cout,dil", [("dilated", 4, 12, 20, 64, 128, 2), ("dilated", 3, 8, 16, 192, 192, 1),
+                                                     ("halo", 4, 9, 11, 16, 32, 2), ("halo", 3, 10, 14, 32, 16, 1),
+                                                     ("wpackn", 4, 20, 24, 32, 16, 2), ("wpackn", 3, 18, 40, 16, 16, 1),
+                                                     ("wpackn", 3, 17, 12, 32, 32, 4), ("wpack8", 3, 20, 48, 8, 8, 1),
+                                                     ("convT", 3, 10, 12, 64, 32, 0), ("convT", 2, 9, 8, 16, 8, 0),
+                                                     ("nvalid", 1, 1, 4096, 128, 16, 0), ("nvalid", 1, 1, 1000, 512, 192, 0),
+                                                     ("cfirst", 1, 1, 2048, 384, 1024, 0)])
+def test_fused_activation_epilogues(cuda_lib, kind, D, H, W, Cin, Cout, dil):
+    """The *_aux entry points against the separate element-wise kernels: act 2 leaves the act-0 pre-activation in `out`
+    bit for bit and gelu of it in `aux`; act 3 multiplies the act-0 result by gelu'(aux) (what gelu_bwd computes)."""
+    from cryovit_b200 import ops, train_ops as T
+    from cryovit_b200.head import _conv_taps, halo_weight_image, wpack_weight_image, wpackn_weight_image
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    oshape = (D, 2 * H, 2 * W, Cout) if kind == "convT" else (D, H, W, Cout)
+    if kind in ("dilated", "halo", "wpackn", "wpack8"):
+        w = _rand(Cout, Cin, 3, 3, 3, scale=(27 * Cin) ** -0.5, seed=2)
+        bias = _rand(Cout, seed=3)
+        if kind == "dilated":
+            op = _conv_taps(w.cpu(), Cout).bfloat16().to(DEV)
+            run = lambda out, act, aux: T.conv3d_dilated_act(x, op, bias, out, dil, act, aux)
+        elif kind == "halo":
+            cp = 32 if Cout > 16 else 16
+            op = halo_weight_image(w.cpu(), cp).bfloat16().to(DEV)
+            b = torch.zeros(cp, device=DEV)
+            b[:Cout] = bias
+            run = lambda out, act, aux: T.conv3d_halo_act(x, op, b, out, dil, cp, act, aux)
+        elif kind == "wpackn":
+            cp = 32 if Cout > 16 else 16
+            op = wpackn_weight_image(w, cp, ops.wpackn_group(Cin, cp)).bfloat16()
+            b = torch.zeros(cp, device=DEV)
+            b[:Cout] = bias
+            run = lambda out, act, aux: ops.conv3d_wpackn(x, op, b.repeat(64), out, dil, cp, act=act, aux=aux)
+        else:
+            op = wpack_weight_image(w, 8).bfloat16()
+            run = lambda out, act, aux: ops.conv3d_wpack8_gelu(x, op, bias.repeat(8).contiguous(), out, act=act, aux=aux)
+    elif kind == "convT":
+        wsub = _rand(4 * Cout, Cin, scale=Cin ** -0.5, seed=2).bfloat16()
+        b4 = _rand(Cout, seed=3).repeat(4).contiguous()
+        run = lambda out, act, aux: T.convT_act(x, wsub, b4, out, act, aux)
+    elif kind == "nvalid":
+        n_pad = max(32, Cout)
+        wd = torch.zeros(n_pad, Cin, device=DEV, dtype=torch.bfloat16)
+        wd[:Cout] = _rand(Cout, Cin, scale=Cin ** -0.5, seed=2).bfloat16()
+        rows = x.view(W, Cin)
+        oshape = (W, Cout)
+        run = lambda out, act, aux: T.linear_nvalid(rows, wd, torch.zeros(n_pad, device=DEV), out, Cout, z=aux if act == 3 else None)
+    else:
+        at = _rand(Cin, W, seed=1).half()
+        w16 = _rand(Cout, Cin, scale=Cin ** -0.5, seed=2).half()
+        bias = _rand(Cout, seed=3)
+        oshape = (W, Cout)
+        run = lambda out, act, aux: ops.linear_bias_cfirst(at, w16, bias, out, gelu=act, aux=aux)
+    z0 = torch.full(oshape, float("nan"), device=DEV, dtype=torch.bfloat16)
+    run(z0, 0, None)
+    assert torch.isfinite(z0.float()).all()
+    if kind != "nvalid":  # (the narrow linear only offers act 3)
+        _check_dual(run, z0, T)
+    if kind in ("convT", "cfirst"):
+        return
+    # act 3
+    zb = (_rand(*oshape, scale=1.5, seed=5)).bfloat16()
+    dz, dz_ref = torch.full_like(z0, float("nan")), torch.empty_like(z0)
+    run(dz, 3, zb)
+    T.gelu_bwd(z0, zb, dz_ref)
+    assert _relerr(dz, dz_ref) < 4e-3, _relerr(dz, dz_ref)
+
+
+def _check_dual(run, z0, T):
+    z, a = torch.full_like(z0, float("nan")), torch.full_like(z0, float("nan"))
+    run(z, 2, a)
+    assert torch.equal(z, z0)
+    a_ref = torch.empty_like(z0)
+    T.gelu_fwd(z0, a_ref)
+    assert _relerr(a, a_ref) < 4e-3 and (a.float() - a_ref.float()).abs().max() < 0.05
 
 
 @pytest.mark.parametrize("C,G", [(1024, 128), (128, 16), (32, 8)])

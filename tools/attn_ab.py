@@ -64,8 +64,7 @@ q, k, v = qkv[: 4 * T].view(4, T, 3, H, 64).permute(2, 0, 3, 1, 4).float()
 ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(4 * T, H * 64)
 err = (out[: 4 * T].float() - ref).abs().max().item()
 tag = f"lib={Path(os.environ.get('CRYOVIT_B200_LIB', 'product')).name} exact={os.environ.get('CVIT_FA_EXACT', '0')} scale={scale} out={odt}"
-print(f"[{tag}] alone {alone:.4f} ms (min {best:.4f}) | between GEMMs {seq:.4f} ms | max abs err {err:.3e} | exact-pass items "
-      f"{_lib.load().cvit_attention_redo_items()}", flush=True)
+print(f"[{tag}] alone {alone:.4f} ms (min {best:.4f}) | between GEMMs {seq:.4f} ms | max abs err {err:.3e}", flush=True)
 if os.environ.get("ATTN_AB_SDPA"):
     qq, kk, vv = qkv.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ts = []
