@@ -70,15 +70,6 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t addr, uint32_t lbo, 
          (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
 }
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];" ::"r"(dst),
-      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloArgs args) {

@@ -13,7 +13,7 @@
 //     bytes, the next 8 voxels follow 128 bytes on (LBO).
 //   * A = X. The three column taps kw are the SAME row read one voxel further on, and one voxel is 16 bytes = the stride
 //     between core matrices along M (SBO = 16): accumulator row m = kw * 8 + ci reads X[.., x0 + k - 1 + kw][ci]. No
-//     shifted copies. (M = 128 reads 13 more "taps"; those accumulator rows are never looked at.)
+//     shifted copies. (The MMA's other rows read further "taps"; those accumulator rows are never looked at.)
 //   * B = dZ. For the X row (z0, y0) the nine (kd, kh) taps pair it with the dZ rows (z0 - (kd-1) dil, y0 - (kh-1)). A stage
 //     holds the dZ rows y0 - 1 .. y0 + R of the three planes as equal-sized arrays ordered [row][plane], so the nine arrays
 //     of one X row are consecutive: accumulator column n = ((yr * 3 + kd) * 8 + co), SBO = array size. R consecutive X
@@ -21,7 +21,7 @@
 //   * Every TMA box is whole 128-byte lines ([8 voxels][8 channels]); out-of-bounds zero fill is the convolution's
 //     padding (x = -1, x = W, rows and planes outside the volume) and the ragged ends of the tiling.
 //
-// One MMA (M 128, N 80, K 16 voxels) per 16 voxels of a row for all 27 taps: 2.1 M MMAs per launch over 148 SMs. The
+// One MMA (M 64, N 80, K 16 voxels) per 16 voxels of a row for all 27 taps: 2.1 M MMAs per launch over 148 SMs. The
 // accumulator (80 TMEM columns) lives for the whole kernel; one red.global.add pass per CTA at the end.
 // One CTA per SM, 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warp 4 the final read-out.
 #include "ptx.cuh"
@@ -40,6 +40,11 @@ constexpr int WT_STAGE = (WT_X_BYTES + WT_Z_BYTES + 1023) / 1024 * 1024;
 constexpr int WT_STAGES = 2;
 constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 256 + 1024;
 constexpr int WT_N = 80, WT_TMEM_COLS = 128;
+// M = 64 halves the A tile the tensor core streams per MMA (24 of the rows are used either way): 0.475 -> 0.382 ms per
+// launch. -DWT_M=128 builds the full-height variant (A/B).
+#ifndef WT_M
+#define WT_M 64
+#endif
 constexpr uint32_t WT_TX_BYTES = WT_R * WT_XARR + (WT_R + 2) * 3 * WT_ZARR;
 
 struct WtArgs {
@@ -105,7 +110,7 @@ wgrad_tc8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, WT_N) | (1u << 15) | (1u << 16);  // A and B MN-major
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(WT_M, WT_N) | (1u << 15) | (1u << 16);  // A and B MN-major
     uint32_t it = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
       const uint32_t s = it % WT_STAGES;
@@ -128,18 +133,21 @@ wgrad_tc8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     if (elect_one_sync()) umma_commit(bar_done);
     __syncwarp();
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ read-out: lanes 0..23 = (kw, ci)
+  } else if (warp == 4 || (WT_M == 64 && warp == 5)) {
+    // ------------------------------------------------------------------ read-out: accumulator row m = (kw, ci) < 24.
+    // M = 128: TMEM lane = row. M = 64: rows 16 q .. 16 q + 15 sit in lanes 32 q .. 32 q + 15 (one 16-lane slice per warp quarter).
     mbar_wait(bar_done, 0);
     tcgen05_fence_after();
-    if (blockIdx.x < num_blocks) {
-      const int kw = lane >> 3, ci = lane & 7;
+    {
+      const int q = warp & 3;
+      const int m = WT_M == 64 ? (lane < 16 ? q * 16 + lane : 99) : lane;
+      const int kw = m >> 3, ci = m & 7;
 #pragma unroll 1
       for (int c = 0; c < 5; ++c) {
         uint32_t v[16];
-        tmem_ld_32x16(tmem_base + c * 16, v);
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 16, v);
         tmem_ld_wait();
-        if (lane < 24) {
+        if (m < 24) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int n = c * 16 + i;
@@ -161,6 +169,185 @@ wgrad_tc8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tcgen05_fence_after();
     tmem_dealloc<WT_TMEM_COLS>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 16 / 32 channels: the same formulation with the volumes split into 8-channel chunks. TMA boxes of (8 channels, one
+// chunk, KSEG voxels) land as [voxel][8] arrays, i.e. the operand layout above; the accumulator rows are
+// m = (kw * NCX + j) * 8 + t (array (kw, j) = chunk j of the row shifted by kw - 1 voxels: with more than one chunk per
+// voxel the column taps are separate arrays, equally spaced), the columns n = ((yr * 3 + kd) * NCZ + jz) * 8 + t'.
+// One MMA (M 128, N 144) per 16 voxels and 144 columns: 96 x 144 useful of 128 x 144 for 32 -> 16.
+template <int CIN, int COUT, int R, int KSEG>
+struct WtnCfg {
+  static constexpr int NCX = CIN / 8, NCZ = COUT / 8;
+  static constexpr int S = KSEG * 16;                              // one [KSEG][8] array
+  static constexpr int XA = R * 3 * NCX, ZA = (R + 2) * 3 * NCZ;   // arrays per stage
+  static constexpr int STAGE = ((XA + ZA) * S + 1023) / 1024 * 1024;
+  static constexpr int STAGES_RAW = (227 * 1024 - 2048) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+  static constexpr int MROWS = 24 * NCX;
+  static constexpr int MM = MROWS <= 64 ? 64 : 128;                // MMA height
+  static constexpr int N = 72 * NCZ, NSPLIT = N > 256 ? 2 : 1, NH = N / NSPLIT;
+  static constexpr int TMEM_COLS = N <= 128 ? 128 : N <= 256 ? 256 : 512;
+  static constexpr uint32_t TX_BYTES = (XA + ZA) * S;
+  static_assert(NCX >= 2 && NCZ >= 2 && NH % 16 == 0 && NH <= 256 && STAGES >= 2, "unsupported layer");
+  static_assert(16 <= XA - 3 * NCX * (R - 1) + ZA, "M = 128 over-reads 16 arrays from the last row's first");
+};
+
+template <int CIN, int COUT, int R, int KSEG>
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad_tcn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, const WtArgs args) {
+  using Cfg = WtnCfg<CIN, COUT, R, KSEG>;
+  constexpr int STAGES = Cfg::STAGES, S = Cfg::S, NCX = Cfg::NCX, NCZ = Cfg::NCZ;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = smem_base + STAGES * Cfg::STAGE;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_done = sBar + 16 * STAGES, tmem_slot = bar_done + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int segs = (args.W + KSEG - 1) / KSEG, hblocks = (args.H + R - 1) / R;
+  const int num_blocks = args.D * hblocks * segs;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: the whole warp issues boxes
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      const int seg = blk % segs, hb = (blk / segs) % hblocks, z0 = blk / (segs * hblocks);
+      const int x0 = seg * KSEG, yb = hb * R;
+      const uint32_t s = it % STAGES;
+      const uint32_t sX = smem_base + s * Cfg::STAGE, sZ = sX + Cfg::XA * S, bar = bar_full + 8 * s;
+      if (lane == 0) {
+        mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar, Cfg::TX_BYTES);
+      }
+      __syncwarp();
+      for (int i = lane; i < Cfg::XA; i += 32) {  // array i = (r * 3 + kw) * NCX + j
+        const int j = i % NCX, kw = (i / NCX) % 3, r = i / (3 * NCX);
+        tma_load_5d(sX + i * S, &tmX, bar, 0, j, x0 - 1 + kw, yb + r, z0);
+      }
+      for (int i = lane; i < Cfg::ZA; i += 32) {  // array i = (rr * 3 + kd) * NCZ + jz
+        const int jz = i % NCZ, kd = (i / NCZ) % 3, rr = i / (3 * NCZ);
+        tma_load_5d(sZ + i * S, &tmZ, bar, 0, jz, x0, yb - 1 + rr, z0 - (kd - 1) * args.dil);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::MM, Cfg::NH) | (1u << 15) | (1u << 16);  // A and B MN-major
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      const uint32_t s = it % STAGES;
+      mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sX = smem_base + s * Cfg::STAGE, sZ = sX + Cfg::XA * S;
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+          const uint64_t ad = wt_desc(sX + r * 3 * NCX * S, 128, S);
+#pragma unroll
+          for (int h = 0; h < Cfg::NSPLIT; ++h) {
+            const uint64_t bd = wt_desc(sZ + (r * 3 * NCZ + h * (Cfg::NH / 8)) * S, 128, S);
+#pragma unroll
+            for (int ks = 0; ks < KSEG / 16; ++ks)
+              umma_bf16(tmem_base + h * Cfg::NH, ad + 16 * ks, bd + 16 * ks, idesc, (it | r | ks) != 0);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(bar_done);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ read-out: TMEM lane = (kw, j, t)
+    const int q = warp & 3;
+    mbar_wait(bar_done, 0);
+    tcgen05_fence_after();
+    // M = 128: TMEM lane = accumulator row; M = 64: rows 16 q .. 16 q + 15 sit in lanes 32 q .. 32 q + 15
+    const int m = Cfg::MM == 64 ? (lane < 16 ? q * 16 + lane : Cfg::MROWS) : q * 32 + lane;
+    if ((Cfg::MM == 64 ? q * 16 : q * 32) < Cfg::MROWS) {
+      const int t = m & 7, j = (m >> 3) % NCX, kw = m / (8 * NCX), ci = j * 8 + t;
+#pragma unroll 1
+      for (int c2 = 0; c2 < Cfg::N / 16; ++c2) {  // two column blocks c = (yr * 3 + kd) * NCZ + jz at a time
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c2 * 16, v);
+        tmem_ld_wait();
+        if (m < Cfg::MROWS) {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int c = 2 * c2 + hb;
+            const int jz = c % NCZ, rest = c / NCZ, yr = rest / 3, kd = rest - 3 * yr, kh = 2 - yr;
+            float* dst = args.dw + ((size_t)(((kd * 3 + kh) * 3 + kw) * COUT + jz * 8) * CIN + ci);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dst + (size_t)i * CIN, __uint_as_float(v[hb * 8 + i]));
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int CIN, int COUT, int R, int KSEG>
+static int launch_wgrad_tcn(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil, cudaStream_t stream) {
+  using Cfg = WtnCfg<CIN, COUT, R, KSEG>;
+  CUtensorMap tmX, tmZ;
+  // (8 channels, chunk, x, y, z)
+  uint64_t dimsX[5] = {8, (uint64_t)Cfg::NCX, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+  uint64_t strX[5] = {0, 16, (uint64_t)CIN * 2, (uint64_t)W * CIN * 2, (uint64_t)H * W * CIN * 2};
+  uint64_t dimsZ[5] = {8, (uint64_t)Cfg::NCZ, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+  uint64_t strZ[5] = {0, 16, (uint64_t)COUT * 2, (uint64_t)W * COUT * 2, (uint64_t)H * W * COUT * 2};
+  uint32_t box[5] = {8, 1, KSEG, 1, 1};
+  int rc = encode_tmap(&tmX, TmapDtype::BF16, 5, x, dimsX, strX, box, 0);
+  if (rc) return rc;
+  rc = encode_tmap(&tmZ, TmapDtype::BF16, 5, dz, dimsZ, strZ, box, 0);
+  if (rc) return rc;
+  auto kern = wgrad_tcn_kernel<CIN, COUT, R, KSEG>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tcn: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t blocks = D * ((H + R - 1) / R) * ((W + KSEG - 1) / KSEG);
+  int grid = num_sms();
+  if (grid > blocks) grid = (int)blocks;
+  WtArgs a;
+  a.dw = dw;
+  a.D = (int)D;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.dil = (int)dil;
+  kern<<<grid, WT_THREADS, Cfg::SMEM, stream>>>(tmX, tmZ, a);
+  return check_launch("wgrad_tcn_kernel");
 }
 
 }  // namespace cvit
@@ -212,4 +399,24 @@ extern "C" int cvit_wgrad_tc8_ndhwc(const void* x, const void* dz, float* dw, in
   a.dil = (int)dil;
   wgrad_tc8_kernel<<<grid, WT_THREADS, WT_SMEM, (cudaStream_t)stream>>>(tmX, tmZ, a);
   return check_launch("wgrad_tc8_kernel");
+}
+
+// The 16- / 32-channel layers (SynthesisBlocks 3-4): (Cin, Cout) in {(16,16), (32,16), (32,32)}, any W. Same contract as
+// cvit_wgrad_narrow_ndhwc: dw fp32 [27][Cout][Cin] accumulated into.
+extern "C" int cvit_wgrad_tcn_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                                    int64_t Cout, int64_t dil, void* stream) {
+  if (!x || !dz || !dw || D <= 0 || H <= 0 || W <= 0 || dil <= 0) {
+    set_error("wgrad_tcn: bad arguments (D=%lld H=%lld W=%lld dil=%lld)", (long long)D, (long long)H, (long long)W, (long long)dil);
+    return CVIT_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz)) & 15u) {
+    set_error("wgrad_tcn: x and dz must be 16-byte aligned");
+    return CVIT_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 16 && Cout == 16) return launch_wgrad_tcn<16, 16, 4, 64>(x, dz, dw, D, H, W, dil, st);
+  if (Cin == 32 && Cout == 16) return launch_wgrad_tcn<32, 16, 4, 64>(x, dz, dw, D, H, W, dil, st);
+  if (Cin == 32 && Cout == 32) return launch_wgrad_tcn<32, 32, 2, 64>(x, dz, dw, D, H, W, dil, st);
+  set_error("wgrad_tcn: (Cin, Cout) = (%lld, %lld) unsupported: (16,16), (32,16), (32,32)", (long long)Cin, (long long)Cout);
+  return CVIT_ERR_UNSUPPORTED;
 }

@@ -23,7 +23,9 @@ def test_step(model, batch) -> BatchedModelResult:
     """base_model.py:176-241 for one collated batch (one tomogram): probabilities over the whole volume, loss and
     metrics over the voxels with label > -1."""
     assert batch.aux_data is not None and "data" in batch.aux_data, "Batch aux_data must contain 'data' key for testing."
-    out = model._masked_predict(batch)
+    # the reference's opt-in mito mask (base_model.py:192-199): granule predictions scored inside mitochondria only
+    mito = batch.aux_data.get("labels/mito")
+    out = model._masked_predict(batch, use_mito_mask=mito is not None and len(mito) > 0)
     probs, labels = out["preds_full"], out["labels"]
     losses = {k: float(fn(probs, labels)) for k, fn in model.loss_fns.items()}
     losses["total"] = float(sum(losses.values()))

@@ -97,13 +97,26 @@ class CryoVIT:
     __call__ = forward
 
     # ------------------------------------------------------------------ evaluation (base_model.py:91-164,176-241)
-    def _masked_predict(self, batch) -> dict[str, torch.Tensor]:
+    def _masked_predict(self, batch, use_mito_mask: bool = False) -> dict[str, torch.Tensor]:
+        """Probabilities and the labels they are scored against. With ``use_mito_mask`` (reference
+        base_model.py:91-111: granule experiments, batch size 1) voxels outside ``aux_data["labels/mito"] > 0`` are
+        excluded too: their label becomes -1, which every fused reduction pass already ignores."""
         probs = self(batch)
-        return {"preds_full": probs, "labels": batch.labels.to(probs.device)}
+        labels = batch.labels.to(probs.device)
+        if use_mito_mask:
+            aux = getattr(batch, "aux_data", None)
+            if not aux or "labels/mito" not in aux:
+                raise CryovitB200Error("Batch aux_data must contain 'labels/mito' key for mito masking.")
+            mito = torch.as_tensor(aux["labels/mito"][0]).to(labels.device) > 0
+            labels = torch.where(mito.view_as(labels[0]).expand_as(labels), labels, torch.full_like(labels, -1.0))
+        return {"preds_full": probs, "labels": labels}
 
     def test_step(self, batch) -> dict[str, float]:
-        """Losses and metrics over the voxels with label > -1 (one fused reduction pass per quantity)."""
-        out = self._masked_predict(batch)
+        """Losses and metrics over the voxels with label > -1 (one fused reduction pass per quantity); the reference's
+        opt-in mito mask (base_model.py:192-199) applies when 'labels/mito' travels in aux_data."""
+        aux = getattr(batch, "aux_data", None)
+        use_mito = bool(aux) and "labels/mito" in aux and aux["labels/mito"] is not None and len(aux["labels/mito"]) > 0
+        out = self._masked_predict(batch, use_mito_mask=use_mito)
         res = {}
         for k, fn in self.loss_fns.items():
             res[k] = float(fn(out["preds_full"], out["labels"]))

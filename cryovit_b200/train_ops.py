@@ -149,6 +149,10 @@ def conv_weight_gradient(x, dz, dil: int, pool: dict | None = None) -> torch.Ten
         if Cin == 8 and W % 8 == 0 and os.environ.get("CVIT_WGRAD_TC8", "1") != "0":  # tcgen05, voxels as K (csrc/wgrad_tc.cu)
             _lib.call("cvit_wgrad_tc8_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, dil, _stream())
             return dwn
+        if Cin > 8 and os.environ.get("CVIT_WGRAD_TCN", "1") != "0":
+            _lib.call("cvit_wgrad_tcn_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
+                      dil, _stream())
+            return dwn
         _lib.call("cvit_wgrad_narrow_ndhwc", _chk(x, BF16, "x"), _chk(dz, BF16, "dz"), _chk(dwn, F32, "dw"), D, H, W, Cin, Cout,
                   dil, _stream())
         return dwn

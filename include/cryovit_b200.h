@@ -391,6 +391,11 @@ int cvit_wgrad_narrow_ndhwc(const void* x, const void* dz, float* dw, int64_t D,
  * Cin = Cout = 8; W must be a multiple of 8. */
 int cvit_wgrad_tc8_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil,
                          void* stream);
+/* The 16- / 32-channel layers, (Cin, Cout) in {(16,16), (32,16), (32,32)}, the same way: TMA boxes of (8 channels, one
+ * chunk, 64 voxels) land as the [voxel][8] operand arrays, the column taps are separate (shifted) arrays of x, one MMA
+ * (M 128, N 144) per 16 voxels and 144 accumulator columns. Same contract as cvit_wgrad_narrow_ndhwc, any W. */
+int cvit_wgrad_tcn_ndhwc(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                         int64_t Cout, int64_t dil, void* stream);
 
 /* AdamW step over a flat fp32 parameter vector, torch.optim.AdamW semantics (models/base_model.py:58-63):
  * decoupled weight decay, bias-corrected moments; g is multiplied by grad_scale first. step counts from 1. */

@@ -87,6 +87,12 @@ def test_cryovit_model_surface_and_parity(cuda_lib):
     assert set(res) == {"dice_loss", "dice_metric", "f1_metric"} and all(np.isfinite(v) for v in res.values())
     vol = model.forward_volume(batch.tomo_batch.permute(0, 2, 1, 3, 4).contiguous())
     assert tuple(vol.shape) == (1, 1, 6, 48, 64) and float(vol.abs().max()) <= 5.0
+    # opt-in mito mask (base_model.py:91-111): scoring only inside aux_data["labels/mito"] > 0 == relabelling the rest -1
+    mito = (torch.rand(6, 48, 64, generator=g) < 0.5).to(torch.int8)
+    masked = collate_fn([TomogramData("S", "t", 0, feats, labels, {"labels/mito": mito.numpy()})])
+    relabelled = collate_fn([TomogramData("S", "t", 0, feats, torch.where(mito > 0, labels, torch.full_like(labels, -1)), {})])
+    res_m, res_r = model.test_step(masked), model.test_step(relabelled)
+    assert res_m != res and all(abs(res_m[k] - res_r[k]) < 1e-6 for k in res_m)
 
 
 def test_module_entry_point_end_to_end(cuda_lib, tmp_path):
