@@ -109,18 +109,21 @@ def config_dict(world: int) -> dict:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
-# kernels at the same shapes (profiles/r01_ncu_full_v14_hot_kernels.json); bench.py itself never runs under ncu.
+# kernels at the same shapes (profiles/r02_ncu_full_v1_*_kernels.json); bench.py itself never runs under ncu.
 NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu": "w12_swiglu", "layernorm": "layernorm",
             "proj_scale_residual": "proj_gemm", "w3_scale_residual": "w3_gemm"}
 
 
+NCU_TRAFFIC_FILE = "r02_ncu_traffic.json"  # curated from profiles/r02_ncu_full_v1_*_kernels.json by tools/ncu_traffic_table.py
+
+
 def ncu_traffic(kernel: str) -> float | None:
-    p = ROOT / "profiles" / "r01_ncu_full_v14_hot_kernels.json"
+    p = ROOT / "profiles" / NCU_TRAFFIC_FILE
     if not p.exists() or kernel not in NCU_KEYS:
         return None
     for d in json.loads(p.read_text()):
-        if d["kernel"].startswith(NCU_KEYS[kernel]):
-            return round(d["dram_traffic_GB"] * 1e9)
+        if d["kernel"] == NCU_KEYS[kernel]:
+            return d["dram_bytes"]
     return None
 
 
@@ -138,9 +141,12 @@ class CallProfiler:
     def executed_fraction(name: str, i) -> float:
         """Share of a dilated convolution's algorithmic FLOPs that the kernels execute: depth taps that fall outside
         [0, D) are skipped outright (with dilation 32 of 128 planes that is one tap in six)."""
-        if "conv3d_dilated" not in name and "conv3d_halo" not in name and "conv3d_wpackn" not in name:
+        if "wgrad_mn" in name and i[6] == 27:  # K chunks whose depth tap leaves the volume are skipped
+            D, dil = i[0], i[5]
+        elif "conv3d_dilated" in name or "conv3d_halo" in name or "conv3d_wpackn" in name:
+            D, dil = i[0], i[6]
+        else:
             return 1.0
-        D, dil = i[0], i[6]
         valid = sum((d - dil >= 0) + 1 + (d + dil < D) for d in range(D))
         return valid / (3.0 * D)
 
@@ -164,6 +170,17 @@ class CallProfiler:
         "cvit_conv3d_wpack8_final": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 8,
         "cvit_wgrad_splitk": lambda i: 2 * i[5] * i[0] * i[1] * i[2],           # M, N, k, lda, ldb, T
         "cvit_wgrad_narrow_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[4],
+        "cvit_wgrad_tc8_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 64,                       # D, H, W, dil
+        "cvit_wgrad_tcn_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[4],              # D, H, W, Cin, Cout, dil
+        "cvit_wgrad_mn_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * i[4] * i[6],             # D, H, W, Ca, Cb, dil, ntaps, shift_a
+        # the *_aux entry points (explicit activation mode + second tensor): same integer arguments, one more flag
+        "cvit_linear_bias_cfirst_f16_aux": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_linear_bias_bf16_nvalid_aux": lambda i: 2 * i[2] * i[3] * i[4],
+        "cvit_conv3d_dilated_ndhwc_aux": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_halo_ndhwc_aux": lambda i: CallProfiler._conv(i),
+        "cvit_conv3d_wpackn_ndhwc_aux": lambda i: CallProfiler._conv(i),
+        "cvit_convT_1x2x2_ndhwc_aux": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * 4 * i[4],
+        "cvit_conv3d_wpack8_aux": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 64,
     }
 
     def __init__(self, torch):
@@ -221,7 +238,10 @@ def _roofline_of(rows: list[dict], peaks: dict, peak_src: str, traffic_file: str
     if not cand:
         return None
     top = max(cand, key=lambda r: r["ms"])
-    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    # these kernels are timed one by one (an event pair per launch inside a 5-25 ms pass), not inside a long power-capped
+    # step: the burst figure is their ceiling (MEASURED_PEAKS.json: bf16_tflops), the sustained one is quoted beside it
+    peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained"))
+    sustained = peaks.get("bf16_tflops_sustained", peak)
     traffic, src = None, None
     p = ROOT / "profiles" / traffic_file
     if p.exists():
@@ -230,13 +250,13 @@ def _roofline_of(rows: list[dict], peaks: dict, peak_src: str, traffic_file: str
                 traffic, src = d.get("dram_bytes"), f"profiles/{traffic_file} ({d.get('build', '?')})"
     executed = top.get("tflops_executed", top["tflops"])
     return {"kernel": f"{top['kernel']} {top['dims']}", "what": what, "bound": "tensor", "achieved": top["tflops"], "peak": peak,
-            "unit": "TFLOP/s", "frac": round(top["tflops"] / peak, 4), "frac_burst": round(top["tflops"] / peaks["bf16_tflops"], 4),
-            "achieved_executed": executed, "frac_executed": round(executed / peak, 4),
-            "note": "achieved counts the algorithmic FLOPs (all 27 taps, SURVEY.md a13); *_executed discounts the zero-padded depth "
-                    "taps the kernel skips",
+            "unit": "TFLOP/s", "frac": round(executed / peak, 4), "frac_algorithmic": round(top["tflops"] / peak, 4),
+            "achieved_executed": executed, "frac_vs_sustained": round(executed / sustained, 4), "peak_sustained": sustained,
+            "note": "achieved counts the algorithmic FLOPs (all 27 taps, SURVEY.md a13); achieved_executed and frac discount the "
+                    "zero-padded depth taps the kernel skips",
             "avg_launch_ms": round(top["ms"] / max(top["launches"], 1), 4), "flop_per_launch": top["flop"] // max(top["launches"], 1),
             "share_of_pass": round(top["ms"] / sum(r["ms"] for r in rows), 4), "traffic": traffic, "traffic_source": src,
-            "peak_source": f"{peak_src} (sustained bf16)"}
+            "peak_source": f"{peak_src} (burst bf16: kernel timed alone)"}
 
 
 def head_cpu_baseline(torch) -> dict:
@@ -914,11 +934,22 @@ def run_b200(args) -> None:
                 "frac": round(tf / peak, 4), "peak_burst": peaks.get("bf16_tflops"),
                 "frac_burst": round(tf / peaks["bf16_tflops"], 4) if peaks.get("bf16_tflops") else None,
                 "traffic": ncu_traffic(top),
-                "traffic_source": "profiles/r01_ncu_full_v14_hot_kernels.json (ncu --set full, one launch, same shapes)",
+                "traffic_source": f"profiles/{NCU_TRAFFIC_FILE} (ncu --set full of build r02 v1, one launch, same shapes; the GEMM kernels "
+                                  "are unchanged since)",
                 "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
                 "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
     kernels = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
                    "share_of_step": round(shares[k] * (2 if k == "layernorm" else 1), 4)} for k, v in ks.items()}
+    if "layernorm" in kernels and peaks.get("hbm_gbs"):
+        # LayerNorm reads the fp32 residual stream once and writes the 16-bit operand: 6 bytes per element, nothing else
+        ln_bytes = BATCH * T * C * 6
+        gbps = ln_bytes / ks["layernorm"]["ms"] / 1e6
+        kernels["layernorm"]["roofline"] = {"bound": "hbm", "achieved": round(gbps, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                            "frac": round(gbps / peaks["hbm_gbs"], 4), "algorithmic_bytes": ln_bytes,
+                                            "traffic": ncu_traffic("layernorm")}
+    for k in kernels:  # DRAM bytes per launch of every block kernel from the committed ncu capture
+        if k != "layernorm" and ncu_traffic(k) is not None:
+            kernels[k]["traffic"] = ncu_traffic(k)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "slices/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 3), "higher_is_better": True, "scaling": "weak",

@@ -66,6 +66,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_gelu_fwd_bf16": [P, P, I64, P],
     "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
     "cvit_gelu_bwd_colsum_bf16": [P, P, P, P, I64, I64, P],
+    "cvit_gelu_bwd_colsum_unshuffle_bf16": [P, P, P, P, I64, I64, I64, I64, P],
     "cvit_dice_bwd": [P, P, P, P, F32, P, I64, P],
     "cvit_colsum_bf16": [P, P, I64, I64, P],
     "cvit_groupnorm_bwd_ndhwc_bf16": [P, P, P, P, P, P, P, I64, I64, I64, F32, P],

@@ -50,9 +50,12 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const uint4* __restrict__
 // The same with the bias gradient db[c] += sum over rows of dz[r, c] accumulated on the way (the column sums of dz that
 // every convolution's bias gradient is): thread t owns the 8-channel vector t % (C/8) and strides over the rows of its
 // block's range, so the partial sums stay in registers; one shared-memory and one global atomic pass per block.
+// W2 > 0: the rows are the voxels of a [D, H2, W2, C] volume (H2, W2 even) and dz is written PIXEL-UNSHUFFLED, as
+// [D, H2/2, W2/2, (i, j, C)] with (i, j) the sub-pixel -- the row layout the transposed convolution's input-gradient and
+// weight-gradient GEMMs read -- instead of through a separate permutation pass over the largest gradient volumes.
 __global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
                                                                uint4* __restrict__ dz, float* __restrict__ db, int64_t R, int C,
-                                                               int64_t rows_per_block) {
+                                                               int64_t rows_per_block, int W2) {
   extern __shared__ float s_db[];  // [C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
   __syncthreads();
@@ -77,7 +80,13 @@ __global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const uint4* __res
         acc[2 * k] += dr.x;
         acc[2 * k + 1] += dr.y;
       }
-      dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      int64_t io = i;
+      if (W2 > 0) {
+        const int64_t dh2 = r / W2;
+        const int wx = (int)(r - dh2 * W2);
+        io = (((dh2 >> 1) * (W2 >> 1) + (wx >> 1)) * 4 + ((dh2 & 1) * 2 + (wx & 1))) * nvec + vec;
+      }
+      dz[io] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) atomicAdd(&s_db[vec * 8 + k], acc[k]);
@@ -280,15 +289,28 @@ int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void*
 }
 
 // dz = da * gelu'(z) over a bf16 [R, C] matrix and db[c] += sum_r dz[r, c] (fp32 [C], caller zeroes); C % 8 == 0, C <= 2048.
-int cvit_gelu_bwd_colsum_bf16(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, void* stream) {
+static int gelu_bwd_colsum_launch(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, int W2, void* stream) {
   if (!da || !z || !dz || !db || R <= 0 || C <= 0 || (C % 8) || C > 2048) { set_error("gelu_bwd_colsum: bad arguments"); return CVIT_ERR_INVALID; }
   int64_t blocks = (int64_t)num_sms() * 8;
   int64_t rpb = (R + blocks - 1) / blocks;
   if (rpb < 1) rpb = 1;
   blocks = (R + rpb - 1) / rpb;
   gelu_bwd_colsum_kernel<<<(unsigned)blocks, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-      static_cast<const uint4*>(da), static_cast<const uint4*>(z), static_cast<uint4*>(dz), db, R, (int)C, rpb);
+      static_cast<const uint4*>(da), static_cast<const uint4*>(z), static_cast<uint4*>(dz), db, R, (int)C, rpb, W2);
   return check_launch("gelu_bwd_colsum_kernel");
+}
+
+int cvit_gelu_bwd_colsum_bf16(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, void* stream) {
+  return gelu_bwd_colsum_launch(da, z, dz, db, R, C, 0, stream);
+}
+
+// The same over a [D, H2, W2, C] volume with dz stored pixel-unshuffled, [D, H2/2, W2/2, 4 C] (sub-pixel (i, j) major): the
+// gradient of a transposed convolution's pre-activation in the row layout its GEMMs read (replaces the pass of
+// cvit_pixel_unshuffle_1x2x2_bf16 over the step's largest gradient volumes).
+int cvit_gelu_bwd_colsum_unshuffle_bf16(const void* da, const void* z, void* dzun, float* db, int64_t D, int64_t H2, int64_t W2,
+                                        int64_t C, void* stream) {
+  if (D <= 0 || H2 <= 0 || W2 <= 0 || (H2 & 1) || (W2 & 1)) { set_error("gelu_bwd_colsum_unshuffle: H2 and W2 must be even"); return CVIT_ERR_INVALID; }
+  return gelu_bwd_colsum_launch(da, z, dzun, db, D * H2 * W2, C, (int)W2, stream);
 }
 
 int cvit_dice_bwd(const float* logits, const float* probs, const float* labels, const double* stats8, float scale,

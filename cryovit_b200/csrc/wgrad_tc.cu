@@ -48,7 +48,9 @@ constexpr int WT_N = 80, WT_TMEM_COLS = 128;
 constexpr uint32_t WT_TX_BYTES = WT_R * WT_XARR + (WT_R + 2) * 3 * WT_ZARR;
 
 struct WtArgs {
-  float* dw;  // [27][8][8] fp32, accumulated into (tap = (kd*3+kh)*3+kw, then co, then ci)
+  float* dw;  // [27][Cout][Cin] fp32, accumulated into (tap = (kd*3+kh)*3+kw, then co, then ci)
+  const __nv_bfloat16* x;   // [D, H, W, Cin]  (read directly by the cp.async loaders of the 16 / 32-channel kernel)
+  const __nv_bfloat16* dz;  // [D, H, W, Cout]
   int D, H, W, dil;
 };
 
@@ -177,6 +179,19 @@ wgrad_tc8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // m = (kw * NCX + j) * 8 + t (array (kw, j) = chunk j of the row shifted by kw - 1 voxels: with more than one chunk per
 // voxel the column taps are separate arrays, equally spaced), the columns n = ((yr * 3 + kd) * NCZ + jz) * 8 + t'.
 // One MMA (M 128, N 144) per 16 voxels and 144 columns: 96 x 144 useful of 128 x 144 for 32 -> 16.
+// Loader of the chunk arrays: TMA boxes (default) or, with -DWTN_CPASYNC=1, four warps of 16-byte cp.async (A/B arm, measured
+// SLOWER: 32 -> 16 1.16 ms against 0.70 ms, 16 -> 16 0.95 against 0.52 -- an LDGSTS warp instruction with 32 scattered 16-byte
+// destinations costs ~58 cycles on this chip, 9 B/clk/SM against TMA's 14; profiles/r02_train_notes.md).
+#ifndef WTN_CPASYNC
+#define WTN_CPASYNC 0
+#endif
+__device__ __forceinline__ void wt_cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void wt_cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 template <int CIN, int COUT, int R, int KSEG>
 struct WtnCfg {
   static constexpr int NCX = CIN / 8, NCZ = COUT / 8;
@@ -214,7 +229,7 @@ wgrad_tcn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmZ);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, WTN_CPASYNC ? 4 : 1);  // one arrival per loader warp / the TMA transaction count
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
@@ -227,7 +242,9 @@ wgrad_tcn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp == 0) {
+#if !WTN_CPASYNC
     // ------------------------------------------------------------------ TMA producer: the whole warp issues boxes
+    // (A/B arm: boxes with a 16-byte inner extent move ~14 B/clk/SM, which bounds the kernel: 0.70 ms for 32 -> 16)
     uint32_t it = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
       const int seg = blk % segs, hb = (blk / segs) % hblocks, z0 = blk / (segs * hblocks);
@@ -248,6 +265,7 @@ wgrad_tcn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_load_5d(sZ + i * S, &tmZ, bar, 0, jz, x0, yb - 1 + rr, z0 - (kd - 1) * args.dil);
       }
     }
+#endif
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::MM, Cfg::NH) | (1u << 15) | (1u << 16);  // A and B MN-major
@@ -276,6 +294,66 @@ wgrad_tcn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (elect_one_sync()) umma_commit(bar_done);
     __syncwarp();
   } else {
+#if WTN_CPASYNC
+    // ------------------------------------------------------------------ loaders (warps 2-5): global -> chunk arrays, cp.async
+    // A row segment is contiguous in global memory: consecutive threads copy consecutive 16-byte chunks (chunk c = voxel
+    // c / NC, channel block c % NC) to array (c % NC) -- and, for x, to the three column-tap arrays, shifted by one voxel
+    // each (the second and third read of a chunk hit L1). Zero fill is the padding. A thread signals stage n - 1 after
+    // issuing stage n (cp.async.wait_group 1, proxy fence, one arrival per warp): two stages of loads in flight.
+    {
+      const int t = threadIdx.x - 64;
+      uint32_t it = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+        const int seg = blk % segs, hb = (blk / segs) % hblocks, z0 = blk / (segs * hblocks);
+        const int x0 = seg * KSEG, yb = hb * R;
+        const uint32_t s = it % STAGES;
+        const uint32_t sX = smem_base + s * Cfg::STAGE, sZ = sX + Cfg::XA * S;
+        mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1u);
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+          const int y = yb + r;
+          const bool row_ok = y < args.H;
+          const __nv_bfloat16* src_row = args.x + (((int64_t)z0 * args.H + (row_ok ? y : 0)) * args.W) * CIN;
+          for (int c = t; c < (KSEG + 2) * NCX; c += 128) {
+            const int v = c / NCX, j = c % NCX, xg = x0 - 1 + v;
+            const bool ok = row_ok && xg >= 0 && xg < args.W;
+            const __nv_bfloat16* src = ok ? src_row + (int64_t)xg * CIN + j * 8 : args.x;
+            const uint32_t dst = sX + (r * 3 * NCX + j) * S + v * 16;  // array (r, kw = 0, j), voxel v
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int k = v - kw;
+              if (k >= 0 && k < KSEG) wt_cp_async16_ca(dst + kw * (NCX * S - 16), src, ok ? 16u : 0u);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int a = 0; a < (R + 2) * 3; ++a) {
+          const int rr = a / 3, kd = a - 3 * rr;
+          const int y = yb - 1 + rr, z = z0 - (kd - 1) * args.dil;
+          const bool row_ok = y >= 0 && y < args.H && z >= 0 && z < args.D;
+          const __nv_bfloat16* src_row = args.dz + (((int64_t)(row_ok ? z : 0) * args.H + (row_ok ? y : 0)) * args.W) * COUT;
+          for (int c = t; c < KSEG * NCZ; c += 128) {
+            const int v = c / NCZ, jz = c % NCZ, xg = x0 + v;
+            const bool ok = row_ok && xg < args.W;
+            wt_cp_async16_cg(sZ + (a * NCZ + jz) * S + v * 16, ok ? src_row + (int64_t)xg * COUT + jz * 8 : args.dz, ok ? 16u : 0u);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it > 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * ((it - 1) % STAGES));
+        }
+      }
+      if (it > 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * ((it - 1) % STAGES));
+      }
+    }
+#endif
     // ------------------------------------------------------------------ read-out: TMEM lane = (kw, j, t)
     const int q = warp & 3;
     mbar_wait(bar_done, 0);
@@ -342,6 +420,8 @@ static int launch_wgrad_tcn(const void* x, const void* dz, float* dw, int64_t D,
   if (grid > blocks) grid = (int)blocks;
   WtArgs a;
   a.dw = dw;
+  a.x = static_cast<const __nv_bfloat16*>(x);
+  a.dz = static_cast<const __nv_bfloat16*>(dz);
   a.D = (int)D;
   a.H = (int)H;
   a.W = (int)W;
@@ -393,6 +473,8 @@ extern "C" int cvit_wgrad_tc8_ndhwc(const void* x, const void* dz, float* dw, in
   if (grid > blocks) grid = (int)blocks;
   WtArgs a;
   a.dw = dw;
+  a.x = static_cast<const __nv_bfloat16*>(x);
+  a.dz = static_cast<const __nv_bfloat16*>(dz);
   a.D = (int)D;
   a.H = (int)H;
   a.W = (int)W;

@@ -394,15 +394,17 @@ class CryoVITHeadTrainerB200:
             pre = f"layers.{bi + 2}.layers."
             blk_in, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W = saved[bi]
             # transposed convolution: dcur is d(at) [D, 2H, 2W, c3]
+            dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
             if dcur_is_dz:  # the producer's epilogue already applied gelu'(zt)
-                dzt = dcur
-                self._bias_grad(dzt, pre + "5.bias")
+                self._bias_grad(dcur, pre + "5.bias")
+                T.pixel_unshuffle(dcur, dzun)
                 dcur_is_dz = False
             else:
-                dzt = self._buf(f"dzt{bi}", (D, 2 * H, 2 * W, c3))
-                self._gelu_bwd_bias(dcur, zt, dzt, pre + "5.bias")  # summed over voxels AND sub-pixels: dzt is [.., c3]
-            dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
-            T.pixel_unshuffle(dzt, dzun)
+                # d(zt) = d(at) * gelu'(zt), written straight in the sub-pixel-major row layout of the GEMMs below; the bias
+                # gradient (summed over voxels AND sub-pixels) from the same pass
+                db = torch.zeros(c3, device=dev, dtype=F32)
+                T.gelu_bwd_unshuffle(dcur, zt, dzun, db)
+                g[pre + "5.bias"].copy_(db)
             rows = D * H * W
             dwt = self._wgrad_rows(ab.view(rows, c2), dzun.view(rows, 4 * c3))          # [(ij, c3), c2]
             g[pre + "5.weight"].copy_(dwt.view(2, 2, c3, c2).permute(3, 2, 0, 1)[:, :, None])

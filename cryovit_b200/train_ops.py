@@ -48,6 +48,16 @@ def gelu_fwd(z, a) -> None:
     _lib.call("cvit_gelu_fwd_bf16", _chk(z, BF16, "z"), _chk(a, BF16, "a"), z.numel(), _stream())
 
 
+def gelu_bwd_unshuffle(da, z, dzun, db) -> None:
+    """dz = da * gelu'(z) over a [D, H2, W2, C] volume, stored pixel-unshuffled into dzun [D, H2/2, W2/2, 4C]
+    ((i, j, c) channel order), db += column sums of dz."""
+    D, H2, W2, C = z.shape
+    if tuple(dzun.shape) != (D, H2 // 2, W2 // 2, 4 * C):
+        raise _lib.CryovitB200Error(f"gelu_bwd_unshuffle: dzun {tuple(dzun.shape)} does not match z {tuple(z.shape)}")
+    _lib.call("cvit_gelu_bwd_colsum_unshuffle_bf16", _chk(da, BF16, "da"), _chk(z, BF16, "z"), _chk(dzun, BF16, "dzun"),
+              _chk(db, F32, "db"), D, H2, W2, C, _stream())
+
+
 def gelu_bwd(da, z, dz, db=None) -> None:
     """dz = da * gelu'(z); with ``db`` (fp32 [C], zeroed by the caller) also db += column sums of dz over the last axis."""
     if db is None:

@@ -328,6 +328,11 @@ int cvit_gelu_bwd_bf16(const void* da, const void* z, void* dz, int64_t n, void*
 /* The same over a bf16 [R, C] matrix with the bias gradient on the way: db[c] += sum_r dz[r, c] (fp32 [C], caller zeroes;
  * C % 8 == 0, C <= 2048) -- what autograd's conv bias gradient reduces, without a second pass over dz. */
 int cvit_gelu_bwd_colsum_bf16(const void* da, const void* z, void* dz, float* db, int64_t R, int64_t C, void* stream);
+/* The same over a bf16 [D, H2, W2, C] volume (H2, W2 even) with dz stored PIXEL-UNSHUFFLED, [D, H2/2, W2/2, (i, j, C)]:
+ * the row layout the transposed convolution's input- and weight-gradient GEMMs read (saves the separate
+ * cvit_pixel_unshuffle_1x2x2_bf16 pass over the step's largest gradient volumes). */
+int cvit_gelu_bwd_colsum_unshuffle_bf16(const void* da, const void* z, void* dzun, float* db, int64_t D, int64_t H2, int64_t W2,
+                                        int64_t C, void* stream);
 
 /* Gradient of DiceLoss (models/losses.py:17-32) w.r.t. the raw logits, through sigmoid and clip(-5, 5)
  * (models/cryovit.py:39,49), masked to label > -1 (models/base_model.py:91-112). stats8 = the device-resident sums

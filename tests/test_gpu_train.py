@@ -37,6 +37,21 @@ def test_gelu_fwd_bwd(cuda_lib):
         assert (db - ref).abs().max() <= 1e-3 * ref.abs().max() + 1e-3, C
 
 
+def test_gelu_bwd_unshuffle(cuda_lib):
+    """The fused pass == gelu_bwd_colsum followed by pixel_unshuffle, bit for bit."""
+    from cryovit_b200 import train_ops as T
+    for D, H2, W2, C in [(3, 8, 12, 8), (2, 6, 10, 32), (1, 4, 4, 128)]:
+        z, da = (_rand(D, H2, W2, C, scale=2.0, seed=1)).bfloat16(), _rand(D, H2, W2, C, seed=2).bfloat16()
+        dz, db = torch.empty_like(z), torch.zeros(C, device=DEV)
+        T.gelu_bwd(da, z, dz, db)
+        ref = torch.empty(D, H2 // 2, W2 // 2, 4 * C, device=DEV, dtype=torch.bfloat16)
+        T.pixel_unshuffle(dz, ref)
+        got, db2 = torch.full_like(ref, float("nan")), torch.zeros(C, device=DEV)
+        T.gelu_bwd_unshuffle(da, z, got, db2)
+        assert torch.equal(got, ref)
+        assert (db - db2).abs().max() <= 1e-3 * db.abs().max() + 1e-3
+
+
 @pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(6, 12, 20, 64, 192, 2), (5, 16, 8, 32, 32, 1), (4, 9, 11, 16, 16, 1),
                                                  (3, 16, 16, 8, 8, 1), (9, 8, 8, 192, 64, 4),
                                                  # Cin a multiple of 128, Cout = 192: operands swapped (dW^T, negated shifts), one exact 192-wide N tile
