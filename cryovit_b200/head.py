@@ -100,6 +100,25 @@ def wpack_weight_image(w: torch.Tensor, P: int) -> torch.Tensor:
     return img.reshape(3, (P + 2) // 2, 2, 3, P, cout, 8).reshape(-1)
 
 
+def rows8_weight_image(w: torch.Tensor) -> torch.Tensor:
+    """Conv3d weight [8, 8, 3, 3, 3] -> the shared-memory image of csrc/conv_rows8.cu (fp32, flat):
+    [v = input plane mod 3][K step][chunk][96 rows][8 ci]. Row n = (yr * 3 + p) * 8 + co holds
+    w[co, ci, kd, kh = 2 - yr, kw] with kw = 2 * step + chunk (the fourth tap is zero) and kd = (v + 1 - p) mod 3: an input
+    row (z', y') feeds output row y' - 1 + yr of the output plane whose slot is p = (z' - (kd - 1)) mod 3. Rows 72..95 are zero."""
+    cout, cin = w.shape[:2]
+    assert cout <= 8 and cin == 8
+    img = torch.zeros(3, 2, 2, 96, 8, device=w.device)
+    wf = w.float()
+    for v in range(3):
+        for yr in range(3):
+            for p_ in range(3):
+                kd, kh = (v + 1 - p_) % 3, 2 - yr
+                n0 = (yr * 3 + p_) * 8
+                for kw in range(3):
+                    img[v, kw // 2, kw % 2, n0:n0 + cout] = wf[:, :, kd, kh, kw]
+    return img.reshape(-1)
+
+
 class CryoVITHeadB200:
     def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool | None = None, wpack_narrow: bool | None = None):
         import os
@@ -109,6 +128,7 @@ class CryoVITHeadB200:
         self.fuse_groupnorm = os.environ.get("CVIT_HEAD_FUSE_GN", "1") != "0" if fuse_groupnorm is None else fuse_groupnorm
         # False: the 16- / 32-channel layers run on the per-tap halo kernel
         self.wpack_narrow = os.environ.get("CVIT_HEAD_WPACKN", "1") != "0" if wpack_narrow is None else wpack_narrow
+        self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # the two 8-channel output convolutions on conv_rows8.cu
         self.device: torch.device | None = None
         self._sd_cpu: dict | None = None
         self._w: dict = {}
@@ -196,6 +216,9 @@ class CryoVITHeadB200:
         # W-packed tensor-core versions of both output convolutions (planes whose width is a multiple of 16)
         w["o1_wp"], w["o1_wp_b"] = bf(wpack_weight_image(sd["output_layer.0.weight"], 8)), f32(sd["output_layer.0.bias"].repeat(8))
         w["o2_wp"], w["o2_wp_b"] = bf(wpack_weight_image(sd["output_layer.2.weight"], 16)), f32(sd["output_layer.2.bias"].repeat(16))
+        # one voxel per MMA row, partial sums meeting in tensor memory (csrc/conv_rows8.cu; widths that are a multiple of 8)
+        w["o1_r8"], w["o1_r8_b"] = bf(rows8_weight_image(sd["output_layer.0.weight"])), f32(sd["output_layer.0.bias"])
+        w["o2_r8"], w["o2_r8_b"] = bf(rows8_weight_image(sd["output_layer.2.weight"])), f32(sd["output_layer.2.bias"])
         self._w = w
 
     def _buf(self, name: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
@@ -299,7 +322,10 @@ class CryoVITHeadB200:
         scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
         logits = torch.empty(D, H, W, device=self.device) if want_logits else None
         probs = torch.empty(D, H, W, device=self.device) if want_probs else None
-        if W % 16 == 0:  # always true downstream of the ViT (W = 16 w); both on tensor cores, voxels packed into the MMA N
+        if W % 8 == 0 and self.rows8:  # always true downstream of the ViT (W = 16 w): one voxel per MMA row (conv_rows8.cu)
+            ops.conv3d_rows8(cur, w_["o1_r8"], w_["o1_r8_b"], scratch)                    # output_layer.0 + GELU
+            ops.conv3d_rows8_final(scratch, w_["o2_r8"], w_["o2_r8_b"], logits, probs)    # output_layer.2 + clip (+ sigmoid)
+        elif W % 16 == 0:  # both on tensor cores, voxels packed into the MMA N (conv_wpack.cu; A/B arm: CVIT_HEAD_ROWS8=0)
             ops.conv3d_wpack8_gelu(cur, w_["o1_wp"], w_["o1_wp_b"], scratch)              # output_layer.0 + GELU
             ops.conv3d_wpack8_final(scratch, w_["o2_wp"], w_["o2_wp_b"], logits, probs)   # output_layer.2 + clip (+ sigmoid)
         else:

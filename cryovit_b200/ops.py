@@ -286,6 +286,26 @@ def conv3d_wpack8_gelu(x, w_img, bias_n, out, act=True, aux=None) -> None:
               _chk(out, BF16, "out"), D, H, W, act, auxp, _stream())
 
 
+def conv3d_rows8(x, w_img, bias8, out, act=True, aux=None) -> None:
+    """output_layer.0 (8 -> 8, k3, dilation 1) + bias (+ GELU), one voxel per MMA row (csrc/conv_rows8.cu); W % 8 == 0."""
+    D, H, W, Cin = x.shape
+    if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_rows8_weight_bytes():
+        raise _lib.CryovitB200Error("conv3d_rows8: needs 8 input channels and the rows8 weight image")
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_rows8", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias8, F32, "bias8"),
+              _chk(out, BF16, "out"), D, H, W, act, auxp, _stream())
+
+
+def conv3d_rows8_final(x, w_img, bias1, logits=None, probs=None) -> None:
+    """output_layer.2 (8 -> 1, k3) + bias + clip(-5, 5) (+ sigmoid), one voxel per MMA row (csrc/conv_rows8.cu); W % 8 == 0."""
+    D, H, W, Cin = x.shape
+    if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_rows8_weight_bytes():
+        raise _lib.CryovitB200Error("conv3d_rows8_final: needs 8 input channels and the rows8 weight image")
+    _lib.call("cvit_conv3d_rows8_final", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias1, F32, "bias1"),
+              _chk(logits, F32, "logits") if logits is not None else None, _chk(probs, F32, "probs") if probs is not None else None,
+              D, H, W, _stream())
+
+
 def conv3d_wpack8_final(x, w_img, bias_n, logits=None, probs=None) -> None:
     """output_layer.2 (8 -> 1, k3) + bias + clip(-5, 5) (+ sigmoid) with 16 output voxels of a row per MMA row."""
     D, H, W, Cin = x.shape

@@ -23,7 +23,7 @@ import torch
 from . import ops
 from . import train_ops as T
 from ._lib import CryovitB200Error
-from .head import BLOCKS, state_dict_keys, wpack_weight_image, wpackn_weight_image
+from .head import BLOCKS, rows8_weight_image, state_dict_keys, wpack_weight_image, wpackn_weight_image
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -76,6 +76,17 @@ class _Conv:
     def run(self, tag, x, wfn, bias, out, cin, cout, dil, act=0, aux=None):
         """wfn: fp32 parameter -> the [cout, cin, 3,3,3] weight of THIS convolution (identity, or flip + transpose).
         act / aux: the fused element-wise pass of the epilogue (2: out = z, aux = gelu(z); 3: out = y * gelu'(aux))."""
+        if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 8 == 0 and act != 3 and self.tr.rows8:
+            # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): one voxel per MMA row,
+            # partial sums meeting in tensor memory (csrc/conv_rows8.cu)
+            b = bias.contiguous() if bias is not None else torch.zeros(8, device=x.device, dtype=F32)
+            op = self.tr._pk(f"{self.key}/{tag}/rows8", self.key, lambda w: rows8_weight_image(wfn(w)))
+            if act == 2 and not self.tr.fuse_store_bound:
+                ops.conv3d_rows8(x, op, b, out, act=0)
+                T.gelu_fwd(out, aux)
+            else:
+                ops.conv3d_rows8(x, op, b, out, act=act, aux=aux)
+            return
         if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 16 == 0:
             # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): W-packed kernel
             b = bias.repeat(8).contiguous() if bias is not None else torch.zeros(64, device=x.device, dtype=F32)
@@ -155,6 +166,7 @@ class CryoVITHeadTrainerB200:
         # and gelu' in the input-gradient epilogues: both measured slower than the separate passes, off by default
         self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "0") != "0"
         self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
+        self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # 8-channel full-resolution convolutions on conv_rows8.cu
         if state_dict is None:
             from .host.models import default_state_dict
 
@@ -353,7 +365,10 @@ class CryoVITHeadTrainerB200:
             co.forward(cur, p["output_layer.0.bias"], z1)
             T.gelu_fwd(z1, a1)
         logits, probs = self._buf("logits", (D, H, W), F32), self._buf("probs", (D, H, W), F32)
-        if W % 16 == 0:
+        if W % 8 == 0 and self.rows8:
+            ops.conv3d_rows8_final(a1, self._pk("out2/f/rows8", "output_layer.2.weight", rows8_weight_image),
+                                   p["output_layer.2.bias"], logits, probs)
+        elif W % 16 == 0:
             ops.conv3d_wpack8_final(a1, self._pk("out2/f/wpack", "output_layer.2.weight", lambda w_: wpack_weight_image(w_, 16)),
                                     p["output_layer.2.bias"].repeat(16).contiguous(), logits, probs)
         else:

@@ -253,6 +253,20 @@ int cvit_conv3d_wpack8_gelu(const void* x, const void* w_img, const float* bias_
 int cvit_conv3d_wpack8_final(const void* x, const void* w_img, const float* bias_n, float* logits, float* probs,
                              int64_t D, int64_t H, int64_t W, void* stream);
 
+/* output_layer.0 (8 -> 8 channels, 3x3x3, dilation 1; models/cryovit.py:30-32) with ONE VOXEL PER MMA ROW and the channels-last
+ * volume as the operand as it lies (csrc/conv_rows8.cu): a row of voxels at its 16-byte pitch is a K-major operand whose K
+ * chunks -- the three column taps -- are the same bytes one voxel further on; the nine (plane, row) partial sums of an
+ * output voxel meet in sliding windows of tensor memory. x, out (and aux) bf16 [D,H,W,8], W a multiple of 8; bias fp32 [8];
+ * w_img bf16, cvit_conv3d_rows8_weight_bytes() bytes (cryovit_b200.head.rows8_weight_image);
+ * act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it. */
+int64_t cvit_conv3d_rows8_weight_bytes(void);
+int cvit_conv3d_rows8(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H, int64_t W,
+                      int act, void* aux, void* stream);
+/* output_layer.2 (8 -> 1) the same way (w_img: the image of the [1,8,3,3,3] weight, bias fp32 [1]) + clip(-5, 5) -> logits
+ * fp32 [D,H,W] and/or their sigmoid -> probs (cryovit.py:39,49); either pointer may be null. */
+int cvit_conv3d_rows8_final(const void* x, const void* w_img, const float* bias, float* logits, float* probs, int64_t D,
+                            int64_t H, int64_t W, void* stream);
+
 /* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
  * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;
  * bias4 fp32 [4 * Cout] (the bias repeated per sub-pixel); out bf16 [D, 2H, 2W, Cout]. */

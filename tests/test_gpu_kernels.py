@@ -578,3 +578,39 @@ def test_conv3d_wpack_rejects_unpackable_width(cuda_lib):
     w = wpack_weight_image(torch.zeros(8, 8, 3, 3, 3), 8).to(DEV).bfloat16()
     with pytest.raises(CryovitB200Error, match="multiple of 8"):
         ops.conv3d_wpack8_gelu(x, w, torch.zeros(64, device=DEV), torch.empty_like(x))
+
+
+@pytest.mark.parametrize("D,H,W", [(3, 8, 128), (5, 20, 136), (20, 17, 264), (35, 9, 8), (2, 3, 520)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_conv3d_rows8(cuda_lib, D, H, W, act):
+    """8 -> 8 convolution with one voxel per MMA row (sliding accumulator windows in tensor memory) against F.conv3d:
+    ragged row tiles / segments / plane chunks, all three activation modes."""
+    from cryovit_b200 import ops
+    from cryovit_b200.head import rows8_weight_image
+    x = _rand(D, H, W, 8, seed=1).bfloat16()
+    w = (_rand(8, 8, 3, 3, 3, seed=2) * (27 * 8) ** -0.5).bfloat16()
+    b = _rand(8, seed=3)
+    out = torch.full((D, H, W, 8), float("nan"), device=DEV, dtype=torch.bfloat16)
+    aux = torch.full_like(out, float("nan")) if act == 2 else None
+    ops.conv3d_rows8(x, rows8_weight_image(w).bfloat16(), b, out, act=act, aux=aux)
+    z = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding=1)[0].permute(1, 2, 3, 0)
+    if act == 1:
+        _close(out, F.gelu(z), atol=2e-2, rtol=2e-2, what="rows8 gelu")
+    else:
+        _close(out, z, atol=2e-2, rtol=2e-2, what="rows8 pre-activation")
+        if act == 2:
+            _close(aux, F.gelu(z), atol=2e-2, rtol=2e-2, what="rows8 aux")
+
+
+@pytest.mark.parametrize("D,H,W", [(3, 8, 128), (5, 20, 136), (18, 17, 264)])
+def test_conv3d_rows8_final(cuda_lib, D, H, W):
+    from cryovit_b200 import ops
+    from cryovit_b200.head import rows8_weight_image
+    x = _rand(D, H, W, 8, seed=1).bfloat16()
+    w = (_rand(1, 8, 3, 3, 3, seed=2) * 0.3).bfloat16()
+    b = _rand(1, seed=3)
+    logits, probs = torch.full((D, H, W), float("nan"), device=DEV), torch.full((D, H, W), float("nan"), device=DEV)
+    ops.conv3d_rows8_final(x, rows8_weight_image(w).bfloat16(), b, logits, probs)
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding=1)[0, 0].clamp(-5, 5)
+    _close(logits, ref, atol=2e-2, rtol=2e-2, what="rows8 final logits")
+    _close(probs, torch.sigmoid(ref), atol=5e-3, rtol=5e-3, what="rows8 final probs")
