@@ -65,6 +65,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_conv3d_wpack8_aux": [P, P, P, P, I64, I64, I64, I32, P, P],
     "cvit_conv3d_rows8": [P, P, P, P, I64, I64, I64, I32, P, P],
     "cvit_conv3d_rows8_final": [P, P, P, P, P, I64, I64, I64, P],
+    "cvit_conv3d_rows_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I32, P, P],
     "cvit_gelu_fwd_bf16": [P, P, I64, P],
     "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
     "cvit_gelu_bwd_colsum_bf16": [P, P, P, P, I64, I64, P],
@@ -122,6 +123,8 @@ def load() -> ctypes.CDLL:
     lib.cvit_conv3d_wpack_weight_bytes.argtypes = [c_int64, c_int64]
     lib.cvit_conv3d_rows8_weight_bytes.restype = c_int64
     lib.cvit_conv3d_rows8_weight_bytes.argtypes = []
+    lib.cvit_conv3d_rows_weight_bytes.restype = c_int64
+    lib.cvit_conv3d_rows_weight_bytes.argtypes = [c_int64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = c_int

@@ -97,11 +97,17 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restri
 //                channel = c2*16 + k*8 + e
 //   LAYOUT_WPACKN: conv3d_wpackn (conv_wpackn.cu): [kd*3+kh][K step][2 chunks][n = j_out * coutp + co][8], chunk k = 2 step + c
 //                = (window voxel j_in, c_hi) = divmod(k, cin / 8), channel = c_hi*8 + e, tap kw = j_in - j_out; `p` voxels per row
-enum { LAYOUT_TAPS = 0, LAYOUT_HALO = 1, LAYOUT_WPACKN = 2 };
+//   LAYOUT_ROWS: conv3d_rows (conv_rows.cu): [pass h = co / 16][rotation v][chunk j = ci / 8][K step][2 chunks c][row 144][8],
+//                row = ((yr * 3 + slot) * 16 + co % 16), kw = 2 step + c (the fourth tap is zero), kh = 2 - yr,
+//                kd = (v + 1 - slot) mod 3, channel = j*8 + e; `p` = cin / 8
+enum { LAYOUT_TAPS = 0, LAYOUT_HALO = 1, LAYOUT_WPACKN = 2, LAYOUT_ROWS = 3 };
 
 template <int LAYOUT>
 __device__ __forceinline__ void decode(int64_t idx, int cin, int coutp, int& tap, int& co, int& ci, int p = 0) {
-  if (LAYOUT == LAYOUT_WPACKN) {
+  if (LAYOUT == LAYOUT_ROWS) {
+    ci = (int)((idx / (8 * 144 * 4)) % (cin / 8)) * 8 + (int)(idx & 7);
+    tap = co = 0;
+  } else if (LAYOUT == LAYOUT_WPACKN) {
     const int ch = cin / 8, ksteps = (p + 2) * ch / 2, n_cols = p * coutp;
     const int e = (int)(idx & 7);
     int64_t r = idx >> 3;
@@ -163,6 +169,11 @@ __global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ 
       int64_t idx;
       if (LAYOUT == LAYOUT_TAPS) {
         idx = ((int64_t)tap * coutp + co) * cin + ci;
+      } else if (LAYOUT == LAYOUT_ROWS) {
+        // the tap's weight as it sits in rotation v = 0: slot = (1 - kd) mod 3
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3, slot = (4 - kd) % 3, yr = 2 - kh;
+        const int row = (yr * 3 + slot) * 16 + (co & 15);
+        idx = ((((((int64_t)(co >> 4) * 3 + 0) * (cin / 8) + (ci >> 3)) * 2 + (kw >> 1)) * 2 + (kw & 1)) * 144 + row) * 8 + (ci & 7);
       } else if (LAYOUT == LAYOUT_WPACKN) {
         // the tap's weights as they sit in the column of output voxel j_out = 0: window voxel j_in = kw
         const int ch = cin / 8, ksteps = (p + 2) * ch / 2, n_cols = p * coutp, t9 = tap / 3, kw = tap - t9 * 3;
@@ -215,7 +226,7 @@ extern "C" int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_
                                    const float* bias, float* table, void* stream) {
   if (!partials || !gamma || !beta || !ab || !w32 || !w_out || !bias || !table || rows32 <= 0 || groups <= 0 ||
       channels % groups != 0 || partial_cols % groups != 0 || cin != channels || cout_pad <= 0 || n_per_group <= 0.0 ||
-      n_elems >= (1ll << 31) || layout < LAYOUT_TAPS || layout > LAYOUT_WPACKN || (layout == LAYOUT_HALO && (cin % 16) != 0)) {
+      n_elems >= (1ll << 31) || layout < LAYOUT_TAPS || layout > LAYOUT_ROWS || (layout == LAYOUT_HALO && (cin % 16) != 0)) {
     set_error("groupnorm_fold: bad arguments (rows32=%lld cols=%lld G=%lld C=%lld cin=%lld coutp=%lld n=%lld layout=%d)", (long long)rows32,
               (long long)partial_cols, (long long)groups, (long long)channels, (long long)cin, (long long)cout_pad, (long long)n_elems,
               layout);
@@ -226,6 +237,12 @@ extern "C" int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_
     p = (int)cvit_conv3d_wpackn_group(cin, cout_pad);
     if (p == 0 || n_elems != 9 * (p + 2) * cin * p * cout_pad) {
       set_error("groupnorm_fold: no W-packed layout for cin=%lld cout_pad=%lld (or n_elems=%lld does not match it)", (long long)cin,
+                (long long)cout_pad, (long long)n_elems);
+      return CVIT_ERR_INVALID;
+    }
+  } else if (layout == LAYOUT_ROWS) {
+    if ((cin != 16 && cin != 32) || (cout_pad != 16 && cout_pad != 32) || n_elems != (cout_pad / 16) * 3 * (cin / 8) * 4 * 144 * 8) {
+      set_error("groupnorm_fold: no rows layout for cin=%lld cout=%lld (or n_elems=%lld does not match it)", (long long)cin,
                 (long long)cout_pad, (long long)n_elems);
       return CVIT_ERR_INVALID;
     }
@@ -259,6 +276,9 @@ extern "C" int cvit_groupnorm_fold(const float* partials, int64_t rows32, int64_
                                                      (int)channels, bias, table, 0);
   else if (layout == LAYOUT_HALO)
     gn_fold_kernel<LAYOUT_HALO><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,
+                                                     (int)channels, bias, table, 0);
+  else if (layout == LAYOUT_ROWS)
+    gn_fold_kernel<LAYOUT_ROWS><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,
                                                      (int)channels, bias, table, 0);
   else
     gn_fold_kernel<LAYOUT_WPACKN><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w_out), n_elems, (int)cin, (int)cout_pad, ab,

@@ -119,6 +119,24 @@ def rows8_weight_image(w: torch.Tensor) -> torch.Tensor:
     return img.reshape(-1)
 
 
+def rowsn_weight_image(w: torch.Tensor) -> torch.Tensor:
+    """Conv3d weight [Cout, Cin, 3, 3, 3] (Cin, Cout in {16, 32}) -> the shared-memory images of csrc/conv_rows.cu (fp32, flat):
+    [pass h = co // 16][rotation v][chunk j = ci // 8][K step][chunk c][144 rows][8]; row = (yr * 3 + slot) * 16 + co % 16 holds
+    w[co, j*8 + e, kd, kh = 2 - yr, kw = 2 step + c] with kd = (v + 1 - slot) mod 3 (the fourth column tap is zero)."""
+    cout, cin = w.shape[:2]
+    assert cin in (16, 32) and cout in (16, 32)
+    wf = w.float().reshape(cout // 16, 16, cin // 8, 8, 3, 3, 3)  # [h][col][j][e][kd][kh][kw]
+    img = torch.zeros(cout // 16, 3, cin // 8, 2, 2, 144, 8, device=w.device)
+    for v in range(3):
+        for yr in range(3):
+            for slot in range(3):
+                kd, kh = (v + 1 - slot) % 3, 2 - yr
+                n0 = (yr * 3 + slot) * 16
+                for kw in range(3):
+                    img[:, v, :, kw // 2, kw % 2, n0:n0 + 16] = wf[:, :, :, :, kd, kh, kw].permute(0, 2, 1, 3)
+    return img.reshape(-1)
+
+
 class CryoVITHeadB200:
     def __init__(self, in_channels: int = 1536, fuse_groupnorm: bool | None = None, wpack_narrow: bool | None = None):
         import os
@@ -129,6 +147,7 @@ class CryoVITHeadB200:
         # False: the 16- / 32-channel layers run on the per-tap halo kernel
         self.wpack_narrow = os.environ.get("CVIT_HEAD_WPACKN", "1") != "0" if wpack_narrow is None else wpack_narrow
         self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # the two 8-channel output convolutions on conv_rows8.cu
+        self.rowsn = os.environ.get("CVIT_HEAD_ROWSN", "1") != "0"  # the 16 / 32-channel layers on conv_rows.cu (else W-packed)
         self.device: torch.device | None = None
         self._sd_cpu: dict | None = None
         self._w: dict = {}
@@ -177,8 +196,13 @@ class CryoVITHeadB200:
             ba, bb = torch.zeros(c2p), torch.zeros(c2p)
             ba[:c2], bb[:c2] = sd[p + "1.bias"], sd[p + "3.bias"]
             wT = sd[p + "5.weight"]  # [c2, c3, 1, 2, 2]
-            halo, wpn = {}, {}
+            halo, wpn, rws = {}, {}, {}
             for tag, key, cin in (("a", "1", c1), ("b", "3", c2)):
+                if ops.rows_supported(cin, c2):  # one voxel per tensor-core row (csrc/conv_rows.cu): the 16 / 32-channel layers
+                    img32 = f32(rowsn_weight_image(sd[p + key + ".weight"]))
+                    rws[tag] = {"w32": img32, "w": img32.to(torch.bfloat16), "bias": f32(sd[p + key + ".bias"]),
+                                "table": f32(sd[p + key + ".bias"].repeat(64)), "fold": torch.empty_like(img32, dtype=torch.bfloat16),
+                                "gn_table": torch.empty(64 * c2, device=dev, dtype=torch.float32)}
                 if cin in (8, 16, 32):  # narrow layer: shared-memory halo kernel (csrc/conv_halo.cu)
                     cp = 32 if c2 > 16 else 16
                     hb = torch.zeros(cp)
@@ -196,7 +220,7 @@ class CryoVITHeadB200:
             else:
                 a32, a_layout, a_cp, a_bias = f32(_conv_taps(sd[p + "1.weight"], c2p)).reshape(-1), ops.LAYOUT_TAPS, c2p, f32(ba)
             blocks.append({
-                "wpn": wpn,
+                "wpn": wpn, "rows": rws,
                 "halo": halo, "a_w32": a32, "a_layout": a_layout, "a_cp": a_cp, "a_bias": a_bias,
                 "a_fold": torch.empty(a32.numel(), device=dev, dtype=torch.bfloat16),
                 "a_table": torch.empty(64 * a_cp, device=dev, dtype=torch.float32),
@@ -276,18 +300,24 @@ class CryoVITHeadB200:
             c1, c2, c3 = b["c1"], b["c2"], b["c3"]
             vox = D * H * W
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            wa = b["wpn"].get("a") if self.wpack_narrow and "a" in b["wpn"] and W % b["wpn"]["a"]["P"] == 0 else None
-            wb = b["wpn"].get("b") if self.wpack_narrow and "b" in b["wpn"] and W % b["wpn"]["b"]["P"] == 0 else None
+            ra = b["rows"].get("a") if self.rowsn else None
+            rb = b["rows"].get("b") if self.rowsn else None
+            wa = b["wpn"].get("a") if ra is None and self.wpack_narrow and "a" in b["wpn"] and W % b["wpn"]["a"]["P"] == 0 else None
+            wb = b["wpn"].get("b") if rb is None and self.wpack_narrow and "b" in b["wpn"] and W % b["wpn"]["b"]["P"] == 0 else None
             if fuse:
                 # statistics -> scale / shift -> folded weights + border-aware bias table -> convolution of the RAW tensor
-                if wa is not None:
+                if ra is not None:
+                    ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3,
+                                       b["gn_ab"], ra["w32"], ra["fold"], c1, c2, ops.LAYOUT_ROWS, ra["bias"], ra["gn_table"])
+                    ops.conv3d_rows(cur, ra["fold"], ra["gn_table"], nxt, b["d1"])
+                elif wa is not None:
                     ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3,
                                        b["gn_ab"], wa["w32"], wa["fold"], c1, wa["cp"], ops.LAYOUT_WPACKN, b["a_bias"], b["a_table"])
                     ops.conv3d_wpackn(cur, wa["fold"], b["a_table"], nxt, b["d1"], wa["cp"])
                 else:
                     ops.groupnorm_fold(partials, prod_rows, prod_cols // cpg[bi], b["groups"], vox * cpg[bi], b["gn_w"], b["gn_b"], 1e-3,
                                        b["gn_ab"], b["a_w32"], b["a_fold"], c1, b["a_cp"], b["a_layout"], b["a_bias"], b["a_table"])
-                if wa is not None:
+                if wa is not None or ra is not None:
                     pass
                 elif "a" in b["halo"]:
                     ops.conv3d_halo_tab(cur, b["a_fold"], b["a_table"], nxt, b["d1"], b["a_cp"])
@@ -295,7 +325,9 @@ class CryoVITHeadB200:
                     ops.conv3d_dilated_tab(cur, b["a_fold"].view(27 * b["a_cp"], c1), b["a_table"], nxt, b["d1"])
             else:
                 ops.groupnorm_ndhwc(cur, cur, b["gn_w"], b["gn_b"], stats[: 2 * b["groups"]], b["groups"], 1e-3)
-                if wa is not None:
+                if ra is not None:
+                    ops.conv3d_rows(cur, ra["w"], ra["table"], nxt, b["d1"])
+                elif wa is not None:
                     ops.conv3d_wpackn(cur, wa["w"], wa["table"], nxt, b["d1"], wa["cp"])
                 elif "a" in b["halo"]:
                     ops.conv3d_halo(cur, b["halo"]["a"][0], b["halo"]["a"][1], nxt, b["d1"], b["halo"]["a"][2])
@@ -303,7 +335,9 @@ class CryoVITHeadB200:
                     ops.conv3d_dilated(cur, b["a_w"], b["a_b"], nxt, b["d1"])
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], vox * c2).view(D, H, W, c2)
-            if wb is not None:
+            if rb is not None:
+                ops.conv3d_rows(cur, rb["w"], rb["table"], nxt, b["d2"])
+            elif wb is not None:
                 ops.conv3d_wpackn(cur, wb["w"], wb["table"], nxt, b["d2"], wb["cp"])
             elif "b" in b["halo"]:
                 ops.conv3d_halo(cur, b["halo"]["b"][0], b["halo"]["b"][1], nxt, b["d2"], b["halo"]["b"][2])

@@ -147,7 +147,7 @@ def convT_1x2x2_gn(x, w_sub, bias4, out, partials, cpg: int) -> None:
               _chk(out, BF16, "out"), D, H, W, Cin, Cout, _chk(partials, F32, "partials"), cpg, _stream())
 
 
-LAYOUT_TAPS, LAYOUT_HALO, LAYOUT_WPACKN = 0, 1, 2
+LAYOUT_TAPS, LAYOUT_HALO, LAYOUT_WPACKN, LAYOUT_ROWS = 0, 1, 2, 3
 
 
 def groupnorm_fold_ab(channels: int, groups: int, device) -> torch.Tensor:
@@ -284,6 +284,23 @@ def conv3d_wpack8_gelu(x, w_img, bias_n, out, act=True, aux=None) -> None:
     act, auxp = _aux(act, aux, out)
     _lib.call("cvit_conv3d_wpack8_aux", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias_n, F32, "bias_n"),
               _chk(out, BF16, "out"), D, H, W, act, auxp, _stream())
+
+
+def rows_supported(cin: int, cout: int) -> bool:
+    """Is there a one-voxel-per-row kernel (csrc/conv_rows.cu) for this narrow layer?"""
+    return cin in (16, 32) and cout in (16, 32)
+
+
+def conv3d_rows(x, w_img, table, out, dil: int, act=True, aux=None) -> None:
+    """Narrow-layer (16 / 32 channels) dilated conv + bias-table row (+ GELU), one voxel per MMA row (csrc/conv_rows.cu)."""
+    D, H, W, Cin = x.shape
+    Cout = out.shape[-1]
+    if not rows_supported(Cin, Cout) or w_img.numel() * 2 != (Cout // 16) * _lib.load().cvit_conv3d_rows_weight_bytes(Cin) or \
+            table.numel() != 64 * Cout:
+        raise _lib.CryovitB200Error("conv3d_rows: weight image / bias table do not match the layer")
+    act, auxp = _aux(act, aux, out)
+    _lib.call("cvit_conv3d_rows_ndhwc", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, dil, act, auxp, _stream())
 
 
 def conv3d_rows8(x, w_img, bias8, out, act=True, aux=None) -> None:

@@ -23,7 +23,7 @@ import torch
 from . import ops
 from . import train_ops as T
 from ._lib import CryovitB200Error
-from .head import BLOCKS, rows8_weight_image, state_dict_keys, wpack_weight_image, wpackn_weight_image
+from .head import BLOCKS, rows8_weight_image, rowsn_weight_image, state_dict_keys, wpack_weight_image, wpackn_weight_image
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -99,6 +99,12 @@ class _Conv:
             else:
                 ops.conv3d_wpack8_gelu(x, op, b, out, act=act, aux=aux)
             return
+        if ops.rows_supported(cin, cout) and act != 3 and self.tr.rowsn:
+            # 16- / 32-channel layers (forward and input gradients alike): one voxel per tensor-core row (csrc/conv_rows.cu)
+            b = bias if bias is not None else torch.zeros(cout, device=x.device, dtype=F32)
+            op = self.tr._pk(f"{self.key}/{tag}/rowsn", self.key, lambda w: rowsn_weight_image(wfn(w)))
+            ops.conv3d_rows(x, op, b.repeat(64).contiguous(), out, dil, act=act, aux=aux)
+            return
         halo = cin in (8, 16, 32)
         cp = (32 if cout > 16 else 16) if halo else max(32, cout)
         b = torch.zeros(cp, device=x.device, dtype=F32)
@@ -167,6 +173,7 @@ class CryoVITHeadTrainerB200:
         self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "0") != "0"
         self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
         self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # 8-channel full-resolution convolutions on conv_rows8.cu
+        self.rowsn = os.environ.get("CVIT_HEAD_ROWSN", "1") != "0"  # 16 / 32-channel convolutions on conv_rows.cu
         if state_dict is None:
             from .host.models import default_state_dict
 

@@ -267,6 +267,16 @@ int cvit_conv3d_rows8(const void* x, const void* w_img, const float* bias, void*
 int cvit_conv3d_rows8_final(const void* x, const void* w_img, const float* bias, float* logits, float* probs, int64_t D,
                             int64_t H, int64_t W, void* stream);
 
+/* The 16- / 32-channel depth-dilated convolutions of SynthesisBlocks 3-4 the same way (csrc/conv_rows.cu): 8-channel chunk arrays
+ * of the input rows as K-major operands (column taps = 16-byte shifts), a 144-column accumulator window per input row sliding
+ * through tensor memory, the planes of one dilation residue class walked like a dilation-1 stack. Cin, Cout in {16, 32};
+ * x bf16 [D,H,W,Cin], out (aux) bf16 [D,H,W,Cout]; bias_table fp32 [64][Cout] (the *_tab layout; a plain bias = 64 equal rows);
+ * w_img: Cout / 16 images of cvit_conv3d_rows_weight_bytes(Cin) bytes (cryovit_b200.head.rowsn_weight_image);
+ * act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it. */
+int64_t cvit_conv3d_rows_weight_bytes(int64_t Cin);
+int cvit_conv3d_rows_ndhwc(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
+                           int64_t W, int64_t Cin, int64_t Cout, int64_t dil, int act, void* aux, void* stream);
+
 /* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
  * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;
  * bias4 fp32 [4 * Cout] (the bias repeated per sub-pixel); out bf16 [D, 2H, 2W, Cout]. */

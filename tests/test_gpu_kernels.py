@@ -520,6 +520,17 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
         out2 = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
         ops.conv3d_wpackn(y, w_foldp, table2, out2, dil, cp)
         _close(out2, ref, atol=4e-2, rtol=3e-2, what="GroupNorm folded into the W-packed conv")
+    if halo and ops.rows_supported(Cout, Cn):  # ... and into the one-voxel-per-row kernel's rotated chunk images
+        from cryovit_b200.head import rowsn_weight_image
+        w32r = rowsn_weight_image(wc).to(DEV)
+        w_foldr = torch.empty(w32r.numel(), device=DEV, dtype=torch.bfloat16)
+        table3 = torch.empty(64 * Cn, device=DEV)
+        ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32r, w_foldr, Cout, Cn,
+                           ops.LAYOUT_ROWS, bc, table3)
+        assert torch.allclose(table3.view(64, Cn), table.view(64, cp)[:, :Cn], rtol=1e-4, atol=1e-5)
+        out3 = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.conv3d_rows(y, w_foldr, table3, out3, dil)
+        _close(out3, ref, atol=4e-2, rtol=3e-2, what="GroupNorm folded into the rows conv")
 
 
 @pytest.mark.parametrize("D,H,W", [(3, 16, 128), (2, 10, 200)])
@@ -614,3 +625,27 @@ def test_conv3d_rows8_final(cuda_lib, D, H, W):
     ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding=1)[0, 0].clamp(-5, 5)
     _close(logits, ref, atol=2e-2, rtol=2e-2, what="rows8 final logits")
     _close(probs, torch.sigmoid(ref), atol=5e-3, rtol=5e-3, what="rows8 final probs")
+
+
+@pytest.mark.parametrize("D,H,W,Cin,Cout,dil", [(5, 11, 128, 16, 16, 1), (9, 20, 136, 32, 16, 2), (20, 9, 264, 32, 32, 4),
+                                                 (7, 6, 40, 16, 32, 3), (40, 5, 130, 16, 16, 1), (3, 4, 12, 32, 32, 8)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_conv3d_rows(cuda_lib, D, H, W, Cin, Cout, dil, act):
+    """16 / 32-channel dilated convolution with one voxel per MMA row against F.conv3d: chunked operands, 144-column windows,
+    dilation residue classes, ragged tiles / odd tile counts, a per-mask bias table, the three activation modes."""
+    from cryovit_b200 import ops
+    from cryovit_b200.head import rowsn_weight_image
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = (_rand(Cout, Cin, 3, 3, 3, seed=2) * (27 * Cin) ** -0.5).bfloat16()
+    b = _rand(Cout, seed=3)
+    table = b.repeat(64).contiguous()
+    out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    aux = torch.full_like(out, float("nan")) if act == 2 else None
+    ops.conv3d_rows(x, rowsn_weight_image(w).bfloat16(), table, out, dil, act=act, aux=aux)
+    z = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b, padding="same", dilation=(dil, 1, 1))[0].permute(1, 2, 3, 0)
+    if act == 1:
+        _close(out, F.gelu(z), atol=2e-2, rtol=2e-2, what="rows gelu")
+    else:
+        _close(out, z, atol=2e-2, rtol=2e-2, what="rows pre-activation")
+        if act == 2:
+            _close(aux, F.gelu(z), atol=2e-2, rtol=2e-2, what="rows aux")
