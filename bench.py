@@ -145,6 +145,8 @@ class CallProfiler:
             D, dil = i[0], i[5]
         elif "conv3d_dilated" in name or "conv3d_halo" in name or "conv3d_wpackn" in name:
             D, dil = i[0], i[6]
+        elif "conv3d_rows_ndhwc" in name:  # planes of a residue class outside the volume are skipped
+            D, dil = i[0], i[5]
         else:
             return 1.0
         valid = sum((d - dil >= 0) + 1 + (d + dil < D) for d in range(D))
@@ -181,6 +183,10 @@ class CallProfiler:
         "cvit_conv3d_wpackn_ndhwc_aux": lambda i: CallProfiler._conv(i),
         "cvit_convT_1x2x2_ndhwc_aux": lambda i: 2 * i[0] * i[1] * i[2] * i[3] * 4 * i[4],
         "cvit_conv3d_wpack8_aux": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 64,
+        # one voxel per MMA row (csrc/conv_rows8.cu, csrc/conv_rows.cu)
+        "cvit_conv3d_rows8": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 64,                          # D, H, W, act
+        "cvit_conv3d_rows8_final": lambda i: 2 * i[0] * i[1] * i[2] * 27 * 8,
+        "cvit_conv3d_rows_ndhwc": lambda i: 2 * i[0] * i[1] * i[2] * 27 * i[3] * i[4],            # D, H, W, Cin, Cout, dil, act
     }
 
     def __init__(self, torch):

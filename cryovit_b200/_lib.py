@@ -125,6 +125,8 @@ def load() -> ctypes.CDLL:
     lib.cvit_conv3d_rows8_weight_bytes.argtypes = []
     lib.cvit_conv3d_rows_weight_bytes.restype = c_int64
     lib.cvit_conv3d_rows_weight_bytes.argtypes = [c_int64]
+    lib.cvit_convT_gn_partial_rows.restype = c_int64
+    lib.cvit_convT_gn_partial_rows.argtypes = [c_int64, c_int64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = c_int

@@ -254,6 +254,7 @@ static GemmArgs base_args(int64_t M, int64_t N, int64_t K, void* out, int64_t ld
 
 extern "C" {
 
+int64_t cvit_convT_gn_partial_rows(int64_t Cout, int64_t gn_cpg);
 int cvit_linear_bias_bf16_nvalid_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, int64_t ldo,
                                      int64_t M, int64_t N, int64_t K, int64_t n_valid, int act, const void* aux, void* stream);
 int cvit_linear_bias_cfirst_f16_aux(const void* At, int64_t ldat, const void* W, const float* bias, void* out, int64_t ldo,
@@ -493,7 +494,21 @@ int cvit_convT_1x2x2_ndhwc_gn(const void* x, const void* w_sub, const float* bia
   a.act = 1;
   a.gn_partials = gn_partials;
   a.gn_cpg = (int)gn_cpg;
+  if (cvit_convT_gn_partial_rows(Cout, gn_cpg) > 0) {
+    // register-accumulated statistics: one partials row per epilogue thread of every CTA that could run; rows of CTAs that
+    // are not launched (fewer tiles than SMs) must read as zero
+    a.gn_direct = 1;
+    cudaError_t e = cudaMemsetAsync(gn_partials, 0, (size_t)cvit_convT_gn_partial_rows(Cout, gn_cpg) * 8 * 2 * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("convT_gn: cudaMemsetAsync: %s", cudaGetErrorString(e)); return CVIT_ERR_CUDA; }
+  }
   return gemm_rows(x, Cin, w_sub, a, EPI_CONVT_GELU, (cudaStream_t)stream);
+}
+
+// Rows of the statistics buffer cvit_convT_1x2x2_ndhwc_gn writes for this layer when it keeps the group sums in registers
+// (32 output channels in groups of 4): [rows][8 groups][2] fp32, to be folded with rows32 = rows, partial columns = 8.
+// 0: the per-32-voxel layout of the other producers ([ceil(voxels / 32)][4 Cout / cpg][2]).
+int64_t cvit_convT_gn_partial_rows(int64_t Cout, int64_t gn_cpg) {
+  return (CONVT_DIRECT && Cout == 32 && gn_cpg == 4) ? (int64_t)num_sms() * 256 : 0;
 }
 
 // Consumer variant (see GemmArgs::bias_table): the convolution after a folded GroupNorm.

@@ -67,6 +67,8 @@ struct GemmArgs {
   //    shift b_c contributes  sum over the IN-BOUNDS taps of sum_c w[tap][c] * b_c, which depends on exactly that.
   float* gn_partials;
   int gn_cpg;
+  int gn_direct;      // EPI_CONVT_GELU with 32 channels in groups of 4: every epilogue thread keeps the 8 group sums of everything it
+                      // stores in registers and writes ONE partials row [8][2] at the end of the kernel (row = block * 256 + thread)
   const float* bias_table;
 };
 // A and B hold IEEE fp16 instead of bf16 (same type on both sides: tcgen05 kind::f16 rule); EPI_BIAS / _GELU / _SWIGLU
@@ -398,6 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         *dst = make_float2(sm, sq);
       }
     };
+    float gsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gsq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // gn_direct
     for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const TileCoord t = coord(tile);
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
@@ -422,14 +425,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int c0 = ch * 32;
-        if (EPI == EPI_CONVT_GELU && !args.gn_partials && CONVT_DIRECT && args.c3 < 32) {
-          // Transposed convolution to 8 / 16 channels, no statistics: NO shared-memory transpose. The thread keeps its
-          // accumulator row (one input voxel, 32 output columns = the 16-byte channel blocks of 2..4 sub-pixels) and stores
-          // each block where the pixel shuffle puts it: ~9 instructions per output value instead of ~20 (ncu: the
-          // transposing epilogue ran 19-25 instructions per value at 46 % issue utilisation, tensor pipe 1-2 %).
-          // 16 -> 8 at 256^2: 0.325 -> 0.260 ms (GELU), 0.220 -> 0.170 ms (training, no activation). With 32 channels
-          // per sub-pixel a thread's 64 contiguous bytes sit 128 bytes from its neighbour's and the transposing path's
-          // full-sector stores win (0.221 vs 0.238 ms): kept there.
+        if (EPI == EPI_CONVT_GELU && CONVT_DIRECT && args.c3 <= 32 && (!args.gn_partials || args.gn_direct)) {
+          // Transposed convolution to 8 / 16 / 32 channels: NO shared-memory transpose. The thread keeps its accumulator row
+          // (one input voxel, 32 output columns = whole channel blocks of 1..4 sub-pixels) and stores them where the pixel
+          // shuffle puts them, 32 bytes (one full sector) per store: columns 0..15 and 16..31 of a chunk are contiguous in
+          // the output for every channel count (8: sub-pixels (i,0),(i,1); 16 / 32: one sub-pixel). ~9 instructions per
+          // output value instead of 19-25 (ncu: the transposing epilogue ran at 46 % issue utilisation, tensor pipe 1-2 %).
+          // GroupNorm statistics (gn_direct): 32 columns = the 8 groups of 4 channels of one sub-pixel, the same 8 groups in
+          // every chunk: two FMAs per value into 16 registers that live for the whole kernel.
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c0, v);
           tmem_ld_wait();
@@ -440,29 +443,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __nv_bfloat16* o1 = static_cast<__nv_bfloat16*>(args.out);
             __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(args.act == ACT_DUAL ? args.aux : args.out);
 #pragma unroll
-            for (int b8 = 0; b8 < 4; ++b8) {
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(args.bias + t.n0 + c0 + 8 * b8));
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + t.n0 + c0 + 8 * b8 + 4));
-              float y[8] = {__uint_as_float(v[8 * b8]) + ba.x,     __uint_as_float(v[8 * b8 + 1]) + ba.y,
-                            __uint_as_float(v[8 * b8 + 2]) + ba.z, __uint_as_float(v[8 * b8 + 3]) + ba.w,
-                            __uint_as_float(v[8 * b8 + 4]) + bb.x, __uint_as_float(v[8 * b8 + 5]) + bb.y,
-                            __uint_as_float(v[8 * b8 + 6]) + bb.z, __uint_as_float(v[8 * b8 + 7]) + bb.w};
-              const size_t off = ((size_t)(2 * dh + (ij >> 1)) * W2 + 2 * w + (ij & 1)) * args.c3 + co;
-              if (args.act == ACT_DUAL)
-                *reinterpret_cast<uint4*>(o1 + off) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                                 pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-              if (args.act) {
-                gelu_erf2(y[0], y[1]);
-                gelu_erf2(y[2], y[3]);
-                gelu_erf2(y[4], y[5]);
-                gelu_erf2(y[6], y[7]);
+            for (int b16 = 0; b16 < 2; ++b16) {
+              float y[16];
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(args.bias + t.n0 + c0 + 16 * b16 + 4 * c4));
+                y[4 * c4] = __uint_as_float(v[16 * b16 + 4 * c4]) + bq.x;
+                y[4 * c4 + 1] = __uint_as_float(v[16 * b16 + 4 * c4 + 1]) + bq.y;
+                y[4 * c4 + 2] = __uint_as_float(v[16 * b16 + 4 * c4 + 2]) + bq.z;
+                y[4 * c4 + 3] = __uint_as_float(v[16 * b16 + 4 * c4 + 3]) + bq.w;
               }
-              *reinterpret_cast<uint4*>(o2 + off) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                               pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-              co += 8;
-              const int wrap = co >= args.c3 ? 1 : 0;
-              co -= wrap * args.c3;
-              ij += wrap;
+              const size_t off = ((size_t)(2 * dh + (ij >> 1)) * W2 + 2 * w + (ij & 1)) * args.c3 + co;
+              if (args.act == ACT_DUAL) {
+                uint32_t pz[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pz[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
+                st_global_v8(o1 + off, pz);
+              }
+              if (args.act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gelu_erf2(y[2 * i], y[2 * i + 1]);
+              }
+              if (args.gn_direct) {
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                  const float a0 = y[4 * gi], a1 = y[4 * gi + 1], a2 = y[4 * gi + 2], a3 = y[4 * gi + 3];
+                  gsum[4 * b16 + gi] += (a0 + a1) + (a2 + a3);
+                  gsq[4 * b16 + gi] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                }
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
+              st_global_v8(o2 + off, pk);
+              co += 16;
+              while (co >= args.c3) {  // 16 columns on: the next sub-pixel(s) when a sub-pixel has 8 or 16 channels
+                co -= args.c3;
+                ++ij;
+              }
             }
           }
           continue;
@@ -668,6 +686,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
+    }
+    if (EPI == EPI_CONVT_GELU && args.gn_partials && args.gn_direct) {
+      // one partials row per epilogue thread: [8 groups][sum, sum of squares] of everything it stored
+      float4* dst = reinterpret_cast<float4*>(args.gn_partials) + ((size_t)blockIdx.x * 256 + (ew * 32 + lane)) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(gsum[2 * i], gsq[2 * i], gsum[2 * i + 1], gsq[2 * i + 1]);
     }
   }
 

@@ -444,6 +444,12 @@ template <bool F16>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
   return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
+// 32-byte store (one full sector per lane; sm_100: STG.256). p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -273,7 +273,7 @@ class CryoVITHeadB200:
             need = ops.gn_partials_numel(vox0, 1024, cpg[0])
             Hc, Wc = h, w
             for bi in range(len(blocks) - 1):
-                need = max(need, ops.gn_partials_numel(D * Hc * Wc, 4 * blocks[bi]["c3"], cpg[bi + 1]))
+                need = max(need, ops.gn_partials_numel(D * Hc * Wc, 4 * blocks[bi]["c3"], cpg[bi + 1]), 16 * 256 * 1024)
                 Hc, Wc = 2 * Hc, 2 * Wc
             partials = self._buf("gn_partials", need, torch.float32)
         if features.dtype == torch.float16 and "proj_w16" in w_ and vox0 % 8 == 0 and C % 8 == 0 and C >= 64:
@@ -346,13 +346,13 @@ class CryoVITHeadB200:
             cur, flip = nxt, flip ^ 1
             nxt = self._buf(names[flip], 4 * vox * c3).view(D, 2 * H, 2 * W, c3)
             if fuse and bi + 1 < len(blocks):
-                ops.convT_1x2x2_gn(cur, b["t_w"], b["t_b"], nxt, partials, cpg[bi + 1])
-                prod_rows, prod_cols = vox, 4 * c3
+                prod_rows, prod_cols = ops.convT_1x2x2_gn(cur, b["t_w"], b["t_b"], nxt, partials, cpg[bi + 1])
             else:
                 ops.convT_1x2x2(cur, b["t_w"], b["t_b"], nxt)
             cur, flip = nxt, flip ^ 1
             H, W = 2 * H, 2 * W
             self.launches += 5 if fuse else 6  # fused: finalize + fold + 3 layers; else memset + 2 GroupNorm kernels + 3 layers
+            self.launches += sum(c2 // 16 - 1 for r_ in (ra, rb) if r_ is not None)  # conv3d_rows: one kernel per 16 output channels
         scratch = self._buf(names[flip], D * H * W * 8).view(D, H, W, 8)
         logits = torch.empty(D, H, W, device=self.device) if want_logits else None
         probs = torch.empty(D, H, W, device=self.device) if want_probs else None

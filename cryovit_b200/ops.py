@@ -138,13 +138,18 @@ def linear_bias_gelu_gn(a, w, bias, out, partials, cpg: int) -> None:
               _chk(out, BF16, "out"), out.stride(0), M, N, K, _chk(partials, F32, "partials"), cpg, _stream())
 
 
-def convT_1x2x2_gn(x, w_sub, bias4, out, partials, cpg: int) -> None:
+def convT_1x2x2_gn(x, w_sub, bias4, out, partials, cpg: int) -> tuple[int, int]:
+    """Transposed convolution + GELU + the statistics of what it stores. Returns (rows, columns) of the statistics as
+    ``groupnorm_fold`` wants them: (voxels, 4 Cout) in the per-32-voxel layout, or (32 R, 8 cpg) when the kernel kept the group
+    sums in registers and wrote R rows of 8 groups (32 channels in groups of 4)."""
     D, H, W, Cin = x.shape
     Cout = w_sub.shape[0] // 4
-    if partials.numel() < gn_partials_numel(D * H * W, 4 * Cout, cpg):
+    R = int(_lib.load().cvit_convT_gn_partial_rows(Cout, cpg))
+    if partials.numel() < max(gn_partials_numel(D * H * W, 4 * Cout, cpg), R * 16):
         raise _lib.CryovitB200Error("convT_1x2x2_gn: statistics buffer too small")
     _lib.call("cvit_convT_1x2x2_ndhwc_gn", _chk(x, BF16, "x"), _chk(w_sub, BF16, "w_sub"), _chk(bias4, F32, "bias4"),
               _chk(out, BF16, "out"), D, H, W, Cin, Cout, _chk(partials, F32, "partials"), cpg, _stream())
+    return (32 * R, 8 * cpg) if R else (D * H * W, 4 * Cout)
 
 
 LAYOUT_TAPS, LAYOUT_HALO, LAYOUT_WPACKN, LAYOUT_ROWS = 0, 1, 2, 3

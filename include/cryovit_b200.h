@@ -199,6 +199,10 @@ int cvit_linear_bias_gelu_bf16_gn(const void* A, int64_t lda, const void* W, con
                                   int64_t M, int64_t N, int64_t K, float* gn_partials, int64_t gn_cpg, void* stream);
 int cvit_convT_1x2x2_ndhwc_gn(const void* x, const void* w_sub, const float* bias4, void* out, int64_t D, int64_t H,
                               int64_t W, int64_t Cin, int64_t Cout, float* gn_partials, int64_t gn_cpg, void* stream);
+/* Layout of the statistics that cvit_convT_1x2x2_ndhwc_gn writes: with 32 output channels in groups of 4 every epilogue thread
+ * keeps its group sums in registers for the whole kernel and writes one row [8 groups][2]: this returns that row count (fold
+ * with rows32 = rows, partial columns = 8; the buffer must hold rows * 16 floats). 0: the per-32-voxel layout described above. */
+int64_t cvit_convT_gn_partial_rows(int64_t Cout, int64_t gn_cpg);
  /* ab must hold cvit_groupnorm_fold_ab_elems(channels, groups) floats (scale / shift first, then the reduction's
   * scratch), 16-byte aligned, ZERO-FILLED once before its first use (the kernels leave the scratch as they found it). */
 int64_t cvit_groupnorm_fold_ab_elems(int64_t channels, int64_t groups);

@@ -34,7 +34,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert bound.cvit_abi_version() == 1
     assert set(_lib.SIGNATURES) | {"cvit_last_error", "cvit_abi_version", "cvit_conv3d_halo_weight_bytes", "cvit_conv3d_wpack_weight_bytes",
                                    "cvit_groupnorm_fold_ab_elems", "cvit_conv3d_wpackn_group", "cvit_conv3d_wpackn_weight_bytes",
-                                   "cvit_conv3d_rows8_weight_bytes", "cvit_conv3d_rows_weight_bytes"} == set(_declared())
+                                   "cvit_conv3d_rows8_weight_bytes", "cvit_conv3d_rows_weight_bytes", "cvit_convT_gn_partial_rows"} == set(_declared())
     assert bound.cvit_conv3d_wpack_weight_bytes(8, 8) == 9 * 5 * 2 * 64 * 16 and bound.cvit_conv3d_wpack_weight_bytes(16, 1) == 9 * 9 * 2 * 16 * 16
     assert bound.cvit_conv3d_halo_weight_bytes(32, 32) == 9 * 6 * 2 * 32 * 16 and bound.cvit_conv3d_halo_weight_bytes(8, 16) == 9 * 2 * 2 * 16 * 16
 

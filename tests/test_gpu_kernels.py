@@ -477,9 +477,9 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
     G = Cout // cpg
     # producer: transposed convolution + GELU with statistics
     y = torch.empty(D, 2 * H, 2 * W, Cout, device=DEV, dtype=torch.bfloat16)
-    partials = torch.full((ops.gn_partials_numel(D * H * W, 4 * Cout, cpg),), float("nan"), device=DEV)
+    partials = torch.full((max(ops.gn_partials_numel(D * H * W, 4 * Cout, cpg), 16 * 256 * 1024),), float("nan"), device=DEV)
     w_sub = wt[:, :, 0].permute(2, 3, 1, 0).reshape(4 * Cout, Cin).bfloat16().contiguous()
-    ops.convT_1x2x2_gn(x, w_sub, bt.repeat(4).contiguous(), y, partials, cpg)
+    prows, pcols = ops.convT_1x2x2_gn(x, w_sub, bt.repeat(4).contiguous(), y, partials, cpg)
     yr = F.gelu(F.conv_transpose3d(x.float().permute(3, 0, 1, 2)[None], wt.bfloat16().float(), bt, stride=(1, 2, 2)))  # [1,Cout,D,2H,2W]
     _close(y, yr[0].permute(1, 2, 3, 0), atol=3e-2, rtol=2e-2, what="convT")
     # fold + consumer
@@ -494,7 +494,7 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
     w_fold = torch.empty(w32.numel(), device=DEV, dtype=torch.bfloat16)
     table = torch.empty(64 * cp, device=DEV)
     vox = D * 2 * H * 2 * W
-    ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32, w_fold, Cout, cp, layout, bias, table)
+    ops.groupnorm_fold(partials, prows, pcols // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32, w_fold, Cout, cp, layout, bias, table)
     # scale / shift against torch's statistics of the STORED tensor
     ys = y.float().permute(3, 0, 1, 2).reshape(G, -1)
     mean, var = ys.mean(1), ys.var(1, unbiased=False)
@@ -514,7 +514,7 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
         w32p = wpackn_weight_image(wc.cpu(), cp, ops.wpackn_group(Cout, cp)).to(DEV)
         w_foldp = torch.empty(w32p.numel(), device=DEV, dtype=torch.bfloat16)
         table2 = torch.empty(64 * cp, device=DEV)
-        ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32p, w_foldp, Cout, cp,
+        ops.groupnorm_fold(partials, prows, pcols // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32p, w_foldp, Cout, cp,
                            ops.LAYOUT_WPACKN, bias, table2)
         assert torch.allclose(table2, table, rtol=1e-4, atol=1e-5)
         out2 = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
@@ -525,7 +525,7 @@ def test_groupnorm_folded_between_convT_and_conv(cuda_lib, D, H, W, Cin, Cout, c
         w32r = rowsn_weight_image(wc).to(DEV)
         w_foldr = torch.empty(w32r.numel(), device=DEV, dtype=torch.bfloat16)
         table3 = torch.empty(64 * Cn, device=DEV)
-        ops.groupnorm_fold(partials, D * H * W, 4 * Cout // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32r, w_foldr, Cout, Cn,
+        ops.groupnorm_fold(partials, prows, pcols // cpg, G, vox * cpg, gamma, beta, 1e-3, ab, w32r, w_foldr, Cout, Cn,
                            ops.LAYOUT_ROWS, bc, table3)
         assert torch.allclose(table3.view(64, Cn), table.view(64, cp)[:, :Cn], rtol=1e-4, atol=1e-5)
         out3 = torch.full((D, 2 * H, 2 * W, Cn), float("nan"), device=DEV, dtype=torch.bfloat16)
