@@ -223,16 +223,32 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
           const int x = x0 + q * 32 + lane;
           mbar_wait(bar_done + 8 * g, nd & 1);
           tcgen05_fence_after();
-          if (to >= ta && to < tb) {
+          // Read this half's rows of the finished plane, zero the slot and hand it back BEFORE the math and the stores: the
+          // other tile's MMAs cover the drain's TMEM round trips, not its GELUs.
+          const bool live = to >= ta && to < tb;
+          constexpr int RMAX = (HT + 1) / 2;
+          uint32_t v[RMAX][16];
+          if (live) {
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k)
+              if (rlo + k < rhi) tmem_ld_32x16(t_seg + (rlo + k) * RN_SLOT + p * RN_CO, v[k]);
+            tmem_ld_wait();
+          }
+          if (t == tb) {
+            zero_all(g);  // the unit's last step: the halo planes' leftovers go too
+          } else {
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k)
+              if (rlo + k < rhi) tmem_st_32x16(t_seg + (rlo + k) * RN_SLOT + p * RN_CO, zeros);
+          }
+          hand_back(g);
+          if (live) {
             const int dm = (zo >= d ? 1 : 0) | (zo + d < args.D ? 2 : 0);
             const int wm = (x >= 1 ? 1 : 0) | (x + 1 < args.W ? 2 : 0);
-#pragma unroll 1
-            for (int rr = rlo; rr < rhi; ++rr) {
-              uint32_t v[16];
-              tmem_ld_32x16(t_seg + rr * RN_SLOT + p * RN_CO, v);
-              tmem_ld_wait();
-              const int y = yt0 + rr;
-              if (y < args.H && x < args.W) {
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k) {
+              const int y = yt0 + rlo + k;
+              if (rlo + k < rhi && y < args.H && x < args.W) {
                 const int hm = (y >= 1 ? 1 : 0) | (y + 1 < args.H ? 2 : 0);
                 const float4* row = tab4 + ((dm * 4 + hm) * 4 + wm) * (RN_CO / 4);
                 const size_t off = (((size_t)zo * args.H + y) * args.W + x) * args.out_stride;
@@ -240,38 +256,27 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   const float4 tb4 = row[c];
-                  o[4 * c] = __uint_as_float(v[4 * c]) + tb4.x;
-                  o[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + tb4.y;
-                  o[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + tb4.z;
-                  o[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + tb4.w;
+                  o[4 * c] = __uint_as_float(v[k][4 * c]) + tb4.x;
+                  o[4 * c + 1] = __uint_as_float(v[k][4 * c + 1]) + tb4.y;
+                  o[4 * c + 2] = __uint_as_float(v[k][4 * c + 2]) + tb4.z;
+                  o[4 * c + 3] = __uint_as_float(v[k][4 * c + 3]) + tb4.w;
                 }
+                uint32_t pk[8];
                 if (args.act == ACT_DUAL) {
 #pragma unroll
-                  for (int c = 0; c < 2; ++c)
-                    *reinterpret_cast<uint4*>(args.out + off + 8 * c) =
-                        make_uint4(pack_bf16x2(o[8 * c], o[8 * c + 1]), pack_bf16x2(o[8 * c + 2], o[8 * c + 3]),
-                                   pack_bf16x2(o[8 * c + 4], o[8 * c + 5]), pack_bf16x2(o[8 * c + 6], o[8 * c + 7]));
+                  for (int c = 0; c < 8; ++c) pk[c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+                  st_global_v8(args.out + off, pk);
                 }
                 if (args.act) {
 #pragma unroll
                   for (int c = 0; c < 8; ++c) gelu_erf2(o[2 * c], o[2 * c + 1]);
                 }
-                __nv_bfloat16* dst = (args.act == ACT_DUAL ? args.aux : args.out) + off;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-                  *reinterpret_cast<uint4*>(dst + 8 * c) =
-                      make_uint4(pack_bf16x2(o[8 * c], o[8 * c + 1]), pack_bf16x2(o[8 * c + 2], o[8 * c + 3]),
-                                 pack_bf16x2(o[8 * c + 4], o[8 * c + 5]), pack_bf16x2(o[8 * c + 6], o[8 * c + 7]));
+                for (int c = 0; c < 8; ++c) pk[c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+                st_global_v8((args.act == ACT_DUAL ? args.aux : args.out) + off, pk);  // 16 channels = one 32-byte sector
               }
             }
           }
-          if (t == tb) {
-            zero_all(g);  // the unit's last step: the halo planes' leftovers go too
-          } else {
-#pragma unroll 1
-            for (int rr = rlo; rr < rhi; ++rr) tmem_st_32x16(t_seg + rr * RN_SLOT + p * RN_CO, zeros);
-          }
-          hand_back(g);
         }
       }
     }

@@ -233,12 +233,23 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
           const int x = xp + g * CR_SEG + q * 32 + lane;
           mbar_wait(bar_done + 8 * g, nd & 1);
           tcgen05_fence_after();
-          if (zo >= za && zo < zb) {
-            // output plane zo is complete: this half's rows of this thread's voxel column
-            uint32_t v[RH][8];
+          // Read this half's rows of the finished plane, zero the slot and hand it back BEFORE the math and the stores: the other
+          // segment's MMAs cover the drain's TMEM round trips, not its GELUs.
+          const bool live = zo >= za && zo < zb;
+          uint32_t v[RH][8];
+          if (live) {
 #pragma unroll
             for (int r = 0; r < RH; ++r) cr_tmem_ld8(t_seg + (half * RH + r) * CR_SLOT + p * 8, v[r]);
             tmem_ld_wait();
+          }
+          if (zi == zb) {
+            zero_all(g);  // the unit's last plane: everything (the halo planes' leftovers too) is cleared for the next unit
+          } else {
+#pragma unroll
+            for (int r = 0; r < RH; ++r) tmem_st_32x8(t_seg + (half * RH + r) * CR_SLOT + p * 8, zeros);  // slot p: plane zo + 3 next
+          }
+          hand_back(g);
+          if (live) {
 #pragma unroll
             for (int r = 0; r < RH; ++r) {
               const int y = yt0 + half * RH + r;
@@ -269,13 +280,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
               }
             }
           }
-          if (zi == zb) {
-            zero_all(g);  // the unit's last plane: everything (the halo planes' leftovers too) is cleared for the next unit
-          } else {
-#pragma unroll
-            for (int r = 0; r < RH; ++r) tmem_st_32x8(t_seg + (half * RH + r) * CR_SLOT + p * 8, zeros);  // slot p: plane zo + 3 next
-          }
-          hand_back(g);
         }
       }
     }

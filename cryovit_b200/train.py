@@ -168,9 +168,10 @@ class CryoVITHeadTrainerB200:
         # GELU forward (z and gelu(z) from one epilogue) and backward (gelu'(z) applied by the input-gradient epilogue)
         # fused into the convolutions; CVIT_TRAIN_FUSE_ACT=0 keeps the separate element-wise kernels (A/B, tests)
         self.fuse_activations = os.environ.get("CVIT_TRAIN_FUSE_ACT", "1") != "0"
-        # ... also in the two kernels that are bound by their stores (transposed convolution, 8 -> 8 at full resolution),
-        # and gelu' in the input-gradient epilogues: both measured slower than the separate passes, off by default
-        self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "0") != "0"
+        # ... also in the two kernels that are bound by their stores (transposed convolution, 8 -> 8 at full resolution): a loss
+        # with the transposing epilogues (profiles/r02_train_notes.md), a small win since both store straight from the
+        # accumulator row (19.58 -> 19.41 ms). gelu' in the input-gradient epilogues: slower than the separate pass, off.
+        self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "1") != "0"
         self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
         self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # 8-channel full-resolution convolutions on conv_rows8.cu
         self.rowsn = os.environ.get("CVIT_HEAD_ROWSN", "1") != "0"  # 16 / 32-channel convolutions on conv_rows.cu
