@@ -10,9 +10,9 @@ python tools/ncu_target.py 128 > /dev/null 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|attention_tcgen05|layernorm" -s 6 -c 6 \
       -o /tmp/${rnd}_full_${tag} python tools/ncu_target.py 128 > $log 2>&1
 python tools/ncu_extract.py /tmp/${rnd}_full_${tag}.ncu-rep > gpurun_out/${rnd}_ncu_full_${tag}_hot_kernels.json 2>> $log
-# head forward: the third volume of tools/head_probe.py (23 launches per volume, warm)
+# head forward: the third volume of tools/head_probe.py (25 launches per volume, warm)
 python tools/head_probe.py > /dev/null 2>&1 && \
-  ncu --set full --clock-control none -k regex:"conv3d|gemm_tcgen05|gn_f|groupnorm" -s 46 -c 23 -o /tmp/${rnd}_head_full_${tag} python tools/head_probe.py >> $log 2>&1
+  ncu --set full --clock-control none -k regex:"conv3d|gemm_tcgen05|gn_f|groupnorm" -s 50 -c 25 -o /tmp/${rnd}_head_full_${tag} python tools/head_probe.py >> $log 2>&1
 python tools/ncu_extract.py /tmp/${rnd}_head_full_${tag}.ncu-rep > gpurun_out/${rnd}_ncu_full_${tag}_head_kernels.json 2>> $log
 # training: the tcgen05 weight-gradient kernels of one step
 python tools/train_probe.py > /dev/null 2>&1 && \
