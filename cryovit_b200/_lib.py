@@ -73,6 +73,7 @@ SIGNATURES: dict[str, list] = {
     "cvit_dice_bwd": [P, P, P, P, F32, P, I64, P],
     "cvit_colsum_bf16": [P, P, I64, I64, P],
     "cvit_groupnorm_bwd_ndhwc_bf16": [P, P, P, P, P, P, P, I64, I64, I64, F32, P],
+    "cvit_groupnorm_bwd_gelu_ndhwc_bf16": [P, P, P, P, P, P, P, I64, I64, I64, F32, P, P, I64, P],
     "cvit_pixel_unshuffle_1x2x2_bf16": [P, P, I64, I64, I64, I64, P],
     "cvit_ndhwc_to_cfirst_padded": [P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],
     "cvit_ndhwc_to_cfirst_padded_x3": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, P],

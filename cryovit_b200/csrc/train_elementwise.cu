@@ -194,8 +194,13 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_reduce_kernel(const __nv_bf
 __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                    __nv_bfloat16* __restrict__ dx, const float* __restrict__ gamma,
                                                                    const float* __restrict__ stats, const float* __restrict__ dgamma,
-                                                                   const float* __restrict__ dbeta, int64_t DHW, int C, int G, float eps) {
-  extern __shared__ float s_g[];  // [4][G]: mean, rstd, s1/N, s2/N
+                                                                   const float* __restrict__ dbeta, int64_t DHW, int C, int G, float eps,
+                                                                   const __nv_bfloat16* __restrict__ z, float* __restrict__ db, int W2) {
+  // z != null: the GroupNorm's input was gelu(z) (the block before ends in a transposed convolution + GELU, or the
+  // projection + GELU): the result is multiplied by gelu'(z) right here -- dx is then the gradient of z -- its column sums
+  // (that layer's bias gradient) go to db, and with W2 > 0 it is stored pixel-unshuffled ([D, H2/2, W2/2, 4C], see
+  // gelu_bwd_colsum_kernel): one pass instead of two over the step's largest gradient volumes.
+  extern __shared__ float s_g[];  // [4][G]: mean, rstd, s1/N, s2/N | z != null: + [C] column sums
   const int cpg = C / G;
   const float inv_n = 1.0f / (static_cast<float>(DHW) * cpg);
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -214,10 +219,18 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfl
   __syncthreads();
   const int nvec = C / 8;
   const int64_t total = DHW * nvec;
+  float* s_db = s_g + 4 * G;
+  if (z)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // this thread's 8 channels (the grid stride is a multiple of nvec)
+  __syncthreads();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int vec = (int)(idx % nvec);
     const uint4 rx = *reinterpret_cast<const uint4*>(x + idx * 8);
     const uint4 rd = *reinterpret_cast<const uint4*>(dy + idx * 8);
+    uint4 rz = make_uint4(0u, 0u, 0u, 0u);
+    if (z) rz = *reinterpret_cast<const uint4*>(z + idx * 8);
+    const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&rz);
     const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&rx);
     const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&rd);
     uint32_t o[4];
@@ -229,9 +242,31 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfl
       const float xh0 = (fx.x - s_g[g0]) * s_g[G + g0], xh1 = (fx.y - s_g[g1]) * s_g[G + g1];
       const float d0 = s_g[G + g0] * (__ldg(gamma + c) * fd.x - (s_g[2 * G + g0] + xh0 * s_g[3 * G + g0]));
       const float d1 = s_g[G + g1] * (__ldg(gamma + c + 1) * fd.y - (s_g[2 * G + g1] + xh1 * s_g[3 * G + g1]));
-      o[k] = pack_bf16x2(d0, d1);
+      if (z) {
+        const float2 fz = __bfloat1622float2(hz[k]);
+        const __nv_bfloat162 d2 = __floats2bfloat162_rn(d0 * gelu_grad(fz.x), d1 * gelu_grad(fz.y));
+        o[k] = *reinterpret_cast<const uint32_t*>(&d2);
+        const float2 dr = __bfloat1622float2(d2);  // sums over the STORED gradient, as the separate pass computes them
+        acc[2 * k] += dr.x;
+        acc[2 * k + 1] += dr.y;
+      } else {
+        o[k] = pack_bf16x2(d0, d1);
+      }
     }
-    *reinterpret_cast<uint4*>(dx + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    int64_t io = idx;
+    if (W2 > 0) {
+      const int64_t r = idx / nvec, dh2 = r / W2;
+      const int wx = (int)(r - dh2 * W2);
+      io = (((dh2 >> 1) * (W2 >> 1) + (wx >> 1)) * 4 + ((dh2 & 1) * 2 + (wx & 1))) * nvec + vec;
+    }
+    *reinterpret_cast<uint4*>(dx + io * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (z) {
+    const int vec = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % nvec);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_db[vec * 8 + k], acc[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(db + i, s_db[i]);
   }
 }
 
@@ -331,9 +366,22 @@ int cvit_colsum_bf16(const void* x, float* out, int64_t R, int64_t C, void* stre
   return check_launch("colsum_kernel");
 }
 
+int cvit_groupnorm_bwd_gelu_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats, float* dgamma,
+                                       float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, const void* z, float* db,
+                                       int64_t W2, void* stream);
+
 int cvit_groupnorm_bwd_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats,
                                   float* dgamma, float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, void* stream) {
-  if (!x || !dy || !dx || !gamma || !stats || !dgamma || !dbeta || DHW <= 0 || C <= 0 || G <= 0 || (C % 8) || (C % G) || C > 2048) {
+  return cvit_groupnorm_bwd_gelu_ndhwc_bf16(x, dy, dx, gamma, stats, dgamma, dbeta, DHW, C, G, eps, nullptr, nullptr, 0, stream);
+}
+
+// GroupNorm backward; with z (bf16, x's shape: x = gelu(z)) the result is d(z) = d(x) * gelu'(z), db (fp32 [C], zeroed by the
+// caller) += its column sums, and W2 > 0 (x is a [D, H2, W2, C] volume, H2 and W2 even) stores it pixel-unshuffled.
+int cvit_groupnorm_bwd_gelu_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats, float* dgamma,
+                                       float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, const void* z, float* db,
+                                       int64_t W2, void* stream) {
+  if (!x || !dy || !dx || !gamma || !stats || !dgamma || !dbeta || DHW <= 0 || C <= 0 || G <= 0 || (C % 8) || (C % G) || C > 2048 ||
+      (z && !db) || (!z && W2 != 0) || W2 < 0 || (W2 & 1) || (W2 > 0 && (DHW % (2 * W2)) != 0)) {
     set_error("groupnorm_bwd: bad arguments");
     return CVIT_ERR_INVALID;
   }
@@ -351,9 +399,9 @@ int cvit_groupnorm_bwd_ndhwc_bf16(const void* x, const void* dy, void* dx, const
                                                                           DHW, (int)C, (int)G, eps, rpb);
   int rc = check_launch("groupnorm_bwd_reduce_kernel");
   if (rc) return rc;
-  groupnorm_bwd_apply_kernel<<<ew_grid(DHW * (C / 8), 4), 256, 4 * G * sizeof(float), st>>>(
+  groupnorm_bwd_apply_kernel<<<ew_grid(DHW * (C / 8), 4), 256, (4 * G + (z ? C : 0)) * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), gamma, stats,
-      dgamma, dbeta, DHW, (int)C, (int)G, eps);
+      dgamma, dbeta, DHW, (int)C, (int)G, eps, static_cast<const __nv_bfloat16*>(z), db, (int)W2);
   return check_launch("groupnorm_bwd_apply_kernel");
 }
 

@@ -173,6 +173,7 @@ class CryoVITHeadTrainerB200:
         # accumulator row (19.58 -> 19.41 ms). gelu' in the input-gradient epilogues: slower than the separate pass, off.
         self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "1") != "0"
         self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
+        self.fuse_gn_gelu = os.environ.get("CVIT_TRAIN_FUSE_GN_GELU", "1") != "0"  # GELU backward inside the GroupNorm backward pass
         self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # 8-channel full-resolution convolutions on conv_rows8.cu
         self.rowsn = os.environ.get("CVIT_HEAD_ROWSN", "1") != "0"  # 16 / 32-channel convolutions on conv_rows.cu
         if state_dict is None:
@@ -411,6 +412,7 @@ class CryoVITHeadTrainerB200:
         dcur = self._buf("d_top", (D, H, W, 8))  # d(at) of the last block, or (fused) already d(zt)
         co.input_gradient(dz1, dcur, z_below=saved[3][10] if fuse_bwd else None)
         dcur_is_dz = fuse_bwd
+        dzun_ready = False
         self.launches += 14
         for bi in reversed(range(4)):
             c1, c2, c3, d1, d2 = BLOCKS[bi]
@@ -418,7 +420,9 @@ class CryoVITHeadTrainerB200:
             blk_in, n_out, stats, G, ca, za, aa, cb, zb, ab, zt, at, H, W = saved[bi]
             # transposed convolution: dcur is d(at) [D, 2H, 2W, c3]
             dzun = self._buf(f"dzun{bi}", (D, H, W, 4 * c3))
-            if dcur_is_dz:  # the producer's epilogue already applied gelu'(zt)
+            if dzun_ready:  # the GroupNorm backward of the block above already wrote d(zt), unshuffled, and the bias gradient
+                dzun_ready = False
+            elif dcur_is_dz:  # the producer's epilogue already applied gelu'(zt)
                 self._bias_grad(dcur, pre + "5.bias")
                 T.pixel_unshuffle(dcur, dzun)
                 dcur_is_dz = False
@@ -462,16 +466,33 @@ class CryoVITHeadTrainerB200:
             dn = self._buf(f"dn{bi}", (D, H, W, c1))
             ca.input_gradient(dza, dn)
             # GroupNorm
-            dblk = self._buf(f"dblk{bi}", (D, H, W, c1))
             dgam, dbet = torch.empty(c1, device=dev, dtype=F32), torch.empty(c1, device=dev, dtype=F32)
-            T.groupnorm_bwd(blk_in, dn, dblk, p[pre + "0.weight"], stats, dgam, dbet, G, 1e-3)
+            if self.fuse_gn_gelu:
+                # the block's input is gelu(z) of the layer below (a transposed convolution, or the projection): its GELU
+                # backward, bias gradient and (transposed convolution) pixel-unshuffle ride on the GroupNorm backward's pass
+                db = torch.zeros(c1, device=dev, dtype=F32)
+                if bi > 0:
+                    c3p = BLOCKS[bi - 1][2]
+                    dz_below = self._buf(f"dzun{bi - 1}", (D, H // 2, W // 2, 4 * c3p))
+                    T.groupnorm_bwd_gelu(blk_in, dn, dz_below, p[pre + "0.weight"], stats, dgam, dbet, G, 1e-3, saved[bi - 1][10], db, True)
+                    g[f"layers.{bi + 1}.layers.5.bias"].copy_(db)
+                    dzun_ready = True
+                else:
+                    dzp = self._buf("dz_proj", (vox, 1024))
+                    T.groupnorm_bwd_gelu(blk_in, dn, dzp.view(D, H, W, 1024), p[pre + "0.weight"], stats, dgam, dbet, G, 1e-3,
+                                         z_proj.view(D, H, W, 1024), db, False)
+                    g["layers.0.bias"].copy_(db)
+            else:
+                dblk = self._buf(f"dblk{bi}", (D, H, W, c1))
+                T.groupnorm_bwd(blk_in, dn, dblk, p[pre + "0.weight"], stats, dgam, dbet, G, 1e-3)
+                dcur = dblk
             g[pre + "0.weight"].copy_(dgam)
             g[pre + "0.bias"].copy_(dbet)
-            dcur = dblk
             self.launches += 14
         # projection (1x1x1): only the weight / bias gradient (the features are data)
         dzp = self._buf("dz_proj", (vox, 1024))
-        self._gelu_bwd_bias(dcur.view(vox, 1024), z_proj, dzp, "layers.0.bias")
+        if not self.fuse_gn_gelu:
+            self._gelu_bwd_bias(dcur.view(vox, 1024), z_proj, dzp, "layers.0.bias")
         if cfirst:
             dw0 = self._wgrad_rows(None, dzp, xt=feats.view(C, vox).to(BF16))
         else:

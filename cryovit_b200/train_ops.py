@@ -85,6 +85,16 @@ def groupnorm_bwd(x, dy, dx, gamma, stats, dgamma, dbeta, groups: int, eps: floa
               x.numel() // C, C, groups, float(eps), _stream())
 
 
+def groupnorm_bwd_gelu(x, dy, dz, gamma, stats, dgamma, dbeta, groups: int, eps: float, z, db, unshuffle: bool) -> None:
+    """GroupNorm backward fused with the GELU backward of the layer that produced x = gelu(z): dz = d(z), db += its column sums;
+    ``unshuffle``: x is [D, H2, W2, C] and dz is written as [D, H2/2, W2/2, 4C] (sub-pixel-major channels)."""
+    C = x.shape[-1]
+    W2 = x.shape[2] if unshuffle else 0
+    _lib.call("cvit_groupnorm_bwd_gelu_ndhwc_bf16", _chk(x, BF16, "x"), _chk(dy, BF16, "dy"), _chk(dz, BF16, "dz"),
+              _chk(gamma, F32, "gamma"), _chk(stats, F32, "stats"), _chk(dgamma, F32, "dgamma"), _chk(dbeta, F32, "dbeta"),
+              x.numel() // C, C, groups, float(eps), _chk(z, BF16, "z"), _chk(db, F32, "db"), W2, _stream())
+
+
 def pixel_unshuffle(src, dst) -> None:
     D, H2, W2, C = src.shape
     _lib.call("cvit_pixel_unshuffle_1x2x2_bf16", _chk(src, BF16, "src"), _chk(dst, BF16, "dst"), D, H2 // 2, W2 // 2, C, _stream())

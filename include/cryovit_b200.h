@@ -378,6 +378,13 @@ int cvit_colsum_bf16(const void* x, float* out, int64_t R, int64_t C, void* stre
  * here). */
 int cvit_groupnorm_bwd_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats,
                                   float* dgamma, float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, void* stream);
+/* The same followed by the GELU backward of the layer below in ONE pass: z (bf16, x's shape) is the pre-activation with
+ * x = gelu(z); dx receives d(z) = d(x) * gelu'(z), db (fp32 [C], zeroed by the caller) += its column sums (that layer's bias
+ * gradient), and with W2 > 0 (x a [D, H2, W2, C] volume, H2 and W2 even) it is stored pixel-unshuffled, [D, H2/2, W2/2, 4C]
+ * (the row layout of the transposed convolution's gradient GEMMs). z = null: exactly cvit_groupnorm_bwd_ndhwc_bf16. */
+int cvit_groupnorm_bwd_gelu_ndhwc_bf16(const void* x, const void* dy, void* dx, const float* gamma, const float* stats, float* dgamma,
+                                       float* dbeta, int64_t DHW, int64_t C, int64_t G, float eps, const void* z, float* db,
+                                       int64_t W2, void* stream);
 
 /* [D, 2H, 2W, C] -> [D, H, W, 4C], column (i*2+j)*C + c: the transposed convolution's output gradient laid out as the
  * rows of the GEMM that yields its input gradient. */

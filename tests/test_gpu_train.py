@@ -223,6 +223,35 @@ def test_groupnorm_backward(cuda_lib, C, G):
     assert _relerr(dx, xr.grad[0].t()) < 6e-3 and _relerr(dg, gr.grad) < 6e-3 and _relerr(db, br.grad) < 6e-3
 
 
+@pytest.mark.parametrize("D,H2,W2,C,G,unshuffle", [(3, 8, 12, 32, 8, True), (2, 6, 10, 128, 16, True), (4, 5, 7, 1024, 128, False)])
+def test_groupnorm_backward_fused_with_gelu_backward(cuda_lib, D, H2, W2, C, G, unshuffle):
+    """One pass == groupnorm_bwd, then gelu_bwd_colsum (+ pixel_unshuffle) of the layer below, up to the bf16 rounding of the
+    intermediate gradient that the fused pass no longer makes."""
+    from cryovit_b200 import ops, train_ops as T
+    z = (_rand(D, H2, W2, C, scale=1.5, seed=1)).bfloat16()
+    x = torch.empty_like(z)
+    T.gelu_fwd(z, x)
+    dy = _rand(D, H2, W2, C, seed=2).bfloat16()
+    gamma = 1.0 + 0.2 * _rand(C, seed=3)
+    y, stats = torch.empty_like(x), torch.zeros(2 * G, device=DEV)
+    ops.groupnorm_ndhwc(x, y, gamma, torch.zeros(C, device=DEV), stats, G, 1e-3)
+    dx, dg, db_ = torch.empty_like(x), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    T.groupnorm_bwd(x, dy, dx, gamma, stats, dg, db_, G, 1e-3)
+    dz, dbias = torch.empty_like(z), torch.zeros(C, device=DEV)
+    T.gelu_bwd(dx, z, dz, dbias)
+    if unshuffle:
+        ref = torch.empty(D, H2 // 2, W2 // 2, 4 * C, device=DEV, dtype=torch.bfloat16)
+        T.pixel_unshuffle(dz, ref)
+    else:
+        ref = dz
+    got = torch.full_like(ref, float("nan"))
+    dg2, db2, dbias2 = torch.empty(C, device=DEV), torch.empty(C, device=DEV), torch.zeros(C, device=DEV)
+    T.groupnorm_bwd_gelu(x, dy, got, gamma, stats, dg2, db2, G, 1e-3, z, dbias2, unshuffle)
+    assert _relerr(got, ref) < 4e-3 and (got.float() - ref.float()).abs().max() <= 2e-2 * ref.float().abs().max()
+    assert torch.allclose(dg2, dg, rtol=1e-4, atol=1e-4) and torch.allclose(db2, db_, rtol=1e-4, atol=1e-4)
+    assert (dbias2 - dbias).abs().max() <= 1e-2 * dbias.abs().max() + 1e-2
+
+
 def test_dice_backward_pixel_unshuffle_colsum_adamw(cuda_lib):
     from cryovit_b200 import ops, train_ops as T
     g = torch.Generator().manual_seed(5)
