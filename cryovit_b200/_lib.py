@@ -63,9 +63,9 @@ SIGNATURES: dict[str, list] = {
     "cvit_convT_1x2x2_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I32, P, P],
     "cvit_conv3d_wpackn_ndhwc_aux": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P, P],
     "cvit_conv3d_wpack8_aux": [P, P, P, P, I64, I64, I64, I32, P, P],
-    "cvit_conv3d_rows8": [P, P, P, P, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_rows8": [P, P, P, P, I64, I64, I64, I32, P, P, P],
     "cvit_conv3d_rows8_final": [P, P, P, P, P, I64, I64, I64, P],
-    "cvit_conv3d_rows_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I32, P, P],
+    "cvit_conv3d_rows_ndhwc": [P, P, P, P, I64, I64, I64, I64, I64, I64, I32, P, P, P],
     "cvit_gelu_fwd_bf16": [P, P, I64, P],
     "cvit_gelu_bwd_bf16": [P, P, P, I64, P],
     "cvit_gelu_bwd_colsum_bf16": [P, P, P, P, I64, I64, P],

@@ -53,7 +53,8 @@ struct RnArgs {
   const __nv_bfloat16* w_img;  // RnCfg::IMG_BYTES of this pass, host-arranged (cryovit_b200.head.rowsn_weight_image)
   const float* table;          // fp32 [64][tab_stride]: bias row by in-bounds tap masks; this pass's 16 columns start at table
   __nv_bfloat16* out;          // [D, H, W, out_stride], this pass's 16 channels start at out
-  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out), same indexing
+  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out); ACT_GELU_GRAD: the pre-activation z whose gelu' scales the result
+  float* db;                   // ACT_GELU_GRAD: fp32 [16] column sums of what is stored are added here (may be null)
   int D, H, W, dil, act, out_stride, tab_stride;
 };
 
@@ -211,6 +212,9 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
       hand_back(g);
     }
     uint32_t nd = 0;
+    float bsum[RN_CO];  // ACT_GELU_GRAD: column sums of everything this thread stores (the bias gradient of the layer below)
+#pragma unroll
+    for (int c = 0; c < RN_CO; ++c) bsum[c] = 0.f;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       int pair, r, ta, tb, T;
       unit_of(u, pair, r, ta, tb, T);
@@ -221,12 +225,28 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
           tile_of(pair, g, x0, yt0);
           const uint32_t t_seg = seg_addr(g);
           const int x = x0 + q * 32 + lane;
+          const bool live = to >= ta && to < tb;
+          constexpr int RMAX = (HT + 1) / 2;
+          // ACT_GELU_GRAD: this thread's z values of the plane about to be drained are requested BEFORE the wait for its MMAs,
+          // so the round trip to L2 / DRAM hides behind them (a load inside the drain is what made the W-packed kernels'
+          // gelu' epilogue slower than a separate pass, profiles/r02_train_notes.md)
+          uint4 zz[RMAX][2];
+          if (args.act == ACT_GELU_GRAD && live) {
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k) {
+              const int y = yt0 + rlo + k;
+              zz[k][0] = zz[k][1] = make_uint4(0u, 0u, 0u, 0u);
+              if (rlo + k < rhi && y < args.H && x < args.W) {
+                const uint4* zp = reinterpret_cast<const uint4*>(args.aux + (((size_t)zo * args.H + y) * args.W + x) * args.out_stride);
+                zz[k][0] = __ldg(zp);
+                zz[k][1] = __ldg(zp + 1);
+              }
+            }
+          }
           mbar_wait(bar_done + 8 * g, nd & 1);
           tcgen05_fence_after();
           // Read this half's rows of the finished plane, zero the slot and hand it back BEFORE the math and the stores: the
           // other tile's MMAs cover the drain's TMEM round trips, not its GELUs.
-          const bool live = to >= ta && to < tb;
-          constexpr int RMAX = (HT + 1) / 2;
           uint32_t v[RMAX][16];
           if (live) {
 #pragma unroll
@@ -262,6 +282,17 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
                   o[4 * c + 3] = __uint_as_float(v[k][4 * c + 3]) + tb4.w;
                 }
                 uint32_t pk[8];
+                if (args.act == ACT_GELU_GRAD) {
+                  const uint32_t zw[8] = {zz[k][0].x, zz[k][0].y, zz[k][0].z, zz[k][0].w, zz[k][1].x, zz[k][1].y, zz[k][1].z, zz[k][1].w};
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    pk[c] = act_gelu_grad_pair(o[2 * c], o[2 * c + 1], zw[c]);
+                    bsum[2 * c] += __uint_as_float(pk[c] << 16);  // sums over the STORED gradient
+                    bsum[2 * c + 1] += __uint_as_float(pk[c] & 0xffff0000u);
+                  }
+                  st_global_v8(args.out + off, pk);
+                  continue;
+                }
                 if (args.act == ACT_DUAL) {
 #pragma unroll
                   for (int c = 0; c < 8; ++c) pk[c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
@@ -278,6 +309,13 @@ __global__ void __launch_bounds__(RN_THREADS, 1) conv3d_rows_kernel(const __grid
             }
           }
         }
+      }
+    }
+    if (args.act == ACT_GELU_GRAD && args.db) {  // bias gradient: one shuffle tree and 16 atomics per warp
+#pragma unroll
+      for (int c = 0; c < RN_CO; ++c) {
+        const float tot = warp_sum(bsum[c]);
+        if (lane == 0) atomicAdd(args.db + c, tot);
       }
     }
   }
@@ -332,11 +370,12 @@ extern "C" int64_t cvit_conv3d_rows_weight_bytes(int64_t Cin) {
 }
 
 // out (bf16 [D,H,W,Cout]) = conv3d(x bf16 [D,H,W,Cin], 3x3x3, "same", dilation (dil,1,1)) + bias_table row of the voxel, act as
-// the other *_aux entry points (0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it). Cin, Cout in {16, 32};
+// the other *_aux entry points (0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it, 3 out = result * gelu'(aux), with
+// db (fp32 [Cout], may be null) += the column sums of what is stored: the bias gradient of the layer below). Cin, Cout in {16, 32};
 // w_img: Cout / 16 images of cvit_conv3d_rows_weight_bytes(Cin) bytes each (output channels 16 h .. 16 h + 15);
 // bias_table fp32 [64][Cout] (the *_tab layout: a plain bias = 64 equal rows).
 extern "C" int cvit_conv3d_rows_ndhwc(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
-                                      int64_t W, int64_t Cin, int64_t Cout, int64_t dil, int act, void* aux, void* stream) {
+                                      int64_t W, int64_t Cin, int64_t Cout, int64_t dil, int act, void* aux, float* db, void* stream) {
   if (!x || !w_img || !bias_table || !out || D <= 0 || H <= 0 || W <= 0 || dil <= 0) {
     set_error("conv3d_rows: bad arguments (D=%lld H=%lld W=%lld Cin=%lld Cout=%lld dil=%lld)", (long long)D, (long long)H,
               (long long)W, (long long)Cin, (long long)Cout, (long long)dil);
@@ -347,10 +386,10 @@ extern "C" int cvit_conv3d_rows_ndhwc(const void* x, const void* w_img, const fl
               (long long)Cin, (long long)Cout);
     return CVIT_ERR_UNSUPPORTED;
   }
-  if (act < 0 || act > 2 || (act == 2 && !aux) ||
+  if (act < 0 || act > 3 || (act >= 2 && !aux) ||
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_img) | reinterpret_cast<uintptr_t>(out) |
         reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(bias_table)) & 15u)) {
-    set_error("conv3d_rows: act must be 0, 1 or 2 (with aux); x, w_img, bias_table, out and aux 16-byte aligned");
+    set_error("conv3d_rows: act must be 0, 1, 2 or 3 (2, 3 with aux); x, w_img, bias_table, out and aux 16-byte aligned");
     return CVIT_ERR_INVALID;
   }
   const int64_t img = cvit_conv3d_rows_weight_bytes(Cin);
@@ -360,6 +399,7 @@ extern "C" int cvit_conv3d_rows_ndhwc(const void* x, const void* w_img, const fl
     a.table = bias_table + h * RN_CO;
     a.out = static_cast<__nv_bfloat16*>(out) + h * RN_CO;
     a.aux = aux ? static_cast<__nv_bfloat16*>(aux) + h * RN_CO : nullptr;
+    a.db = db ? db + h * RN_CO : nullptr;
     a.D = (int)D;
     a.H = (int)H;
     a.W = (int)W;

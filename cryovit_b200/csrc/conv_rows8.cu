@@ -67,7 +67,8 @@ struct CrArgs {
   const __nv_bfloat16* w_img;  // CR_IMG_BYTES, host-arranged (cryovit_b200.head.rows8_weight_image)
   const float* bias;           // [8] (FINAL: only bias[0] is used)
   __nv_bfloat16* out;          // [D, H, W, 8]
-  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out)
+  __nv_bfloat16* aux;          // act = ACT_DUAL: gelu(out); ACT_GELU_GRAD: the pre-activation z whose gelu' scales the result
+  float* db;                   // ACT_GELU_GRAD: fp32 [8] column sums of what is stored are added here (may be null)
   float* logits;               // FINAL: [D, H, W] clipped logits (may be null)
   float* probs;                // FINAL: [D, H, W] sigmoid of the clipped logits (may be null)
   int D, H, W, act;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
       hand_back(g);
     }
     uint32_t nd = 0;  // planes drained per segment (phase of bar_done)
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // ACT_GELU_GRAD: column sums of what this thread stores
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       int xp, yt0, za, zb;
       unit_of(u, xp, yt0, za, zb);
@@ -231,6 +233,16 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
         for (int g = 0; g < 2; ++g) {
           const uint32_t t_seg = seg_addr(g);
           const int x = xp + g * CR_SEG + q * 32 + lane;
+          // ACT_GELU_GRAD: the z values of the plane about to be drained are requested before the wait for its MMAs
+          uint4 zz[RH];
+          if (!FINAL && args.act == ACT_GELU_GRAD && zo >= za && zo < zb) {
+#pragma unroll
+            for (int r = 0; r < RH; ++r) {
+              const int y = yt0 + half * RH + r;
+              zz[r] = make_uint4(0u, 0u, 0u, 0u);
+              if (y < args.H && x < args.W) zz[r] = __ldg(reinterpret_cast<const uint4*>(args.aux + (((size_t)zo * args.H + y) * args.W + x) * 8));
+            }
+          }
           mbar_wait(bar_done + 8 * g, nd & 1);
           tcgen05_fence_after();
           // Read this half's rows of the finished plane, zero the slot and hand it back BEFORE the math and the stores: the other
@@ -265,6 +277,18 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
                 float o[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[r][c]) + bias[c];
+                if (args.act == ACT_GELU_GRAD) {
+                  const uint32_t zw[4] = {zz[r].x, zz[r].y, zz[r].z, zz[r].w};
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    pk[c] = act_gelu_grad_pair(o[2 * c], o[2 * c + 1], zw[c]);
+                    bsum[2 * c] += __uint_as_float(pk[c] << 16);  // sums over the STORED gradient
+                    bsum[2 * c + 1] += __uint_as_float(pk[c] & 0xffff0000u);
+                  }
+                  *reinterpret_cast<uint4*>(args.out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  continue;
+                }
                 if (args.act == ACT_DUAL)
                   *reinterpret_cast<uint4*>(args.out + off) =
                       make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
@@ -281,6 +305,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv3d_rows8_kernel(const __gri
             }
           }
         }
+      }
+    }
+    if (!FINAL && args.act == ACT_GELU_GRAD && args.db) {  // bias gradient: one shuffle tree and 8 atomics per warp
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float tot = warp_sum(bsum[c]);
+        if (lane == 0) atomicAdd(args.db + c, tot);
       }
     }
   }
@@ -301,7 +332,7 @@ using namespace cvit;
 extern "C" int64_t cvit_conv3d_rows8_weight_bytes() { return CR_IMG_BYTES; }
 
 // out (bf16 [D,H,W,8]) = conv3d(x bf16 [D,H,W,8], 3x3x3, "same", dilation 1) + bias, act: 0 none, 1 GELU, 2 out = pre-activation
-// and aux = GELU of it (ptx.cuh ACT_*). w_img: cvit_conv3d_rows8_weight_bytes() bytes in the layout of
+// and aux = GELU of it, 3 out = result * gelu'(aux) with db (fp32 [8], may be null) += the column sums of what is stored (ptx.cuh ACT_*). w_img: cvit_conv3d_rows8_weight_bytes() bytes in the layout of
 // cryovit_b200.head.rows8_weight_image. W must be a multiple of 8.
 static int rows8_launch(const void* x, CrArgs a, bool final, cudaStream_t stream) {
   CUtensorMap tmX;
@@ -345,10 +376,10 @@ static int rows8_check(const void* x, const void* w_img, const float* bias, int6
 }
 
 extern "C" int cvit_conv3d_rows8(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H, int64_t W,
-                                 int act, void* aux, void* stream) {
+                                 int act, void* aux, float* db, void* stream) {
   if (int rc = rows8_check(x, w_img, bias, D, H, W)) return rc;
-  if (!out || act < 0 || act > 2 || (act == 2 && !aux) || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(aux)) & 15u)) {
-    set_error("conv3d_rows8: act must be 0, 1 or 2 (with aux); out and aux 16-byte aligned bf16 [D,H,W,8]");
+  if (!out || act < 0 || act > 3 || (act >= 2 && !aux) || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(aux)) & 15u)) {
+    set_error("conv3d_rows8: act must be 0, 1, 2 or 3 (2, 3 with aux); out and aux 16-byte aligned bf16 [D,H,W,8]");
     return CVIT_ERR_INVALID;
   }
   CrArgs a;
@@ -356,6 +387,7 @@ extern "C" int cvit_conv3d_rows8(const void* x, const void* w_img, const float* 
   a.bias = bias;
   a.out = static_cast<__nv_bfloat16*>(out);
   a.aux = static_cast<__nv_bfloat16*>(aux);
+  a.db = db;
   a.logits = nullptr;
   a.probs = nullptr;
   a.D = (int)D;
@@ -379,6 +411,7 @@ extern "C" int cvit_conv3d_rows8_final(const void* x, const void* w_img, const f
   a.bias = bias;
   a.out = nullptr;
   a.aux = nullptr;
+  a.db = nullptr;
   a.logits = logits;
   a.probs = probs;
   a.D = (int)D;

@@ -296,7 +296,7 @@ def rows_supported(cin: int, cout: int) -> bool:
     return cin in (16, 32) and cout in (16, 32)
 
 
-def conv3d_rows(x, w_img, table, out, dil: int, act=True, aux=None) -> None:
+def conv3d_rows(x, w_img, table, out, dil: int, act=True, aux=None, db=None) -> None:
     """Narrow-layer (16 / 32 channels) dilated conv + bias-table row (+ GELU), one voxel per MMA row (csrc/conv_rows.cu)."""
     D, H, W, Cin = x.shape
     Cout = out.shape[-1]
@@ -305,17 +305,17 @@ def conv3d_rows(x, w_img, table, out, dil: int, act=True, aux=None) -> None:
         raise _lib.CryovitB200Error("conv3d_rows: weight image / bias table do not match the layer")
     act, auxp = _aux(act, aux, out)
     _lib.call("cvit_conv3d_rows_ndhwc", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(table, F32, "table"),
-              _chk(out, BF16, "out"), D, H, W, Cin, Cout, dil, act, auxp, _stream())
+              _chk(out, BF16, "out"), D, H, W, Cin, Cout, dil, act, auxp, _chk(db, F32, "db") if db is not None else None, _stream())
 
 
-def conv3d_rows8(x, w_img, bias8, out, act=True, aux=None) -> None:
+def conv3d_rows8(x, w_img, bias8, out, act=True, aux=None, db=None) -> None:
     """output_layer.0 (8 -> 8, k3, dilation 1) + bias (+ GELU), one voxel per MMA row (csrc/conv_rows8.cu); W % 8 == 0."""
     D, H, W, Cin = x.shape
     if Cin != 8 or w_img.numel() * 2 != _lib.load().cvit_conv3d_rows8_weight_bytes():
         raise _lib.CryovitB200Error("conv3d_rows8: needs 8 input channels and the rows8 weight image")
     act, auxp = _aux(act, aux, out)
     _lib.call("cvit_conv3d_rows8", _chk(x, BF16, "x"), _chk(w_img, BF16, "w_img"), _chk(bias8, F32, "bias8"),
-              _chk(out, BF16, "out"), D, H, W, act, auxp, _stream())
+              _chk(out, BF16, "out"), D, H, W, act, auxp, _chk(db, F32, "db") if db is not None else None, _stream())
 
 
 def conv3d_rows8_final(x, w_img, bias1, logits=None, probs=None) -> None:

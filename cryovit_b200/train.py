@@ -73,10 +73,10 @@ class _Conv:
     def __init__(self, trainer, key: str, cin: int, cout: int, dil: int, pre=None):
         self.tr, self.key, self.cin, self.cout, self.dil, self.pre = trainer, key, cin, cout, dil, pre
 
-    def run(self, tag, x, wfn, bias, out, cin, cout, dil, act=0, aux=None):
+    def run(self, tag, x, wfn, bias, out, cin, cout, dil, act=0, aux=None, db=None):
         """wfn: fp32 parameter -> the [cout, cin, 3,3,3] weight of THIS convolution (identity, or flip + transpose).
         act / aux: the fused element-wise pass of the epilogue (2: out = z, aux = gelu(z); 3: out = y * gelu'(aux))."""
-        if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 8 == 0 and act != 3 and self.tr.rows8:
+        if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 8 == 0 and self.tr.rows8:
             # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): one voxel per MMA row,
             # partial sums meeting in tensor memory (csrc/conv_rows8.cu)
             b = bias.contiguous() if bias is not None else torch.zeros(8, device=x.device, dtype=F32)
@@ -85,7 +85,7 @@ class _Conv:
                 ops.conv3d_rows8(x, op, b, out, act=0)
                 T.gelu_fwd(out, aux)
             else:
-                ops.conv3d_rows8(x, op, b, out, act=act, aux=aux)
+                ops.conv3d_rows8(x, op, b, out, act=act, aux=aux, db=db)
             return
         if cin == 8 and cout == 8 and dil == 1 and x.shape[2] % 16 == 0:
             # the full-resolution 8-channel layers (output_layer.0 forward, both input gradients there): W-packed kernel
@@ -99,11 +99,11 @@ class _Conv:
             else:
                 ops.conv3d_wpack8_gelu(x, op, b, out, act=act, aux=aux)
             return
-        if ops.rows_supported(cin, cout) and act != 3 and self.tr.rowsn:
+        if ops.rows_supported(cin, cout) and self.tr.rowsn:
             # 16- / 32-channel layers (forward and input gradients alike): one voxel per tensor-core row (csrc/conv_rows.cu)
             b = bias if bias is not None else torch.zeros(cout, device=x.device, dtype=F32)
             op = self.tr._pk(f"{self.key}/{tag}/rowsn", self.key, lambda w: rowsn_weight_image(wfn(w)))
-            ops.conv3d_rows(x, op, b.repeat(64).contiguous(), out, dil, act=act, aux=aux)
+            ops.conv3d_rows(x, op, b.repeat(64).contiguous(), out, dil, act=act, aux=aux, db=db)
             return
         halo = cin in (8, 16, 32)
         cp = (32 if cout > 16 else 16) if halo else max(32, cout)
@@ -129,12 +129,20 @@ class _Conv:
         """z = conv(x) + bias; with ``a`` also a = gelu(z) from the same epilogue."""
         self.run("f", x, self._w, bias, z, self.cin, self.cout, self.dil, 2 if a is not None else 0, a)
 
-    def input_gradient(self, dz, dx, z_below=None):
+    def fuses_gelu_grad(self, dz) -> bool:
+        """Does the input-gradient kernel of this layer apply gelu'(z) and sum the bias gradient itself (the one-voxel-per-row
+        kernels: z is prefetched before the accumulator wait)?"""
+        if self.cin == 8 and self.cout == 8:
+            return self.dil == 1 and dz.shape[2] % 8 == 0 and self.tr.rows8
+        return ops.rows_supported(self.cout, self.cin) and self.tr.rowsn
+
+    def input_gradient(self, dz, dx, z_below=None, db=None):
         """dx = conv^T(dz); with ``z_below`` (the pre-activation whose GELU produced this convolution's input) the
-        epilogue multiplies by gelu'(z_below): dx is then the gradient of that pre-activation."""
+        epilogue multiplies by gelu'(z_below): dx is then the gradient of that pre-activation, and ``db`` (fp32, zeroed;
+        only with ``fuses_gelu_grad``) receives its column sums."""
         # [cin, cout, 3,3,3]: the gradient convolution's weight
         self.run("g", dz, lambda w: self._w(w).flip(2, 3, 4).transpose(0, 1).contiguous(), None, dx, self.cout, self.cin, self.dil,
-                 3 if z_below is not None else 0, z_below)
+                 3 if z_below is not None else 0, z_below, db)
 
 
 class _KeepAlivePool(dict):
@@ -174,6 +182,10 @@ class CryoVITHeadTrainerB200:
         self.fuse_store_bound = os.environ.get("CVIT_TRAIN_FUSE_STORE_BOUND", "1") != "0"
         self.fuse_backward = os.environ.get("CVIT_TRAIN_FUSE_BWD", "0") != "0"
         self.fuse_gn_gelu = os.environ.get("CVIT_TRAIN_FUSE_GN_GELU", "1") != "0"  # GELU backward inside the GroupNorm backward pass
+        # ... and inside the rows kernels' drains (z prefetched before the accumulator wait, bias gradient in registers): correct,
+        # measured SLOWER in the step (19.69 vs 19.22 ms: the 8 -> 8 drain grows by 0.27 ms for a 0.39 ms pass saved, but the
+        # MMAs it used to hide behind no longer cover it), off by default (profiles/r02_train_notes.md)
+        self.fuse_dgrad_gelu = os.environ.get("CVIT_TRAIN_FUSE_DGRAD_GELU", "0") != "0"
         self.rows8 = os.environ.get("CVIT_HEAD_ROWS8", "1") != "0"  # 8-channel full-resolution convolutions on conv_rows8.cu
         self.rowsn = os.environ.get("CVIT_HEAD_ROWSN", "1") != "0"  # 16 / 32-channel convolutions on conv_rows.cu
         if state_dict is None:
@@ -264,6 +276,18 @@ class CryoVITHeadTrainerB200:
         db = torch.zeros(z.shape[-1], device=self.device, dtype=F32)
         T.gelu_bwd(da, z, dz, db)
         self.g[key_b].copy_(db)
+
+    def _dgrad_gelu(self, conv, dz, z_below, dz_out, key_b, tmp_name):
+        """dz_out = conv^T(dz) * gelu'(z_below) (the gradient of the pre-activation below ``conv``) and that layer's bias
+        gradient: inside the input-gradient kernel where it prefetches z (csrc/conv_rows*.cu), else as a second pass."""
+        if self.fuse_dgrad_gelu and conv.fuses_gelu_grad(dz):
+            db = torch.zeros(z_below.shape[-1], device=self.device, dtype=F32)
+            conv.input_gradient(dz, dz_out, z_below=z_below, db=db)
+            self.g[key_b].copy_(db)
+        else:
+            da = self._buf(tmp_name, tuple(dz_out.shape))
+            conv.input_gradient(dz, da)
+            self._gelu_bwd_bias(da, z_below, dz_out, key_b)
 
     def _bias_grad(self, dz, key_b):
         """The bias gradient alone (column sums of dz), for layers whose gelu' was applied by the producing epilogue."""
@@ -405,9 +429,7 @@ class CryoVITHeadTrainerB200:
             c_out2.input_gradient(dl8, dz1, z_below=z1)
             self._bias_grad(dz1, "output_layer.0.bias")
         else:
-            da1 = self._buf("da_o0", (D, H, W, 8))
-            c_out2.input_gradient(dl8, da1)
-            self._gelu_bwd_bias(da1, z1, dz1, "output_layer.0.bias")
+            self._dgrad_gelu(c_out2, dl8, z1, dz1, "output_layer.0.bias", "da_o0")
         self._wgrad_conv(cur, dz1, 1, "output_layer.0.weight")
         dcur = self._buf("d_top", (D, H, W, 8))  # d(at) of the last block, or (fused) already d(zt)
         co.input_gradient(dz1, dcur, z_below=saved[3][10] if fuse_bwd else None)
@@ -458,10 +480,8 @@ class CryoVITHeadTrainerB200:
                 # conv b
                 self._gelu_bwd_bias(dab, zb, dzb, pre + "3.bias")
                 self._wgrad_conv(aa, dzb, d2, pre + "3.weight")
-                daa = self._buf(f"daa{bi}", (D, H, W, c2))
-                cb.input_gradient(dzb, daa)
                 # conv a
-                self._gelu_bwd_bias(daa, za, dza, pre + "1.bias")
+                self._dgrad_gelu(cb, dzb, za, dza, pre + "1.bias", f"daa{bi}")
             self._wgrad_conv(n_out, dza, d1, pre + "1.weight")
             dn = self._buf(f"dn{bi}", (D, H, W, c1))
             ca.input_gradient(dza, dn)

@@ -262,10 +262,12 @@ int cvit_conv3d_wpack8_final(const void* x, const void* w_img, const float* bias
  * chunks -- the three column taps -- are the same bytes one voxel further on; the nine (plane, row) partial sums of an
  * output voxel meet in sliding windows of tensor memory. x, out (and aux) bf16 [D,H,W,8], W a multiple of 8; bias fp32 [8];
  * w_img bf16, cvit_conv3d_rows8_weight_bytes() bytes (cryovit_b200.head.rows8_weight_image);
- * act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it. */
+ * act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it, 3 out = result * gelu'(aux) (an input-gradient convolution
+ * handing on the gradient of the pre-activation aux; the z values are prefetched before the accumulator wait) with
+ * db (fp32 [8], may be null) += the column sums of what is stored: the bias gradient of the layer below. */
 int64_t cvit_conv3d_rows8_weight_bytes(void);
 int cvit_conv3d_rows8(const void* x, const void* w_img, const float* bias, void* out, int64_t D, int64_t H, int64_t W,
-                      int act, void* aux, void* stream);
+                      int act, void* aux, float* db, void* stream);
 /* output_layer.2 (8 -> 1) the same way (w_img: the image of the [1,8,3,3,3] weight, bias fp32 [1]) + clip(-5, 5) -> logits
  * fp32 [D,H,W] and/or their sigmoid -> probs (cryovit.py:39,49); either pointer may be null. */
 int cvit_conv3d_rows8_final(const void* x, const void* w_img, const float* bias, float* logits, float* probs, int64_t D,
@@ -276,10 +278,10 @@ int cvit_conv3d_rows8_final(const void* x, const void* w_img, const float* bias,
  * through tensor memory, the planes of one dilation residue class walked like a dilation-1 stack. Cin, Cout in {16, 32};
  * x bf16 [D,H,W,Cin], out (aux) bf16 [D,H,W,Cout]; bias_table fp32 [64][Cout] (the *_tab layout; a plain bias = 64 equal rows);
  * w_img: Cout / 16 images of cvit_conv3d_rows_weight_bytes(Cin) bytes (cryovit_b200.head.rowsn_weight_image);
- * act: 0 none, 1 GELU, 2 out = pre-activation and aux = GELU of it. */
+ * act / aux / db as cvit_conv3d_rows8 (db fp32 [Cout]). */
 int64_t cvit_conv3d_rows_weight_bytes(int64_t Cin);
 int cvit_conv3d_rows_ndhwc(const void* x, const void* w_img, const float* bias_table, void* out, int64_t D, int64_t H,
-                           int64_t W, int64_t Cin, int64_t Cout, int64_t dil, int act, void* aux, void* stream);
+                           int64_t W, int64_t Cin, int64_t Cout, int64_t dil, int act, void* aux, float* db, void* stream);
 
 /* ConvTranspose3d(Cin -> Cout, kernel (1,2,2), stride (1,2,2)) + bias + GELU (models/cryovit.py:74-77) as a
  * per-voxel GEMM with a pixel-shuffle store.  w_sub bf16 [4 * Cout, Cin], row (i*2+j)*Cout + co;

@@ -649,3 +649,27 @@ def test_conv3d_rows(cuda_lib, D, H, W, Cin, Cout, dil, act):
         _close(out, z, atol=2e-2, rtol=2e-2, what="rows pre-activation")
         if act == 2:
             _close(aux, F.gelu(z), atol=2e-2, rtol=2e-2, what="rows aux")
+
+
+@pytest.mark.parametrize("kind,D,H,W,Cin,Cout,dil", [("rows8", 5, 20, 136, 8, 8, 1), ("rows", 9, 10, 136, 32, 16, 2), ("rows", 6, 9, 40, 16, 32, 3),
+                                                     ("rows", 20, 6, 128, 32, 32, 4)])
+def test_conv3d_rows_gelu_grad(cuda_lib, kind, D, H, W, Cin, Cout, dil):
+    """act 3 of the one-voxel-per-row kernels: out = conv(x) * gelu'(z) with z prefetched before the accumulator wait, and the
+    column sums of what is stored (the bias gradient of the layer below) from the same kernel."""
+    from cryovit_b200 import ops, train_ops as T
+    from cryovit_b200.head import rows8_weight_image, rowsn_weight_image
+    x = _rand(D, H, W, Cin, seed=1).bfloat16()
+    w = (_rand(Cout, Cin, 3, 3, 3, seed=2) * (27 * Cin) ** -0.5).bfloat16()
+    z = (_rand(D, H, W, Cout, seed=4) * 1.5).bfloat16()
+    out = torch.full((D, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    db = torch.zeros(Cout, device=DEV)
+    zero = torch.zeros(Cout, device=DEV)
+    if kind == "rows8":
+        ops.conv3d_rows8(x, rows8_weight_image(w).bfloat16(), zero, out, act=3, aux=z, db=db)
+    else:
+        ops.conv3d_rows(x, rowsn_weight_image(w).bfloat16(), zero.repeat(64).contiguous(), out, dil, act=3, aux=z, db=db)
+    y = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), None, padding="same", dilation=(dil, 1, 1))[0].permute(1, 2, 3, 0)
+    ref, dbr = torch.empty_like(out), torch.zeros(Cout, device=DEV)
+    T.gelu_bwd(y.bfloat16().contiguous(), z, ref, dbr)
+    _close(out, ref, atol=2e-2, rtol=2e-2, what="rows gelu-grad")
+    assert (db - dbr).abs().max() <= 2e-2 * dbr.abs().max() + 5e-2, (db, dbr)
