@@ -24,6 +24,8 @@
 // One MMA (M 64, N 80, K 16 voxels) per 16 voxels of a row for all 27 taps: 2.1 M MMAs per launch over 148 SMs. The
 // accumulator (80 TMEM columns) lives for the whole kernel; one red.global.add pass per CTA at the end.
 // One CTA per SM, 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warp 4 the final read-out.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -430,6 +432,240 @@ static int launch_wgrad_tcn(const void* x, const void* dz, float* dw, int64_t D,
   return check_launch("wgrad_tcn_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same kernel fed differently (default): TMA moves WHOLE ROWS of both volumes (boxes {all channels, voxels, rows}: 32- / 64-byte
+// inner extents, four boxes per stage) into a raw staging buffer, and the four otherwise idle warps de-interleave them into the
+// 8-channel chunk arrays with LDS.128 / STS.128 -- writing each x chunk to its three column-tap arrays, so x is fetched once
+// instead of three times. The chunk boxes of wgrad_tcn_kernel (16-byte inner extent) arrive at ~14 B/clk/SM and bound it.
+template <int CIN, int COUT, int R, int KSEG, int RS>
+struct WtsCfg {
+  static constexpr int NCX = CIN / 8, NCZ = COUT / 8;
+  static constexpr int S = KSEG * 16;
+  static constexpr int XA = R * 3 * NCX, ZA = (R + 2) * 3 * NCZ;
+  static constexpr int ARR_STAGE = (XA + ZA) * S;
+  static constexpr int RAW_X = (R * (KSEG + 2) * CIN * 2 + 127) / 128 * 128;
+  static constexpr int RAW_ZP = (R + 2) * KSEG * COUT * 2;  // one plane's rows
+  static constexpr int RAW_STAGE = RAW_X + 3 * RAW_ZP;
+  // RS raw stages: the kernel is bound by bytes in flight x L2 latency (~2 us under load: 2 x 33 KB per SM gave 3.9 TB/s
+  // aggregate, exactly what the chunk-box version reached), so the raw ring is as deep as shared memory allows
+  static constexpr int SMEM = 2 * ARR_STAGE + RS * RAW_STAGE + 256 + 1024;
+  static constexpr int MROWS = 24 * NCX;
+  static constexpr int MM = MROWS <= 64 ? 64 : 128;
+  static constexpr int N = 72 * NCZ, NSPLIT = N > 256 ? 2 : 1, NH = N / NSPLIT;
+  static constexpr int TMEM_COLS = N <= 128 ? 128 : N <= 256 ? 256 : 512;
+  static constexpr uint32_t TX_BYTES = R * (KSEG + 2) * CIN * 2 + 3 * RAW_ZP;
+  static_assert(NCX >= 2 && NCZ >= 2 && NH % 16 == 0 && NH <= 256 && SMEM <= 232448 && RAW_ZP % 128 == 0, "unsupported layer");
+  static_assert(16 <= XA - 3 * NCX * (R - 1) + ZA, "M = 128 over-reads 16 arrays from the last row's first");
+};
+
+template <int CIN, int COUT, int R, int KSEG, int RS>
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad_tcs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, const WtArgs args) {
+  using Cfg = WtsCfg<CIN, COUT, R, KSEG, RS>;
+  constexpr int S = Cfg::S, NCX = Cfg::NCX, NCZ = Cfg::NCZ;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sArr = smem_base, sRaw = smem_base + 2 * Cfg::ARR_STAGE, sBar = sRaw + RS * Cfg::RAW_STAGE;
+  const uint32_t raw_full = sBar, raw_empty = sBar + 8 * RS, arr_full = sBar + 16 * RS, arr_empty = arr_full + 16, bar_done = arr_full + 32,
+                 tmem_slot = arr_full + 40;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int segs = (args.W + KSEG - 1) / KSEG, hblocks = (args.H + R - 1) / R;
+  const int num_blocks = args.D * hblocks * segs;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmZ);
+    for (int s = 0; s < RS; ++s) {
+      mbar_init(raw_full + 8 * s, 1);
+      mbar_init(raw_empty + 8 * s, 4);   // one arrival per copy warp
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(arr_full + 8 * s, 4);
+      mbar_init(arr_empty + 8 * s, 1);   // the MMAs that read the arrays have retired
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: four boxes of whole rows per stage
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+        const int seg = blk % segs, hb = (blk / segs) % hblocks, z0 = blk / (segs * hblocks);
+        const int x0 = seg * KSEG, yb = hb * R;
+        const uint32_t s = it % RS, dst = sRaw + s * Cfg::RAW_STAGE, bar = raw_full + 8 * s;
+        mbar_wait(raw_empty + 8 * s, ((it / RS) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar, Cfg::TX_BYTES);
+        tma_load_4d(dst, &tmX, bar, 0, x0 - 1, yb, z0);  // [R][KSEG + 2][CIN]
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)                   // [R + 2][KSEG][COUT] of plane z0 - (kd - 1) dil
+          tma_load_4d(dst + Cfg::RAW_X + kd * Cfg::RAW_ZP, &tmZ, bar, 0, x0, yb - 1, z0 - (kd - 1) * args.dil);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::MM, Cfg::NH) | (1u << 15) | (1u << 16);  // A and B MN-major
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      const uint32_t s = it & 1;
+      mbar_wait(arr_full + 8 * s, (it >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sX = sArr + s * Cfg::ARR_STAGE, sZ = sX + Cfg::XA * S;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint64_t ad = wt_desc(sX + r * 3 * NCX * S, 128, S);
+#pragma unroll
+          for (int h = 0; h < Cfg::NSPLIT; ++h) {
+            const uint64_t bd = wt_desc(sZ + (r * 3 * NCZ + h * (Cfg::NH / 8)) * S, 128, S);
+#pragma unroll
+            for (int ks = 0; ks < KSEG / 16; ++ks)
+              umma_bf16(tmem_base + h * Cfg::NH, ad + 16 * ks, bd + 16 * ks, idesc, (it | r | ks) != 0);
+          }
+        }
+        umma_commit(arr_empty + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(bar_done);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ warps 2-5: raw rows -> chunk arrays, then the read-out
+    {
+      const int t = threadIdx.x - 64;
+      uint32_t it = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+        const uint32_t s = it & 1, rs = it % RS;
+        const uint32_t rX = sRaw + rs * Cfg::RAW_STAGE, rZ = rX + Cfg::RAW_X;
+        const uint32_t aX = sArr + s * Cfg::ARR_STAGE, aZ = aX + Cfg::XA * S;
+        mbar_wait(raw_full + 8 * rs, (it / RS) & 1);
+        mbar_wait(arr_empty + 8 * s, ((it >> 1) & 1) ^ 1u);
+        // x: chunk (voxel v = x0 - 1 + .., channel block j) of row r -> arrays (r, kw, j) at voxel v - kw. A thread keeps its
+        // channel block and strides over the voxels (no division per chunk: the copy is instruction-bound otherwise).
+        {
+          const int j = t % NCX;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+#pragma unroll 2
+            for (int v = t / NCX; v < KSEG + 2; v += 128 / NCX) {
+              uint32_t a, b, cc, d;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d)
+                           : "r"(rX + ((r * (KSEG + 2) + v) * NCX + j) * 16));
+              const uint32_t dst = aX + (r * 3 * NCX + j) * S + v * 16;  // array (r, kw = 0, j), voxel v
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const int k = v - kw;
+                if (k >= 0 && k < KSEG)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kw * (NCX * S - 16)), "r"(a), "r"(b), "r"(cc), "r"(d) : "memory");
+              }
+            }
+          }
+        }
+        // dz: raw [kd][rr][v][jz] -> array ((rr * 3 + kd) * NCZ + jz), voxel v: a row is KSEG * NCZ = 128 chunks, one per thread
+        {
+          static_assert(KSEG * NCZ == 128, "one dz chunk per copy thread and row");
+          const int v = t / NCZ, jz = t % NCZ;
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+            for (int rr = 0; rr < R + 2; ++rr) {
+              uint32_t a, b, cc, d;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d)
+                           : "r"(rZ + ((kd * (R + 2) + rr) * 128 + t) * 16));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aZ + ((rr * 3 + kd) * NCZ + jz) * S + v * 16), "r"(a), "r"(b),
+                           "r"(cc), "r"(d)
+                           : "memory");
+            }
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(arr_full + 8 * s);
+          mbar_arrive(raw_empty + 8 * rs);
+        }
+      }
+    }
+    const int q = warp & 3;
+    mbar_wait(bar_done, 0);
+    tcgen05_fence_after();
+    const int m = Cfg::MM == 64 ? (lane < 16 ? q * 16 + lane : Cfg::MROWS) : q * 32 + lane;
+    if ((Cfg::MM == 64 ? q * 16 : q * 32) < Cfg::MROWS) {
+      const int tt = m & 7, j = (m >> 3) % NCX, kw = m / (8 * NCX), ci = j * 8 + tt;
+#pragma unroll 1
+      for (int c2 = 0; c2 < Cfg::N / 16; ++c2) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c2 * 16, v);
+        tmem_ld_wait();
+        if (m < Cfg::MROWS) {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int c = 2 * c2 + hb;
+            const int jz = c % NCZ, rest = c / NCZ, yr = rest / 3, kd = rest - 3 * yr, kh = 2 - yr;
+            float* dst = args.dw + ((size_t)(((kd * 3 + kh) * 3 + kw) * COUT + jz * 8) * CIN + ci);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dst + (size_t)i * CIN, __uint_as_float(v[hb * 8 + i]));
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int CIN, int COUT, int R, int KSEG, int RS>
+static int launch_wgrad_tcs(const void* x, const void* dz, float* dw, int64_t D, int64_t H, int64_t W, int64_t dil, cudaStream_t stream) {
+  using Cfg = WtsCfg<CIN, COUT, R, KSEG, RS>;
+  CUtensorMap tmX, tmZ;
+  uint64_t dimsX[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+  uint64_t strX[4] = {0, (uint64_t)CIN * 2, (uint64_t)W * CIN * 2, (uint64_t)H * W * CIN * 2};
+  uint64_t dimsZ[4] = {(uint64_t)COUT, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+  uint64_t strZ[4] = {0, (uint64_t)COUT * 2, (uint64_t)W * COUT * 2, (uint64_t)H * W * COUT * 2};
+  uint32_t boxX[4] = {(uint32_t)CIN, KSEG + 2, R, 1}, boxZ[4] = {(uint32_t)COUT, KSEG, R + 2, 1};
+  int rc = encode_tmap(&tmX, TmapDtype::BF16, 4, x, dimsX, strX, boxX, 0);
+  if (rc) return rc;
+  rc = encode_tmap(&tmZ, TmapDtype::BF16, 4, dz, dimsZ, strZ, boxZ, 0);
+  if (rc) return rc;
+  auto kern = wgrad_tcs_kernel<CIN, COUT, R, KSEG, RS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tcs: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return CVIT_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t blocks = D * ((H + R - 1) / R) * ((W + KSEG - 1) / KSEG);
+  int grid = num_sms();
+  if (grid > blocks) grid = (int)blocks;
+  WtArgs a;
+  a.dw = dw;
+  a.x = static_cast<const __nv_bfloat16*>(x);
+  a.dz = static_cast<const __nv_bfloat16*>(dz);
+  a.D = (int)D;
+  a.H = (int)H;
+  a.W = (int)W;
+  a.dil = (int)dil;
+  kern<<<grid, WT_THREADS, Cfg::SMEM, stream>>>(tmX, tmZ, a);
+  return check_launch("wgrad_tcs_kernel");
+}
+
 }  // namespace cvit
 
 using namespace cvit;
@@ -496,6 +732,13 @@ extern "C" int cvit_wgrad_tcn_ndhwc(const void* x, const void* dz, float* dw, in
     return CVIT_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // default: whole rows by TMA + shared-memory de-interleave (wgrad_tcs_kernel); CVIT_WGRAD_CHUNK_TMA=1: 16-byte chunk boxes (A/B arm)
+  static const bool chunk_tma = getenv("CVIT_WGRAD_CHUNK_TMA") && atoi(getenv("CVIT_WGRAD_CHUNK_TMA")) != 0;
+  if (!chunk_tma) {
+    if (Cin == 16 && Cout == 16) return launch_wgrad_tcs<16, 16, 4, 64, 2>(x, dz, dw, D, H, W, dil, st);
+    if (Cin == 32 && Cout == 16) return launch_wgrad_tcs<32, 16, 2, 64, 3>(x, dz, dw, D, H, W, dil, st);
+    if (Cin == 32 && Cout == 32) return launch_wgrad_tcs<32, 32, 2, 32, 5>(x, dz, dw, D, H, W, dil, st);
+  }
   if (Cin == 16 && Cout == 16) return launch_wgrad_tcn<16, 16, 4, 64>(x, dz, dw, D, H, W, dil, st);
   if (Cin == 32 && Cout == 16) return launch_wgrad_tcn<32, 16, 4, 64>(x, dz, dw, D, H, W, dil, st);
   if (Cin == 32 && Cout == 32) return launch_wgrad_tcn<32, 32, 2, 64>(x, dz, dw, D, H, W, dil, st);
