@@ -5,10 +5,16 @@ datasets/tomo_dataset.py:89-146):
     labels/<name>        (D, H, W) int8, -1 = ignore                      gzip
     dino_features        (C, D, H/16, W/16) float16                       uncompressed, contiguous
 
-The container is HDF5 through ``h5py`` whenever that package is importable (production). This image ships no h5py,
-so a same-key ``.npz`` container stands in (one zip member per dataset, ``labels/<name>`` keys kept verbatim, gzip
-= zip deflate): the file NAME and every key are unchanged, only the byte container differs. Which one is in use is
-reported by :func:`backend`.
+The files are HDF5, as the reference's are. Three byte-level back ends, reported by :func:`backend`:
+
+* ``"h5py"``          -- whenever that package is importable (production);
+* ``"hdf5-classic"``  -- the self-contained writer / reader of the classic HDF5 format in :mod:`.hdf5_classic` (what
+                         h5py's default ``libver="earliest"`` emits). This image ships no h5py, so this is what runs
+                         here and on the GPU box: the files are real HDF5 (signature, superblock, symbol-table groups,
+                         gzip'd chunk B-trees, contiguous ``dino_features``), not a stand-in container;
+* ``"npz"``           -- the same-key zip container of the first round, only with ``CRYOVIT_HDF_BACKEND=npz``.
+
+Reading sniffs the file: HDF5 signature -> h5py / hdf5-classic, ``PK`` -> npz, so files of either kind stay readable.
 """
 from __future__ import annotations
 
@@ -19,6 +25,8 @@ from pathlib import Path
 
 import numpy as np
 
+from . import hdf5_classic
+
 try:  # pragma: no cover - depends on the deployment image
     import h5py  # type: ignore
 
@@ -27,22 +35,42 @@ except Exception:  # noqa: BLE001
     h5py = None
     _H5 = False
 
+GZIP_LEVEL = 4  # h5py's ``compression="gzip"`` default (``compression_opts`` unset)
+
 
 def backend() -> str:
-    return "h5py" if _H5 else "npz"
+    want = os.environ.get("CRYOVIT_HDF_BACKEND", "").strip().lower()
+    if want in ("npz", "hdf5-classic"):
+        return want
+    if want == "h5py" and not _H5:
+        raise ImportError("CRYOVIT_HDF_BACKEND=h5py, but h5py is not importable")
+    return "h5py" if _H5 else "hdf5-classic"
+
+
+def _kind(path: Path) -> str:
+    with open(path, "rb") as fh:
+        magic = fh.read(8)
+    if magic[:2] == b"PK":
+        return "npz"
+    if magic == hdf5_classic.SIGNATURE or hdf5_classic.is_hdf5(path):
+        return "h5py" if _H5 and backend() == "h5py" else "hdf5-classic"
+    raise ValueError(f"{path}: neither an HDF5 file nor the zip container")
 
 
 def read_tomogram(path: Path | str, keys: list[str] | None = None) -> dict[str, np.ndarray]:
     """All datasets of a tomogram file as {key: array}; group members come back as ``group/member``."""
     path = Path(path)
     out: dict[str, np.ndarray] = {}
-    if _H5:
+    kind = _kind(path)
+    if kind == "h5py":  # pragma: no cover - needs h5py
         with h5py.File(path, "r") as fh:
             def visit(name, obj):
                 if isinstance(obj, h5py.Dataset) and (keys is None or name in keys):
                     out[name] = obj[()]
             fh.visititems(visit)
         return out
+    if kind == "hdf5-classic":
+        return hdf5_classic.read_file(path, keys)
     with zipfile.ZipFile(path, "r") as zf:
         for member in zf.namelist():
             name = member[:-4] if member.endswith(".npy") else member
@@ -53,11 +81,14 @@ def read_tomogram(path: Path | str, keys: list[str] | None = None) -> dict[str, 
 
 def list_keys(path: Path | str) -> list[str]:
     path = Path(path)
-    if _H5:
+    kind = _kind(path)
+    if kind == "h5py":  # pragma: no cover - needs h5py
         names: list[str] = []
         with h5py.File(path, "r") as fh:
             fh.visititems(lambda n, o: names.append(n) if isinstance(o, h5py.Dataset) else None)
         return names
+    if kind == "hdf5-classic":
+        return hdf5_classic.list_keys(path)
     with zipfile.ZipFile(path, "r") as zf:
         return [m[:-4] if m.endswith(".npy") else m for m in zf.namelist()]
 
@@ -70,14 +101,18 @@ def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompress
     # written next to the target and renamed over it: an interrupted run never leaves a truncated result file
     # behind (``skip_existing`` would have to trust it), and a reader never sees a half-written one
     tmp = path.with_name(path.name + f".tmp{os.getpid()}")
+    kind = backend()
     try:
-        if _H5:
+        if kind == "h5py":  # pragma: no cover - needs h5py
             with h5py.File(tmp, "w") as fh:
                 for key, arr in datasets.items():
-                    kw = {} if key in uncompressed else {"compression": "gzip"}  # h5py default: level 4
+                    kw = {} if key in uncompressed else {"compression": "gzip"}
                     fh.create_dataset(key, data=arr, shape=arr.shape, dtype=arr.dtype, **kw)
+        elif kind == "hdf5-classic":
+            hdf5_classic.write_file(tmp, datasets, gzip={k: GZIP_LEVEL for k, a in datasets.items()
+                                                         if k not in uncompressed and np.ndim(a) > 0})
         else:
-            with zipfile.ZipFile(tmp, "w", compresslevel=4) as zf:  # h5py's gzip default is level 4 too
+            with zipfile.ZipFile(tmp, "w", compresslevel=GZIP_LEVEL) as zf:
                 for key, arr in datasets.items():
                     info = zipfile.ZipInfo(key + ".npy")
                     info.compress_type = zipfile.ZIP_STORED if key in uncompressed else zipfile.ZIP_DEFLATED
