@@ -40,12 +40,17 @@ constexpr uint32_t FA_COL_S = 0, FA_COL_P = 256, FA_COL_O = 384;
 // cycles it spends in each phase in registers and dumps the totals once at the end (a timeline of global stores
 // proved too intrusive: it moved the phases it was measuring).
 #ifdef CVIT_FA_TRACE
-#define FA_PROF_DECL uint32_t prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t prof_last = clock()
+__device__ __forceinline__ unsigned long long fa_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FA_PROF_DECL uint32_t prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const unsigned long long prof_t0 = fa_globaltimer(); uint32_t prof_last = clock()
 #define FA_PROF(slot) do { const uint32_t now_ = clock(); prof_acc[slot] += now_ - prof_last; prof_last = now_; } while (0)
 #define FA_PROF_DUMP(tiles) do { if (args.trace && blockIdx.x < 4 && lane == 0) {                      \
     long long* d_ = args.trace + (blockIdx.x * 16 + warp) * 10;                                        \
     for (int i_ = 0; i_ < 8; ++i_) d_[i_] = prof_acc[i_];                                              \
-    d_[8] = (tiles); } } while (0)
+    d_[8] = (tiles); d_[9] = (long long)(fa_globaltimer() - prof_t0); } } while (0)
 #else
 #define FA_PROF_DECL do { } while (0)
 #define FA_PROF(slot) do { } while (0)

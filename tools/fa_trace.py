@@ -47,4 +47,4 @@ for cta in range(2):
         names = mma_names if w >= 13 else sm_names
         label = "MMA " if w >= 13 else f"{'AB'[w >> 2]}q{w & 3} "
         print(f"CTA{cta} {label} tiles {tiles:4d} per-tile:", "  ".join(f"{n} {r[i] / tiles:6.0f}" for i, n in enumerate(names)),
-              f" | total {r[:8].sum() / tiles:6.0f}")
+              f" | total {r[:8].sum() / tiles:6.0f} | {r[:8].sum() / max(int(r[9]), 1):.3f} GHz over {r[9] / 1e6:.3f} ms")
