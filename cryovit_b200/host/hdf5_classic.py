@@ -165,12 +165,14 @@ class _Writer:
         rank = arr.ndim
         space = struct.pack("<BBB5x", 1, rank, 0) + b"".join(struct.pack("<Q", s) for s in arr.shape)
         msgs = [(MSG_DATASPACE, 0, space), (MSG_DATATYPE, 1, _encode_datatype(arr.dtype))]
-        if gzip_level is None or rank == 0 or arr.size == 0:
+        if (gzip_level is None and chunks is None) or rank == 0 or arr.size == 0:
             addr = self.add(memoryview(arr).cast("B")) if arr.size else UNDEF
             msgs.append((MSG_FILL, 1, struct.pack("<BBBBI", 2, 2, 2, 1, 0)))  # late allocation, default fill value
             msgs.append((MSG_LAYOUT, 0, struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)))
             return self.object_header(msgs)
         chunks = tuple(int(c) for c in (chunks or default_chunks(arr.shape, arr.itemsize)))
+        if len(chunks) == rank:  # libhdf5 refuses chunks larger than a fixed-size dataset
+            chunks = tuple(min(c, s) for c, s in zip(chunks, arr.shape))
         if len(chunks) != rank or any(c < 1 for c in chunks):
             raise Hdf5FormatError(f"chunk shape {chunks} does not fit a rank-{rank} dataset")
         grid = [range(0, s, c) for s, c in zip(arr.shape, chunks)]
@@ -181,7 +183,8 @@ class _Writer:
                 full = np.zeros(chunks, arr.dtype)
                 full[tuple(slice(0, s) for s in block.shape)] = block
                 block = full
-            return zlib.compress(np.ascontiguousarray(block), gzip_level)
+            block = np.ascontiguousarray(block)
+            return zlib.compress(block, gzip_level) if gzip_level is not None else block.tobytes()
 
         origins = list(product(*grid))  # C order = the lexicographic key order of the chunk B-tree
         entries = []
@@ -189,9 +192,10 @@ class _Writer:
             entries.append((origin, len(blob), self.add(blob)))
         btree = self.chunk_btree(entries, chunks, arr.itemsize)
         filters = struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", FILTER_DEFLATE, 8, 1, 1) + b"deflate\x00" \
-            + struct.pack("<I4x", gzip_level)
+            + struct.pack("<I4x", gzip_level or 0)
         msgs.append((MSG_FILL, 1, struct.pack("<BBBBI", 2, 3, 2, 1, 0)))  # incremental allocation
-        msgs.append((MSG_FILTERS, 1, filters))
+        if gzip_level is not None:
+            msgs.append((MSG_FILTERS, 1, filters))
         msgs.append((MSG_LAYOUT, 0, struct.pack("<BBBQ", 3, 2, rank + 1, btree)
                      + b"".join(struct.pack("<I", c) for c in chunks) + struct.pack("<I", arr.itemsize)))
         return self.object_header(msgs)
@@ -267,8 +271,9 @@ def write_file(path, datasets: dict[str, np.ndarray], gzip: dict[str, int | None
                chunks: dict[str, tuple[int, ...]] | None = None, threads: int = 8) -> None:
     """One HDF5 file holding ``datasets`` (keys may contain ``/``: intermediate groups are created, as
     ``h5py.File.create_dataset`` does). ``gzip[key]`` = deflate level for a chunked, compressed dataset (h5py's
-    ``compression="gzip"`` is level 4); keys absent from it are stored contiguous and raw. Chunks are compressed on
-    ``threads`` threads (zlib releases the GIL)."""
+    ``compression="gzip"`` is level 4); keys absent from it are stored contiguous and raw, unless ``chunks[key]`` asks
+    for a chunked (uncompressed) layout, e.g. ``dino_features`` in depth slabs so that a training crop reads only its
+    slabs. Chunks are compressed on ``threads`` threads (zlib releases the GIL)."""
     gzip = gzip or {}
     chunks = chunks or {}
     tree: dict = {}

@@ -238,3 +238,48 @@ def test_hdf_module_writes_real_hdf5_and_still_reads_the_zip_container(tmp_path,
     for f in (a, b):  # either container is read back whatever the write back end is now
         got = hdf.read_tomogram(f)
         assert all(np.array_equal(got[k], v) for k, v in sets.items())
+
+
+def test_uncompressed_chunked_features(tmp_path):
+    """dino_features in depth slabs (SURVEY.md 8f row f2's chunked option): chunk B-tree, no filter pipeline."""
+    feats = np.random.default_rng(2).standard_normal((24, 10, 3, 5)).astype(np.float16)
+    path = tmp_path / "f.hdf"
+    h5c.write_file(path, {"dino_features": feats}, chunks={"dino_features": (24, 4, 3, 5)})
+    with h5c.File(path) as fh:
+        info = fh.info("dino_features")
+        assert info.layout == "chunked" and info.chunks == (24, 4, 3, 5) and info.filters == []
+        assert np.array_equal(fh.read("dino_features"), feats)
+
+
+def test_round_trip_property():
+    """Random shapes / dtypes / chunkings / compression levels survive the write -> read round trip bit for bit."""
+    import tempfile
+
+    from hypothesis import given, settings, strategies as st
+
+    dtypes = [np.uint8, np.int8, np.int16, np.uint16, np.int32, np.int64, np.float16, np.float32, np.float64]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.data())
+    def run(data):
+        rank = data.draw(st.integers(1, 4))
+        shape = tuple(data.draw(st.integers(1, 9)) for _ in range(rank))
+        dtype = data.draw(st.sampled_from(dtypes))
+        chunk = tuple(data.draw(st.integers(1, s + 2)) for s in shape)
+        level = data.draw(st.sampled_from([None, 1, 4, 9]))
+        chunked = level is not None or data.draw(st.booleans())
+        arr = np.random.default_rng(data.draw(st.integers(0, 1 << 30))).integers(0, 120, shape).astype(dtype)
+        with tempfile.TemporaryDirectory() as d:
+            path = Path(d) / "p.hdf"
+            h5c.write_file(path, {"grp/x": arr, "y": arr.T.copy()}, gzip={"grp/x": level} if level is not None else None,
+                           chunks={"grp/x": chunk} if chunked else None, threads=1)
+            got = h5c.read_file(path)
+            assert got["grp/x"].dtype == arr.dtype and np.array_equal(got["grp/x"], arr) and np.array_equal(got["y"], arr.T)
+            if chunked:
+                _walk_if_deflate(path, level)
+
+    def _walk_if_deflate(path, level):
+        if level is not None:
+            _walk(path)
+
+    run()
