@@ -39,16 +39,21 @@ def _dino_features(data: torch.Tensor, model: DinoVisionTransformerB200, batch_s
     return extract._dino_features(data, model, batch_size)
 
 
-def _save_data(data: dict[str, np.ndarray], features: np.ndarray, tomo_name: str, dst_dir: Path) -> None:
+def _save_data(data: dict[str, np.ndarray], features: np.ndarray, tomo_name: str, dst_dir: Path, feature_chunk_depth: int = 0) -> None:
     """:109-153: ``data`` stays ``data`` (gzip), every other source dataset goes under ``labels/`` (gzip), a stale
-    ``dino_features`` is dropped, the new features are stored uncompressed."""
+    ``dino_features`` is dropped, the new features are stored uncompressed -- contiguous as the reference does, or with
+    ``feature_chunk_depth`` = n > 0 (entry point: ``+feature_chunk_depth=n``) as (C, n, h, w) slabs so
+    that a reader of a depth crop touches only its slabs."""
     out: dict[str, np.ndarray] = {}
     for key, arr in data.items():
         if key == "dino_features":
             continue
         out["data" if key == "data" else f"labels/{key}"] = arr
     out["dino_features"] = features
-    hdf.write_tomogram(Path(dst_dir) / tomo_name, out)
+    chunks = None
+    if feature_chunk_depth > 0 and features.ndim == 4:
+        chunks = {"dino_features": (features.shape[0], int(feature_chunk_depth), features.shape[2], features.shape[3])}
+    hdf.write_tomogram(Path(dst_dir) / tomo_name, out, chunks=chunks)
 
 
 def _read_source(path: Path) -> dict[str, np.ndarray]:
@@ -57,7 +62,8 @@ def _read_source(path: Path) -> dict[str, np.ndarray]:
 
 
 def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: str, datamodule, batch_size: int,
-                    image_dir: Path | None = None, use_sam: bool = False, skip_existing: bool = False, writers: int = 3) -> list[str]:
+                    image_dir: Path | None = None, use_sam: bool = False, skip_existing: bool = False, writers: int = 3,
+                    feature_chunk_depth: int = 0) -> list[str]:
     """:156-205. Returns the records this rank processed.
 
     The reference reads, extracts and writes one tomogram after the other (:186-204). At a third of a second of GPU time
@@ -112,7 +118,7 @@ def _process_sample(src_dir: Path, dst_dir: Path, csv_dir: Path, model, sample: 
             features = _dino_features(item, model, batch_size)
             while len(pending) >= max(1, writers):
                 pending.pop(0).result()
-            pending.append(writer.submit(_save_data, source, features, records[i], result_dir))
+            pending.append(writer.submit(_save_data, source, features, records[i], result_dir, feature_chunk_depth))
         for f in pending:
             f.result()
     return records
@@ -173,6 +179,6 @@ def _run_samples(cfg, paths, src_dir, dst_dir, csv_dir, image_dir, sample_names,
         t0 = time.perf_counter()
         done = _process_sample(src_dir, dst_dir, csv_dir, model, name, cfg["datamodule"], int(cfg["batch_size"]),
                                image_dir if cfg.get("export_features") else None, False, bool(cfg.get("skip_existing", False)),
-                               int(cfg.get("writers", 3)))
+                               int(cfg.get("writers", 3)), int(cfg.get("feature_chunk_depth", 0)))
         logging.info("rank %d/%d: %d tomograms of %s in %.2f s (files in -> files out, %s container)", rank, world, len(done), name,
                      time.perf_counter() - t0, hdf.backend())

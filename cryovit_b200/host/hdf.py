@@ -93,9 +93,11 @@ def list_keys(path: Path | str) -> list[str]:
         return [m[:-4] if m.endswith(".npy") else m for m in zf.namelist()]
 
 
-def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompressed: tuple[str, ...] = ("dino_features",)) -> None:
+def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompressed: tuple[str, ...] = ("dino_features",),
+                   chunks: dict[str, tuple[int, ...]] | None = None) -> None:
     """Write (overwrite: the reference opens with "w", dino_features.py:119) a tomogram file. Every dataset is
-    gzip-compressed except those named in ``uncompressed`` (the reference stores dino_features raw, :148-153)."""
+    gzip-compressed except those named in ``uncompressed`` (the reference stores dino_features raw and contiguous,
+    :148-153); ``chunks[key]`` stores an uncompressed dataset in chunks instead (HDF5 back ends only)."""
     path = Path(path)
     path.parent.mkdir(parents=True, exist_ok=True)
     # written next to the target and renamed over it: an interrupted run never leaves a truncated result file
@@ -107,10 +109,13 @@ def write_tomogram(path: Path | str, datasets: dict[str, np.ndarray], uncompress
             with h5py.File(tmp, "w") as fh:
                 for key, arr in datasets.items():
                     kw = {} if key in uncompressed else {"compression": "gzip"}
+                    if chunks and key in chunks:
+                        kw["chunks"] = tuple(min(c, n) for c, n in zip(chunks[key], arr.shape))
                     fh.create_dataset(key, data=arr, shape=arr.shape, dtype=arr.dtype, **kw)
         elif kind == "hdf5-classic":
             hdf5_classic.write_file(tmp, datasets, gzip={k: GZIP_LEVEL for k, a in datasets.items()
-                                                         if k not in uncompressed and np.ndim(a) > 0})
+                                                         if k not in uncompressed and np.ndim(a) > 0},
+                                    chunks={k: c for k, c in (chunks or {}).items() if k in uncompressed})
         else:
             with zipfile.ZipFile(tmp, "w", compresslevel=GZIP_LEVEL) as zf:
                 for key, arr in datasets.items():

@@ -77,6 +77,16 @@ def test_save_data_layout_roundtrip(tmp_path):
     assert np.array_equal(back["labels/mito"], src["mito"]) and back["labels/mito"].dtype == np.int8
     _save_data({"data": src["data"]}, feats[:1], "t0.hdf", tmp_path / "out" / "S")  # "w": overwrite, no merge
     assert sorted(hdf.list_keys(path)) == ["data", "dino_features"]
+    # SURVEY 8f row f2's option: the features in depth slabs (the default above is the reference's contiguous layout)
+    _save_data({"data": src["data"]}, feats, "t1.hdf", tmp_path / "out" / "S", feature_chunk_depth=3)
+    assert np.array_equal(hdf.read_tomogram(tmp_path / "out" / "S" / "t1.hdf", keys=["dino_features"])["dino_features"], feats)
+    if hdf.backend() == "hdf5-classic":
+        from cryovit_b200.host import hdf5_classic
+
+        with hdf5_classic.File(tmp_path / "out" / "S" / "t1.hdf") as fh:
+            assert fh.info("dino_features").chunks == (384, 3, 2, 3) and fh.info("dino_features").filters == []
+        with hdf5_classic.File(path) as fh:
+            assert fh.info("dino_features").layout == "contiguous" and fh.info("data").layout == "chunked"
 
 
 # ------------------------------------------------------------------------------------------------- crop / collate (a8)

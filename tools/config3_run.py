@@ -52,7 +52,7 @@ def main():
     wall = time.perf_counter() - t0
     log = r.stdout + r.stderr
     per_rank = [(int(m.group(1)), int(m.group(2)), float(m.group(3)), m.group(4))
-                for m in re.finditer(r"rank (\d+)/\d+: (\d+) tomograms of Q18 in ([0-9.]+) s \(files in -> files out, (\w+) container\)", log)]
+                for m in re.finditer(r"rank (\d+)/\d+: (\d+) tomograms of Q18 in ([0-9.]+) s \(files in -> files out, ([\w-]+) container\)", log)]
     out_files = sorted((base / "tomograms" / "Q18").glob("*.hdf"))
     res = {
         "workload": f"BASELINE config 3: {n_tomo} x ({D},{H},{W}) uint8 tomogram files -> ViT-g/14 features, {n_gpus} GPUs, "
