@@ -411,8 +411,11 @@ class File:
             if any(t == MSG_LAYOUT for t, _ in msgs):
                 self._datasets[prefix.strip("/")] = self._dataset(msgs)
                 return
+            if any(t in (0x02, 0x06) for t, _ in msgs):  # link info / link messages
+                raise Hdf5FormatError(f"group '{prefix or '/'}' is stored in the new link-message format (libver='latest' or "
+                                      "track_order): outside the classic subset, needs h5py")
             if cached is None:
-                return  # committed datatype or new-style group: nothing the tomogram layout holds
+                return  # committed datatype: nothing the tomogram layout holds
             btree, heap = cached
         else:
             btree, heap = struct.unpack("<QQ", table[:16])
