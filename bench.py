@@ -114,7 +114,7 @@ NCU_KEYS = {"linear_bias": "qkv_gemm", "attention": "attention", "linear_swiglu"
             "proj_scale_residual": "proj_gemm", "w3_scale_residual": "w3_gemm"}
 
 
-NCU_TRAFFIC_FILE = "r02_ncu_traffic.json"  # curated from profiles/r02_ncu_full_v1_*_kernels.json by tools/ncu_traffic_table.py
+NCU_TRAFFIC_FILE = "r02_ncu_traffic.json"  # curated from profiles/r02_ncu_full_v3_*_kernels.json by tools/ncu_traffic_table.py
 
 
 def ncu_traffic(kernel: str) -> float | None:
@@ -940,8 +940,8 @@ def run_b200(args) -> None:
                 "frac": round(tf / peak, 4), "peak_burst": peaks.get("bf16_tflops"),
                 "frac_burst": round(tf / peaks["bf16_tflops"], 4) if peaks.get("bf16_tflops") else None,
                 "traffic": ncu_traffic(top),
-                "traffic_source": f"profiles/{NCU_TRAFFIC_FILE} (ncu --set full of build r02 v1, one launch, same shapes; the GEMM kernels "
-                                  "are unchanged since)",
+                "traffic_source": f"profiles/{NCU_TRAFFIC_FILE} (ncu --set full of the round's final library, capture r02 v3, one launch, "
+                                  "same shapes)",
                 "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
                 "avg_launch_ms": round(tensor_ks[top]["ms"], 4)}
     kernels = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
