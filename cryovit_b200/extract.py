@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import nvtx, ops
 from ._lib import CryovitB200Error
 from .vit import DinoVisionTransformerB200
 
@@ -58,7 +58,8 @@ def extract_tomogram_device(tomo: torch.Tensor, model: DinoVisionTransformerB200
     _, _, gh, gw = ops.patch_grid(H, W)
     feats = out if out is not None else _features_buffer(model, D, gh, gw)
     for i in range(0, D, batch_size):
-        model.extract_into(tomo[i:i + batch_size], feats, i)
+        with nvtx.span(f"extract.slices[{i}:{min(i + batch_size, D)}]"):
+            model.extract_into(tomo[i:i + batch_size], feats, i)
     return feats
 
 

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import nvtx, ops
 from . import train_ops as T
 from ._lib import CryovitB200Error
 from .head import BLOCKS, rows8_weight_image, rowsn_weight_image, state_dict_keys, wpack_weight_image, wpackn_weight_image
@@ -534,8 +534,10 @@ class CryoVITHeadTrainerB200:
         import torch.distributed as dist
 
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        loss = self._forward_backward_graphed(features, labels, 1.0 / world)
-        self.optimizer_step()
+        with nvtx.span("head.train.forward_backward"):
+            loss = self._forward_backward_graphed(features, labels, 1.0 / world)
+        with nvtx.span("head.train.optimizer"):
+            self.optimizer_step()
         return loss
 
     # ----------------------------------------------------------------------------- CUDA graph of forward + backward

@@ -37,7 +37,7 @@ from dataclasses import dataclass
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import nvtx, ops
 from ._lib import CryovitB200Error
 
 
@@ -290,17 +290,19 @@ class DinoVisionTransformerB200:
     def _blocks(self, ws: dict, B: int, T: int) -> None:
         cfg = self.cfg
         x, ln, qkv, attn, hidden = ws["x"], ws["ln"], ws["qkv"], ws["attn"], ws["hidden"]
-        for b in self._w["blocks"]:
-            ops.layernorm(x, b["n1w"], b["n1b"], ln, cfg.ln_eps)
-            ops.linear_bias(ln, b["qkv_w"], b["qkv_b"], qkv)
-            ops.attention(qkv, attn, B, T, cfg.num_heads)
-            ops.linear_scale_residual(attn, b["proj_w"], b["proj_b"], b["ls1"], x)
-            ops.layernorm(x, b["n2w"], b["n2b"], ln, cfg.ln_eps)
-            if cfg.ffn == "swiglu":
-                ops.linear_swiglu(ln, b["w12i"], b["b12i"], hidden)
-            else:
-                ops.linear_bias(ln, b["fc1_w"], b["fc1_b"], hidden, gelu=True)
-            ops.linear_scale_residual(hidden, b["out_w"], b["out_b"], b["ls2"], x)
+        for i, b in enumerate(self._w["blocks"]):
+            with nvtx.span(f"vit.block{i}.attn"):
+                ops.layernorm(x, b["n1w"], b["n1b"], ln, cfg.ln_eps)
+                ops.linear_bias(ln, b["qkv_w"], b["qkv_b"], qkv)
+                ops.attention(qkv, attn, B, T, cfg.num_heads)
+                ops.linear_scale_residual(attn, b["proj_w"], b["proj_b"], b["ls1"], x)
+            with nvtx.span(f"vit.block{i}.ffn"):
+                ops.layernorm(x, b["n2w"], b["n2b"], ln, cfg.ln_eps)
+                if cfg.ffn == "swiglu":
+                    ops.linear_swiglu(ln, b["w12i"], b["b12i"], hidden)
+                else:
+                    ops.linear_bias(ln, b["fc1_w"], b["fc1_b"], hidden, gelu=True)
+                ops.linear_scale_residual(hidden, b["out_w"], b["out_b"], b["ls2"], x)
         self.launches += 7 * len(self._w["blocks"])
 
     def _embed(self, ws: dict, B: int, T: int, gh: int, gw: int, pe_w: torch.Tensor) -> None:

@@ -52,3 +52,15 @@ def test_product_fails_loudly_without_gpu():
         m.cuda()
     with pytest.raises(CryovitB200Error):
         m.forward_features(torch.zeros(1, 3, 28, 28))
+
+
+def test_nvtx_spans_are_free_when_disabled(monkeypatch):
+    """CRYOVIT_B200_NVTX unset: every span is the same no-op context manager (nothing on the measured path)."""
+    import importlib
+
+    monkeypatch.delenv("CRYOVIT_B200_NVTX", raising=False)
+    from cryovit_b200 import nvtx
+    nvtx = importlib.reload(nvtx)
+    assert not nvtx.ENABLED and nvtx.span("a") is nvtx.span("b")
+    with nvtx.span("x"):
+        pass
