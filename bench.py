@@ -37,7 +37,8 @@ T, NP, C, FH, HEADS, DEPTH = 1029, 1024, 1536, 4096, 24, 40
 FLOP_PER_SLICE = DEPTH * T * (2 * C * 3 * C + 2 * C * C + 2 * C * 2 * FH + 2 * FH * C + 4 * T * C) + 2 * 588 * C * NP
 METRIC = "DINOv2 ViT-g/14 feature slices/sec"
 # arithmetic type of the path per --operands mode (all accumulate in fp32 on the tensor cores, fp32 residual stream)
-DTYPES = {"mixed": "fp16 (LayerNorm out, attention out, qkv/proj/w12 weights) + bf16 (q/k/v, probabilities, FFN hidden, w3) operands, fp32 accumulate",
+DTYPES = {"mixed-attn": "fp16 (norm1 out, attention out, qkv/proj weights) + bf16 (q/k/v, probabilities, norm2 out, w12, FFN hidden, w3) operands, fp32 accumulate",
+          "mixed": "fp16 (LayerNorm out, attention out, qkv/proj/w12 weights) + bf16 (q/k/v, probabilities, FFN hidden, w3) operands, fp32 accumulate",
           "fp16": "fp16 (LayerNorm out, q/k/v, probabilities, attention out, qkv/proj/w12 weights) + bf16 (FFN hidden, w3) operands, fp32 accumulate",
           "bf16": "bf16 operands, fp32 accumulate"}
 
@@ -995,9 +996,9 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-oracle and GPU-eager baseline legs")
     ap.add_argument("--no-dataset", action="store_true", help="skip the file-based BASELINE config 3 leg")
-    ap.add_argument("--operands", default="mixed", choices=["mixed", "fp16", "bf16"],
-                    help="16-bit formats of the ViT operands (cryovit_b200/vit.py): mixed = fp16 LayerNorm / attention output and "
-                         "their weights, bf16 q/k/v/P and FFN hidden (default, the product path)")
+    ap.add_argument("--operands", default="mixed-attn", choices=["mixed-attn", "mixed", "fp16", "bf16"],
+                    help="16-bit formats of the ViT operands (cryovit_b200/vit.py): mixed-attn = fp16 norm1 / attention output and "
+                         "the qkv / proj weights, everything else bf16 (default, the product path); mixed = the FFN input side fp16 too")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.steps_ref, args.warmup_ref = min(args.steps, 3), min(args.warmup, 1)

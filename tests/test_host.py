@@ -298,7 +298,7 @@ def test_dino_features_argument_errors_match_the_reference():
 
 def test_operand_format_switch(monkeypatch):
     """The 16-bit format of the bounded ViT operands: constructor argument, CRYOVIT_B200_OPERANDS for the Hydra entry
-    points, "mixed" by default (fp16 LayerNorm / attention output and their weights, bf16 q/k/v and probabilities);
+    points, "mixed-attn" by default (fp16 norm1 / attention output and their weights, bf16 q/k/v, probabilities and FFN);
     anything else is refused before any GPU work."""
     import torch
 
@@ -307,7 +307,9 @@ def test_operand_format_switch(monkeypatch):
 
     monkeypatch.delenv("CRYOVIT_B200_OPERANDS", raising=False)
     m = build_model("dinov2_vits14_reg")
-    assert (m.operands, m.operand_dtype, m.qkv_dtype) == ("mixed", torch.float16, torch.bfloat16)
+    assert (m.operands, m.operand_dtype, m.qkv_dtype, m.ffn_dtype) == ("mixed-attn", torch.float16, torch.bfloat16, torch.bfloat16)
+    m = build_model("dinov2_vits14_reg", operands="mixed")
+    assert (m.operands, m.operand_dtype, m.qkv_dtype, m.ffn_dtype) == ("mixed", torch.float16, torch.bfloat16, torch.float16)
     m = build_model("dinov2_vits14_reg", operands=torch.float16)
     assert (m.operands, m.operand_dtype, m.qkv_dtype) == ("fp16", torch.float16, torch.float16)
     monkeypatch.setenv("CRYOVIT_B200_OPERANDS", "bf16")
