@@ -8,22 +8,41 @@ the step is ``CryoVITHeadTrainerB200.train_step`` (native forward / backward / a
 from __future__ import annotations
 
 import logging
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
 import torch
 
 from ..train import CryoVITHeadTrainerB200
-from .datasets import TomoDataset
+from .datasets import ResidentTomoCache, TomoDataset
 from .shard import rank_world, require_process_group
+
+
+def _cache_budget_bytes(cache_gb: float | None) -> int:
+    """HBM the resident training set may take: ``cache_gb`` (``CRYOVIT_B200_FEATURE_CACHE_GB`` when None; 0 disables),
+    by default 60 % of what is free on the device right now (the trainer's own buffers for a full-size crop are ~6 GB)."""
+    if cache_gb is None:
+        env = os.environ.get("CRYOVIT_B200_FEATURE_CACHE_GB", "").strip()
+        cache_gb = float(env) if env else None
+    if cache_gb is not None:
+        return int(cache_gb * 1e9)
+    free, _total = torch.cuda.mem_get_info()
+    return int(0.6 * free)
 
 
 def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50, lr: float = 1e-4, weight_decay: float = 1e-3,
              swa_epoch_start: int | None = 40, seed: int = 42, exp_dir: Path | str | None = None, state_dict: dict | None = None,
-             log_every: int = 10) -> dict[str, torch.Tensor]:
+             log_every: int = 10, cache_gb: float | None = None) -> dict[str, torch.Tensor]:
     """Trains on the items of ``dataset`` (``train=True`` gives the reference's random 128 x 32 x 32 feature crops);
     with several ranks (torchrun) every rank walks its own round-robin share of a common shuffled order and the
-    gradients are averaged over the ranks each step. Returns the final (SWA-averaged if enabled) state dict."""
+    gradients are averaged over the ranks each step. Returns the final (SWA-averaged if enabled) state dict.
+
+    The tomograms this rank trains on stay resident in HBM after their first read (:class:`ResidentTomoCache`, up to
+    ``cache_gb``), and the next item's file read (first epoch) and crop draw happen on a helper thread under the current
+    step; crops and order are those of the plain ``dataset[i]`` loop."""
     rank, world = rank_world()
     require_process_group("fit_head")  # the data is sharded by rank below: the gradients must really be exchanged
     torch.manual_seed(seed)
@@ -34,6 +53,15 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
     order_rng = np.random.default_rng(seed)
     swa_avg, swa_n = None, 0
     step = 0
+    cache = None
+    if hasattr(dataset, "_crop_slices") and hasattr(dataset, "_load_tomogram"):
+        budget = _cache_budget_bytes(cache_gb)
+        if budget > 0:
+            cache = ResidentTomoCache(dataset, torch.device("cuda", torch.cuda.current_device()), budget)
+    # the helper thread does host work only (file read, crop draw): the trainer captures CUDA graphs on this thread, and a
+    # CUDA call from another thread during a capture is an error. ONE helper thread: the crop draws stay in order.
+    fetch = (lambda i: cache.prepare(int(i))) if cache is not None else (lambda i: dataset[int(i)])
+    pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-fit-fetch")
     for epoch in range(max_epochs):
         # Lightning's StochasticWeightAveraging.on_train_epoch_START: epochs swa_start .. max_epochs - 1 each add the
         # weights they START from to the running mean (so the last epoch's own updates are not in it), and the mean
@@ -41,17 +69,27 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
         if swa_epoch_start is not None and epoch >= swa_epoch_start:
             swa_n += 1
             swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
+        t_epoch = time.perf_counter()
         order = order_rng.permutation(len(dataset))
         usable = len(order) // world * world  # every rank takes the same number of steps (the all-reduce is collective)
         losses = []
-        for i in order[:usable][rank::world]:
-            item = dataset[int(i)]
+        mine = [int(i) for i in order[:usable][rank::world]]
+        nxt = pool.submit(fetch, mine[0]) if mine else None
+        for k in range(len(mine)):
+            item = cache.finish(nxt.result()) if cache is not None else nxt.result()
+            nxt = pool.submit(fetch, mine[k + 1]) if k + 1 < len(mine) else None
             loss = trainer.train_step(item.data.cuda(non_blocking=True), item.label.cuda(non_blocking=True))
             step += 1
             if step % log_every == 0 or len(losses) == 0:
                 losses.append(float(loss))
         if rank == 0:
-            logging.info("epoch %d: %d steps/rank, DiceLoss %.4f", epoch, usable // world, float(np.mean(losses)) if losses else float("nan"))
+            torch.cuda.synchronize()
+            logging.info("epoch %d: %d steps/rank, DiceLoss %.4f, %.2f s", epoch, usable // world,
+                         float(np.mean(losses)) if losses else float("nan"), time.perf_counter() - t_epoch)
+    pool.shutdown(wait=True)
+    if cache is not None and rank == 0:
+        logging.info("resident training set: %d tomograms, %.2f GB in HBM, %d file reads for %d steps", len(cache._items),
+                     cache.used / 1e9, cache.file_reads, step)
     if swa_avg is not None:
         trainer.flat_p.copy_(swa_avg)
     sd = trainer.state_dict()

@@ -386,3 +386,35 @@ def test_process_sample_overlaps_io_and_can_resume(tmp_path, monkeypatch):
     monkeypatch.setattr(df, "_save_data", lambda *a, **k: (_ for _ in ()).throw(OSError("disk full")))
     with pytest.raises(OSError, match="disk full"):
         df._process_sample(*args)
+
+
+def test_resident_cache_gives_the_same_items_as_the_dataset(tmp_path):
+    """ResidentTomoCache (the fit loop's HBM-resident training set; here on the CPU device): same records, same crop
+    draws and same tensors as ``dataset[i]`` under the same seed, one file read per tomogram however many epochs, and
+    items past the budget still served (from their file)."""
+    from cryovit.datasets import TomoDataset
+    from cryovit_b200.host import hdf
+    from cryovit_b200.host.datasets import ResidentTomoCache
+
+    rng = np.random.default_rng(0)
+    recs = []
+    for i, (d, h) in enumerate([(5, 34), (3, 32), (6, 40)]):
+        feats = rng.standard_normal((8, d, h, 36)).astype(np.float16)
+        lab = rng.integers(-1, 2, (d, 16 * h, 16 * 36)).astype(np.int8)
+        hdf.write_tomogram(tmp_path / "S" / f"t{i}.hdf", {"data": np.zeros((d, 16, 16), np.uint8), "labels/mito": lab, "dino_features": feats})
+        recs.append({"sample": "S", "tomo_name": f"t{i}.hdf", "split_id": i})
+    order = [0, 1, 2, 2, 0, 1, 1, 0, 2]
+    ds = TomoDataset(recs, "dino_features", "mito", "split_id", tmp_path, train=True)
+    np.random.seed(7)
+    plain = [ds[i] for i in order]
+    first_item_bytes = 8 * 5 * 34 * 36 * 2 + 5 * (16 * 34) * (16 * 36)  # fp16 features + int8 labels of t0
+    for budget, kept in ((1 << 30, 3), (first_item_bytes + 10, 1)):
+        cache = ResidentTomoCache(ds, "cpu", budget)
+        np.random.seed(7)
+        got = [cache.get(i) for i in order]
+        for a, b in zip(plain, got):
+            assert (a.sample, a.tomo_name, a.split_id) == (b.sample, b.tomo_name, b.split_id)
+            assert a.data.shape[-2:] == (32, 32) and torch.equal(a.data, b.data) and torch.equal(a.label, b.label)
+            assert b.data.is_contiguous() and b.label.is_contiguous()
+        assert len(cache._items) == kept
+        assert cache.file_reads == (3 if kept == 3 else 1 + sum(1 for i in order if i != 0))
