@@ -573,6 +573,57 @@ def _autocast_head(sd, x):
         return torch.clip(x, -5.0, 5.0)
 
 
+def fit_loop_line(torch, dist, world: int, n_per_rank: int = 4, epochs: int = 3) -> dict:
+    """The head's fit loop (host/fit.py: the schedule of configs/trainer/fit.yaml around the native training step) on
+    tomogram FILES of BASELINE config 5's size: every rank owns ``n_per_rank`` files with fp16 (1536,128,32,32) features
+    and int8 labels. Seconds per epoch with the training set resident in HBM after its first read (the default) against
+    re-reading every file in every epoch (``cache_gb=0``: what the reference's loader does, tomo_dataset.py:89-146)."""
+    import shutil
+    import tempfile
+
+    from cryovit_b200.host import fit, hdf
+    from cryovit_b200.host.datasets import TomoDataset
+
+    rank = int(os.environ.get("RANK", "0"))
+    root = Path(tempfile.mkdtemp(prefix=f"cryovit_fit_r{rank}_"))
+    try:
+        g = torch.Generator(device="cuda").manual_seed(900 + rank)
+        recs = []
+        for i in range(n_per_rank):
+            feats = (torch.randn(1536, D, 32, 32, device="cuda", generator=g) * 0.5).half().cpu().numpy()
+            lab = (torch.rand(D, H, W, device="cuda", generator=g) < 0.3).to(torch.int8).cpu().numpy()
+            hdf.write_tomogram(root / "S" / f"t{rank}_{i}.hdf", {"labels/mito": lab, "dino_features": feats})
+            recs.append({"sample": "S", "tomo_name": f"t{rank}_{i}.hdf"})
+        ds = TomoDataset(recs, "dino_features", "mito", "split_id", root, train=True)
+        env_rank, env_world = os.environ.get("RANK"), os.environ.get("WORLD_SIZE")
+        out = {}
+        for label, gb in (("resident_in_hbm", None), ("files_every_epoch", 0.0)):
+            secs: list = []
+            # every rank trains on its own private files (same count): the rank sharding inside fit_head is switched off,
+            # the gradient all-reduce is not (it looks at the process group, not at the environment)
+            os.environ["RANK"], os.environ["WORLD_SIZE"] = "0", "1"
+            try:
+                fit.fit_head(ds, in_channels=1536, max_epochs=epochs, swa_epoch_start=None, cache_gb=gb, epoch_seconds=secs)
+            finally:
+                for k, v in (("RANK", env_rank), ("WORLD_SIZE", env_world)):
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            t = torch.tensor(secs, device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = t.tolist()
+            out[label] = {"first_epoch_s": round(secs[0], 3), "later_epochs_s": [round(s, 3) for s in secs[1:]],
+                          "ms_per_step_steady": round(min(secs[1:]) / n_per_rank * 1e3, 2)}
+        out["workload"] = (f"{epochs} epochs over {n_per_rank} tomogram files per GPU (fp16 (1536,{D},32,32) features + int8 labels, "
+                           f"{hdf.backend()} files on /tmp), one full-size crop per step, same crops and losses in both modes")
+        out["speedup_steady"] = round(out["files_every_epoch"]["ms_per_step_steady"] / out["resident_in_hbm"]["ms_per_step_steady"], 2)
+        return out
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def dataset_line(torch, dist, world: int, model, n_per_rank: int = 6) -> dict:
     """BASELINE config 3 through the FILES: every rank owns ``n_per_rank`` synthetic 128x512x512 uint8 tomogram files of
     one sample directory on the box's local disk and runs them through ``host.dino_features._process_sample`` -- the
@@ -915,6 +966,8 @@ def run_b200(args) -> None:
     del head_voxels_per_s.head
     torch.cuda.empty_cache()
     train_line = head_train_voxels_per_s(torch, dist, world)
+    if not args.no_dataset:
+        train_line["fit_loop"] = fit_loop_line(torch, dist, world)
     data_line = None if args.no_dataset else dataset_line(torch, dist, world, model)
     if rank != 0:
         if world > 1:

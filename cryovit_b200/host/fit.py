@@ -35,14 +35,15 @@ def _cache_budget_bytes(cache_gb: float | None) -> int:
 
 def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50, lr: float = 1e-4, weight_decay: float = 1e-3,
              swa_epoch_start: int | None = 40, seed: int = 42, exp_dir: Path | str | None = None, state_dict: dict | None = None,
-             log_every: int = 10, cache_gb: float | None = None) -> dict[str, torch.Tensor]:
+             log_every: int = 10, cache_gb: float | None = None, epoch_seconds: list | None = None) -> dict[str, torch.Tensor]:
     """Trains on the items of ``dataset`` (``train=True`` gives the reference's random 128 x 32 x 32 feature crops);
     with several ranks (torchrun) every rank walks its own round-robin share of a common shuffled order and the
     gradients are averaged over the ranks each step. Returns the final (SWA-averaged if enabled) state dict.
 
     The tomograms this rank trains on stay resident in HBM after their first read (:class:`ResidentTomoCache`, up to
     ``cache_gb``), and the next item's file read (first epoch) and crop draw happen on a helper thread under the current
-    step; crops and order are those of the plain ``dataset[i]`` loop."""
+    step; crops and order are those of the plain ``dataset[i]`` loop. ``epoch_seconds`` (a list) receives the wall clock of
+    every epoch, device work included."""
     rank, world = rank_world()
     require_process_group("fit_head")  # the data is sharded by rank below: the gradients must really be exchanged
     torch.manual_seed(seed)
@@ -82,8 +83,11 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
             step += 1
             if step % log_every == 0 or len(losses) == 0:
                 losses.append(float(loss))
-        if rank == 0:
+        if rank == 0 or epoch_seconds is not None:
             torch.cuda.synchronize()
+            if epoch_seconds is not None:
+                epoch_seconds.append(time.perf_counter() - t_epoch)
+        if rank == 0:
             logging.info("epoch %d: %d steps/rank, DiceLoss %.4f, %.2f s", epoch, usable // world,
                          float(np.mean(losses)) if losses else float("nan"), time.perf_counter() - t_epoch)
     pool.shutdown(wait=True)
