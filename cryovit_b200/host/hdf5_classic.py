@@ -585,3 +585,17 @@ def read_file(path, keys: list[str] | None = None) -> dict[str, np.ndarray]:
 def list_keys(path) -> list[str]:
     with File(path) as fh:
         return fh.keys()
+
+
+if __name__ == "__main__":  # python -m cryovit_b200.host.hdf5_classic FILE...: what `h5ls -r -v` would say, without libhdf5
+    import sys
+
+    for arg in sys.argv[1:]:
+        with File(arg) as fh_:
+            print(f"{arg}: superblock at {fh_.base}, end of file address {fh_.eof}")
+            for key_ in fh_.keys():
+                d_ = fh_.info(key_)
+                how = d_.layout + (f" {d_.chunks}" if d_.chunks else "") + ("".join(
+                    f" + {'deflate' if f == FILTER_DEFLATE else 'shuffle' if f == FILTER_SHUFFLE else f'filter {f}'}{list(v)}"
+                    for f, v in d_.filters))
+                print(f"  /{key_}  {d_.dtype}  {d_.shape}  {how}")
