@@ -38,7 +38,7 @@ FREE_NULL = 1           # local heap: "no free block"
 
 MSG_DATASPACE, MSG_DATATYPE, MSG_FILL_OLD, MSG_FILL, MSG_LAYOUT, MSG_FILTERS = 0x01, 0x03, 0x04, 0x05, 0x08, 0x0B
 MSG_CONTINUATION, MSG_SYMBOL_TABLE = 0x10, 0x11
-FILTER_DEFLATE, FILTER_SHUFFLE = 1, 2
+FILTER_DEFLATE, FILTER_SHUFFLE, FILTER_FLETCHER32 = 1, 2, 3
 
 
 class Hdf5FormatError(ValueError):
@@ -106,6 +106,26 @@ def _decode_datatype(buf: bytes) -> np.dtype:
             return np.dtype(f"{order}f{size}")
         raise Hdf5FormatError("non-IEEE floating-point datatype")
     raise Hdf5FormatError(f"datatype class {cls} (only fixed-point and floating-point datasets are read)")
+
+
+def undo_filters(blob: bytes, filters: list[tuple[int, tuple[int, ...]]], mask: int, itemsize: int) -> bytes:
+    """A stored chunk back to raw element bytes: the pipeline's filters in reverse order, skipping those the chunk's
+    filter mask switched off. deflate, shuffle and fletcher32 (the checksum is dropped, not verified) are what h5py
+    offers without plug-ins; anything else needs h5py itself."""
+    for idx in range(len(filters) - 1, -1, -1):
+        if mask >> idx & 1:
+            continue
+        fid, vals = filters[idx]
+        if fid == FILTER_DEFLATE:
+            blob = zlib.decompress(blob)
+        elif fid == FILTER_SHUFFLE:
+            width = vals[0] if vals else itemsize
+            blob = np.frombuffer(blob, np.uint8).reshape(width, -1).T.tobytes()
+        elif fid == FILTER_FLETCHER32:
+            blob = blob[:-4]
+        else:
+            raise Hdf5FormatError(f"filter {fid} needs h5py")
+    return blob
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -553,17 +573,7 @@ class File:
 
         def unpack(item):
             origin, mask, blob = item
-            for idx in range(len(d.filters) - 1, -1, -1):
-                if mask >> idx & 1:
-                    continue
-                fid, vals = d.filters[idx]
-                if fid == FILTER_DEFLATE:
-                    blob = zlib.decompress(blob)
-                elif fid == FILTER_SHUFFLE:
-                    width = vals[0] if vals else d.dtype.itemsize
-                    blob = np.frombuffer(blob, np.uint8).reshape(width, -1).T.tobytes()
-                else:
-                    raise Hdf5FormatError(f"{key}: filter {fid} needs h5py")
+            blob = undo_filters(blob, d.filters, mask, d.dtype.itemsize)
             block = np.frombuffer(blob, d.dtype, int(np.prod(d.chunks))).reshape(d.chunks)
             sel = tuple(slice(o, min(o + c, s)) for o, c, s in zip(origin, d.chunks, d.shape))
             out[sel] = block[tuple(slice(0, s.stop - s.start) for s in sel)]

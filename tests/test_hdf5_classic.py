@@ -283,3 +283,16 @@ def test_round_trip_property():
             _walk(path)
 
     run()
+
+
+def test_filter_pipeline_is_undone_in_reverse_order():
+    """shuffle -> deflate -> fletcher32, as h5py applies them with shuffle=True, compression="gzip", fletcher32=True; a
+    chunk whose filter mask skipped deflate (libhdf5 does that when a chunk does not shrink); unknown filters refuse."""
+    raw = np.arange(600, dtype=np.int32)
+    shuffled = raw.view(np.uint8).reshape(-1, 4).T.tobytes()
+    stored = zlib.compress(shuffled, 4) + b"\x12\x34\x56\x78"
+    filters = [(h5c.FILTER_SHUFFLE, (4,)), (h5c.FILTER_DEFLATE, (4,)), (h5c.FILTER_FLETCHER32, ())]
+    assert h5c.undo_filters(stored, filters, 0, 4) == raw.tobytes()
+    assert h5c.undo_filters(shuffled + b"\x00" * 4, filters, 0b010, 4) == raw.tobytes()
+    with pytest.raises(h5c.Hdf5FormatError, match="filter 32015"):
+        h5c.undo_filters(stored, [(32015, (3,))], 0, 4)
