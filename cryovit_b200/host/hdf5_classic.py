@@ -336,10 +336,11 @@ def write_file(path, datasets: dict[str, np.ndarray], gzip: dict[str, int | None
 # ------------------------------------------------------------------------------------------------------------------
 
 class DatasetInfo:
-    __slots__ = ("shape", "dtype", "layout", "address", "size", "chunks", "btree", "filters", "compact")
+    __slots__ = ("shape", "dtype", "layout", "address", "size", "chunks", "btree", "filters", "compact", "error")
 
     def __init__(self):
         self.shape = self.dtype = self.layout = self.address = self.size = self.chunks = self.btree = self.compact = None
+        self.error: str | None = None  # why this dataset cannot be read (the others of the file still can)
         self.filters: list[tuple[int, tuple[int, ...]]] = []
 
 
@@ -429,7 +430,12 @@ class File:
         table = next((d for t, d in msgs if t == MSG_SYMBOL_TABLE), None)
         if table is None:
             if any(t == MSG_LAYOUT for t, _ in msgs):
-                self._datasets[prefix.strip("/")] = self._dataset(msgs)
+                try:
+                    self._datasets[prefix.strip("/")] = self._dataset(msgs)
+                except Hdf5FormatError as e:  # e.g. a string / compound dataset next to the tomogram's own ones
+                    bad = DatasetInfo()
+                    bad.error = str(e)
+                    self._datasets[prefix.strip("/")] = bad
                 return
             if any(t in (0x02, 0x06) for t, _ in msgs):  # link info / link messages
                 raise Hdf5FormatError(f"group '{prefix or '/'}' is stored in the new link-message format (libver='latest' or "
@@ -553,6 +559,8 @@ class File:
 
     def read(self, key: str, threads: int = 8) -> np.ndarray:
         d = self.info(key)
+        if d.error:
+            raise Hdf5FormatError(f"{key}: {d.error}")
         count = int(np.prod(d.shape, dtype=np.int64)) if d.shape else 1
         native = d.dtype.newbyteorder("=") if d.dtype.byteorder == ">" else d.dtype
         if d.layout == "compact":

@@ -296,3 +296,22 @@ def test_filter_pipeline_is_undone_in_reverse_order():
     assert h5c.undo_filters(shuffled + b"\x00" * 4, filters, 0b010, 4) == raw.tobytes()
     with pytest.raises(h5c.Hdf5FormatError, match="filter 32015"):
         h5c.undo_filters(stored, [(32015, (3,))], 0, 4)
+
+
+def test_an_unreadable_dataset_does_not_hide_the_others(tmp_path):
+    """A dataset of a type outside the subset (here: the datatype class byte patched to 'string') is listed, refuses to
+    be read with the reason, and leaves the tomogram's own datasets readable."""
+    path = tmp_path / "s.hdf"
+    data = np.arange(24, dtype=np.uint8).reshape(2, 3, 4)
+    h5c.write_file(path, {"data": data, "note": np.zeros(5, np.int16)})
+    raw = bytearray(path.read_bytes())
+    i16 = struct.pack("<BBBBI", 0x10, 0x08, 0, 0, 2)  # the int16 datatype message body as the writer emits it
+    at = raw.index(i16)
+    raw[at] = 0x13  # class 3 = string
+    path.write_bytes(bytes(raw))
+    with h5c.File(path) as fh:
+        assert sorted(fh.keys()) == ["data", "note"] and "class 3" in fh.info("note").error
+        assert np.array_equal(fh.read("data"), data)
+        with pytest.raises(h5c.Hdf5FormatError, match="note"):
+            fh.read("note")
+    assert np.array_equal(hdf.read_tomogram(path, keys=["data"])["data"], data)
