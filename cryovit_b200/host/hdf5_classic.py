@@ -613,6 +613,9 @@ if __name__ == "__main__":  # python -m cryovit_b200.host.hdf5_classic FILE...: 
             print(f"{arg}: superblock at {fh_.base}, end of file address {fh_.eof}")
             for key_ in fh_.keys():
                 d_ = fh_.info(key_)
+                if d_.error:
+                    print(f"  /{key_}  (not readable here: {d_.error})")
+                    continue
                 how = d_.layout + (f" {d_.chunks}" if d_.chunks else "") + ("".join(
                     f" + {'deflate' if f == FILTER_DEFLATE else 'shuffle' if f == FILTER_SHUFFLE else f'filter {f}'}{list(v)}"
                     for f, v in d_.filters))
