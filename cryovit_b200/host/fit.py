@@ -58,7 +58,7 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
     if hasattr(dataset, "_crop_slices") and hasattr(dataset, "_load_tomogram"):
         budget = _cache_budget_bytes(cache_gb)
         if budget > 0:
-            cache = ResidentTomoCache(dataset, torch.device("cuda", torch.cuda.current_device()), budget)
+            cache = ResidentTomoCache(dataset, trainer.device, budget)  # where the trainer lives
     # the helper thread does host work only (file read, crop draw): the trainer captures CUDA graphs on this thread, and a
     # CUDA call from another thread during a capture is an error. ONE helper thread: the crop draws stay in order.
     fetch = (lambda i: cache.prepare(int(i))) if cache is not None else (lambda i: dataset[int(i)])
@@ -79,12 +79,13 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
         for k in range(len(mine)):
             item = cache.finish(nxt.result()) if cache is not None else nxt.result()
             nxt = pool.submit(fetch, mine[k + 1]) if k + 1 < len(mine) else None
-            loss = trainer.train_step(item.data.cuda(non_blocking=True), item.label.cuda(non_blocking=True))
+            loss = trainer.train_step(item.data.to(trainer.device, non_blocking=True), item.label.to(trainer.device, non_blocking=True))
             step += 1
             if step % log_every == 0 or len(losses) == 0:
                 losses.append(float(loss))
         if rank == 0 or epoch_seconds is not None:
-            torch.cuda.synchronize()
+            if torch.device(trainer.device).type == "cuda":
+                torch.cuda.synchronize()
             if epoch_seconds is not None:
                 epoch_seconds.append(time.perf_counter() - t_epoch)
         if rank == 0:

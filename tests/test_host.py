@@ -418,3 +418,61 @@ def test_resident_cache_gives_the_same_items_as_the_dataset(tmp_path):
             assert b.data.is_contiguous() and b.label.is_contiguous()
         assert len(cache._items) == kept
         assert cache.file_reads == (3 if kept == 3 else 1 + sum(1 for i in order if i != 0))
+
+
+def test_fit_loop_schedule_cache_and_prefetch_with_a_stub_trainer(tmp_path, monkeypatch):
+    """host/fit.py without a GPU: the trainer is a stub that records what it is given. The loop must (a) walk a fresh
+    permutation of the dataset per epoch, (b) hand the trainer exactly the crops the plain ``dataset[i]`` loop draws under
+    the same seed, with or without the resident cache, (c) read every tomogram file once when the cache holds the set
+    and once per use when it is off, (d) average the weights of the epoch starts from ``swa_epoch_start`` on."""
+    from cryovit.datasets import TomoDataset
+    from cryovit_b200.host import fit, hdf
+
+    rng = np.random.default_rng(1)
+    recs = []
+    for i in range(3):
+        feats = rng.standard_normal((4, 3 + i, 33, 35)).astype(np.float16)
+        lab = rng.integers(-1, 2, (3 + i, 16 * 33, 16 * 35)).astype(np.int8)
+        hdf.write_tomogram(tmp_path / "S" / f"t{i}.hdf", {"labels/mito": lab, "dino_features": feats})
+        recs.append({"sample": "S", "tomo_name": f"t{i}.hdf"})
+
+    class StubTrainer:
+        device = torch.device("cpu")
+        seen: list = []
+
+        def __init__(self, in_channels, lr, weight_decay, state_dict, seed):
+            self.flat_p = torch.zeros(2)
+            type(self).seen = []
+
+        def train_step(self, features, labels):
+            assert features.shape[-2:] == (32, 32) and labels.shape[-2:] == (512, 512) and features.is_contiguous()
+            type(self).seen.append((features.clone(), labels.clone()))
+            self.flat_p += 1.0  # "weights" = number of steps taken
+            return torch.tensor(0.5)
+
+        def state_dict(self):
+            return {"w": self.flat_p.clone()}
+
+    monkeypatch.setattr(fit, "CryoVITHeadTrainerB200", StubTrainer)
+    reads = []
+    real = hdf.read_tomogram
+    monkeypatch.setattr(hdf, "read_tomogram", lambda path, keys=None: (reads.append(Path(path).name), real(path, keys))[1])
+    epochs = 4
+    ds = TomoDataset(recs, "dino_features", "mito", "split_id", tmp_path, train=True)
+    # what the plain loop would feed: same order generator, same global crop generator
+    np.random.seed(42)
+    order_rng, want = np.random.default_rng(42), []
+    for _ in range(epochs):
+        for i in order_rng.permutation(3):
+            it = ds[int(i)]
+            want.append((it.data, it.label))
+    for cache_gb, n_reads in ((1.0, 3), (0.0, 3 * epochs)):
+        reads.clear()
+        secs: list = []
+        sd = fit.fit_head(ds, in_channels=4, max_epochs=epochs, swa_epoch_start=2, seed=42, cache_gb=cache_gb, epoch_seconds=secs)
+        got = StubTrainer.seen
+        assert len(got) == len(want) == 3 * epochs and len(secs) == epochs
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, want))
+        assert len(reads) == n_reads and (cache_gb == 0.0 or sorted(reads) == ["t0.hdf", "t1.hdf", "t2.hdf"])
+        # SWA: mean of the weights at the starts of epochs 2 and 3 = (6 + 9) / 2 steps
+        assert torch.allclose(sd["w"], torch.full((2,), 7.5))
