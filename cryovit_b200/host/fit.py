@@ -63,35 +63,38 @@ def fit_head(dataset: TomoDataset, in_channels: int = 1536, max_epochs: int = 50
     # CUDA call from another thread during a capture is an error. ONE helper thread: the crop draws stay in order.
     fetch = (lambda i: cache.prepare(int(i))) if cache is not None else (lambda i: dataset[int(i)])
     pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cryovit-fit-fetch")
-    for epoch in range(max_epochs):
-        # Lightning's StochasticWeightAveraging.on_train_epoch_START: epochs swa_start .. max_epochs - 1 each add the
-        # weights they START from to the running mean (so the last epoch's own updates are not in it), and the mean
-        # replaces the weights when training ends.
-        if swa_epoch_start is not None and epoch >= swa_epoch_start:
-            swa_n += 1
-            swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
-        t_epoch = time.perf_counter()
-        order = order_rng.permutation(len(dataset))
-        usable = len(order) // world * world  # every rank takes the same number of steps (the all-reduce is collective)
-        losses = []
-        mine = [int(i) for i in order[:usable][rank::world]]
-        nxt = pool.submit(fetch, mine[0]) if mine else None
-        for k in range(len(mine)):
-            item = cache.finish(nxt.result()) if cache is not None else nxt.result()
-            nxt = pool.submit(fetch, mine[k + 1]) if k + 1 < len(mine) else None
-            loss = trainer.train_step(item.data.to(trainer.device, non_blocking=True), item.label.to(trainer.device, non_blocking=True))
-            step += 1
-            if step % log_every == 0 or len(losses) == 0:
-                losses.append(float(loss))
-        if rank == 0 or epoch_seconds is not None:
-            if torch.device(trainer.device).type == "cuda":
-                torch.cuda.synchronize()
-            if epoch_seconds is not None:
-                epoch_seconds.append(time.perf_counter() - t_epoch)
-        if rank == 0:
-            logging.info("epoch %d: %d steps/rank, DiceLoss %.4f, %.2f s", epoch, usable // world,
-                         float(np.mean(losses)) if losses else float("nan"), time.perf_counter() - t_epoch)
-    pool.shutdown(wait=True)
+    try:
+        for epoch in range(max_epochs):
+            # Lightning's StochasticWeightAveraging.on_train_epoch_START: epochs swa_start .. max_epochs - 1 each add the
+            # weights they START from to the running mean (so the last epoch's own updates are not in it), and the mean
+            # replaces the weights when training ends.
+            if swa_epoch_start is not None and epoch >= swa_epoch_start:
+                swa_n += 1
+                swa_avg = trainer.flat_p.clone() if swa_avg is None else swa_avg + (trainer.flat_p - swa_avg) / swa_n
+            t_epoch = time.perf_counter()
+            order = order_rng.permutation(len(dataset))
+            usable = len(order) // world * world  # every rank takes the same number of steps (the all-reduce is collective)
+            losses = []
+            mine = [int(i) for i in order[:usable][rank::world]]
+            nxt = pool.submit(fetch, mine[0]) if mine else None
+            for k in range(len(mine)):
+                item = cache.finish(nxt.result()) if cache is not None else nxt.result()
+                nxt = pool.submit(fetch, mine[k + 1]) if k + 1 < len(mine) else None
+                dev = trainer.device
+                loss = trainer.train_step(item.data.to(dev, non_blocking=True), item.label.to(dev, non_blocking=True))
+                step += 1
+                if step % log_every == 0 or len(losses) == 0:
+                    losses.append(float(loss))
+            if rank == 0 or epoch_seconds is not None:
+                if torch.device(trainer.device).type == "cuda":
+                    torch.cuda.synchronize()
+                if epoch_seconds is not None:
+                    epoch_seconds.append(time.perf_counter() - t_epoch)
+            if rank == 0:
+                logging.info("epoch %d: %d steps/rank, DiceLoss %.4f, %.2f s", epoch, usable // world,
+                             float(np.mean(losses)) if losses else float("nan"), time.perf_counter() - t_epoch)
+    finally:
+        pool.shutdown(wait=True)
     if cache is not None and rank == 0:
         logging.info("resident training set: %d tomograms, %.2f GB in HBM, %d file reads for %d steps", len(cache._items),
                      cache.used / 1e9, cache.file_reads, step)
